@@ -1,0 +1,19 @@
+"""istvt_b200 — B200-native (sm_100a) implementation of the ISTVT forward hot path.
+
+The directory name (`2023-tifs-istvt_b200`) is not a Python identifier; import it with
+
+    import importlib
+    istvt = importlib.import_module("2023-tifs-istvt_b200")
+
+or put this directory itself on `sys.path` to shadow the reference's `network` package
+(`from network.models import model_selection` then resolves to the B200 implementation).
+"""
+from . import _lib, ops  # noqa: F401
+from .engine import ISTVTEngine, entry_flow_features  # noqa: F401
+from .network.models import TransferModel, model_selection  # noqa: F401
+from .network.vivit.vivit import DSTTr, STTransformer, XceptionVidTr  # noqa: F401
+
+ISTVT = XceptionVidTr
+
+__all__ = ["ISTVT", "XceptionVidTr", "DSTTr", "STTransformer", "TransferModel", "model_selection", "ISTVTEngine",
+           "entry_flow_features", "ops"]

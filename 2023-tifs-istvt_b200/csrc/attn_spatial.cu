@@ -1,0 +1,354 @@
+// Spatial self-attention over the tokens of one frame (network/vivit/module.py:84-91).
+//
+// bf16 path (tcgen05): one CTA = one (frame bf, head h, 128-query tile).  Q, K, V tiles are fetched by
+// TMA straight out of the packed projection output [rows, 3*heads*64] through a 3-D tensor map
+// (col, token-in-frame, frame), so rows past the frame's last token are zero-filled instead of
+// leaking the next frame — no permute copies (the reference makes 3 in, 1 out).
+//   S[128 x 384] = Q Kᵀ          tcgen05.mma, both operands K-major SW128, accumulator in TMEM (384 cols)
+//   P = exp2(S*c - max*c)        8 softmax warps, 2 threads per row (192 columns each), whole key
+//                                range resident in TMEM so no online rescaling is needed
+//   O[128 x 64] = P V            P staged in smem (bf16, K-major SW128), V is the MN-major B operand
+//   out = O / rowsum             TMEM -> registers -> global (128 B per row)
+// fp32 path: SIMT validation kernel (online softmax, K/V in smem).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "simt_util.cuh"
+
+namespace istvt {
+
+constexpr int SA_DH = 64;
+constexpr int SA_BM = 128;        // queries per CTA
+constexpr int SA_KMAX = 384;      // keys held in TMEM / smem
+constexpr int SA_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: softmax + epilogue
+constexpr int SA_Q_BYTES = SA_BM * SA_DH * 2;        // 16 KB
+constexpr int SA_KV_BYTES = SA_KMAX * SA_DH * 2;     // 48 KB
+constexpr int SA_P_BYTES = SA_BM * SA_KMAX * 2;      // 96 KB
+constexpr int SA_SMEM = SA_Q_BYTES + 2 * SA_KV_BYTES + SA_P_BYTES + 1024 + 2048;
+constexpr int SA_TMEM_COLS = 512;                     // S: 384, O: 64 (at column 384)
+
+__global__ void __launch_bounds__(SA_THREADS, 1)
+attn_spatial_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
+                            float* __restrict__ probs, int tokens, int heads, float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_q = smem;
+    uint8_t* s_k = s_q + SA_Q_BYTES;
+    uint8_t* s_v = s_k + SA_KV_BYTES;
+    uint8_t* s_p = s_v + SA_KV_BYTES;
+    uint8_t* s_misc = s_p + SA_P_BYTES;
+    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(s_misc);
+    uint64_t* bar_v = bar_qk + 1;
+    uint64_t* bar_s = bar_qk + 2;
+    uint64_t* bar_p = bar_qk + 3;
+    uint64_t* bar_o = bar_qk + 4;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_qk + 5);
+    float* s_red = reinterpret_cast<float*>(s_misc + 64);  // [2][128] partial max, then partial sums
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int q_tiles = (tokens + SA_BM - 1) / SA_BM;
+    const int qt = blockIdx.x % q_tiles;
+    const int h = (blockIdx.x / q_tiles) % heads;
+    const int bf = blockIdx.x / (q_tiles * heads);
+    const int inner = heads * SA_DH;
+    const int k_chunks = (tokens + 127) / 128;        // 128-key TMA boxes / MMA N-chunks
+    const int keys_pad = k_chunks * 128;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_qkv);
+    if (warp == 1 && lane == 0) {
+        mbar_init(bar_qk, 1);
+        mbar_init(bar_v, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_p, 8);   // one arrive per softmax warp
+        mbar_init(bar_o, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_holder, SA_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tmem_s = tmem_base;
+    const uint32_t tmem_o = tmem_base + SA_KMAX;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_qk, SA_Q_BYTES + k_chunks * 128 * SA_DH * 2);
+            tma_load_3d(s_q, &tm_qkv, bar_qk, h * SA_DH, qt * SA_BM, bf);
+            for (int c = 0; c < k_chunks; ++c)
+                tma_load_3d(s_k + c * 128 * SA_DH * 2, &tm_qkv, bar_qk, inner + h * SA_DH, c * 128, bf);
+            mbar_arrive_expect_tx(bar_v, k_chunks * 128 * SA_DH * 2);
+            for (int c = 0; c < k_chunks; ++c)
+                tma_load_3d(s_v + c * 128 * SA_DH * 2, &tm_qkv, bar_v, 2 * inner + h * SA_DH, c * 128, bf);
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---- S = Q K^T ----
+        mbar_wait(bar_qk, 0);
+        tc_fence_after();
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(SA_BM, 128, 0, 0);
+            const uint32_t q_addr = smem_u32(s_q);
+            const uint32_t k_addr = smem_u32(s_k);
+            for (int c = 0; c < k_chunks; ++c) {
+#pragma unroll
+                for (int k = 0; k < SA_DH / 16; ++k) {
+                    const uint64_t a_desc = make_smem_desc(q_addr + k * 32, 0, 1024, SWZ_128B);
+                    const uint64_t b_desc = make_smem_desc(k_addr + c * 128 * 128 + k * 32, 0, 1024, SWZ_128B);
+                    umma_f16_ss(tmem_s + c * 128, a_desc, b_desc, idesc, k != 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(bar_s);
+        }
+        __syncwarp();
+        // ---- O = P V ----
+        mbar_wait(bar_v, 0);
+        mbar_wait(bar_p, 0);
+        tc_fence_after();
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(SA_BM, SA_DH, 0, 1);  // B (= V) is MN-major
+            const uint32_t p_addr = smem_u32(s_p);
+            const uint32_t v_addr = smem_u32(s_v);
+            const int ksteps = (tokens + 15) / 16;
+            for (int k = 0; k < ksteps; ++k) {
+                const uint64_t a_desc =
+                    make_smem_desc(p_addr + (k >> 2) * (SA_BM * 128) + (k & 3) * 32, 0, 1024, SWZ_128B);
+                const uint64_t b_desc = make_smem_desc(v_addr + k * 16 * 128, 64 * 128, 1024, SWZ_128B);
+                umma_f16_ss(tmem_o, a_desc, b_desc, idesc, k != 0 ? 1u : 0u);
+            }
+            umma_commit(bar_o);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ---- softmax + epilogue: thread -> (row, column half) ----
+        const int quad = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int row = quad * 32 + lane;               // row inside the q tile == TMEM lane
+        const int q_idx = qt * SA_BM + row;             // token index of this query
+        const int cols_half = keys_pad / 2;             // 192 (or 128 / 64 for short frames)
+        const int col_lo = half * cols_half;
+        const uint32_t t_row = tmem_s + (static_cast<uint32_t>(quad * 32) << 16);
+
+        mbar_wait(bar_s, 0);
+        tc_fence_after();
+
+        // pass 1: row max over valid keys
+        float mx = -INFINITY;
+        for (int c0 = col_lo; c0 < col_lo + cols_half; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+        s_red[half * 128 + row] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(s_red[row], s_red[128 + row]);
+        const float mxs = mx * scale_log2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read the maxima; s_red reused for sums
+
+        // pass 2: p = exp2(s*c - max*c), bf16 P -> smem (K-major SW128 atoms of 64 keys), row sums
+        float sum = 0.0f;
+        for (int c0 = col_lo; c0 < col_lo + cols_half; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + c0, r);
+            tmem_ld_wait();
+            float pv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float e = exp2f(fmaf(__uint_as_float(r[j]), scale_log2, -mxs));
+                pv[j] = (c0 + j < tokens) ? e : 0.0f;
+            }
+            // The PV MMA consumes bf16 P; accumulate the denominator from the same rounded values so
+            // that the normalised rows sum to one in the precision actually used.
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                pk[j] = pack_bf16x2(pv[2 * j], pv[2 * j + 1]);
+                const float2 f = unpack_bf16x2(pk[j]);
+                sum += f.x + f.y;
+            }
+            const int atom = c0 >> 6;                   // 64-key atom
+            const int chunk0 = (c0 & 63) >> 3;          // first 16-byte chunk inside the 128-byte row
+            uint8_t* prow = s_p + atom * (SA_BM * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int chunk = (chunk0 + g) ^ (row & 7);
+                *reinterpret_cast<uint4*>(prow + chunk * 16) =
+                    make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            }
+        }
+        fence_proxy_async_smem();  // st.shared P -> visible to the tensor core (async proxy)
+        s_red[half * 128 + row] = sum;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float inv = 1.0f / (s_red[row] + s_red[128 + row]);
+
+        if (probs != nullptr) {  // warp-uniform
+            // optional attention-map output: probs[bf, h, q, key], fp32, normalised.  The TMEM loads are
+            // warp-collective, so rows past the frame end take part in them and only skip the stores.
+            const bool row_ok = q_idx < tokens;
+            float* pr = probs + ((static_cast<int64_t>(bf) * heads + h) * tokens + (row_ok ? q_idx : 0)) * tokens;
+            for (int c0 = col_lo; c0 < col_lo + cols_half; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_row + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (row_ok && c0 + j < tokens)
+                        pr[c0 + j] = exp2f(fmaf(__uint_as_float(r[j]), scale_log2, -mxs)) * inv;
+            }
+        }
+
+        // epilogue: this thread normalises 32 of the 64 output columns of its row
+        mbar_wait(bar_o, 0);
+        tc_fence_after();
+        {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_o + (static_cast<uint32_t>(quad * 32) << 16) + half * 32, r);
+            tmem_ld_wait();
+            if (q_idx < tokens) {
+                __nv_bfloat16* op = out + (static_cast<int64_t>(bf) * tokens + q_idx) * inner + h * SA_DH + half * 32;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
+                    o.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
+                    o.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
+                    o.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
+                    *reinterpret_cast<uint4*>(op + 8 * g) = o;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, SA_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 validation kernel: one CTA per (frame, head); K and V in shared memory, one query per thread.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attn_spatial_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ probs,
+                        int tokens, int heads, float scale) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float* sk = reinterpret_cast<float*>(smem_raw);  // [tokens][64]
+    float* sv = sk + static_cast<size_t>(tokens) * SA_DH;
+    const int h = blockIdx.x % heads;
+    const int bf = blockIdx.x / heads;
+    const int inner = heads * SA_DH;
+    const int64_t row0 = static_cast<int64_t>(bf) * tokens;
+    for (int c = threadIdx.x; c < tokens * (SA_DH / 4); c += blockDim.x) {
+        const int j = c / (SA_DH / 4);
+        const int d = (c - j * (SA_DH / 4)) * 4;
+        const float* base = qkv + (row0 + j) * (3 * inner) + h * SA_DH + d;
+        *reinterpret_cast<float4*>(sk + j * SA_DH + d) = *reinterpret_cast<const float4*>(base + inner);
+        *reinterpret_cast<float4*>(sv + j * SA_DH + d) = *reinterpret_cast<const float4*>(base + 2 * inner);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < tokens; i += blockDim.x) {
+        float q[SA_DH], o[SA_DH];
+        const float* qp = qkv + (row0 + i) * (3 * inner) + h * SA_DH;
+#pragma unroll
+        for (int d = 0; d < SA_DH; d += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(qp + d);
+            q[d] = t.x * scale; q[d + 1] = t.y * scale; q[d + 2] = t.z * scale; q[d + 3] = t.w * scale;
+        }
+#pragma unroll
+        for (int d = 0; d < SA_DH; ++d) o[d] = 0.0f;
+        float mx = -INFINITY, l = 0.0f;
+        for (int j = 0; j < tokens; ++j) {
+            float s = 0.0f;
+#pragma unroll
+            for (int d = 0; d < SA_DH; d += 4) {
+                const float4 kk = *reinterpret_cast<const float4*>(sk + j * SA_DH + d);
+                s = fmaf(q[d], kk.x, s); s = fmaf(q[d + 1], kk.y, s);
+                s = fmaf(q[d + 2], kk.z, s); s = fmaf(q[d + 3], kk.w, s);
+            }
+            const float mnew = fmaxf(mx, s);
+            const float corr = expf(mx - mnew);
+            const float pj = expf(s - mnew);
+            l = l * corr + pj;
+#pragma unroll
+            for (int d = 0; d < SA_DH; d += 4) {
+                const float4 vv = *reinterpret_cast<const float4*>(sv + j * SA_DH + d);
+                o[d] = fmaf(o[d], corr, pj * vv.x); o[d + 1] = fmaf(o[d + 1], corr, pj * vv.y);
+                o[d + 2] = fmaf(o[d + 2], corr, pj * vv.z); o[d + 3] = fmaf(o[d + 3], corr, pj * vv.w);
+            }
+            mx = mnew;
+        }
+        const float inv = 1.0f / l;
+        float* op = out + (row0 + i) * inner + h * SA_DH;
+#pragma unroll
+        for (int d = 0; d < SA_DH; d += 4)
+            *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+        if (probs != nullptr) {
+            float* pr = probs + ((static_cast<int64_t>(bf) * heads + h) * tokens + i) * tokens;
+            for (int j = 0; j < tokens; ++j) {
+                float s = 0.0f;
+#pragma unroll
+                for (int d = 0; d < SA_DH; d += 4) {
+                    const float4 kk = *reinterpret_cast<const float4*>(sk + j * SA_DH + d);
+                    s = fmaf(q[d], kk.x, s); s = fmaf(q[d + 1], kk.y, s);
+                    s = fmaf(q[d + 2], kk.z, s); s = fmaf(q[d + 3], kk.w, s);
+                }
+                pr[j] = expf(s - mx) * inv;
+            }
+        }
+    }
+}
+
+}  // namespace istvt
+
+using namespace istvt;
+
+extern "C" int istvt_attn_spatial_fwd(const void* qkv, void* out, float* probs, int dtype, int batch_frames,
+                                      int tokens, int heads, float scale, istvt_stream_t stream) {
+    ISTVT_REQUIRE(qkv && out);
+    ISTVT_REQUIRE(batch_frames > 0 && tokens > 0 && heads > 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int inner = heads * SA_DH;
+    if (dtype == ISTVT_F32) {
+        const size_t smem = 2 * static_cast<size_t>(tokens) * SA_DH * sizeof(float);
+        ISTVT_REQUIRE(smem <= 220 * 1024);
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(smem)));
+        attn_spatial_f32_kernel<<<batch_frames * heads, 128, smem, st>>>(
+            static_cast<const float*>(qkv), static_cast<float*>(out), probs, tokens, heads, scale);
+        count_launch();
+        return launch_status();
+    }
+    ISTVT_REQUIRE(dtype == ISTVT_BF16);
+    ISTVT_REQUIRE(tokens <= SA_KMAX);
+    ISTVT_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    CUtensorMap tm;
+    {
+        const uint64_t dims[3] = {static_cast<uint64_t>(3 * inner), static_cast<uint64_t>(tokens),
+                                  static_cast<uint64_t>(batch_frames)};
+        const uint64_t strides[2] = {static_cast<uint64_t>(3 * inner) * 2,
+                                     static_cast<uint64_t>(tokens) * 3 * inner * 2};
+        const uint32_t box[3] = {SA_DH, 128, 1};
+        int rc = encode_tmap(&tm, qkv, ISTVT_BF16, 3, dims, strides, box, 3);
+        if (rc != ISTVT_OK) return rc;
+    }
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          SA_SMEM));
+    const int q_tiles = (tokens + SA_BM - 1) / SA_BM;
+    const float scale_log2 = scale * 1.4426950408889634f;
+    attn_spatial_tcgen05_kernel<<<batch_frames * heads * q_tiles, SA_THREADS, SA_SMEM, st>>>(
+        tm, static_cast<__nv_bfloat16*>(out), probs, tokens, heads, scale_log2);
+    count_launch();
+    return launch_status();
+}

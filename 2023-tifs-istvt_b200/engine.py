@@ -1,0 +1,289 @@
+"""Forward engine of the ISTVT hot path: weight packing + the kernel schedule.
+
+`ISTVTEngine.forward` is what `XceptionVidTr.forward` (reference: network/vivit/vivit.py:202-208) runs.
+It owns no arithmetic: every step below is one call into libistvt_b200.so (see include/istvt_b200.h).
+
+Data layout in HBM:
+  * feature maps NHWC, activation dtype = bf16 (fp32 in the validation mode);
+  * token / residual stream: fp32 [B, F=T+1, P=362, 728]; block-3's pool+add kernel writes straight into it,
+    so the reference's `b t c h w -> b t (h w) c` permute, both `cat`s and the `+= pos_embedding`
+    (vivit.py:133-142) cost no extra pass;
+  * projections are plain row-major [rows, N] and the attention kernels read q/k/v in place.
+
+BatchNorm (eval mode) is folded: scale into the bf16 weights, shift into the GEMM epilogue bias.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+PRECISIONS = {"bf16": torch.bfloat16, "fp32": torch.float32}
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing
+# ------------------------------------------------------------------------------------------------
+def _bn_fold(bn) -> Tuple[torch.Tensor, torch.Tensor]:
+    scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale, shift
+
+
+@dataclass
+class _SepPack:
+    dw: torch.Tensor      # fp32 [3, 3, C]
+    pw: torch.Tensor      # act dtype [Cout, Cin], BN scale folded
+    bias: torch.Tensor    # fp32 [Cout]
+
+
+@dataclass
+class _BlockPack:
+    skip_w: torch.Tensor
+    skip_b: torch.Tensor
+    seps: List[_SepPack]
+    start_with_relu: bool
+
+
+@dataclass
+class _LayerPack:
+    ln1: Tuple[torch.Tensor, torch.Tensor]
+    w_qk: torch.Tensor
+    w_v: torch.Tensor
+    w_to: torch.Tensor
+    b_to: torch.Tensor
+    ln2: Tuple[torch.Tensor, torch.Tensor]
+    w_qkv: torch.Tensor
+    w_so: torch.Tensor
+    b_so: torch.Tensor
+    ln3: Tuple[torch.Tensor, torch.Tensor]
+    w_1: torch.Tensor
+    b_1: torch.Tensor
+    w_2: torch.Tensor
+    b_2: torch.Tensor
+
+
+@dataclass
+class _EntryPack:
+    stem_w: torch.Tensor
+    stem_b: torch.Tensor
+    conv2_w: torch.Tensor
+    conv2_b: torch.Tensor
+    blocks: List[_BlockPack]
+
+
+@dataclass
+class _Pack:
+    entry: _EntryPack
+    pos_emb: torch.Tensor
+    space_token: torch.Tensor
+    temporal_token: torch.Tensor
+    layers: List[_LayerPack]
+    norm: Tuple[torch.Tensor, torch.Tensor]
+    head_ln: Tuple[torch.Tensor, torch.Tensor]
+    head_w: torch.Tensor
+    head_b: torch.Tensor
+    fingerprint: tuple = field(default_factory=tuple)
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+def _pack_block(block, dt: torch.dtype) -> _BlockPack:
+    sc, sh = _bn_fold(block.skipbn)
+    skip_w = (block.skip.weight.detach().float().flatten(1) * sc[:, None]).to(dt).contiguous()
+    seps = []
+    mods = list(block.rep)
+    for i, m in enumerate(mods):
+        if hasattr(m, "pointwise"):
+            bn = mods[i + 1]
+            s, b = _bn_fold(bn)
+            dw = m.conv1.weight.detach().float()[:, 0].permute(1, 2, 0).contiguous()      # [C,1,3,3] -> [3,3,C]
+            pw = (m.pointwise.weight.detach().float().flatten(1) * s[:, None]).to(dt).contiguous()
+            seps.append(_SepPack(dw=dw, pw=pw, bias=b.contiguous()))
+    return _BlockPack(skip_w=skip_w, skip_b=sh.contiguous(), seps=seps, start_with_relu=block.start_with_relu)
+
+
+def pack_entry(xcep, dt: torch.dtype) -> _EntryPack:
+    """xcep: the `Xception` parameter tree (network/xception.py)."""
+    s1, b1 = _bn_fold(xcep.bn1)
+    stem_w = (xcep.conv1.weight.detach().float() * s1[:, None, None, None]).contiguous()   # fp32 [32,3,3,3]
+    s2, b2 = _bn_fold(xcep.bn2)
+    conv2_w = (xcep.conv2.weight.detach().float() * s2[:, None, None, None]).permute(0, 2, 3, 1).to(dt).contiguous()
+    blocks = [_pack_block(b, dt) for b in (xcep.block1, xcep.block2, xcep.block3)]
+    return _EntryPack(stem_w=stem_w, stem_b=b1.contiguous(), conv2_w=conv2_w, conv2_b=b2.contiguous(), blocks=blocks)
+
+
+def _on_path_tensors(model) -> List[torch.Tensor]:
+    x = model.xcep.model
+    mods = [x.conv1, x.bn1, x.conv2, x.bn2, x.block1, x.block2, x.block3, model.vit]
+    out: List[torch.Tensor] = []
+    for m in mods:
+        out += list(m.parameters()) + list(m.buffers())
+    return out
+
+
+def _fingerprint(model) -> tuple:
+    return tuple((t.data_ptr(), t._version) for t in _on_path_tensors(model))
+
+
+def pack_model(model, dt: torch.dtype) -> _Pack:
+    vit = model.vit
+    ln = lambda m: (_f32(m.weight), _f32(m.bias))
+    wt = lambda m: m.weight.detach().to(dt).contiguous()
+    layers = []
+    for attn_t, attn_s, ff in vit.transformer.layers:
+        layers.append(_LayerPack(
+            ln1=ln(attn_t.norm), w_qk=wt(attn_t.fn.to_qk), w_v=wt(attn_t.fn.to_v),
+            w_to=wt(attn_t.fn.to_out[0]), b_to=_f32(attn_t.fn.to_out[0].bias),
+            ln2=ln(attn_s.norm), w_qkv=wt(attn_s.fn.to_qkv),
+            w_so=wt(attn_s.fn.to_out[0]), b_so=_f32(attn_s.fn.to_out[0].bias),
+            ln3=ln(ff.norm), w_1=wt(ff.fn.net[0]), b_1=_f32(ff.fn.net[0].bias),
+            w_2=wt(ff.fn.net[3]), b_2=_f32(ff.fn.net[3].bias)))
+    return _Pack(
+        entry=pack_entry(model.xcep.model, dt),
+        pos_emb=_f32(vit.pos_embedding[0]), space_token=_f32(vit.space_token.reshape(-1)),
+        temporal_token=_f32(vit.temporal_token.reshape(-1)),
+        layers=layers, norm=ln(vit.transformer.norm), head_ln=ln(vit.mlp_head[0]),
+        head_w=_f32(vit.mlp_head[1].weight.reshape(-1)), head_b=_f32(vit.mlp_head[1].bias),
+        fingerprint=_fingerprint(model))
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel schedule
+# ------------------------------------------------------------------------------------------------
+def _run_block(bp: _BlockPack, x: torch.Tensor, taps: Optional[dict], name: str):
+    """Xception Block (reference xception.py:91-101): returns (body [n,h,w,C] before the pool, skip)."""
+    n, h, w, _ = x.shape
+    skip_in = ops.subsample2(x)                                        # gather of the stride-2 1x1 (:57, :94)
+    skip = ops.gemm(skip_in, bp.skip_w, bias=bp.skip_b)                # skip conv + skipbn (:94-96)
+    y = x
+    for i, sp in enumerate(bp.seps):
+        relu_in = bp.start_with_relu and i == 0                        # leading ReLU reads the block input (:82-85)
+        d = ops.dwconv3x3(y, sp.dw, relu_in=relu_in)                   # depthwise (:47)
+        last = i == len(bp.seps) - 1
+        # pointwise + BN (+ the ReLU that precedes the next separable conv) (:48, :69-75)
+        y = ops.gemm(d, sp.pw, bias=sp.bias, act=ops.ACT_NONE if last else ops.ACT_RELU)
+        y = y.view(n, h, w, -1)
+    return y, skip.view(n, skip_in.shape[1], skip_in.shape[2], -1)
+
+
+def run_entry_flow(ep: _EntryPack, frames: torch.Tensor, dt: torch.dtype, taps: Optional[dict] = None):
+    """frames: fp32 NCHW [n, 3, H, W] -> (block-3 body [n, 37, 37, 728], block-3 skip [n, 19, 19, 728])."""
+    a = ops.conv_stem(frames, ep.stem_w, ep.stem_b, dt)                                # conv1+bn1+relu
+    a = ops.conv3x3(a, ep.conv2_w, ep.conv2_b, act=ops.ACT_RELU)                       # conv2+bn2+relu
+    if taps is not None:
+        taps["stem"] = a
+    for bi, bp in enumerate(ep.blocks[:2]):
+        body, skip = _run_block(bp, a, taps, f"block{bi + 1}")
+        a = ops.pool_add(body, skip)                                                    # maxpool + residual
+        if taps is not None:
+            taps[f"block{bi + 1}"] = a
+    return _run_block(ep.blocks[2], a, taps, "block3")
+
+
+def entry_flow_features(xcep, x: torch.Tensor, precision: str = "fp32") -> torch.Tensor:
+    """`Xception.low_level_features` in the reference's NCHW fp32 layout (parity / debugging entry)."""
+    if xcep.training:
+        raise NotImplementedError("istvt_b200: BatchNorm batch-statistics (training-mode) forward is not built yet")
+    dt = PRECISIONS[precision]
+    ep = pack_entry(xcep, dt)
+    body, skip = run_entry_flow(ep, x.contiguous().float(), dt)
+    y = ops.pool_add(body, skip)
+    return y.float().permute(0, 3, 1, 2)
+
+
+class ISTVTEngine:
+    def __init__(self, model):
+        self._packs: Dict[Tuple[str, str], _Pack] = {}
+
+    def _pack(self, model, dev: torch.device, precision: str) -> _Pack:
+        key = (str(dev), precision)
+        pack = self._packs.get(key)
+        fp = _fingerprint(model)
+        if pack is None or pack.fingerprint != fp:
+            pack = pack_model(model, PRECISIONS[precision])
+            self._packs[key] = pack
+        return pack
+
+    @torch.no_grad()
+    def forward(self, model, x: torch.Tensor, precision: str = "bf16", return_attention: bool = False,
+                taps: Optional[dict] = None):
+        vit = model.vit
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        if not isinstance(x, torch.Tensor) or x.dim() != 5 or x.shape[2] != 3:
+            raise ValueError("ISTVT expects a clip tensor [B, T, 3, H, W]")
+        if not x.is_cuda:
+            raise ValueError("ISTVT (istvt_b200) runs on CUDA tensors only: there is no CPU fallback by design")
+        b, t, _, hh, ww = x.shape
+        if t != vit.num_frames:
+            raise ValueError(f"clip has {t} frames but the model was built with num_frames={vit.num_frames}")
+        if model.training:
+            raise NotImplementedError(
+                "istvt_b200: training-mode forward (BatchNorm batch statistics + backward) is not built yet; "
+                "call model.eval()")
+        side = vit.image_size
+        feat = lambda s: (((((s - 3) // 2 + 1) - 2) - 1) // 2 + 1)      # stem: 3x3 s2, 3x3 s1; then three s2 stages
+        fh, fw = feat(hh), feat(ww)
+        for _ in range(2):
+            fh, fw = (fh - 1) // 2 + 1, (fw - 1) // 2 + 1
+        if (fh, fw) != (side, side):
+            raise ValueError(f"input {hh}x{ww} reduces to {fh}x{fw} feature maps, the model needs {side}x{side}")
+
+        dt = PRECISIONS[precision]
+        dev = x.device
+        pk = self._pack(model, dev, precision)
+        heads, dim = vit.heads, vit.dim
+        p_tok = vit.num_patches + 1
+        f_tok = t + 1
+        scale = 64 ** -0.5
+
+        frames = x.reshape(b * t, 3, hh, ww)
+        if frames.dtype != torch.float32 or not frames.is_contiguous():
+            frames = frames.float().contiguous()
+
+        # ---- Xception entry flow; block 3's pool+add lands in the token buffer ----
+        body, skip = run_entry_flow(pk.entry, frames, dt, taps)
+        tokens = torch.empty(b, f_tok, p_tok, dim, dtype=torch.float32, device=dev)
+        ops.pool_add_tokens(body, skip, pk.pos_emb, tokens, b, t)
+        ops.token_fill(tokens, pk.space_token, pk.temporal_token, pk.pos_emb)
+        del body, skip
+        if taps is not None:
+            taps["tokens"] = tokens.clone()
+
+        attn: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        rows = b * f_tok * p_tok
+        xn = torch.empty(b, f_tok, p_tok, dim, dtype=dt, device=dev)
+        diff = torch.empty_like(xn)
+        for li, lp in enumerate(pk.layers):
+            # temporal self-subtract attention (module.py:190-208), no residual of its own (vivit.py:99)
+            ops.layernorm_diff(tokens, lp.ln1[0], lp.ln1[1], dt, out=(xn, diff))
+            qk = ops.gemm(diff.view(rows, dim), lp.w_qk)
+            v = ops.gemm(xn.view(rows, dim), lp.w_v)
+            at, p_t = ops.attn_temporal(qk, v, b, f_tok, p_tok, heads, scale, want_probs=return_attention)
+            y1 = ops.gemm(at, lp.w_to, bias=lp.b_to, out_dtype=dt)
+            # spatial attention (module.py:81-93) + the residual spanning both attentions (vivit.py:99)
+            yn = ops.layernorm(y1, lp.ln2[0], lp.ln2[1], dt, out=xn.view(rows, dim))
+            qkv = ops.gemm(yn, lp.w_qkv)
+            as_, p_s = ops.attn_spatial(qkv, b * f_tok, p_tok, heads, scale, want_probs=return_attention)
+            tok2d = tokens.view(rows, dim)
+            ops.gemm(as_, lp.w_so, bias=lp.b_so, residual=tok2d, out=tok2d)
+            # MLP (module.py:33-34) + residual (vivit.py:100)
+            zn = ops.layernorm(tok2d, lp.ln3[0], lp.ln3[1], dt, out=xn.view(rows, dim))
+            hid = ops.gemm(zn, lp.w_1, bias=lp.b_1, act=ops.ACT_GELU, out_dtype=dt)
+            ops.gemm(hid, lp.w_2, bias=lp.b_2, residual=tok2d, out=tok2d)
+            if return_attention:
+                attn.append((p_t, p_s.view(b, f_tok, heads, p_tok, p_tok)))
+            if taps is not None:
+                taps[f"layer{li}"] = tokens.clone()
+            del qk, v, at, y1, qkv, as_, hid
+
+        logits = ops.head(tokens, pk.norm[0], pk.norm[1], pk.head_ln[0], pk.head_ln[1], pk.head_w, pk.head_b)
+        if return_attention:
+            return logits, attn
+        return logits

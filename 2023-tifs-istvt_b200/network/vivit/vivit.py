@@ -1,0 +1,85 @@
+"""ISTVT model = Xception entry flow + decomposed spatial-temporal transformer (B200-native forward).
+
+API mirror of the reference's `network/vivit/vivit.py`: `STTransformer` (:85-101), `DSTTr` (:103-148),
+`XceptionVidTr` (:193-208).  Constructor signatures, attribute paths (`xcep.model.*`,
+`vit.transformer.layers[i][{0,1,2}].{norm,fn}`, `vit.mlp_head`) and therefore `state_dict` keys are the
+reference's.  `forward` hands the clip to `engine.ISTVTEngine`, which runs the hand-written sm_100a
+kernels through the C ABI; there is no torch-op or CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .module import FeedForward, PreNorm, SpatialOnlyAttention, TemporalResidualAttention
+
+
+class STTransformer(nn.Module):
+    def __init__(self, dim: int, depth: int, heads: int, dim_head: int, mlp_dim: int, dropout: float = 0.0):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        self.norm = nn.LayerNorm(dim)
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                PreNorm(dim, TemporalResidualAttention(dim, heads=heads, dim_head=dim_head, dropout=dropout)),
+                PreNorm(dim, SpatialOnlyAttention(dim, heads=heads, dim_head=dim_head, dropout=dropout)),
+                PreNorm(dim, FeedForward(dim, mlp_dim, dropout=dropout)),
+            ]))
+
+
+class DSTTr(nn.Module):
+    def __init__(self, image_size: int, patch_size: int, num_classes: int, num_frames: int, dim: int = 728,
+                 depth: int = 12, heads: int = 8, pool: str = "cls", in_channels: int = 728, dim_head: int = 64,
+                 dropout: float = 0.0, emb_dropout: float = 0.0, scale_dim: int = 4):
+        super().__init__()
+        if pool not in ("cls", "mean"):
+            raise ValueError("pool type must be either cls (cls token) or mean (mean pooling)")
+        if image_size % patch_size != 0:
+            raise ValueError("Image dimensions must be divisible by the patch size.")
+        if patch_size != 1 or in_channels != dim or dim_head != 64:
+            raise ValueError("the B200 path supports the ISTVT configuration only (patch 1, dim == channels, head 64)")
+        if num_classes != 1:
+            raise ValueError("the B200 head kernel emits one logit (num_classes=1, vivit.py:201)")
+        self.image_size, self.num_frames, self.dim, self.depth, self.heads = image_size, num_frames, dim, depth, heads
+        num_patches = (image_size // patch_size) ** 2
+        self.num_patches = num_patches
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_frames, num_patches + 1, dim))
+        self.space_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.temporal_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.transformer = STTransformer(dim, depth, heads, dim_head, dim * scale_dim, dropout)
+        self.dropout = nn.Dropout(emb_dropout)
+        self.pool = pool
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
+
+
+class XceptionVidTr(nn.Module):
+    """`XceptionVidTr()` as in the reference; `num_frames` / `precision` are additions with preserving defaults.
+
+    forward(x: [B, T, 3, H, W] fp32 CUDA) -> logits [B, 1] fp32 (prediction = logit > 0, train_CNN.py:527).
+    """
+
+    def __init__(self, num_frames: int = 6, precision: str = "bf16"):
+        super().__init__()
+        from ..models import model_selection
+        self.xcep = model_selection(modelname="xception", num_out_classes=2, dropout=0.5, batch_size=1)
+        self.vit = DSTTr(19, 1, 1, num_frames)
+        self.num_frames = num_frames
+        self.precision = precision
+        self._engine = None
+
+    def engine(self):
+        from ...engine import ISTVTEngine
+        if self._engine is None:
+            self._engine = ISTVTEngine(self)
+        return self._engine
+
+    def forward(self, x: torch.Tensor, return_attention: bool = False):
+        return self.engine().forward(self, x, precision=self.precision, return_attention=return_attention)
+
+    def _apply(self, fn, *args, **kwargs):  # .cuda() / .to(): drop the packed-weight cache
+        self._engine = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._engine = None
+        return super().load_state_dict(*args, **kwargs)

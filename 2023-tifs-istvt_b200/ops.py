@@ -1,0 +1,279 @@
+"""Tensor-level wrappers over the C ABI: one Python function per kernel family.
+
+torch is used here for device memory, streams and nothing else — every function validates its
+arguments, allocates the output with `torch.empty`, and hands raw device pointers plus the current CUDA
+stream to libistvt_b200.so.  Non-CUDA tensors are rejected (there is no CPU path).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+BF16, F32 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(f"istvt_b200: unsupported dtype {t.dtype} (bf16 or fp32 only)")
+
+
+def _torch_dt(code: int) -> torch.dtype:
+    return torch.bfloat16 if code == BF16 else torch.float32
+
+
+def _chk(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise ValueError("istvt_b200: tensors must live on a CUDA device (no CPU fallback by design)")
+        if not t.is_contiguous():
+            raise ValueError("istvt_b200: tensors must be contiguous")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError("istvt_b200: all tensors of one call must be on the same device")
+    assert dev is not None
+    return dev
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class _on:
+    """Make `dev` the current CUDA device for the duration of a launch (cheap when it already is)."""
+
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, dev: torch.device):
+        self.dev = dev
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.dev.index:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+# ----------------------------------------------------------------------------------------------
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype: torch.dtype,
+              eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _chk(x, gamma, beta, out)
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype, device=dev)
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_layernorm_fwd(_ptr(x), _dt(x), _ptr(gamma), _ptr(beta), _ptr(out), _dt(out),
+                                                  rows, dim, eps, _stream(dev)), "istvt_layernorm_fwd")
+    return out
+
+
+def layernorm_diff(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype: torch.dtype,
+                   eps: float = 1e-5, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x: fp32 [B, F, P, D] -> (LN(x), self-subtract difference), both [B, F, P, D] in out_dtype."""
+    dev = _chk(x, gamma, beta)
+    if x.dtype != torch.float32 or x.dim() != 4:
+        raise ValueError("layernorm_diff expects an fp32 [B, F, P, D] token tensor")
+    b, f, p, d = x.shape
+    if out is None:
+        xn = torch.empty(x.shape, dtype=out_dtype, device=dev)
+        diff = torch.empty(x.shape, dtype=out_dtype, device=dev)
+    else:
+        xn, diff = out
+        _chk(xn, diff)
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_layernorm_diff_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(xn), _ptr(diff),
+                                                       _dt(xn), b, f, p, d, eps, _stream(dev)),
+                   "istvt_layernorm_diff_fwd")
+    return xn, diff
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[m, n] = act(a[m, :] . w[n, :] + bias[n]) + residual[m, n].  a: [..., K], w: [N, K].
+
+    bf16 operands run the tcgen05 kernel, fp32 operands the SIMT validation kernel.
+    `residual` must be fp32; pass `out=residual` for the in-place residual update.
+    """
+    dev = _chk(a, w, bias, residual, out)
+    k = a.shape[-1]
+    m = a.numel() // k
+    n = w.shape[0]
+    if w.shape[1] != k or a.dtype != w.dtype:
+        raise ValueError(f"gemm: a {tuple(a.shape)} {a.dtype} vs w {tuple(w.shape)} {w.dtype}")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != n):
+        raise ValueError("gemm: bias must be fp32 [N]")
+    if residual is not None and (residual.dtype != torch.float32 or residual.numel() != m * n):
+        raise ValueError("gemm: residual must be fp32 [M, N]")
+    if out is None:
+        if out_dtype is None:
+            out_dtype = torch.float32 if (residual is not None or a.dtype == torch.float32) else a.dtype
+        out = torch.empty(*a.shape[:-1], n, dtype=out_dtype, device=dev)
+    elif out.numel() != m * n:
+        raise ValueError("gemm: out has the wrong size")
+    st = _stream(dev)
+    with _on(dev):
+        if a.dtype == torch.bfloat16:
+            _lib.check(_lib.lib().istvt_gemm_fwd(_ptr(a), k, _ptr(w), k, _ptr(out), n, _dt(out), m, n, k, _ptr(bias),
+                                                 _ptr(residual), n, act, st), "istvt_gemm_fwd")
+        else:
+            if out.dtype != torch.float32:
+                raise ValueError("gemm: fp32 operands need an fp32 output")
+            _lib.check(_lib.lib().istvt_gemm_f32_fwd(_ptr(a), k, _ptr(w), k, _ptr(out), n, m, n, k, _ptr(bias),
+                                                     _ptr(residual), n, act, st), "istvt_gemm_f32_fwd")
+    return out
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int = ACT_RELU) -> torch.Tensor:
+    """x: NHWC [n, h, w, cin]; w: [cout, 3, 3, cin] (same dtype); -> NHWC [n, h-2, w-2, cout]."""
+    dev = _chk(x, w, bias)
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    if tuple(w.shape) != (cout, 3, 3, cin) or w.dtype != x.dtype:
+        raise ValueError("conv3x3: weight must be [cout, 3, 3, cin] in the activation dtype")
+    y = torch.empty(n, h - 2, wd - 2, cout, dtype=x.dtype, device=dev)
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_conv3x3_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), _dt(x), n, h, wd, cin, cout,
+                                                act, _stream(dev)), "istvt_conv3x3_fwd")
+    return y
+
+
+def conv_stem(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """x: fp32 NCHW [n, 3, h, w]; w: fp32 [32, 3, 3, 3]; -> NHWC [n, ho, wo, 32]."""
+    dev = _chk(x, w, bias)
+    if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError("conv_stem expects an fp32 NCHW [n, 3, h, w] input")
+    n, _, h, wd = x.shape
+    cout = w.shape[0]
+    ho, wo = (h - 3) // 2 + 1, (wd - 3) // 2 + 1
+    y = torch.empty(n, ho, wo, cout, dtype=out_dtype, device=dev)
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_conv_stem_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), _dt(y), n, h, wd, cout,
+                                                  _stream(dev)), "istvt_conv_stem_fwd")
+    return y
+
+
+def dwconv3x3(x: torch.Tensor, w: torch.Tensor, relu_in: bool) -> torch.Tensor:
+    """x: NHWC; w: fp32 [3, 3, c]."""
+    dev = _chk(x, w)
+    n, h, wd, c = x.shape
+    if tuple(w.shape) != (3, 3, c) or w.dtype != torch.float32:
+        raise ValueError("dwconv3x3: weight must be fp32 [3, 3, c]")
+    y = torch.empty_like(x)
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_dwconv3x3_fwd(_ptr(x), _ptr(w), _ptr(y), _dt(x), n, h, wd, c, int(relu_in),
+                                                  _stream(dev)), "istvt_dwconv3x3_fwd")
+    return y
+
+
+def subsample2(x: torch.Tensor) -> torch.Tensor:
+    dev = _chk(x)
+    n, h, wd, c = x.shape
+    y = torch.empty(n, (h - 1) // 2 + 1, (wd - 1) // 2 + 1, c, dtype=x.dtype, device=dev)
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_subsample2_fwd(_ptr(x), _ptr(y), _dt(x), n, h, wd, c, _stream(dev)),
+                   "istvt_subsample2_fwd")
+    return y
+
+
+def pool_add(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+    dev = _chk(x, skip)
+    n, h, wd, c = x.shape
+    ho, wo = (h - 1) // 2 + 1, (wd - 1) // 2 + 1
+    if skip.numel() != n * ho * wo * c or skip.dtype != x.dtype:
+        raise ValueError("pool_add: skip must be [n, ho, wo, c] in the activation dtype")
+    y = torch.empty(n, ho, wo, c, dtype=x.dtype, device=dev)
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_pool_add_fwd(_ptr(x), _ptr(skip), _ptr(y), _dt(x), n, h, wd, c, _stream(dev)),
+                   "istvt_pool_add_fwd")
+    return y
+
+
+def pool_add_tokens(x: torch.Tensor, skip: torch.Tensor, pos_emb: torch.Tensor, tokens: torch.Tensor,
+                    batch: int, t: int) -> None:
+    """Writes tokens[b, f+1, 1+p, :] = maxpool(x)+skip+pos_emb[f, 1+p, :]; tokens: fp32 [B, T+1, P, C]."""
+    dev = _chk(x, skip, pos_emb, tokens)
+    n, h, wd, c = x.shape
+    ho, wo = (h - 1) // 2 + 1, (wd - 1) // 2 + 1
+    if n != batch * t or tokens.dtype != torch.float32 or pos_emb.dtype != torch.float32:
+        raise ValueError("pool_add_tokens: bad batch/frames or dtypes")
+    if tokens.numel() != batch * (t + 1) * (ho * wo + 1) * c or pos_emb.numel() != t * (ho * wo + 1) * c:
+        raise ValueError("pool_add_tokens: token / pos_emb buffers have the wrong size")
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_pool_add_tokens_fwd(_ptr(x), _ptr(skip), _ptr(pos_emb), _ptr(tokens), _dt(x),
+                                                        batch, t, h, wd, c, _stream(dev)),
+                   "istvt_pool_add_tokens_fwd")
+
+
+def token_fill(tokens: torch.Tensor, space_token: torch.Tensor, temporal_token: torch.Tensor,
+               pos_emb: torch.Tensor) -> None:
+    dev = _chk(tokens, space_token, temporal_token, pos_emb)
+    b, f, p, d = tokens.shape
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_token_fill_fwd(_ptr(tokens), _ptr(space_token), _ptr(temporal_token),
+                                                   _ptr(pos_emb), b, f - 1, p, d, _stream(dev)),
+                   "istvt_token_fill_fwd")
+
+
+def attn_temporal(qk: torch.Tensor, v: torch.Tensor, batch: int, frames: int, tokens: int, heads: int,
+                  scale: float, want_probs: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    dev = _chk(qk, v)
+    inner = heads * 64
+    rows = batch * frames * tokens
+    if qk.numel() != rows * 2 * inner or v.numel() != rows * inner or qk.dtype != v.dtype:
+        raise ValueError("attn_temporal: qk must be [rows, 2*heads*64] and v [rows, heads*64]")
+    out = torch.empty(rows, inner, dtype=qk.dtype, device=dev)
+    probs = torch.empty(batch, heads, tokens, frames, frames, dtype=torch.float32, device=dev) if want_probs else None
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_attn_temporal_fwd(_ptr(qk), _ptr(v), _ptr(out), _ptr(probs), _dt(qk), batch,
+                                                      frames, tokens, heads, scale, _stream(dev)),
+                   "istvt_attn_temporal_fwd")
+    return out, probs
+
+
+def attn_spatial(qkv: torch.Tensor, batch_frames: int, tokens: int, heads: int, scale: float,
+                 want_probs: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    dev = _chk(qkv)
+    inner = heads * 64
+    rows = batch_frames * tokens
+    if qkv.numel() != rows * 3 * inner:
+        raise ValueError("attn_spatial: qkv must be [rows, 3*heads*64]")
+    out = torch.empty(rows, inner, dtype=qkv.dtype, device=dev)
+    probs = torch.empty(batch_frames, heads, tokens, tokens, dtype=torch.float32, device=dev) if want_probs else None
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_attn_spatial_fwd(_ptr(qkv), _ptr(out), _ptr(probs), _dt(qkv), batch_frames,
+                                                     tokens, heads, scale, _stream(dev)), "istvt_attn_spatial_fwd")
+    return out, probs
+
+
+def head(tokens: torch.Tensor, norm_g, norm_b, head_g, head_b, head_w, head_bias, eps: float = 1e-5) -> torch.Tensor:
+    """tokens: fp32 [B, F, P, D] -> logits fp32 [B, 1] from token (0, 0)."""
+    dev = _chk(tokens, norm_g, norm_b, head_g, head_b, head_w, head_bias)
+    b, f, p, d = tokens.shape
+    logits = torch.empty(b, 1, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _lib.check(_lib.lib().istvt_head_fwd(_ptr(tokens), f * p, _ptr(norm_g), _ptr(norm_b), _ptr(head_g),
+                                             _ptr(head_b), _ptr(head_w), _ptr(head_bias), _ptr(logits), b, d, eps,
+                                             _stream(dev)), "istvt_head_fwd")
+    return logits

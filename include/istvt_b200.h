@@ -1,0 +1,191 @@
+/*
+ * istvt_b200 — C ABI of the B200-native ISTVT forward hot path.
+ *
+ * One entry point per kernel family.  Every function takes raw DEVICE pointers, plain sizes and the
+ * CUDA stream to launch on (a `cudaStream_t` passed as `void*`), and returns 0 on success, a positive
+ * `cudaError_t` value, or a negative ISTVT_ERR_* code.  No C++ exceptions, no Python / torch objects
+ * cross this boundary.  All functions are re-entrant across host threads bound to different devices
+ * (the `nn.DataParallel` use at train_CNN.py:185-186): they launch on the caller's current device and
+ * the given stream and keep only immutable per-device caches.
+ *
+ * The reference (Vill-Lab/2023-TIFS-ISTVT) has no FFI of its own — every op on its hot path is an ATen
+ * call made from Python.  Each entry below therefore cites the reference Python call site(s) whose
+ * arithmetic it replaces (paths relative to the reference root).
+ *
+ * Layout conventions (differ from the reference's NCHW on purpose):
+ *   - images / feature maps: NHWC, channel innermost;
+ *   - token sequences: row-major [rows, dim], row = ((b * F + f) * P + p), F = T+1 frames, P = 362;
+ *   - `dtype` arguments: ISTVT_BF16 (0) or ISTVT_F32 (1) select the activation element type.
+ */
+#ifndef ISTVT_B200_H
+#define ISTVT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISTVT_OK 0
+#define ISTVT_ERR_INVALID_ARG (-1)
+#define ISTVT_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled entry point not available */
+#define ISTVT_ERR_TMAP (-3)      /* tensor-map encoding rejected the shape/strides */
+#define ISTVT_ERR_UNSUPPORTED (-4)
+
+#define ISTVT_BF16 0
+#define ISTVT_F32 1
+
+#define ISTVT_ACT_NONE 0
+#define ISTVT_ACT_RELU 1
+#define ISTVT_ACT_GELU 2 /* exact erf GELU, nn.GELU() default (network/vivit/module.py:28) */
+
+typedef void* istvt_stream_t; /* cudaStream_t */
+
+/* Library ABI version (bumped when a signature changes). */
+int istvt_abi_version(void);
+/* Human-readable text for a return code of any function below (static storage). */
+const char* istvt_error_string(int code);
+/* Number of kernel launches issued through this library by the calling process (all threads). */
+int64_t istvt_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm(dim) over the last axis, eps inside the sqrt, affine gamma/beta (fp32).
+ * Replaces: PreNorm.norm at network/vivit/module.py:18,21 (LN before spatial attention and before
+ * the MLP), STTransformer.norm at network/vivit/vivit.py:89,101.
+ * x: [rows, dim] (x_dtype), y: [rows, dim] (y_dtype).
+ * ------------------------------------------------------------------------------------------- */
+int istvt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
+                        int y_dtype, int64_t rows, int dim, float eps, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm fused with the temporal self-subtract of TemporalResidualAttention.
+ * Replaces: PreNorm.norm (module.py:21) followed by module.py:191-194:
+ *   xn   = LN(x)                                             -> `xn`   (operand of to_v,  module.py:196)
+ *   diff = cat(xn[:, :2], xn[:, 2:] - xn[:, 1:-1], dim=1)    -> `diff` (operand of to_qk, module.py:195)
+ * x: fp32 [batch, frames, tokens, dim]; xn/diff: [batch, frames, tokens, dim] (out_dtype).
+ * The difference is formed in fp32 before rounding to out_dtype.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_layernorm_diff_fwd(const float* x, const float* gamma, const float* beta, void* xn, void* diff,
+                             int out_dtype, int batch, int frames, int tokens, int dim, float eps,
+                             istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * C[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] ) + residual[m, n]
+ * tcgen05 / TMEM tensor-core GEMM, bf16 operands, fp32 accumulation, TMA-fed.
+ * Replaces every nn.Linear on the path — to_qk / to_v / to_out (module.py:182-188,195-196,206),
+ * to_qkv / to_out (module.py:74-79,83,92), FeedForward.net (module.py:27-31,34) with the residual adds of
+ * vivit.py:99-100 — and every 1x1 convolution + BatchNorm(+ReLU) of the Xception entry flow
+ * (SeparableConv2d.pointwise xception.py:44,48; Block.skip/skipbn xception.py:57-58,94-96) once BN is
+ * folded into W and bias.
+ * A: bf16 [m, k] row pitch lda; W: bf16 [n, k] row pitch ldw (nn.Linear weight layout);
+ * C: c_dtype [m, n] row pitch ldc; bias: fp32 [n] or NULL; residual: fp32 [m, n] row pitch ldr or NULL
+ * (may alias C when c_dtype is F32).  Pitches are in elements; lda, ldw, ldc must be multiples of 8.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_gemm_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c, int64_t ldc, int c_dtype,
+                   int64_t m, int n, int k, const float* bias, const float* residual, int64_t ldr, int act,
+                   istvt_stream_t stream);
+
+/* Same contract in fp32 (SIMT FFMA kernel; the 1e-4 validation mode, not the performance path).
+ * A, W, C, residual all fp32. */
+int istvt_gemm_f32_fwd(const float* a, int64_t lda, const float* w, int64_t ldw, float* c, int64_t ldc, int64_t m,
+                       int n, int k, const float* bias, const float* residual, int64_t ldr, int act,
+                       istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense 3x3 stride-1 pad-0 convolution as an implicit GEMM on the tensor cores, + folded BN + act.
+ * Replaces: conv2 + bn2 + relu, xception.py:122-123,198-200.
+ * x: NHWC [n, h, w, cin] (dtype); wt: [cout, 3, 3, cin] (dtype, BN scale folded in); bias fp32 [cout];
+ * y: NHWC [n, h-2, w-2, cout] (dtype).  bf16 runs on tcgen05, fp32 on the SIMT kernel.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_conv3x3_fwd(const void* x, const void* wt, const float* bias, void* y, int dtype, int n, int h, int w,
+                      int cin, int cout, int act, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stem: 3x3 stride-2 pad-0 convolution 3 -> cout on an NCHW fp32 clip + folded BN + ReLU, NHWC out.
+ * Replaces: conv1 + bn1 + relu, xception.py:118-120,194-196 (input rearrange vivit.py:204 is a view).
+ * x: fp32 NCHW [n, 3, h, w]; wt: fp32 [cout, 3, 3, 3] (BN scale folded); bias fp32 [cout];
+ * y: NHWC [n, (h-3)/2+1, (w-3)/2+1, cout] (dtype).  cout must be 32.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_conv_stem_fwd(const float* x, const float* wt, const float* bias, void* y, int dtype, int n, int h,
+                        int w, int cout, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depthwise 3x3 stride-1 pad-1 convolution, optional ReLU applied to the input on load.
+ * Replaces: SeparableConv2d.conv1 (xception.py:43,47) and the ReLU that precedes it inside Block.rep
+ * (xception.py:66-67,72-73,82-85).
+ * x, y: NHWC [n, h, w, c] (dtype); wt: fp32 [3, 3, c] (tap-major, channel innermost). c % 8 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_dwconv3x3_fwd(const void* x, const float* wt, void* y, int dtype, int n, int h, int w, int c,
+                        int relu_in, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pixel subsampling by 2 in both axes (rows/cols 0, 2, 4, ...): the gather of a stride-2 1x1 convolution.
+ * Replaces the stride of Block.skip (xception.py:57, 94); the 1x1 itself is istvt_gemm_fwd.
+ * x: NHWC [n, h, w, c]; y: NHWC [n, (h-1)/2+1, (w-1)/2+1, c].
+ * ------------------------------------------------------------------------------------------- */
+int istvt_subsample2_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MaxPool2d(3, stride 2, pad 1) of the block body + residual add of the skip branch.
+ * Replaces: nn.MaxPool2d at xception.py:87-88 and `x += skip` at xception.py:100.
+ * x: NHWC [n, h, w, c]; skip: NHWC [n, ho, wo, c], ho = (h-1)/2+1; y: NHWC [n, ho, wo, c].
+ * ------------------------------------------------------------------------------------------- */
+int istvt_pool_add_fwd(const void* x, const void* skip, void* y, int dtype, int n, int h, int w, int c,
+                       istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Block-3 variant of pool+add that writes straight into the transformer token buffer and adds the
+ * positional embedding, so the NCHW->tokens permute copy of the reference disappears.
+ * Replaces: xception.py:87-88,100 + Rearrange 'b t c h w -> b t (h w) c' (vivit.py:115,133) + the patch
+ * part of `x += pos_embedding` (vivit.py:138).
+ * x: NHWC [batch*t, h, w, c]; skip: NHWC [batch*t, ho, wo, c]; pos_emb: fp32 [t, ho*wo+1, c];
+ * tokens: fp32 [batch, t+1, ho*wo+1, c]; element (b, f+1, 1+p, :) = pool(x)+skip+pos_emb[f, 1+p, :].
+ * ------------------------------------------------------------------------------------------- */
+int istvt_pool_add_tokens_fwd(const void* x, const void* skip, const float* pos_emb, float* tokens, int dtype,
+                              int batch, int t, int h, int w, int c, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Class-token fill of the token buffer.
+ * Replaces: vivit.py:136-140 — tokens[b, 0, p, :] = temporal_token (no positional embedding, all p);
+ * tokens[b, f+1, 0, :] = space_token + pos_emb[f, 0, :].
+ * ------------------------------------------------------------------------------------------- */
+int istvt_token_fill_fwd(float* tokens, const float* space_token, const float* temporal_token,
+                         const float* pos_emb, int batch, int t, int tokens_per_frame, int dim,
+                         istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Temporal self-attention across frames at each token position (F x F per (clip, head, position)).
+ * Replaces: module.py:197-205 (the rearranges, einsum, softmax, einsum, rearrange).
+ * qk: [batch*frames*tokens, 2*heads*64] (q columns then k columns, head-major); v: [rows, heads*64];
+ * out: [rows, heads*64]; probs (optional, may be NULL): fp32 [batch, heads, tokens, frames, frames].
+ * q/k/v are read in place: consecutive frames of one position are `tokens` rows apart.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_attn_temporal_fwd(const void* qk, const void* v, void* out, float* probs, int dtype, int batch,
+                            int frames, int tokens, int heads, float scale, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spatial self-attention over the tokens of each frame (tokens x tokens per (clip, head, frame)).
+ * Replaces: module.py:84-91.  bf16: tcgen05 QK^T and PV with the softmax fused in between, q/k/v tiles
+ * fetched by TMA straight from the packed [rows, 3*heads*64] projection output (no permute copies).
+ * qkv: [batch_frames*tokens, 3*heads*64]; out: [rows, heads*64];
+ * probs (optional, may be NULL): fp32 [batch_frames, heads, tokens, tokens], laid out so that a
+ * [batch, frames] split of batch_frames reproduces the reference's [b, h, t, hw, hw] after a transpose.
+ * dim_head is fixed at 64; tokens <= 384.  fp32 dtype runs the SIMT validation kernel.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_attn_spatial_fwd(const void* qkv, void* out, float* probs, int dtype, int batch_frames, int tokens,
+                           int heads, float scale, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Classification head on token (0, 0) of every clip: final transformer LayerNorm (row-wise, so only
+ * that row is needed), mlp_head LayerNorm, Linear(dim -> 1).
+ * Replaces: vivit.py:101 (restricted to the rows read afterwards), vivit.py:144-148.
+ * tokens: fp32 [batch, rows_per_clip, dim]; logits: fp32 [batch].
+ * ------------------------------------------------------------------------------------------- */
+int istvt_head_fwd(const float* tokens, int64_t rows_per_clip, const float* norm_g, const float* norm_b,
+                   const float* head_g, const float* head_b, const float* head_w, const float* head_bias,
+                   float* logits, int batch, int dim, float eps, istvt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISTVT_B200_H */

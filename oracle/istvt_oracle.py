@@ -1,0 +1,212 @@
+"""TEST INFRASTRUCTURE — CPU oracle of the ISTVT forward hot path.
+
+A plain-op fp32 restatement of the reference's algorithm, written against a *state_dict* (reference key
+names) so that it needs none of the reference's classes.  Every function cites the
+reference lines it follows (paths relative to the reference root).  It exists to check the CUDA path:
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it; the
+product package (2023-tifs-istvt_b200/) never does.
+
+Pinning: tests/test_oracle.py checks this file (a) against the golden vectors in tests/golden/ that
+oracle/make_golden.py produced by running the UNMODIFIED reference modules in the build container, and
+(b), where /root/reference is present, against the reference modules directly.
+The relevance-propagation part of the path has no reference implementation in the tree:
+nothing here covers it — parity for it would be "unpinned".
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+BN_EPS = 1e-5   # nn.BatchNorm2d default (xception.py:119,123,58,69,75)
+LN_EPS = 1e-5   # nn.LayerNorm default (module.py:18, vivit.py:89,128)
+TOKENS_PER_FRAME = 19 * 19 + 1   # hard-coded in module.py:84,192,197-198 and vivit.py:144
+
+
+def _bn(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """BatchNorm2d in eval mode (running statistics)."""
+    return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
+                        sd[prefix + ".bias"], training=False, eps=BN_EPS)
+
+
+def _sep(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """SeparableConv2d.forward, xception.py:46-49: depthwise 3x3 pad 1 (groups = C) then pointwise 1x1."""
+    x = F.conv2d(x, sd[prefix + ".conv1.weight"], None, 1, 1, 1, groups=x.shape[1])
+    return F.conv2d(x, sd[prefix + ".pointwise.weight"])
+
+
+def _block(sd: SD, prefix: str, inp: torch.Tensor, start_with_relu: bool) -> torch.Tensor:
+    """Block.forward, xception.py:91-101, for the entry-flow configuration (reps=2, stride 2, grow_first).
+
+    rep = [ReLU] Sep BN ReLU Sep BN MaxPool(3,2,1) (xception.py:66-89); the leading ReLU is out-of-place
+    (xception.py:82-85), so `skip` sees the un-rectified block input.
+    """
+    i0 = 1 if start_with_relu else 0          # index of the first SeparableConv2d inside rep
+    x = F.relu(inp) if start_with_relu else inp
+    x = _bn(sd, f"{prefix}.rep.{i0 + 1}", _sep(sd, f"{prefix}.rep.{i0}", x))
+    x = F.relu(x)
+    x = _bn(sd, f"{prefix}.rep.{i0 + 4}", _sep(sd, f"{prefix}.rep.{i0 + 3}", x))
+    x = F.max_pool2d(x, 3, 2, 1)
+    skip = _bn(sd, f"{prefix}.skipbn", F.conv2d(inp, sd[f"{prefix}.skip.weight"], None, 2))   # xception.py:94-96
+    return x + skip                                                                            # xception.py:100
+
+
+def entry_flow(sd: SD, frames: torch.Tensor, taps: Optional[dict] = None, prefix: str = "xcep.model") -> torch.Tensor:
+    """Xception.low_level_features, xception.py:193-206.  frames [n,3,H,W] -> [n,728,19,19]."""
+    x = F.relu(_bn(sd, f"{prefix}.bn1", F.conv2d(frames, sd[f"{prefix}.conv1.weight"], None, 2)))   # :194-196
+    x = F.relu(_bn(sd, f"{prefix}.bn2", F.conv2d(x, sd[f"{prefix}.conv2.weight"])))                 # :198-200
+    if taps is not None:
+        taps["stem"] = x
+    x = _block(sd, f"{prefix}.block1", x, start_with_relu=False)   # xception.py:126
+    if taps is not None:
+        taps["block1"] = x
+    x = _block(sd, f"{prefix}.block2", x, start_with_relu=True)    # xception.py:127
+    if taps is not None:
+        taps["block2"] = x
+    x = _block(sd, f"{prefix}.block3", x, start_with_relu=True)    # xception.py:128
+    if taps is not None:
+        taps["block3"] = x
+    return x
+
+
+def build_tokens(sd: SD, feats: torch.Tensor, prefix: str = "vit") -> torch.Tensor:
+    """DSTTr.forward up to the transformer, vivit.py:133-142.  feats [B,T,C,h,w] -> [B,(T+1)*362,C]."""
+    b, t, c, h, w = feats.shape
+    x = feats.permute(0, 1, 3, 4, 2).reshape(b, t, h * w, c)                     # 'b t c h w -> b t (h w) c' (:115)
+    space = sd[f"{prefix}.space_token"].reshape(1, 1, 1, c).expand(b, t, 1, c)   # :136
+    x = torch.cat((space, x), dim=2)                                             # :137
+    x = x + sd[f"{prefix}.pos_embedding"][:, :, : h * w + 1]                     # :138
+    temporal = sd[f"{prefix}.temporal_token"].reshape(1, 1, 1, c).expand(b, 1, h * w + 1, c)   # :139
+    x = torch.cat((temporal, x), dim=1)                                          # :140 (no pos-emb on frame 0)
+    return x.reshape(b, (t + 1) * (h * w + 1), c)                                # :142
+
+
+def _ln(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], LN_EPS)
+
+
+def temporal_attention(sd: SD, prefix: str, xn: torch.Tensor, heads: int = 8, taps: Optional[dict] = None,
+                       tag: str = "") -> torch.Tensor:
+    """TemporalResidualAttention.forward, module.py:190-208.  xn is the PreNorm output (module.py:21)."""
+    b, n, d = xn.shape
+    p = TOKENS_PER_FRAME
+    f = n // p
+    xr = xn.reshape(b, f, p, d)                                                          # :191
+    res = torch.cat((xr[:, 0:2], xr[:, 2:] - xr[:, 1:-1]), dim=1).reshape(b, n, d)       # :192-193
+    qk = F.linear(res, sd[prefix + ".to_qk.weight"])                                      # :194
+    v = F.linear(xn, sd[prefix + ".to_v.weight"])                                         # :195
+    q, k = qk.chunk(2, dim=-1)
+    split = lambda t: t.reshape(b, f, p, heads, -1).permute(0, 3, 2, 1, 4)               # 'b (t hw) (h d) -> b h hw t d'
+    q, k, v = split(q), split(k), split(v)                                                # :196-197
+    dots = torch.matmul(q, k.transpose(-1, -2)) * (q.shape[-1] ** -0.5)                   # :199, scale :180
+    attn = dots.softmax(dim=-1)                                                           # :201
+    if taps is not None:
+        taps[tag + "A_t"] = attn                                                          # [b, h, hw, f, f]
+    out = torch.matmul(attn, v)                                                           # :203
+    out = out.permute(0, 3, 2, 1, 4).reshape(b, n, -1)                                    # 'b h hw t d -> b (t hw) (h d)'
+    return F.linear(out, sd[prefix + ".to_out.0.weight"], sd[prefix + ".to_out.0.bias"])  # :205
+
+
+def spatial_attention(sd: SD, prefix: str, xn: torch.Tensor, heads: int = 8, taps: Optional[dict] = None,
+                      tag: str = "") -> torch.Tensor:
+    """SpatialOnlyAttention.forward, module.py:81-93."""
+    b, n, d = xn.shape
+    p = TOKENS_PER_FRAME
+    f = n // p
+    qkv = F.linear(xn, sd[prefix + ".to_qkv.weight"]).chunk(3, dim=-1)                    # :83
+    split = lambda t: t.reshape(b, f, p, heads, -1).permute(0, 3, 1, 2, 4)               # 'b (t hw) (h d) -> b h t hw d'
+    q, k, v = map(split, qkv)                                                             # :84
+    dots = torch.matmul(q, k.transpose(-1, -2)) * (q.shape[-1] ** -0.5)                   # :86, scale :72
+    attn = dots.softmax(dim=-1)                                                           # :88
+    if taps is not None:
+        taps[tag + "A_s"] = attn                                                          # [b, h, f, hw, hw]
+    out = torch.matmul(attn, v)                                                           # :90
+    out = out.permute(0, 2, 3, 1, 4).reshape(b, n, -1)                                    # 'b h t hw d -> b (t hw) (h d)'
+    return F.linear(out, sd[prefix + ".to_out.0.weight"], sd[prefix + ".to_out.0.bias"])  # :92
+
+
+def feed_forward(sd: SD, prefix: str, xn: torch.Tensor) -> torch.Tensor:
+    """FeedForward.forward, module.py:27-34: Linear, exact-erf GELU, Linear (dropout p = 0)."""
+    h = F.gelu(F.linear(xn, sd[prefix + ".net.0.weight"], sd[prefix + ".net.0.bias"]))
+    return F.linear(h, sd[prefix + ".net.3.weight"], sd[prefix + ".net.3.bias"])
+
+
+def transformer_layer(sd: SD, layer: int, x: torch.Tensor, taps: Optional[dict] = None,
+                      prefix: str = "vit.transformer") -> torch.Tensor:
+    """One iteration of STTransformer.forward's loop, vivit.py:98-100."""
+    lp = f"{prefix}.layers.{layer}"
+    tag = f"layer{layer}."
+    y = temporal_attention(sd, f"{lp}.0.fn", _ln(sd, f"{lp}.0.norm", x), taps=taps, tag=tag)
+    y = spatial_attention(sd, f"{lp}.1.fn", _ln(sd, f"{lp}.1.norm", y), taps=taps, tag=tag)
+    x = y + x                                                                             # vivit.py:99
+    x = feed_forward(sd, f"{lp}.2.fn", _ln(sd, f"{lp}.2.norm", x)) + x                    # vivit.py:100
+    if taps is not None:
+        taps[tag + "out"] = x
+    return x
+
+
+def num_layers(sd: SD, prefix: str = "vit.transformer") -> int:
+    n = 0
+    while f"{prefix}.layers.{n}.0.norm.weight" in sd:
+        n += 1
+    return n
+
+
+def transformer(sd: SD, x: torch.Tensor, taps: Optional[dict] = None, prefix: str = "vit.transformer") -> torch.Tensor:
+    """STTransformer.forward, vivit.py:97-101."""
+    for layer in range(num_layers(sd, prefix)):
+        x = transformer_layer(sd, layer, x, taps, prefix)
+    return _ln(sd, f"{prefix}.norm", x)                                                   # vivit.py:101
+
+
+def forward(sd: SD, clips: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+    """XceptionVidTr.forward, vivit.py:202-208, + DSTTr.forward vivit.py:132-148.  clips [B,T,3,H,W] -> [B,1]."""
+    b, t = clips.shape[:2]
+    feats = entry_flow(sd, clips.reshape(b * t, *clips.shape[2:]), taps)                  # vivit.py:204-205
+    feats = feats.reshape(b, t, *feats.shape[1:])                                         # vivit.py:206
+    x = build_tokens(sd, feats)
+    if taps is not None:
+        taps["tokens"] = x
+    x = transformer(sd, x, taps)
+    x = x.reshape(b, t + 1, TOKENS_PER_FRAME, -1)[:, 0, 0]                                # vivit.py:144-146
+    return F.linear(_ln(sd, "vit.mlp_head.0", x), sd["vit.mlp_head.1.weight"], sd["vit.mlp_head.1.bias"])  # :148
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic "trained-like" weights: at default init every BatchNorm / LayerNorm is
+# ~identity and BN/LN folding bugs are invisible; tests randomise them, reproducibly from key names.
+# ------------------------------------------------------------------------------------------------
+def sensitise_(sd: SD, seed: int = 1234) -> SD:
+    """In-place: randomise BN gamma/beta/running stats and LN gamma/beta, shrink pos-emb/tokens to the
+    feature scale so that entry-flow errors reach the logit.  Deterministic in (seed, key order)."""
+    g = torch.Generator().manual_seed(seed)
+    rnd = lambda shape: torch.rand(shape, generator=g)
+    for k in sorted(sd.keys()):
+        v = sd[k]
+        on_path = k.startswith("vit.") or any(
+            k.startswith(f"xcep.model.{m}") for m in ("conv1", "bn1", "conv2", "bn2", "block1.", "block2.", "block3."))
+        if not on_path:
+            continue
+        if k.endswith("running_mean"):
+            v.copy_((rnd(v.shape) - 0.5) * 0.2)
+        elif k.endswith("running_var"):
+            v.copy_(0.5 + rnd(v.shape))
+        elif k.endswith("num_batches_tracked"):
+            continue
+        elif ".norm." in k or "mlp_head.0" in k or "skipbn" in k or ".bn" in k or (
+                "xcep.model.block" in k and ".rep." in k and v.dim() == 1):
+            if k.endswith("weight"):
+                v.copy_(0.75 + 0.5 * rnd(v.shape))
+            elif k.endswith("bias"):
+                v.copy_((rnd(v.shape) - 0.5) * 0.2)
+        elif k in ("vit.pos_embedding", "vit.space_token", "vit.temporal_token"):
+            v.mul_(0.05)
+    return sd
+
+
+def fingerprint_indices(numel: int, count: int = 2048, seed: int = 7) -> torch.Tensor:
+    """Fixed pseudo-random sample positions used by the golden fixtures for large tensors."""
+    g = torch.Generator().manual_seed(seed + numel % 1000003)
+    return torch.randint(0, numel, (min(count, numel),), generator=g)

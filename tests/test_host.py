@@ -1,0 +1,71 @@
+"""CPU: host-side logic — module tree / state_dict schema, registry, error behaviour, BN folding."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import pkg
+
+
+@pytest.fixture(scope="module")
+def model():
+    torch.manual_seed(0)
+    return pkg().XceptionVidTr().eval()
+
+
+def test_state_dict_schema(model):
+    sd = model.state_dict()
+    assert len(sd) == 489
+    assert sd["xcep.model.conv1.weight"].shape == (32, 3, 3, 3)
+    assert sd["xcep.model.block1.rep.0.conv1.weight"].shape == (64, 1, 3, 3)
+    assert sd["xcep.model.block1.rep.3.pointwise.weight"].shape == (128, 128, 1, 1)
+    assert sd["xcep.model.block3.skip.weight"].shape == (728, 256, 1, 1)
+    assert sd["xcep.model.block3.rep.4.pointwise.weight"].shape == (728, 728, 1, 1)
+    assert sd["xcep.model.block12.rep.4.pointwise.weight"].shape == (1024, 728, 1, 1)
+    assert sd["xcep.model.last_linear.1.weight"].shape == (2, 2048)
+    assert sd["vit.pos_embedding"].shape == (1, 6, 362, 728)
+    assert sd["vit.transformer.layers.11.0.fn.to_qk.weight"].shape == (1024, 728)
+    assert sd["vit.transformer.layers.0.0.fn.to_v.weight"].shape == (512, 728)
+    assert sd["vit.transformer.layers.0.1.fn.to_qkv.weight"].shape == (1536, 728)
+    assert sd["vit.transformer.layers.0.2.fn.net.3.weight"].shape == (728, 2912)
+    assert sd["vit.mlp_head.1.weight"].shape == (1, 728)
+    assert sum(p.numel() for p in model.parameters()) == 109172051
+
+
+def test_registry():
+    m = pkg()
+    assert isinstance(m.model_selection("resnet_3d", num_out_classes=1), m.XceptionVidTr)
+    x = m.model_selection("xception", num_out_classes=2, dropout=0.5)
+    assert isinstance(x, m.TransferModel) and hasattr(x.model, "block12")
+    with pytest.raises(NotImplementedError):
+        m.model_selection("jigsaw_multi_xcep_adv", num_out_classes=2)
+
+
+def test_no_cpu_fallback(model):
+    with pytest.raises(ValueError, match="CUDA"):
+        model(torch.zeros(1, 6, 3, 300, 300))
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 6, 300, 300))
+
+
+def test_long_clip_ctor():
+    m = pkg().XceptionVidTr(num_frames=32)
+    assert m.vit.pos_embedding.shape == (1, 32, 362, 728)
+
+
+def test_bn_folding_matches_torch(model):
+    """pack_entry's folded conv2 weights/bias reproduce conv2 -> bn2 (eval) on CPU."""
+    eng = __import__("importlib").import_module("2023-tifs-istvt_b200.engine")
+    x = model.xcep.model
+    with torch.no_grad():
+        x.bn2.running_mean.uniform_(-0.2, 0.2)
+        x.bn2.running_var.uniform_(0.5, 1.5)
+        x.bn2.weight.uniform_(0.7, 1.3)
+        x.bn2.bias.uniform_(-0.1, 0.1)
+        ep = eng.pack_entry(x, torch.float32)
+        inp = torch.randn(1, 32, 12, 12)
+        want = x.bn2(x.conv2(inp))
+        got = F.conv2d(inp, ep.conv2_w.permute(0, 3, 1, 2), ep.conv2_b)
+        assert torch.allclose(got, want, atol=1e-5)
+        b3 = ep.blocks[2]
+        assert b3.skip_w.shape == (728, 256) and b3.seps[1].pw.shape == (728, 728) and b3.seps[0].dw.shape == (3, 3, 256)
+        assert b3.start_with_relu and not ep.blocks[0].start_with_relu

@@ -1,0 +1,23 @@
+"""`-m gpu`: the whole CUDA forward (XceptionVidTr.forward -> C ABI) against the golden vectors produced from the
+unmodified reference, and against the CPU oracle."""
+import pytest
+
+import model_checks
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", ["default_init_b1", "sensitised_b2", "sensitised_t32_b1"])
+def test_golden(case, precision):
+    model_checks.run_golden_case(case, precision)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_against_cpu_oracle(precision):
+    model_checks.run_oracle_case(precision)
+
+
+@pytest.mark.gpu
+def test_api_boundary():
+    model_checks.run_api_checks()

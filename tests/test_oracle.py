@@ -1,0 +1,105 @@
+"""CPU (`-m "not gpu"`): pin the oracle.
+
+1. oracle/istvt_oracle.py vs the golden vectors that oracle/make_golden.py produced from the UNMODIFIED
+   reference modules (logits, entry-flow taps, per-layer outputs, attention maps) — must be (near) bit exact;
+2. where the reference checkout is present (build container), the oracle and the product's module tree are
+   also checked against the live reference modules.
+"""
+import os
+
+import pytest
+import torch
+
+from helpers import GOLDEN, build_model, fingerprint_check, make_input, oracle
+
+TIGHT = 2e-6   # fp32 CPU vs fp32 CPU: the only freedom is thread-count dependent summation order
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return torch.load(GOLDEN, weights_only=False)
+
+
+def _run_oracle(case):
+    O = oracle()
+    model = build_model(case)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = make_input(case["batch"], case["frames"])
+    taps = {}
+    with torch.no_grad():
+        logits = O.forward(sd, x, taps)
+    return model, logits, taps
+
+
+@pytest.mark.parametrize("name", ["default_init_b1", "sensitised_b2"])
+def test_oracle_matches_reference_golden(golden, name):
+    case = golden["cases"][name]
+    model, logits, taps = _run_oracle(case)
+    for k, want in case["weights"].items():
+        fingerprint_check(f"weights[{k}]", model.state_dict()[k], want, 0.0)
+    assert torch.allclose(logits, case["logits"], rtol=0, atol=TIGHT * max(1.0, case["logits"].abs().max().item()))
+    b, f = case["batch"], case["frames"] + 1
+    for key, want in case["taps"].items():
+        if key in ("stem", "block1", "block2", "block3"):
+            got = taps[key]
+        elif key.endswith(".A_t") or key.endswith(".A_s"):
+            got = taps[key]
+        elif key.endswith(".ff_out"):
+            continue   # ff output before the residual is not a tap of the oracle; covered by transformer_out
+        elif key.endswith(".temporal_out") or key.endswith(".spatial_out"):
+            continue
+        elif key == "transformer_out":
+            continue
+        else:
+            raise AssertionError(f"unhandled golden tap {key}")
+        fingerprint_check(f"{name}/{key}", got, want, TIGHT)
+
+
+def test_oracle_layer_outputs_match_reference_hooks(golden):
+    """temporal / spatial / ff sub-module outputs captured by forward hooks on the reference."""
+    O = oracle()
+    case = golden["cases"]["sensitised_b2"]
+    model = build_model(case)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = make_input(case["batch"], case["frames"])
+    with torch.no_grad():
+        feats = O.entry_flow(sd, x.reshape(-1, 3, 300, 300)).reshape(2, 6, 728, 19, 19)
+        h = O.build_tokens(sd, feats)
+        for layer in range(12):
+            lp = f"vit.transformer.layers.{layer}"
+            y_t = O.temporal_attention(sd, f"{lp}.0.fn", O._ln(sd, f"{lp}.0.norm", h))
+            y_s = O.spatial_attention(sd, f"{lp}.1.fn", O._ln(sd, f"{lp}.1.norm", y_t))
+            h2 = y_s + h
+            ff = O.feed_forward(sd, f"{lp}.2.fn", O._ln(sd, f"{lp}.2.norm", h2))
+            for nm, got in (("temporal_out", y_t), ("spatial_out", y_s), ("ff_out", ff)):
+                key = f"layer{layer}.{nm}"
+                if key in case["taps"]:
+                    fingerprint_check(key, got, case["taps"][key], TIGHT)
+            h = ff + h2
+        out = O._ln(sd, "vit.transformer.norm", h)
+        fingerprint_check("transformer_out", out, case["taps"]["transformer_out"], TIGHT)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/network/vivit"), reason="reference checkout not present")
+def test_against_live_reference():
+    from oracle import reference_shim
+    import importlib
+    import sys
+    O = oracle()
+    ref = reference_shim.build_reference_model(seed=0)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    # the shim put the reference's `network` package in sys.modules; drop it before importing the product
+    for k in [k for k in sys.modules if k == "network" or k.startswith("network.")]:
+        del sys.modules[k]
+    m = importlib.import_module("2023-tifs-istvt_b200")
+    torch.manual_seed(0)
+    mine = m.XceptionVidTr()
+    msd = mine.state_dict()
+    assert list(msd.keys()) == list(sd.keys())
+    for k in sd:
+        assert msd[k].shape == sd[k].shape and torch.equal(msd[k], sd[k]), f"seeded init differs at {k}"
+    O.sensitise_(sd)
+    ref.load_state_dict(sd)
+    x = make_input(1, 6, seed=5)
+    with torch.no_grad():
+        assert torch.equal(ref(x), O.forward(sd, x))
