@@ -53,24 +53,66 @@ def _stream(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-class _on:
-    """Make `dev` the current CUDA device for the duration of a launch (cheap when it already is)."""
+# ----------------------------------------------------------------------------------------------
+# Launch-level profiling (bench.py's roofline): when a recorder is installed every wrapper brackets its
+# kernel launch with a CUDA event pair recorded on the launching stream and notes the ALGORITHMIC work
+# of that launch (flops for tensor-bound kernels, bytes for HBM-bound ones; DESIGN.md §4 has the formulas).
+# ----------------------------------------------------------------------------------------------
+class LaunchRecorder:
+    def __init__(self):
+        self.records = []   # (family, flops, bytes, start_event, end_event)
 
-    __slots__ = ("dev", "prev")
+    def summary(self):
+        """{family: {"launches", "ms", "flops", "bytes"}} — call after torch.cuda.synchronize()."""
+        out = {}
+        for fam, fl, by, e0, e1 in self.records:
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
 
-    def __init__(self, dev: torch.device):
-        self.dev = dev
+
+_recorder: Optional[LaunchRecorder] = None
+
+
+def set_recorder(rec: Optional[LaunchRecorder]) -> None:
+    global _recorder
+    _recorder = rec
+
+
+class _launch:
+    """`with _launch(dev, family, flops, bytes): <one C-ABI call>` — device guard + optional event pair."""
+
+    __slots__ = ("dev", "prev", "fam", "flops", "bytes", "e0")
+
+    def __init__(self, dev: torch.device, fam: str, flops: float = 0.0, nbytes: float = 0.0):
+        self.dev, self.fam, self.flops, self.bytes = dev, fam, flops, nbytes
         self.prev = None
+        self.e0 = None
 
     def __enter__(self):
         cur = torch.cuda.current_device()
         if cur != self.dev.index:
             self.prev = cur
             torch.cuda.set_device(self.dev)
+        if _recorder is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.dev))
 
     def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(self.dev))
+            if _recorder is not None:
+                _recorder.records.append((self.fam, self.flops, self.bytes, self.e0, e1))
         if self.prev is not None:
             torch.cuda.set_device(self.prev)
+
+
+def _nbytes(*ts: Optional[torch.Tensor]) -> int:
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -81,7 +123,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtyp
     rows = x.numel() // dim
     if out is None:
         out = torch.empty(x.shape, dtype=out_dtype, device=dev)
-    with _on(dev):
+    with _launch(dev, "layernorm", 0.0, _nbytes(x, out)):
         _lib.check(_lib.lib().istvt_layernorm_fwd(_ptr(x), _dt(x), _ptr(gamma), _ptr(beta), _ptr(out), _dt(out),
                                                   rows, dim, eps, _stream(dev)), "istvt_layernorm_fwd")
     return out
@@ -101,7 +143,7 @@ def layernorm_diff(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out
     else:
         xn, diff = out
         _chk(xn, diff)
-    with _on(dev):
+    with _launch(dev, "layernorm_diff", 0.0, _nbytes(x, xn, diff)):
         _lib.check(_lib.lib().istvt_layernorm_diff_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(xn), _ptr(diff),
                                                        _dt(xn), b, f, p, d, eps, _stream(dev)),
                    "istvt_layernorm_diff_fwd")
@@ -133,7 +175,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     elif out.numel() != m * n:
         raise ValueError("gemm: out has the wrong size")
     st = _stream(dev)
-    with _on(dev):
+    with _launch(dev, "gemm_bf16" if a.dtype == torch.bfloat16 else "gemm_f32", 2.0 * m * n * k,
+                 _nbytes(a, w, out, residual)):
         if a.dtype == torch.bfloat16:
             _lib.check(_lib.lib().istvt_gemm_fwd(_ptr(a), k, _ptr(w), k, _ptr(out), n, _dt(out), m, n, k, _ptr(bias),
                                                  _ptr(residual), n, act, st), "istvt_gemm_fwd")
@@ -153,7 +196,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int = ACT
     if tuple(w.shape) != (cout, 3, 3, cin) or w.dtype != x.dtype:
         raise ValueError("conv3x3: weight must be [cout, 3, 3, cin] in the activation dtype")
     y = torch.empty(n, h - 2, wd - 2, cout, dtype=x.dtype, device=dev)
-    with _on(dev):
+    with _launch(dev, "conv3x3", 2.0 * y.numel() * 9 * cin, _nbytes(x, w, y)):
         _lib.check(_lib.lib().istvt_conv3x3_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), _dt(x), n, h, wd, cin, cout,
                                                 act, _stream(dev)), "istvt_conv3x3_fwd")
     return y
@@ -168,7 +211,7 @@ def conv_stem(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out_dtype: t
     cout = w.shape[0]
     ho, wo = (h - 3) // 2 + 1, (wd - 3) // 2 + 1
     y = torch.empty(n, ho, wo, cout, dtype=out_dtype, device=dev)
-    with _on(dev):
+    with _launch(dev, "conv_stem", 2.0 * y.numel() * 27, _nbytes(x, y)):
         _lib.check(_lib.lib().istvt_conv_stem_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), _dt(y), n, h, wd, cout,
                                                   _stream(dev)), "istvt_conv_stem_fwd")
     return y
@@ -181,7 +224,7 @@ def dwconv3x3(x: torch.Tensor, w: torch.Tensor, relu_in: bool) -> torch.Tensor:
     if tuple(w.shape) != (3, 3, c) or w.dtype != torch.float32:
         raise ValueError("dwconv3x3: weight must be fp32 [3, 3, c]")
     y = torch.empty_like(x)
-    with _on(dev):
+    with _launch(dev, "dwconv3x3", 2.0 * y.numel() * 9, _nbytes(x, y)):
         _lib.check(_lib.lib().istvt_dwconv3x3_fwd(_ptr(x), _ptr(w), _ptr(y), _dt(x), n, h, wd, c, int(relu_in),
                                                   _stream(dev)), "istvt_dwconv3x3_fwd")
     return y
@@ -191,7 +234,7 @@ def subsample2(x: torch.Tensor) -> torch.Tensor:
     dev = _chk(x)
     n, h, wd, c = x.shape
     y = torch.empty(n, (h - 1) // 2 + 1, (wd - 1) // 2 + 1, c, dtype=x.dtype, device=dev)
-    with _on(dev):
+    with _launch(dev, "subsample2", 0.0, 2 * _nbytes(y)):
         _lib.check(_lib.lib().istvt_subsample2_fwd(_ptr(x), _ptr(y), _dt(x), n, h, wd, c, _stream(dev)),
                    "istvt_subsample2_fwd")
     return y
@@ -204,7 +247,7 @@ def pool_add(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
     if skip.numel() != n * ho * wo * c or skip.dtype != x.dtype:
         raise ValueError("pool_add: skip must be [n, ho, wo, c] in the activation dtype")
     y = torch.empty(n, ho, wo, c, dtype=x.dtype, device=dev)
-    with _on(dev):
+    with _launch(dev, "pool_add", 0.0, _nbytes(x, skip, y)):
         _lib.check(_lib.lib().istvt_pool_add_fwd(_ptr(x), _ptr(skip), _ptr(y), _dt(x), n, h, wd, c, _stream(dev)),
                    "istvt_pool_add_fwd")
     return y
@@ -220,7 +263,7 @@ def pool_add_tokens(x: torch.Tensor, skip: torch.Tensor, pos_emb: torch.Tensor, 
         raise ValueError("pool_add_tokens: bad batch/frames or dtypes")
     if tokens.numel() != batch * (t + 1) * (ho * wo + 1) * c or pos_emb.numel() != t * (ho * wo + 1) * c:
         raise ValueError("pool_add_tokens: token / pos_emb buffers have the wrong size")
-    with _on(dev):
+    with _launch(dev, "pool_add", 0.0, _nbytes(x, skip) + 2 * skip.numel() * 4):
         _lib.check(_lib.lib().istvt_pool_add_tokens_fwd(_ptr(x), _ptr(skip), _ptr(pos_emb), _ptr(tokens), _dt(x),
                                                         batch, t, h, wd, c, _stream(dev)),
                    "istvt_pool_add_tokens_fwd")
@@ -230,7 +273,7 @@ def token_fill(tokens: torch.Tensor, space_token: torch.Tensor, temporal_token: 
                pos_emb: torch.Tensor) -> None:
     dev = _chk(tokens, space_token, temporal_token, pos_emb)
     b, f, p, d = tokens.shape
-    with _on(dev):
+    with _launch(dev, "token_fill", 0.0, b * (p + f - 1) * d * 4):
         _lib.check(_lib.lib().istvt_token_fill_fwd(_ptr(tokens), _ptr(space_token), _ptr(temporal_token),
                                                    _ptr(pos_emb), b, f - 1, p, d, _stream(dev)),
                    "istvt_token_fill_fwd")
@@ -245,7 +288,7 @@ def attn_temporal(qk: torch.Tensor, v: torch.Tensor, batch: int, frames: int, to
         raise ValueError("attn_temporal: qk must be [rows, 2*heads*64] and v [rows, heads*64]")
     out = torch.empty(rows, inner, dtype=qk.dtype, device=dev)
     probs = torch.empty(batch, heads, tokens, frames, frames, dtype=torch.float32, device=dev) if want_probs else None
-    with _on(dev):
+    with _launch(dev, "attn_temporal", 4.0 * batch * tokens * heads * frames * frames * 64, _nbytes(qk, v, out, probs)):
         _lib.check(_lib.lib().istvt_attn_temporal_fwd(_ptr(qk), _ptr(v), _ptr(out), _ptr(probs), _dt(qk), batch,
                                                       frames, tokens, heads, scale, _stream(dev)),
                    "istvt_attn_temporal_fwd")
@@ -261,7 +304,7 @@ def attn_spatial(qkv: torch.Tensor, batch_frames: int, tokens: int, heads: int, 
         raise ValueError("attn_spatial: qkv must be [rows, 3*heads*64]")
     out = torch.empty(rows, inner, dtype=qkv.dtype, device=dev)
     probs = torch.empty(batch_frames, heads, tokens, tokens, dtype=torch.float32, device=dev) if want_probs else None
-    with _on(dev):
+    with _launch(dev, "attn_spatial", 4.0 * batch_frames * heads * tokens * tokens * 64, _nbytes(qkv, out, probs)):
         _lib.check(_lib.lib().istvt_attn_spatial_fwd(_ptr(qkv), _ptr(out), _ptr(probs), _dt(qkv), batch_frames,
                                                      tokens, heads, scale, _stream(dev)), "istvt_attn_spatial_fwd")
     return out, probs
@@ -272,7 +315,7 @@ def head(tokens: torch.Tensor, norm_g, norm_b, head_g, head_b, head_w, head_bias
     dev = _chk(tokens, norm_g, norm_b, head_g, head_b, head_w, head_bias)
     b, f, p, d = tokens.shape
     logits = torch.empty(b, 1, dtype=torch.float32, device=dev)
-    with _on(dev):
+    with _launch(dev, "head", 0.0, b * d * 4):
         _lib.check(_lib.lib().istvt_head_fwd(_ptr(tokens), f * p, _ptr(norm_g), _ptr(norm_b), _ptr(head_g),
                                              _ptr(head_b), _ptr(head_w), _ptr(head_bias), _ptr(logits), b, d, eps,
                                              _stream(dev)), "istvt_head_fwd")

@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""ISTVT forward throughput on B200 (BASELINE.json metric: clips/sec forward; config C2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one forward of the hot path (Xception entry flow + 12 spatial-temporal blocks + head) over one
+batch of 64 synthetic clips [64, 6, 3, 300, 300] per GPU, bf16 mode, random-init weights (seed 0).
+Clips shard across GPUs with no collective on the data path (weak scaling: 64 clips per GPU);
+torch.distributed (NCCL) is used for the barrier and the max-over-ranks of the device-timed duration only.
+
+One JSON line on rank 0:
+  value        whole-job clips/s with the input batch already resident in HBM (CUDA events, max over ranks)
+  e2e          the same metric through the public API (`model(x)`) from PINNED HOST clips, H2D copy of the
+               batch and D2H read of the logits inside the timed region, every step
+  roofline     the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs of its launches / their summed
+               CUDA-event durations, measured live in the timed region (ops.LaunchRecorder), against the
+               measured bf16 peak in MEASURED_PEAKS.json (or the profiling guide's fallback)
+  cpu_baseline the CPU oracle port of the reference forward (oracle/istvt_oracle.py, fp32, all host threads)
+               on a bounded sample of the same workload — rank 0, N=1 only
+  kernels      per-kernel-family share of the step (launches, ms, TFLOP/s or GB/s) — explains `value`
+
+`--impl reference` times the reference's own algorithm on the host cores (the oracle port: the reference
+is Python and /root/reference does not exist on the GPU box) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "2023-tifs-istvt_b200"
+
+METRIC = "clips/sec forward"
+UNIT = "clips/s"
+GFLOP_PER_CLIP_T6 = 494.5            # 12 x 38.515 + 6 x 5.386
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            out = dict(FALLBACK_PEAKS)
+            for k in out:
+                if k in d and d[k]:
+                    out[k] = float(d[k])
+            return out, "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return dict(FALLBACK_PEAKS), "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w": round(sum(pw) / len(pw), 1),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_clips_per_s(batch: int, frames: int, budget_s: float, min_iters: int = 2):
+    """Reference algorithm on the host cores (oracle port), fp32, eval, no_grad (SURVEY.md §8d CPU baseline)."""
+    import torch
+    from oracle import istvt_oracle as O
+    pkg = importlib.import_module(PKG)
+    torch.manual_seed(0)
+    model = pkg.XceptionVidTr(num_frames=frames).eval()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    x = torch.rand(batch, frames, 3, 300, 300, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        O.forward(sd, x)  # warm-up
+        t0 = time.perf_counter()
+        iters = 0
+        while iters < min_iters or (time.perf_counter() - t0) < budget_s:
+            O.forward(sd, x)
+            iters += 1
+            if time.perf_counter() - t0 > 3 * budget_s:
+                break
+        dt = time.perf_counter() - t0
+    return batch * iters / dt, iters, torch.get_num_threads()
+
+
+def run_reference(args) -> int:
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import istvt_oracle as O
+    pkg = importlib.import_module(PKG)
+    torch.manual_seed(0)
+    model = pkg.XceptionVidTr(num_frames=args.frames).eval()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    sample = args.ref_clips
+    x = torch.rand(sample, args.frames, 3, 300, 300, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.forward(sd, x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(sd, x)
+        dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    threads = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, note=f"CPU arm: each step is a bounded sample of {sample} clip(s) of the workload"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} clip(s) x {args.frames} frames x 300x300 per step, {args.steps} steps, "
+                                   f"fp32, torch CPU ops, {threads} threads of {os.cpu_count()} logical CPUs"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, note: str = "") -> dict:
+    cfg = {
+        "workload": f"C2: ISTVT bf16 inference, {args.batch} clips x {args.frames} frames x 300x300 per GPU "
+                    "(Xception entry flow + 12 spatial-temporal blocks + head), random-init weights seed 0",
+        "batch_per_gpu": args.batch, "frames": args.frames, "image": 300, "precision": args.precision,
+        "sharding": "clips sharded across GPUs, no data-path collective",
+        "l2_policy": "no flush needed: the per-step input (%.0f MB) and every activation tensor exceed the 126 MB L2"
+                     % (args.batch * args.frames * 3 * 300 * 300 * 4 / 1e6),
+    }
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+def run_ours(args) -> int:
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference "
+                         "for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pkg = importlib.import_module(PKG)
+    ops = pkg.ops
+    torch.manual_seed(0)
+    model = pkg.XceptionVidTr(num_frames=args.frames, precision=args.precision).eval().to(dev)
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.rand(args.batch, args.frames, 3, 300, 300, generator=gen).pin_memory()
+    x_dev = x_host.to(dev)
+    logits_host = torch.empty(args.batch, 1).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model(x_dev)
+        barrier()
+
+        # ---------------- device-resident timed region ----------------
+        sampler = ClockSampler(local) if rank == 0 else None
+        time.sleep(0.25)
+        rec = ops.LaunchRecorder()
+        ops.set_recorder(rec)
+        n0 = pkg._lib.launch_count()
+        barrier()
+        t_wall0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            logits = model(x_dev)
+        e1.record()
+        barrier()
+        t_wall1 = time.time()
+        launches = pkg._lib.launch_count() - n0
+        ops.set_recorder(None)
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
+
+        # ---------------- end-to-end region: pinned host clips -> logits on the host ----------------
+        for _ in range(2):
+            logits_host.copy_(model(x_host.to(dev, non_blocking=True)))
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            xd = x_host.to(dev, non_blocking=True)          # H2D of this step's clips
+            logits_host.copy_(model(xd))                     # public API call + D2H of the step's result (syncs)
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+
+    if rank == 0:
+        total_clips = args.batch * world * args.steps
+        value = total_clips / (ms / 1e3)
+        e2e = total_clips / (ms_e2e / 1e3)
+        peaks, peak_src = load_peaks()
+        fam = rec.summary()
+        kernels = {}
+        for name, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+            k = {"launches": d["launches"], "ms_per_step": d["ms"] / args.steps, "share": d["ms"] / ms}
+            if d["flops"] > 0:
+                k["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            k["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            kernels[name] = k
+        g = fam.get("gemm_bf16")
+        roofline = None
+        if g is not None and g["ms"] > 0:
+            achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            roofline = {"kernel": "gemm_tcgen05_kernel (istvt_gemm_fwd)", "bound": "tensor", "achieved": achieved,
+                        "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                        "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
+                        "launches_per_step": g["launches"] / args.steps,
+                        "flops_per_step": g["flops"] / args.steps,
+                        "share_of_step": g["ms"] / ms}
+        flops_step = GFLOP_PER_CLIP_T6 * 1e9 * args.batch if args.frames == 6 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size() * world,
+                    "d2h_bytes_per_step": logits_host.numel() * logits_host.element_size() * world},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        }
+        if flops_step is not None:
+            line["whole_step"] = {"algorithmic_tflop_per_step": flops_step / 1e12,
+                                  "achieved_tflops_per_gpu": flops_step / (ms / args.steps * 1e-3) / 1e12,
+                                  "frac_of_bf16_sustained": flops_step / (ms / args.steps * 1e-3) / 1e12
+                                                            / peaks["bf16_tflops_sustained"]}
+        if world == 1 and not args.no_cpu_baseline:
+            v, iters, threads = cpu_oracle_clips_per_s(1, args.frames, args.cpu_budget)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{iters} forwards of 1 clip x {args.frames} frames x 300x300 "
+                                              f"(oracle/istvt_oracle.py, fp32, {threads} torch threads of "
+                                              f"{os.cpu_count()} logical CPUs)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU")
+    ap.add_argument("--frames", type=int, default=6)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--ref-clips", type=int, default=2, help="--impl reference: clips per CPU step")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
