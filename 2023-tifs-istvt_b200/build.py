@@ -22,6 +22,7 @@ SOURCES = [
     "common.cu",
     "layernorm.cu",
     "gemm_tcgen05.cu",
+    "gemm_tcgen05_2cta.cu",
     "gemm_f32.cu",
     "attn_temporal.cu",
     "attn_spatial.cu",

@@ -1,10 +1,11 @@
 // HBM-bound kernels of the Xception entry flow, NHWC activations (channel innermost, 16-byte vectors):
 //   conv_stem      3x3 s2 conv 3->32 on the NCHW fp32 clip + folded BN + ReLU            (xception.py:194-196)
-//   dwconv3x3      depthwise 3x3 p1, ReLU-on-load, sliding register window down a column (xception.py:43,47)
+//   dwconv3x3      depthwise 3x3 p1, ReLU-on-load, TMA halo tiles + rolling accumulators      (xception.py:43,47)
 //   subsample2     pixel gather of the stride-2 1x1 skip convolution                     (xception.py:57,94)
 //   pool_add       MaxPool2d(3,2,1) + skip add                                           (xception.py:87-88,100)
 //   pool_add_tokens  same, writing fp32 tokens + positional embedding                    (+ vivit.py:133-138)
 #include "common.cuh"
+#include "ptx.cuh"
 #include "simt_util.cuh"
 
 namespace istvt {
@@ -89,86 +90,130 @@ conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ wt, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// depthwise 3x3 pad 1.  Thread = (8 channels, one column x, a strip of DW_ROWS output rows); the 3x3
-// window slides down the strip so each new output row costs 3 vector loads.  Threads are ordered
-// channel-group fastest then x, so a warp reads contiguous NHWC memory.
+// depthwise 3x3 pad 1, HBM-bound.  Persistent CTAs walk (image, channel-group, tile) work items; the
+// (TH+2) x (TW+2) x 64-channel halo tile of each item is fetched by ONE TMA load of a 4-D tensor map
+// (c, x, y, n) — the pad-1 border and ragged edges are the TMA's out-of-bounds zero fill — into a
+// double-buffered smem slot, so the load of tile i+1 overlaps the arithmetic of tile i.
+// Thread = (4 channels, one tile column): it walks down the column, reads 3 smem vectors per input
+// row and keeps three rolling output-row accumulators in registers (each input row feeds output rows
+// r-2, r-1, r with ky = 2, 1, 0), so every smem element is read 3x and every output written once.
 // ------------------------------------------------------------------------------------------
-constexpr int DW_ROWS = 8;
+constexpr int DW_TW = 16;          // tile width  (outputs)
+constexpr int DW_CG = 64;          // channels per work item
+constexpr int DW_THREADS = 256;    // 16 channel quads x 16 columns
+template <typename T> struct DwCfg;
+template <> struct DwCfg<__nv_bfloat16> { static constexpr int TH = 16; };
+template <> struct DwCfg<float> { static constexpr int TH = 8; };
+
+__device__ __forceinline__ void lds4(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+__device__ __forceinline__ void lds4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
 
 template <typename T>
-__global__ void __launch_bounds__(256)
-dwconv3x3_kernel(const T* __restrict__ x, const float* __restrict__ wt, T* __restrict__ y, int n, int h, int w,
-                 int c, int relu_in) {
-    const int c8 = c >> 3;
-    const int strips = (h + DW_ROWS - 1) / DW_ROWS;
-    const int64_t total = static_cast<int64_t>(n) * strips * w * c8;
-    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int cg = static_cast<int>(idx % c8);
-    int64_t t = idx / c8;
-    const int xo = static_cast<int>(t % w);
-    t /= w;
-    const int strip = static_cast<int>(t % strips);
-    const int img = static_cast<int>(t / strips);
-    const int ch = cg * 8;
-    const int y0 = strip * DW_ROWS;
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ wt, T* __restrict__ y,
+                     int n, int h, int w, int c, int relu_in) {
+    constexpr int TH = DwCfg<T>::TH;
+    constexpr int IN_H = TH + 2, IN_W = DW_TW + 2;
+    constexpr uint32_t TILE_BYTES = IN_H * IN_W * DW_CG * sizeof(T);
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem) + 127) & ~uintptr_t(127));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * TILE_BYTES);
 
-    float wk[9][8];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(wt + k * c + ch));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(wt + k * c + ch + 4));
-        wk[k][0] = a.x; wk[k][1] = a.y; wk[k][2] = a.z; wk[k][3] = a.w;
-        wk[k][4] = b.x; wk[k][5] = b.y; wk[k][6] = b.z; wk[k][7] = b.w;
+    const int tiles_x = (w + DW_TW - 1) / DW_TW;
+    const int tiles_y = (h + TH - 1) / TH;
+    const int cgroups = (c + DW_CG - 1) / DW_CG;
+    const int64_t total = static_cast<int64_t>(n) * cgroups * tiles_y * tiles_x;
+
+    const int tid = threadIdx.x;
+    const int cq = tid & 15;          // channel quad inside the 64-channel group
+    const int col = tid >> 4;         // tile column
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_x);
     }
+    __syncthreads();
 
-    const T* xin = x + static_cast<int64_t>(img) * h * w * c + ch;
-    T* yout = y + static_cast<int64_t>(img) * h * w * c + ch;
-    const bool left = xo > 0, right = xo + 1 < w;
+    auto issue = [&](int64_t item, int buf) {
+        const int tx = static_cast<int>(item % tiles_x);
+        int64_t r = item / tiles_x;
+        const int ty = static_cast<int>(r % tiles_y);
+        r /= tiles_y;
+        const int cg = static_cast<int>(r % cgroups);
+        const int img = static_cast<int>(r / cgroups);
+        mbar_arrive_expect_tx(&bars[buf], TILE_BYTES);
+        tma_load_4d(base + buf * TILE_BYTES, &tm_x, &bars[buf], cg * DW_CG, tx * DW_TW - 1, ty * TH - 1, img);
+    };
 
-    // rows[r][dx][8]: r = 0 -> row y-1, 1 -> row y, 2 -> row y+1
-    float win[3][3][8];
-    auto load_row = [&](int yy, float (&dst)[3][8]) {
-        const bool row_ok = (yy >= 0) && (yy < h);
+    int64_t item = blockIdx.x;
+    if (tid == 0 && item < total) issue(item, 0);
+    int buf = 0;
+    uint32_t phase[2] = {0, 0};
+    for (; item < total; item += gridDim.x) {
+        const int64_t next = item + gridDim.x;
+        if (tid == 0 && next < total) issue(next, buf ^ 1);   // slot buf^1 was released by the barrier below
+
+        const int tx = static_cast<int>(item % tiles_x);
+        int64_t r = item / tiles_x;
+        const int ty = static_cast<int>(r % tiles_y);
+        r /= tiles_y;
+        const int cg = static_cast<int>(r % cgroups);
+        const int img = static_cast<int>(r / cgroups);
+        const int ch = cg * DW_CG + cq * 4;
+        const bool ch_ok = ch < c;
+        const int ox = tx * DW_TW + col;
+        const int oy0 = ty * TH;
+
+        float wk[9][4];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const bool ok = row_ok && (dx == 1 || (dx == 0 ? left : right));
-            if (ok) {
-                load8(xin + (static_cast<int64_t>(yy) * w + (xo + dx - 1)) * c, dst[dx]);
+        for (int k = 0; k < 9; ++k) {
+            const float4 t = ch_ok ? __ldg(reinterpret_cast<const float4*>(wt + k * c + ch)) : make_float4(0, 0, 0, 0);
+            wk[k][0] = t.x; wk[k][1] = t.y; wk[k][2] = t.z; wk[k][3] = t.w;
+        }
+
+        mbar_wait(&bars[buf], phase[buf]);
+        phase[buf] ^= 1;
+
+        const T* tile = reinterpret_cast<const T*>(base + buf * TILE_BYTES) + col * DW_CG + cq * 4;
+        T* yout = y + ((static_cast<int64_t>(img) * h + oy0) * w + ox) * c + ch;
+        const bool st_ok = ch_ok && ox < w;
+        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int rr = 0; rr < IN_H; ++rr) {
+            float v[3][4];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                lds4(tile + (rr * IN_W + kx) * DW_CG, v[kx]);
                 if (relu_in) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) dst[dx][e] = fmaxf(dst[dx][e], 0.0f);
+                    for (int e = 0; e < 4; ++e) v[kx][e] = fmaxf(v[kx][e], 0.0f);
                 }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) dst[dx][e] = 0.0f;
             }
+            float a2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a0[e] = fmaf(v[0][e], wk[6][e], a0[e]); a0[e] = fmaf(v[1][e], wk[7][e], a0[e]); a0[e] = fmaf(v[2][e], wk[8][e], a0[e]);
+                a1[e] = fmaf(v[0][e], wk[3][e], a1[e]); a1[e] = fmaf(v[1][e], wk[4][e], a1[e]); a1[e] = fmaf(v[2][e], wk[5][e], a1[e]);
+                a2[e] = v[0][e] * wk[0][e]; a2[e] = fmaf(v[1][e], wk[1][e], a2[e]); a2[e] = fmaf(v[2][e], wk[2][e], a2[e]);
+            }
+            if (rr >= 2) {
+                const int orow = rr - 2;
+                if (st_ok && oy0 + orow < h) store4(yout + static_cast<int64_t>(orow) * w * c, a0);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { a0[e] = a1[e]; a1[e] = a2[e]; }
         }
-    };
-    load_row(y0 - 1, win[0]);
-    load_row(y0, win[1]);
-#pragma unroll
-    for (int r = 0; r < DW_ROWS; ++r) {
-        const int yy = y0 + r;
-        if (yy >= h) break;
-        load_row(yy + 1, win[2]);
-        float acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(win[ky][kx][e], wk[ky * 3 + kx][e], acc[e]);
-        store8(yout + (static_cast<int64_t>(yy) * w + xo) * c, acc);
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                win[0][dx][e] = win[1][dx][e];
-                win[1][dx][e] = win[2][dx][e];
-            }
+        __syncthreads();   // everyone is done reading slot `buf`: it may be refilled next iteration
+        buf ^= 1;
     }
 }
 
@@ -277,23 +322,42 @@ extern "C" int istvt_conv_stem_fwd(const float* x, const float* wt, const float*
     return launch_status();
 }
 
+template <typename T>
+static int launch_dwconv(const void* x, const float* wt, void* y, int n, int h, int w, int c, int relu_in,
+                         cudaStream_t st) {
+    constexpr int TH = DwCfg<T>::TH;
+    constexpr int IN_H = TH + 2, IN_W = DW_TW + 2;
+    CUtensorMap tm;
+    const uint64_t es = sizeof(T);
+    const uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(w), static_cast<uint64_t>(h),
+                              static_cast<uint64_t>(n)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(c) * es, static_cast<uint64_t>(w) * c * es,
+                                 static_cast<uint64_t>(h) * w * c * es};
+    const uint32_t box[4] = {DW_CG, IN_W, IN_H, 1};
+    int rc = encode_tmap(&tm, x, sizeof(T) == 2 ? ISTVT_BF16 : ISTVT_F32, 4, dims, strides, box, 0);
+    if (rc != ISTVT_OK) return rc;
+    const int smem = 2 * IN_H * IN_W * DW_CG * static_cast<int>(sizeof(T)) + 128 + 64;
+    auto kern = dwconv3x3_tma_kernel<T>;
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t total = static_cast<int64_t>(n) * ((c + DW_CG - 1) / DW_CG) * ((h + TH - 1) / TH) *
+                          ((w + DW_TW - 1) / DW_TW);
+    int64_t grid = static_cast<int64_t>(sm_count()) * 2;
+    if (grid > total) grid = total;
+    kern<<<static_cast<unsigned>(grid), DW_THREADS, smem, st>>>(tm, wt, static_cast<T*>(y), n, h, w, c, relu_in);
+    count_launch();
+    return launch_status();
+}
+
 extern "C" int istvt_dwconv3x3_fwd(const void* x, const float* wt, void* y, int dtype, int n, int h, int w, int c,
                                    int relu_in, istvt_stream_t stream) {
     ISTVT_REQUIRE(x && wt && y);
     ISTVT_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0);
-    const int strips = (h + DW_ROWS - 1) / DW_ROWS;
-    const int64_t total = static_cast<int64_t>(n) * strips * w * (c / 8);
+    ISTVT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(wt) & 15) == 0);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (dtype == ISTVT_BF16)
-        dwconv3x3_kernel<__nv_bfloat16><<<blocks_for(total, 256), 256, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(x), wt, static_cast<__nv_bfloat16*>(y), n, h, w, c, relu_in);
-    else if (dtype == ISTVT_F32)
-        dwconv3x3_kernel<float><<<blocks_for(total, 256), 256, 0, st>>>(static_cast<const float*>(x), wt,
-                                                                         static_cast<float*>(y), n, h, w, c, relu_in);
-    else
-        return ISTVT_ERR_INVALID_ARG;
-    count_launch();
-    return launch_status();
+    if (dtype == ISTVT_BF16) return launch_dwconv<__nv_bfloat16>(x, wt, y, n, h, w, c, relu_in, st);
+    if (dtype == ISTVT_F32) return launch_dwconv<float>(x, wt, y, n, h, w, c, relu_in, st);
+    return ISTVT_ERR_INVALID_ARG;
 }
 
 extern "C" int istvt_subsample2_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c,

@@ -1,0 +1,181 @@
+// Shared pieces of the two tcgen05 GEMM kernels (gemm_tcgen05.cu: 1-CTA tiles + implicit-GEMM conv mode;
+// gemm_tcgen05_2cta.cu: CTA-pair tiles): problem descriptor and the fused epilogue
+//   C = act(acc + bias) + residual   ->  bf16 / fp32, 16-byte stores.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace istvt {
+
+constexpr int GEMM_BLOCK_M = 128;   // rows per CTA (= TMEM lanes)
+constexpr int UMMA_K = 16;          // bf16
+
+struct GemmParams {
+    int64_t M;        // GEMM rows (conv mode: n_img * h_in * w_in, the padded grid)
+    int N, K;         // K = per-tap K in conv mode
+    int taps;         // 1 (plain GEMM) or 9 (3x3 conv)
+    int conv_w_in;    // conv mode: input width  (row shift of tap = ky * conv_w_in + kx)
+    int conv_h_in;    // conv mode: input height
+    void* C;
+    int64_t ldc;
+    const float* bias;
+    const float* residual;
+    int64_t ldr;
+    int act;
+    int c_f32;
+};
+
+// ------------------------------------------------------------------------------------------
+// Fused epilogue, coalesced.  tcgen05.ld hands every thread ONE output row (TMEM lane) x 32 columns; storing
+// that directly makes each warp-wide 16-byte access touch 32 different 128-byte lines (profiles/r1b: the
+// L1->L2 request path was 73 % busy with half-filled sectors, and the fp32 read-modify-write of the residual
+// stream ran at 255 TFLOP/s).  The smem data pipe (128 B/clk) is shared by the tensor core's operand reads,
+// the TMA fills and every LSU wavefront, so the epilogue is written to minimise wavefronts:
+// each epilogue warp owns 32 rows x 64 columns of the tile and transposes them through a private 4 KB slab
+// (16-byte chunks XOR-swizzled by row, conflict-free both ways) so that afterwards 8 lanes cover 128
+// contiguous bytes of one row:
+//   bf16 output (no residual): bias + activation on the row-owner side, PACKED bf16 staged (64 B less per row),
+//                              then one 16-byte store per lane = 4 full lines per warp instruction;
+//   fp32 output (+ residual) : raw accumulators staged 32 columns at a time; bias / residual / store on full lines.
+// ------------------------------------------------------------------------------------------
+constexpr int EPI_SLAB_BYTES = 32 * 128;   // per epilogue warp
+constexpr int EPI_COLS = 64;               // accumulator columns per epilogue warp
+
+// Output rows handled by this lane in the transposed phase: row (i*4 + lane/8) of the warp's 32, i = 0..7.
+// `drow_lane` = destination row of the accumulator row this lane owns (TMEM lane), or -1 if it is not stored.
+__device__ __forceinline__ void epilogue_rows(int drow_lane, int lane, int (&drow_t)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) drow_t[i] = __shfl_sync(0xffffffffu, drow_lane, i * 4 + (lane >> 3));
+}
+
+// Residual GEMMs (s_out, ff2) read-modify-write the fp32 token stream; those loads were the epilogue's critical
+// path (DRAM latency, 4 x 16 B in flight per lane).  The addresses do not depend on the accumulator, so each
+// epilogue warp pulls its rows' residual lines into L2 before it waits for the MMAs of the tile to finish.
+__device__ __forceinline__ void epilogue_prefetch_residual(const GemmParams& p, int drow_lane, int n_first, int ncols) {
+    if (p.residual == nullptr || drow_lane < 0) return;
+    const float* row = p.residual + static_cast<int64_t>(drow_lane) * p.ldr;
+    for (int n = n_first; n < n_first + ncols && n < p.N; n += 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + n));
+}
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+    if (act == ISTVT_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ISTVT_ACT_GELU) return gelu_erf_fast(v);
+    return v;
+}
+
+// Warp-collective epilogue of 32 rows x 64 columns [n0, n0+64) read from TMEM at `taddr` (lane quadrant and
+// column already applied).  `after_tmem_reads()` is invoked once all TMEM reads of the call have completed.
+// PLAIN_BF16 = bf16 output without residual (compile-time: keeps each kernel instantiation small — the first
+// version inlined both paths twice and the 147 KB of SASS missed in the instruction cache).
+// `slab` is the warp's 4 KB staging area as a shared-space address.
+template <bool PLAIN_BF16, typename F>
+__device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t taddr, uint32_t slab,
+                                                 const int (&drow_t)[8], int n0, int lane, F after_tmem_reads) {
+    const int cchunk = lane & 7;
+    const int sw = lane & 7;
+    if (n0 >= p.N) {   // whole column group is past the matrix edge (ragged last N tile): nothing to read or store
+        after_tmem_reads();
+        return;
+    }
+    if constexpr (PLAIN_BF16) {
+        // ---------------- bf16 output: math first, packed staging ----------------
+        const uint32_t wrow = slab + lane * 128;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int nb = n0 + hh * 32;
+            uint32_t r[32];
+            if (nb < p.N) {   // warp-uniform
+                tmem_ld_32x32b_x32(taddr + hh * 32, r);
+                tmem_ld_wait();
+            }
+            if (hh == 1) after_tmem_reads();
+            if (nb >= p.N) break;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {     // 8 columns -> one 16-byte chunk
+                const int n = nb + g * 8;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+                if (p.bias != nullptr && n < p.N) {
+                    const float4 b0 = ldg_nc_f4_ordered(p.bias + n);
+                    const float4 b1 = ldg_nc_f4_ordered(p.bias + n + 4);
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = epi_act(v[j], p.act);
+                const int c = hh * 4 + g;
+                sts_u4(wrow + ((c ^ sw) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                       pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            }
+        }
+        __syncwarp();
+        const int n = n0 + cchunk * 8;
+        if (n < p.N) {
+            __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C) + n;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = i * 4 + (lane >> 3);
+                const uint4 v = lds_u4(slab + row * 128 + ((cchunk ^ (row & 7)) << 4));
+                if (drow_t[i] >= 0) *reinterpret_cast<uint4*>(cbase + static_cast<int64_t>(drow_t[i]) * p.ldc) = v;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- fp32 output and/or residual: raw staging, 32 columns per pass ----------------
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int nb = n0 + hh * 32;
+            uint32_t r[32];
+            if (nb < p.N) {
+                tmem_ld_32x32b_x32(taddr + hh * 32, r);
+                tmem_ld_wait();
+            }
+            if (hh == 1) after_tmem_reads();
+            if (nb >= p.N) break;
+            const uint32_t wrow = slab + lane * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sts_u4(wrow + ((c ^ sw) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+            __syncwarp();
+            const int n = nb + cchunk * 4;
+            const bool n_ok = n < p.N;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n_ok && p.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+            for (int i0 = 0; i0 < 8; i0 += 4) {
+                float4 res[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.residual != nullptr && n_ok && drow_t[i0 + i] >= 0)
+                        res[i] = *reinterpret_cast<const float4*>(p.residual + static_cast<int64_t>(drow_t[i0 + i]) * p.ldr + n);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = (i0 + i) * 4 + (lane >> 3);
+                    const uint4 u = lds_u4(slab + row * 128 + ((cchunk ^ (row & 7)) << 4));
+                    const int64_t drow = drow_t[i0 + i];
+                    if (!n_ok || drow < 0) continue;
+                    float4 v;
+                    v.x = epi_act(__uint_as_float(u.x) + bias4.x, p.act) + res[i].x;
+                    v.y = epi_act(__uint_as_float(u.y) + bias4.y, p.act) + res[i].y;
+                    v.z = epi_act(__uint_as_float(u.z) + bias4.z, p.act) + res[i].z;
+                    v.w = epi_act(__uint_as_float(u.w) + bias4.w, p.act) + res[i].w;
+                    if (p.c_f32) {
+                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + drow * p.ldc + n) = v;
+                    } else {
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + drow * p.ldc + n) =
+                            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                    }
+                }
+            }
+            __syncwarp();   // slab is rewritten by the next pass
+        }
+    }
+}
+
+// host: launch the CTA-pair kernel (gemm_tcgen05_2cta.cu) for a plain GEMM with N >= 256
+int launch_gemm_2cta(const void* a, int64_t lda, const void* w, int64_t ldw, const GemmParams& p, cudaStream_t stream);
+
+}  // namespace istvt

@@ -5,7 +5,7 @@
 //   C  : bf16 or fp32 [M, N]
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (single lane issues
-// tcgen05.mma), warp 2 = TMEM allocator, warps 4..11 = epilogue (TMEM -> registers -> global).
+// tcgen05.mma), warp 2 = TMEM allocator, warps 4.. = epilogue (TMEM -> registers -> swizzled smem transpose -> coalesced global; 32 rows x 64 columns per warp).
 // Three pipelines: smem ring (full/empty mbarriers, TMA <-> MMA), TMEM double buffer
 // (tmem_full/tmem_empty, MMA <-> epilogue), and the static tile schedule (tile = blockIdx.x + i*grid),
 // n-fastest so that the CTAs in flight share A rows through L2 and the small W stays L2-resident.
@@ -14,47 +14,29 @@
 // mode" every k-block belongs to a filter tap (ky, kx) and the A tile of that tap is the same 2-D box
 // of the NHWC activation matrix shifted down by ky*W_in + kx pixel rows (outputs are computed on the
 // input's W_in-wide grid; the epilogue drops the two junk columns/rows and compacts the row index).
-#include "common.cuh"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace istvt {
 
-constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;  // 384
-constexpr int UMMA_K = 16;                                // bf16
-
-struct GemmParams {
-    int64_t M;        // GEMM rows (conv mode: n_img * h_in * w_in, the padded grid)
-    int N, K;         // K = per-tap K in conv mode
-    int taps;         // 1 (plain GEMM) or 9 (3x3 conv)
-    int conv_w_in;    // conv mode: input width  (row shift of tap = ky * conv_w_in + kx)
-    int conv_h_in;    // conv mode: input height
-    void* C;
-    int64_t ldc;
-    const float* bias;
-    const float* residual;
-    int64_t ldr;
-    int act;
-    int c_f32;
-};
 
 template <int BN, int BK>
 struct GemmCfg {
+    static constexpr int EPI_WARPS = 4 * (BN / EPI_COLS);   // lane quadrant x 64-column group
+    static constexpr int THREADS = 128 + EPI_WARPS * 32;
     static constexpr int A_BYTES = GEMM_BLOCK_M * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BUDGET = 200 * 1024;
+    static constexpr int BUDGET = 192 * 1024;
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr uint32_t SWZ = (BK == 64) ? SWZ_128B : SWZ_64B;
     static constexpr uint32_t SBO = 8 * BK * 2;  // bytes between 8-row groups of a K-major swizzled tile
 };
 
-template <int BN, int BK>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int BK, bool PLAIN_BF16>
+__global__ void __launch_bounds__(GemmCfg<BN, BK>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const GemmParams p) {
     using Cfg = GemmCfg<BN, BK>;
@@ -65,7 +47,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_WARPS * EPI_SLAB_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
@@ -92,7 +75,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
+            mbar_init(&tmem_empty[s], Cfg::EPI_WARPS);
         }
         fence_mbar_init();
     }
@@ -106,73 +89,79 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const uint32_t tmem_base = *tmem_holder;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int64_t m_blk = tile / n_tiles;
-            const int n_blk = static_cast<int>(tile % n_tiles);
-            const int64_t m0 = m_blk * GEMM_BLOCK_M;
-            const int n0 = n_blk * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (lane == 0) {
+        // ===================== TMA producer (one elected thread) =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int64_t m_blk = tile / n_tiles;
+                const int n_blk = static_cast<int>(tile % n_tiles);
+                const int64_t m0 = m_blk * GEMM_BLOCK_M;
+                const int n0 = n_blk * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_hot(&empty_bar[stage], phase ^ 1);
                     const int tap = kb / kb_per_tap;
                     const int kcol = (kb - tap * kb_per_tap) * BK;
                     const int64_t shift = (p.taps == 1) ? 0 : (int64_t)(tap / 3) * p.conv_w_in + (tap % 3);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tm_a, &full_bar[stage], kcol,
-                                static_cast<int>(m0 + shift));
+                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tm_a, &full_bar[stage], kcol, static_cast<int>(m0 + shift));
                     tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tm_b, &full_bar[stage], tap * p.K + kcol, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_blk = static_cast<int>(tile % n_tiles);
-            int n_eff = p.N - n_blk * BN;
-            n_eff = n_eff >= BN ? BN : ((n_eff + 15) & ~15);
-            const uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, static_cast<uint32_t>(n_eff), 0, 0);
-            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+        // ===================== MMA issuer (ONE elected thread; see gemm_tcgen05_2cta.cu for why it is this lean) =====
+        if (elect_one()) {
+            constexpr int KSTEPS = BK / UMMA_K;
+            const uint64_t desc_hi = make_smem_desc(0, 0, Cfg::SBO, Cfg::SWZ);
+            const uint32_t a_field0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4;
+            const uint32_t b_field0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
+            // MMAs of the last k-block of a tap (ragged K: the TMA zero-fills, whole zero k-steps are skipped)
+            const int last_steps = (p.K - (kb_per_tap - 1) * BK + UMMA_K - 1) / UMMA_K;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_blk = static_cast<int>(tile % n_tiles);
+                int n_eff = p.N - n_blk * BN;
+                n_eff = n_eff >= BN ? BN : ((n_eff + 15) & ~15);
+                const uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, static_cast<uint32_t>(n_eff), 0, 0);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
-                    const int kcol = (kb % kb_per_tap) * BK;
-                    int ksteps = (p.K - kcol + UMMA_K - 1) / UMMA_K;
-                    ksteps = ksteps > BK / UMMA_K ? BK / UMMA_K : ksteps;
-                    const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t a_desc = make_smem_desc(a_addr + k * UMMA_K * 2, 0, Cfg::SBO, Cfg::SWZ);
-                        const uint64_t b_desc = make_smem_desc(b_addr + k * UMMA_K * 2, 0, Cfg::SBO, Cfg::SWZ);
-                        umma_f16_ss(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                int kb_in_tap = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_hot(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = desc_hi | (a_field0 + stage * (Cfg::A_BYTES >> 4));
+                    const uint64_t b_desc = desc_hi | (b_field0 + stage * (Cfg::B_BYTES >> 4));
+                    const bool tap_end = (++kb_in_tap == kb_per_tap);
+                    if (tap_end) kb_in_tap = 0;
+                    if (!tap_end || last_steps == KSTEPS) {
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; ++k)
+                            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k != 0 || kb != 0) ? 1u : 0u);
+                    } else {
+                        for (int k = 0; k < last_steps; ++k)
+                            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (k != 0 || kb != 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);                    // smem slot free when these MMAs retire
+                    umma_commit(&empty_bar[stage]);                      // smem slot free when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int ew = warp - 4;
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;   // column half of the tile
-        constexpr int COLS_PER_WARP = BN / 2;
-        constexpr int CHUNKS = COLS_PER_WARP / 32;
-        static_assert(COLS_PER_WARP % 32 == 0, "BN must be a multiple of 64");
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+        const int col0 = (ew >> 2) * EPI_COLS;
+        const uint32_t slab = smem_u32(smem_epi + ew * EPI_SLAB_BYTES);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -192,68 +181,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 row_ok = row_ok && (y < ho) && (x < wo);
                 drow = (img * ho + y) * wo + x;
             }
+            int drow_t[8];
+            const int drow_lane = row_ok ? static_cast<int>(drow) : -1;
+            epilogue_rows(drow_lane, lane, drow_t);
+            if constexpr (!PLAIN_BF16) epilogue_prefetch_residual(p, drow_lane, n_blk * BN + col0, EPI_COLS);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-#pragma unroll
-            for (int ch = 0; ch < CHUNKS; ++ch) {
-                const int col0 = half * COLS_PER_WARP + ch * 32;
-                const int n_base = n_blk * BN + col0;
-                uint32_t r[32];
-                __syncwarp();        // reconverge after the row-predicated stores of the previous chunk
-                if (n_base < p.N) {  // warp-uniform
-                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, r);
-                    tmem_ld_wait();
-                }
-                if (ch == CHUNKS - 1) {
-                    // all TMEM reads of this warp for this accumulator are done
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                }
-                if (n_base >= p.N || !row_ok) continue;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {  // groups of 8 columns (N is a multiple of 8)
-                    const int n = n_base + g * 8;
-                    if (n >= p.N) break;
-                    float* vv = v + g * 8;
-                    if (p.bias != nullptr) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                        vv[0] += b0.x; vv[1] += b0.y; vv[2] += b0.z; vv[3] += b0.w;
-                        vv[4] += b1.x; vv[5] += b1.y; vv[6] += b1.z; vv[7] += b1.w;
-                    }
-                    if (p.act == ISTVT_ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.0f);
-                    } else if (p.act == ISTVT_ACT_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) vv[j] = gelu_erf(vv[j]);
-                    }
-                    if (p.residual != nullptr) {
-                        const float* rp = p.residual + drow * p.ldr + n;
-                        const float4 r0 = *reinterpret_cast<const float4*>(rp);
-                        const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-                        vv[0] += r0.x; vv[1] += r0.y; vv[2] += r0.z; vv[3] += r0.w;
-                        vv[4] += r1.x; vv[5] += r1.y; vv[6] += r1.z; vv[7] += r1.w;
-                    }
-                    if (p.c_f32) {
-                        float* cp = reinterpret_cast<float*>(p.C) + drow * p.ldc + n;
-                        *reinterpret_cast<float4*>(cp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                        *reinterpret_cast<float4*>(cp + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
-                    } else {
-                        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + drow * p.ldc + n;
-                        uint4 o;
-                        o.x = pack_bf16x2(vv[0], vv[1]);
-                        o.y = pack_bf16x2(vv[2], vv[3]);
-                        o.z = pack_bf16x2(vv[4], vv[5]);
-                        o.w = pack_bf16x2(vv[6], vv[7]);
-                        *reinterpret_cast<uint4*>(cp) = o;
-                    }
-                }
-            }
+            uint64_t* te = &tmem_empty[acc];
+            gemm_epilogue_64<PLAIN_BF16>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, slab, drow_t,
+                             n_blk * BN + col0, lane, [&]() {
+                                 tc_fence_before();
+                                 __syncwarp();
+                                 if (lane == 0) mbar_arrive(te);
+                             });
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -269,14 +209,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 template <int BN, int BK>
 static int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, BK>;
-    auto kern = gemm_tcgen05_kernel<BN, BK>;
-    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int n_tiles = (p.N + BN - 1) / BN;
     const int64_t m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
     const int64_t total = m_tiles * n_tiles;
     int grid = sm_count();
     if (total < grid) grid = static_cast<int>(total);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+    if (!p.c_f32 && p.residual == nullptr) {
+        auto kern = gemm_tcgen05_kernel<BN, BK, true>;
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+    } else {
+        auto kern = gemm_tcgen05_kernel<BN, BK, false>;
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+    }
     count_launch();
     return launch_status();
 }
@@ -293,10 +239,13 @@ int gemm_bf16_dispatch(const void* a, int64_t a_rows, int64_t lda, const void* w
                   (reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     ISTVT_REQUIRE(p.M < (int64_t(1) << 31) - 4096);
 
+    // Plain GEMMs with N >= 256 (every transformer Linear, block-3 pointwise/skip) run on CTA pairs.
+    if (p.taps == 1 && p.N >= 256) return launch_gemm_2cta(a, lda, w, ldw, p, stream);
+
     // tile configuration: BK = 64 (128B swizzle) unless the per-tap K is 32; BN by N.
     const int bk = (p.K % 64 == 0 || p.K > 64) ? 64 : 32;
     ISTVT_REQUIRE(bk == 64 || p.K == 32);
-    const int bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256);
+    const int bn = p.N <= 64 ? 64 : 128;
 
     CUtensorMap tm_a, tm_b;
     {
@@ -315,12 +264,10 @@ int gemm_bf16_dispatch(const void* a, int64_t a_rows, int64_t lda, const void* w
     }
     if (bk == 64) {
         if (bn == 64) return launch_gemm<64, 64>(tm_a, tm_b, p, stream);
-        if (bn == 128) return launch_gemm<128, 64>(tm_a, tm_b, p, stream);
-        return launch_gemm<256, 64>(tm_a, tm_b, p, stream);
+        return launch_gemm<128, 64>(tm_a, tm_b, p, stream);
     } else {
         if (bn == 64) return launch_gemm<64, 32>(tm_a, tm_b, p, stream);
-        if (bn == 128) return launch_gemm<128, 32>(tm_a, tm_b, p, stream);
-        return launch_gemm<256, 32>(tm_a, tm_b, p, stream);
+        return launch_gemm<128, 32>(tm_a, tm_b, p, stream);
     }
 }
 

@@ -1,0 +1,248 @@
+// CTA-pair tcgen05 GEMM for sm_100a (cta_group::2):  C = act(A · Wᵀ + bias) + residual,  N >= 256.
+//
+// Why pairs: profiles/r1a showed the 1-CTA 128x256 tile operand-feed bound (L2->SM 11.8 TB/s, tensor pipe
+// 49 %): it pulls (128 + 256) operand rows per 128x256 outputs.  A cluster of two CTAs computes a 256x256 tile
+// with ONE tcgen05.mma.cta_group::2 stream: each CTA stages its own 128 A rows and only HALF of the B tile
+// (128 W rows); the tensor cores of both SMs read both halves.  Operand traffic per output drops by 1/3 and
+// the smem ring gets 5 stages of 32 KB instead of 4 of 48 KB.
+//
+// Roles per CTA (640 threads): warp 0 = TMA producer (both CTAs; transaction bytes are credited to the
+// leader's full barrier), warp 1 = MMA issuer (LEADER CTA only, one lane), warp 2 = TMEM allocator,
+// warps 4..19 = epilogue of this CTA's 128 accumulator rows (32 rows x 64 columns each).  Barriers live at identical smem offsets in both
+// CTAs: full[s] (leader's copy used), empty[s] / tmem_full[a] (tcgen05.commit multicast to both CTAs),
+// tmem_empty[a] (leader's copy, 2 x 8 epilogue-warp arrivals, the peer arrives remotely via mapa).
+#include "gemm_common.cuh"
+
+#include <stdlib.h>
+
+namespace istvt {
+
+constexpr int G2_BN = 256;                    // cluster tile N (UMMA N), 128 W rows staged per CTA
+constexpr int G2_BK = 64;                     // 128-byte swizzle atom
+constexpr int G2_A_BYTES = GEMM_BLOCK_M * G2_BK * 2;   // 16 KB
+constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;    // 16 KB
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+template <int EW> struct G2Cfg {
+    static constexpr int THREADS = 128 + EW * 32;
+    static constexpr int STAGES = EW == 16 ? 5 : 6;
+    static constexpr int PASSES = (G2_BN / EPI_COLS) / (EW / 4);   // 64-column passes per epilogue warp per tile
+    static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + EW * EPI_SLAB_BYTES + 1024 + 256;
+};
+constexpr int G2_TMEM_COLS = 512;             // 2 accumulator buffers x 256 fp32 columns
+
+template <int EW, bool PLAIN_BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Cfg<EW>::THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                         const GemmParams p) {
+    constexpr int G2_STAGES = G2Cfg<EW>::STAGES;
+    constexpr int G2_EPI_WARPS = EW;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
+    uint8_t* smem_epi = smem + G2_STAGES * G2_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + G2_EPI_WARPS * EPI_SLAB_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + G2_STAGES;
+    uint64_t* tmem_full = bars + 2 * G2_STAGES;
+    uint64_t* tmem_empty = bars + 2 * G2_STAGES + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader
+    const uint32_t cluster = cluster_id_x();
+    const uint32_t n_clusters = num_clusters_x();
+
+    const int num_kb = (p.K + G2_BK - 1) / G2_BK;
+    const int n_tiles = (p.N + G2_BN - 1) / G2_BN;
+    const int64_t m_tiles = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+    const int64_t total_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < G2_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);     // leader's arrive.expect_tx; bytes of both CTAs' loads
+            mbar_init(&empty_bar[s], 1);    // one multicast commit
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);                    // one multicast commit
+            mbar_init(&tmem_empty[s], 2 * G2_EPI_WARPS);    // epilogue warps of both CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2cta(tmem_holder, G2_TMEM_COLS);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    cluster_sync_all();    // barrier inits + TMEM allocation visible in both CTAs before any remote arrive / TMA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    // columns of the last N tile rounded up to 16; each CTA stages half of them
+    auto tile_n_eff = [&](int n_blk) {
+        int n_eff = p.N - n_blk * G2_BN;
+        return n_eff >= G2_BN ? G2_BN : ((n_eff + 15) & ~15);
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs, one elected thread each) =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
+                const int64_t m_blk = tile / n_tiles;
+                const int n_blk = static_cast<int>(tile % n_tiles);
+                const int m0 = static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M);
+                const int n0 = n_blk * G2_BN + static_cast<int>(rank) * (tile_n_eff(n_blk) >> 1);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_hot(&empty_bar[stage], phase ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+                    tma_load_2d_2cta(smem_a + stage * G2_A_BYTES, &tm_a, &full_bar[stage], kb * G2_BK, m0);
+                    tma_load_2d_2cta(smem_b + stage * G2_B_BYTES, &tm_b, &full_bar[stage], kb * G2_BK, n0);
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (leader CTA, ONE elected thread) =====================
+        // The issue loop is the critical path of the kernel (profiles/r1f: ~26 SASS instructions per tcgen05.mma
+        // and ~75 per k-block made the issuing thread slower than the tensor core), so it is kept minimal:
+        // descriptors are a precomputed constant plus the stage's address field, the ragged last k-block is
+        // peeled, and the only per-k-block extras are one barrier wait and one commit.
+        if (elect_one()) {
+            const uint64_t desc_hi = make_smem_desc(0, 0, 1024, SWZ_128B);
+            const uint32_t a_field0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4;
+            const uint32_t b_field0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
+            int last_steps = (p.K - (num_kb - 1) * G2_BK + UMMA_K - 1) / UMMA_K;   // 1..4 MMAs in the last k-block
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
+                const int n_blk = static_cast<int>(tile % n_tiles);
+                const uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, static_cast<uint32_t>(tile_n_eff(n_blk)), 0, 0);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * G2_BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_hot(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = desc_hi | (a_field0 + stage * (G2_A_BYTES >> 4));
+                    const uint64_t b_desc = desc_hi | (b_field0 + stage * (G2_B_BYTES >> 4));
+                    if (kb != num_kb - 1) {
+                        umma_f16_ss_2cta(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
+                        umma_f16_ss_2cta(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                        umma_f16_ss_2cta(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                        umma_f16_ss_2cta(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                        umma_commit_2cta(&empty_bar[stage], 3);                  // free the slot in both CTAs
+                    } else {
+                        for (int k = 0; k < last_steps; ++k)
+                            umma_f16_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_2cta(&empty_bar[stage], 3);
+                        umma_commit_2cta(&tmem_full[acc], 3);                    // accumulator ready in both CTAs
+                    }
+                    if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue (this CTA's 128 rows x 256 columns) =====================
+        const int ew = warp - 4;
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+        constexpr int PASSES = G2Cfg<EW>::PASSES;
+        const int colw = (ew >> 2) * (EPI_COLS * PASSES);   // first tile column of this warp
+        const uint32_t slab = smem_u32(smem_epi + ew * EPI_SLAB_BYTES);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
+            const int64_t m_blk = tile / n_tiles;
+            const int n_blk = static_cast<int>(tile % n_tiles);
+            const int64_t m = m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32 + lane;
+            int drow_t[8];
+            const int drow_lane = m < p.M ? static_cast<int>(m) : -1;
+            epilogue_rows(drow_lane, lane, drow_t);
+            if constexpr (!PLAIN_BF16) epilogue_prefetch_residual(p, drow_lane, n_blk * G2_BN + colw, EPI_COLS * PASSES);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            uint64_t* te = &tmem_empty[acc];
+#pragma unroll 1
+            for (int ps = 0; ps < PASSES; ++ps) {
+                const int col0 = colw + ps * EPI_COLS;
+                gemm_epilogue_64<PLAIN_BF16>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * G2_BN + col0, slab, drow_t,
+                                 n_blk * G2_BN + col0, lane, [&]() {
+                                     if (ps != PASSES - 1) return;
+                                     // all TMEM reads of this warp for this accumulator are done: tell the leader's MMA warp
+                                     tc_fence_before();
+                                     __syncwarp();
+                                     if (lane == 0) mbar_arrive_cluster(te, 0);
+                                 });
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    // No CTA may exit (or free TMEM) while its peer can still multicast-arrive on its barriers or read its smem.
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, G2_TMEM_COLS);
+    }
+}
+
+int launch_gemm_2cta(const void* a, int64_t lda, const void* w, int64_t ldw, const GemmParams& p, cudaStream_t stream) {
+    CUtensorMap tm_a, tm_b;
+    {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+        const uint32_t box[2] = {G2_BK, GEMM_BLOCK_M};
+        int rc = encode_tmap(&tm_a, a, ISTVT_BF16, 2, dims, strides, box, 3);
+        if (rc != ISTVT_OK) return rc;
+    }
+    {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+        const uint32_t box[2] = {G2_BK, G2_BN / 2};
+        int rc = encode_tmap(&tm_b, w, ISTVT_BF16, 2, dims, strides, box, 3);
+        if (rc != ISTVT_OK) return rc;
+    }
+    const int n_tiles = (p.N + G2_BN - 1) / G2_BN;
+    const int64_t m_tiles = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+    const int64_t total = m_tiles * n_tiles;
+    int64_t clusters = sm_count() / 2;
+    if (total < clusters) clusters = total;
+    // Epilogue warps per CTA: 16 (32 rows x 64 columns each) for the bf16 path — halves the per-tile epilogue
+    // latency, which matters for the K = 512 / 728 GEMMs — and 8 for the fp32 / residual path, whose register
+    // footprint does not fit 640 threads (measured: profiles/README.md r1i).  ISTVT_G2_EPI_WARPS overrides.
+    static const int ew_env = []() {
+        const char* e = getenv("ISTVT_G2_EPI_WARPS");
+        return e ? atoi(e) : 0;
+    }();
+    const bool plain = !p.c_f32 && p.residual == nullptr;
+    const int ew = ew_env == 8 || ew_env == 16 ? ew_env : (plain ? 16 : 8);
+    const unsigned grid = static_cast<unsigned>(2 * clusters);
+#define ISTVT_G2_LAUNCH(EWV, PL)                                                                                   \
+    do {                                                                                                           \
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<EWV, PL>,                                   \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<EWV>::SMEM_BYTES)); \
+        gemm_tcgen05_2cta_kernel<EWV, PL><<<grid, G2Cfg<EWV>::THREADS, G2Cfg<EWV>::SMEM_BYTES, stream>>>(tm_a, tm_b, p); \
+    } while (0)
+    if (ew == 16) {
+        if (plain) ISTVT_G2_LAUNCH(16, true); else ISTVT_G2_LAUNCH(16, false);
+    } else {
+        if (plain) ISTVT_G2_LAUNCH(8, true); else ISTVT_G2_LAUNCH(8, false);
+    }
+#undef ISTVT_G2_LAUNCH
+    count_launch();
+    return launch_status();
+}
+
+}  // namespace istvt

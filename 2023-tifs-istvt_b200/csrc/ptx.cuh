@@ -63,19 +63,26 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 }
 // Bounded wait: a lost arrive (descriptor / byte-count bug) becomes a trap with a reported launch
 // failure instead of a GPU hang.  try_wait itself suspends the thread for a HW-defined interval, so
-// the bound below is many seconds of wall clock.
+// the bound below is ~15 s of wall clock (measured: 2^26 spins = 4.5 min on B200).
 #ifndef ISTVT_MBAR_SPIN_LIMIT
-#define ISTVT_MBAR_SPIN_LIMIT (1u << 26)
+#define ISTVT_MBAR_SPIN_LIMIT (1u << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > ISTVT_MBAR_SPIN_LIMIT) {
-            printf("istvt: mbarrier timeout block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x,
-                   (int)threadIdx.x, smem_u32(bar), parity);
+            if ((threadIdx.x & 31) == 0)
+                printf("istvt: mbarrier timeout block=%d warp=%d bar=%u parity=%u\n", (int)blockIdx.x,
+                       (int)(threadIdx.x >> 5), smem_u32(bar), parity);
             __trap();
         }
     }
+}
+
+// Wait for the hottest loops (MMA issue): no spin bookkeeping on the success path, bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait(bar, parity);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -96,6 +103,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
         "[%2];" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -188,6 +203,86 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// register re-balancing between warpgroups (all 4 warps of a warpgroup must execute the same one)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// ------------------------------------------------------------------------------------------
+// thread-block clusters / CTA pairs
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster.  Default semantics (release at CTA
+// scope): a .release.cluster here costs an ERRBAR + membar that waits for the thread's outstanding global stores
+// (profiles/r1h: 11 % of the GEMM's stall samples); the TMEM hand-off it signals is ordered by tcgen05 fences.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+// In a CTA pair the shared::cluster address of the even CTA's copy of a barrier = own address with the peer bit cleared.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+// 2-CTA TMA load: data lands in THIS CTA's smem, the transaction bytes are credited to the LEADER CTA's barrier.
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_holder, uint32_t ncols) {  // one warp in EACH CTA
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs, 128 rows each] * B[smem of both CTAs, N/2 rows each]; leader issues.
+__device__ __forceinline__ void umma_f16_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all prior MMAs of this thread retired) on the barrier at this smem offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp in CUTLASS; PTX ISA "tcgen05 descriptors")
 // ------------------------------------------------------------------------------------------
@@ -217,6 +312,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
            | ((M >> 4) << 24);       // M / 16
 }
 
+// Ordered (asm volatile) accesses: the compiler may not hoist these above earlier volatile asm, which keeps
+// the GEMM epilogue from front-loading all of its bias loads (64 live registers) ahead of the arithmetic.
+__device__ __forceinline__ float4 ldg_nc_f4_ordered(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void sts_u4_ordered(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// explicit shared-space 16-byte accesses (a generic pointer into dynamic smem compiles to LD.E / ST.E)
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // small numeric helpers
 // ------------------------------------------------------------------------------------------
@@ -229,5 +345,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     return __bfloat1622float2(v);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU for GEMM epilogues: erf by Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32 noise for
+// 0.5*x*(1+erf)), 2 MUFU (rcp, ex2) + 11 FMA-pipe ops instead of erff's branchy ~40 — the erff version made the
+// ff1 GEMM XU-pipe bound (profiles/r1a).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(z, 0.3275911f, 1.0f)));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+    const float erf_abs = fmaf(-p, e, 1.0f);
+    const float erf_x = copysignf(erf_abs, x);
+    const float h = 0.5f * x;
+    return fmaf(h, erf_x, h);
+}
 
 }  // namespace istvt

@@ -212,7 +212,10 @@ class ISTVTEngine:
 
     @torch.no_grad()
     def forward(self, model, x: torch.Tensor, precision: str = "bf16", return_attention: bool = False,
-                taps: Optional[dict] = None):
+                taps: Optional[dict] = None, entry_precision: Optional[str] = None,
+                ln2_input_fp32: bool = False):
+        """`entry_precision` / `ln2_input_fp32` are error-attribution knobs for tools/precision_probe.py
+        (entry flow in another precision than the transformer; temporal-attention output kept fp32 into LN2)."""
         vit = model.vit
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
@@ -248,7 +251,11 @@ class ISTVTEngine:
             frames = frames.float().contiguous()
 
         # ---- Xception entry flow; block 3's pool+add lands in the token buffer ----
-        body, skip = run_entry_flow(pk.entry, frames, dt, taps)
+        if entry_precision is not None and entry_precision != precision:
+            edt = PRECISIONS[entry_precision]
+            body, skip = run_entry_flow(self._pack(model, dev, entry_precision).entry, frames, edt, taps)
+        else:
+            body, skip = run_entry_flow(pk.entry, frames, dt, taps)
         tokens = torch.empty(b, f_tok, p_tok, dim, dtype=torch.float32, device=dev)
         ops.pool_add_tokens(body, skip, pk.pos_emb, tokens, b, t)
         ops.token_fill(tokens, pk.space_token, pk.temporal_token, pk.pos_emb)
@@ -266,7 +273,7 @@ class ISTVTEngine:
             qk = ops.gemm(diff.view(rows, dim), lp.w_qk)
             v = ops.gemm(xn.view(rows, dim), lp.w_v)
             at, p_t = ops.attn_temporal(qk, v, b, f_tok, p_tok, heads, scale, want_probs=return_attention)
-            y1 = ops.gemm(at, lp.w_to, bias=lp.b_to, out_dtype=dt)
+            y1 = ops.gemm(at, lp.w_to, bias=lp.b_to, out_dtype=torch.float32 if ln2_input_fp32 else dt)
             # spatial attention (module.py:81-93) + the residual spanning both attentions (vivit.py:99)
             yn = ops.layernorm(y1, lp.ln2[0], lp.ln2[1], dt, out=xn.view(rows, dim))
             qkv = ops.gemm(yn, lp.w_qkv)

@@ -152,6 +152,10 @@ def check_gemm_shapes():
         out[f"pw_{k}_{n}"] = _check_gemm_case(1000 + n, n, k, True, False, 1, torch.bfloat16, n + k)
     out["k32"] = _check_gemm_case(300, 64, 32, True, False, 1, torch.bfloat16, 9)
     out["many_tiles"] = _check_gemm_case(128 * 200 + 5, 728, 728, True, False, 0, torch.bfloat16, 10)
+    # >= 6 tiles per cluster with a ragged last N tile whose upper column groups are empty (N = 11*256 + 96, like
+    # ff1): exercises the TMEM double-buffer hand-off on every path (a missed tmem_empty arrival deadlocks here)
+    out["ragged_n_many_tiles"] = _check_gemm_case(256 * 40 + 3, 2912, 128, True, False, 2, torch.bfloat16, 11)
+    out["ragged_n_many_tiles_f32"] = _check_gemm_case(256 * 120 + 3, 1120, 64, True, True, 0, torch.float32, 12)
     return out
 
 

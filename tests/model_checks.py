@@ -58,23 +58,27 @@ def run_golden_case(name: str, precision: str):
     errs = {}
     want_logits = case["logits"]
     errs["logits"] = rel_err(logits, want_logits)
-    assert errs["logits"] <= tol, f"{name}/{precision}: logits {logits.flatten().tolist()} vs {want_logits.flatten().tolist()}"
-    assert torch.equal(logits.cpu() > 0, want_logits > 0), "predictions (logit > 0) differ"
     gt = case["taps"]
     entry = _taps_to_reference_layout(model, x, taps, attn, b, t)
-    # block3 is recovered from fp32 tokens by subtracting the (much larger) positional embedding: allow the
-    # cancellation its due in bf16 mode by measuring against the token magnitude instead.
+    # Measure everything first (tolerance inf), assert afterwards, so a failure reports the whole error profile.
+    inf = float("inf")
     for k in ("stem", "block1", "block2", "block3"):
-        errs[k] = fingerprint_check(f"{name}/{precision}/{k}", entry[k], gt[k], tol if k != "block3" else max(tol, 5e-4))
-    p_tok = 362
+        errs[k] = fingerprint_check(f"{name}/{precision}/{k}", entry[k], gt[k], inf)
     for key, want in gt.items():
         if key.endswith(".A_t"):
             li = int(key.split(".")[0][5:])
-            errs[key] = fingerprint_check(f"{name}/{precision}/{key}", attn[li][0], want, tol)          # [b,h,p,f,f]
+            errs[key] = fingerprint_check(f"{name}/{precision}/{key}", attn[li][0], want, inf)          # [b,h,p,f,f]
         elif key.endswith(".A_s"):
             li = int(key.split(".")[0][5:])
             a_s = attn[li][1].permute(0, 2, 1, 3, 4)                                                    # -> [b,h,f,p,p]
-            errs[key] = fingerprint_check(f"{name}/{precision}/{key}", a_s, want, tol)
+            errs[key] = fingerprint_check(f"{name}/{precision}/{key}", a_s, want, inf)
+    # block3 is recovered from fp32 tokens by subtracting the (much larger) positional embedding: allow the
+    # cancellation its due (5e-4) in fp32 mode.
+    bad = {k: v for k, v in errs.items() if not v <= (max(tol, 5e-4) if k == "block3" else tol)}
+    profile = ", ".join(f"{k}={v:.2e}" for k, v in errs.items())
+    assert not bad, (f"{name}/{precision}: over tolerance {tol:.0e}: {sorted(bad)}; logits {logits.flatten().tolist()} "
+                     f"vs {want_logits.flatten().tolist()}; profile: {profile}")
+    assert torch.equal(logits.cpu() > 0, want_logits > 0), "predictions (logit > 0) differ"
     return errs
 
 

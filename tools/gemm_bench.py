@@ -1,0 +1,91 @@
+"""Per-shape timing of the tcgen05 GEMMs of the C2 workload (M = 64 clips x 2534 tokens = 162176 rows).
+
+    python tools/gemm_bench.py [--iters 20] [--m 162176] [--only ff1,ff2]
+
+Prints one line per (call site): ms, TFLOP/s, effective GB/s.  Inputs are rotated over several buffers so that
+consecutive launches do not hit in L2 more than the real schedule does.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("2023-tifs-istvt_b200")
+ops = pkg.ops
+
+# name: (N, K, bias, residual(fp32 in-place), act, out dtype)
+SHAPES = {
+    "to_qk": (1024, 728, False, False, 0, torch.bfloat16),
+    "to_v": (512, 728, False, False, 0, torch.bfloat16),
+    "t_out": (728, 512, True, False, 0, torch.bfloat16),
+    "to_qkv": (1536, 728, False, False, 0, torch.bfloat16),
+    "s_out": (728, 512, True, True, 0, torch.float32),
+    "ff1": (2912, 728, True, False, 2, torch.bfloat16),
+    "ff2": (728, 2912, True, True, 0, torch.float32),
+}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--m", type=int, default=162176)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--custom", default="", help="extra shapes 'N,K;N,K' (bf16 out, no bias)")
+    ap.add_argument("--cublas", action="store_true", help="also time torch.matmul (cuBLAS) on the same operands: a "
+                                                          "yardstick for what the shape can reach, not a product path")
+    args = ap.parse_args()
+    for i, nk in enumerate(filter(None, args.custom.split(";"))):
+        n_, k_ = (int(v) for v in nk.split(","))
+        SHAPES[f"c{n_}x{k_}"] = (n_, k_, False, False, 0, torch.bfloat16)
+    m = args.m
+    dev = "cuda"
+    tot_ms, tot_fl = 0.0, 0.0
+    for name, (n, k, bias, res, act, odt) in SHAPES.items():
+        if args.only and name not in args.only.split(","):
+            continue
+        nbuf = 3
+        a = [torch.randn(m, k, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+        w = torch.randn(n, k, device=dev, dtype=torch.bfloat16) * k ** -0.5
+        b = torch.randn(n, device=dev) if bias else None
+        outs = [torch.zeros(m, n, device=dev, dtype=odt) for _ in range(nbuf)]
+        for i in range(3):
+            ops.gemm(a[i % nbuf], w, bias=b, residual=outs[i % nbuf] if res else None, act=act, out=outs[i % nbuf])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.iters):
+            ops.gemm(a[i % nbuf], w, bias=b, residual=outs[i % nbuf] if res else None, act=act, out=outs[i % nbuf])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        fl = 2.0 * m * n * k
+        by = m * k * 2 + n * k * 2 + m * n * outs[0].element_size() * (2 if res else 1)
+        tot_ms += ms
+        tot_fl += fl
+        extra = ""
+        if args.cublas:
+            wt = w.t()
+            for i in range(3):
+                torch.matmul(a[i % nbuf], wt)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.iters):
+                torch.matmul(a[i % nbuf], wt)
+            e1.record()
+            torch.cuda.synchronize()
+            msc = e0.elapsed_time(e1) / args.iters
+            extra = f"   | cuBLAS (plain A.Wt, bf16 out) {msc:7.3f} ms {fl / msc / 1e9:7.1f} TFLOP/s"
+        print(f"{name:10s} N={n:5d} K={k:5d} {ms:7.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s  {by / ms / 1e6:7.0f} GB/s{extra}", flush=True)
+        del a, outs
+    if tot_ms:
+        print(f"layer sum {tot_ms:7.3f} ms  {tot_fl / tot_ms / 1e9:7.1f} TFLOP/s  (x12 layers = {12 * tot_ms:.1f} ms)")
+
+
+if __name__ == "__main__":
+    main()
