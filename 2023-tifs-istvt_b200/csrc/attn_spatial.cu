@@ -238,6 +238,305 @@ attn_spatial_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
 }
 
 // ------------------------------------------------------------------------------------------
+// bf16 production kernel: persistent, software-pipelined.
+//
+// One CTA per SM walks (frame, head) items; an item is q_tiles (3) query tiles of 128 against the
+// same K / V (3 chunks of 128 keys).  Warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4-11 = softmax + epilogue (2 threads per query row, 64 columns of every chunk each).
+//   TMEM : S[128 x 384] fp32 (cols 0-383), O0 / O1 [128 x 64] fp32 (cols 384-447 / 448-511).
+//   smem : Q ring 4 x 16 KB, K double buffer 2 x 48 KB (the next item's K and Q are prefetched),
+//          V 48 KB (reloaded as soon as the item's last PV retires).
+// P never touches shared memory: the softmax warps overwrite the S chunk they have just consumed
+// with bf16 P (tcgen05.st, two keys per 32-bit column) and the PV MMA takes its A operand from TMEM.
+// Chunk-level hand-off keeps the tensor pipe and the MUFU pipe busy at the same time: the issuer
+// interleaves PV(t-1).c with S(t).c as soon as the softmax warps release chunk c, so S(t) is ready
+// when they finish tile t-1, and the O epilogue of tile t-1 is deferred until after the max pass of
+// tile t (O is double buffered).  Bound: MUFU (ex2) — 128 x 362 exponentials per tile at 16/clk/SM.
+// ------------------------------------------------------------------------------------------
+constexpr int SP_QSLOTS = 4;
+constexpr int SP_CHUNK_BYTES = 128 * SA_DH * 2;                  // 16 KB: 128 rows x 64 bf16
+constexpr int SP_Q_OFF = 0;
+constexpr int SP_K_OFF = SP_QSLOTS * SP_CHUNK_BYTES;              // 64 KB
+constexpr int SP_V_OFF = SP_K_OFF + 2 * SA_KV_BYTES;              // + 96 KB
+constexpr int SP_MISC_OFF = SP_V_OFF + SA_KV_BYTES;               // + 48 KB = 208 KB
+constexpr int SP_SMEM = SP_MISC_OFF + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * 4 /*row max, row sum*/;
+
+__global__ void __launch_bounds__(SA_THREADS, 1)
+attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
+                         int tokens, int heads, int items, float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_q = smem + SP_Q_OFF;
+    uint8_t* s_k = smem + SP_K_OFF;
+    uint8_t* s_v = smem + SP_V_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_MISC_OFF);
+    uint64_t* q_full = bars;            // [4]
+    uint64_t* q_empty = bars + 4;       // [4]
+    uint64_t* k_full = bars + 8;        // [2]
+    uint64_t* k_empty = bars + 10;      // [2]
+    uint64_t* v_full = bars + 12;
+    uint64_t* v_empty = bars + 13;
+    uint64_t* s_full = bars + 14;       // [3] S chunk c of the current tile is in TMEM
+    uint64_t* p_full = bars + 17;       // [3] P chunk c written (and S chunk c consumed) by all softmax warps
+    uint64_t* o_full = bars + 20;       // [2]
+    uint64_t* o_empty = bars + 22;      // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 24);
+    float* s_max = reinterpret_cast<float*>(smem + SP_MISC_OFF + 256);   // [2][128]
+    float* s_sum = s_max + 256;                                            // [2][128]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int inner = heads * SA_DH;
+    const int q_tiles = (tokens + SA_BM - 1) / SA_BM;
+    const int k_chunks = q_tiles;
+    const int my_items = (items > static_cast<int>(blockIdx.x))
+                             ? (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                   static_cast<int>(gridDim.x)
+                             : 0;
+    const int n_tiles = my_items * q_tiles;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_qkv);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(q_full + i, 1); mbar_init(q_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
+            mbar_init(o_full + i, 1); mbar_init(o_empty + i, 8);
+        }
+        mbar_init(v_full, 1); mbar_init(v_empty, 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, 8); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_holder, SA_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tmem_s = tmem_base;
+    const uint32_t tmem_o = tmem_base + SA_KMAX;    // + 64 * buffer
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int n = 0; n < my_items; ++n) {
+                const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+                const int h = item % heads;
+                const int bf = item / heads;
+                const int kb = n & 1;
+                mbar_wait(k_empty + kb, ((n >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(k_full + kb, k_chunks * SP_CHUNK_BYTES);
+                for (int c = 0; c < k_chunks; ++c)
+                    tma_load_3d(s_k + kb * SA_KV_BYTES + c * SP_CHUNK_BYTES, &tm_qkv, k_full + kb, inner + h * SA_DH,
+                                c * 128, bf);
+                for (int qt = 0; qt < q_tiles; ++qt) {
+                    const int t = n * q_tiles + qt;
+                    const int slot = t & 3;
+                    mbar_wait(q_empty + slot, ((t >> 2) & 1) ^ 1);
+                    mbar_arrive_expect_tx(q_full + slot, SP_CHUNK_BYTES);
+                    tma_load_3d(s_q + slot * SP_CHUNK_BYTES, &tm_qkv, q_full + slot, h * SA_DH, qt * SA_BM, bf);
+                }
+                mbar_wait(v_empty, (n & 1) ^ 1);
+                mbar_arrive_expect_tx(v_full, k_chunks * SP_CHUNK_BYTES);
+                for (int c = 0; c < k_chunks; ++c)
+                    tma_load_3d(s_v + c * SP_CHUNK_BYTES, &tm_qkv, v_full, 2 * inner + h * SA_DH, c * 128, bf);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_bf16(SA_BM, 128, 0, 0);
+            const uint32_t idesc_pv = make_idesc_bf16(SA_BM, SA_DH, 0, 1);   // B (= V) is MN-major
+            const uint32_t q_addr = smem_u32(s_q);
+            const uint32_t k_addr = smem_u32(s_k);
+            const uint32_t v_addr = smem_u32(s_v);
+            const int last_ksteps = (tokens - (k_chunks - 1) * 128 + 15) / 16;
+            for (int t = 0; t <= n_tiles; ++t) {
+                for (int c = 0; c < k_chunks; ++c) {
+                    if (t > 0) {
+                        // ---- O(t-1) += P(t-1).c V.c ----
+                        const int tp = t - 1;
+                        const int np = tp / q_tiles;
+                        const int qp = tp - np * q_tiles;
+                        const int ob = tp & 1;
+                        if (c == 0) {
+                            if (qp == 0) mbar_wait(v_full, np & 1);
+                            mbar_wait(o_empty + ob, ((tp >> 1) & 1) ^ 1);
+                        }
+                        mbar_wait(p_full + c, tp & 1);
+                        tc_fence_after();
+                        const int ksteps = (c == k_chunks - 1) ? last_ksteps : 8;
+                        for (int j = 0; j < ksteps; ++j) {
+                            const uint32_t a_tmem = tmem_s + c * 128 + (j >> 2) * 64 + (j & 3) * 8;
+                            const uint64_t b_desc =
+                                make_smem_desc(v_addr + (c * 8 + j) * 16 * 128, 64 * 128, 1024, SWZ_128B);
+                            umma_f16_ts(tmem_o + ob * SA_DH, a_tmem, b_desc, idesc_pv, (c | j) != 0 ? 1u : 0u);
+                        }
+                        if (c == k_chunks - 1) {
+                            umma_commit(o_full + ob);
+                            if (qp == q_tiles - 1) umma_commit(v_empty);
+                        }
+                    }
+                    if (t < n_tiles) {
+                        // ---- S(t).c = Q(t) K.c^T ----
+                        const int n = t / q_tiles;
+                        const int qt = t - n * q_tiles;
+                        const int slot = t & 3;
+                        const int kb = n & 1;
+                        if (c == 0) {
+                            mbar_wait(q_full + slot, (t >> 2) & 1);
+                            if (qt == 0) mbar_wait(k_full + kb, (n >> 1) & 1);
+                            tc_fence_after();
+                        }
+#pragma unroll
+                        for (int k = 0; k < SA_DH / 16; ++k) {
+                            const uint64_t a_desc =
+                                make_smem_desc(q_addr + slot * SP_CHUNK_BYTES + k * 32, 0, 1024, SWZ_128B);
+                            const uint64_t b_desc = make_smem_desc(
+                                k_addr + kb * SA_KV_BYTES + c * SP_CHUNK_BYTES + k * 32, 0, 1024, SWZ_128B);
+                            umma_f16_ss(tmem_s + c * 128, a_desc, b_desc, idesc_s, k != 0 ? 1u : 0u);
+                        }
+                        umma_commit(s_full + c);
+                        if (c == k_chunks - 1) {
+                            umma_commit(q_empty + slot);
+                            if (qt == q_tiles - 1) umma_commit(k_empty + kb);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ================= softmax + epilogue =================
+        const int quad = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int row = quad * 32 + lane;                 // row inside the q tile == TMEM lane
+        const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t t_row = tmem_s + lane_base + half * 64;   // this thread's 64 columns of chunk 0
+        float inv_prev = 0.0f;
+        int64_t out_prev = -1;                             // element offset of this thread's 32 outputs, -1 = no store
+
+        auto epilogue = [&](int tp) {
+            const int ob = tp & 1;
+            mbar_wait(o_full + ob, (tp >> 1) & 1);
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_o + ob * SA_DH + lane_base + half * 32, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty + ob);
+            if (out_prev >= 0) {
+                __nv_bfloat16* op = out + out_prev;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv_prev, __uint_as_float(r[8 * g + 1]) * inv_prev);
+                    o.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv_prev, __uint_as_float(r[8 * g + 3]) * inv_prev);
+                    o.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv_prev, __uint_as_float(r[8 * g + 5]) * inv_prev);
+                    o.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv_prev, __uint_as_float(r[8 * g + 7]) * inv_prev);
+                    *reinterpret_cast<uint4*>(op + 8 * g) = o;
+                }
+            }
+        };
+
+        for (int t = 0; t < n_tiles; ++t) {
+            const int n = t / q_tiles;
+            const int qt = t - n * q_tiles;
+            const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+            const int h = item % heads;
+            const int bf = item / heads;
+            const int q_idx = qt * SA_BM + row;
+
+            // ---- pass 1: row max over the valid keys ----
+            float mx = -INFINITY;
+            for (int c = 0; c < k_chunks; ++c) {
+                mbar_wait(s_full + c, t & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int key0 = c * 128 + half * 64 + b * 32;
+                    if (key0 >= tokens) continue;          // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_row + c * 128 + b * 32, r);
+                    tmem_ld_wait();
+                    if (key0 + 32 <= tokens) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (key0 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    }
+                }
+            }
+            s_max[half * 128 + row] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mx = fmaxf(s_max[row], s_max[128 + row]);
+            const float mxs = mx * scale_log2;
+
+            // ---- deferred epilogue of the previous tile (its PV retired while pass 1 ran) ----
+            if (t > 0) epilogue(t - 1);
+
+            // ---- pass 2: P = exp2(S*c - max*c) -> bf16 -> TMEM (over the S columns just read), row sums ----
+            float sum = 0.0f;
+            for (int c = 0; c < k_chunks; ++c) {
+                uint32_t pk[32];
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int key0 = c * 128 + half * 64 + b * 32;
+                    if (key0 >= tokens) {                  // warp-uniform: fully masked batch
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[b * 16 + j] = 0u;
+                        continue;
+                    }
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_row + c * 128 + b * 32, r);
+                    tmem_ld_wait();
+                    const bool full = key0 + 32 <= tokens;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+                        float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
+                        if (!full) {
+                            if (key0 + 2 * j >= tokens) e0 = 0.0f;
+                            if (key0 + 2 * j + 1 >= tokens) e1 = 0.0f;
+                        }
+                        // The PV MMA consumes bf16 P: accumulate the denominator from the rounded values so the
+                        // normalised rows sum to one in the precision actually used.
+                        const uint32_t u = pack_bf16x2(e0, e1);
+                        pk[b * 16 + j] = u;
+                        const float2 f = unpack_bf16x2(u);
+                        sum += f.x + f.y;
+                    }
+                }
+                tmem_st_32x32b_x32(t_row + c * 128, pk);   // keys [64*half, 64*half+64) of chunk c -> 32 columns
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full + c);
+            }
+            s_sum[half * 128 + row] = sum;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            inv_prev = 1.0f / (s_sum[row] + s_sum[128 + row]);
+            out_prev = (q_idx < tokens)
+                           ? (static_cast<int64_t>(bf) * tokens + q_idx) * inner + h * SA_DH + half * 32
+                           : -1;
+        }
+        if (n_tiles > 0) epilogue(n_tiles - 1);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, SA_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // fp32 validation kernel: one CTA per (frame, head); K and V in shared memory, one query per thread.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -343,10 +642,22 @@ extern "C" int istvt_attn_spatial_fwd(const void* qkv, void* out, float* probs, 
         int rc = encode_tmap(&tm, qkv, ISTVT_BF16, 3, dims, strides, box, 3);
         if (rc != ISTVT_OK) return rc;
     }
+    const float scale_log2 = scale * 1.4426950408889634f;
+    if (probs == nullptr) {
+        // production path: persistent pipelined kernel, one CTA per SM
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              SP_SMEM));
+        const int items = batch_frames * heads;
+        const int grid = items < sm_count() ? items : sm_count();
+        attn_spatial_pipe_kernel<<<grid, SA_THREADS, SP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), tokens,
+                                                                   heads, items, scale_log2);
+        count_launch();
+        return launch_status();
+    }
+    // attention-map mode (parity tests, relevance pass): one CTA per (frame, head, query tile), S kept in TMEM
     ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           SA_SMEM));
     const int q_tiles = (tokens + SA_BM - 1) / SA_BM;
-    const float scale_log2 = scale * 1.4426950408889634f;
     attn_spatial_tcgen05_kernel<<<batch_frames * heads * q_tiles, SA_THREADS, SA_SMEM, st>>>(
         tm, static_cast<__nv_bfloat16*>(out), probs, tokens, heads, scale_log2);
     count_launch();

@@ -118,6 +118,127 @@ attn_temporal_kernel(const T* __restrict__ qk, const T* __restrict__ v, T* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// bf16 production kernel for F <= 8 frames (the ISTVT configuration, F = 7): one WARP per
+// (clip, position, head) on the legacy warp-level tensor-core path (mma.sync m16n8k16) — the
+// problem (7x7x64) is far below a tcgen05 tile, but mma.sync consumes the bf16 rows exactly as
+// they sit in HBM, so the kernel is ~100 instructions per warp with every global access a 16-byte
+// vector: 2+2 for Q/K row g (lane = 4g+t), 2 for V rows 2t/2t+1, 2 stores.  Index tricks:
+//   * the k (head-dim) order of Q.K^T is permuted identically for A and B, so each lane's two
+//     16-byte loads feed the fragments directly (no shuffles);
+//   * the n (head-dim) order of P.V is permuted (n = g  <->  dim 8g + nt) so that the B fragment
+//     {V[2t][d], V[2t+1][d]} is a byte-permute of two 16-byte row loads and each lane ends up
+//     owning 16 contiguous output dims of row g.
+// A CTA (8 warps) covers all heads of one (clip, position): full 1 KB rows per request.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+attn_temporal_mma_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
+                         __nv_bfloat16* __restrict__ out, float* __restrict__ probs, int frames, int tokens,
+                         int heads, float scale_log2, int64_t units) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2;          // fragment row: query frame (A / D), key frame (B of Q.K^T)
+    const int t = lane & 3;
+    const int64_t unit = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (unit >= units) return;
+    const int h = static_cast<int>(unit % heads);
+    const int64_t bp = unit / heads;
+    const int64_t b = bp / tokens;
+    const int pos = static_cast<int>(bp - b * tokens);
+    const int inner = heads * TA_DH;
+    const int64_t row0 = b * frames * tokens + pos;
+
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    uint4 q0 = zero, q1 = zero, k0 = zero, k1 = zero, v0 = zero, v1 = zero;
+    if (g < frames) {
+        const __nv_bfloat16* qp = qk + (row0 + static_cast<int64_t>(g) * tokens) * (2 * inner) + h * TA_DH;
+        q0 = ldg_nc_u4(qp + 8 * t);
+        q1 = ldg_nc_u4(qp + 8 * (t + 4));
+        k0 = ldg_nc_u4(qp + inner + 8 * t);
+        k1 = ldg_nc_u4(qp + inner + 8 * (t + 4));
+    }
+    if (2 * t < frames)
+        v0 = ldg_nc_u4(v + (row0 + static_cast<int64_t>(2 * t) * tokens) * inner + h * TA_DH + 8 * g);
+    if (2 * t + 1 < frames)
+        v1 = ldg_nc_u4(v + (row0 + static_cast<int64_t>(2 * t + 1) * tokens) * inner + h * TA_DH + 8 * g);
+
+    // S[g][2t], S[g][2t+1] (rows 8-15 of the tile are padding)
+    float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    mma_bf16_16816(s, q0.x, 0u, q0.y, 0u, k0.x, k0.y);
+    mma_bf16_16816(s, q0.z, 0u, q0.w, 0u, k0.z, k0.w);
+    mma_bf16_16816(s, q1.x, 0u, q1.y, 0u, k1.x, k1.y);
+    mma_bf16_16816(s, q1.z, 0u, q1.w, 0u, k1.z, k1.w);
+
+    const float s0 = (2 * t < frames) ? s[0] * scale_log2 : -INFINITY;
+    const float s1 = (2 * t + 1 < frames) ? s[1] * scale_log2 : -INFINITY;
+    float mx = fmaxf(s0, s1);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float p0, p1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(s0 - mx));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(s1 - mx));
+    // the P.V MMA consumes bf16 P: normalise by the sum of the rounded values
+    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+    const uint32_t pp = *reinterpret_cast<const uint32_t*>(&pb);
+    const float2 pf = __bfloat1622float2(pb);
+    float sum = pf.x + pf.y;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.0f / sum;
+
+    if (probs != nullptr) {  // probs[b, h, pos, i, j], fp32, from the unrounded exponentials
+        float sum32 = p0 + p1;
+        sum32 += __shfl_xor_sync(0xffffffffu, sum32, 1);
+        sum32 += __shfl_xor_sync(0xffffffffu, sum32, 2);
+        const float inv32 = 1.0f / sum32;
+        if (g < frames) {
+            float* pr = probs + ((((b * heads + h) * tokens + pos) * frames) + g) * frames;
+            if (2 * t < frames) pr[2 * t] = p0 * inv32;
+            if (2 * t + 1 < frames) pr[2 * t + 1] = p1 * inv32;
+        }
+    }
+
+    // O[g][16t + nt] and O[g][16t + 8 + nt] for nt = 0..7
+    const uint32_t vw0[4] = {v0.x, v0.y, v0.z, v0.w};
+    const uint32_t vw1[4] = {v1.x, v1.y, v1.z, v1.w};
+    float olo[8], ohi[8];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t b0 = __byte_perm(vw0[nt >> 1], vw1[nt >> 1], (nt & 1) ? 0x7632 : 0x5410);
+        float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        mma_bf16_16816(d, pp, 0u, 0u, 0u, b0, 0u);
+        olo[nt] = d[0] * inv;
+        ohi[nt] = d[1] * inv;
+    }
+    if (g < frames) {
+        __nv_bfloat16* op = out + (row0 + static_cast<int64_t>(g) * tokens) * inner + h * TA_DH + 16 * t;
+        uint4 a, c;
+        auto pk = [](float x, float y) {
+            const __nv_bfloat162 r = __floats2bfloat162_rn(x, y);
+            return *reinterpret_cast<const uint32_t*>(&r);
+        };
+        a.x = pk(olo[0], olo[1]); a.y = pk(olo[2], olo[3]); a.z = pk(olo[4], olo[5]); a.w = pk(olo[6], olo[7]);
+        c.x = pk(ohi[0], ohi[1]); c.y = pk(ohi[2], ohi[3]); c.z = pk(ohi[4], ohi[5]); c.w = pk(ohi[6], ohi[7]);
+        *reinterpret_cast<uint4*>(op) = a;
+        *reinterpret_cast<uint4*>(op + 8) = c;
+    }
+}
+
 template <typename T>
 static int launch_temporal(const void* qk, const void* v, void* out, float* probs, int batch, int frames,
                            int tokens, int heads, float scale, cudaStream_t st) {
@@ -141,9 +262,21 @@ extern "C" int istvt_attn_temporal_fwd(const void* qk, const void* v, void* out,
                                        int frames, int tokens, int heads, float scale, istvt_stream_t stream) {
     ISTVT_REQUIRE(qk && v && out);
     ISTVT_REQUIRE(batch > 0 && frames > 0 && tokens > 0 && heads > 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == ISTVT_BF16 && frames <= 8) {
+        ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(v) |
+                        reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+        const int64_t units = static_cast<int64_t>(batch) * tokens * heads;
+        const int64_t grid = (units + 7) / 8;
+        ISTVT_REQUIRE(grid < (int64_t(1) << 31));
+        attn_temporal_mma_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v),
+            static_cast<__nv_bfloat16*>(out), probs, frames, tokens, heads, scale * 1.4426950408889634f, units);
+        count_launch();
+        return launch_status();
+    }
     ISTVT_REQUIRE(heads * frames <= 288);
     ISTVT_REQUIRE(static_cast<int64_t>(batch) * tokens < (int64_t(1) << 31));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == ISTVT_BF16)
         return launch_temporal<__nv_bfloat16>(qk, v, out, probs, batch, frames, tokens, heads, scale, st);
     if (dtype == ISTVT_F32) return launch_temporal<float>(qk, v, out, probs, batch, frames, tokens, heads, scale, st);

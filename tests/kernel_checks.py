@@ -262,7 +262,8 @@ def check_attn_temporal():
     ops = _ops()
     out = {}
     heads, scale = 8, 0.125
-    for (b, f, p) in ((2, 7, 362), (1, 33, 362), (1, 2, 5)):
+    # f <= 8 in bf16 runs the warp-per-(clip, position, head) mma.sync kernel; f = 33 / fp32 the SIMT kernel
+    for (b, f, p) in ((2, 7, 362), (1, 33, 362), (1, 2, 5), (3, 8, 101), (1, 1, 9)):
         for dt, tol in ((torch.float32, 5e-5), (torch.bfloat16, TOL_BF16)):
             rows = b * f * p
             qk = (_rand(rows, 1024, seed=f) * 1.5).to(dt)
@@ -274,6 +275,8 @@ def check_attn_temporal():
             oref = oref.permute(0, 3, 2, 1, 4).reshape(rows, 512)
             out[f"out_{dt}_{f}"] = _assert_close("attn_t out", o, oref, tol)
             out[f"probs_{dt}_{f}"] = _assert_close("attn_t probs", probs, aref, 5e-5 if dt == torch.float32 else 2e-3)
+            o2, none = ops.attn_temporal(qk, v, b, f, p, heads, scale, want_probs=False)
+            assert none is None and torch.equal(o, o2), "probs emission must not change the output"
     return out
 
 
@@ -295,7 +298,9 @@ def check_attn_spatial_bf16():
     ops = _ops()
     out = {}
     heads, scale = 8, 0.125
-    for (bf, p, amp) in ((1, 362, 1.0), (5, 362, 2.0), (2, 128, 1.0), (2, 200, 1.0), (3, 50, 1.0)):
+    # (40, 362): 320 (frame, head) items on 148 persistent CTAs -> the cross-item prefetch / ring wrap-around paths
+    for (bf, p, amp) in ((1, 362, 1.0), (5, 362, 2.0), (2, 128, 1.0), (2, 200, 1.0), (3, 50, 1.0), (40, 362, 1.5),
+                         (21, 130, 1.0), (45, 384, 1.0)):
         qkv = (_rand(bf * p, 1536, seed=p + bf) * amp).to(torch.bfloat16)
         o, probs = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=True)
         torch.cuda.synchronize()
@@ -305,8 +310,13 @@ def check_attn_spatial_bf16():
         out[f"probs_{name}"] = _assert_close(f"attn_s bf16 probs {name}", probs.reshape(-1, p), aref.reshape(-1, p), 2e-3)
         out[f"out_{name}"] = _assert_close(f"attn_s bf16 out {name}", o,
                                            oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 1.5e-2)
+        # production kernel (persistent, P in TMEM) vs the attention-map kernel: same math, different schedule
         o2, none = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=False)
-        assert none is None and torch.equal(o, o2), "probs emission must not change the output"
+        torch.cuda.synchronize()
+        assert none is None
+        out[f"pipe_{name}"] = _assert_close(f"attn_s bf16 pipelined out {name}", o2,
+                                            oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 1.5e-2)
+        out[f"pipe_vs_map_{name}"] = _assert_close(f"attn_s bf16 pipelined vs map kernel {name}", o2, o, 8e-3)
     return out
 
 
