@@ -35,6 +35,19 @@ SIGNATURES = {
     "istvt_attn_temporal_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "istvt_attn_spatial_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "istvt_head_fwd": [_P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    # training step
+    "istvt_attn_spatial_fwd_lse": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "istvt_attn_spatial_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "istvt_attn_temporal_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "istvt_layernorm_bwd": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    "istvt_gelu_fwd": [_P, _P, _L, _P],
+    "istvt_gelu_bwd": [_P, _P, _P, _L, _P],
+    "istvt_cast_f32_bf16": [_P, _P, _L, _P],
+    "istvt_transpose_colsum": [_P, _P, _P, _L, _I, _L, _P],
+    "istvt_gemm_splitk_accum": [_P, _L, _P, _L, _P, _L, _L, _I, _L, _P],
+    "istvt_head_bwd": [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "istvt_token_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "istvt_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
 }
 _RESTYPES = {"istvt_error_string": c_char_p, "istvt_launch_count": c_int64}
 

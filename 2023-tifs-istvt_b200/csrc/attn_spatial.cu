@@ -242,28 +242,33 @@ attn_spatial_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
 //
 // One CTA per SM walks (frame, head) items; an item is q_tiles (3) query tiles of 128 against the
 // same K / V (3 chunks of 128 keys).  Warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-11 = softmax + epilogue (2 threads per query row, 64 columns of every chunk each).
+// allocator, warps 4-19 = softmax + epilogue (4 threads per query row, 32 columns of every chunk each:
+// 4 softmax warps per scheduler — with 2 the issue slots were 42 % used, profiles/r1o).
 //   TMEM : S[128 x 384] fp32 (cols 0-383), O0 / O1 [128 x 64] fp32 (cols 384-447 / 448-511).
 //   smem : Q ring 4 x 16 KB, K double buffer 2 x 48 KB (the next item's K and Q are prefetched),
 //          V 48 KB (reloaded as soon as the item's last PV retires).
-// P never touches shared memory: the softmax warps overwrite the S chunk they have just consumed
+// P never touches shared memory: the softmax warps overwrite the S columns they have just consumed
 // with bf16 P (tcgen05.st, two keys per 32-bit column) and the PV MMA takes its A operand from TMEM.
 // Chunk-level hand-off keeps the tensor pipe and the MUFU pipe busy at the same time: the issuer
 // interleaves PV(t-1).c with S(t).c as soon as the softmax warps release chunk c, so S(t) is ready
 // when they finish tile t-1, and the O epilogue of tile t-1 is deferred until after the max pass of
 // tile t (O is double buffered).  Bound: MUFU (ex2) — 128 x 362 exponentials per tile at 16/clk/SM.
+// Optional `lse` output (training): log2-domain log-sum-exp of every query row, consumed by the backward.
 // ------------------------------------------------------------------------------------------
 constexpr int SP_QSLOTS = 4;
+constexpr int SP_PARTS = 4;                                      // softmax threads per query row
+constexpr int SP_SM_WARPS = 4 * SP_PARTS;                        // 16 softmax warps
+constexpr int SP_THREADS = 128 + 32 * SP_SM_WARPS;               // 640
 constexpr int SP_CHUNK_BYTES = 128 * SA_DH * 2;                  // 16 KB: 128 rows x 64 bf16
 constexpr int SP_Q_OFF = 0;
 constexpr int SP_K_OFF = SP_QSLOTS * SP_CHUNK_BYTES;              // 64 KB
 constexpr int SP_V_OFF = SP_K_OFF + 2 * SA_KV_BYTES;              // + 96 KB
 constexpr int SP_MISC_OFF = SP_V_OFF + SA_KV_BYTES;               // + 48 KB = 208 KB
-constexpr int SP_SMEM = SP_MISC_OFF + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * 4 /*row max, row sum*/;
+constexpr int SP_SMEM = SP_MISC_OFF + 1024 /*align*/ + 256 /*barriers*/ + 2 * SP_PARTS * 128 * 4 /*row max, row sum*/;
 
-__global__ void __launch_bounds__(SA_THREADS, 1)
+__global__ void __launch_bounds__(SP_THREADS, 1)
 attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                         int tokens, int heads, int items, float scale_log2) {
+                         float* __restrict__ lse, int tokens, int heads, int items, float scale_log2) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_q = smem + SP_Q_OFF;
@@ -281,8 +286,8 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     uint64_t* o_full = bars + 20;       // [2]
     uint64_t* o_empty = bars + 22;      // [2]
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 24);
-    float* s_max = reinterpret_cast<float*>(smem + SP_MISC_OFF + 256);   // [2][128]
-    float* s_sum = s_max + 256;                                            // [2][128]
+    float* s_max = reinterpret_cast<float*>(smem + SP_MISC_OFF + 256);   // [SP_PARTS][128]
+    float* s_sum = s_max + SP_PARTS * 128;                                // [SP_PARTS][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -300,10 +305,10 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
         for (int i = 0; i < 4; ++i) { mbar_init(q_full + i, 1); mbar_init(q_empty + i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
-            mbar_init(o_full + i, 1); mbar_init(o_empty + i, 8);
+            mbar_init(o_full + i, 1); mbar_init(o_empty + i, SP_SM_WARPS);
         }
         mbar_init(v_full, 1); mbar_init(v_empty, 1);
-        for (int i = 0; i < 3; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, 8); }
+        for (int i = 0; i < 3; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, SP_SM_WARPS); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -325,7 +330,7 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
                 const int h = item % heads;
                 const int bf = item / heads;
                 const int kb = n & 1;
-                mbar_wait(k_empty + kb, ((n >> 1) & 1) ^ 1);
+                mbar_wait_sleep(k_empty + kb, ((n >> 1) & 1) ^ 1);
                 mbar_arrive_expect_tx(k_full + kb, k_chunks * SP_CHUNK_BYTES);
                 for (int c = 0; c < k_chunks; ++c)
                     tma_load_3d(s_k + kb * SA_KV_BYTES + c * SP_CHUNK_BYTES, &tm_qkv, k_full + kb, inner + h * SA_DH,
@@ -333,11 +338,11 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
                 for (int qt = 0; qt < q_tiles; ++qt) {
                     const int t = n * q_tiles + qt;
                     const int slot = t & 3;
-                    mbar_wait(q_empty + slot, ((t >> 2) & 1) ^ 1);
+                    mbar_wait_sleep(q_empty + slot, ((t >> 2) & 1) ^ 1);
                     mbar_arrive_expect_tx(q_full + slot, SP_CHUNK_BYTES);
                     tma_load_3d(s_q + slot * SP_CHUNK_BYTES, &tm_qkv, q_full + slot, h * SA_DH, qt * SA_BM, bf);
                 }
-                mbar_wait(v_empty, (n & 1) ^ 1);
+                mbar_wait_sleep(v_empty, (n & 1) ^ 1);
                 mbar_arrive_expect_tx(v_full, k_chunks * SP_CHUNK_BYTES);
                 for (int c = 0; c < k_chunks; ++c)
                     tma_load_3d(s_v + c * SP_CHUNK_BYTES, &tm_qkv, v_full, 2 * inner + h * SA_DH, c * 128, bf);
@@ -346,58 +351,62 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // One elected thread; descriptors are constants plus an address field (the GEMM's lesson, profiles/r1f:
+        // an `if (lane == 0)` region costs ~26 SASS instructions per tcgen05.mma, an elect.sync region ~2).
+        if (elect_one()) {
             const uint32_t idesc_s = make_idesc_bf16(SA_BM, 128, 0, 0);
             const uint32_t idesc_pv = make_idesc_bf16(SA_BM, SA_DH, 0, 1);   // B (= V) is MN-major
-            const uint32_t q_addr = smem_u32(s_q);
-            const uint32_t k_addr = smem_u32(s_k);
-            const uint32_t v_addr = smem_u32(s_v);
+            const uint64_t desc_kmaj = make_smem_desc(0, 0, 1024, SWZ_128B);
+            const uint64_t desc_v = make_smem_desc(smem_u32(s_v), 64 * 128, 1024, SWZ_128B);
+            const uint32_t q_field = (smem_u32(s_q) & 0x3FFFFu) >> 4;
+            const uint32_t k_field = (smem_u32(s_k) & 0x3FFFFu) >> 4;
             const int last_ksteps = (tokens - (k_chunks - 1) * 128 + 15) / 16;
+            int qt = 0, n = 0;          // tile t = n * q_tiles + qt
+            int qp = 0, np = 0;         // tile t - 1
             for (int t = 0; t <= n_tiles; ++t) {
+                const int slot = t & 3;
+                const int kb = n & 1;
+                const int tp = t - 1;
+                const int ob = tp & 1;
+                const uint64_t q_desc = desc_kmaj | (q_field + slot * (SP_CHUNK_BYTES >> 4));
+                const uint64_t k_desc = desc_kmaj | (k_field + kb * (SA_KV_BYTES >> 4));
+                const uint32_t d_o = tmem_o + ob * SA_DH;
                 for (int c = 0; c < k_chunks; ++c) {
                     if (t > 0) {
-                        // ---- O(t-1) += P(t-1).c V.c ----
-                        const int tp = t - 1;
-                        const int np = tp / q_tiles;
-                        const int qp = tp - np * q_tiles;
-                        const int ob = tp & 1;
+                        // ---- O(t-1) += P(t-1).c V.c ----  (P: 16 keys = 8 packed columns; part q owns columns 32q..)
                         if (c == 0) {
                             if (qp == 0) mbar_wait(v_full, np & 1);
                             mbar_wait(o_empty + ob, ((tp >> 1) & 1) ^ 1);
                         }
-                        mbar_wait(p_full + c, tp & 1);
+                        mbar_wait_hot(p_full + c, tp & 1);
                         tc_fence_after();
-                        const int ksteps = (c == k_chunks - 1) ? last_ksteps : 8;
-                        for (int j = 0; j < ksteps; ++j) {
-                            const uint32_t a_tmem = tmem_s + c * 128 + (j >> 2) * 64 + (j & 3) * 8;
-                            const uint64_t b_desc =
-                                make_smem_desc(v_addr + (c * 8 + j) * 16 * 128, 64 * 128, 1024, SWZ_128B);
-                            umma_f16_ts(tmem_o + ob * SA_DH, a_tmem, b_desc, idesc_pv, (c | j) != 0 ? 1u : 0u);
-                        }
-                        if (c == k_chunks - 1) {
+                        const uint32_t a0 = tmem_s + c * 128;
+                        const uint64_t b0 = desc_v + static_cast<uint64_t>(c * 8 * (16 * 128 >> 4));
+                        if (c != k_chunks - 1) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                umma_f16_ts(d_o, a0 + (j >> 1) * 32 + (j & 1) * 8, b0 + j * (16 * 128 >> 4), idesc_pv,
+                                            (c | j) != 0 ? 1u : 0u);
+                        } else {
+                            for (int j = 0; j < last_ksteps; ++j)
+                                umma_f16_ts(d_o, a0 + (j >> 1) * 32 + (j & 1) * 8, b0 + j * (16 * 128 >> 4), idesc_pv,
+                                            (c | j) != 0 ? 1u : 0u);
                             umma_commit(o_full + ob);
                             if (qp == q_tiles - 1) umma_commit(v_empty);
                         }
                     }
                     if (t < n_tiles) {
                         // ---- S(t).c = Q(t) K.c^T ----
-                        const int n = t / q_tiles;
-                        const int qt = t - n * q_tiles;
-                        const int slot = t & 3;
-                        const int kb = n & 1;
                         if (c == 0) {
-                            mbar_wait(q_full + slot, (t >> 2) & 1);
-                            if (qt == 0) mbar_wait(k_full + kb, (n >> 1) & 1);
+                            mbar_wait_hot(q_full + slot, (t >> 2) & 1);
+                            if (qt == 0) mbar_wait_hot(k_full + kb, (n >> 1) & 1);
                             tc_fence_after();
                         }
-#pragma unroll
-                        for (int k = 0; k < SA_DH / 16; ++k) {
-                            const uint64_t a_desc =
-                                make_smem_desc(q_addr + slot * SP_CHUNK_BYTES + k * 32, 0, 1024, SWZ_128B);
-                            const uint64_t b_desc = make_smem_desc(
-                                k_addr + kb * SA_KV_BYTES + c * SP_CHUNK_BYTES + k * 32, 0, 1024, SWZ_128B);
-                            umma_f16_ss(tmem_s + c * 128, a_desc, b_desc, idesc_s, k != 0 ? 1u : 0u);
-                        }
+                        const uint64_t kc = k_desc + static_cast<uint64_t>(c * (SP_CHUNK_BYTES >> 4));
+                        umma_f16_ss(tmem_s + c * 128, q_desc, kc, idesc_s, 0u);
+                        umma_f16_ss(tmem_s + c * 128, q_desc + 2, kc + 2, idesc_s, 1u);
+                        umma_f16_ss(tmem_s + c * 128, q_desc + 4, kc + 4, idesc_s, 1u);
+                        umma_f16_ss(tmem_s + c * 128, q_desc + 6, kc + 6, idesc_s, 1u);
                         umma_commit(s_full + c);
                         if (c == k_chunks - 1) {
                             umma_commit(q_empty + slot);
@@ -405,25 +414,27 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
                         }
                     }
                 }
+                qp = qt; np = n;
+                if (++qt == q_tiles) { qt = 0; ++n; }
             }
         }
         __syncwarp();
     } else if (warp >= 4) {
         // ================= softmax + epilogue =================
         const int quad = warp & 3;
-        const int half = (warp - 4) >> 2;
+        const int part = (warp - 4) >> 2;                 // which 32 columns of every 128-key chunk
         const int row = quad * 32 + lane;                 // row inside the q tile == TMEM lane
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t t_row = tmem_s + lane_base + half * 64;   // this thread's 64 columns of chunk 0
+        const uint32_t t_row = tmem_s + lane_base + part * 32;   // this thread's 32 columns of chunk 0
         float inv_prev = 0.0f;
-        int64_t out_prev = -1;                             // element offset of this thread's 32 outputs, -1 = no store
+        int64_t out_prev = -1;                             // element offset of this thread's 16 outputs, -1 = no store
 
         auto epilogue = [&](int tp) {
             const int ob = tp & 1;
             mbar_wait(o_full + ob, (tp >> 1) & 1);
             tc_fence_after();
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_o + ob * SA_DH + lane_base + half * 32, r);
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tmem_o + ob * SA_DH + lane_base + part * 16, r);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -431,7 +442,7 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
             if (out_prev >= 0) {
                 __nv_bfloat16* op = out + out_prev;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 2; ++g) {
                     uint4 o;
                     o.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv_prev, __uint_as_float(r[8 * g + 1]) * inv_prev);
                     o.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv_prev, __uint_as_float(r[8 * g + 3]) * inv_prev);
@@ -442,9 +453,8 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
             }
         };
 
+        int qt = 0, n = 0;
         for (int t = 0; t < n_tiles; ++t) {
-            const int n = t / q_tiles;
-            const int qt = t - n * q_tiles;
             const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
             const int h = item % heads;
             const int bf = item / heads;
@@ -455,75 +465,80 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
             for (int c = 0; c < k_chunks; ++c) {
                 mbar_wait(s_full + c, t & 1);
                 tc_fence_after();
+                const int key0 = c * 128 + part * 32;
+                if (key0 >= tokens) continue;              // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_row + c * 128, r);
+                tmem_ld_wait();
+                if (key0 + 32 <= tokens) {
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const int key0 = c * 128 + half * 64 + b * 32;
-                    if (key0 >= tokens) continue;          // warp-uniform
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_row + c * 128 + b * 32, r);
-                    tmem_ld_wait();
-                    if (key0 + 32 <= tokens) {
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (key0 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
-                    }
+                    for (int j = 0; j < 32; ++j)
+                        if (key0 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
                 }
             }
-            s_max[half * 128 + row] = mx;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            mx = fmaxf(s_max[row], s_max[128 + row]);
+            s_max[part * 128 + row] = mx;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * SP_SM_WARPS) : "memory");
+            mx = fmaxf(fmaxf(s_max[row], s_max[128 + row]), fmaxf(s_max[256 + row], s_max[384 + row]));
             const float mxs = mx * scale_log2;
 
             // ---- deferred epilogue of the previous tile (its PV retired while pass 1 ran) ----
             if (t > 0) epilogue(t - 1);
 
             // ---- pass 2: P = exp2(S*c - max*c) -> bf16 -> TMEM (over the S columns just read), row sums ----
+            // Instruction budget per element (profiles/r1m: the first version spent 7.5, XU and ALU pipes both
+            // saturated): FFMA + MUFU.EX2 + FADD + integer rounding to bf16 (F2FP sits on the XU pipe with the
+            // exponentials).  The denominator sums the unrounded exponentials.
             float sum = 0.0f;
             for (int c = 0; c < k_chunks; ++c) {
-                uint32_t pk[32];
+                uint32_t pk[16];
+                const int key0 = c * 128 + part * 32;
+                if (key0 >= tokens) {                      // warp-uniform: fully masked
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const int key0 = c * 128 + half * 64 + b * 32;
-                    if (key0 >= tokens) {                  // warp-uniform: fully masked batch
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[b * 16 + j] = 0u;
-                        continue;
-                    }
+                    for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                } else {
                     uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_row + c * 128 + b * 32, r);
+                    tmem_ld_32x32b_x32(t_row + c * 128, r);
                     tmem_ld_wait();
-                    const bool full = key0 + 32 <= tokens;
+                    if (key0 + 32 <= tokens) {             // warp-uniform: no masking
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
-                        float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
-                        if (!full) {
-                            if (key0 + 2 * j >= tokens) e0 = 0.0f;
-                            if (key0 + 2 * j + 1 >= tokens) e1 = 0.0f;
+                        for (int j = 0; j < 16; ++j) {
+                            const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+                            const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
+                            sum += e0 + e1;
+                            pk[j] = pack_bf16x2_rne_alu(e0, e1);
                         }
-                        // The PV MMA consumes bf16 P: accumulate the denominator from the rounded values so the
-                        // normalised rows sum to one in the precision actually used.
-                        const uint32_t u = pack_bf16x2(e0, e1);
-                        pk[b * 16 + j] = u;
-                        const float2 f = unpack_bf16x2(u);
-                        sum += f.x + f.y;
+                    } else {
+                        const int nvalid = tokens - key0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+                            float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
+                            if (2 * j >= nvalid) e0 = 0.0f;
+                            if (2 * j + 1 >= nvalid) e1 = 0.0f;
+                            sum += e0 + e1;
+                            pk[j] = pack_bf16x2_rne_alu(e0, e1);
+                        }
                     }
                 }
-                tmem_st_32x32b_x32(t_row + c * 128, pk);   // keys [64*half, 64*half+64) of chunk c -> 32 columns
+                tmem_st_32x32b_x16(t_row + c * 128, pk);   // keys [32*part, 32*part+32) of chunk c -> 16 columns
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full + c);
             }
-            s_sum[half * 128 + row] = sum;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            inv_prev = 1.0f / (s_sum[row] + s_sum[128 + row]);
+            s_sum[part * 128 + row] = sum;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * SP_SM_WARPS) : "memory");
+            const float total = (s_sum[row] + s_sum[128 + row]) + (s_sum[256 + row] + s_sum[384 + row]);
+            inv_prev = 1.0f / total;
             out_prev = (q_idx < tokens)
-                           ? (static_cast<int64_t>(bf) * tokens + q_idx) * inner + h * SA_DH + half * 32
+                           ? (static_cast<int64_t>(bf) * tokens + q_idx) * inner + h * SA_DH + part * 16
                            : -1;
+            if (lse != nullptr && part == 0 && q_idx < tokens)
+                lse[(static_cast<int64_t>(bf) * heads + h) * tokens + q_idx] = mxs + log2f(total);
+            if (++qt == q_tiles) { qt = 0; ++n; }
         }
         if (n_tiles > 0) epilogue(n_tiles - 1);
     }
@@ -613,13 +628,13 @@ attn_spatial_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, 
 
 using namespace istvt;
 
-extern "C" int istvt_attn_spatial_fwd(const void* qkv, void* out, float* probs, int dtype, int batch_frames,
-                                      int tokens, int heads, float scale, istvt_stream_t stream) {
+static int attn_spatial_launch(const void* qkv, void* out, float* probs, float* lse, int dtype, int batch_frames,
+                               int tokens, int heads, float scale, cudaStream_t st) {
     ISTVT_REQUIRE(qkv && out);
     ISTVT_REQUIRE(batch_frames > 0 && tokens > 0 && heads > 0);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int inner = heads * SA_DH;
     if (dtype == ISTVT_F32) {
+        ISTVT_REQUIRE(lse == nullptr);
         const size_t smem = 2 * static_cast<size_t>(tokens) * SA_DH * sizeof(float);
         ISTVT_REQUIRE(smem <= 220 * 1024);
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -649,12 +664,13 @@ extern "C" int istvt_attn_spatial_fwd(const void* qkv, void* out, float* probs, 
                                               SP_SMEM));
         const int items = batch_frames * heads;
         const int grid = items < sm_count() ? items : sm_count();
-        attn_spatial_pipe_kernel<<<grid, SA_THREADS, SP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), tokens,
+        attn_spatial_pipe_kernel<<<grid, SP_THREADS, SP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
                                                                    heads, items, scale_log2);
         count_launch();
         return launch_status();
     }
     // attention-map mode (parity tests, relevance pass): one CTA per (frame, head, query tile), S kept in TMEM
+    ISTVT_REQUIRE(lse == nullptr);
     ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           SA_SMEM));
     const int q_tiles = (tokens + SA_BM - 1) / SA_BM;
@@ -662,4 +678,19 @@ extern "C" int istvt_attn_spatial_fwd(const void* qkv, void* out, float* probs, 
         tm, static_cast<__nv_bfloat16*>(out), probs, tokens, heads, scale_log2);
     count_launch();
     return launch_status();
+}
+
+extern "C" int istvt_attn_spatial_fwd(const void* qkv, void* out, float* probs, int dtype, int batch_frames,
+                                      int tokens, int heads, float scale, istvt_stream_t stream) {
+    return attn_spatial_launch(qkv, out, probs, nullptr, dtype, batch_frames, tokens, heads, scale,
+                               static_cast<cudaStream_t>(stream));
+}
+
+// Training-mode forward: same kernel, additionally writes lse[batch_frames, heads, tokens] (fp32, log2 domain:
+// log2(sum_j exp2(s_ij * scale * log2 e))) for istvt_attn_spatial_bwd.  bf16 only.
+extern "C" int istvt_attn_spatial_fwd_lse(const void* qkv, void* out, float* lse, int batch_frames, int tokens,
+                                          int heads, float scale, istvt_stream_t stream) {
+    ISTVT_REQUIRE(lse != nullptr);
+    return attn_spatial_launch(qkv, out, nullptr, lse, ISTVT_BF16, batch_frames, tokens, heads, scale,
+                               static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,300 @@
+// Backward of the spatial self-attention (network/vivit/module.py:84-91), bf16, flash-attention-2 style on the
+// warp-level tensor-core path (mma.sync m16n8k16 + ldmatrix):
+//   one CTA = (frame, head, block of 128 keys); it keeps dK / dV [128 x 64] in registers and walks the query
+//   blocks of 64 rows:  S = Q K^T,  P = exp2(S * c - lse),  dP = dO V^T,  D = rowsum(dO o O),
+//                       dS = P o (dP - D) * scale,  dV += P^T dO,  dK += dS^T Q,  dQ += dS K
+//   dQ is accumulated across the (up to 3) key blocks with red.global.add.f32 into an fp32 scratch buffer and
+//   converted to bf16 by a second small kernel.
+// P uses the log-sum-exp saved by the forward (istvt_attn_spatial_fwd_lse), so no second softmax pass is needed.
+// (A tcgen05 version is the follow-up; this kernel is ~5 % of the training step.)
+#include "common.cuh"
+#include "simt_util.cuh"
+
+#include <cuda_bf16.h>
+
+namespace istvt {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int SB_DH = 64;
+constexpr int SB_KB = 128;            // keys per CTA
+constexpr int SB_QB = 64;             // queries per iteration
+constexpr int SB_LD = SB_DH + 8;      // smem row pitch (elements) of the [*, 64] tiles: 144 B, conflict-free ldmatrix
+constexpr int SB_LDP = SB_KB + 8;     // pitch of the P / dS tiles: 272 B
+constexpr int SB_THREADS = 256;
+constexpr int SB_SMEM = (2 * SB_KB * SB_LD + 2 * SB_QB * SB_LD + 2 * SB_QB * SB_LDP) * 2 + 2 * SB_QB * 4;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pkbf(float a, float b) {
+    const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+__global__ void __launch_bounds__(SB_THREADS, 1)
+attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ dout,
+                        const float* __restrict__ lse, bf16* __restrict__ dqkv, float* __restrict__ dq_acc,
+                        int tokens, int heads, float scale) {
+    extern __shared__ __align__(16) uint8_t sb_smem[];
+    bf16* sK = reinterpret_cast<bf16*>(sb_smem);          // [128][72]
+    bf16* sV = sK + SB_KB * SB_LD;                        // [128][72]
+    bf16* sQ = sV + SB_KB * SB_LD;                        // [64][72]
+    bf16* sdO = sQ + SB_QB * SB_LD;                       // [64][72]
+    bf16* sP = sdO + SB_QB * SB_LD;                       // [64][136]
+    bf16* sdS = sP + SB_QB * SB_LDP;                      // [64][136]
+    float* sD = reinterpret_cast<float*>(sdS + SB_QB * SB_LDP);   // [64]
+    float* sL = sD + SB_QB;                                        // [64]
+
+    const int k_blocks = (tokens + SB_KB - 1) / SB_KB;
+    const int kb = blockIdx.x % k_blocks;
+    const int h = (blockIdx.x / k_blocks) % heads;
+    const int bf = blockIdx.x / (k_blocks * heads);
+    const int inner = heads * SB_DH;
+    const int64_t row0 = static_cast<int64_t>(bf) * tokens;
+    const int key0 = kb * SB_KB;
+    const float scale_log2 = scale * 1.4426950408889634f;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int lmat = lane >> 3, lr = lane & 7;
+
+    // ---- K / V block -> smem (rows past the frame end are zero) ----
+    for (int idx = tid; idx < SB_KB * 8; idx += SB_THREADS) {
+        const int r = idx >> 3, c = (idx & 7) * 8;
+        uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+        if (key0 + r < tokens) {
+            const bf16* base = qkv + (row0 + key0 + r) * (3 * inner) + h * SB_DH + c;
+            kv = *reinterpret_cast<const uint4*>(base + inner);
+            vv = *reinterpret_cast<const uint4*>(base + 2 * inner);
+        }
+        *reinterpret_cast<uint4*>(sK + r * SB_LD + c) = kv;
+        *reinterpret_cast<uint4*>(sV + r * SB_LD + c) = vv;
+    }
+
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dk[j][e] = 0.f; dv[j][e] = 0.f; }
+
+    const int wm = warp & 3;      // 16-row slab of the query block (S / dP / dQ)
+    const int wn = warp >> 2;     // 64-key half (S / dP), 32-dim half (dQ)
+    const int q_blocks = (tokens + SB_QB - 1) / SB_QB;
+
+    for (int qb = 0; qb < q_blocks; ++qb) {
+        const int q0 = qb * SB_QB;
+        __syncthreads();   // previous iteration's readers of sQ / sdO / sP / sdS are done (also orders the K/V fill)
+        // ---- Q / dO block -> smem, D = rowsum(dO o O), lse ----
+        for (int idx = tid; idx < SB_QB * 8; idx += SB_THREADS) {
+            const int r = idx >> 3, c = (idx & 7) * 8;
+            uint4 qv = make_uint4(0u, 0u, 0u, 0u), dov = qv;
+            if (q0 + r < tokens) {
+                qv = *reinterpret_cast<const uint4*>(qkv + (row0 + q0 + r) * (3 * inner) + h * SB_DH + c);
+                dov = *reinterpret_cast<const uint4*>(dout + (row0 + q0 + r) * inner + h * SB_DH + c);
+            }
+            *reinterpret_cast<uint4*>(sQ + r * SB_LD + c) = qv;
+            *reinterpret_cast<uint4*>(sdO + r * SB_LD + c) = dov;
+        }
+        {
+            const int r = tid >> 2, part = tid & 3;    // 4 threads per row, 16 dims each
+            float acc = 0.f;
+            if (q0 + r < tokens) {
+                float a[8], b[8];
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    load8(dout + (row0 + q0 + r) * inner + h * SB_DH + part * 16 + hlf * 8, a);
+                    load8(o + (row0 + q0 + r) * inner + h * SB_DH + part * 16 + hlf * 8, b);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc = fmaf(a[e], b[e], acc);
+                }
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (part == 0) {
+                sD[r] = acc;
+                sL[r] = (q0 + r < tokens) ? lse[(static_cast<int64_t>(bf) * heads + h) * tokens + q0 + r] : INFINITY;
+            }
+        }
+        __syncthreads();
+
+        // ---- S = Q K^T and dP = dO V^T for this warp's 16 x 64 sub-tile ----
+        float s[8][4], dp[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s[j][e] = 0.f; dp[j][e] = 0.f; }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t aq[4], ao[4];
+            ldsm_x4(aq, sQ + (wm * 16 + (lmat & 1) * 8 + lr) * SB_LD + kk * 16 + (lmat >> 1) * 8);
+            ldsm_x4(ao, sdO + (wm * 16 + (lmat & 1) * 8 + lr) * SB_LD + kk * 16 + (lmat >> 1) * 8);
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {       // two 8-key n-tiles per ldmatrix.x4
+                uint32_t bk[4], bv[4];
+                const int krow = wn * 64 + jp * 16 + (lmat >> 1) * 8 + lr;
+                ldsm_x4(bk, sK + krow * SB_LD + kk * 16 + (lmat & 1) * 8);
+                ldsm_x4(bv, sV + krow * SB_LD + kk * 16 + (lmat & 1) * 8);
+                mma16816(s[2 * jp], aq, bk[0], bk[1]);
+                mma16816(s[2 * jp + 1], aq, bk[2], bk[3]);
+                mma16816(dp[2 * jp], ao, bv[0], bv[1]);
+                mma16816(dp[2 * jp + 1], ao, bv[2], bv[3]);
+            }
+        }
+        // ---- P, dS -> smem (bf16) ----
+        {
+            const int r0 = wm * 16 + g, r1 = r0 + 8;
+            const float l0 = sL[r0], l1 = sL[r1];
+            const float d0 = sD[r0], d1 = sD[r1];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kl = wn * 64 + j * 8 + 2 * t;          // key inside the block
+                const bool ok0 = key0 + kl < tokens, ok1 = key0 + kl + 1 < tokens;
+                float p00 = ok0 ? exp2f(fmaf(s[j][0], scale_log2, -l0)) : 0.f;
+                float p01 = ok1 ? exp2f(fmaf(s[j][1], scale_log2, -l0)) : 0.f;
+                float p10 = ok0 ? exp2f(fmaf(s[j][2], scale_log2, -l1)) : 0.f;
+                float p11 = ok1 ? exp2f(fmaf(s[j][3], scale_log2, -l1)) : 0.f;
+                *reinterpret_cast<uint32_t*>(sP + r0 * SB_LDP + kl) = pkbf(p00, p01);
+                *reinterpret_cast<uint32_t*>(sP + r1 * SB_LDP + kl) = pkbf(p10, p11);
+                *reinterpret_cast<uint32_t*>(sdS + r0 * SB_LDP + kl) =
+                    pkbf(p00 * (dp[j][0] - d0) * scale, p01 * (dp[j][1] - d0) * scale);
+                *reinterpret_cast<uint32_t*>(sdS + r1 * SB_LDP + kl) =
+                    pkbf(p10 * (dp[j][2] - d1) * scale, p11 * (dp[j][3] - d1) * scale);
+            }
+        }
+        __syncthreads();
+
+        // ---- dV += P^T dO, dK += dS^T Q: this warp owns keys [16 warp, 16 warp + 16) x 64 dims ----
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {           // 16 queries per step
+            uint32_t ap[4], as_[4];
+            // A[m = key][k = query] = X[query][key]: transposed 8x8 loads
+            ldsm_x4_t(ap, sP + (kk * 16 + (lmat >> 1) * 8 + lr) * SB_LDP + warp * 16 + (lmat & 1) * 8);
+            ldsm_x4_t(as_, sdS + (kk * 16 + (lmat >> 1) * 8 + lr) * SB_LDP + warp * 16 + (lmat & 1) * 8);
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {       // two 8-dim n-tiles per ldmatrix.x4
+                uint32_t bo[4], bq[4];
+                // B[k = query][n = dim] = X[query][dim]: rows are k -> transposed loads
+                ldsm_x4_t(bo, sdO + (kk * 16 + (lmat & 1) * 8 + lr) * SB_LD + jp * 16 + (lmat >> 1) * 8);
+                ldsm_x4_t(bq, sQ + (kk * 16 + (lmat & 1) * 8 + lr) * SB_LD + jp * 16 + (lmat >> 1) * 8);
+                mma16816(dv[2 * jp], ap, bo[0], bo[1]);
+                mma16816(dv[2 * jp + 1], ap, bo[2], bo[3]);
+                mma16816(dk[2 * jp], as_, bq[0], bq[1]);
+                mma16816(dk[2 * jp + 1], as_, bq[2], bq[3]);
+            }
+        }
+        // ---- dQ partial = dS K for rows [16 wm, +16) x dims [32 wn, +32), accumulated across key blocks ----
+        {
+            float dq[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dq[j][e] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {       // 16 keys per step
+                uint32_t a[4];
+                ldsm_x4(a, sdS + (wm * 16 + (lmat & 1) * 8 + lr) * SB_LDP + kk * 16 + (lmat >> 1) * 8);
+#pragma unroll
+                for (int jp = 0; jp < 2; ++jp) {
+                    uint32_t b[4];
+                    ldsm_x4_t(b, sK + (kk * 16 + (lmat & 1) * 8 + lr) * SB_LD + wn * 32 + jp * 16 + (lmat >> 1) * 8);
+                    mma16816(dq[2 * jp], a, b[0], b[1]);
+                    mma16816(dq[2 * jp + 1], a, b[2], b[3]);
+                }
+            }
+            const int r0 = q0 + wm * 16 + g, r1 = r0 + 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int d = h * SB_DH + wn * 32 + j * 8 + 2 * t;
+                if (r0 < tokens) {
+                    float* dst = dq_acc + (row0 + r0) * inner + d;
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(dq[j][0]), "f"(dq[j][1]) : "memory");
+                }
+                if (r1 < tokens) {
+                    float* dst = dq_acc + (row0 + r1) * inner + d;
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(dq[j][2]), "f"(dq[j][3]) : "memory");
+                }
+            }
+        }
+    }
+
+    // ---- dK, dV -> dqkv (k columns at inner, v columns at 2 inner) ----
+    {
+        const int r0 = key0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int d = h * SB_DH + j * 8 + 2 * t;
+            if (r0 < tokens) {
+                bf16* base = dqkv + (row0 + r0) * (3 * inner) + d;
+                *reinterpret_cast<uint32_t*>(base + inner) = pkbf(dk[j][0], dk[j][1]);
+                *reinterpret_cast<uint32_t*>(base + 2 * inner) = pkbf(dv[j][0], dv[j][1]);
+            }
+            if (r1 < tokens) {
+                bf16* base = dqkv + (row0 + r1) * (3 * inner) + d;
+                *reinterpret_cast<uint32_t*>(base + inner) = pkbf(dk[j][2], dk[j][3]);
+                *reinterpret_cast<uint32_t*>(base + 2 * inner) = pkbf(dv[j][2], dv[j][3]);
+            }
+        }
+    }
+}
+
+// dq_acc fp32 [rows, inner] -> q columns of dqkv [rows, 3 inner] (bf16)
+__global__ void __launch_bounds__(256)
+attn_spatial_bwd_dq_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv, int64_t rows, int inner) {
+    const int c8 = inner >> 3;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= rows * c8) return;
+    const int64_t r = idx / c8;
+    const int c = static_cast<int>(idx - r * c8) * 8;
+    float v[8];
+    load8(dq_acc + r * inner + c, v);
+    store8(dqkv + r * (3 * inner) + c, v);
+}
+
+}  // namespace istvt
+
+using namespace istvt;
+
+// qkv: bf16 [batch_frames*tokens, 3*heads*64]; o, dout: bf16 [rows, heads*64]; lse: fp32 [batch_frames, heads, tokens]
+// (log2 domain, from istvt_attn_spatial_fwd_lse); dqkv: bf16 [rows, 3*heads*64] (fully written);
+// dq_scratch: fp32 [rows, heads*64] workspace (zero-filled by this call).
+extern "C" int istvt_attn_spatial_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
+                                      float* dq_scratch, int batch_frames, int tokens, int heads, float scale,
+                                      istvt_stream_t stream) {
+    ISTVT_REQUIRE(qkv && o && dout && lse && dqkv && dq_scratch);
+    ISTVT_REQUIRE(batch_frames > 0 && tokens > 0 && heads > 0);
+    ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(dout) |
+                    reinterpret_cast<uintptr_t>(dqkv) | reinterpret_cast<uintptr_t>(dq_scratch)) & 15) == 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int inner = heads * SB_DH;
+    const int64_t rows = static_cast<int64_t>(batch_frames) * tokens;
+    ISTVT_CHECK_CUDA(cudaMemsetAsync(dq_scratch, 0, static_cast<size_t>(rows) * inner * sizeof(float), st));
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
+    const int k_blocks = (tokens + SB_KB - 1) / SB_KB;
+    const int64_t grid = static_cast<int64_t>(batch_frames) * heads * k_blocks;
+    ISTVT_REQUIRE(grid < (int64_t(1) << 31));
+    attn_spatial_bwd_kernel<<<static_cast<unsigned>(grid), SB_THREADS, SB_SMEM, st>>>(
+        static_cast<const bf16*>(qkv), static_cast<const bf16*>(o), static_cast<const bf16*>(dout), lse,
+        static_cast<bf16*>(dqkv), dq_scratch, tokens, heads, scale);
+    count_launch();
+    const int64_t n = rows * (inner / 8);
+    attn_spatial_bwd_dq_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(dq_scratch,
+                                                                                       static_cast<bf16*>(dqkv), rows, inner);
+    count_launch();
+    return launch_status();
+}

@@ -239,6 +239,137 @@ attn_temporal_mma_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward of the temporal attention for F <= 8 frames, same one-warp-per-(clip, position, head) mma.sync
+// scheme as the forward (everything stays in registers; probabilities are recomputed):
+//   S = Q K^T, P = softmax(S * scale), dP = dO V^T, D_i = sum_j P_ij dP_ij, dS = P o (dP - D) * scale
+//   dV = P^T dO,  dQ = dS K,  dK = dS^T Q
+// P^T and dS^T come from movmatrix (8x8 b16 transpose across the warp); the B operands whose k index is the
+// frame ({X[2t][d], X[2t+1][d]}) are byte-permutes of two 16-byte row loads, as for V in the forward.
+// dqk: [rows, 2*heads*64] (dQ columns then dK columns), dv: [rows, heads*64].
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+
+__global__ void __launch_bounds__(256)
+attn_temporal_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
+                             const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqk,
+                             __nv_bfloat16* __restrict__ dv, int frames, int tokens, int heads, float scale,
+                             int64_t units) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int64_t unit = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (unit >= units) return;
+    const int h = static_cast<int>(unit % heads);
+    const int64_t bp = unit / heads;
+    const int64_t b = bp / tokens;
+    const int pos = static_cast<int>(bp - b * tokens);
+    const int inner = heads * TA_DH;
+    const int64_t row0 = b * frames * tokens + pos;
+    const float scale_log2 = scale * 1.4426950408889634f;
+
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    // pattern A: row g, 16-byte chunks t and t+4 of the head's 64 dims
+    uint4 qa0 = zero, qa1 = zero, ka0 = zero, ka1 = zero, va0 = zero, va1 = zero, oa0 = zero, oa1 = zero;
+    if (g < frames) {
+        const int64_t r = row0 + static_cast<int64_t>(g) * tokens;
+        const __nv_bfloat16* qp = qk + r * (2 * inner) + h * TA_DH;
+        const __nv_bfloat16* vp = v + r * inner + h * TA_DH;
+        const __nv_bfloat16* op = dout + r * inner + h * TA_DH;
+        qa0 = ldg_nc_u4(qp + 8 * t);         qa1 = ldg_nc_u4(qp + 8 * (t + 4));
+        ka0 = ldg_nc_u4(qp + inner + 8 * t); ka1 = ldg_nc_u4(qp + inner + 8 * (t + 4));
+        va0 = ldg_nc_u4(vp + 8 * t);         va1 = ldg_nc_u4(vp + 8 * (t + 4));
+        oa0 = ldg_nc_u4(op + 8 * t);         oa1 = ldg_nc_u4(op + 8 * (t + 4));
+    }
+    // pattern B: rows 2t and 2t+1, dims [8g, 8g+8)
+    uint4 qb0 = zero, qb1 = zero, kb0 = zero, kb1 = zero, ob0 = zero, ob1 = zero;
+    if (2 * t < frames) {
+        const int64_t r = row0 + static_cast<int64_t>(2 * t) * tokens;
+        qb0 = ldg_nc_u4(qk + r * (2 * inner) + h * TA_DH + 8 * g);
+        kb0 = ldg_nc_u4(qk + r * (2 * inner) + inner + h * TA_DH + 8 * g);
+        ob0 = ldg_nc_u4(dout + r * inner + h * TA_DH + 8 * g);
+    }
+    if (2 * t + 1 < frames) {
+        const int64_t r = row0 + static_cast<int64_t>(2 * t + 1) * tokens;
+        qb1 = ldg_nc_u4(qk + r * (2 * inner) + h * TA_DH + 8 * g);
+        kb1 = ldg_nc_u4(qk + r * (2 * inner) + inner + h * TA_DH + 8 * g);
+        ob1 = ldg_nc_u4(dout + r * inner + h * TA_DH + 8 * g);
+    }
+
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(s, qa0.x, 0u, qa0.y, 0u, ka0.x, ka0.y);
+    mma_bf16_16816(s, qa0.z, 0u, qa0.w, 0u, ka0.z, ka0.w);
+    mma_bf16_16816(s, qa1.x, 0u, qa1.y, 0u, ka1.x, ka1.y);
+    mma_bf16_16816(s, qa1.z, 0u, qa1.w, 0u, ka1.z, ka1.w);
+    mma_bf16_16816(dp, oa0.x, 0u, oa0.y, 0u, va0.x, va0.y);
+    mma_bf16_16816(dp, oa0.z, 0u, oa0.w, 0u, va0.z, va0.w);
+    mma_bf16_16816(dp, oa1.x, 0u, oa1.y, 0u, va1.x, va1.y);
+    mma_bf16_16816(dp, oa1.z, 0u, oa1.w, 0u, va1.z, va1.w);
+
+    const float s0 = (2 * t < frames) ? s[0] * scale_log2 : -INFINITY;
+    const float s1 = (2 * t + 1 < frames) ? s[1] * scale_log2 : -INFINITY;
+    float mx = fmaxf(s0, s1);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float p0, p1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(s0 - mx));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(s1 - mx));
+    float sum = p0 + p1;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.0f / sum;
+    p0 *= inv; p1 *= inv;
+    float dsum = p0 * dp[0] + p1 * dp[1];
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+    const float ds0 = p0 * (dp[0] - dsum) * scale;
+    const float ds1 = p1 * (dp[1] - dsum) * scale;
+    auto pk = [](float x, float y) {
+        const __nv_bfloat162 r = __floats2bfloat162_rn(x, y);
+        return *reinterpret_cast<const uint32_t*>(&r);
+    };
+    const uint32_t pp = pk(p0, p1);
+    const uint32_t dsp = pk(ds0, ds1);
+    const uint32_t ppT = movmatrix_trans(pp);
+    const uint32_t dsT = movmatrix_trans(dsp);
+
+    const uint32_t wq0[4] = {qb0.x, qb0.y, qb0.z, qb0.w}, wq1[4] = {qb1.x, qb1.y, qb1.z, qb1.w};
+    const uint32_t wk0[4] = {kb0.x, kb0.y, kb0.z, kb0.w}, wk1[4] = {kb1.x, kb1.y, kb1.z, kb1.w};
+    const uint32_t wo0[4] = {ob0.x, ob0.y, ob0.z, ob0.w}, wo1[4] = {ob1.x, ob1.y, ob1.z, ob1.w};
+    float dq_lo[8], dq_hi[8], dk_lo[8], dk_hi[8], dv_lo[8], dv_hi[8];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t sel = (nt & 1) ? 0x7632 : 0x5410;
+        float d[4];
+        d[0] = d[1] = d[2] = d[3] = 0.f;
+        mma_bf16_16816(d, ppT, 0u, 0u, 0u, __byte_perm(wo0[nt >> 1], wo1[nt >> 1], sel), 0u);   // dV = P^T dO
+        dv_lo[nt] = d[0]; dv_hi[nt] = d[1];
+        d[0] = d[1] = d[2] = d[3] = 0.f;
+        mma_bf16_16816(d, dsp, 0u, 0u, 0u, __byte_perm(wk0[nt >> 1], wk1[nt >> 1], sel), 0u);   // dQ = dS K
+        dq_lo[nt] = d[0]; dq_hi[nt] = d[1];
+        d[0] = d[1] = d[2] = d[3] = 0.f;
+        mma_bf16_16816(d, dsT, 0u, 0u, 0u, __byte_perm(wq0[nt >> 1], wq1[nt >> 1], sel), 0u);   // dK = dS^T Q
+        dk_lo[nt] = d[0]; dk_hi[nt] = d[1];
+    }
+    if (g < frames) {
+        const int64_t r = row0 + static_cast<int64_t>(g) * tokens;
+        auto store16 = [&](__nv_bfloat16* dst, const float (&lo)[8], const float (&hi)[8]) {
+            uint4 a, c;
+            a.x = pk(lo[0], lo[1]); a.y = pk(lo[2], lo[3]); a.z = pk(lo[4], lo[5]); a.w = pk(lo[6], lo[7]);
+            c.x = pk(hi[0], hi[1]); c.y = pk(hi[2], hi[3]); c.z = pk(hi[4], hi[5]); c.w = pk(hi[6], hi[7]);
+            *reinterpret_cast<uint4*>(dst) = a;
+            *reinterpret_cast<uint4*>(dst + 8) = c;
+        };
+        store16(dqk + r * (2 * inner) + h * TA_DH + 16 * t, dq_lo, dq_hi);
+        store16(dqk + r * (2 * inner) + inner + h * TA_DH + 16 * t, dk_lo, dk_hi);
+        store16(dv + r * inner + h * TA_DH + 16 * t, dv_lo, dv_hi);
+    }
+}
+
 template <typename T>
 static int launch_temporal(const void* qk, const void* v, void* out, float* probs, int batch, int frames,
                            int tokens, int heads, float scale, cudaStream_t st) {
@@ -281,4 +412,22 @@ extern "C" int istvt_attn_temporal_fwd(const void* qk, const void* v, void* out,
         return launch_temporal<__nv_bfloat16>(qk, v, out, probs, batch, frames, tokens, heads, scale, st);
     if (dtype == ISTVT_F32) return launch_temporal<float>(qk, v, out, probs, batch, frames, tokens, heads, scale, st);
     return ISTVT_ERR_INVALID_ARG;
+}
+
+extern "C" int istvt_attn_temporal_bwd(const void* qk, const void* v, const void* dout, void* dqk, void* dv, int batch,
+                                       int frames, int tokens, int heads, float scale, istvt_stream_t stream) {
+    ISTVT_REQUIRE(qk && v && dout && dqk && dv);
+    ISTVT_REQUIRE(batch > 0 && frames > 0 && tokens > 0 && heads > 0);
+    if (frames > 8) return ISTVT_ERR_UNSUPPORTED;   // training is built for the ISTVT configuration (T = 6, F = 7)
+    ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dout) |
+                    reinterpret_cast<uintptr_t>(dqk) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0);
+    const int64_t units = static_cast<int64_t>(batch) * tokens * heads;
+    const int64_t grid = (units + 7) / 8;
+    ISTVT_REQUIRE(grid < (int64_t(1) << 31));
+    attn_temporal_bwd_mma_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v),
+        static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv),
+        frames, tokens, heads, scale, units);
+    count_launch();
+    return launch_status();
 }

@@ -1,0 +1,493 @@
+// Backward / training-step kernels of the transformer part that are HBM-bound SIMT work:
+//   LayerNorm backward (+ the temporal self-subtract backward, + residual-gradient accumulation),
+//   erf-GELU forward / backward, fp32 -> bf16 cast, [M, C] -> [C, M] transpose with column sums (operands of
+//   the weight-gradient GEMMs and the bias gradients), head / token-build backward, AdamW.
+// They back `loss.backward()` / `optimizer.step()` of the reference's training loop (train_CNN.py:513-533) for the
+// modules of network/vivit/module.py and network/vivit/vivit.py; each entry point cites the forward lines.
+#include "common.cuh"
+#include "simt_util.cuh"
+
+#include <cuda_bf16.h>
+
+namespace istvt {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const bf16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+    const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pk2(v[0], v[1]), pk2(v[2], v[3]));
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm backward, one warp per row, the row in registers (dim <= 768, dim % 4 == 0).
+//   x^ = (x - mean) * rstd;  a = gamma * dy;  dx = rstd * (a - mean(a) - x^ * mean(a * x^))
+//   dgamma += sum_rows dy * x^;  dbeta += sum_rows dy          (per-lane partials -> smem -> global atomics)
+// dy_total = dy + dy2[row] - dy2[row + tokens] for frames 1..F-2 when dy2 != NULL: the backward of
+//   res = cat(xn[:, :2], xn[:, 2:] - xn[:, 1:-1]) (module.py:192) fused in front of LN1's backward.
+// ACCUM: g (fp32 residual-stream gradient) += dx, optional bf16 copy of the updated g (the next GEMM's operand).
+// ------------------------------------------------------------------------------------------
+constexpr int LNB_MAXC = 6;
+template <typename TX, bool ACCUM>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, int frames, int tokens_pf,
+                     const TX* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ g,
+                     bf16* __restrict__ g_bf, bf16* __restrict__ dx_out, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int64_t rows, int dim, float eps) {
+    __shared__ float s_dg[768], s_db[768];
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int nch = dim >> 2;
+    const float inv_dim = 1.0f / static_cast<float>(dim);
+    float dg[LNB_MAXC][4], db[LNB_MAXC][4];
+#pragma unroll
+    for (int i = 0; i < LNB_MAXC; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dg[i][e] = 0.f; db[i][e] = 0.f; }
+
+    const int64_t wid = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t wstride = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+    for (int64_t row = wid; row < rows; row += wstride) {
+        float xv[LNB_MAXC][4], dv[LNB_MAXC][4];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nch) {
+                ld4(x + row * dim + 4 * c, xv[i]);
+                s += xv[i][0] + xv[i][1] + xv[i][2] + xv[i][3];
+            } else {
+                xv[i][0] = xv[i][1] = xv[i][2] = xv[i][3] = 0.f;
+            }
+        }
+        const float mean = warp_sum(s) * inv_dim;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nch) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float d = xv[i][e] - mean; sq = fmaf(d, d, sq); }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * inv_dim + eps);
+        bool sub_next = false;
+        if (dy2 != nullptr) {
+            const int f = static_cast<int>((row / tokens_pf) % frames);
+            sub_next = f >= 1 && f <= frames - 2;
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nch) {
+                ld4(dy + row * dim + 4 * c, dv[i]);
+                if (dy2 != nullptr) {
+                    float t[4];
+                    ld4(dy2 + row * dim + 4 * c, t);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dv[i][e] += t[e];
+                    if (sub_next) {
+                        ld4(dy2 + (row + tokens_pf) * dim + 4 * c, t);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) dv[i][e] -= t[e];
+                    }
+                }
+                float gm[4];
+                ld4(gamma + 4 * c, gm);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float xh = (xv[i][e] - mean) * rstd;
+                    xv[i][e] = xh;
+                    const float a = gm[e] * dv[i][e];
+                    s1 += a;
+                    s2 = fmaf(a, xh, s2);
+                    dg[i][e] = fmaf(dv[i][e], xh, dg[i][e]);
+                    db[i][e] += dv[i][e];
+                    dv[i][e] = a;
+                }
+            }
+        }
+        s1 = warp_sum(s1) * inv_dim;
+        s2 = warp_sum(s2) * inv_dim;
+#pragma unroll
+        for (int i = 0; i < LNB_MAXC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nch) {
+                float dx[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dx[e] = rstd * (dv[i][e] - s1 - xv[i][e] * s2);
+                if (ACCUM) {
+                    float gv[4];
+                    ld4(g + row * dim + 4 * c, gv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) gv[e] += dx[e];
+                    st4(g + row * dim + 4 * c, gv);
+                    if (g_bf != nullptr) st4(g_bf + row * dim + 4 * c, gv);
+                } else {
+                    st4(dx_out + row * dim + 4 * c, dx);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LNB_MAXC; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nch) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                atomicAdd(&s_dg[4 * c + e], dg[i][e]);
+                atomicAdd(&s_db[4 * c + e], db[i][e]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        atomicAdd(dgamma + i, s_dg[i]);
+        atomicAdd(dbeta + i, s_db[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact-erf GELU (nn.GELU(), module.py:28), elementwise on bf16: forward and backward
+//   gelu'(x) = 0.5 * (1 + erf(x / sqrt 2)) + x * exp(-x^2 / 2) / sqrt(2 pi)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t n8) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    float v[8];
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.0f + erff(v[e] * 0.70710678118654752440f));
+    store8(y + i * 8, v);
+}
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, int64_t n8) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    float v[8], d[8];
+    load8(x + i * 8, v);
+    load8(dy + i * 8, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float cdf = 0.5f * (1.0f + erff(v[e] * 0.70710678118654752440f));
+        const float pdf = 0.3989422804014327f * __expf(-0.5f * v[e] * v[e]);
+        d[e] *= fmaf(v[e], pdf, cdf);
+    }
+    store8(dx + i * 8, d);
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n4) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float v[4];
+    ld4(x + i * 4, v);
+    st4(y + i * 4, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// out[c, m] = in[m, c] (bf16), out row pitch ldo >= M (pad columns are written as zero), optional
+// colsum[c] += sum_m in[m, c] (the bias gradient of the Linear whose dY is being transposed).
+// 64 x 64 tiles through shared memory; both global sides move 16-byte vectors.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transpose_colsum_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, float* __restrict__ colsum, int64_t M,
+                        int C, int64_t ldo) {
+    __shared__ bf16 tile[64][72];
+    const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 64;
+    const int c0 = blockIdx.y * 64;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int idx = tid + it * 256;          // 512 chunks of 8 columns
+        const int r = idx >> 3, cc = (idx & 7) * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (m0 + r < M && c0 + cc < C) v = *reinterpret_cast<const uint4*>(in + (m0 + r) * C + c0 + cc);
+        *reinterpret_cast<uint4*>(&tile[r][cc]) = v;
+    }
+    __syncthreads();
+    if (colsum != nullptr && tid < 64 && c0 + tid < C) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) s += __bfloat162float(tile[r][tid]);
+        atomicAdd(colsum + c0 + tid, s);
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int idx = tid + it * 256;
+        const int c = idx >> 3, mm = (idx & 7) * 8;   // output row c, 8 consecutive m
+        if (c0 + c < C && m0 + mm < ldo) {
+            bf16 tmp[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) tmp[e] = tile[mm + e][c];
+            *reinterpret_cast<uint4*>(out + static_cast<int64_t>(c0 + c) * ldo + m0 + mm) =
+                *reinterpret_cast<const uint4*>(tmp);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Head backward (vivit.py:101 restricted to token (0,0), vivit.py:144-148): one warp per clip.
+// Writes the residual-stream gradient of token (0,0) (the caller zero-fills the rest of g) and accumulates the
+// gradients of transformer.norm, mlp_head LayerNorm and mlp_head Linear.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+head_bwd_kernel(const float* __restrict__ tokens, int64_t rows_per_clip, const float* __restrict__ dlogits,
+                const float* __restrict__ ng, const float* __restrict__ nb, const float* __restrict__ hg,
+                const float* __restrict__ hb, const float* __restrict__ hw, float* __restrict__ g,
+                float* __restrict__ d_ng, float* __restrict__ d_nb, float* __restrict__ d_hg, float* __restrict__ d_hb,
+                float* __restrict__ d_hw, float* __restrict__ d_hbias, int dim, float eps) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const float* x = tokens + static_cast<int64_t>(b) * rows_per_clip * dim;
+    float* gx = g + static_cast<int64_t>(b) * rows_per_clip * dim;
+    const float inv = 1.0f / dim;
+    const float dz = dlogits[b];
+    float s = 0.f;
+    for (int i = lane; i < dim; i += 32) s += x[i];
+    const float m1 = warp_sum(s) * inv;
+    s = 0.f;
+    for (int i = lane; i < dim; i += 32) { const float d = x[i] - m1; s = fmaf(d, d, s); }
+    const float r1 = rsqrtf(warp_sum(s) * inv + eps);
+    s = 0.f;
+    for (int i = lane; i < dim; i += 32) s += (x[i] - m1) * r1 * ng[i] + nb[i];
+    const float m2 = warp_sum(s) * inv;
+    s = 0.f;
+    for (int i = lane; i < dim; i += 32) { const float d = (x[i] - m1) * r1 * ng[i] + nb[i] - m2; s = fmaf(d, d, s); }
+    const float r2 = rsqrtf(warp_sum(s) * inv + eps);
+    // through mlp_head: z = sum(w * hw) + bias, w = uh * hg + hb
+    float a_s1 = 0.f, a_s2 = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const float u = (x[i] - m1) * r1 * ng[i] + nb[i];
+        const float uh = (u - m2) * r2;
+        const float w = uh * hg[i] + hb[i];
+        const float dw = dz * hw[i];
+        atomicAdd(d_hw + i, dz * w);
+        atomicAdd(d_hg + i, dw * uh);
+        atomicAdd(d_hb + i, dw);
+        const float a = dw * hg[i];
+        a_s1 += a;
+        a_s2 = fmaf(a, uh, a_s2);
+    }
+    if (lane == 0) atomicAdd(d_hbias, dz);
+    a_s1 = warp_sum(a_s1) * inv;
+    a_s2 = warp_sum(a_s2) * inv;
+    float b_s1 = 0.f, b_s2 = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const float xh = (x[i] - m1) * r1;
+        const float u = xh * ng[i] + nb[i];
+        const float uh = (u - m2) * r2;
+        const float du = r2 * (dz * hw[i] * hg[i] - a_s1 - uh * a_s2);
+        atomicAdd(d_ng + i, du * xh);
+        atomicAdd(d_nb + i, du);
+        const float a = du * ng[i];
+        b_s1 += a;
+        b_s2 = fmaf(a, xh, b_s2);
+    }
+    b_s1 = warp_sum(b_s1) * inv;
+    b_s2 = warp_sum(b_s2) * inv;
+    for (int i = lane; i < dim; i += 32) {
+        const float xh = (x[i] - m1) * r1;
+        const float u = xh * ng[i] + nb[i];
+        const float uh = (u - m2) * r2;
+        const float du = r2 * (dz * hw[i] * hg[i] - a_s1 - uh * a_s2);
+        gx[i] = r1 * (du * ng[i] - b_s1 - xh * b_s2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Token-build backward (vivit.py:136-140): g is the gradient of the token buffer [B, T+1, P, D].
+//   d pos_embedding[t, p, :] = sum_b g[b, t+1, p, :]          (all P positions, incl. the space token)
+//   d space_token           = sum_{b, t} g[b, t+1, 0, :]
+//   d temporal_token        = sum_{b, p} g[b, 0, p, :]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+token_bwd_pos_kernel(const float* __restrict__ g, float* __restrict__ dpos, float* __restrict__ dspace, int batch,
+                     int t_frames, int tpf, int dim) {
+    const int d4 = dim >> 2;
+    const int64_t total = static_cast<int64_t>(t_frames) * tpf * d4;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % d4);
+    const int64_t tp = idx / d4;                 // t * tpf + p
+    const int p = static_cast<int>(tp % tpf);
+    const int t = static_cast<int>(tp / tpf);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int b = 0; b < batch; ++b) {
+        float v[4];
+        ld4(g + ((static_cast<int64_t>(b) * (t_frames + 1) + t + 1) * tpf + p) * dim + 4 * c, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += v[e];
+    }
+    float* o = dpos + tp * dim + 4 * c;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] += acc[e];
+    if (p == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicAdd(dspace + 4 * c + e, acc[e]);
+    }
+}
+__global__ void __launch_bounds__(256)
+token_bwd_temporal_kernel(const float* __restrict__ g, float* __restrict__ dtemporal, int t_frames, int tpf, int dim) {
+    const int b = blockIdx.x;
+    const float* base = g + static_cast<int64_t>(b) * (t_frames + 1) * tpf * dim;   // frame 0 of clip b
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+        float acc = 0.f;
+        for (int p = 0; p < tpf; ++p) acc += base[static_cast<int64_t>(p) * dim + c];
+        atomicAdd(dtemporal + c, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// AdamW, torch.optim.AdamW semantics (train_CNN.py:199): decoupled weight decay, bias-corrected moments.
+// One launch over a flat fp32 parameter / gradient / moment buffer.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             int64_t n4, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+             float grad_scale) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float pv[4], gv[4], mv[4], vv[4];
+    ld4(p + 4 * i, pv); ld4(g + 4 * i, gv); ld4(m + 4 * i, mv); ld4(v + 4 * i, vv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float gr = gv[e] * grad_scale;
+        pv[e] *= 1.0f - lr * wd;
+        mv[e] = beta1 * mv[e] + (1.0f - beta1) * gr;
+        vv[e] = beta2 * vv[e] + (1.0f - beta2) * gr * gr;
+        const float denom = sqrtf(vv[e]) / bc2_sqrt + eps;
+        pv[e] -= (lr / bc1) * (mv[e] / denom);
+    }
+    st4(p + 4 * i, pv); st4(m + 4 * i, mv); st4(v + 4 * i, vv);
+}
+
+static inline unsigned nblk(int64_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+}  // namespace istvt
+
+using namespace istvt;
+
+extern "C" int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, int tokens_per_frame, const void* x,
+                                   int x_dtype, const float* gamma, float* g_accum, void* g_bf16, void* dx_out,
+                                   float* dgamma, float* dbeta, int64_t rows, int dim, float eps,
+                                   istvt_stream_t stream) {
+    ISTVT_REQUIRE(dy && x && gamma && dgamma && dbeta && rows > 0);
+    ISTVT_REQUIRE(dim % 4 == 0 && dim <= 768);
+    ISTVT_REQUIRE((g_accum != nullptr) != (dx_out != nullptr));
+    ISTVT_REQUIRE(dy2 == nullptr || (frames > 0 && tokens_per_frame > 0));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int64_t blocks = (rows + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+    if (blocks > cap) blocks = cap;
+    const bf16* d1 = static_cast<const bf16*>(dy);
+    const bf16* d2 = static_cast<const bf16*>(dy2);
+    bf16* gb = static_cast<bf16*>(g_bf16);
+    bf16* dxo = static_cast<bf16*>(dx_out);
+    const unsigned gr = static_cast<unsigned>(blocks);
+    if (x_dtype == ISTVT_F32) {
+        const float* xx = static_cast<const float*>(x);
+        if (g_accum)
+            layernorm_bwd_kernel<float, true><<<gr, 256, 0, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
+                                                                   nullptr, dgamma, dbeta, rows, dim, eps);
+        else
+            layernorm_bwd_kernel<float, false><<<gr, 256, 0, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
+                                                                    nullptr, dxo, dgamma, dbeta, rows, dim, eps);
+    } else if (x_dtype == ISTVT_BF16) {
+        const bf16* xx = static_cast<const bf16*>(x);
+        if (g_accum)
+            layernorm_bwd_kernel<bf16, true><<<gr, 256, 0, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
+                                                                  nullptr, dgamma, dbeta, rows, dim, eps);
+        else
+            layernorm_bwd_kernel<bf16, false><<<gr, 256, 0, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
+                                                                   nullptr, dxo, dgamma, dbeta, rows, dim, eps);
+    } else {
+        return ISTVT_ERR_INVALID_ARG;
+    }
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_gelu_fwd(const void* x, void* y, int64_t n, istvt_stream_t stream) {
+    ISTVT_REQUIRE(x && y && n > 0 && n % 8 == 0);
+    gelu_fwd_kernel<<<nblk(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(x), static_cast<bf16*>(y), n / 8);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, istvt_stream_t stream) {
+    ISTVT_REQUIRE(dy && x && dx && n > 0 && n % 8 == 0);
+    gelu_bwd_kernel<<<nblk(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(dy), static_cast<const bf16*>(x), static_cast<bf16*>(dx), n / 8);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_cast_f32_bf16(const float* x, void* y, int64_t n, istvt_stream_t stream) {
+    ISTVT_REQUIRE(x && y && n > 0 && n % 4 == 0);
+    cast_f32_bf16_kernel<<<nblk(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<bf16*>(y), n / 4);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_transpose_colsum(const void* in, void* out, float* colsum, int64_t m, int c, int64_t ldo,
+                                      istvt_stream_t stream) {
+    ISTVT_REQUIRE(in && out && m > 0 && c > 0 && c % 8 == 0 && ldo % 8 == 0 && ldo >= m);
+    const dim3 grid(static_cast<unsigned>((ldo + 63) / 64), static_cast<unsigned>((c + 63) / 64));
+    transpose_colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(in), static_cast<bf16*>(out), colsum, m, c, ldo);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_head_bwd(const float* tokens, int64_t rows_per_clip, const float* dlogits, const float* norm_g,
+                              const float* norm_b, const float* head_g, const float* head_b, const float* head_w,
+                              float* g, float* d_norm_g, float* d_norm_b, float* d_head_g, float* d_head_b,
+                              float* d_head_w, float* d_head_bias, int batch, int dim, float eps,
+                              istvt_stream_t stream) {
+    ISTVT_REQUIRE(tokens && dlogits && g && batch > 0 && dim > 0);
+    head_bwd_kernel<<<batch, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        tokens, rows_per_clip, dlogits, norm_g, norm_b, head_g, head_b, head_w, g, d_norm_g, d_norm_b, d_head_g,
+        d_head_b, d_head_w, d_head_bias, dim, eps);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_token_bwd(const float* g, float* d_pos, float* d_space, float* d_temporal, int batch, int t,
+                               int tokens_per_frame, int dim, istvt_stream_t stream) {
+    ISTVT_REQUIRE(g && d_pos && d_space && d_temporal && batch > 0 && t > 0 && dim % 4 == 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t total = static_cast<int64_t>(t) * tokens_per_frame * (dim / 4);
+    token_bwd_pos_kernel<<<nblk(total, 256), 256, 0, st>>>(g, d_pos, d_space, batch, t, tokens_per_frame, dim);
+    token_bwd_temporal_kernel<<<batch, 256, 0, st>>>(g, d_temporal, t, tokens_per_frame, dim);
+    count_launch();
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                float grad_scale, istvt_stream_t stream) {
+    ISTVT_REQUIRE(params && grads && exp_avg && exp_avg_sq && n > 0 && n % 4 == 0 && step >= 1);
+    const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+    const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+    adamw_kernel<<<nblk(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        params, grads, exp_avg, exp_avg_sq, n / 4, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+    count_launch();
+    return launch_status();
+}

@@ -23,6 +23,8 @@ struct GemmParams {
     int64_t ldr;
     int act;
     int c_f32;
+    int split_k;      // > 1 (CTA-pair kernel only): K is cut into split_k ranges of kb_per_split 64-wide k-blocks,
+    int kb_per_split; // every (tile, range) adds its partial product to the fp32 C with red.global (C pre-initialised)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -157,6 +159,13 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
                     const uint4 u = lds_u4(slab + row * 128 + ((cchunk ^ (row & 7)) << 4));
                     const int64_t drow = drow_t[i0 + i];
                     if (!n_ok || drow < 0) continue;
+                    if (p.split_k > 1) {   // split-K partial: accumulate into C (weight-gradient GEMMs)
+                        float* dst = reinterpret_cast<float*>(p.C) + drow * p.ldc + n;
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(u.x)),
+                                     "f"(__uint_as_float(u.y)), "f"(__uint_as_float(u.z)), "f"(__uint_as_float(u.w))
+                                     : "memory");
+                        continue;
+                    }
                     float4 v;
                     v.x = epi_act(__uint_as_float(u.x) + bias4.x, p.act) + res[i].x;
                     v.y = epi_act(__uint_as_float(u.y) + bias4.y, p.act) + res[i].y;

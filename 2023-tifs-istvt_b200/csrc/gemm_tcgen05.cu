@@ -301,3 +301,36 @@ extern "C" int istvt_gemm_fwd(const void* a, int64_t lda, const void* w, int64_t
     p.act = act; p.c_f32 = (c_dtype == ISTVT_F32);
     return gemm_bf16_dispatch(a, m, lda, w, ldw, k, p, static_cast<cudaStream_t>(stream));
 }
+
+// Weight-gradient GEMM: C[m, n] += sum_k A[m, k] * W[n, k] with a very long K (the token rows) and a small
+// output: split-K over CTA pairs, partial products accumulated with red.global.add into the fp32 C.
+extern "C" int istvt_gemm_splitk_accum(const void* a, int64_t lda, const void* w, int64_t ldw, float* c, int64_t ldc,
+                                       int64_t m, int n, int64_t k, istvt_stream_t stream) {
+    ISTVT_REQUIRE(a && w && c);
+    ISTVT_REQUIRE(m > 0 && n > 0 && k > 0 && k < (int64_t(1) << 31));
+    ISTVT_REQUIRE(n % 4 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 4 == 0);
+    ISTVT_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(c) & 15) == 0);
+    GemmParams p{};
+    p.M = m; p.N = n; p.K = static_cast<int>(k);
+    p.taps = 1;
+    p.C = c; p.ldc = ldc;
+    p.bias = nullptr; p.residual = nullptr; p.ldr = 0;
+    p.act = ISTVT_ACT_NONE; p.c_f32 = 1;
+    const int num_kb = (p.K + 63) / 64;
+    const int64_t mn_tiles = ((m + 255) / 256) * ((n + 255) / 256);
+    // enough (tile, range) items for ~4 waves over the CTA pairs, at least 8 k-blocks per range
+    int64_t want = (4 * (sm_count() / 2) + mn_tiles - 1) / mn_tiles;
+    if (want < 2) want = 2;
+    int kb_per = static_cast<int>((num_kb + want - 1) / want);
+    if (kb_per < 8) kb_per = 8;
+    if (kb_per > num_kb) kb_per = num_kb;
+    p.kb_per_split = kb_per;
+    p.split_k = (num_kb + kb_per - 1) / kb_per;
+    if (p.split_k < 2) { p.split_k = 2; p.kb_per_split = (num_kb + 1) / 2; if (p.kb_per_split * 1 >= num_kb) { p.split_k = 1; } }
+    if (p.split_k == 1) {
+        // degenerate (K <= 64): plain accumulate through the residual epilogue
+        p.split_k = 0; p.kb_per_split = 0; p.residual = c; p.ldr = ldc;
+    }
+    return launch_gemm_2cta(a, lda, w, ldw, p, static_cast<cudaStream_t>(stream));
+}

@@ -57,7 +57,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     const int num_kb = (p.K + G2_BK - 1) / G2_BK;
     const int n_tiles = (p.N + G2_BN - 1) / G2_BN;
     const int64_t m_tiles = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
-    const int64_t total_tiles = m_tiles * n_tiles;
+    const int splits = p.split_k > 1 ? p.split_k : 1;
+    const int kb_per = p.split_k > 1 ? p.kb_per_split : num_kb;
+    const int64_t mn_tiles = m_tiles * n_tiles;
+    const int64_t total_tiles = mn_tiles * splits;     // tile = split * mn_tiles + (m_blk * n_tiles + n_blk)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -95,11 +98,14 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
-                const int64_t m_blk = tile / n_tiles;
-                const int n_blk = static_cast<int>(tile % n_tiles);
+                const int ks = static_cast<int>(tile / mn_tiles);
+                const int64_t mn = tile - ks * mn_tiles;
+                const int64_t m_blk = mn / n_tiles;
+                const int n_blk = static_cast<int>(mn % n_tiles);
                 const int m0 = static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M);
                 const int n0 = n_blk * G2_BN + static_cast<int>(rank) * (tile_n_eff(n_blk) >> 1);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_end = (ks + 1) * kb_per < num_kb ? (ks + 1) * kb_per : num_kb;
+                for (int kb = ks * kb_per; kb < kb_end; ++kb) {
                     mbar_wait_hot(&empty_bar[stage], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
                     tma_load_2d_2cta(smem_a + stage * G2_A_BYTES, &tm_a, &full_bar[stage], kb * G2_BK, m0);
@@ -125,25 +131,30 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
-                const int n_blk = static_cast<int>(tile % n_tiles);
+                const int ks = static_cast<int>(tile / mn_tiles);
+                const int n_blk = static_cast<int>((tile - ks * mn_tiles) % n_tiles);
                 const uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, static_cast<uint32_t>(tile_n_eff(n_blk)), 0, 0);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * G2_BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_begin = ks * kb_per;
+                const int kb_end = (ks + 1) * kb_per < num_kb ? (ks + 1) * kb_per : num_kb;
+                const int tail_steps = kb_end == num_kb ? last_steps : G2_BK / UMMA_K;
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait_hot(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t a_desc = desc_hi | (a_field0 + stage * (G2_A_BYTES >> 4));
                     const uint64_t b_desc = desc_hi | (b_field0 + stage * (G2_B_BYTES >> 4));
-                    if (kb != num_kb - 1) {
-                        umma_f16_ss_2cta(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
+                    if (kb != kb_end - 1) {
+                        umma_f16_ss_2cta(d_tmem, a_desc, b_desc, idesc, kb != kb_begin ? 1u : 0u);
                         umma_f16_ss_2cta(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
                         umma_f16_ss_2cta(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
                         umma_f16_ss_2cta(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
                         umma_commit_2cta(&empty_bar[stage], 3);                  // free the slot in both CTAs
                     } else {
-                        for (int k = 0; k < last_steps; ++k)
-                            umma_f16_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < tail_steps; ++k)
+                            umma_f16_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                             (kb != kb_begin || k != 0) ? 1u : 0u);
                         umma_commit_2cta(&empty_bar[stage], 3);
                         umma_commit_2cta(&tmem_full[acc], 3);                    // accumulator ready in both CTAs
                     }
@@ -163,8 +174,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
-            const int64_t m_blk = tile / n_tiles;
-            const int n_blk = static_cast<int>(tile % n_tiles);
+            const int64_t mn = tile % mn_tiles;
+            const int64_t m_blk = mn / n_tiles;
+            const int n_blk = static_cast<int>(mn % n_tiles);
             const int64_t m = m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32 + lane;
             int drow_t[8];
             const int drow_lane = m < p.M ? static_cast<int>(m) : -1;
@@ -216,7 +228,7 @@ int launch_gemm_2cta(const void* a, int64_t lda, const void* w, int64_t ldw, con
     }
     const int n_tiles = (p.N + G2_BN - 1) / G2_BN;
     const int64_t m_tiles = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
-    const int64_t total = m_tiles * n_tiles;
+    const int64_t total = m_tiles * n_tiles * (p.split_k > 1 ? p.split_k : 1);
     int64_t clusters = sm_count() / 2;
     if (total < clusters) clusters = total;
     // Epilogue warps per CTA: 16 (32 rows x 64 columns each) for the bf16 path — halves the per-tile epilogue

@@ -85,6 +85,19 @@ __device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity) {
     mbar_wait(bar, parity);
 }
 
+// Wait for roles that are not latency-critical (TMA producers): back off between polls so the spinning lane
+// does not take issue slots from the compute warps that share its scheduler.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(128);
+        if (++spins > ISTVT_MBAR_SPIN_LIMIT) {
+            printf("istvt: mbarrier timeout (producer) block=%d bar=%u parity=%u\n", (int)blockIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA
 // ------------------------------------------------------------------------------------------
@@ -213,6 +226,14 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
         "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -358,6 +379,12 @@ __device__ __forceinline__ void sts_u4(uint32_t saddr, uint32_t a, uint32_t b, u
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+// Round-to-nearest fp32 -> bf16 pair with integer ALU ops only (finite, non-negative inputs such as softmax
+// numerators): F2FP.BF16.PACK_AB issues on the XU pipe, which the exponentials already saturate.  Ties round
+// up instead of to even — they differ only when the 16 dropped bits are exactly 0x8000.
+__device__ __forceinline__ uint32_t pack_bf16x2_rne_alu(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);

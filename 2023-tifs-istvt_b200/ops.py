@@ -320,3 +320,152 @@ def head(tokens: torch.Tensor, norm_g, norm_b, head_g, head_b, head_w, head_bias
                                              _ptr(head_b), _ptr(head_w), _ptr(head_bias), _ptr(logits), b, d, eps,
                                              _stream(dev)), "istvt_head_fwd")
     return logits
+
+
+# ----------------------------------------------------------------------------------------------
+# training step (backward kernels, optimizer)
+# ----------------------------------------------------------------------------------------------
+def attn_spatial_lse(qkv: torch.Tensor, batch_frames: int, tokens: int, heads: int, scale: float
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Training-mode spatial attention: (out [rows, heads*64] bf16, lse [batch_frames, heads, tokens] fp32)."""
+    dev = _chk(qkv)
+    inner = heads * 64
+    rows = batch_frames * tokens
+    if qkv.dtype != torch.bfloat16 or qkv.numel() != rows * 3 * inner:
+        raise ValueError("attn_spatial_lse: qkv must be bf16 [rows, 3*heads*64]")
+    out = torch.empty(rows, inner, dtype=qkv.dtype, device=dev)
+    lse = torch.empty(batch_frames, heads, tokens, dtype=torch.float32, device=dev)
+    with _launch(dev, "attn_spatial", 4.0 * batch_frames * heads * tokens * tokens * 64, _nbytes(qkv, out, lse)):
+        _lib.check(_lib.lib().istvt_attn_spatial_fwd_lse(_ptr(qkv), _ptr(out), _ptr(lse), batch_frames, tokens, heads,
+                                                         scale, _stream(dev)), "istvt_attn_spatial_fwd_lse")
+    return out, lse
+
+
+def attn_spatial_bwd(qkv: torch.Tensor, o: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, batch_frames: int,
+                     tokens: int, heads: int, scale: float, scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _chk(qkv, o, dout, lse, scratch)
+    inner = heads * 64
+    rows = batch_frames * tokens
+    if any(t.dtype != torch.bfloat16 for t in (qkv, o, dout)) or lse.dtype != torch.float32:
+        raise ValueError("attn_spatial_bwd: qkv / o / dout must be bf16 and lse fp32")
+    if qkv.numel() != rows * 3 * inner or o.numel() != rows * inner or dout.numel() != rows * inner:
+        raise ValueError("attn_spatial_bwd: shape mismatch")
+    dqkv = torch.empty_like(qkv)
+    if scratch is None:
+        scratch = torch.empty(rows, inner, dtype=torch.float32, device=dev)
+    with _launch(dev, "attn_spatial_bwd", 10.0 * batch_frames * heads * tokens * tokens * 64,
+                 _nbytes(qkv, o, dout, dqkv)):
+        _lib.check(_lib.lib().istvt_attn_spatial_bwd(_ptr(qkv), _ptr(o), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                                     _ptr(scratch), batch_frames, tokens, heads, scale, _stream(dev)),
+                   "istvt_attn_spatial_bwd")
+    return dqkv
+
+
+def attn_temporal_bwd(qk: torch.Tensor, v: torch.Tensor, dout: torch.Tensor, batch: int, frames: int, tokens: int,
+                      heads: int, scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    dev = _chk(qk, v, dout)
+    if any(t.dtype != torch.bfloat16 for t in (qk, v, dout)):
+        raise ValueError("attn_temporal_bwd: bf16 only")
+    dqk, dv = torch.empty_like(qk), torch.empty_like(v)
+    with _launch(dev, "attn_temporal_bwd", 10.0 * batch * tokens * heads * frames * frames * 64,
+                 _nbytes(qk, v, dout, dqk, dv)):
+        _lib.check(_lib.lib().istvt_attn_temporal_bwd(_ptr(qk), _ptr(v), _ptr(dout), _ptr(dqk), _ptr(dv), batch, frames,
+                                                      tokens, heads, scale, _stream(dev)), "istvt_attn_temporal_bwd")
+    return dqk, dv
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
+                  g_accum: Optional[torch.Tensor] = None, g_bf16: Optional[torch.Tensor] = None,
+                  dy2: Optional[torch.Tensor] = None, frames: int = 0, tokens_per_frame: int = 0,
+                  eps: float = 1e-5) -> Optional[torch.Tensor]:
+    """Returns dx (bf16) unless `g_accum` (fp32, += dx) is given."""
+    dev = _chk(dy, x, gamma, dgamma, dbeta, g_accum, g_bf16, dy2)
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    if dy.dtype != torch.bfloat16 or dy.numel() != x.numel():
+        raise ValueError("layernorm_bwd: dy must be bf16 with x's shape")
+    dx = None if g_accum is not None else torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "layernorm_bwd", 0.0, _nbytes(dy, x, dx, dy2, g_bf16) + 2 * _nbytes(g_accum)):
+        _lib.check(_lib.lib().istvt_layernorm_bwd(_ptr(dy), _ptr(dy2), frames, tokens_per_frame, _ptr(x), _dt(x),
+                                                  _ptr(gamma), _ptr(g_accum), _ptr(g_bf16), _ptr(dx), _ptr(dgamma),
+                                                  _ptr(dbeta), rows, dim, eps, _stream(dev)), "istvt_layernorm_bwd")
+    return dx
+
+
+def gelu(x: torch.Tensor) -> torch.Tensor:
+    dev = _chk(x)
+    y = torch.empty_like(x)
+    with _launch(dev, "gelu", 0.0, _nbytes(x, y)):
+        _lib.check(_lib.lib().istvt_gelu_fwd(_ptr(x), _ptr(y), x.numel(), _stream(dev)), "istvt_gelu_fwd")
+    return y
+
+
+def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    dev = _chk(dy, x)
+    dx = torch.empty_like(x)
+    with _launch(dev, "gelu_bwd", 0.0, _nbytes(dy, x, dx)):
+        _lib.check(_lib.lib().istvt_gelu_bwd(_ptr(dy), _ptr(x), _ptr(dx), x.numel(), _stream(dev)), "istvt_gelu_bwd")
+    return dx
+
+
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _chk(x, out)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "cast", 0.0, _nbytes(x, out)):
+        _lib.check(_lib.lib().istvt_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream(dev)), "istvt_cast_f32_bf16")
+    return out
+
+
+def transpose(x: torch.Tensor, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: bf16 [M, C] -> bf16 [C, ld] with ld = M rounded up to 8 (pad zero); colsum (fp32 [C]) += column sums."""
+    dev = _chk(x, colsum)
+    m, c = x.shape
+    ld = (m + 7) // 8 * 8
+    out = torch.empty(c, ld, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "transpose", 0.0, 2 * _nbytes(x)):
+        _lib.check(_lib.lib().istvt_transpose_colsum(_ptr(x), _ptr(out), _ptr(colsum), m, c, ld, _stream(dev)),
+                   "istvt_transpose_colsum")
+    return out
+
+
+def gemm_wgrad(dyt: torch.Tensor, xt: torch.Tensor, rows: int, dw: torch.Tensor) -> None:
+    """dw[N, K] (fp32) += dyt[N, :rows] . xt[K, :rows]^T  (both operands K-major over the token rows)."""
+    dev = _chk(dyt, xt, dw)
+    n, ld = dyt.shape
+    k = xt.shape[0]
+    if xt.shape[1] != ld or dw.dtype != torch.float32 or dw.numel() != n * k:
+        raise ValueError("gemm_wgrad: operand shapes do not match")
+    with _launch(dev, "gemm_wgrad", 2.0 * n * k * rows, _nbytes(dyt, xt) + 2 * _nbytes(dw)):
+        _lib.check(_lib.lib().istvt_gemm_splitk_accum(_ptr(dyt), ld, _ptr(xt), ld, _ptr(dw), k, n, k, rows,
+                                                      _stream(dev)), "istvt_gemm_splitk_accum")
+
+
+def head_bwd(tokens: torch.Tensor, dlogits: torch.Tensor, norm_g, norm_b, head_g, head_b, head_w, g: torch.Tensor,
+             d_norm_g, d_norm_b, d_head_g, d_head_b, d_head_w, d_head_bias, eps: float = 1e-5) -> None:
+    dev = _chk(tokens, dlogits, g)
+    b, f, p, d = tokens.shape
+    with _launch(dev, "head_bwd", 0.0, 0.0):
+        _lib.check(_lib.lib().istvt_head_bwd(_ptr(tokens), f * p, _ptr(dlogits), _ptr(norm_g), _ptr(norm_b), _ptr(head_g),
+                                             _ptr(head_b), _ptr(head_w), _ptr(g), _ptr(d_norm_g), _ptr(d_norm_b),
+                                             _ptr(d_head_g), _ptr(d_head_b), _ptr(d_head_w), _ptr(d_head_bias), b, d,
+                                             eps, _stream(dev)), "istvt_head_bwd")
+
+
+def token_bwd(g: torch.Tensor, d_pos: torch.Tensor, d_space: torch.Tensor, d_temporal: torch.Tensor) -> None:
+    dev = _chk(g, d_pos, d_space, d_temporal)
+    b, f, p, d = g.shape
+    with _launch(dev, "token_bwd", 0.0, _nbytes(g)):
+        _lib.check(_lib.lib().istvt_token_bwd(_ptr(g), _ptr(d_pos), _ptr(d_space), _ptr(d_temporal), b, f - 1, p, d,
+                                              _stream(dev)), "istvt_token_bwd")
+
+
+def adamw_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float,
+               betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, step: int = 1,
+               grad_scale: float = 1.0) -> None:
+    dev = _chk(params, grads, exp_avg, exp_avg_sq)
+    n = params.numel()
+    with _launch(dev, "adamw", 0.0, 7 * n * 4):
+        _lib.check(_lib.lib().istvt_adamw_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), n, lr,
+                                               betas[0], betas[1], eps, weight_decay, step, grad_scale, _stream(dev)),
+                   "istvt_adamw_step")

@@ -1,0 +1,300 @@
+"""Training step of the ISTVT hot path: forward that keeps activations, hand-written backward, AdamW, DP all-reduce.
+
+Mirrors the ISTVT branch of the reference's training loop (train_CNN.py:146-148,196-201,513-533):
+
+    optimizer.zero_grad(); outputs = model(image)
+    loss = nn.BCEWithLogitsLoss()(outputs.view(-1), labels.float()); loss.backward(); optimizer.step()
+
+with `optim.AdamW(lr, betas=(0.9, 0.999), eps=1e-8, weight_decay)` and, on several GPUs, the gradient reduction
+that `nn.DataParallel` performs (train_CNN.py:185-186) done as ONE NCCL all-reduce of a flat fp32 gradient buffer
+(one process per GPU, BatchNorm statistics rank-local exactly like DataParallel replicas).
+
+Every arithmetic step is a kernel of libistvt_b200.so (see ops.py); torch supplies memory, streams, the
+loss on the [B] logits (the caller-side line train_CNN.py:526) and `torch.distributed`.  bf16 mode only.
+
+Gradient flow per spatial-temporal block (forward: engine.py / vivit.py:97-100), g = dL/d(residual stream), fp32:
+    MLP      : dW2,db2 ; dhid = g W2 ; dhpre = dhid * gelu'(hpre) ; dW1,db1 ; dzn = dhpre W1 ; g += LN3'(dzn)
+    spatial  : dWso,dbso ; das = g Wso ; dqkv = attn_s'(das) ; dWqkv ; dyn = dqkv Wqkv ; dy1 = LN2'(dyn)
+    temporal : dWto,dbto ; dat = dy1 Wto ; (dqk, dv) = attn_t'(dat) ; dWqk, dWv ;
+               g += LN1'( dv Wv  +  self-subtract'(dqk Wqk) )
+Weight gradients are split-K tcgen05 GEMMs over transposed (K-major) copies of dY and X.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .engine import pack_entry, run_entry_flow
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------
+# parameters on the path, flat buffers
+# ------------------------------------------------------------------------------------------------
+def on_path_named_parameters(model, train_entry_flow: bool) -> List[Tuple[str, torch.nn.Parameter]]:
+    """Parameters that receive a gradient (117 Xception-tail tensors never do)."""
+    out = []
+    if train_entry_flow:
+        x = model.xcep.model
+        for name in ("conv1", "bn1", "conv2", "bn2", "block1", "block2", "block3"):
+            for n, p in getattr(x, name).named_parameters():
+                out.append((f"xcep.model.{name}.{n}", p))
+    for n, p in model.vit.named_parameters():
+        out.append((f"vit.{n}", p))
+    return out
+
+
+class FlatState:
+    """fp32 parameters / gradients / Adam moments of the path in four flat buffers; every `nn.Parameter.data`
+    becomes a view into `params`, so state_dict(), the packing code and external optimizers keep working."""
+
+    def __init__(self, model, train_entry_flow: bool):
+        named = on_path_named_parameters(model, train_entry_flow)
+        dev = named[0][1].device
+        sizes = [(p.numel() + 3) // 4 * 4 for _, p in named]       # 16-byte aligned slots
+        total = sum(sizes)
+        self.params = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.grad: Dict[str, torch.Tensor] = {}
+        self.names = [n for n, _ in named]
+        off = 0
+        for (name, p), sz in zip(named, sizes):
+            view = self.params[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            self.grad[name] = self.grads[off:off + p.numel()].view(p.shape)
+            off += sz
+        self.step = 0
+
+    def attach_grads(self, model, train_entry_flow: bool) -> None:
+        """Expose the flat gradient views as `.grad` (for inspection / external optimizers)."""
+        for name, p in on_path_named_parameters(model, train_entry_flow):
+            p.grad = self.grad[name]
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packs for training (bf16 forward weights + their transposes for the data-gradient GEMMs)
+# ------------------------------------------------------------------------------------------------
+def _pack_layers(vit) -> List[SimpleNamespace]:
+    layers = []
+    f32 = lambda t: t.detach().float().contiguous()
+    for attn_t, attn_s, ff in vit.transformer.layers:
+        L = SimpleNamespace()
+        for key, lin in (("qk", attn_t.fn.to_qk), ("v", attn_t.fn.to_v), ("to", attn_t.fn.to_out[0]),
+                         ("qkv", attn_s.fn.to_qkv), ("so", attn_s.fn.to_out[0]), ("1", ff.fn.net[0]), ("2", ff.fn.net[3])):
+            w = lin.weight.detach().to(BF16).contiguous()
+            setattr(L, "w_" + key, w)
+            setattr(L, "wT_" + key, w.t().contiguous())
+            if lin.bias is not None:
+                setattr(L, "b_" + key, f32(lin.bias))
+        L.ln1 = (f32(attn_t.norm.weight), f32(attn_t.norm.bias))
+        L.ln2 = (f32(attn_s.norm.weight), f32(attn_s.norm.bias))
+        L.ln3 = (f32(ff.norm.weight), f32(ff.norm.bias))
+        layers.append(L)
+    return layers
+
+
+def _layer_grad_names(i: int) -> Dict[str, str]:
+    p = f"vit.transformer.layers.{i}"
+    return {
+        "ln1_w": f"{p}.0.norm.weight", "ln1_b": f"{p}.0.norm.bias",
+        "w_qk": f"{p}.0.fn.to_qk.weight", "w_v": f"{p}.0.fn.to_v.weight",
+        "w_to": f"{p}.0.fn.to_out.0.weight", "b_to": f"{p}.0.fn.to_out.0.bias",
+        "ln2_w": f"{p}.1.norm.weight", "ln2_b": f"{p}.1.norm.bias",
+        "w_qkv": f"{p}.1.fn.to_qkv.weight",
+        "w_so": f"{p}.1.fn.to_out.0.weight", "b_so": f"{p}.1.fn.to_out.0.bias",
+        "ln3_w": f"{p}.2.norm.weight", "ln3_b": f"{p}.2.norm.bias",
+        "w_1": f"{p}.2.fn.net.0.weight", "b_1": f"{p}.2.fn.net.0.bias",
+        "w_2": f"{p}.2.fn.net.3.weight", "b_2": f"{p}.2.fn.net.3.bias",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# transformer: forward keeping activations, backward
+# ------------------------------------------------------------------------------------------------
+def transformer_forward_train(vit, layers: List[SimpleNamespace], tokens: torch.Tensor):
+    """tokens: fp32 [B, F, P, D] (not modified).  Returns (logits [B, 1], per-layer contexts, final stream)."""
+    b, f, p, d = tokens.shape
+    rows = b * f * p
+    heads = vit.heads
+    scale = 64 ** -0.5
+    f32 = lambda t: t.detach().float().contiguous()
+    ctxs = []
+    x = tokens
+    for L in layers:
+        c = SimpleNamespace()
+        c.x0 = x
+        c.xn, c.diff = ops.layernorm_diff(x, L.ln1[0], L.ln1[1], BF16)
+        c.qk = ops.gemm(c.diff.view(rows, d), L.w_qk)
+        c.v = ops.gemm(c.xn.view(rows, d), L.w_v)
+        c.at, _ = ops.attn_temporal(c.qk, c.v, b, f, p, heads, scale)
+        c.y1 = ops.gemm(c.at, L.w_to, bias=L.b_to, out_dtype=BF16)
+        c.yn = ops.layernorm(c.y1, L.ln2[0], L.ln2[1], BF16)
+        c.qkv = ops.gemm(c.yn, L.w_qkv)
+        c.as_, c.lse = ops.attn_spatial_lse(c.qkv, b * f, p, heads, scale)
+        x1 = torch.empty_like(x)
+        ops.gemm(c.as_, L.w_so, bias=L.b_so, residual=x.view(rows, d), out=x1.view(rows, d))
+        c.x1 = x1
+        c.zn = ops.layernorm(x1.view(rows, d), L.ln3[0], L.ln3[1], BF16)
+        c.hpre = ops.gemm(c.zn, L.w_1, bias=L.b_1, out_dtype=BF16)
+        c.hid = ops.gelu(c.hpre)
+        x2 = torch.empty_like(x)
+        ops.gemm(c.hid, L.w_2, bias=L.b_2, residual=x1.view(rows, d), out=x2.view(rows, d))
+        x = x2
+        ctxs.append(c)
+    head = SimpleNamespace(norm=(f32(vit.transformer.norm.weight), f32(vit.transformer.norm.bias)),
+                           ln=(f32(vit.mlp_head[0].weight), f32(vit.mlp_head[0].bias)),
+                           w=f32(vit.mlp_head[1].weight.reshape(-1)), b=f32(vit.mlp_head[1].bias))
+    logits = ops.head(x, head.norm[0], head.norm[1], head.ln[0], head.ln[1], head.w, head.b)
+    return logits, ctxs, x, head
+
+
+def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits: torch.Tensor,
+                         G: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """Accumulates every vit.transformer / vit.mlp_head gradient into G and returns g = dL/d(tokens), fp32."""
+    b, f, p, d = x_final.shape
+    rows = b * f * p
+    heads = vit.heads
+    scale = 64 ** -0.5
+    g = torch.zeros_like(x_final)
+    g2 = g.view(rows, d)
+    ops.head_bwd(x_final, dlogits.reshape(-1).float().contiguous(), head.norm[0], head.norm[1], head.ln[0], head.ln[1],
+                 head.w, g, G["vit.transformer.norm.weight"], G["vit.transformer.norm.bias"],
+                 G["vit.mlp_head.0.weight"], G["vit.mlp_head.0.bias"], G["vit.mlp_head.1.weight"].view(-1),
+                 G["vit.mlp_head.1.bias"])
+    g_bf = ops.cast_bf16(g2)
+    scratch = torch.empty(rows, heads * 64, dtype=torch.float32, device=g.device)
+    for li in range(len(layers) - 1, -1, -1):
+        L, c = layers[li], ctxs[li]
+        N = {k: G[v] for k, v in _layer_grad_names(li).items()}
+        # ---- MLP (module.py:27-34) ----
+        ops.gemm_wgrad(ops.transpose(g_bf, colsum=N["b_2"]), ops.transpose(c.hid), rows, N["w_2"])
+        dhid = ops.gemm(g_bf, L.wT_2)
+        dhpre = ops.gelu_bwd(dhid, c.hpre)
+        del dhid
+        ops.gemm_wgrad(ops.transpose(dhpre, colsum=N["b_1"]), ops.transpose(c.zn), rows, N["w_1"])
+        dzn = ops.gemm(dhpre, L.wT_1)
+        del dhpre
+        ops.layernorm_bwd(dzn, c.x1.view(rows, d), L.ln3[0], N["ln3_w"], N["ln3_b"], g_accum=g2, g_bf16=g_bf)
+        del dzn
+        # ---- spatial attention (module.py:81-93) ----
+        ops.gemm_wgrad(ops.transpose(g_bf, colsum=N["b_so"]), ops.transpose(c.as_), rows, N["w_so"])
+        das = ops.gemm(g_bf, L.wT_so)
+        dqkv = ops.attn_spatial_bwd(c.qkv, c.as_, das, c.lse, b * f, p, heads, scale, scratch)
+        del das
+        ops.gemm_wgrad(ops.transpose(dqkv), ops.transpose(c.yn), rows, N["w_qkv"])
+        dyn = ops.gemm(dqkv, L.wT_qkv)
+        del dqkv
+        dy1 = ops.layernorm_bwd(dyn, c.y1, L.ln2[0], N["ln2_w"], N["ln2_b"])
+        del dyn
+        # ---- temporal self-subtract attention (module.py:190-208) ----
+        ops.gemm_wgrad(ops.transpose(dy1, colsum=N["b_to"]), ops.transpose(c.at), rows, N["w_to"])
+        dat = ops.gemm(dy1, L.wT_to)
+        del dy1
+        dqk, dv = ops.attn_temporal_bwd(c.qk, c.v, dat, b, f, p, heads, scale)
+        del dat
+        ops.gemm_wgrad(ops.transpose(dqk), ops.transpose(c.diff.view(rows, d)), rows, N["w_qk"])
+        ops.gemm_wgrad(ops.transpose(dv), ops.transpose(c.xn.view(rows, d)), rows, N["w_v"])
+        ddiff = ops.gemm(dqk, L.wT_qk)
+        dxn_v = ops.gemm(dv, L.wT_v)
+        del dqk, dv
+        ops.layernorm_bwd(dxn_v, c.x0.view(rows, d), L.ln1[0], N["ln1_w"], N["ln1_b"], g_accum=g2, g_bf16=g_bf,
+                          dy2=ddiff, frames=f, tokens_per_frame=p)
+        del ddiff, dxn_v
+        ctxs[li] = None     # release this layer's activations
+    return g
+
+
+# ------------------------------------------------------------------------------------------------
+# the trainer
+# ------------------------------------------------------------------------------------------------
+class Trainer:
+    """fwd + BCE-with-logits + bwd + (all-reduce) + AdamW for `XceptionVidTr` on one GPU per process.
+
+    `train_entry_flow=False` keeps the Xception entry flow in eval mode (running BatchNorm statistics, no
+    gradients): fine-tuning of the spatial-temporal transformer only.
+    """
+
+    def __init__(self, model, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
+                 train_entry_flow: bool = True, process_group=None):
+        if model.precision != "bf16":
+            raise ValueError("istvt_b200 training runs in bf16 mode (fp32 master weights, fp32 gradients)")
+        if next(model.parameters()).device.type != "cuda":
+            raise ValueError("move the model to a CUDA device first: there is no CPU training path")
+        if model.vit.num_frames + 1 > 8:
+            raise NotImplementedError("training is built for the ISTVT configuration (T <= 7 frames)")
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.train_entry_flow = train_entry_flow
+        self.pg = process_group
+        self.state = FlatState(model, train_entry_flow)
+        model._engine = None
+        self._entry = None
+        if train_entry_flow:
+            from .train_entry import EntryFlowTrainer
+            self._entry = EntryFlowTrainer(model.xcep.model)
+
+    # -- pieces (also used by the autograd.Function wrapper) --
+    def forward_train(self, x: torch.Tensor):
+        model, vit = self.model, self.model.vit
+        b, t = x.shape[:2]
+        if t != vit.num_frames:
+            raise ValueError(f"clip has {t} frames but the model was built with num_frames={vit.num_frames}")
+        frames = x.reshape(b * t, *x.shape[2:]).float().contiguous()
+        f32 = lambda z: z.detach().float().contiguous()
+        pos = f32(vit.pos_embedding[0])
+        if self._entry is not None:
+            body, skip, ectx = self._entry.forward(frames)
+        else:
+            body, skip = run_entry_flow(pack_entry(model.xcep.model, BF16), frames, BF16)
+            ectx = None
+        tokens = torch.empty(b, t + 1, vit.num_patches + 1, vit.dim, dtype=torch.float32, device=x.device)
+        ops.pool_add_tokens(body, skip, pos, tokens, b, t)
+        ops.token_fill(tokens, f32(vit.space_token.reshape(-1)), f32(vit.temporal_token.reshape(-1)), pos)
+        layers = _pack_layers(vit)
+        logits, ctxs, x_final, head = transformer_forward_train(vit, layers, tokens)
+        saved = SimpleNamespace(layers=layers, ctxs=ctxs, x_final=x_final, head=head, ectx=ectx, body=body, skip=skip,
+                                b=b, t=t)
+        return logits, saved
+
+    def backward(self, saved, dlogits: torch.Tensor) -> None:
+        vit = self.model.vit
+        G = self.state.grad
+        g = transformer_backward(vit, saved.layers, saved.ctxs, saved.x_final, saved.head, dlogits, G)
+        ops.token_bwd(g, G["vit.pos_embedding"][0], G["vit.space_token"].view(-1), G["vit.temporal_token"].view(-1))
+        if self._entry is not None:
+            self._entry.backward(saved.ectx, saved.body, g, saved.b, saved.t, G)
+
+    def zero_grad(self) -> None:
+        self.state.grads.zero_()
+
+    def optimizer_step(self, world: int = 1) -> None:
+        st = self.state
+        st.step += 1
+        ops.adamw_step(st.params, st.grads, st.exp_avg, st.exp_avg_sq, self.lr, self.betas, self.eps,
+                       self.weight_decay, st.step, grad_scale=1.0 / world)
+
+    def step(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """One training iteration (train_CNN.py:513-533).  Returns the (local) loss."""
+        import torch.distributed as dist
+        self.zero_grad()
+        logits, saved = self.forward_train(x)
+        z = logits.view(-1)
+        y = labels.to(z.device).float()
+        loss = F.binary_cross_entropy_with_logits(z, y)                  # criterion, train_CNN.py:148,526
+        dlogits = (torch.sigmoid(z) - y) / z.numel()                     # d(mean BCE)/dz
+        self.backward(saved, dlogits)
+        world = 1
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(self.pg)
+            if world > 1:
+                dist.all_reduce(self.state.grads, group=self.pg)         # SUM; AdamW scales by 1/world
+        self.optimizer_step(world)
+        return loss

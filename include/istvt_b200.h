@@ -185,6 +185,76 @@ int istvt_head_fwd(const float* tokens, int64_t rows_per_clip, const float* norm
                    const float* head_g, const float* head_b, const float* head_w, const float* head_bias,
                    float* logits, int batch, int dim, float eps, istvt_stream_t stream);
 
+
+/* =============================================================================================
+ * Training step (train_CNN.py:513-533: zero_grad, forward, BCE-with-logits, loss.backward(), AdamW.step()).
+ * The reference gets its backward from torch autograd over the modules cited above; each entry below is
+ * the hand-written gradient of the named forward.  bf16 activations / gradients, fp32 parameters, fp32
+ * parameter gradients (accumulated: callers zero the gradient buffers once per step).
+ * ============================================================================================= */
+
+/* Spatial attention forward that also saves the per-row log-sum-exp (log2 domain) for the backward.
+ * lse: fp32 [batch_frames, heads, tokens].  Same kernel as istvt_attn_spatial_fwd (bf16). */
+int istvt_attn_spatial_fwd_lse(const void* qkv, void* out, float* lse, int batch_frames, int tokens, int heads,
+                               float scale, istvt_stream_t stream);
+
+/* Backward of module.py:84-91.  qkv / dqkv: bf16 [rows, 3*heads*64]; o (forward output) / dout: bf16
+ * [rows, heads*64]; dq_scratch: fp32 [rows, heads*64] workspace. */
+int istvt_attn_spatial_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
+                           float* dq_scratch, int batch_frames, int tokens, int heads, float scale,
+                           istvt_stream_t stream);
+
+/* Backward of module.py:197-205 (frames <= 8).  dqk: bf16 [rows, 2*heads*64], dv: bf16 [rows, heads*64]. */
+int istvt_attn_temporal_bwd(const void* qk, const void* v, const void* dout, void* dqk, void* dv, int batch,
+                            int frames, int tokens, int heads, float scale, istvt_stream_t stream);
+
+/* LayerNorm backward (module.py:18,21; vivit.py:89,101).  dy: bf16 [rows, dim]; x: the forward input (x_dtype).
+ * dy2 (optional): gradient w.r.t. the self-subtract output `diff` of istvt_layernorm_diff_fwd; the backward of
+ * module.py:192 is then fused in: dy_total[f] = dy[f] + dy2[f] - dy2[f+1] (the last term for frames 1..F-2).
+ * Exactly one of g_accum / dx_out is non-NULL:
+ *   g_accum: fp32 [rows, dim] residual-stream gradient, += dx; g_bf16 (optional) receives a bf16 copy of it;
+ *   dx_out : bf16 [rows, dim] = dx.
+ * dgamma / dbeta: fp32 [dim], accumulated.  dim % 4 == 0, dim <= 768. */
+int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, int tokens_per_frame, const void* x, int x_dtype,
+                        const float* gamma, float* g_accum, void* g_bf16, void* dx_out, float* dgamma, float* dbeta,
+                        int64_t rows, int dim, float eps, istvt_stream_t stream);
+
+/* exact-erf GELU (module.py:28) on bf16, elementwise: forward (training keeps the pre-activation) and backward. */
+int istvt_gelu_fwd(const void* x, void* y, int64_t n, istvt_stream_t stream);
+int istvt_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, istvt_stream_t stream);
+
+/* fp32 -> bf16 cast (gradient of the fp32 residual stream as a GEMM operand). */
+int istvt_cast_f32_bf16(const float* x, void* y, int64_t n, istvt_stream_t stream);
+
+/* out[c, m] = in[m, c] (bf16; out row pitch ldo >= m, multiple of 8, pad zero-filled); colsum (optional, fp32 [c])
+ * += column sums of `in` — the bias gradient of the nn.Linear whose output gradient is being transposed.
+ * Produces the K-major operands of the weight-gradient GEMMs. */
+int istvt_transpose_colsum(const void* in, void* out, float* colsum, int64_t m, int c, int64_t ldo,
+                           istvt_stream_t stream);
+
+/* C[m, n] += sum_k A[m, k] * W[n, k], bf16 operands, fp32 C, split-K over CTA pairs with red.global accumulation:
+ * dW = dY^T X for every nn.Linear / 1x1 convolution (A = dY^T [out_features, rows], W = X^T [in_features, rows]). */
+int istvt_gemm_splitk_accum(const void* a, int64_t lda, const void* w, int64_t ldw, float* c, int64_t ldc, int64_t m,
+                            int n, int64_t k, istvt_stream_t stream);
+
+/* Head backward (vivit.py:101 on token (0,0), vivit.py:144-148): writes g[b, 0, :] (the caller zero-fills g) and
+ * accumulates the gradients of transformer.norm, mlp_head.0 (LayerNorm) and mlp_head.1 (Linear). */
+int istvt_head_bwd(const float* tokens, int64_t rows_per_clip, const float* dlogits, const float* norm_g,
+                   const float* norm_b, const float* head_g, const float* head_b, const float* head_w, float* g,
+                   float* d_norm_g, float* d_norm_b, float* d_head_g, float* d_head_b, float* d_head_w,
+                   float* d_head_bias, int batch, int dim, float eps, istvt_stream_t stream);
+
+/* Token-build backward (vivit.py:136-140): g fp32 [batch, t+1, tokens_per_frame, dim] ->
+ * d_pos [t, tokens_per_frame, dim], d_space [dim], d_temporal [dim] (all accumulated). */
+int istvt_token_bwd(const float* g, float* d_pos, float* d_space, float* d_temporal, int batch, int t,
+                    int tokens_per_frame, int dim, istvt_stream_t stream);
+
+/* torch.optim.AdamW step (train_CNN.py:199) over flat fp32 buffers; grad_scale multiplies the gradient first
+ * (1 / world_size after an all-reduce SUM).  n % 4 == 0. */
+int istvt_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                     istvt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

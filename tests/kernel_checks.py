@@ -332,6 +332,193 @@ def check_head():
     return {"head": _assert_close("head", got, ref, TOL_F32)}
 
 
+
+# ------------------------------------------------------------------------------------------------
+# training-step kernels: each against torch autograd of the same op (fp32 / fp64 on the GPU box)
+# ------------------------------------------------------------------------------------------------
+TOL_GRAD = 1.5e-2   # bf16 gradients in, bf16 gradients out
+
+
+def check_layernorm_bwd():
+    ops = _ops()
+    out = {}
+    dim = 728
+    for rows, xdt in ((37, torch.float32), (3 * 7 * 50, torch.float32), (1000, torch.bfloat16)):
+        x = (_rand(rows, dim, seed=rows) * 2 + 0.3).to(xdt)
+        g = _rand(dim, seed=1) * 0.2 + 1
+        b = _rand(dim, seed=2) * 0.1
+        dy = _rand(rows, dim, seed=3).to(torch.bfloat16)
+        xr = x.float().clone().requires_grad_(True)
+        gr = g.clone().requires_grad_(True)
+        br = b.clone().requires_grad_(True)
+        F.layer_norm(xr, (dim,), gr, br, 1e-5).backward(dy.float())
+        dg, db = torch.zeros(dim, device=DEV), torch.zeros(dim, device=DEV)
+        dx = ops.layernorm_bwd(dy, x, g, dg, db)
+        out[f"dx_{rows}"] = _assert_close("ln_bwd dx", dx, xr.grad, TOL_BF16)
+        out[f"dg_{rows}"] = _assert_close("ln_bwd dgamma", dg, gr.grad, 2e-4)
+        out[f"db_{rows}"] = _assert_close("ln_bwd dbeta", db, br.grad, 2e-4)
+        # accumulate mode: g += dx, bf16 copy
+        acc = _rand(rows, dim, seed=9)
+        want = acc + xr.grad
+        gbf = torch.empty(rows, dim, dtype=torch.bfloat16, device=DEV)
+        dg.zero_(); db.zero_()
+        assert ops.layernorm_bwd(dy, x, g, dg, db, g_accum=acc, g_bf16=gbf) is None
+        out[f"acc_{rows}"] = _assert_close("ln_bwd accumulate", acc, want, 5e-3)
+        out[f"accbf_{rows}"] = _assert_close("ln_bwd accumulate bf16 copy", gbf, want, TOL_BF16)
+    # fused self-subtract backward (module.py:192): x [B, F, P, D]
+    bsz, f, p = 2, 7, 11
+    x = _rand(bsz, f, p, dim, seed=5) * 1.5
+    g = _rand(dim, seed=1) * 0.2 + 1
+    b = _rand(dim, seed=2) * 0.1
+    dxn = _rand(bsz, f, p, dim, seed=6).to(torch.bfloat16)
+    dres = _rand(bsz, f, p, dim, seed=7).to(torch.bfloat16)
+    xr = x.clone().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    xn = F.layer_norm(xr, (dim,), gr, br, 1e-5)
+    res = torch.cat((xn[:, :2], xn[:, 2:] - xn[:, 1:-1]), dim=1)
+    (xn * dxn.float()).sum().add((res * dres.float()).sum()).backward()
+    dg, db = torch.zeros(dim, device=DEV), torch.zeros(dim, device=DEV)
+    acc = torch.zeros_like(x)
+    ops.layernorm_bwd(dxn, x, g, dg, db, g_accum=acc, dy2=dres, frames=f, tokens_per_frame=p)
+    out["diff_dx"] = _assert_close("ln_bwd + self-subtract dx", acc, xr.grad, 5e-3)
+    out["diff_dg"] = _assert_close("ln_bwd + self-subtract dgamma", dg, gr.grad, 2e-4)
+    out["diff_db"] = _assert_close("ln_bwd + self-subtract dbeta", db, br.grad, 2e-4)
+    return out
+
+
+def check_gelu_cast_transpose():
+    ops = _ops()
+    out = {}
+    x = (_rand(1000, 2912, seed=1) * 2).to(torch.bfloat16)
+    dy = _rand(1000, 2912, seed=2).to(torch.bfloat16)
+    xr = x.float().requires_grad_(True)
+    y = F.gelu(xr)
+    y.backward(dy.float())
+    out["gelu"] = _assert_close("gelu fwd", ops.gelu(x), y, TOL_BF16)
+    out["gelu_bwd"] = _assert_close("gelu bwd", ops.gelu_bwd(dy, x), xr.grad, TOL_BF16)
+    f = _rand(333, 728, seed=3)
+    out["cast"] = _assert_close("cast", ops.cast_bf16(f), f, TOL_BF16)
+    for (m, c) in ((5068, 728), (64, 64), (1001, 2912), (77, 8)):
+        a = _rand(m, c, seed=m).to(torch.bfloat16)
+        cs = torch.ones(c, device=DEV)
+        t = ops.transpose(a, cs)
+        ld = (m + 7) // 8 * 8
+        assert tuple(t.shape) == (c, ld)
+        assert torch.equal(t[:, :m], a.t()), f"transpose {m}x{c}"
+        assert ld == m or float(t[:, m:].abs().max()) == 0.0, "transpose pad must be zero"
+        out[f"colsum_{m}"] = _assert_close("colsum", cs, 1 + a.float().sum(0), 1e-4)
+    return out
+
+
+def check_gemm_wgrad():
+    ops = _ops()
+    _noTF32()
+    out = {}
+    for (rows, n, k) in ((5068, 1024, 728), (20000, 2912, 728), (5068, 728, 2912), (9000, 128, 64), (700, 512, 728),
+                         (40, 728, 512)):
+        dy = _rand(rows, n, seed=n).to(torch.bfloat16)
+        x = _rand(rows, k, seed=k + 1).to(torch.bfloat16)
+        dw = _rand(n, k, seed=3)                     # accumulates on top of existing gradient content
+        want = dw.double() + dy.double().t() @ x.double()
+        ops.gemm_wgrad(ops.transpose(dy), ops.transpose(x), rows, dw)
+        out[f"{rows}x{n}x{k}"] = _assert_close(f"wgrad {rows}x{n}x{k}", dw, want.float(), 2e-4)
+    return out
+
+
+def check_attn_temporal_bwd():
+    ops = _ops()
+    out = {}
+    heads, scale = 8, 0.125
+    for (b, f, p) in ((2, 7, 362), (1, 2, 5), (3, 8, 33)):
+        rows = b * f * p
+        qk = (_rand(rows, 1024, seed=f) * 1.5).to(torch.bfloat16)
+        v = _rand(rows, 512, seed=f + 1).to(torch.bfloat16)
+        do = _rand(rows, 512, seed=f + 2).to(torch.bfloat16)
+        qkr = qk.double().requires_grad_(True)
+        vr = v.double().requires_grad_(True)
+        split = lambda t: t.reshape(b, f, p, heads, 64).permute(0, 3, 2, 1, 4)   # b h p f d
+        q, k = split(qkr[:, :512]), split(qkr[:, 512:])
+        a = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * scale, dim=-1)
+        o = torch.matmul(a, split(vr)).permute(0, 3, 2, 1, 4).reshape(rows, 512)
+        o.backward(do.double())
+        dqk, dv = ops.attn_temporal_bwd(qk, v, do, b, f, p, heads, scale)
+        out[f"dqk_{f}"] = _assert_close("attn_t bwd dqk", dqk, qkr.grad.float(), TOL_GRAD)
+        out[f"dv_{f}"] = _assert_close("attn_t bwd dv", dv, vr.grad.float(), TOL_GRAD)
+    return out
+
+
+def check_attn_spatial_bwd():
+    ops = _ops()
+    out = {}
+    heads, scale = 8, 0.125
+    for (bf, p, amp) in ((2, 362, 1.5), (3, 130, 1.0), (1, 50, 1.0), (21, 384, 1.0)):
+        rows = bf * p
+        qkv = (_rand(rows, 1536, seed=p + bf) * amp).to(torch.bfloat16)
+        do = _rand(rows, 512, seed=p + 1).to(torch.bfloat16)
+        r = qkv.double().requires_grad_(True)
+        split = lambda t: t.reshape(bf, p, heads, 64).permute(0, 2, 1, 3)
+        q, k, v = split(r[:, :512]), split(r[:, 512:1024]), split(r[:, 1024:])
+        a = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * scale, dim=-1)
+        o_ref = torch.matmul(a, v).permute(0, 2, 1, 3).reshape(rows, 512)
+        o_ref.backward(do.double())
+        o, lse = ops.attn_spatial_lse(qkv, bf, p, heads, scale)
+        name = f"{bf}x{p}"
+        out[f"fwd_{name}"] = _assert_close(f"attn_s lse-mode out {name}", o, o_ref.float(), 1.5e-2)
+        lse_ref = torch.logsumexp(torch.matmul(q, k.transpose(-1, -2)) * scale, dim=-1) / math.log(2.0)
+        out[f"lse_{name}"] = _assert_close(f"attn_s lse {name}", lse, lse_ref.float(), 2e-3)
+        dqkv = ops.attn_spatial_bwd(qkv, o, do, lse, bf, p, heads, scale)
+        for nm, sl in (("dq", slice(0, 512)), ("dk", slice(512, 1024)), ("dv", slice(1024, 1536))):
+            out[f"{nm}_{name}"] = _assert_close(f"attn_s bwd {nm} {name}", dqkv[:, sl], r.grad[:, sl].float(), TOL_GRAD)
+    return out
+
+
+def check_head_token_bwd():
+    ops = _ops()
+    out = {}
+    b, f, p, d = 3, 7, 362, 728
+    tokens = _rand(b, f, p, d, seed=1) * 2
+    prm = [(_rand(d, seed=2) * 0.2 + 1), _rand(d, seed=3) * 0.1, (_rand(d, seed=4) * 0.2 + 1), _rand(d, seed=5) * 0.1,
+           _rand(d, seed=6) * 0.05, _rand(1, seed=7)]
+    dz = _rand(b, seed=8)
+    tr = tokens.clone().requires_grad_(True)
+    pr = [t.clone().requires_grad_(True) for t in prm]
+    x = F.layer_norm(tr[:, 0, 0], (d,), pr[0], pr[1], 1e-5)
+    z = F.layer_norm(x, (d,), pr[2], pr[3], 1e-5) @ pr[4][:, None] + pr[5]
+    z.backward(dz[:, None])
+    g = torch.zeros_like(tokens)
+    grads = [torch.zeros_like(t) for t in prm]
+    ops.head_bwd(tokens, dz, prm[0], prm[1], prm[2], prm[3], prm[4], g, *grads)
+    out["g"] = _assert_close("head_bwd dtokens", g, tr.grad, 1e-4)
+    for i, nm in enumerate(("norm_g", "norm_b", "head_g", "head_b", "head_w", "head_bias")):
+        out[nm] = _assert_close(f"head_bwd d{nm}", grads[i], pr[i].grad, 1e-4)
+    # token-build backward
+    gt = _rand(b, f, p, d, seed=11)
+    dpos, dsp, dtm = torch.zeros(f - 1, p, d, device=DEV), torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    ops.token_bwd(gt, dpos, dsp, dtm)
+    out["dpos"] = _assert_close("token_bwd dpos", dpos, gt[:, 1:].sum(0), 1e-5)
+    out["dspace"] = _assert_close("token_bwd dspace", dsp, gt[:, 1:, 0].sum((0, 1)), 1e-5)
+    out["dtemporal"] = _assert_close("token_bwd dtemporal", dtm, gt[:, 0].sum((0, 1)), 1e-5)
+    return out
+
+
+def check_adamw():
+    ops = _ops()
+    out = {}
+    n = 4 * 1001
+    p0 = _rand(n, seed=1)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        g = _rand(n, seed=10 + step)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adamw_step(p, g * 4.0, m, v, 3e-3, (0.9, 0.999), 1e-8, 0.05, step, grad_scale=0.25)
+        out[f"step{step}"] = _assert_close(f"adamw step {step}", p, ref.data, 1e-5)
+    return out
+
+
 CHECKS = {
     "layernorm": check_layernorm,
     "layernorm_diff": check_layernorm_diff,
@@ -346,4 +533,11 @@ CHECKS = {
     "attn_spatial_f32": check_attn_spatial_f32,
     "attn_spatial_bf16": check_attn_spatial_bf16,
     "head": check_head,
+    "layernorm_bwd": check_layernorm_bwd,
+    "gelu_cast_transpose": check_gelu_cast_transpose,
+    "gemm_wgrad": check_gemm_wgrad,
+    "attn_temporal_bwd": check_attn_temporal_bwd,
+    "attn_spatial_bwd": check_attn_spatial_bwd,
+    "head_token_bwd": check_head_token_bwd,
+    "adamw": check_adamw,
 }
