@@ -48,6 +48,18 @@ SIGNATURES = {
     "istvt_head_bwd": [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
     "istvt_token_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "istvt_adamw_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "istvt_conv_stem_raw_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "istvt_bn_stats_fwd": [_P, _P, _P, _L, _I, _P],
+    "istvt_bn_finalize_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _P],
+    "istvt_bn_apply_fwd": [_P, _P, _P, _P, _L, _I, _I, _P],
+    "istvt_bn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "istvt_pool_add_idx_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "istvt_pool_bwd": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "istvt_token_grad_gather": [_P, _P, _I, _I, _I, _I, _P],
+    "istvt_dwconv3x3_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "istvt_block_input_grad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "istvt_im2col_t": [_P, _P, _I, _I, _I, _I, _L, _P],
+    "istvt_im2col_t_stem": [_P, _P, _I, _I, _I, _L, _P],
 }
 _RESTYPES = {"istvt_error_string": c_char_p, "istvt_launch_count": c_int64}
 

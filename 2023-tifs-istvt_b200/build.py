@@ -28,6 +28,7 @@ SOURCES = [
     "attn_spatial.cu",
     "attn_spatial_bwd.cu",
     "backward.cu",
+    "entry_flow_bwd.cu",
     "entry_flow.cu",
 ]
 NVCC_FLAGS = [

@@ -19,7 +19,7 @@ constexpr int STEM_CO = 32;
 template <typename T>
 __global__ void __launch_bounds__(128)
 conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
-                 T* __restrict__ y, int n, int h, int w, int ho, int wo) {
+                 T* __restrict__ y, int n, int h, int w, int ho, int wo, int relu) {
     __shared__ __align__(16) float sw[27 * STEM_CO];
     __shared__ __align__(16) float sb[STEM_CO];
     // wt is [co][ci][ky][kx] (torch conv weight layout) -> sw[(ci*9 + ky*3 + kx)][co]
@@ -74,7 +74,7 @@ conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ wt, cons
         for (int c = 0; c < STEM_CO; c += 8) {
             float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = fmaxf(acc0[c + e], 0.0f);
+            for (int e = 0; e < 8; ++e) o[e] = relu ? fmaxf(acc0[c + e], 0.0f) : acc0[c + e];
             store8(yp + c, o);
         }
         if (has2) {
@@ -82,7 +82,7 @@ conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ wt, cons
             for (int c = 0; c < STEM_CO; c += 8) {
                 float o[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = fmaxf(acc1[c + e], 0.0f);
+                for (int e = 0; e < 8; ++e) o[e] = relu ? fmaxf(acc1[c + e], 0.0f) : acc1[c + e];
                 store8(yp + STEM_CO + c, o);
             }
         }
@@ -300,8 +300,8 @@ static inline unsigned blocks_for(int64_t total, int threads) {
 
 using namespace istvt;
 
-extern "C" int istvt_conv_stem_fwd(const float* x, const float* wt, const float* bias, void* y, int dtype, int n,
-                                   int h, int w, int cout, istvt_stream_t stream) {
+static int conv_stem_launch(const float* x, const float* wt, const float* bias, void* y, int dtype, int n, int h, int w,
+                            int cout, int relu, cudaStream_t st) {
     ISTVT_REQUIRE(x && wt && bias && y);
     ISTVT_REQUIRE(cout == STEM_CO && n > 0 && h >= 3 && w >= 3);
     const int ho = (h - 3) / 2 + 1, wo = (w - 3) / 2 + 1;
@@ -309,17 +309,27 @@ extern "C" int istvt_conv_stem_fwd(const float* x, const float* wt, const float*
     int64_t blocks = (total + 127) / 128;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
     if (blocks > cap) blocks = cap;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == ISTVT_BF16)
         conv_stem_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 128, 0, st>>>(
-            x, wt, bias, static_cast<__nv_bfloat16*>(y), n, h, w, ho, wo);
+            x, wt, bias, static_cast<__nv_bfloat16*>(y), n, h, w, ho, wo, relu);
     else if (dtype == ISTVT_F32)
         conv_stem_kernel<float><<<static_cast<unsigned>(blocks), 128, 0, st>>>(x, wt, bias, static_cast<float*>(y), n,
-                                                                                 h, w, ho, wo);
+                                                                                 h, w, ho, wo, relu);
     else
         return ISTVT_ERR_INVALID_ARG;
     count_launch();
     return launch_status();
+}
+
+extern "C" int istvt_conv_stem_fwd(const float* x, const float* wt, const float* bias, void* y, int dtype, int n,
+                                   int h, int w, int cout, istvt_stream_t stream) {
+    return conv_stem_launch(x, wt, bias, y, dtype, n, h, w, cout, 1, static_cast<cudaStream_t>(stream));
+}
+
+// Training mode: the raw convolution (+ bias, normally zero) without the ReLU; BatchNorm batch statistics follow.
+extern "C" int istvt_conv_stem_raw_fwd(const float* x, const float* wt, const float* bias, void* y, int dtype, int n,
+                                       int h, int w, int cout, istvt_stream_t stream) {
+    return conv_stem_launch(x, wt, bias, y, dtype, n, h, w, cout, 0, static_cast<cudaStream_t>(stream));
 }
 
 template <typename T>

@@ -227,9 +227,15 @@ class ISTVTEngine:
         if t != vit.num_frames:
             raise ValueError(f"clip has {t} frames but the model was built with num_frames={vit.num_frames}")
         if model.training:
-            raise NotImplementedError(
-                "istvt_b200: training-mode forward (BatchNorm batch statistics + backward) is not built yet; "
-                "call model.eval()")
+            # train mode without autograd (e.g. under torch.no_grad()): BatchNorm batch statistics, as the reference
+            from .train import Trainer
+            tr = model.__dict__.get("_autograd_trainer")
+            if tr is None:
+                tr = Trainer(model)
+                object.__setattr__(model, "_autograd_trainer", tr)
+            if return_attention:
+                raise ValueError("attention maps are an inference-mode output")
+            return tr.forward_train(x)[0]
         side = vit.image_size
         feat = lambda s: (((((s - 3) // 2 + 1) - 2) - 1) // 2 + 1)      # stem: 3x3 s2, 3x3 s1; then three s2 stages
         fh, fw = feat(hh), feat(ww)

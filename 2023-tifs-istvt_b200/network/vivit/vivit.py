@@ -74,10 +74,20 @@ class XceptionVidTr(nn.Module):
         return self._engine
 
     def forward(self, x: torch.Tensor, return_attention: bool = False):
+        if self.training and torch.is_grad_enabled():
+            # model.train() (train_CNN.py:226): BatchNorm batch statistics + activations kept for loss.backward()
+            if return_attention:
+                raise ValueError("attention maps are an inference-mode output")
+            if not x.is_cuda:
+                raise ValueError("ISTVT (istvt_b200) runs on CUDA tensors only: there is no CPU fallback by design")
+            from ...train import autograd_forward
+            return autograd_forward(self, x)
         return self.engine().forward(self, x, precision=self.precision, return_attention=return_attention)
 
-    def _apply(self, fn, *args, **kwargs):  # .cuda() / .to(): drop the packed-weight cache
+    def _apply(self, fn, *args, **kwargs):  # .cuda() / .to(): drop the packed-weight cache and the flat train state
         self._engine = None
+        if "_autograd_trainer" in self.__dict__:
+            del self.__dict__["_autograd_trainer"]
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):

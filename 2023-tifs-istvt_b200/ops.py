@@ -469,3 +469,140 @@ def adamw_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor,
         _lib.check(_lib.lib().istvt_adamw_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), n, lr,
                                                betas[0], betas[1], eps, weight_decay, step, grad_scale, _stream(dev)),
                    "istvt_adamw_step")
+
+
+# ---- entry flow, training mode ----
+def conv_stem_raw(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """conv1 without BN / ReLU: fp32 NCHW [n, 3, h, w] -> bf16 NHWC [n, ho, wo, 32]."""
+    dev = _chk(x, w)
+    n, _, h, wd = x.shape
+    ho, wo = (h - 3) // 2 + 1, (wd - 3) // 2 + 1
+    y = torch.empty(n, ho, wo, w.shape[0], dtype=torch.bfloat16, device=dev)
+    zero = torch.zeros(w.shape[0], dtype=torch.float32, device=dev)
+    with _launch(dev, "conv_stem", 2.0 * y.numel() * 27, _nbytes(x, y)):
+        _lib.check(_lib.lib().istvt_conv_stem_raw_fwd(_ptr(x), _ptr(w), _ptr(zero), _ptr(y), BF16, n, h, wd, w.shape[0],
+                                                      _stream(dev)), "istvt_conv_stem_raw_fwd")
+    return y
+
+
+class BNState:
+    """Per-layer BatchNorm batch statistics kept for the backward."""
+    __slots__ = ("scale", "shift", "mean", "rstd", "m", "c")
+
+
+def batchnorm_train(x: torch.Tensor, bn, relu: bool, update_running: bool = True) -> Tuple[torch.Tensor, BNState]:
+    """x: bf16 [..., c] raw convolution output; bn: nn.BatchNorm2d (parameters fp32).  y = [relu](bn_batch(x))."""
+    dev = _chk(x)
+    c = x.shape[-1]
+    m = x.numel() // c
+    stats = torch.zeros(2, c, dtype=torch.float32, device=dev)
+    st = BNState()
+    st.m, st.c = m, c
+    buf = torch.empty(4, c, dtype=torch.float32, device=dev)
+    st.scale, st.shift, st.mean, st.rstd = buf[0], buf[1], buf[2], buf[3]
+    s = _stream(dev)
+    with _launch(dev, "bn_stats", 0.0, _nbytes(x)):
+        _lib.check(_lib.lib().istvt_bn_stats_fwd(_ptr(x), _ptr(stats[0]), _ptr(stats[1]), m, c, s), "istvt_bn_stats_fwd")
+    rm = bn.running_mean if update_running else None
+    rv = bn.running_var if update_running else None
+    _lib.check(_lib.lib().istvt_bn_finalize_fwd(_ptr(stats[0]), _ptr(stats[1]), _ptr(bn.weight.data), _ptr(bn.bias.data),
+                                                _ptr(st.scale), _ptr(st.shift), _ptr(st.mean), _ptr(st.rstd),
+                                                _ptr(rm), _ptr(rv), m, c, bn.eps, bn.momentum, s),
+               "istvt_bn_finalize_fwd")
+    if update_running:
+        bn.num_batches_tracked += 1
+    y = torch.empty_like(x)
+    with _launch(dev, "bn_apply", 0.0, _nbytes(x, y)):
+        _lib.check(_lib.lib().istvt_bn_apply_fwd(_ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(y), m, c, int(relu), s),
+                   "istvt_bn_apply_fwd")
+    return y, st
+
+
+def batchnorm_bwd(dy: torch.Tensor, x: torch.Tensor, st: BNState, dgamma: torch.Tensor, dbeta: torch.Tensor,
+                  relu: bool) -> torch.Tensor:
+    dev = _chk(dy, x, dgamma, dbeta)
+    dx = torch.empty_like(x)
+    with _launch(dev, "bn_bwd", 0.0, 2 * _nbytes(dy, x) + _nbytes(dx)):
+        _lib.check(_lib.lib().istvt_bn_bwd(_ptr(dy), _ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(st.mean), _ptr(st.rstd),
+                                           _ptr(dgamma), _ptr(dbeta), _ptr(dx), st.m, st.c, int(relu), _stream(dev)),
+                   "istvt_bn_bwd")
+    return dx
+
+
+def pool_add_idx(x: torch.Tensor, skip: torch.Tensor, tokens: Optional[torch.Tensor] = None,
+                 pos_emb: Optional[torch.Tensor] = None, t_frames: int = 1):
+    """Training-mode pool+add: returns (y or None, argmax uint8 [n, ho, wo, c])."""
+    dev = _chk(x, skip, tokens, pos_emb)
+    n, h, wd, c = x.shape
+    ho, wo = (h - 1) // 2 + 1, (wd - 1) // 2 + 1
+    amax = torch.empty(n, ho, wo, c, dtype=torch.uint8, device=dev)
+    y = None if tokens is not None else torch.empty(n, ho, wo, c, dtype=x.dtype, device=dev)
+    with _launch(dev, "pool_add", 0.0, _nbytes(x, skip, y, amax)):
+        _lib.check(_lib.lib().istvt_pool_add_idx_fwd(_ptr(x), _ptr(skip), _ptr(y), _ptr(pos_emb), _ptr(tokens), _ptr(amax),
+                                                     n, t_frames, h, wd, c, _stream(dev)), "istvt_pool_add_idx_fwd")
+    return y, amax
+
+
+def pool_bwd(dy: torch.Tensor, amax: torch.Tensor, h: int, wd: int) -> torch.Tensor:
+    dev = _chk(dy, amax)
+    n, _, _, c = dy.shape
+    dx = torch.empty(n, h, wd, c, dtype=dy.dtype, device=dev)
+    with _launch(dev, "pool_bwd", 0.0, _nbytes(dy, amax, dx)):
+        _lib.check(_lib.lib().istvt_pool_bwd(_ptr(dy), _ptr(amax), _ptr(dx), n, h, wd, c, _stream(dev)), "istvt_pool_bwd")
+    return dx
+
+
+def token_grad_gather(g: torch.Tensor) -> torch.Tensor:
+    """g: fp32 [B, T+1, P, C] -> bf16 NHWC [B*T, side, side, C] (gradient of block 3's output)."""
+    dev = _chk(g)
+    b, f, p, c = g.shape
+    side = int(round((p - 1) ** 0.5))
+    out = torch.empty(b * (f - 1), side, side, c, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "token_grad_gather", 0.0, _nbytes(out) * 3):
+        _lib.check(_lib.lib().istvt_token_grad_gather(_ptr(g), _ptr(out), b, f - 1, p, c, _stream(dev)),
+                   "istvt_token_grad_gather")
+    return out
+
+
+def dwconv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, relu_in: bool) -> None:
+    """dw: fp32 [3, 3, c] (+=)."""
+    dev = _chk(x, dy, dw)
+    n, h, wd, c = x.shape
+    with _launch(dev, "dwconv_wgrad", 2.0 * x.numel() * 9, _nbytes(x, dy)):
+        _lib.check(_lib.lib().istvt_dwconv3x3_wgrad(_ptr(x), _ptr(dy), _ptr(dw), n, h, wd, c, int(relu_in), _stream(dev)),
+                   "istvt_dwconv3x3_wgrad")
+
+
+def block_input_grad(d_main: torch.Tensor, x_in: Optional[torch.Tensor], d_skip: torch.Tensor, relu_in: bool
+                     ) -> torch.Tensor:
+    dev = _chk(d_main, x_in, d_skip)
+    n, h, wd, c = d_main.shape
+    dx = torch.empty_like(d_main)
+    with _launch(dev, "block_input_grad", 0.0, _nbytes(d_main, x_in if relu_in else None, d_skip, dx)):
+        _lib.check(_lib.lib().istvt_block_input_grad(_ptr(d_main), _ptr(x_in), _ptr(d_skip), _ptr(dx), n, h, wd, c,
+                                                     int(relu_in), _stream(dev)), "istvt_block_input_grad")
+    return dx
+
+
+def im2col_t(x: torch.Tensor) -> torch.Tensor:
+    """NHWC bf16 [n, h, w, cin] -> [9*cin, ld] (3x3 valid taps, K-major over output pixels)."""
+    dev = _chk(x)
+    n, h, wd, cin = x.shape
+    m = n * (h - 2) * (wd - 2)
+    ld = (m + 7) // 8 * 8
+    out = torch.empty(9 * cin, ld, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "im2col_t", 0.0, _nbytes(out) * 2):
+        _lib.check(_lib.lib().istvt_im2col_t(_ptr(x), _ptr(out), n, h, wd, cin, ld, _stream(dev)), "istvt_im2col_t")
+    return out
+
+
+def im2col_t_stem(x: torch.Tensor) -> torch.Tensor:
+    """fp32 NCHW [n, 3, h, w] -> bf16 [32, ld] (27 stride-2 taps + 5 zero rows)."""
+    dev = _chk(x)
+    n, _, h, wd = x.shape
+    m = n * ((h - 3) // 2 + 1) * ((wd - 3) // 2 + 1)
+    ld = (m + 7) // 8 * 8
+    out = torch.empty(32, ld, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "im2col_t", 0.0, _nbytes(x, out)):
+        _lib.check(_lib.lib().istvt_im2col_t_stem(_ptr(x), _ptr(out), n, h, wd, ld, _stream(dev)), "istvt_im2col_t_stem")
+    return out

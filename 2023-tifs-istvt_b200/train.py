@@ -250,18 +250,19 @@ class Trainer:
         frames = x.reshape(b * t, *x.shape[2:]).float().contiguous()
         f32 = lambda z: z.detach().float().contiguous()
         pos = f32(vit.pos_embedding[0])
+        tokens = torch.empty(b, t + 1, vit.num_patches + 1, vit.dim, dtype=torch.float32, device=x.device)
         if self._entry is not None:
             body, skip, ectx = self._entry.forward(frames)
+            _, amax3 = ops.pool_add_idx(body, skip, tokens=tokens, pos_emb=pos, t_frames=t)
         else:
             body, skip = run_entry_flow(pack_entry(model.xcep.model, BF16), frames, BF16)
-            ectx = None
-        tokens = torch.empty(b, t + 1, vit.num_patches + 1, vit.dim, dtype=torch.float32, device=x.device)
-        ops.pool_add_tokens(body, skip, pos, tokens, b, t)
+            ectx, amax3 = None, None
+            ops.pool_add_tokens(body, skip, pos, tokens, b, t)
+        del body, skip
         ops.token_fill(tokens, f32(vit.space_token.reshape(-1)), f32(vit.temporal_token.reshape(-1)), pos)
         layers = _pack_layers(vit)
         logits, ctxs, x_final, head = transformer_forward_train(vit, layers, tokens)
-        saved = SimpleNamespace(layers=layers, ctxs=ctxs, x_final=x_final, head=head, ectx=ectx, body=body, skip=skip,
-                                b=b, t=t)
+        saved = SimpleNamespace(layers=layers, ctxs=ctxs, x_final=x_final, head=head, ectx=ectx, amax3=amax3, b=b, t=t)
         return logits, saved
 
     def backward(self, saved, dlogits: torch.Tensor) -> None:
@@ -270,7 +271,7 @@ class Trainer:
         g = transformer_backward(vit, saved.layers, saved.ctxs, saved.x_final, saved.head, dlogits, G)
         ops.token_bwd(g, G["vit.pos_embedding"][0], G["vit.space_token"].view(-1), G["vit.temporal_token"].view(-1))
         if self._entry is not None:
-            self._entry.backward(saved.ectx, saved.body, g, saved.b, saved.t, G)
+            self._entry.backward(saved.ectx, saved.amax3, g, G)
 
     def zero_grad(self) -> None:
         self.state.grads.zero_()
@@ -280,6 +281,7 @@ class Trainer:
         st.step += 1
         ops.adamw_step(st.params, st.grads, st.exp_avg, st.exp_avg_sq, self.lr, self.betas, self.eps,
                        self.weight_decay, st.step, grad_scale=1.0 / world)
+        self.model._engine = None            # the inference-mode packed weights are stale now
 
     def step(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """One training iteration (train_CNN.py:513-533).  Returns the (local) loss."""
@@ -298,3 +300,33 @@ class Trainer:
                 dist.all_reduce(self.state.grads, group=self.pg)         # SUM; AdamW scales by 1/world
         self.optimizer_step(world)
         return loss
+
+
+# ------------------------------------------------------------------------------------------------
+# torch.autograd bridge: `outputs = model(image); loss.backward()` (train_CNN.py:517,532) in train mode
+# ------------------------------------------------------------------------------------------------
+class _ISTVTTrainFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, trainer, *params):
+        logits, saved = trainer.forward_train(x)
+        ctx.trainer, ctx.saved = trainer, saved
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        tr = ctx.trainer
+        tr.zero_grad()                       # the flat buffer holds exactly this backward's gradients
+        tr.backward(ctx.saved, dlogits.contiguous())
+        ctx.saved = None
+        return (None, None) + tuple(tr.state.grad[n].clone() for n in tr.state.names)
+
+
+def autograd_forward(model, x: torch.Tensor) -> torch.Tensor:
+    """Training-mode `XceptionVidTr.forward`: the CUDA forward that keeps activations, differentiable through the
+    hand-written backward.  Any torch optimizer over `model.parameters()` then works as in the reference."""
+    tr = getattr(model, "_autograd_trainer", None)
+    if tr is None:
+        tr = Trainer(model)
+        object.__setattr__(model, "_autograd_trainer", tr)
+    params = [p for _, p in on_path_named_parameters(model, tr.train_entry_flow)]
+    return _ISTVTTrainFunction.apply(x, tr, *params)

@@ -255,6 +255,49 @@ int istvt_adamw_step(float* params, const float* grads, float* exp_avg, float* e
                      float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                      istvt_stream_t stream);
 
+/* ---- Xception entry flow in training mode (BatchNorm batch statistics; xception.py:52-101,193-206) ---- */
+
+/* conv1 without the ReLU (xception.py:194): BatchNorm with batch statistics follows as separate kernels. */
+int istvt_conv_stem_raw_fwd(const float* x, const float* wt, const float* bias, void* y, int dtype, int n, int h,
+                            int w, int cout, istvt_stream_t stream);
+
+/* nn.BatchNorm2d in training mode (xception.py:58,69,75,119,123) on x: bf16 [m, c] (NHWC flattened):
+ *   stats    : sum[c] += sum_m x, sumsq[c] += sum_m x^2 (fp32, caller zeroes them)
+ *   finalize : mean, rstd, scale = gamma*rstd, shift = beta - mean*scale; running_mean/var update (momentum,
+ *              unbiased variance) when the running pointers are non-NULL
+ *   apply    : y = x*scale + shift (+ReLU), bf16 */
+int istvt_bn_stats_fwd(const void* x, float* sum, float* sumsq, int64_t m, int c, istvt_stream_t stream);
+int istvt_bn_finalize_fwd(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* scale,
+                          float* shift, float* mean, float* rstd, float* running_mean, float* running_var, int64_t m,
+                          int c, float eps, float momentum, istvt_stream_t stream);
+int istvt_bn_apply_fwd(const void* x, const float* scale, const float* shift, void* y, int64_t m, int c, int relu,
+                       istvt_stream_t stream);
+/* Backward of BatchNorm(+ReLU): dgamma/dbeta (fp32 [c], must be zero on entry) and dx (bf16). */
+int istvt_bn_bwd(const void* dy, const void* x, const float* scale, const float* shift, const float* mean,
+                 const float* rstd, float* dgamma, float* dbeta, void* dx, int64_t m, int c, int relu,
+                 istvt_stream_t stream);
+
+/* MaxPool2d(3,2,1) + skip add (xception.py:87-88,100) that also records each window's arg-max tap (uint8
+ * [n, ho, wo, c]); exactly one of y (bf16 NHWC) / tokens (fp32 token buffer, + pos_emb, as
+ * istvt_pool_add_tokens_fwd) is non-NULL. */
+int istvt_pool_add_idx_fwd(const void* x, const void* skip, void* y, const float* pos_emb, float* tokens,
+                           void* argmax, int n, int t_frames, int h, int w, int c, istvt_stream_t stream);
+/* Max-pool backward (gather over the <= 4 windows containing each input pixel). dy: bf16 [n, ho, wo, c]. */
+int istvt_pool_bwd(const void* dy, const void* argmax, void* dx, int n, int h, int w, int c, istvt_stream_t stream);
+/* bf16 NHWC [batch*t, 19, 19, c] gradient of the block-3 output from the fp32 token gradient (vivit.py:133-138). */
+int istvt_token_grad_gather(const float* g, void* d_out, int batch, int t, int tokens_per_frame, int c,
+                            istvt_stream_t stream);
+/* Depthwise 3x3 weight gradient, dw: fp32 [3, 3, c] accumulated (xception.py:43,47). */
+int istvt_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int c, int relu_in,
+                          istvt_stream_t stream);
+/* Gradient of a Block's input: main branch (masked by the leading ReLU, xception.py:82-85) + scatter of the
+ * stride-2 skip branch (xception.py:94). */
+int istvt_block_input_grad(const void* d_main, const void* x_in, const void* d_skip, void* dx, int n, int h, int w,
+                           int c, int relu_in, istvt_stream_t stream);
+/* K-major im2col operands of the conv2 / conv1 weight-gradient GEMMs (xception.py:118,122). */
+int istvt_im2col_t(const void* x, void* out, int n, int h, int w, int cin, int64_t ldo, istvt_stream_t stream);
+int istvt_im2col_t_stem(const float* x, void* out, int n, int h, int w, int64_t ldo, istvt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,10 +25,16 @@ LN_EPS = 1e-5   # nn.LayerNorm default (module.py:18, vivit.py:89,128)
 TOKENS_PER_FRAME = 19 * 19 + 1   # hard-coded in module.py:84,192,197-198 and vivit.py:144
 
 
-def _bn(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
-    """BatchNorm2d in eval mode (running statistics)."""
+BN_MOMENTUM = 0.1   # nn.BatchNorm2d default
+
+
+def _bn(sd: SD, prefix: str, x: torch.Tensor, training: bool = False) -> torch.Tensor:
+    """BatchNorm2d: eval mode uses the running statistics; training mode (model.train(), train_CNN.py:226) the
+    batch statistics, and updates running_mean / running_var (unbiased) / num_batches_tracked in `sd` in place."""
+    if training and prefix + ".num_batches_tracked" in sd:
+        sd[prefix + ".num_batches_tracked"] += 1
     return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
-                        sd[prefix + ".bias"], training=False, eps=BN_EPS)
+                        sd[prefix + ".bias"], training=training, momentum=BN_MOMENTUM, eps=BN_EPS)
 
 
 def _sep(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
@@ -37,7 +43,7 @@ def _sep(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
     return F.conv2d(x, sd[prefix + ".pointwise.weight"])
 
 
-def _block(sd: SD, prefix: str, inp: torch.Tensor, start_with_relu: bool) -> torch.Tensor:
+def _block(sd: SD, prefix: str, inp: torch.Tensor, start_with_relu: bool, training: bool = False) -> torch.Tensor:
     """Block.forward, xception.py:91-101, for the entry-flow configuration (reps=2, stride 2, grow_first).
 
     rep = [ReLU] Sep BN ReLU Sep BN MaxPool(3,2,1) (xception.py:66-89); the leading ReLU is out-of-place
@@ -45,27 +51,28 @@ def _block(sd: SD, prefix: str, inp: torch.Tensor, start_with_relu: bool) -> tor
     """
     i0 = 1 if start_with_relu else 0          # index of the first SeparableConv2d inside rep
     x = F.relu(inp) if start_with_relu else inp
-    x = _bn(sd, f"{prefix}.rep.{i0 + 1}", _sep(sd, f"{prefix}.rep.{i0}", x))
+    x = _bn(sd, f"{prefix}.rep.{i0 + 1}", _sep(sd, f"{prefix}.rep.{i0}", x), training)
     x = F.relu(x)
-    x = _bn(sd, f"{prefix}.rep.{i0 + 4}", _sep(sd, f"{prefix}.rep.{i0 + 3}", x))
+    x = _bn(sd, f"{prefix}.rep.{i0 + 4}", _sep(sd, f"{prefix}.rep.{i0 + 3}", x), training)
     x = F.max_pool2d(x, 3, 2, 1)
-    skip = _bn(sd, f"{prefix}.skipbn", F.conv2d(inp, sd[f"{prefix}.skip.weight"], None, 2))   # xception.py:94-96
+    skip = _bn(sd, f"{prefix}.skipbn", F.conv2d(inp, sd[f"{prefix}.skip.weight"], None, 2), training)   # xception.py:94-96
     return x + skip                                                                            # xception.py:100
 
 
-def entry_flow(sd: SD, frames: torch.Tensor, taps: Optional[dict] = None, prefix: str = "xcep.model") -> torch.Tensor:
+def entry_flow(sd: SD, frames: torch.Tensor, taps: Optional[dict] = None, prefix: str = "xcep.model",
+               training: bool = False) -> torch.Tensor:
     """Xception.low_level_features, xception.py:193-206.  frames [n,3,H,W] -> [n,728,19,19]."""
-    x = F.relu(_bn(sd, f"{prefix}.bn1", F.conv2d(frames, sd[f"{prefix}.conv1.weight"], None, 2)))   # :194-196
-    x = F.relu(_bn(sd, f"{prefix}.bn2", F.conv2d(x, sd[f"{prefix}.conv2.weight"])))                 # :198-200
+    x = F.relu(_bn(sd, f"{prefix}.bn1", F.conv2d(frames, sd[f"{prefix}.conv1.weight"], None, 2), training))   # :194-196
+    x = F.relu(_bn(sd, f"{prefix}.bn2", F.conv2d(x, sd[f"{prefix}.conv2.weight"]), training))                 # :198-200
     if taps is not None:
         taps["stem"] = x
-    x = _block(sd, f"{prefix}.block1", x, start_with_relu=False)   # xception.py:126
+    x = _block(sd, f"{prefix}.block1", x, start_with_relu=False, training=training)   # xception.py:126
     if taps is not None:
         taps["block1"] = x
-    x = _block(sd, f"{prefix}.block2", x, start_with_relu=True)    # xception.py:127
+    x = _block(sd, f"{prefix}.block2", x, start_with_relu=True, training=training)    # xception.py:127
     if taps is not None:
         taps["block2"] = x
-    x = _block(sd, f"{prefix}.block3", x, start_with_relu=True)    # xception.py:128
+    x = _block(sd, f"{prefix}.block3", x, start_with_relu=True, training=training)    # xception.py:128
     if taps is not None:
         taps["block3"] = x
     return x
@@ -161,10 +168,11 @@ def transformer(sd: SD, x: torch.Tensor, taps: Optional[dict] = None, prefix: st
     return _ln(sd, f"{prefix}.norm", x)                                                   # vivit.py:101
 
 
-def forward(sd: SD, clips: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
-    """XceptionVidTr.forward, vivit.py:202-208, + DSTTr.forward vivit.py:132-148.  clips [B,T,3,H,W] -> [B,1]."""
+def forward(sd: SD, clips: torch.Tensor, taps: Optional[dict] = None, training: bool = False) -> torch.Tensor:
+    """XceptionVidTr.forward, vivit.py:202-208, + DSTTr.forward vivit.py:132-148.  clips [B,T,3,H,W] -> [B,1].
+    `training` selects BatchNorm batch statistics (the only train/eval difference on the path: dropout p = 0)."""
     b, t = clips.shape[:2]
-    feats = entry_flow(sd, clips.reshape(b * t, *clips.shape[2:]), taps)                  # vivit.py:204-205
+    feats = entry_flow(sd, clips.reshape(b * t, *clips.shape[2:]), taps, training=training)   # vivit.py:204-205
     feats = feats.reshape(b, t, *feats.shape[1:])                                         # vivit.py:206
     x = build_tokens(sd, feats)
     if taps is not None:
@@ -172,6 +180,52 @@ def forward(sd: SD, clips: torch.Tensor, taps: Optional[dict] = None) -> torch.T
     x = transformer(sd, x, taps)
     x = x.reshape(b, t + 1, TOKENS_PER_FRAME, -1)[:, 0, 0]                                # vivit.py:144-146
     return F.linear(_ln(sd, "vit.mlp_head.0", x), sd["vit.mlp_head.1.weight"], sd["vit.mlp_head.1.bias"])  # :148
+
+
+# ------------------------------------------------------------------------------------------------
+# training step (train_CNN.py:146-148,196-201,513-533)
+# ------------------------------------------------------------------------------------------------
+def on_path_parameter_keys(sd: SD) -> List[str]:
+    """state_dict keys of the parameters that receive a gradient."""
+    keys = []
+    for k, v in sd.items():
+        if not v.dtype.is_floating_point or k.endswith(("running_mean", "running_var")):
+            continue
+        if k.startswith("vit.") or any(
+                k.startswith(f"xcep.model.{m}") for m in ("conv1.", "bn1.", "conv2.", "bn2.", "block1.", "block2.", "block3.")):
+            keys.append(k)
+    return keys
+
+
+def loss_and_grads(sd: SD, clips: torch.Tensor, labels: torch.Tensor, train_entry_flow: bool = True):
+    """outputs = model(image); loss = BCEWithLogitsLoss()(outputs.view(-1), labels.float()); loss.backward()
+    (train_CNN.py:517,526,532) with the model in train mode.  Returns (loss, logits, {key: grad}); BatchNorm running
+    statistics in `sd` are updated in place when the entry flow trains."""
+    keys = [k for k in on_path_parameter_keys(sd) if train_entry_flow or k.startswith("vit.")]
+    work = dict(sd)
+    leaves = {}
+    for k in keys:
+        leaves[k] = sd[k].detach().clone().requires_grad_(True)
+        work[k] = leaves[k]
+    logits = forward(work, clips, training=train_entry_flow)
+    loss = F.binary_cross_entropy_with_logits(logits.view(-1), labels.float())
+    grads = torch.autograd.grad(loss, [leaves[k] for k in keys])
+    if train_entry_flow:
+        for k in sd:
+            if k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+                sd[k] = work[k]
+    return loss.detach(), logits.detach(), dict(zip(keys, grads))
+
+
+def adamw_update(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float,
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01) -> None:
+    """torch.optim.AdamW (train_CNN.py:199), in place on p, m, v."""
+    p.mul_(1 - lr * weight_decay)
+    m.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+    v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    bc1 = 1 - betas[0] ** step
+    bc2 = 1 - betas[1] ** step
+    p.addcdiv_(m, (v.sqrt() / bc2 ** 0.5).add_(eps), value=-lr / bc1)
 
 
 # ------------------------------------------------------------------------------------------------

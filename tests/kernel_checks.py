@@ -519,6 +519,104 @@ def check_adamw():
     return out
 
 
+
+def check_entry_train_kernels():
+    """BatchNorm (batch statistics) fwd/bwd, pool+add with arg-max and its backward, depthwise weight gradient,
+    block-input gradient, im2col^T operands — each against torch autograd."""
+    ops = _ops()
+    out = {}
+    # ---- BatchNorm2d training mode ----
+    for (n, h, w, c, relu) in ((3, 19, 17, 728, False), (2, 37, 37, 64, True), (2, 21, 20, 32, True)):
+        x = (_rand(n, h, w, c, seed=c) * 1.7 + 0.4).to(torch.bfloat16)
+        bn = torch.nn.BatchNorm2d(c).to(DEV)
+        with torch.no_grad():
+            bn.weight.copy_(_rand(c, seed=1) * 0.2 + 1); bn.bias.copy_(_rand(c, seed=2) * 0.1)
+            bn.running_mean.copy_(_rand(c, seed=3) * 0.1); bn.running_var.copy_(_rand(c, seed=4).abs() + 0.5)
+        ref_bn = torch.nn.BatchNorm2d(c).to(DEV)
+        ref_bn.load_state_dict(bn.state_dict())
+        xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        yr = ref_bn(xr)
+        yr = torch.relu(yr) if relu else yr
+        dy = _rand(n, h, w, c, seed=9).to(torch.bfloat16)
+        yr.backward(dy.float().permute(0, 3, 1, 2))
+        y, st = ops.batchnorm_train(x, bn, relu)
+        tag = f"bn{c}"
+        out[tag + "_y"] = _assert_close("bn train y", y.float(), yr.permute(0, 2, 3, 1), TOL_BF16)
+        out[tag + "_rm"] = _assert_close("bn running_mean", bn.running_mean, ref_bn.running_mean, 1e-4)
+        out[tag + "_rv"] = _assert_close("bn running_var", bn.running_var, ref_bn.running_var, 1e-4)
+        assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
+        dg, db = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+        dx = ops.batchnorm_bwd(dy, x, st, dg, db, relu)
+        out[tag + "_dx"] = _assert_close("bn bwd dx", dx.float(), xr.grad.permute(0, 2, 3, 1), 1.5e-2)
+        out[tag + "_dg"] = _assert_close("bn bwd dgamma", dg, ref_bn.weight.grad, 5e-3)
+        out[tag + "_db"] = _assert_close("bn bwd dbeta", db, ref_bn.bias.grad, 5e-3)
+    # ---- maxpool(3,2,1) + skip with arg-max, and its backward ----
+    for (n, h, w, c) in ((2, 37, 37, 64), (3, 10, 7, 8)):
+        # distinct values per window (no bf16 ties): arg-max routing is then unambiguous
+        x = (torch.randperm(n * h * w * c, generator=torch.Generator().manual_seed(5)).float().reshape(n, h, w, c)
+             / (n * h * w * c) * 200 - 100).to(DEV)
+        xb = x.to(torch.bfloat16)
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        skip = _rand(n, ho, wo, c, seed=6).to(torch.bfloat16)
+        xr = xb.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        yr = F.max_pool2d(xr, 3, 2, 1) + skip.float().permute(0, 3, 1, 2)
+        dy = _rand(n, ho, wo, c, seed=7).to(torch.bfloat16)
+        yr.backward(dy.float().permute(0, 3, 1, 2))
+        y, amax = ops.pool_add_idx(xb, skip)
+        out[f"pool_y_{h}"] = _assert_close("pool_add_idx y", y.float(), yr.permute(0, 2, 3, 1), TOL_BF16)
+        dx = ops.pool_bwd(dy, amax, h, w)
+        out[f"pool_dx_{h}"] = _assert_close("pool_bwd dx", dx.float(), xr.grad.permute(0, 2, 3, 1), TOL_BF16)
+    # token variant + token-gradient gather
+    b, t, c = 2, 3, 16
+    xb = _rand(b * t, 37, 37, c, seed=8).to(torch.bfloat16)
+    skip = _rand(b * t, 19, 19, c, seed=9).to(torch.bfloat16)
+    pos = _rand(t, 362, c, seed=10)
+    tokens = torch.zeros(b, t + 1, 362, c, device=DEV)
+    _, amax = ops.pool_add_idx(xb, skip, tokens=tokens, pos_emb=pos, t_frames=t)
+    ref = (F.max_pool2d(xb.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1) + skip.float()).reshape(b, t, 361, c)
+    out["pool_tokens"] = _assert_close("pool_add_idx tokens", tokens[:, 1:, 1:], ref + pos[None, :, 1:], 1e-5)
+    gt = _rand(b, t + 1, 362, c, seed=11)
+    out["token_gather"] = _assert_close("token_grad_gather", ops.token_grad_gather(gt).float(),
+                                        gt[:, 1:, 1:].reshape(b * t, 19, 19, c), TOL_BF16)
+    # ---- depthwise weight gradient + data gradient via flipped taps, block-input gradient ----
+    for (n, h, w, c, relu_in) in ((2, 37, 37, 64, True), (3, 19, 21, 728, False), (1, 9, 9, 8, True)):
+        xb = _rand(n, h, w, c, seed=c).to(torch.bfloat16)
+        wt = _rand(3, 3, c, seed=2) * 0.3
+        dy = _rand(n, h, w, c, seed=3).to(torch.bfloat16)
+        xr = xb.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        wr = wt.permute(2, 0, 1).unsqueeze(1).clone().requires_grad_(True)           # [c, 1, 3, 3]
+        yr = F.conv2d(torch.relu(xr) if relu_in else xr, wr, None, 1, 1, 1, groups=c)
+        yr.backward(dy.float().permute(0, 3, 1, 2))
+        dw = torch.zeros(3, 3, c, device=DEV)
+        ops.dwconv3x3_wgrad(xb, dy, dw, relu_in)
+        out[f"dw_wgrad_{c}"] = _assert_close("dwconv wgrad", dw, wr.grad[:, 0].permute(1, 2, 0), 2e-3)
+        d_main = ops.dwconv3x3(dy, wt.flip(0, 1).contiguous(), relu_in=False)
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        d_skip = _rand(n, ho, wo, c, seed=4).to(torch.bfloat16)
+        dx = ops.block_input_grad(d_main, xb, d_skip, relu_in)
+        want = xr.grad.permute(0, 2, 3, 1).clone()
+        want[:, ::2, ::2] += d_skip.float()
+        out[f"block_in_{c}"] = _assert_close("dwconv dgrad + block input grad", dx.float(), want, 1.5e-2)
+    # ---- im2col^T operands ----
+    xb = _rand(2, 11, 9, 32, seed=1).to(torch.bfloat16)
+    cols = ops.im2col_t(xb)
+    m = 2 * 9 * 7
+    ref = torch.stack([xb[:, ky:ky + 9, kx:kx + 7, :].reshape(m, 32) for ky in range(3) for kx in range(3)], 0)  # [9, m, 32]
+    assert torch.equal(cols[:, :m].reshape(9, 32, m), ref.permute(0, 2, 1)), "im2col_t"
+    xf = _rand(2, 3, 21, 19, seed=2)
+    cols = ops.im2col_t_stem(xf)
+    ho, wo = 10, 9
+    unf = F.unfold(xf, 3, stride=2)                                 # [2, 27, ho*wo], k = ci*9 + ky*3 + kx
+    ref = unf.permute(1, 0, 2).reshape(27, 2 * ho * wo)
+    out["im2col_stem"] = _assert_close("im2col_t_stem", cols[:27, :2 * ho * wo].float(), ref, TOL_BF16)
+    assert float(cols[27:].abs().max()) == 0.0
+    # conv stem without ReLU
+    wt = _rand(32, 3, 3, 3, seed=3) * 0.2
+    y = ops.conv_stem_raw(xf, wt)
+    out["stem_raw"] = _assert_close("conv_stem_raw", y.float(), F.conv2d(xf, wt, None, 2).permute(0, 2, 3, 1), TOL_BF16)
+    return out
+
+
 CHECKS = {
     "layernorm": check_layernorm,
     "layernorm_diff": check_layernorm_diff,
@@ -540,4 +638,5 @@ CHECKS = {
     "attn_spatial_bwd": check_attn_spatial_bwd,
     "head_token_bwd": check_head_token_bwd,
     "adamw": check_adamw,
+    "entry_train_kernels": check_entry_train_kernels,
 }

@@ -21,3 +21,8 @@ def test_against_cpu_oracle(precision):
 @pytest.mark.gpu
 def test_api_boundary():
     model_checks.run_api_checks()
+
+
+@pytest.mark.gpu
+def test_training_step_against_reference_golden():
+    model_checks.run_train_golden()

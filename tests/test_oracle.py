@@ -103,3 +103,32 @@ def test_against_live_reference():
     x = make_input(1, 6, seed=5)
     with torch.no_grad():
         assert torch.equal(ref(x), O.forward(sd, x))
+
+
+def test_oracle_training_step_against_reference_golden():
+    """Oracle in train mode (BatchNorm batch statistics) + autograd + AdamW restatement vs the golden vectors that
+    oracle/make_golden_train.py recorded from the UNMODIFIED reference (train_CNN.py:226,513-533)."""
+    O = oracle()
+    path = GOLDEN.replace("istvt_golden.pt", "istvt_golden_train.pt")
+    g = torch.load(path, weights_only=False)
+    model = build_model({"seed": g["seed"], "frames": g["frames"], "sensitised": g["sensitised"]})
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    before = {k: sd[k].clone() for k in g["params_after"]}
+    x = make_input(g["batch"], g["frames"])
+    loss, logits, grads = O.loss_and_grads(sd, x, torch.tensor(g["labels"]))
+    assert abs(float(loss) - g["loss"]) <= 1e-6 * abs(g["loss"])
+    assert torch.allclose(logits, g["logits"], rtol=0, atol=1e-6)
+    assert sorted(grads) == sorted(g["grads"]) and len(grads) == 252
+    assert len(g["params_without_grad"]) == 117                       # SURVEY.md §3.2
+    def fp_err(t, w):
+        flat = t.detach().float().reshape(-1)
+        idx = O.fingerprint_indices(flat.numel(), count=256)
+        return (flat[idx] - w["samples"]).abs().max().item() / max(w["absmax"], 1e-30)
+    for k, gr in grads.items():
+        assert fp_err(gr, g["grads"][k]) <= 1e-5, k
+    for k, w in g["running_after"].items():
+        assert fp_err(sd[k], w) <= 1e-6, k
+    for k, gr in grads.items():
+        p = before[k].clone()
+        O.adamw_update(p, gr, torch.zeros_like(p), torch.zeros_like(p), 1, g["lr"], weight_decay=g["weight_decay"])
+        assert fp_err(p, g["params_after"][k]) <= 1e-5, k
