@@ -60,6 +60,10 @@ SIGNATURES = {
     "istvt_block_input_grad": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "istvt_im2col_t": [_P, _P, _I, _I, _I, _I, _L, _P],
     "istvt_im2col_t_stem": [_P, _P, _I, _I, _I, _L, _P],
+    # relevance pass
+    "istvt_attn_spatial_bwd_cam": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "istvt_attn_temporal_bwd_cam": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "istvt_rollout_row": [_P, _P, _L, _I, _P],
 }
 _RESTYPES = {"istvt_error_string": c_char_p, "istvt_launch_count": c_int64}
 

@@ -21,7 +21,7 @@ constexpr int SB_KB = 128;            // keys per CTA
 constexpr int SB_QB = 64;             // queries per iteration
 constexpr int SB_LD = SB_DH + 8;      // smem row pitch (elements) of the [*, 64] tiles: 144 B, conflict-free ldmatrix
 constexpr int SB_LDP = SB_KB + 8;     // pitch of the P / dS tiles: 272 B
-constexpr int SB_THREADS = 256;
+constexpr int SB_THREADS = 512;   // 16 warps: 4 per scheduler hide the ldmatrix -> mma latency (8 warps: 105 TFLOP/s)
 constexpr int SB_SMEM = (2 * SB_KB * SB_LD + 2 * SB_QB * SB_LD + 2 * SB_QB * SB_LDP) * 2 + 2 * SB_QB * 4;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t pkbf(float a, float b) {
 __global__ void __launch_bounds__(SB_THREADS, 1)
 attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ dout,
                         const float* __restrict__ lse, bf16* __restrict__ dqkv, float* __restrict__ dq_acc,
-                        int tokens, int heads, float scale) {
+                        float* __restrict__ cam, int tokens, int heads, float scale) {
     extern __shared__ __align__(16) uint8_t sb_smem[];
     bf16* sK = reinterpret_cast<bf16*>(sb_smem);          // [128][72]
     bf16* sV = sK + SB_KB * SB_LD;                        // [128][72]
@@ -87,14 +87,16 @@ attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o
         *reinterpret_cast<uint4*>(sV + r * SB_LD + c) = vv;
     }
 
-    float dk[8][4], dv[8][4];
+    float dk[4][4], dv[4][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) { dk[j][e] = 0.f; dv[j][e] = 0.f; }
 
     const int wm = warp & 3;      // 16-row slab of the query block (S / dP / dQ)
-    const int wn = warp >> 2;     // 64-key half (S / dP), 32-dim half (dQ)
+    const int wn = warp >> 2;     // 32-key quarter (S / dP), 16-dim quarter (dQ)
+    const int wk = warp & 7;      // 16-key slab of dK / dV
+    const int wd = warp >> 3;     // 32-dim half of dK / dV
     const int q_blocks = (tokens + SB_QB - 1) / SB_QB;
 
     for (int qb = 0; qb < q_blocks; ++qb) {
@@ -112,20 +114,18 @@ attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o
             *reinterpret_cast<uint4*>(sdO + r * SB_LD + c) = dov;
         }
         {
-            const int r = tid >> 2, part = tid & 3;    // 4 threads per row, 16 dims each
+            const int r = tid >> 3, part = tid & 7;    // 8 threads per row, 8 dims each
             float acc = 0.f;
             if (q0 + r < tokens) {
                 float a[8], b[8];
+                load8(dout + (row0 + q0 + r) * inner + h * SB_DH + part * 8, a);
+                load8(o + (row0 + q0 + r) * inner + h * SB_DH + part * 8, b);
 #pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf) {
-                    load8(dout + (row0 + q0 + r) * inner + h * SB_DH + part * 16 + hlf * 8, a);
-                    load8(o + (row0 + q0 + r) * inner + h * SB_DH + part * 16 + hlf * 8, b);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc = fmaf(a[e], b[e], acc);
-                }
+                for (int e = 0; e < 8; ++e) acc = fmaf(a[e], b[e], acc);
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
             if (part == 0) {
                 sD[r] = acc;
                 sL[r] = (q0 + r < tokens) ? lse[(static_cast<int64_t>(bf) * heads + h) * tokens + q0 + r] : INFINITY;
@@ -134,9 +134,9 @@ attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o
         __syncthreads();
 
         // ---- S = Q K^T and dP = dO V^T for this warp's 16 x 64 sub-tile ----
-        float s[8][4], dp[8][4];
+        float s[4][4], dp[4][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) { s[j][e] = 0.f; dp[j][e] = 0.f; }
 #pragma unroll
@@ -145,9 +145,9 @@ attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o
             ldsm_x4(aq, sQ + (wm * 16 + (lmat & 1) * 8 + lr) * SB_LD + kk * 16 + (lmat >> 1) * 8);
             ldsm_x4(ao, sdO + (wm * 16 + (lmat & 1) * 8 + lr) * SB_LD + kk * 16 + (lmat >> 1) * 8);
 #pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {       // two 8-key n-tiles per ldmatrix.x4
+            for (int jp = 0; jp < 2; ++jp) {       // two 8-key n-tiles per ldmatrix.x4
                 uint32_t bk[4], bv[4];
-                const int krow = wn * 64 + jp * 16 + (lmat >> 1) * 8 + lr;
+                const int krow = wn * 32 + jp * 16 + (lmat >> 1) * 8 + lr;
                 ldsm_x4(bk, sK + krow * SB_LD + kk * 16 + (lmat & 1) * 8);
                 ldsm_x4(bv, sV + krow * SB_LD + kk * 16 + (lmat & 1) * 8);
                 mma16816(s[2 * jp], aq, bk[0], bk[1]);
@@ -162,8 +162,8 @@ attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o
             const float l0 = sL[r0], l1 = sL[r1];
             const float d0 = sD[r0], d1 = sD[r1];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int kl = wn * 64 + j * 8 + 2 * t;          // key inside the block
+            for (int j = 0; j < 4; ++j) {
+                const int kl = wn * 32 + j * 8 + 2 * t;          // key inside the block
                 const bool ok0 = key0 + kl < tokens, ok1 = key0 + kl + 1 < tokens;
                 float p00 = ok0 ? exp2f(fmaf(s[j][0], scale_log2, -l0)) : 0.f;
                 float p01 = ok1 ? exp2f(fmaf(s[j][1], scale_log2, -l0)) : 0.f;
@@ -175,52 +175,63 @@ attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o
                     pkbf(p00 * (dp[j][0] - d0) * scale, p01 * (dp[j][1] - d0) * scale);
                 *reinterpret_cast<uint32_t*>(sdS + r1 * SB_LDP + kl) =
                     pkbf(p10 * (dp[j][2] - d1) * scale, p11 * (dp[j][3] - d1) * scale);
+                if (cam != nullptr) {
+                    // relevance pass: cam[frame, q, k] += relu(dA o A) / heads, dA = dP (gradient w.r.t. the probabilities)
+                    const float ih = 1.0f / static_cast<float>(heads);
+                    const int kg = key0 + kl;
+                    float* c0 = cam + (static_cast<int64_t>(bf) * tokens + q0 + r0) * tokens + kg;
+                    float* c1 = cam + (static_cast<int64_t>(bf) * tokens + q0 + r1) * tokens + kg;
+                    if (q0 + r0 < tokens) {
+                        if (ok0) atomicAdd(c0, fmaxf(p00 * dp[j][0], 0.f) * ih);
+                        if (ok1) atomicAdd(c0 + 1, fmaxf(p01 * dp[j][1], 0.f) * ih);
+                    }
+                    if (q0 + r1 < tokens) {
+                        if (ok0) atomicAdd(c1, fmaxf(p10 * dp[j][2], 0.f) * ih);
+                        if (ok1) atomicAdd(c1 + 1, fmaxf(p11 * dp[j][3], 0.f) * ih);
+                    }
+                }
             }
         }
         __syncthreads();
 
-        // ---- dV += P^T dO, dK += dS^T Q: this warp owns keys [16 warp, 16 warp + 16) x 64 dims ----
+        // ---- dV += P^T dO, dK += dS^T Q: this warp owns keys [16 wk, 16 wk + 16) x dims [32 wd, 32 wd + 32) ----
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {           // 16 queries per step
             uint32_t ap[4], as_[4];
             // A[m = key][k = query] = X[query][key]: transposed 8x8 loads
-            ldsm_x4_t(ap, sP + (kk * 16 + (lmat >> 1) * 8 + lr) * SB_LDP + warp * 16 + (lmat & 1) * 8);
-            ldsm_x4_t(as_, sdS + (kk * 16 + (lmat >> 1) * 8 + lr) * SB_LDP + warp * 16 + (lmat & 1) * 8);
+            ldsm_x4_t(ap, sP + (kk * 16 + (lmat >> 1) * 8 + lr) * SB_LDP + wk * 16 + (lmat & 1) * 8);
+            ldsm_x4_t(as_, sdS + (kk * 16 + (lmat >> 1) * 8 + lr) * SB_LDP + wk * 16 + (lmat & 1) * 8);
 #pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {       // two 8-dim n-tiles per ldmatrix.x4
+            for (int jp = 0; jp < 2; ++jp) {       // two 8-dim n-tiles per ldmatrix.x4
                 uint32_t bo[4], bq[4];
                 // B[k = query][n = dim] = X[query][dim]: rows are k -> transposed loads
-                ldsm_x4_t(bo, sdO + (kk * 16 + (lmat & 1) * 8 + lr) * SB_LD + jp * 16 + (lmat >> 1) * 8);
-                ldsm_x4_t(bq, sQ + (kk * 16 + (lmat & 1) * 8 + lr) * SB_LD + jp * 16 + (lmat >> 1) * 8);
+                ldsm_x4_t(bo, sdO + (kk * 16 + (lmat & 1) * 8 + lr) * SB_LD + wd * 32 + jp * 16 + (lmat >> 1) * 8);
+                ldsm_x4_t(bq, sQ + (kk * 16 + (lmat & 1) * 8 + lr) * SB_LD + wd * 32 + jp * 16 + (lmat >> 1) * 8);
                 mma16816(dv[2 * jp], ap, bo[0], bo[1]);
                 mma16816(dv[2 * jp + 1], ap, bo[2], bo[3]);
                 mma16816(dk[2 * jp], as_, bq[0], bq[1]);
                 mma16816(dk[2 * jp + 1], as_, bq[2], bq[3]);
             }
         }
-        // ---- dQ partial = dS K for rows [16 wm, +16) x dims [32 wn, +32), accumulated across key blocks ----
+        // ---- dQ partial = dS K for rows [16 wm, +16) x dims [16 wn, +16), accumulated across key blocks ----
         {
-            float dq[4][4];
+            float dq[2][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) dq[j][e] = 0.f;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {       // 16 keys per step
-                uint32_t a[4];
+                uint32_t a[4], b[4];
                 ldsm_x4(a, sdS + (wm * 16 + (lmat & 1) * 8 + lr) * SB_LDP + kk * 16 + (lmat >> 1) * 8);
-#pragma unroll
-                for (int jp = 0; jp < 2; ++jp) {
-                    uint32_t b[4];
-                    ldsm_x4_t(b, sK + (kk * 16 + (lmat & 1) * 8 + lr) * SB_LD + wn * 32 + jp * 16 + (lmat >> 1) * 8);
-                    mma16816(dq[2 * jp], a, b[0], b[1]);
-                    mma16816(dq[2 * jp + 1], a, b[2], b[3]);
-                }
+                ldsm_x4_t(b, sK + (kk * 16 + (lmat & 1) * 8 + lr) * SB_LD + wn * 16 + (lmat >> 1) * 8);
+                mma16816(dq[0], a, b[0], b[1]);
+                mma16816(dq[1], a, b[2], b[3]);
             }
             const int r0 = q0 + wm * 16 + g, r1 = r0 + 8;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int d = h * SB_DH + wn * 32 + j * 8 + 2 * t;
+            for (int j = 0; j < 2; ++j) {
+                const int d = h * SB_DH + wn * 16 + j * 8 + 2 * t;
                 if (r0 < tokens) {
                     float* dst = dq_acc + (row0 + r0) * inner + d;
                     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(dq[j][0]), "f"(dq[j][1]) : "memory");
@@ -235,10 +246,10 @@ attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o
 
     // ---- dK, dV -> dqkv (k columns at inner, v columns at 2 inner) ----
     {
-        const int r0 = key0 + warp * 16 + g, r1 = r0 + 8;
+        const int r0 = key0 + wk * 16 + g, r1 = r0 + 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int d = h * SB_DH + j * 8 + 2 * t;
+        for (int j = 0; j < 4; ++j) {
+            const int d = h * SB_DH + wd * 32 + j * 8 + 2 * t;
             if (r0 < tokens) {
                 bf16* base = dqkv + (row0 + r0) * (3 * inner) + d;
                 *reinterpret_cast<uint32_t*>(base + inner) = pkbf(dk[j][0], dk[j][1]);
@@ -273,9 +284,9 @@ using namespace istvt;
 // qkv: bf16 [batch_frames*tokens, 3*heads*64]; o, dout: bf16 [rows, heads*64]; lse: fp32 [batch_frames, heads, tokens]
 // (log2 domain, from istvt_attn_spatial_fwd_lse); dqkv: bf16 [rows, 3*heads*64] (fully written);
 // dq_scratch: fp32 [rows, heads*64] workspace (zero-filled by this call).
-extern "C" int istvt_attn_spatial_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
-                                      float* dq_scratch, int batch_frames, int tokens, int heads, float scale,
-                                      istvt_stream_t stream) {
+static int attn_spatial_bwd_launch(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
+                                   float* dq_scratch, float* cam, int batch_frames, int tokens, int heads, float scale,
+                                   istvt_stream_t stream) {
     ISTVT_REQUIRE(qkv && o && dout && lse && dqkv && dq_scratch);
     ISTVT_REQUIRE(batch_frames > 0 && tokens > 0 && heads > 0);
     ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(dout) |
@@ -290,11 +301,26 @@ extern "C" int istvt_attn_spatial_bwd(const void* qkv, const void* o, const void
     ISTVT_REQUIRE(grid < (int64_t(1) << 31));
     attn_spatial_bwd_kernel<<<static_cast<unsigned>(grid), SB_THREADS, SB_SMEM, st>>>(
         static_cast<const bf16*>(qkv), static_cast<const bf16*>(o), static_cast<const bf16*>(dout), lse,
-        static_cast<bf16*>(dqkv), dq_scratch, tokens, heads, scale);
+        static_cast<bf16*>(dqkv), dq_scratch, cam, tokens, heads, scale);
     count_launch();
     const int64_t n = rows * (inner / 8);
     attn_spatial_bwd_dq_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(dq_scratch,
                                                                                        static_cast<bf16*>(dqkv), rows, inner);
     count_launch();
     return launch_status();
+}
+
+extern "C" int istvt_attn_spatial_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
+                                      float* dq_scratch, int batch_frames, int tokens, int heads, float scale,
+                                      istvt_stream_t stream) {
+    return attn_spatial_bwd_launch(qkv, o, dout, lse, dqkv, dq_scratch, nullptr, batch_frames, tokens, heads, scale, stream);
+}
+
+// Same backward, additionally accumulating the head-averaged gradient-weighted attention of the relevance pass:
+// cam[batch_frames, tokens, tokens] (fp32, zero-filled by the caller) += relu(dA o A) / heads.
+extern "C" int istvt_attn_spatial_bwd_cam(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
+                                          float* dq_scratch, float* cam, int batch_frames, int tokens, int heads,
+                                          float scale, istvt_stream_t stream) {
+    ISTVT_REQUIRE(cam != nullptr);
+    return attn_spatial_bwd_launch(qkv, o, dout, lse, dqkv, dq_scratch, cam, batch_frames, tokens, heads, scale, stream);
 }

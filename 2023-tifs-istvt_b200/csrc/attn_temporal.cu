@@ -257,8 +257,8 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
 __global__ void __launch_bounds__(256)
 attn_temporal_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
                              const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqk,
-                             __nv_bfloat16* __restrict__ dv, int frames, int tokens, int heads, float scale,
-                             int64_t units) {
+                             __nv_bfloat16* __restrict__ dv, float* __restrict__ cam, int frames, int tokens, int heads,
+                             float scale, int64_t units) {
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2;
     const int t = lane & 3;
@@ -328,6 +328,13 @@ attn_temporal_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bf
     dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
     const float ds0 = p0 * (dp[0] - dsum) * scale;
     const float ds1 = p1 * (dp[1] - dsum) * scale;
+    if (cam != nullptr && g < frames) {
+        // relevance pass: cam[b, pos, i, j] += relu(dA o A) / heads
+        float* cr = cam + ((b * tokens + pos) * frames + g) * frames;
+        const float ih = 1.0f / static_cast<float>(heads);
+        if (2 * t < frames) atomicAdd(cr + 2 * t, fmaxf(p0 * dp[0], 0.f) * ih);
+        if (2 * t + 1 < frames) atomicAdd(cr + 2 * t + 1, fmaxf(p1 * dp[1], 0.f) * ih);
+    }
     auto pk = [](float x, float y) {
         const __nv_bfloat162 r = __floats2bfloat162_rn(x, y);
         return *reinterpret_cast<const uint32_t*>(&r);
@@ -414,8 +421,8 @@ extern "C" int istvt_attn_temporal_fwd(const void* qk, const void* v, void* out,
     return ISTVT_ERR_INVALID_ARG;
 }
 
-extern "C" int istvt_attn_temporal_bwd(const void* qk, const void* v, const void* dout, void* dqk, void* dv, int batch,
-                                       int frames, int tokens, int heads, float scale, istvt_stream_t stream) {
+static int attn_temporal_bwd_launch(const void* qk, const void* v, const void* dout, void* dqk, void* dv, float* cam,
+                                    int batch, int frames, int tokens, int heads, float scale, istvt_stream_t stream) {
     ISTVT_REQUIRE(qk && v && dout && dqk && dv);
     ISTVT_REQUIRE(batch > 0 && frames > 0 && tokens > 0 && heads > 0);
     if (frames > 8) return ISTVT_ERR_UNSUPPORTED;   // training is built for the ISTVT configuration (T = 6, F = 7)
@@ -426,8 +433,21 @@ extern "C" int istvt_attn_temporal_bwd(const void* qk, const void* v, const void
     ISTVT_REQUIRE(grid < (int64_t(1) << 31));
     attn_temporal_bwd_mma_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v),
-        static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv),
+        static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), cam,
         frames, tokens, heads, scale, units);
     count_launch();
     return launch_status();
+}
+
+extern "C" int istvt_attn_temporal_bwd(const void* qk, const void* v, const void* dout, void* dqk, void* dv, int batch,
+                                       int frames, int tokens, int heads, float scale, istvt_stream_t stream) {
+    return attn_temporal_bwd_launch(qk, v, dout, dqk, dv, nullptr, batch, frames, tokens, heads, scale, stream);
+}
+
+// Relevance pass variant: cam[batch, tokens, frames, frames] (fp32, zero-filled by the caller) += relu(dA o A) / heads.
+extern "C" int istvt_attn_temporal_bwd_cam(const void* qk, const void* v, const void* dout, void* dqk, void* dv, float* cam,
+                                           int batch, int frames, int tokens, int heads, float scale,
+                                           istvt_stream_t stream) {
+    ISTVT_REQUIRE(cam != nullptr);
+    return attn_temporal_bwd_launch(qk, v, dout, dqk, dv, cam, batch, frames, tokens, heads, scale, stream);
 }

@@ -43,22 +43,21 @@ __device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
 // ------------------------------------------------------------------------------------------
 constexpr int LNB_MAXC = 6;
 template <typename TX, bool ACCUM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, int frames, int tokens_pf,
                      const TX* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ g,
                      bf16* __restrict__ g_bf, bf16* __restrict__ dx_out, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, int64_t rows, int dim, float eps) {
-    __shared__ float s_dg[768], s_db[768];
-    for (int i = threadIdx.x; i < dim; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
-    __syncthreads();
+    // dgamma / dbeta partials live in a per-warp slab of shared memory (each lane owns its columns, no atomics):
+    // keeping them in registers cost 48 registers per thread and held the kernel to one CTA per SM (1.4 TB/s).
+    extern __shared__ __align__(16) float s_part[];          // [warps][2][dim]
     const int lane = threadIdx.x & 31;
     const int nch = dim >> 2;
     const float inv_dim = 1.0f / static_cast<float>(dim);
-    float dg[LNB_MAXC][4], db[LNB_MAXC][4];
-#pragma unroll
-    for (int i = 0; i < LNB_MAXC; ++i)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { dg[i][e] = 0.f; db[i][e] = 0.f; }
+    float* s_dg = s_part + (threadIdx.x >> 5) * 2 * dim;
+    float* s_db = s_dg + dim;
+    for (int i = lane; i < dim; i += 32) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+    __syncwarp();
 
     const int64_t wid = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t wstride = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
@@ -108,8 +107,10 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
                         for (int e = 0; e < 4; ++e) dv[i][e] -= t[e];
                     }
                 }
-                float gm[4];
+                float gm[4], pg[4], pb[4];
                 ld4(gamma + 4 * c, gm);
+                ld4(s_dg + 4 * c, pg);
+                ld4(s_db + 4 * c, pb);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float xh = (xv[i][e] - mean) * rstd;
@@ -117,10 +118,12 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
                     const float a = gm[e] * dv[i][e];
                     s1 += a;
                     s2 = fmaf(a, xh, s2);
-                    dg[i][e] = fmaf(dv[i][e], xh, dg[i][e]);
-                    db[i][e] += dv[i][e];
+                    pg[e] = fmaf(dv[i][e], xh, pg[e]);
+                    pb[e] += dv[i][e];
                     dv[i][e] = a;
                 }
+                st4(s_dg + 4 * c, pg);
+                st4(s_db + 4 * c, pb);
             }
         }
         s1 = warp_sum(s1) * inv_dim;
@@ -145,21 +148,16 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < LNB_MAXC; ++i) {
-        const int c = lane + 32 * i;
-        if (c < nch) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                atomicAdd(&s_dg[4 * c + e], dg[i][e]);
-                atomicAdd(&s_db[4 * c + e], db[i][e]);
-            }
-        }
-    }
     __syncthreads();
+    const int warps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-        atomicAdd(dgamma + i, s_dg[i]);
-        atomicAdd(dbeta + i, s_db[i]);
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < warps; ++w) {
+            a += s_part[w * 2 * dim + i];
+            b += s_part[w * 2 * dim + dim + i];
+        }
+        atomicAdd(dgamma + i, a);
+        atomicAdd(dbeta + i, b);
     }
 }
 
@@ -208,35 +206,43 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
 __global__ void __launch_bounds__(256)
 transpose_colsum_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, float* __restrict__ colsum, int64_t M,
                         int C, int64_t ldo) {
-    __shared__ bf16 tile[64][72];
+    // tile2[rp][c] = (in[2rp][c], in[2rp+1][c]) as one 32-bit word: the read-out side then needs 4 conflict-free
+    // 32-bit loads per 16-byte store instead of 8 two-byte loads (8-way bank conflicts in the first version).
+    __shared__ uint32_t tile2[32][65];
     const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 64;
     const int c0 = blockIdx.y * 64;
     const int tid = threadIdx.x;
+    {
+        const int rp = tid >> 3, cc = (tid & 7) * 8;
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+        if (c0 + cc < C) {
+            if (m0 + 2 * rp < M) a = *reinterpret_cast<const uint4*>(in + (m0 + 2 * rp) * C + c0 + cc);
+            if (m0 + 2 * rp + 1 < M) b = *reinterpret_cast<const uint4*>(in + (m0 + 2 * rp + 1) * C + c0 + cc);
+        }
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int idx = tid + it * 256;          // 512 chunks of 8 columns
-        const int r = idx >> 3, cc = (idx & 7) * 8;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (m0 + r < M && c0 + cc < C) v = *reinterpret_cast<const uint4*>(in + (m0 + r) * C + c0 + cc);
-        *reinterpret_cast<uint4*>(&tile[r][cc]) = v;
+        for (int j = 0; j < 4; ++j) {
+            tile2[rp][cc + 2 * j] = __byte_perm(aw[j], bw[j], 0x5410);
+            tile2[rp][cc + 2 * j + 1] = __byte_perm(aw[j], bw[j], 0x7632);
+        }
     }
     __syncthreads();
     if (colsum != nullptr && tid < 64 && c0 + tid < C) {
         float s = 0.f;
 #pragma unroll 8
-        for (int r = 0; r < 64; ++r) s += __bfloat162float(tile[r][tid]);
+        for (int r = 0; r < 32; ++r) {
+            const uint32_t w = tile2[r][tid];
+            s += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
+        }
         atomicAdd(colsum + c0 + tid, s);
     }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const int idx = tid + it * 256;
-        const int c = idx >> 3, mm = (idx & 7) * 8;   // output row c, 8 consecutive m
-        if (c0 + c < C && m0 + mm < ldo) {
-            bf16 tmp[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) tmp[e] = tile[mm + e][c];
-            *reinterpret_cast<uint4*>(out + static_cast<int64_t>(c0 + c) * ldo + m0 + mm) =
-                *reinterpret_cast<const uint4*>(tmp);
+        const int c = idx >> 3, mg = idx & 7;          // output row c, 8 consecutive m = row pairs 4 mg .. 4 mg + 3
+        if (c0 + c < C && m0 + mg * 8 < ldo) {
+            const uint4 v = make_uint4(tile2[mg * 4][c], tile2[mg * 4 + 1][c], tile2[mg * 4 + 2][c], tile2[mg * 4 + 3][c]);
+            *reinterpret_cast<uint4*>(out + static_cast<int64_t>(c0 + c) * ldo + m0 + mg * 8) = v;
         }
     }
 }
@@ -376,6 +382,27 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     st4(p + 4 * i, pv); st4(m + 4 * i, mv); st4(v + 4 * i, vv);
 }
 
+// ------------------------------------------------------------------------------------------
+// Relevance rollout, one row: v[n, :] <- v[n, :] (I + C[n]) = v + v C  (C: [n, L, L], L <= 1024).
+// Only row 0 (the class token's row) of the rolled-out product R = (I + C_12) ... (I + C_1) is ever read
+// (visualize_rel.py:257-262), and e_0^T R can be accumulated from the last layer to the first as vector-matrix
+// products — which is the order the backward pass produces the C_l in.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rollout_row_kernel(float* __restrict__ v, const float* __restrict__ cmat, int len) {
+    __shared__ float sv[1024];
+    const int64_t n = blockIdx.x;
+    float* vr = v + n * len;
+    const float* cm = cmat + n * len * len;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) sv[i] = vr[i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < len; j += blockDim.x) {
+        float acc = sv[j];
+        for (int i = 0; i < len; ++i) acc = fmaf(sv[i], cm[static_cast<int64_t>(i) * len + j], acc);
+        vr[j] = acc;
+    }
+}
+
 static inline unsigned nblk(int64_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
 }  // namespace istvt
@@ -392,28 +419,33 @@ extern "C" int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, 
     ISTVT_REQUIRE(dy2 == nullptr || (frames > 0 && tokens_per_frame > 0));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int64_t blocks = (rows + 7) / 8;
-    const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 2;     // 2 resident CTAs per SM (46 KB smem, <= 128 registers)
     if (blocks > cap) blocks = cap;
     const bf16* d1 = static_cast<const bf16*>(dy);
     const bf16* d2 = static_cast<const bf16*>(dy2);
     bf16* gb = static_cast<bf16*>(g_bf16);
     bf16* dxo = static_cast<bf16*>(dx_out);
     const unsigned gr = static_cast<unsigned>(blocks);
+    const size_t smem = 8 * 2 * static_cast<size_t>(dim) * sizeof(float);
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
     if (x_dtype == ISTVT_F32) {
         const float* xx = static_cast<const float*>(x);
         if (g_accum)
-            layernorm_bwd_kernel<float, true><<<gr, 256, 0, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
+            layernorm_bwd_kernel<float, true><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
                                                                    nullptr, dgamma, dbeta, rows, dim, eps);
         else
-            layernorm_bwd_kernel<float, false><<<gr, 256, 0, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
+            layernorm_bwd_kernel<float, false><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
                                                                     nullptr, dxo, dgamma, dbeta, rows, dim, eps);
     } else if (x_dtype == ISTVT_BF16) {
         const bf16* xx = static_cast<const bf16*>(x);
         if (g_accum)
-            layernorm_bwd_kernel<bf16, true><<<gr, 256, 0, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
+            layernorm_bwd_kernel<bf16, true><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
                                                                   nullptr, dgamma, dbeta, rows, dim, eps);
         else
-            layernorm_bwd_kernel<bf16, false><<<gr, 256, 0, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
+            layernorm_bwd_kernel<bf16, false><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
                                                                    nullptr, dxo, dgamma, dbeta, rows, dim, eps);
     } else {
         return ISTVT_ERR_INVALID_ARG;
@@ -488,6 +520,13 @@ extern "C" int istvt_adamw_step(float* params, const float* grads, float* exp_av
     const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
     adamw_kernel<<<nblk(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         params, grads, exp_avg, exp_avg_sq, n / 4, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_rollout_row(float* v, const float* cmat, int64_t n, int len, istvt_stream_t stream) {
+    ISTVT_REQUIRE(v && cmat && n > 0 && len > 0 && len <= 1024 && n < (int64_t(1) << 31));
+    rollout_row_kernel<<<static_cast<unsigned>(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(v, cmat, len);
     count_launch();
     return launch_status();
 }

@@ -342,8 +342,10 @@ def attn_spatial_lse(qkv: torch.Tensor, batch_frames: int, tokens: int, heads: i
 
 
 def attn_spatial_bwd(qkv: torch.Tensor, o: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, batch_frames: int,
-                     tokens: int, heads: int, scale: float, scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
-    dev = _chk(qkv, o, dout, lse, scratch)
+                     tokens: int, heads: int, scale: float, scratch: Optional[torch.Tensor] = None,
+                     cam: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cam (optional, fp32 [batch_frames, tokens, tokens], zeroed by the caller) += relu(dA o A) / heads."""
+    dev = _chk(qkv, o, dout, lse, scratch, cam)
     inner = heads * 64
     rows = batch_frames * tokens
     if any(t.dtype != torch.bfloat16 for t in (qkv, o, dout)) or lse.dtype != torch.float32:
@@ -355,22 +357,38 @@ def attn_spatial_bwd(qkv: torch.Tensor, o: torch.Tensor, dout: torch.Tensor, lse
         scratch = torch.empty(rows, inner, dtype=torch.float32, device=dev)
     with _launch(dev, "attn_spatial_bwd", 10.0 * batch_frames * heads * tokens * tokens * 64,
                  _nbytes(qkv, o, dout, dqkv)):
-        _lib.check(_lib.lib().istvt_attn_spatial_bwd(_ptr(qkv), _ptr(o), _ptr(dout), _ptr(lse), _ptr(dqkv),
-                                                     _ptr(scratch), batch_frames, tokens, heads, scale, _stream(dev)),
-                   "istvt_attn_spatial_bwd")
+        if cam is None:
+            _lib.check(_lib.lib().istvt_attn_spatial_bwd(_ptr(qkv), _ptr(o), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                                         _ptr(scratch), batch_frames, tokens, heads, scale,
+                                                         _stream(dev)), "istvt_attn_spatial_bwd")
+        else:
+            if cam.dtype != torch.float32 or cam.numel() != batch_frames * tokens * tokens:
+                raise ValueError("attn_spatial_bwd: cam must be fp32 [batch_frames, tokens, tokens]")
+            _lib.check(_lib.lib().istvt_attn_spatial_bwd_cam(_ptr(qkv), _ptr(o), _ptr(dout), _ptr(lse), _ptr(dqkv),
+                                                             _ptr(scratch), _ptr(cam), batch_frames, tokens, heads,
+                                                             scale, _stream(dev)), "istvt_attn_spatial_bwd_cam")
     return dqkv
 
 
 def attn_temporal_bwd(qk: torch.Tensor, v: torch.Tensor, dout: torch.Tensor, batch: int, frames: int, tokens: int,
-                      heads: int, scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
-    dev = _chk(qk, v, dout)
+                      heads: int, scale: float, cam: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cam (optional, fp32 [batch, tokens, frames, frames], zeroed by the caller) += relu(dA o A) / heads."""
+    dev = _chk(qk, v, dout, cam)
     if any(t.dtype != torch.bfloat16 for t in (qk, v, dout)):
         raise ValueError("attn_temporal_bwd: bf16 only")
     dqk, dv = torch.empty_like(qk), torch.empty_like(v)
     with _launch(dev, "attn_temporal_bwd", 10.0 * batch * tokens * heads * frames * frames * 64,
                  _nbytes(qk, v, dout, dqk, dv)):
-        _lib.check(_lib.lib().istvt_attn_temporal_bwd(_ptr(qk), _ptr(v), _ptr(dout), _ptr(dqk), _ptr(dv), batch, frames,
-                                                      tokens, heads, scale, _stream(dev)), "istvt_attn_temporal_bwd")
+        if cam is None:
+            _lib.check(_lib.lib().istvt_attn_temporal_bwd(_ptr(qk), _ptr(v), _ptr(dout), _ptr(dqk), _ptr(dv), batch,
+                                                          frames, tokens, heads, scale, _stream(dev)),
+                       "istvt_attn_temporal_bwd")
+        else:
+            if cam.dtype != torch.float32 or cam.numel() != batch * tokens * frames * frames:
+                raise ValueError("attn_temporal_bwd: cam must be fp32 [batch, tokens, frames, frames]")
+            _lib.check(_lib.lib().istvt_attn_temporal_bwd_cam(_ptr(qk), _ptr(v), _ptr(dout), _ptr(dqk), _ptr(dv), _ptr(cam),
+                                                              batch, frames, tokens, heads, scale, _stream(dev)),
+                       "istvt_attn_temporal_bwd_cam")
     return dqk, dv
 
 
@@ -606,3 +624,13 @@ def im2col_t_stem(x: torch.Tensor) -> torch.Tensor:
     with _launch(dev, "im2col_t", 0.0, _nbytes(x, out)):
         _lib.check(_lib.lib().istvt_im2col_t_stem(_ptr(x), _ptr(out), n, h, wd, ld, _stream(dev)), "istvt_im2col_t_stem")
     return out
+
+
+def rollout_row(v: torch.Tensor, cmat: torch.Tensor) -> None:
+    """v: fp32 [n, L] (in place) <- v (I + cmat), cmat fp32 [n, L, L]."""
+    dev = _chk(v, cmat)
+    n, ln = v.shape
+    if cmat.numel() != n * ln * ln or v.dtype != torch.float32 or cmat.dtype != torch.float32:
+        raise ValueError("rollout_row: cmat must be fp32 [n, L, L]")
+    with _launch(dev, "rollout_row", 2.0 * n * ln * ln, _nbytes(cmat)):
+        _lib.check(_lib.lib().istvt_rollout_row(_ptr(v), _ptr(cmat), n, ln, _stream(dev)), "istvt_rollout_row")

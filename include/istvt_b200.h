@@ -298,6 +298,20 @@ int istvt_block_input_grad(const void* d_main, const void* x_in, const void* d_s
 int istvt_im2col_t(const void* x, void* out, int n, int h, int w, int cin, int64_t ldo, istvt_stream_t stream);
 int istvt_im2col_t_stem(const float* x, void* out, int n, int h, int w, int64_t ldo, istvt_stream_t stream);
 
+/* ---- Relevance propagation (visualize_rel.py:206,257-262; the reference's implementation, `tfe...LRP`, is NOT in its
+ * tree — this is the published gradient-weighted attention rollout, see DESIGN.md "relevance pass") ---- */
+
+/* Attention backward kernels that also accumulate cam += relu(dA o A) / heads (A = attention probabilities,
+ * dA = gradient of the logit w.r.t. them).  cam is fp32 and zero-filled by the caller:
+ * spatial [batch_frames, tokens, tokens], temporal [batch, tokens, frames, frames]. */
+int istvt_attn_spatial_bwd_cam(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
+                               float* dq_scratch, float* cam, int batch_frames, int tokens, int heads, float scale,
+                               istvt_stream_t stream);
+int istvt_attn_temporal_bwd_cam(const void* qk, const void* v, const void* dout, void* dqk, void* dv, float* cam,
+                                int batch, int frames, int tokens, int heads, float scale, istvt_stream_t stream);
+/* One rollout step on the class-token row: v[n, :] <- v[n, :] (I + cmat[n]), cmat fp32 [n, len, len]. */
+int istvt_rollout_row(float* v, const float* cmat, int64_t n, int len, istvt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
