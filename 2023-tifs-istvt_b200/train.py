@@ -156,24 +156,47 @@ def transformer_forward_train(vit, layers: List[SimpleNamespace], tokens: torch.
     return logits, ctxs, x, head
 
 
+class _ScratchGrads(dict):
+    """Stand-in for the gradient dictionary when only activation gradients are wanted (relevance pass): the
+    LayerNorm / head kernels still need somewhere to put dgamma / dbeta."""
+
+    def __init__(self, dev):
+        super().__init__()
+        self.dev = dev
+
+    def __missing__(self, key):
+        t = torch.zeros(4096, dtype=torch.float32, device=self.dev)
+        self[key] = t
+        return t
+
+
 def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits: torch.Tensor,
-                         G: Dict[str, torch.Tensor]) -> torch.Tensor:
-    """Accumulates every vit.transformer / vit.mlp_head gradient into G and returns g = dL/d(tokens), fp32."""
+                         G: Optional[Dict[str, torch.Tensor]], relevance=None) -> torch.Tensor:
+    """Accumulates every vit.transformer / vit.mlp_head gradient into G and returns g = dL/d(tokens), fp32.
+    G = None: activation gradients only (no weight-gradient GEMMs).  `relevance` (relevance.py): per-layer hook that
+    receives the head-averaged relu(dA o A) of both attentions."""
     b, f, p, d = x_final.shape
     rows = b * f * p
     heads = vit.heads
     scale = 64 ** -0.5
+    wgrad = G is not None
+    if G is None:
+        G = _ScratchGrads(x_final.device)
     g = torch.zeros_like(x_final)
     g2 = g.view(rows, d)
     ops.head_bwd(x_final, dlogits.reshape(-1).float().contiguous(), head.norm[0], head.norm[1], head.ln[0], head.ln[1],
                  head.w, g, G["vit.transformer.norm.weight"], G["vit.transformer.norm.bias"],
-                 G["vit.mlp_head.0.weight"], G["vit.mlp_head.0.bias"], G["vit.mlp_head.1.weight"].view(-1),
+                 G["vit.mlp_head.0.weight"], G["vit.mlp_head.0.bias"], G["vit.mlp_head.1.weight"].view(-1)[:d],
                  G["vit.mlp_head.1.bias"])
     g_bf = ops.cast_bf16(g2)
     scratch = torch.empty(rows, heads * 64, dtype=torch.float32, device=g.device)
     for li in range(len(layers) - 1, -1, -1):
         L, c = layers[li], ctxs[li]
         N = {k: G[v] for k, v in _layer_grad_names(li).items()}
+        if not wgrad:
+            _transformer_layer_backward_acts(L, c, N, g2, g_bf, scratch, b, f, p, d, heads, scale, relevance, li)
+            ctxs[li] = None
+            continue
         # ---- MLP (module.py:27-34) ----
         ops.gemm_wgrad(ops.transpose(g_bf, colsum=N["b_2"]), ops.transpose(c.hid), rows, N["w_2"])
         dhid = ops.gemm(g_bf, L.wT_2)
@@ -210,6 +233,34 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
         del ddiff, dxn_v
         ctxs[li] = None     # release this layer's activations
     return g
+
+
+def _transformer_layer_backward_acts(L, c, N, g2, g_bf, scratch, b, f, p, d, heads, scale, relevance, li) -> None:
+    """One block's backward without the weight-gradient GEMMs (same data path as transformer_backward)."""
+    rows = b * f * p
+    dhpre = ops.gelu_bwd(ops.gemm(g_bf, L.wT_2), c.hpre)
+    dzn = ops.gemm(dhpre, L.wT_1)
+    del dhpre
+    ops.layernorm_bwd(dzn, c.x1.view(rows, d), L.ln3[0], N["ln3_w"], N["ln3_b"], g_accum=g2, g_bf16=g_bf)
+    del dzn
+    das = ops.gemm(g_bf, L.wT_so)
+    cam_s = relevance.spatial_buffer() if relevance is not None else None
+    dqkv = ops.attn_spatial_bwd(c.qkv, c.as_, das, c.lse, b * f, p, heads, scale, scratch, cam=cam_s)
+    del das
+    dy1 = ops.layernorm_bwd(ops.gemm(dqkv, L.wT_qkv), c.y1, L.ln2[0], N["ln2_w"], N["ln2_b"])
+    del dqkv
+    dat = ops.gemm(dy1, L.wT_to)
+    del dy1
+    cam_t = relevance.temporal_buffer() if relevance is not None else None
+    dqk, dv = ops.attn_temporal_bwd(c.qk, c.v, dat, b, f, p, heads, scale, cam=cam_t)
+    del dat
+    ddiff = ops.gemm(dqk, L.wT_qk)
+    dxn_v = ops.gemm(dv, L.wT_v)
+    del dqk, dv
+    ops.layernorm_bwd(dxn_v, c.x0.view(rows, d), L.ln1[0], N["ln1_w"], N["ln1_b"], g_accum=g2, g_bf16=g_bf,
+                      dy2=ddiff, frames=f, tokens_per_frame=p)
+    if relevance is not None:
+        relevance.layer_done(li)
 
 
 # ------------------------------------------------------------------------------------------------

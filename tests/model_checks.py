@@ -159,8 +159,9 @@ GOLDEN_TRAIN = GOLDEN.replace("istvt_golden.pt", "istvt_golden_train.pt")
 # bf16 training step vs the fp32 reference: loss / logits 2e-2 (the forward budget); per-tensor gradients norm-wise
 # (max|a-b| / max|ref| over the sampled entries); parameters after one AdamW step compare the UPDATE (|dp| ~ lr).
 # Measured (profiles/README.md r1q): loss 1.1e-3, gradient error median 6e-3, growing along the backward chain to
-# 6e-2 (bn1) / 1e-1 (conv1.weight, the last tensor of the chain) — bf16 activations and activation gradients.
-TOL_TRAIN = {"loss": 2e-2, "grad_vit": 4e-2, "grad_entry": 1.3e-1, "running": 2e-2, "update": 5e-2}
+# 6e-2 (bn1) / 1e-1 (conv1.weight, the last tensor of the chain; run-to-run 0.097-0.105 because the split-K
+# reductions use floating-point atomics) — bf16 activations and activation gradients.
+TOL_TRAIN = {"loss": 2e-2, "grad_vit": 4e-2, "grad_entry": 1.5e-1, "running": 2e-2, "update": 5e-2}
 
 
 def _fp_err(got: torch.Tensor, want: dict, count: int = 256) -> float:
@@ -218,4 +219,40 @@ def run_train_golden():
     assert errs["running_worst"] <= TOL_TRAIN["running"], profile
     assert errs["update_worst_over_lr"] <= TOL_TRAIN["update"], profile
     print("train golden profile:", profile)
+    return errs
+
+
+def run_relevance_check(batch: int = 2):
+    """Relevance pass (BASELINE config 4) on the GPU vs oracle/relevance_oracle.py — PARITY UNPINNED: the reference's
+    own implementation is absent from its tree, the oracle restates the rule the product implements."""
+    from oracle import relevance_oracle as R
+    O = oracle()
+    m = pkg()
+    model = build_model({"seed": 0, "frames": 6, "sensitised": True})
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = make_input(batch, 6, seed=77)
+    want_s, want_t, want_logits = R.relevance_maps(sd, x)
+    model = model.cuda().eval()
+    cam_s, cam_t, logits = m.relevance_maps(model, x.cuda())
+    torch.cuda.synchronize()
+    errs = {"logits": rel_err(logits, want_logits), "cam_s": rel_err(cam_s, want_s), "cam_t": rel_err(cam_t, want_t)}
+    # ranking agreement of the maps (what the heat-map overlay of visualize_rel.py:263-294 shows)
+    def corr(a, b):
+        a = a.detach().double().cpu().flatten(); b = b.detach().double().cpu().flatten()
+        a = a - a.mean(); b = b - b.mean()
+        return float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-300))
+    errs["corr_s"] = 1.0 - corr(cam_s, want_s)
+    errs["corr_t"] = 1.0 - corr(cam_t, want_t)
+    profile = ", ".join(f"{k}={v:.3e}" for k, v in errs.items())
+    assert errs["logits"] <= 2e-2, profile
+    assert errs["cam_s"] <= 1e-1 and errs["cam_t"] <= 1e-1, profile
+    assert errs["corr_s"] <= 5e-2 and errs["corr_t"] <= 5e-2, profile   # measured 2.0e-2 / 3.7e-4 (bf16)
+    # reference call-site shapes (visualize_rel.py:257-262), batch 1
+    seq_s, seq_t = m.LRP(model).generate_LRP(x[:1].cuda(), method="transformer_attribution", index=0)
+    cs = torch.cat(seq_s, 0)
+    ct = torch.cat(seq_t, 0).transpose(0, 1)
+    assert tuple(cs.shape) == (6, 361) and tuple(ct.shape) == (6, 361)
+    assert cs[0].reshape(1, 1, 19, 19).shape == (1, 1, 19, 19)
+    assert torch.allclose(cs, cam_s[0], rtol=1e-3, atol=0) and torch.allclose(ct, cam_t[0], rtol=1e-3, atol=0)
+    print("relevance profile:", profile)
     return errs

@@ -26,3 +26,8 @@ def test_api_boundary():
 @pytest.mark.gpu
 def test_training_step_against_reference_golden():
     model_checks.run_train_golden()
+
+
+@pytest.mark.gpu
+def test_relevance_pass_against_oracle():
+    model_checks.run_relevance_check()

@@ -31,6 +31,7 @@ def all_checks():
     checks["golden_t32_bf16"] = lambda: model_checks.run_golden_case("sensitised_t32_b1", "bf16")
     checks["golden_t32_fp32"] = lambda: model_checks.run_golden_case("sensitised_t32_b1", "fp32")
     checks["train_golden"] = model_checks.run_train_golden
+    checks["relevance"] = model_checks.run_relevance_check
     return checks
 
 
