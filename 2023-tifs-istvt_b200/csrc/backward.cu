@@ -403,6 +403,24 @@ rollout_row_kernel(float* __restrict__ v, const float* __restrict__ cmat, int le
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Row gather: dst[o, r, :] = src[o * outer_stride + r * row_stride + (0 .. row_bytes)], 16-byte units.
+// Used by the pruned last transformer layer (only token (0,0) of every clip reaches the head, vivit.py:144-148):
+// frame-0 rows of a clip are contiguous, clips are (T+1)*362 rows apart.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n_outer, int64_t outer_stride16,
+                   int64_t rows, int64_t row_stride16, int row16) {
+    const int64_t total = n_outer * rows * row16;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = static_cast<int>(idx % row16);
+    const int64_t t = idx / row16;
+    const int64_t r = t % rows;
+    const int64_t o = t / rows;
+    dst[idx] = src[o * outer_stride16 + r * row_stride16 + c];
+}
+
 static inline unsigned nblk(int64_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
 }  // namespace istvt
@@ -527,6 +545,20 @@ extern "C" int istvt_adamw_step(float* params, const float* grads, float* exp_av
 extern "C" int istvt_rollout_row(float* v, const float* cmat, int64_t n, int len, istvt_stream_t stream) {
     ISTVT_REQUIRE(v && cmat && n > 0 && len > 0 && len <= 1024 && n < (int64_t(1) << 31));
     rollout_row_kernel<<<static_cast<unsigned>(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(v, cmat, len);
+    count_launch();
+    return launch_status();
+}
+
+// dst [n_outer, rows, row_bytes] (contiguous) <- src; strides and row_bytes in BYTES, all multiples of 16.
+extern "C" int istvt_gather_rows(const void* src, void* dst, int64_t n_outer, int64_t outer_stride_bytes, int64_t rows,
+                                 int64_t row_stride_bytes, int64_t row_bytes, istvt_stream_t stream) {
+    ISTVT_REQUIRE(src && dst && n_outer > 0 && rows > 0 && row_bytes > 0);
+    ISTVT_REQUIRE(outer_stride_bytes % 16 == 0 && row_stride_bytes % 16 == 0 && row_bytes % 16 == 0);
+    ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
+    const int64_t total = n_outer * rows * (row_bytes / 16);
+    gather_rows_kernel<<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(src), static_cast<uint4*>(dst), n_outer, outer_stride_bytes / 16, rows,
+        row_stride_bytes / 16, static_cast<int>(row_bytes / 16));
     count_launch();
     return launch_status();
 }

@@ -273,12 +273,32 @@ class ISTVTEngine:
         rows = b * f_tok * p_tok
         xn = torch.empty(b, f_tok, p_tok, dim, dtype=dt, device=dev)
         diff = torch.empty_like(xn)
+        # After the last block only token (0, 0) of every clip is read (vivit.py:144-148).  Unless intermediates
+        # were asked for, the last block therefore runs its temporal attention in full (frame-0 queries need every
+        # frame's K / V) and everything after it on the rows that can reach that token: frame-0 rows for the
+        # spatial attention, the class-token row for its output projection and the MLP.  bench.py reports the
+        # work actually executed.
+        prune_last = not return_attention and taps is None and not ln2_input_fp32
+        cls_stream = None
         for li, lp in enumerate(pk.layers):
             # temporal self-subtract attention (module.py:190-208), no residual of its own (vivit.py:99)
             ops.layernorm_diff(tokens, lp.ln1[0], lp.ln1[1], dt, out=(xn, diff))
             qk = ops.gemm(diff.view(rows, dim), lp.w_qk)
             v = ops.gemm(xn.view(rows, dim), lp.w_v)
             at, p_t = ops.attn_temporal(qk, v, b, f_tok, p_tok, heads, scale, want_probs=return_attention)
+            if prune_last and li == len(pk.layers) - 1:
+                inner = heads * 64
+                at0 = ops.gather_rows(at, b, f_tok * p_tok * inner, p_tok, inner, inner)            # frame-0 rows
+                yn0 = ops.layernorm(ops.gemm(at0, lp.w_to, bias=lp.b_to, out_dtype=dt), lp.ln2[0], lp.ln2[1], dt)
+                as0, _ = ops.attn_spatial(ops.gemm(yn0, lp.w_qkv), b, p_tok, heads, scale)
+                as_cls = ops.gather_rows(as0, b, p_tok * inner, 1, inner, inner)                     # query (0, 0)
+                x_cls = ops.gather_rows(tokens, b, f_tok * p_tok * dim, 1, dim, dim)                 # fp32 residual rows
+                ops.gemm(as_cls, lp.w_so, bias=lp.b_so, residual=x_cls, out=x_cls)
+                zn = ops.layernorm(x_cls, lp.ln3[0], lp.ln3[1], dt)
+                hid = ops.gemm(zn, lp.w_1, bias=lp.b_1, act=ops.ACT_GELU, out_dtype=dt)
+                ops.gemm(hid, lp.w_2, bias=lp.b_2, residual=x_cls, out=x_cls)
+                cls_stream = x_cls.view(b, 1, 1, dim)
+                break
             y1 = ops.gemm(at, lp.w_to, bias=lp.b_to, out_dtype=torch.float32 if ln2_input_fp32 else dt)
             # spatial attention (module.py:81-93) + the residual spanning both attentions (vivit.py:99)
             yn = ops.layernorm(y1, lp.ln2[0], lp.ln2[1], dt, out=xn.view(rows, dim))
@@ -296,6 +316,8 @@ class ISTVTEngine:
                 taps[f"layer{li}"] = tokens.clone()
             del qk, v, at, y1, qkv, as_, hid
 
+        if cls_stream is not None:
+            tokens = cls_stream
         logits = ops.head(tokens, pk.norm[0], pk.norm[1], pk.head_ln[0], pk.head_ln[1], pk.head_w, pk.head_b)
         if return_attention:
             return logits, attn

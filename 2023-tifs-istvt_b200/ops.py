@@ -634,3 +634,15 @@ def rollout_row(v: torch.Tensor, cmat: torch.Tensor) -> None:
         raise ValueError("rollout_row: cmat must be fp32 [n, L, L]")
     with _launch(dev, "rollout_row", 2.0 * n * ln * ln, _nbytes(cmat)):
         _lib.check(_lib.lib().istvt_rollout_row(_ptr(v), _ptr(cmat), n, ln, _stream(dev)), "istvt_rollout_row")
+
+
+def gather_rows(src: torch.Tensor, n_outer: int, outer_stride: int, rows: int, row_stride: int, width: int
+                ) -> torch.Tensor:
+    """dst[o, r, :width] = src.flatten()[o*outer_stride + r*row_stride : ... + width] (element units) -> [n_outer*rows, width]."""
+    dev = _chk(src)
+    es = src.element_size()
+    dst = torch.empty(n_outer * rows, width, dtype=src.dtype, device=dev)
+    with _launch(dev, "gather_rows", 0.0, 2 * _nbytes(dst)):
+        _lib.check(_lib.lib().istvt_gather_rows(_ptr(src), _ptr(dst), n_outer, outer_stride * es, rows, row_stride * es,
+                                                width * es, _stream(dev)), "istvt_gather_rows")
+    return dst

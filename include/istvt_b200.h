@@ -312,6 +312,12 @@ int istvt_attn_temporal_bwd_cam(const void* qk, const void* v, const void* dout,
 /* One rollout step on the class-token row: v[n, :] <- v[n, :] (I + cmat[n]), cmat fp32 [n, len, len]. */
 int istvt_rollout_row(float* v, const float* cmat, int64_t n, int len, istvt_stream_t stream);
 
+/* Strided row gather (data movement only): dst [n_outer, rows, row_bytes] contiguous <- src + o*outer_stride +
+ * r*row_stride.  Used by the pruned last transformer layer: after layer 12 only token (0,0) of every clip is read
+ * (vivit.py:144-148), so its spatial attention / MLP run on the frame-0 rows / the class-token row only. */
+int istvt_gather_rows(const void* src, void* dst, int64_t n_outer, int64_t outer_stride_bytes, int64_t rows,
+                      int64_t row_stride_bytes, int64_t row_bytes, istvt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,13 @@ def run_golden_case(name: str, precision: str):
     assert not bad, (f"{name}/{precision}: over tolerance {tol:.0e}: {sorted(bad)}; logits {logits.flatten().tolist()} "
                      f"vs {want_logits.flatten().tolist()}; profile: {profile}")
     assert torch.equal(logits.cpu() > 0, want_logits > 0), "predictions (logit > 0) differ"
+    # production call (`model(x)`): no intermediates requested, so the last block is pruned to the rows that can
+    # reach token (0, 0) (engine.py) — same logits within the same tolerance
+    logits_pruned = model(x)
+    torch.cuda.synchronize()
+    errs["logits_pruned"] = rel_err(logits_pruned, want_logits)
+    assert errs["logits_pruned"] <= tol, f"{name}/{precision}: pruned-last-layer logits {logits_pruned.flatten().tolist()}"
+    assert torch.equal(logits_pruned.cpu() > 0, want_logits > 0)
     return errs
 
 
