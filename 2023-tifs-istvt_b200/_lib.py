@@ -65,6 +65,8 @@ SIGNATURES = {
     "istvt_attn_temporal_bwd_cam": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "istvt_rollout_row": [_P, _P, _L, _I, _P],
     "istvt_gather_rows": [_P, _P, _L, _L, _L, _L, _L, _P],
+    "istvt_gemm_wgrad_accum": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P],
+    "istvt_colsum": [_P, _P, _L, _I, _P],
 }
 _RESTYPES = {"istvt_error_string": c_char_p, "istvt_launch_count": c_int64}
 

@@ -404,6 +404,35 @@ rollout_row_kernel(float* __restrict__ v, const float* __restrict__ cmat, int le
 }
 
 // ------------------------------------------------------------------------------------------
+// colsum[c] += sum_m x[m, c]  (bf16 in, fp32 out): bias gradient of an nn.Linear from its output gradient.
+// thread = (row lane, 8-column group), groups fastest; per-CTA partials through shared memory.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+colsum_kernel(const bf16* __restrict__ x, float* __restrict__ colsum, int64_t m, int c) {
+    extern __shared__ float s_cs[];
+    for (int i = threadIdx.x; i < c; i += blockDim.x) s_cs[i] = 0.f;
+    __syncthreads();
+    const int c8 = c >> 3;
+    const int lanes = blockDim.x / c8 > 0 ? blockDim.x / c8 : 1;
+    const int cg = threadIdx.x % c8, rl = threadIdx.x / c8;
+    if (rl < lanes) {
+        float s[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = 0.f;
+        for (int64_t r = static_cast<int64_t>(blockIdx.x) * lanes + rl; r < m; r += static_cast<int64_t>(gridDim.x) * lanes) {
+            float v[8];
+            load8(x + r * c + cg * 8, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += v[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[cg * 8 + e], s[e]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(colsum + i, s_cs[i]);
+}
+
+// ------------------------------------------------------------------------------------------
 // Row gather: dst[o, r, :] = src[o * outer_stride + r * row_stride + (0 .. row_bytes)], 16-byte units.
 // Used by the pruned last transformer layer (only token (0,0) of every clip reaches the head, vivit.py:144-148):
 // frame-0 rows of a clip are contiguous, clips are (T+1)*362 rows apart.
@@ -559,6 +588,23 @@ extern "C" int istvt_gather_rows(const void* src, void* dst, int64_t n_outer, in
     gather_rows_kernel<<<nblk(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(src), static_cast<uint4*>(dst), n_outer, outer_stride_bytes / 16, rows,
         row_stride_bytes / 16, static_cast<int>(row_bytes / 16));
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_colsum(const void* x, float* colsum, int64_t m, int c, istvt_stream_t stream) {
+    ISTVT_REQUIRE(x && colsum && m > 0 && c > 0 && c % 8 == 0 && c <= 8192);
+    const int c8 = c / 8;
+    int lanes = 256 / c8;
+    if (lanes < 1) lanes = 1;
+    int threads = lanes * c8;
+    threads = (threads + 31) / 32 * 32;
+    ISTVT_REQUIRE(threads <= 1024);
+    int64_t blocks = (m + 63) / 64;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    colsum_kernel<<<static_cast<unsigned>(blocks), threads, c * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(x), colsum, m, c);
     count_launch();
     return launch_status();
 }

@@ -217,6 +217,11 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
     }
 }
 
+// (A warp-level tensor-core variant — mma.sync with diagonal B fragments, ldmatrix row pointers into a swizzled
+// halo tile, 6 instructions per output instead of ~20 — was built, validated and measured SLOWER: 6.0 vs 4.4 ms
+// per step.  Legacy mma.sync on sm_100a peaks near 512 FLOP/clk/SM, 1/16 of tcgen05, and the diagonal trick
+// wastes 7/8 of it.  profiles/README.md r1x.)
+
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)

@@ -7,6 +7,7 @@
 //   token-gradient gather (vivit.py:133-138 backward), im2col^T operands for the conv1 / conv2 weight gradients.
 // All are HBM-bound SIMT kernels; the GEMM-shaped gradients run on the tcgen05 GEMMs (gemm_tcgen05*.cu).
 #include "common.cuh"
+#include "ptx.cuh"
 #include "simt_util.cuh"
 
 #include <cuda_bf16.h>
@@ -289,58 +290,140 @@ token_grad_gather_kernel(const float* __restrict__ g, bf16* __restrict__ d_out, 
 
 // ------------------------------------------------------------------------------------------
 // depthwise 3x3 weight gradient: dw[ky][kx][c] += sum_{n,y,x} in[n, y+ky-1, x+kx-1, c] * dy[n, y, x, c]
-// (in = relu(x) when the forward applied the ReLU on load).  One CTA = one image x a strip of rows.
+// (in = relu(x) when the forward applied the ReLU on load).
+// Same machinery as the forward kernel (entry_flow.cu): persistent CTAs, per item ONE TMA load of the x halo tile
+// (10 x 18 x 64 channels; pad-1 border = TMA zero fill) and one of the dy tile (8 x 16 x 64) into a double-buffered
+// slot; thread = (4 channels, one tile column) walks down the rows with the last three dy rows in registers and
+// 9 x 4 accumulators.  Items are ordered channel-group-major and every CTA takes a contiguous range, so the
+// accumulators live in registers across tiles and are flushed (shared atomics -> global atomics) only when the
+// channel group changes: the first version (one CTA per strip, 9 uncached neighbour loads per pixel) ran at 0.8 TB/s.
 // ------------------------------------------------------------------------------------------
-constexpr int DWG_ROWS = 8;
-__global__ void __launch_bounds__(256)
-dwconv_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw, int h, int w, int c,
-                    int relu_in) {
-    extern __shared__ float s_acc[];   // [9][c]
-    for (int i = threadIdx.x; i < 9 * c; i += blockDim.x) s_acc[i] = 0.f;
+constexpr int DWG_TW = 16, DWG_TH = 8, DWG_CG = 64, DWG_THREADS = 256;
+constexpr int DWG_X_BYTES = (DWG_TH + 2) * (DWG_TW + 2) * DWG_CG * 2;     // 23040
+constexpr int DWG_DY_BYTES = DWG_TH * DWG_TW * DWG_CG * 2;                // 16384
+constexpr int DWG_STAGE = DWG_X_BYTES + DWG_DY_BYTES;                     // 39424 (multiple of 128)
+constexpr int DWG_SMEM = 2 * DWG_STAGE + 9 * DWG_CG * 4 + 128 + 64;
+
+__device__ __forceinline__ void dwg_lds4(const bf16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+
+__global__ void __launch_bounds__(DWG_THREADS, 2)
+dwconv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
+                        float* __restrict__ dw, int n, int h, int w, int c, int relu_in) {
+    extern __shared__ __align__(128) uint8_t dwg_smem[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dwg_smem) + 127) & ~uintptr_t(127));
+    float* s_acc = reinterpret_cast<float*>(base + 2 * DWG_STAGE);              // [9][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 2 * DWG_STAGE + 9 * DWG_CG * 4);
+
+    const int tiles_x = (w + DWG_TW - 1) / DWG_TW;
+    const int tiles_y = (h + DWG_TH - 1) / DWG_TH;
+    const int cgroups = (c + DWG_CG - 1) / DWG_CG;
+    const int64_t per_cg = static_cast<int64_t>(n) * tiles_y * tiles_x;
+    const int64_t total = per_cg * cgroups;
+    const int64_t per_cta = (total + gridDim.x - 1) / gridDim.x;
+    const int64_t it0 = per_cta * blockIdx.x;
+    const int64_t it1 = (it0 + per_cta < total) ? it0 + per_cta : total;
+
+    const int tid = threadIdx.x;
+    const int cq = tid & 15;          // channel quad inside the 64-channel group
+    const int col = tid >> 4;         // tile column
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_dy);
+    }
+    for (int i = tid; i < 9 * DWG_CG; i += DWG_THREADS) s_acc[i] = 0.f;
     __syncthreads();
-    const ChanLayout L(c);
-    const int strips = (h + DWG_ROWS - 1) / DWG_ROWS;
-    const int img = blockIdx.x / strips;
-    const int y0 = (blockIdx.x - img * strips) * DWG_ROWS;
-    const int y1 = min(h, y0 + DWG_ROWS);
-    if (L.active) {
-        float acc[9][8];
+
+    auto decode = [&](int64_t item, int& tx, int& ty, int& img, int& cg) {
+        cg = static_cast<int>(item / per_cg);
+        int64_t r = item - cg * per_cg;
+        tx = static_cast<int>(r % tiles_x);
+        r /= tiles_x;
+        ty = static_cast<int>(r % tiles_y);
+        img = static_cast<int>(r / tiles_y);
+    };
+    auto issue = [&](int64_t item, int buf) {
+        int tx, ty, img, cg;
+        decode(item, tx, ty, img, cg);
+        mbar_arrive_expect_tx(&bars[buf], DWG_STAGE);
+        tma_load_4d(base + buf * DWG_STAGE, &tm_x, &bars[buf], cg * DWG_CG, tx * DWG_TW - 1, ty * DWG_TH - 1, img);
+        tma_load_4d(base + buf * DWG_STAGE + DWG_X_BYTES, &tm_dy, &bars[buf], cg * DWG_CG, tx * DWG_TW, ty * DWG_TH, img);
+    };
+
+    float acc[9][4];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[k][e] = 0.f;
+    int cg_cur = -1;
+
+    auto flush = [&](int cg) {   // all threads: fold the register partials of channel group cg into dw
 #pragma unroll
         for (int k = 0; k < 9; ++k)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
-        const bf16* xi = x + static_cast<int64_t>(img) * h * w * c + L.cg * 8;
-        const bf16* di = dy + static_cast<int64_t>(img) * h * w * c + L.cg * 8;
-        const int npix = (y1 - y0) * w;
-        for (int pix = L.rl; pix < npix; pix += L.lanes) {
-            const int yy = y0 + pix / w, xx = pix % w;
-            float d[8];
-            load8(di + (static_cast<int64_t>(yy) * w + xx) * c, d);
+            for (int e = 0; e < 4; ++e) {
+                atomicAdd(&s_acc[k * DWG_CG + cq * 4 + e], acc[k][e]);
+                acc[k][e] = 0.f;
+            }
+        __syncthreads();
+        for (int i = tid; i < 9 * DWG_CG; i += DWG_THREADS) {
+            const int k = i / DWG_CG, ch = cg * DWG_CG + (i - k * DWG_CG);
+            if (ch < c) atomicAdd(dw + k * c + ch, s_acc[i]);
+            s_acc[i] = 0.f;
+        }
+        __syncthreads();
+    };
+
+    if (tid == 0 && it0 < it1) issue(it0, 0);
+    int buf = 0;
+    uint32_t phase[2] = {0, 0};
+    for (int64_t item = it0; item < it1; ++item) {
+        if (tid == 0 && item + 1 < it1) issue(item + 1, buf ^ 1);   // slot buf^1 was released by the barrier below
+        int tx, ty, img, cg;
+        decode(item, tx, ty, img, cg);
+        if (cg != cg_cur) {
+            if (cg_cur >= 0) flush(cg_cur);
+            cg_cur = cg;
+        }
+        mbar_wait(&bars[buf], phase[buf]);
+        phase[buf] ^= 1;
+        const bf16* xt = reinterpret_cast<const bf16*>(base + buf * DWG_STAGE) + col * DWG_CG + cq * 4;
+        const bf16* dt = reinterpret_cast<const bf16*>(base + buf * DWG_STAGE + DWG_X_BYTES) + col * DWG_CG + cq * 4;
+        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4];   // dy rows i-2, i-1, i
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int iy = yy + ky - 1;
-                if (iy < 0 || iy >= h) continue;
+        for (int i = 0; i < DWG_TH + 2; ++i) {     // input (halo) row i pairs with dy rows i, i-1, i-2 under ky = 0, 1, 2
+            if (i < DWG_TH) dwg_lds4(dt + i * DWG_TW * DWG_CG, d2);
+            else d2[0] = d2[1] = d2[2] = d2[3] = 0.f;
+            float v[3][4];
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = xx + kx - 1;
-                    if (ix < 0 || ix >= w) continue;
-                    float v[8];
-                    load8(xi + (static_cast<int64_t>(iy) * w + ix) * c, v);
+            for (int kx = 0; kx < 3; ++kx) {
+                dwg_lds4(xt + (i * (DWG_TW + 2) + kx) * DWG_CG, v[kx]);
+                if (relu_in) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float a = relu_in ? fmaxf(v[e], 0.f) : v[e];
-                        acc[ky * 3 + kx][e] = fmaf(a, d[e], acc[ky * 3 + kx][e]);
-                    }
+                    for (int e = 0; e < 4; ++e) v[kx][e] = fmaxf(v[kx][e], 0.f);
                 }
             }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc[0 * 3 + kx][e] = fmaf(v[kx][e], d2[e], acc[0 * 3 + kx][e]);
+                    acc[1 * 3 + kx][e] = fmaf(v[kx][e], d1[e], acc[1 * 3 + kx][e]);
+                    acc[2 * 3 + kx][e] = fmaf(v[kx][e], d0[e], acc[2 * 3 + kx][e]);
+                }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { d0[e] = d1[e]; d1[e] = d2[e]; }
         }
-#pragma unroll
-        for (int k = 0; k < 9; ++k)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(&s_acc[k * c + L.cg * 8 + e], acc[k][e]);
+        __syncthreads();   // everyone is done reading slot `buf`
+        buf ^= 1;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 9 * c; i += blockDim.x) atomicAdd(dw + i, s_acc[i]);
+    if (cg_cur >= 0) flush(cg_cur);
 }
 
 // dx_in = d_main * (relu_in ? x_in > 0 : 1) + (even pixel ? d_skip[n, y/2, x/2, :] : 0)
@@ -551,11 +634,26 @@ extern "C" int istvt_token_grad_gather(const float* g, void* d_out, int batch, i
 
 extern "C" int istvt_dwconv3x3_wgrad(const void* x, const void* dy, float* dw, int n, int h, int w, int c, int relu_in,
                                      istvt_stream_t stream) {
-    ISTVT_REQUIRE(x && dy && dw && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && c <= 1024);
-    const int strips = (h + DWG_ROWS - 1) / DWG_ROWS;
-    const size_t smem = 9 * static_cast<size_t>(c) * sizeof(float);
-    dwconv_wgrad_kernel<<<static_cast<unsigned>(n * strips), chan_threads(c), smem, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(x), static_cast<const bf16*>(dy), dw, h, w, c, relu_in);
+    ISTVT_REQUIRE(x && dy && dw && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0);
+    ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0);
+    CUtensorMap tm_x, tm_dy;
+    const uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(w), static_cast<uint64_t>(h),
+                              static_cast<uint64_t>(n)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(w) * c * 2,
+                                 static_cast<uint64_t>(h) * w * c * 2};
+    const uint32_t box_x[4] = {DWG_CG, DWG_TW + 2, DWG_TH + 2, 1};
+    const uint32_t box_d[4] = {DWG_CG, DWG_TW, DWG_TH, 1};
+    int rc = encode_tmap(&tm_x, x, ISTVT_BF16, 4, dims, strides, box_x, 0);
+    if (rc != ISTVT_OK) return rc;
+    rc = encode_tmap(&tm_dy, dy, ISTVT_BF16, 4, dims, strides, box_d, 0);
+    if (rc != ISTVT_OK) return rc;
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(dwconv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWG_SMEM));
+    const int64_t total = static_cast<int64_t>(n) * ((c + DWG_CG - 1) / DWG_CG) * ((h + DWG_TH - 1) / DWG_TH) *
+                          ((w + DWG_TW - 1) / DWG_TW);
+    int64_t grid = static_cast<int64_t>(sm_count()) * 2;
+    if (grid > total) grid = total;
+    dwconv_wgrad_tma_kernel<<<static_cast<unsigned>(grid), DWG_THREADS, DWG_SMEM, static_cast<cudaStream_t>(stream)>>>(
+        tm_x, tm_dy, dw, n, h, w, c, relu_in);
     count_launch();
     return launch_status();
 }

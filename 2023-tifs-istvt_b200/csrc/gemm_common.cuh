@@ -25,6 +25,8 @@ struct GemmParams {
     int c_f32;
     int split_k;      // > 1 (CTA-pair kernel only): K is cut into split_k ranges of kb_per_split 64-wide k-blocks,
     int kb_per_split; // every (tile, range) adds its partial product to the fp32 C with red.global (C pre-initialised)
+    int mn_major;     // CTA-pair kernel: both operands are stored K-rows x MN-contiguous (A = dY [k, m], B = X [k, n]):
+                      // the weight-gradient GEMM dW = dY^T X reads dY and X as they sit in HBM, no transposed copies
 };
 
 // ------------------------------------------------------------------------------------------
@@ -186,5 +188,7 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
 
 // host: launch the CTA-pair kernel (gemm_tcgen05_2cta.cu) for a plain GEMM with N >= 256
 int launch_gemm_2cta(const void* a, int64_t lda, const void* w, int64_t ldw, const GemmParams& p, cudaStream_t stream);
+// MN-major operands (p.mn_major = 1): a = [K rows, M] pitch lda, w = [K rows, N] pitch ldw
+int launch_gemm_2cta_mn(const void* a, int64_t lda, const void* w, int64_t ldw, const GemmParams& p, cudaStream_t stream);
 
 }  // namespace istvt

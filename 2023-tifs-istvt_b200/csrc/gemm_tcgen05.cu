@@ -302,6 +302,44 @@ extern "C" int istvt_gemm_fwd(const void* a, int64_t lda, const void* w, int64_t
     return gemm_bf16_dispatch(a, m, lda, w, ldw, k, p, static_cast<cudaStream_t>(stream));
 }
 
+// split-K plan shared by the two weight-gradient entry points
+static void plan_splitk(GemmParams& p, int64_t m, int n) {
+    const int num_kb = (p.K + 63) / 64;
+    const int64_t mn_tiles = ((m + 255) / 256) * ((n + 255) / 256);
+    int64_t want = (4 * (sm_count() / 2) + mn_tiles - 1) / mn_tiles;   // ~4 waves of (tile, range) items
+    if (want < 2) want = 2;
+    int kb_per = static_cast<int>((num_kb + want - 1) / want);
+    if (kb_per < 8) kb_per = 8;
+    if (kb_per > num_kb) kb_per = num_kb;
+    p.kb_per_split = kb_per;
+    p.split_k = (num_kb + kb_per - 1) / kb_per;
+}
+
+// Weight gradient without transposed copies: dW[n_out, k_in] += dY[rows, n_out]^T X[rows, k_in], both operands read
+// in place as MN-major tiles (the token rows are the contraction dimension).  Always split-K + red.global.add.
+extern "C" int istvt_gemm_wgrad_accum(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, float* dw,
+                                      int64_t ld_dw, int64_t rows, int n_out, int k_in, istvt_stream_t stream) {
+    ISTVT_REQUIRE(dy && x && dw);
+    ISTVT_REQUIRE(rows > 0 && rows < (int64_t(1) << 31) && n_out > 0 && k_in > 0);
+    ISTVT_REQUIRE(n_out % 8 == 0 && k_in % 8 == 0 && ld_dy % 8 == 0 && ld_x % 8 == 0 && ld_dw % 4 == 0);
+    ISTVT_REQUIRE((reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(dw) & 15) == 0);
+    GemmParams p{};
+    p.M = n_out; p.N = k_in; p.K = static_cast<int>(rows);
+    p.taps = 1;
+    p.C = dw; p.ldc = ld_dw;
+    p.act = ISTVT_ACT_NONE; p.c_f32 = 1;
+    p.mn_major = 1;
+    const int num_kb = (p.K + 63) / 64;
+    if (num_kb < 2) return ISTVT_ERR_UNSUPPORTED;      // the accumulate epilogue needs >= 2 non-empty K ranges
+    plan_splitk(p, n_out, k_in);
+    if (p.split_k < 2) {
+        p.kb_per_split = (num_kb + 1) / 2;
+        p.split_k = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // == 2
+    }
+    return launch_gemm_2cta_mn(dy, ld_dy, x, ld_x, p, static_cast<cudaStream_t>(stream));
+}
+
 // Weight-gradient GEMM: C[m, n] += sum_k A[m, k] * W[n, k] with a very long K (the token rows) and a small
 // output: split-K over CTA pairs, partial products accumulated with red.global.add into the fp32 C.
 extern "C" int istvt_gemm_splitk_accum(const void* a, int64_t lda, const void* w, int64_t ldw, float* c, int64_t ldc,

@@ -108,8 +108,17 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                 for (int kb = ks * kb_per; kb < kb_end; ++kb) {
                     mbar_wait_hot(&empty_bar[stage], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
-                    tma_load_2d_2cta(smem_a + stage * G2_A_BYTES, &tm_a, &full_bar[stage], kb * G2_BK, m0);
-                    tma_load_2d_2cta(smem_b + stage * G2_B_BYTES, &tm_b, &full_bar[stage], kb * G2_BK, n0);
+                    if (!p.mn_major) {
+                        tma_load_2d_2cta(smem_a + stage * G2_A_BYTES, &tm_a, &full_bar[stage], kb * G2_BK, m0);
+                        tma_load_2d_2cta(smem_b + stage * G2_B_BYTES, &tm_b, &full_bar[stage], kb * G2_BK, n0);
+                    } else {
+                        // MN-major: a 128 (mn) x 64 (k) operand tile = two boxes of 64 k-rows x 64 contiguous mn
+                        // elements (128 B, SW128), 8 KB each, placed back to back (LBO = 8192)
+                        tma_load_2d_2cta(smem_a + stage * G2_A_BYTES, &tm_a, &full_bar[stage], m0, kb * G2_BK);
+                        tma_load_2d_2cta(smem_a + stage * G2_A_BYTES + 8192, &tm_a, &full_bar[stage], m0 + 64, kb * G2_BK);
+                        tma_load_2d_2cta(smem_b + stage * G2_B_BYTES, &tm_b, &full_bar[stage], n0, kb * G2_BK);
+                        tma_load_2d_2cta(smem_b + stage * G2_B_BYTES + 8192, &tm_b, &full_bar[stage], n0 + 64, kb * G2_BK);
+                    }
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -122,7 +131,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         // descriptors are a precomputed constant plus the stage's address field, the ragged last k-block is
         // peeled, and the only per-k-block extras are one barrier wait and one commit.
         if (elect_one()) {
-            const uint64_t desc_hi = make_smem_desc(0, 0, 1024, SWZ_128B);
+            // K-major: SBO = 1024 (8 rows x 128 B), k-step = +32 B.  MN-major: LBO = 8192 (next 64-wide mn atom),
+            // SBO = 1024 (next 8 k-rows), k-step = 16 k-rows = +2048 B.
+            const uint64_t desc_hi = p.mn_major ? make_smem_desc(0, 8192, 1024, SWZ_128B) : make_smem_desc(0, 0, 1024, SWZ_128B);
+            const uint64_t kadv = p.mn_major ? (2048u >> 4) : (32u >> 4);
             const uint32_t a_field0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4;
             const uint32_t b_field0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
             int last_steps = (p.K - (num_kb - 1) * G2_BK + UMMA_K - 1) / UMMA_K;   // 1..4 MMAs in the last k-block
@@ -133,7 +145,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
                 const int ks = static_cast<int>(tile / mn_tiles);
                 const int n_blk = static_cast<int>((tile - ks * mn_tiles) % n_tiles);
-                const uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, static_cast<uint32_t>(tile_n_eff(n_blk)), 0, 0);
+                const uint32_t mnm = p.mn_major ? 1u : 0u;
+                const uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, static_cast<uint32_t>(tile_n_eff(n_blk)), mnm, mnm);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * G2_BN;
@@ -147,13 +160,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                     const uint64_t b_desc = desc_hi | (b_field0 + stage * (G2_B_BYTES >> 4));
                     if (kb != kb_end - 1) {
                         umma_f16_ss_2cta(d_tmem, a_desc, b_desc, idesc, kb != kb_begin ? 1u : 0u);
-                        umma_f16_ss_2cta(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
-                        umma_f16_ss_2cta(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-                        umma_f16_ss_2cta(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                        umma_f16_ss_2cta(d_tmem, a_desc + kadv, b_desc + kadv, idesc, 1u);
+                        umma_f16_ss_2cta(d_tmem, a_desc + 2 * kadv, b_desc + 2 * kadv, idesc, 1u);
+                        umma_f16_ss_2cta(d_tmem, a_desc + 3 * kadv, b_desc + 3 * kadv, idesc, 1u);
                         umma_commit_2cta(&empty_bar[stage], 3);                  // free the slot in both CTAs
                     } else {
                         for (int k = 0; k < tail_steps; ++k)
-                            umma_f16_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                            umma_f16_ss_2cta(d_tmem, a_desc + k * kadv, b_desc + k * kadv, idesc,
                                              (kb != kb_begin || k != 0) ? 1u : 0u);
                         umma_commit_2cta(&empty_bar[stage], 3);
                         umma_commit_2cta(&tmem_full[acc], 3);                    // accumulator ready in both CTAs
@@ -210,6 +223,27 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
 }
 
+static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmParams& p, cudaStream_t stream);
+
+int launch_gemm_2cta_mn(const void* a, int64_t lda, const void* w, int64_t ldw, const GemmParams& p, cudaStream_t stream) {
+    CUtensorMap tm_a, tm_b;
+    {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.K)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+        const uint32_t box[2] = {64, G2_BK};
+        int rc = encode_tmap(&tm_a, a, ISTVT_BF16, 2, dims, strides, box, 3);
+        if (rc != ISTVT_OK) return rc;
+    }
+    {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.K)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+        const uint32_t box[2] = {64, G2_BK};
+        int rc = encode_tmap(&tm_b, w, ISTVT_BF16, 2, dims, strides, box, 3);
+        if (rc != ISTVT_OK) return rc;
+    }
+    return launch_gemm_2cta_maps(tm_a, tm_b, p, stream);
+}
+
 int launch_gemm_2cta(const void* a, int64_t lda, const void* w, int64_t ldw, const GemmParams& p, cudaStream_t stream) {
     CUtensorMap tm_a, tm_b;
     {
@@ -226,6 +260,10 @@ int launch_gemm_2cta(const void* a, int64_t lda, const void* w, int64_t ldw, con
         int rc = encode_tmap(&tm_b, w, ISTVT_BF16, 2, dims, strides, box, 3);
         if (rc != ISTVT_OK) return rc;
     }
+    return launch_gemm_2cta_maps(tm_a, tm_b, p, stream);
+}
+
+static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmParams& p, cudaStream_t stream) {
     const int n_tiles = (p.N + G2_BN - 1) / G2_BN;
     const int64_t m_tiles = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
     const int64_t total = m_tiles * n_tiles * (p.split_k > 1 ? p.split_k : 1);

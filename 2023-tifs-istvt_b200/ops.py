@@ -646,3 +646,29 @@ def gather_rows(src: torch.Tensor, n_outer: int, outer_stride: int, rows: int, r
         _lib.check(_lib.lib().istvt_gather_rows(_ptr(src), _ptr(dst), n_outer, outer_stride * es, rows, row_stride * es,
                                                 width * es, _stream(dev)), "istvt_gather_rows")
     return dst
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out (fp32 [C]) += column sums of x (bf16 [M, C])."""
+    dev = _chk(x, out)
+    m, c = x.shape
+    with _launch(dev, "colsum", 0.0, _nbytes(x)):
+        _lib.check(_lib.lib().istvt_colsum(_ptr(x), _ptr(out), m, c, _stream(dev)), "istvt_colsum")
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, bias_grad: Optional[torch.Tensor] = None) -> None:
+    """dw[N, K] (fp32) += dy[rows, N]^T x[rows, K]; bias_grad (fp32 [N]) += column sums of dy.
+    Operands are read in place (MN-major tcgen05 tiles); tiny problems (rows <= 64) take the transposed-copy path."""
+    dev = _chk(dy, x, dw, bias_grad)
+    rows, n = dy.shape
+    k = x.shape[1]
+    if x.shape[0] != rows or dw.numel() != n * k or dw.dtype != torch.float32:
+        raise ValueError("wgrad: operand shapes do not match")
+    if rows <= 64:
+        gemm_wgrad(transpose(dy, colsum=bias_grad), transpose(x), rows, dw)
+        return
+    if bias_grad is not None:
+        colsum(dy, bias_grad)
+    with _launch(dev, "gemm_wgrad", 2.0 * n * k * rows, _nbytes(dy, x) + 2 * _nbytes(dw)):
+        _lib.check(_lib.lib().istvt_gemm_wgrad_accum(_ptr(dy), n, _ptr(x), k, _ptr(dw), k, rows, n, k, _stream(dev)),
+                   "istvt_gemm_wgrad_accum")

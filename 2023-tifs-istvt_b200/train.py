@@ -17,7 +17,7 @@ Gradient flow per spatial-temporal block (forward: engine.py / vivit.py:97-100),
     spatial  : dWso,dbso ; das = g Wso ; dqkv = attn_s'(das) ; dWqkv ; dyn = dqkv Wqkv ; dy1 = LN2'(dyn)
     temporal : dWto,dbto ; dat = dy1 Wto ; (dqk, dv) = attn_t'(dat) ; dWqk, dWv ;
                g += LN1'( dv Wv  +  self-subtract'(dqk Wqk) )
-Weight gradients are split-K tcgen05 GEMMs over transposed (K-major) copies of dY and X.
+Weight gradients are split-K tcgen05 GEMMs that read dY and X in place as MN-major operand tiles.
 """
 from __future__ import annotations
 
@@ -198,33 +198,33 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
             ctxs[li] = None
             continue
         # ---- MLP (module.py:27-34) ----
-        ops.gemm_wgrad(ops.transpose(g_bf, colsum=N["b_2"]), ops.transpose(c.hid), rows, N["w_2"])
+        ops.wgrad(g_bf, c.hid, N["w_2"], bias_grad=N["b_2"])
         dhid = ops.gemm(g_bf, L.wT_2)
         dhpre = ops.gelu_bwd(dhid, c.hpre)
         del dhid
-        ops.gemm_wgrad(ops.transpose(dhpre, colsum=N["b_1"]), ops.transpose(c.zn), rows, N["w_1"])
+        ops.wgrad(dhpre, c.zn, N["w_1"], bias_grad=N["b_1"])
         dzn = ops.gemm(dhpre, L.wT_1)
         del dhpre
         ops.layernorm_bwd(dzn, c.x1.view(rows, d), L.ln3[0], N["ln3_w"], N["ln3_b"], g_accum=g2, g_bf16=g_bf)
         del dzn
         # ---- spatial attention (module.py:81-93) ----
-        ops.gemm_wgrad(ops.transpose(g_bf, colsum=N["b_so"]), ops.transpose(c.as_), rows, N["w_so"])
+        ops.wgrad(g_bf, c.as_, N["w_so"], bias_grad=N["b_so"])
         das = ops.gemm(g_bf, L.wT_so)
         dqkv = ops.attn_spatial_bwd(c.qkv, c.as_, das, c.lse, b * f, p, heads, scale, scratch)
         del das
-        ops.gemm_wgrad(ops.transpose(dqkv), ops.transpose(c.yn), rows, N["w_qkv"])
+        ops.wgrad(dqkv, c.yn, N["w_qkv"])
         dyn = ops.gemm(dqkv, L.wT_qkv)
         del dqkv
         dy1 = ops.layernorm_bwd(dyn, c.y1, L.ln2[0], N["ln2_w"], N["ln2_b"])
         del dyn
         # ---- temporal self-subtract attention (module.py:190-208) ----
-        ops.gemm_wgrad(ops.transpose(dy1, colsum=N["b_to"]), ops.transpose(c.at), rows, N["w_to"])
+        ops.wgrad(dy1, c.at, N["w_to"], bias_grad=N["b_to"])
         dat = ops.gemm(dy1, L.wT_to)
         del dy1
         dqk, dv = ops.attn_temporal_bwd(c.qk, c.v, dat, b, f, p, heads, scale)
         del dat
-        ops.gemm_wgrad(ops.transpose(dqk), ops.transpose(c.diff.view(rows, d)), rows, N["w_qk"])
-        ops.gemm_wgrad(ops.transpose(dv), ops.transpose(c.xn.view(rows, d)), rows, N["w_v"])
+        ops.wgrad(dqk, c.diff.view(rows, d), N["w_qk"])
+        ops.wgrad(dv, c.xn.view(rows, d), N["w_v"])
         ddiff = ops.gemm(dqk, L.wT_qk)
         dxn_v = ops.gemm(dv, L.wT_v)
         del dqk, dv

@@ -99,8 +99,7 @@ class EntryFlowTrainer:
         dp2 = ops.batchnorm_bwd(dy2, bc.p2_raw, bc.bn_b, G[f"{prefix}.rep.{i2 + 1}.weight"],
                                 G[f"{prefix}.rep.{i2 + 1}.bias"], relu=False)
         del dy2
-        ops.gemm_wgrad(ops.transpose(dp2.view(m, c2)), ops.transpose(bc.d2.view(m, c1)), m,
-                       G[f"{prefix}.rep.{i2}.pointwise.weight"].view(c2, c1))
+        ops.wgrad(dp2.view(m, c2), bc.d2.view(m, c1), G[f"{prefix}.rep.{i2}.pointwise.weight"].view(c2, c1))
         dd2 = ops.gemm(dp2.view(m, c2), bc.pw2T).view(n, h, w, c1)
         del dp2
         dw_grad(bc.y1, dd2, f"{prefix}.rep.{i2}.conv1.weight", False)
@@ -109,8 +108,7 @@ class EntryFlowTrainer:
         dp1 = ops.batchnorm_bwd(dy1, bc.p1_raw, bc.bn_a, G[f"{prefix}.rep.{i1 + 1}.weight"],
                                 G[f"{prefix}.rep.{i1 + 1}.bias"], relu=True)
         del dy1
-        ops.gemm_wgrad(ops.transpose(dp1.view(m, c1)), ops.transpose(bc.d1.view(m, cin)), m,
-                       G[f"{prefix}.rep.{i1}.pointwise.weight"].view(c1, cin))
+        ops.wgrad(dp1.view(m, c1), bc.d1.view(m, cin), G[f"{prefix}.rep.{i1}.pointwise.weight"].view(c1, cin))
         dd1 = ops.gemm(dp1.view(m, c1), bc.pw1T).view(n, h, w, cin)
         del dp1
         dw_grad(bc.xin, dd1, f"{prefix}.rep.{i1}.conv1.weight", blk.start_with_relu)
@@ -121,8 +119,7 @@ class EntryFlowTrainer:
         ms = n * ho * wo
         ds_raw = ops.batchnorm_bwd(d_out, bc.s_raw, bc.bn_s, G[f"{prefix}.skipbn.weight"], G[f"{prefix}.skipbn.bias"],
                                    relu=False)
-        ops.gemm_wgrad(ops.transpose(ds_raw.view(ms, c2)), ops.transpose(bc.skip_in.view(ms, cin)), ms,
-                       G[f"{prefix}.skip.weight"].view(c2, cin))
+        ops.wgrad(ds_raw.view(ms, c2), bc.skip_in.view(ms, cin), G[f"{prefix}.skip.weight"].view(c2, cin))
         d_skip_in = ops.gemm(ds_raw.view(ms, c2), bc.wskT).view(n, ho, wo, cin)
         return ops.block_input_grad(d_main, bc.xin, d_skip_in, relu_in=blk.start_with_relu)
 

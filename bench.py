@@ -295,11 +295,20 @@ def run_ours(args) -> int:
             kernels[name] = k
         g = fam.get("gemm_bf16")
         roofline = None
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per GEMM launch from the committed ncu capture of this same command
+            with open(os.path.join(ROOT, "profiles", "r1v_gemm_traffic.json")) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["gemm_dram_bytes_per_launch"], tj["source"]
+        except Exception:  # noqa: BLE001
+            pass
         if g is not None and g["ms"] > 0:
             achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
             roofline = {"kernel": "gemm_tcgen05_kernel (istvt_gemm_fwd)", "bound": "tensor", "achieved": achieved,
-                        "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                        "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                        "traffic_source": traffic_src,
+                        "algorithmic_bytes_per_launch": g["bytes"] / g["launches"],
                         "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                         "launches_per_step": g["launches"] / args.steps,
                         "flops_per_step": g["flops"] / args.steps,

@@ -318,6 +318,14 @@ int istvt_rollout_row(float* v, const float* cmat, int64_t n, int len, istvt_str
 int istvt_gather_rows(const void* src, void* dst, int64_t n_outer, int64_t outer_stride_bytes, int64_t rows,
                       int64_t row_stride_bytes, int64_t row_bytes, istvt_stream_t stream);
 
+/* Weight gradient WITHOUT transposed operand copies: dW[n_out, k_in] (fp32, +=) = dY[rows, n_out]^T X[rows, k_in].
+ * Both bf16 operands are read in place as MN-major tcgen05 operand tiles (the token rows are the contraction
+ * dimension); split-K over CTA pairs with red.global accumulation.  rows > 64.  n_out, k_in, pitches % 8 == 0. */
+int istvt_gemm_wgrad_accum(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, float* dw, int64_t ld_dw,
+                           int64_t rows, int n_out, int k_in, istvt_stream_t stream);
+/* colsum[c] (fp32, +=) = sum_m x[m, c] (bf16): the bias gradient from an output gradient. */
+int istvt_colsum(const void* x, float* colsum, int64_t m, int c, istvt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

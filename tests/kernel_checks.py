@@ -423,6 +423,12 @@ def check_gemm_wgrad():
         want = dw.double() + dy.double().t() @ x.double()
         ops.gemm_wgrad(ops.transpose(dy), ops.transpose(x), rows, dw)
         out[f"{rows}x{n}x{k}"] = _assert_close(f"wgrad {rows}x{n}x{k}", dw, want.float(), 2e-4)
+        # in-place (MN-major operand) weight gradient + bias gradient
+        dw2 = _rand(n, k, seed=3)
+        db = torch.ones(n, device=DEV)
+        ops.wgrad(dy, x, dw2, bias_grad=db)
+        out[f"mn_{rows}x{n}x{k}"] = _assert_close(f"wgrad MN-major {rows}x{n}x{k}", dw2, want.float(), 2e-4)
+        out[f"db_{rows}x{n}"] = _assert_close(f"bias grad {rows}x{n}", db, 1 + dy.float().sum(0), 2e-4)
     return out
 
 
