@@ -5,6 +5,7 @@
 // They back `loss.backward()` / `optimizer.step()` of the reference's training loop (train_CNN.py:513-533) for the
 // modules of network/vivit/module.py and network/vivit/vivit.py; each entry point cites the forward lines.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "simt_util.cuh"
 
 #include <cuda_bf16.h>
@@ -63,17 +64,44 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
     const int64_t wstride = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
     for (int64_t row = wid; row < rows; row += wstride) {
         float xv[LNB_MAXC][4], dv[LNB_MAXC][4];
+        bool sub_next = false;
+        if (dy2 != nullptr) {
+            const int f = static_cast<int>((row / tokens_pf) % frames);
+            sub_next = f >= 1 && f <= frames - 2;
+        }
+        // issue every global load of the row up front (x, dy, dy2): the statistics below do not depend on dy, and
+        // with one row per warp in flight the kernel is latency-bound otherwise
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < LNB_MAXC; ++i) {
             const int c = lane + 32 * i;
             if (c < nch) {
                 ld4(x + row * dim + 4 * c, xv[i]);
-                s += xv[i][0] + xv[i][1] + xv[i][2] + xv[i][3];
+                ld4(dy + row * dim + 4 * c, dv[i]);
             } else {
                 xv[i][0] = xv[i][1] = xv[i][2] = xv[i][3] = 0.f;
+                dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
             }
         }
+        if (dy2 != nullptr) {
+#pragma unroll
+            for (int i = 0; i < LNB_MAXC; ++i) {
+                const int c = lane + 32 * i;
+                if (c < nch) {
+                    float t[4];
+                    ld4(dy2 + row * dim + 4 * c, t);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dv[i][e] += t[e];
+                    if (sub_next) {
+                        ld4(dy2 + (row + tokens_pf) * dim + 4 * c, t);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) dv[i][e] -= t[e];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < LNB_MAXC; ++i) s += xv[i][0] + xv[i][1] + xv[i][2] + xv[i][3];
         const float mean = warp_sum(s) * inv_dim;
         float sq = 0.f;
 #pragma unroll
@@ -85,28 +113,11 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
             }
         }
         const float rstd = rsqrtf(warp_sum(sq) * inv_dim + eps);
-        bool sub_next = false;
-        if (dy2 != nullptr) {
-            const int f = static_cast<int>((row / tokens_pf) % frames);
-            sub_next = f >= 1 && f <= frames - 2;
-        }
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < LNB_MAXC; ++i) {
             const int c = lane + 32 * i;
             if (c < nch) {
-                ld4(dy + row * dim + 4 * c, dv[i]);
-                if (dy2 != nullptr) {
-                    float t[4];
-                    ld4(dy2 + row * dim + 4 * c, t);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) dv[i][e] += t[e];
-                    if (sub_next) {
-                        ld4(dy2 + (row + tokens_pf) * dim + 4 * c, t);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) dv[i][e] -= t[e];
-                    }
-                }
                 float gm[4], pg[4], pb[4];
                 ld4(gamma + 4 * c, gm);
                 ld4(s_dg + 4 * c, pg);
@@ -165,13 +176,32 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
 // exact-erf GELU (nn.GELU(), module.py:28), elementwise on bf16: forward and backward
 //   gelu'(x) = 0.5 * (1 + erf(x / sqrt 2)) + x * exp(-x^2 / 2) / sqrt(2 pi)
 // ------------------------------------------------------------------------------------------
+// erf by Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7: fp32 noise for these uses), 2 MUFU (rcp, ex2) + FMAs —
+// erff + expf made both kernels XU-bound at 3.4-3.8 TB/s.  Returns Phi(x) and phi(x) together (they share the
+// exponential exp(-x^2 / 2)).
+__device__ __forceinline__ void gauss_cdf_pdf(float x, float& cdf, float& pdf) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(z, 0.3275911f, 1.0f)));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));   // exp(-x^2 / 2)
+    const float erf_abs = fmaf(-p, e, 1.0f);
+    cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
+    pdf = 0.3989422804014327f * e;
+}
+
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t n8) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n8) return;
     float v[8];
     load8(x + i * 8, v);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.5f * v[e] * (1.0f + erff(v[e] * 0.70710678118654752440f));
+    for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
     store8(y + i * 8, v);
 }
 __global__ void __launch_bounds__(256)
@@ -183,8 +213,8 @@ gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* _
     load8(dy + i * 8, d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const float cdf = 0.5f * (1.0f + erff(v[e] * 0.70710678118654752440f));
-        const float pdf = 0.3989422804014327f * __expf(-0.5f * v[e] * v[e]);
+        float cdf, pdf;
+        gauss_cdf_pdf(v[e], cdf, pdf);
         d[e] *= fmaf(v[e], pdf, cdf);
     }
     store8(dx + i * 8, d);

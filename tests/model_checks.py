@@ -263,3 +263,36 @@ def run_relevance_check(batch: int = 2):
     assert torch.allclose(cs, cam_s[0], rtol=1e-3, atol=0) and torch.allclose(ct, cam_t[0], rtol=1e-3, atol=0)
     print("relevance profile:", profile)
     return errs
+
+
+def run_graph_check():
+    """CUDA-graph replay of the forward (batch 1, the test_time.py use case) == eager forward, and is faster."""
+    import time
+    m = pkg()
+    model = build_model({"seed": 0, "frames": 6, "sensitised": True}).cuda().eval()
+    x = make_input(1, 6, seed=5).cuda()
+    with torch.no_grad():
+        want = model(x).clone()
+    g = m.GraphedForward(model, x)
+    got = g(x).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(got, want), f"graph replay {got.flatten().tolist()} != eager {want.flatten().tolist()}"
+    x2 = make_input(1, 6, seed=6).cuda()
+    with torch.no_grad():
+        want2 = model(x2).clone()
+    assert torch.equal(g(x2), want2)
+    def timeit(fn, n=50):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+    with torch.no_grad():
+        eager_ms = timeit(lambda: model(x))
+    graph_ms = timeit(lambda: g(x))
+    print(f"batch-1 latency: eager {eager_ms:.3f} ms, CUDA graph {graph_ms:.3f} ms")
+    assert graph_ms < eager_ms
+    return {"eager_ms": eager_ms, "graph_ms": graph_ms}

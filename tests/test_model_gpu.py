@@ -31,3 +31,8 @@ def test_training_step_against_reference_golden():
 @pytest.mark.gpu
 def test_relevance_pass_against_oracle():
     model_checks.run_relevance_check()
+
+
+@pytest.mark.gpu
+def test_cuda_graph_forward():
+    model_checks.run_graph_check()

@@ -32,6 +32,7 @@ def all_checks():
     checks["golden_t32_fp32"] = lambda: model_checks.run_golden_case("sensitised_t32_b1", "fp32")
     checks["train_golden"] = model_checks.run_train_golden
     checks["relevance"] = model_checks.run_relevance_check
+    checks["cuda_graph"] = model_checks.run_graph_check
     return checks
 
 
