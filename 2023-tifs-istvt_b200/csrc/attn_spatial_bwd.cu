@@ -8,9 +8,11 @@
 // P uses the log-sum-exp saved by the forward (istvt_attn_spatial_fwd_lse), so no second softmax pass is needed.
 // (A tcgen05 version is the follow-up; this kernel is ~5 % of the training step.)
 #include "common.cuh"
+#include "ptx.cuh"
 #include "simt_util.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace istvt {
 
@@ -264,6 +266,256 @@ attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// tcgen05 version.  Legacy mma.sync peaks near 512 FLOP/clk/SM on sm_100a (the kernel above sits at that ceiling,
+// 112-126 TFLOP/s), so the five contractions move to the 5th-gen tensor cores:
+//   one CTA = (frame, head, 128-key chunk); loop over the 128-query tiles.
+//   TMEM : S [128q x 128k] cols 0-127, dP cols 128-255, dV [128k x 64] 256-319, dK 320-383, dQ [128q x 64] 384-447.
+//   smem : K, V chunk (16 KB each), Q / dO tile double buffered (2 x 32 KB), P and dS [128q x 128k] bf16 (32 KB each),
+//          all 128-byte swizzled.  One byte layout serves every operand role: a [rows x 64] tile is K-major for
+//          S = Q K^T / dP = dO V^T and MN-major (N = 64 contiguous) as the B of dV = P^T dO, dK = dS^T Q, dQ = dS K;
+//          the P / dS tile [atom(64 keys)][query row][128 B] is K-major A for dQ and MN-major A (M = keys) for dV / dK.
+//   roles: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4-11: D = rowsum(dO o O), P = exp2(S c - lse),
+//          dS = P o (dP - D) * scale -> smem, dQ tile -> red.global.add (summed over the key chunks), final dK / dV.
+// ------------------------------------------------------------------------------------------
+constexpr int TB_THREADS = 384;
+constexpr int TB_TILE = 128 * 64 * 2;                 // 16 KB: 128 rows x 64 bf16
+constexpr int TB_K_OFF = 0, TB_V_OFF = TB_TILE, TB_Q_OFF = 2 * TB_TILE, TB_DO_OFF = 4 * TB_TILE;
+constexpr int TB_P_OFF = 6 * TB_TILE, TB_DS_OFF = 8 * TB_TILE, TB_MISC_OFF = 10 * TB_TILE;      // 160 KB
+constexpr int TB_SMEM = TB_MISC_OFF + 1024 + 256 + 2 * 128 * 4 + 128 * 4;
+
+__global__ void __launch_bounds__(TB_THREADS, 1)
+attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                           const bf16* __restrict__ o, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                           bf16* __restrict__ dqkv, float* __restrict__ dq_acc, float* __restrict__ cam, int tokens,
+                           int heads, float scale) {
+    extern __shared__ uint8_t tb_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tb_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TB_MISC_OFF);
+    uint64_t* kv_full = bars;
+    uint64_t* q_full = bars + 1;      // [2]
+    uint64_t* q_empty = bars + 3;     // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* p_ready = bars + 6;
+    uint64_t* dq_full = bars + 7;
+    uint64_t* dq_empty = bars + 8;
+    uint64_t* fin = bars + 9;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
+    float* s_dpart = reinterpret_cast<float*>(smem + TB_MISC_OFF + 256);    // [2][128] partial D
+    float* s_lse = s_dpart + 256;                                            // [128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k_chunks = (tokens + 127) / 128;
+    const int q_tiles = k_chunks;
+    const int kc = blockIdx.x % k_chunks;
+    const int h = (blockIdx.x / k_chunks) % heads;
+    const int bf = blockIdx.x / (k_chunks * heads);
+    const int inner = heads * SB_DH;
+    const int64_t row0 = static_cast<int64_t>(bf) * tokens;
+    const float scale_log2 = scale * 1.4426950408889634f;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do); }
+    if (warp == 1 && lane == 0) {
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(q_full + i, 1); mbar_init(q_empty + i, 1); }
+        mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(dq_full, 1); mbar_init(dq_empty, 8); mbar_init(fin, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+    const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem + 256, t_dk = tmem + 320, t_dq = tmem + 384;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(kv_full, 2 * TB_TILE);
+            tma_load_3d(smem + TB_K_OFF, &tm_qkv, kv_full, inner + h * SB_DH, kc * 128, bf);
+            tma_load_3d(smem + TB_V_OFF, &tm_qkv, kv_full, 2 * inner + h * SB_DH, kc * 128, bf);
+            for (int t = 0; t < q_tiles; ++t) {
+                const int slot = t & 1;
+                mbar_wait_sleep(q_empty + slot, ((t >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(q_full + slot, 2 * TB_TILE);
+                tma_load_3d(smem + TB_Q_OFF + slot * TB_TILE, &tm_qkv, q_full + slot, h * SB_DH, t * 128, bf);
+                tma_load_3d(smem + TB_DO_OFF + slot * TB_TILE, &tm_do, q_full + slot, h * SB_DH, t * 128, bf);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (elect_one()) {
+            const uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);     // S, dP: A, B K-major
+            const uint32_t id_t = make_idesc_bf16(128, 64, 1, 1);      // dV, dK: A (P^T / dS^T) and B MN-major
+            const uint32_t id_q = make_idesc_bf16(128, 64, 0, 1);      // dQ: A K-major, B MN-major
+            const uint64_t d_kmaj = make_smem_desc(0, 0, 1024, SWZ_128B);
+            const uint64_t d_mn_a = make_smem_desc(0, 128 * 128, 1024, SWZ_128B);   // atoms of 64 keys are 16 KB apart
+            const uint64_t d_mn_b = make_smem_desc(0, 128 * 128, 1024, SWZ_128B);   // N = 64: a single atom
+            auto fld = [&](int off) { return static_cast<uint64_t>((smem_u32(smem + off) & 0x3FFFFu) >> 4); };
+            const uint64_t k_f = fld(TB_K_OFF), v_f = fld(TB_V_OFF), p_f = fld(TB_P_OFF), ds_f = fld(TB_DS_OFF);
+            mbar_wait(kv_full, 0);
+            for (int t = 0; t < q_tiles; ++t) {
+                const int slot = t & 1;
+                const uint64_t q_f = fld(TB_Q_OFF + slot * TB_TILE), do_f = fld(TB_DO_OFF + slot * TB_TILE);
+                mbar_wait(q_full + slot, (t >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)      // S = Q K^T
+                    umma_f16_ss(t_s, d_kmaj | (q_f + 2 * k), d_kmaj | (k_f + 2 * k), id_s, k != 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)      // dP = dO V^T
+                    umma_f16_ss(t_dp, d_kmaj | (do_f + 2 * k), d_kmaj | (v_f + 2 * k), id_s, k != 0 ? 1u : 0u);
+                umma_commit(s_full);
+                mbar_wait(p_ready, t & 1);                       // P, dS in smem; S / dP TMEM consumed
+                mbar_wait(dq_empty, (t & 1) ^ 1);                // previous dQ tile drained
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)      // dQ = dS K   (A K-major: key atom j>>2, 32 B per k-step; B = K MN-major)
+                    umma_f16_ss(t_dq, d_kmaj | (ds_f + (j >> 2) * (128 * 128 >> 4) + (j & 3) * 2),
+                                d_mn_b | (k_f + j * (16 * 128 >> 4)), id_q, j != 0 ? 1u : 0u);
+                umma_commit(dq_full);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)      // dV += P^T dO   (k-step = 16 queries = 2048 B in both operands)
+                    umma_f16_ss(t_dv, d_mn_a | (p_f + j * (16 * 128 >> 4)), d_mn_b | (do_f + j * (16 * 128 >> 4)), id_t,
+                                (t | j) != 0 ? 1u : 0u);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)      // dK += dS^T Q
+                    umma_f16_ss(t_dk, d_mn_a | (ds_f + j * (16 * 128 >> 4)), d_mn_b | (q_f + j * (16 * 128 >> 4)), id_t,
+                                (t | j) != 0 ? 1u : 0u);
+                umma_commit(q_empty + slot);
+            }
+            umma_commit(fin);
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ================= softmax / dS / epilogues =================
+        const int quad = warp & 3, half = (warp - 4) >> 2;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+        const float ih = 1.0f / static_cast<float>(heads);
+        for (int t = 0; t < q_tiles; ++t) {
+            const int q_idx = t * 128 + row;
+            const bool row_ok = q_idx < tokens;
+            // D = rowsum(dO o O): this thread's 32 of the 64 dims (overlaps the S / dP MMAs)
+            float dpart = 0.f;
+            if (row_ok) {
+                const bf16* dop = dout + (row0 + q_idx) * inner + h * SB_DH + half * 32;
+                const bf16* op = o + (row0 + q_idx) * inner + h * SB_DH + half * 32;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float a[8], b[8];
+                    load8(dop + c * 8, a);
+                    load8(op + c * 8, b);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dpart = fmaf(a[e], b[e], dpart);
+                }
+            }
+            s_dpart[half * 128 + row] = dpart;
+            if (half == 0) s_lse[row] = row_ok ? lse[(static_cast<int64_t>(bf) * heads + h) * tokens + q_idx] : INFINITY;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float dsum = s_dpart[row] + s_dpart[128 + row];
+            const float l = s_lse[row];
+
+            mbar_wait(s_full, t & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int col0 = half * 64 + b * 32;               // key column inside the chunk
+                uint32_t rs[32], rd[32];
+                tmem_ld_32x32b_x32(t_s + lane_base + col0, rs);
+                tmem_ld_32x32b_x32(t_dp + lane_base + col0, rd);
+                tmem_ld_wait();
+                uint32_t pk[16], dk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float p[2], ds[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int kg = kc * 128 + col0 + 2 * j + e;
+                        const float dpv = __uint_as_float(rd[2 * j + e]);
+                        p[e] = (kg < tokens) ? ex2_approx(fmaf(__uint_as_float(rs[2 * j + e]), scale_log2, -l)) : 0.f;
+                        ds[e] = p[e] * (dpv - dsum) * scale;
+                        if (cam != nullptr && row_ok && kg < tokens)
+                            atomicAdd(cam + (static_cast<int64_t>(bf) * tokens + q_idx) * tokens + kg,
+                                      fmaxf(p[e] * dpv, 0.f) * ih);
+                    }
+                    pk[j] = pack_bf16x2(p[0], p[1]);
+                    dk[j] = pack_bf16x2(ds[0], ds[1]);
+                }
+                // [atom = 64 keys][query row][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+                const int atom = col0 >> 6, chunk0 = (col0 & 63) >> 3;
+                uint8_t* prow = smem + TB_P_OFF + atom * (128 * 128) + row * 128;
+                uint8_t* drow = smem + TB_DS_OFF + atom * (128 * 128) + row * 128;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int chunk = (chunk0 + g) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    *reinterpret_cast<uint4*>(drow + chunk * 16) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+
+            // dQ tile: this thread's 32 of the 64 dims of its query row, accumulated over the key chunks in global
+            mbar_wait(dq_full, t & 1);
+            tc_fence_after();
+            {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_dq + lane_base + half * 32, r);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dq_empty);
+                if (row_ok) {
+                    float* dst = dq_acc + (row0 + q_idx) * inner + h * SB_DH + half * 32;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
+                                     "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
+                                     "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
+                                     : "memory");
+                }
+            }
+        }
+        // ---- dK, dV of this key chunk ----
+        mbar_wait(fin, 0);
+        tc_fence_after();
+        {
+            const int key = kc * 128 + row;
+            uint32_t rk[32], rv[32];
+            tmem_ld_32x32b_x32(t_dk + lane_base + half * 32, rk);
+            tmem_ld_32x32b_x32(t_dv + lane_base + half * 32, rv);
+            tmem_ld_wait();
+            if (key < tokens) {
+                bf16* base = dqkv + (row0 + key) * (3 * inner) + h * SB_DH + half * 32;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 a, b;
+                    a.x = pack_bf16x2(__uint_as_float(rk[8 * g]), __uint_as_float(rk[8 * g + 1]));
+                    a.y = pack_bf16x2(__uint_as_float(rk[8 * g + 2]), __uint_as_float(rk[8 * g + 3]));
+                    a.z = pack_bf16x2(__uint_as_float(rk[8 * g + 4]), __uint_as_float(rk[8 * g + 5]));
+                    a.w = pack_bf16x2(__uint_as_float(rk[8 * g + 6]), __uint_as_float(rk[8 * g + 7]));
+                    b.x = pack_bf16x2(__uint_as_float(rv[8 * g]), __uint_as_float(rv[8 * g + 1]));
+                    b.y = pack_bf16x2(__uint_as_float(rv[8 * g + 2]), __uint_as_float(rv[8 * g + 3]));
+                    b.z = pack_bf16x2(__uint_as_float(rv[8 * g + 4]), __uint_as_float(rv[8 * g + 5]));
+                    b.w = pack_bf16x2(__uint_as_float(rv[8 * g + 6]), __uint_as_float(rv[8 * g + 7]));
+                    *reinterpret_cast<uint4*>(base + inner + 8 * g) = a;
+                    *reinterpret_cast<uint4*>(base + 2 * inner + 8 * g) = b;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 // dq_acc fp32 [rows, inner] -> q columns of dqkv [rows, 3 inner] (bf16)
 __global__ void __launch_bounds__(256)
 attn_spatial_bwd_dq_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv, int64_t rows, int inner) {
@@ -295,13 +547,38 @@ static int attn_spatial_bwd_launch(const void* qkv, const void* o, const void* d
     const int inner = heads * SB_DH;
     const int64_t rows = static_cast<int64_t>(batch_frames) * tokens;
     ISTVT_CHECK_CUDA(cudaMemsetAsync(dq_scratch, 0, static_cast<size_t>(rows) * inner * sizeof(float), st));
-    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
+    static const bool legacy = []() { const char* e = getenv("ISTVT_ATTN_BWD_LEGACY"); return e && atoi(e) != 0; }();
     const int k_blocks = (tokens + SB_KB - 1) / SB_KB;
     const int64_t grid = static_cast<int64_t>(batch_frames) * heads * k_blocks;
     ISTVT_REQUIRE(grid < (int64_t(1) << 31));
-    attn_spatial_bwd_kernel<<<static_cast<unsigned>(grid), SB_THREADS, SB_SMEM, st>>>(
-        static_cast<const bf16*>(qkv), static_cast<const bf16*>(o), static_cast<const bf16*>(dout), lse,
-        static_cast<bf16*>(dqkv), dq_scratch, cam, tokens, heads, scale);
+    if (legacy || tokens > 384) {
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
+        attn_spatial_bwd_kernel<<<static_cast<unsigned>(grid), SB_THREADS, SB_SMEM, st>>>(
+            static_cast<const bf16*>(qkv), static_cast<const bf16*>(o), static_cast<const bf16*>(dout), lse,
+            static_cast<bf16*>(dqkv), dq_scratch, cam, tokens, heads, scale);
+    } else {
+        CUtensorMap tm_qkv, tm_do;
+        {
+            const uint64_t dims[3] = {static_cast<uint64_t>(3 * inner), static_cast<uint64_t>(tokens),
+                                      static_cast<uint64_t>(batch_frames)};
+            const uint64_t strides[2] = {static_cast<uint64_t>(3 * inner) * 2, static_cast<uint64_t>(tokens) * 3 * inner * 2};
+            const uint32_t box[3] = {SB_DH, 128, 1};
+            int rc = encode_tmap(&tm_qkv, qkv, ISTVT_BF16, 3, dims, strides, box, 3);
+            if (rc != ISTVT_OK) return rc;
+        }
+        {
+            const uint64_t dims[3] = {static_cast<uint64_t>(inner), static_cast<uint64_t>(tokens),
+                                      static_cast<uint64_t>(batch_frames)};
+            const uint64_t strides[2] = {static_cast<uint64_t>(inner) * 2, static_cast<uint64_t>(tokens) * inner * 2};
+            const uint32_t box[3] = {SB_DH, 128, 1};
+            int rc = encode_tmap(&tm_do, dout, ISTVT_BF16, 3, dims, strides, box, 3);
+            if (rc != ISTVT_OK) return rc;
+        }
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM));
+        attn_spatial_bwd_tc_kernel<<<static_cast<unsigned>(grid), TB_THREADS, TB_SMEM, st>>>(
+            tm_qkv, tm_do, static_cast<const bf16*>(o), static_cast<const bf16*>(dout), lse, static_cast<bf16*>(dqkv),
+            dq_scratch, cam, tokens, heads, scale);
+    }
     count_launch();
     const int64_t n = rows * (inner / 8);
     attn_spatial_bwd_dq_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(dq_scratch,
