@@ -8,6 +8,8 @@
 #include "ptx.cuh"
 #include "simt_util.cuh"
 
+#include <stdlib.h>
+
 namespace istvt {
 
 // ------------------------------------------------------------------------------------------
@@ -217,6 +219,179 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// depthwise 3x3 pad 1, bf16 production kernel: column strips walked top to bottom.
+//
+// ncu of the tile kernel above (profiles/README.md r1k) showed it instruction-issue bound, not HBM bound: 64 % of
+// the issue slots at 2.7-3.1 TB/s, ~34 thread-instructions per output once the (TH+2)/TH halo rows, the 16x16
+// tile padding of the 147 / 74 / 37-wide maps (up to 1.68x) and the 3x re-load + ReLU + unpack of every input
+// element are counted.  This kernel cuts the count to ~14 per output:
+//   * work item = (image, 64-channel group, column strip, row segment); a dedicated producer warp streams the
+//     strip through a ring of DS_R-row TMA slabs (4-D map, zero-filled pad-1 border and ragged edges), so there
+//     is no per-tile restart and the only halo rows are the 2 at each segment boundary;
+//   * thread = 4 channels x TWO adjacent columns: 4 smem vectors per input row feed 2 outputs (was 3 per 1),
+//     ReLU on packed bf16 pairs (HMNMX2), three rolling accumulator sets renamed by the 6-row unroll (no moves);
+//   * strips are sized to the map (38 outputs: 147 -> 4, 74 -> 2, 37 -> 1 strips, <= 3.4 % padding) and row
+//     segments are chosen so that the persistent grid sees >= 12 waves of items.
+// HBM floor: (2 + 2) B per output; the FMA pipe needs 9 of the ~14 issue slots.
+// ------------------------------------------------------------------------------------------
+constexpr int DS_CG = 64;            // channels per item (one 128-byte line per pixel)
+constexpr int DS_R = 6;              // input rows per ring stage (multiple of 3: accumulator roles realign)
+constexpr int DS_STAGES = 3;
+constexpr int DS_MAX_PAIRS = 19;     // column pairs per strip -> strips of <= 38 outputs
+constexpr int DS_MAX_THREADS = ((16 * DS_MAX_PAIRS + 31) / 32) * 32;   // 320 (a producer warp would cap the
+                                                                        // kernel at 80 registers and spill)
+
+// predicated 8-byte store of 4 fp32 values rounded to bf16 (no branch, no divergence bookkeeping in the hot loop)
+__device__ __forceinline__ void stg_bf16x4_pred(__nv_bfloat16* p, const float (&v)[4], bool pred) {
+    const uint32_t lo = pack_bf16x2(v[0], v[1]), hi = pack_bf16x2(v[2], v[3]);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.b32 [%0], {%1, %2};\n\t}" ::"l"(p), "r"(lo),
+                 "r"(hi), "r"(static_cast<uint32_t>(pred))
+                 : "memory");
+}
+
+struct DwStripPlan {
+    int pairs, strips, segs, seg_h, cgroups, warps;
+    int64_t items;
+};
+
+template <bool RELU>
+__global__ void __launch_bounds__(DS_MAX_THREADS, 2)
+dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ wt,
+                       __nv_bfloat16* __restrict__ y, int n, int h, int w, int c, const DwStripPlan plan) {
+    extern __shared__ __align__(128) uint8_t dw_smem[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem) + 127) & ~uintptr_t(127));
+    const int in_w = 2 * plan.pairs + 2;
+    const uint32_t stage_bytes = static_cast<uint32_t>(DS_R * in_w * DS_CG * 2);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + DS_STAGES * stage_bytes);
+    uint64_t* empty_bar = full_bar + DS_STAGES;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int n_st = (plan.seg_h + 2 + DS_R - 1) / DS_R;          // ring stages per item
+    const int my_items = plan.items > static_cast<int64_t>(blockIdx.x)
+                             ? static_cast<int>((plan.items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int total_g = my_items * n_st;                           // ring stages this CTA consumes
+
+    if (tid == 0) {
+        for (int s = 0; s < DS_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], plan.warps);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tm_x);
+    }
+    __syncthreads();
+
+    // item -> (img, cg, strip, seg); seg fastest so that a CTA's consecutive items continue down the same strip
+    auto decode = [&](int64_t item, int& img, int& cg, int& x0, int& y0) {
+        const int seg = static_cast<int>(item % plan.segs);
+        int64_t r = item / plan.segs;
+        const int strip = static_cast<int>(r % plan.strips);
+        r /= plan.strips;
+        cg = static_cast<int>(r % plan.cgroups);
+        img = static_cast<int>(r / plan.cgroups);
+        x0 = strip * 2 * plan.pairs;
+        y0 = seg * plan.seg_h;
+    };
+    // thread 0 only: TMA load of ring stage g (slot g % DS_STAGES), after every warp released the slot's previous use
+    auto produce = [&](int g) {
+        if (g >= total_g) return;
+        const int k = g / n_st, st = g - k * n_st;
+        int img, cg, x0, y0;
+        decode(static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(k) * gridDim.x, img, cg, x0, y0);
+        const int slot = g % DS_STAGES;
+        const int use = g / DS_STAGES;
+        if (use > 0) mbar_wait(&empty_bar[slot], (use - 1) & 1);
+        mbar_arrive_expect_tx(&full_bar[slot], stage_bytes);
+        tma_load_4d(base + slot * stage_bytes, &tm_x, &full_bar[slot], cg * DS_CG, x0 - 1, y0 - 1 + st * DS_R, img);
+    };
+    if (tid == 0) {
+        for (int g = 0; g < DS_STAGES - 1; ++g) produce(g);
+    }
+
+    const int cq = tid & 15;                       // channel quad inside the group
+    const int pair = tid >> 4;                     // column pair inside the strip
+    const bool active = pair < plan.pairs;         // the last warp may be half empty
+    const int pair_c = active ? pair : 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    int g = 0;
+    for (int k = 0; k < my_items; ++k) {
+        int img, cg, x0, y0;
+        decode(static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(k) * gridDim.x, img, cg, x0, y0);
+        const int ch = cg * DS_CG + cq * 4;
+        const bool ch_ok = active && ch < c;
+        const int ox = x0 + 2 * pair_c;
+        const bool st0 = ch_ok && ox < w, st1 = ch_ok && ox + 1 < w;
+        const int y_end = min(y0 + plan.seg_h, h);
+
+        float wk[9][4];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const float4 t = ch_ok ? __ldg(reinterpret_cast<const float4*>(wt + q * c + ch)) : make_float4(0, 0, 0, 0);
+            wk[q][0] = t.x; wk[q][1] = t.y; wk[q][2] = t.z; wk[q][3] = t.w;
+        }
+        // output pointer of "input row r - 2"; advanced by one image row per input row (no per-store multiplies)
+        const int64_t pitch = static_cast<int64_t>(w) * c;
+        __nv_bfloat16* yp = y + (static_cast<int64_t>(img) * h * w + ox) * c + ch + static_cast<int64_t>(y0 - 2) * pitch;
+        const uint32_t rows_valid = static_cast<uint32_t>(y_end - y0);
+        // three accumulator sets; at input row r, set r % 3 is fresh (ky = 0), (r-1) % 3 takes ky = 1 and (r-2) % 3
+        // takes ky = 2 and is complete (output row r - 2).  Rows 0 / 1 of an item leave garbage in the sets that
+        // would belong to output rows -2 / -1: never stored.
+        float acc[3][2][4];
+        for (int st = 0; st < n_st; ++st, ++g) {
+            if (tid == 0) produce(g + DS_STAGES - 1);
+            __syncwarp();
+            mbar_wait(&full_bar[stage], phase);
+            const uint32_t srow = smem_u32(base) + stage * stage_bytes + (2 * pair_c) * (DS_CG * 2) + cq * 8;
+            const uint32_t rbase = static_cast<uint32_t>(st * DS_R - 2);
+#pragma unroll
+            for (int i = 0; i < DS_R; ++i) {
+                float f[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint2 t;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t.x), "=r"(t.y) : "r"(srow + (i * in_w + q) * (DS_CG * 2)));
+                    if (RELU) {
+                        const __nv_bfloat162 z = __float2bfloat162_rn(0.0f);
+                        __nv_bfloat162 lo = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&t.x), z);
+                        __nv_bfloat162 hi = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&t.y), z);
+                        t.x = *reinterpret_cast<uint32_t*>(&lo);
+                        t.y = *reinterpret_cast<uint32_t*>(&hi);
+                    }
+                    f[q][0] = __uint_as_float(t.x << 16); f[q][1] = __uint_as_float(t.x & 0xffff0000u);
+                    f[q][2] = __uint_as_float(t.y << 16); f[q][3] = __uint_as_float(t.y & 0xffff0000u);
+                }
+                const int s_new = i % 3, s_mid = (i + 2) % 3, s_old = (i + 1) % 3;   // rows r, r-1, r-2 (DS_R % 3 == 0)
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a = acc[s_old][o][e];
+                        a = fmaf(f[o][e], wk[6][e], a); a = fmaf(f[o + 1][e], wk[7][e], a); a = fmaf(f[o + 2][e], wk[8][e], a);
+                        acc[s_old][o][e] = a;
+                        float b = acc[s_mid][o][e];
+                        b = fmaf(f[o][e], wk[3][e], b); b = fmaf(f[o + 1][e], wk[4][e], b); b = fmaf(f[o + 2][e], wk[5][e], b);
+                        acc[s_mid][o][e] = b;
+                        float d = f[o][e] * wk[0][e];
+                        d = fmaf(f[o + 1][e], wk[1][e], d); d = fmaf(f[o + 2][e], wk[2][e], d);
+                        acc[s_new][o][e] = d;
+                    }
+                }
+                // input row r = st * DS_R + i of the segment completes output row y0 + r - 2
+                const bool row_ok = rbase + i < rows_valid;        // unsigned: also false for r < 2
+                stg_bf16x4_pred(yp, acc[s_old][0], row_ok && st0);
+                stg_bf16x4_pred(yp + c, acc[s_old][1], row_ok && st1);
+                yp += pitch;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == DS_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+}
+
 // (A warp-level tensor-core variant — mma.sync with diagonal B fragments, ldmatrix row pointers into a swizzled
 // halo tile, 6 instructions per output instead of ~20 — was built, validated and measured SLOWER: 6.0 vs 4.4 ms
 // per step.  Legacy mma.sync on sm_100a peaks near 512 FLOP/clk/SM, 1/16 of tcgen05, and the diagonal trick
@@ -262,21 +437,49 @@ pool_add_kernel(const T* __restrict__ x, const T* __restrict__ skip, T* __restri
     const int ch = cg * 8;
 
     float m[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
     const T* xin = x + static_cast<int64_t>(img) * h * w * c + ch;
+    if constexpr (sizeof(T) == 2) {
+        // bf16: the maximum is exact in bf16, so the 9 taps are reduced on PACKED pairs (4 HMNMX2 per 16-byte load
+        // instead of 8 unpacks + 8 FMNMX: the fp32 version was issue-bound at 63 % of the HBM peak, profiles r1k/r1w)
+        const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+        __nv_bfloat162 pm[4] = {ninf, ninf, ninf, ninf};
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-        const int iy = 2 * oy - 1 + dy;
-        if (iy < 0 || iy >= h) continue;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = 2 * oy - 1 + dy;
+            if (iy < 0 || iy >= h) continue;
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const int ix = 2 * ox - 1 + dx;
-            if (ix < 0 || ix >= w) continue;
-            float v[8];
-            load8(xin + (static_cast<int64_t>(iy) * w + ix) * c, v);
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = 2 * ox - 1 + dx;
+                if (ix < 0 || ix >= w) continue;
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(xin + (static_cast<int64_t>(iy) * w + ix) * c));
+                pm[0] = __hmax2(pm[0], *reinterpret_cast<const __nv_bfloat162*>(&t.x));
+                pm[1] = __hmax2(pm[1], *reinterpret_cast<const __nv_bfloat162*>(&t.y));
+                pm[2] = __hmax2(pm[2], *reinterpret_cast<const __nv_bfloat162*>(&t.z));
+                pm[3] = __hmax2(pm[3], *reinterpret_cast<const __nv_bfloat162*>(&t.w));
+            }
+        }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(pm[i]);
+            m[2 * i] = f.x;
+            m[2 * i + 1] = f.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = 2 * oy - 1 + dy;
+            if (iy < 0 || iy >= h) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = 2 * ox - 1 + dx;
+                if (ix < 0 || ix >= w) continue;
+                float v[8];
+                load8(xin + (static_cast<int64_t>(iy) * w + ix) * c, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+            }
         }
     }
     float s[8];
@@ -363,6 +566,54 @@ static int launch_dwconv(const void* x, const float* wt, void* y, int n, int h, 
     return launch_status();
 }
 
+// strip / segment plan of the bf16 kernel for an [n, h, w, c] map on a persistent grid of `grid` CTAs
+static DwStripPlan plan_dw_strips(int n, int h, int w, int c, int64_t grid) {
+    DwStripPlan pl{};
+    pl.strips = (w + 2 * DS_MAX_PAIRS - 1) / (2 * DS_MAX_PAIRS);
+    const int tw = (w + pl.strips - 1) / pl.strips;
+    pl.pairs = (tw + 1) / 2;
+    pl.cgroups = (c + DS_CG - 1) / DS_CG;
+    const int64_t base_items = static_cast<int64_t>(n) * pl.cgroups * pl.strips;
+    int64_t segs = (12 * grid + base_items - 1) / base_items;      // >= 12 waves of items ...
+    const int64_t max_segs = (h + 17) / 18;                         // ... but segments of >= 18 rows (2 halo rows each)
+    if (segs > max_segs) segs = max_segs;
+    if (segs < 1) segs = 1;
+    pl.seg_h = static_cast<int>((h + segs - 1) / segs);
+    pl.segs = (h + pl.seg_h - 1) / pl.seg_h;
+    pl.warps = (16 * pl.pairs + 31) / 32;
+    pl.items = base_items * pl.segs;
+    return pl;
+}
+
+static int launch_dwconv_strips(const void* x, const float* wt, void* y, int n, int h, int w, int c, int relu_in,
+                                cudaStream_t st) {
+    const int64_t grid_max = static_cast<int64_t>(sm_count()) * 2;
+    const DwStripPlan pl = plan_dw_strips(n, h, w, c, grid_max);
+    const int in_w = 2 * pl.pairs + 2;
+    CUtensorMap tm;
+    const uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(w), static_cast<uint64_t>(h),
+                              static_cast<uint64_t>(n)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(w) * c * 2,
+                                 static_cast<uint64_t>(h) * w * c * 2};
+    const uint32_t box[4] = {DS_CG, static_cast<uint32_t>(in_w), DS_R, 1};
+    int rc = encode_tmap(&tm, x, ISTVT_BF16, 4, dims, strides, box, 0);
+    if (rc != ISTVT_OK) return rc;
+    const int smem = DS_STAGES * DS_R * in_w * DS_CG * 2 + 128 + 64;
+    const int threads = pl.warps * 32;
+    const int64_t grid = pl.items < grid_max ? pl.items : grid_max;
+    if (relu_in) {
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        dwconv3x3_strip_kernel<true><<<static_cast<unsigned>(grid), threads, smem, st>>>(
+            tm, wt, static_cast<__nv_bfloat16*>(y), n, h, w, c, pl);
+    } else {
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        dwconv3x3_strip_kernel<false><<<static_cast<unsigned>(grid), threads, smem, st>>>(
+            tm, wt, static_cast<__nv_bfloat16*>(y), n, h, w, c, pl);
+    }
+    count_launch();
+    return launch_status();
+}
+
 extern "C" int istvt_dwconv3x3_fwd(const void* x, const float* wt, void* y, int dtype, int n, int h, int w, int c,
                                    int relu_in, istvt_stream_t stream) {
     ISTVT_REQUIRE(x && wt && y);
@@ -370,7 +621,12 @@ extern "C" int istvt_dwconv3x3_fwd(const void* x, const float* wt, void* y, int 
     ISTVT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(wt) & 15) == 0);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (dtype == ISTVT_BF16) return launch_dwconv<__nv_bfloat16>(x, wt, y, n, h, w, c, relu_in, st);
+    if (dtype == ISTVT_BF16) {
+        // ISTVT_DW_TILES=1 selects the older 16x16-tile kernel (A/B measurements only)
+        static const bool tiles = []() { const char* e = getenv("ISTVT_DW_TILES"); return e && atoi(e) != 0; }();
+        if (tiles) return launch_dwconv<__nv_bfloat16>(x, wt, y, n, h, w, c, relu_in, st);
+        return launch_dwconv_strips(x, wt, y, n, h, w, c, relu_in, st);
+    }
     if (dtype == ISTVT_F32) return launch_dwconv<float>(x, wt, y, n, h, w, c, relu_in, st);
     return ISTVT_ERR_INVALID_ARG;
 }

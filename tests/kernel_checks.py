@@ -209,7 +209,8 @@ def check_dwconv():
     _noTF32()
     out = {}
     for (n, h, w, c, relu) in ((2, 147, 147, 64, False), (1, 74, 74, 128, True), (2, 37, 37, 728, True),
-                               (1, 5, 3, 8, False), (1, 1, 1, 16, True), (1, 9, 2, 256, False)):
+                               (1, 5, 3, 8, False), (1, 1, 1, 16, True), (1, 9, 2, 256, False),
+                               (20, 37, 37, 728, True), (3, 40, 77, 72, False)):   # several items per CTA; ragged strips
         x = _rand(n, h, w, c, seed=c)
         wt = _rand(3, 3, c, seed=7) * 0.3
         xin = F.relu(x) if relu else x
