@@ -27,6 +27,7 @@ SIGNATURES = {
     "istvt_gemm_f32_fwd": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _P, _L, _I, _P],
     "istvt_conv3x3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "istvt_conv_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "istvt_conv_stem_u8_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "istvt_dwconv3x3_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "istvt_subsample2_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "istvt_pool_add_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],

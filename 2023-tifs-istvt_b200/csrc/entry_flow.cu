@@ -92,6 +92,98 @@ conv_stem_kernel(const float* __restrict__ x, const float* __restrict__ wt, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// conv stem on decoded frames: uint8 NHWC [n, h, w, 3] in, same arithmetic.  The input normalisation
+// ((x / 255 - mean_c) / std_c) is affine per input channel and conv1 has no padding, so the host folds it into
+// `wt` / `bias` exactly like the BatchNorm scale; the kernel only converts bytes.  Each thread reads the 3 x 15
+// contiguous bytes under its two output pixels (7 aligned 16-bit loads + 1 byte per row).  Cuts the H2D copy and
+// the stem's HBM read 4x against the fp32 NCHW clip.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+conv_stem_u8_kernel(const uint8_t* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
+                    T* __restrict__ y, int n, int h, int w, int ho, int wo) {
+    __shared__ __align__(16) float sw[27 * STEM_CO];
+    __shared__ __align__(16) float sb[STEM_CO];
+    // wt is [co][ci][ky][kx] -> sw[(ky*9 + px*3 + ci)][co] for px = kx: byte order of an input row is (pixel, channel)
+    for (int i = threadIdx.x; i < 27 * STEM_CO; i += blockDim.x) {
+        const int co = i / 27, r = i - co * 27;
+        const int ci = r / 9, ky = (r - ci * 9) / 3, kx = r % 3;
+        sw[(ky * 9 + kx * 3 + ci) * STEM_CO + co] = wt[i];
+    }
+    if (threadIdx.x < STEM_CO) sb[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+
+    const int pairs = (wo + 1) >> 1;
+    const int64_t total = static_cast<int64_t>(n) * ho * pairs;
+    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int px = static_cast<int>(idx % pairs);
+        const int64_t t = idx / pairs;
+        const int oy = static_cast<int>(t % ho);
+        const int img = static_cast<int>(t / ho);
+        const int ox0 = px * 2;
+        const bool has2 = ox0 + 1 < wo;
+
+        float acc0[STEM_CO], acc1[STEM_CO];
+#pragma unroll
+        for (int c = 0; c < STEM_CO; ++c) { acc0[c] = sb[c]; acc1[c] = sb[c]; }
+
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            // 5 pixels x 3 channels = 15 bytes at an even offset (6 * ox0 + 3 * w * row): 16-bit loads are aligned
+            // when the row pitch 3 * w is even; otherwise fall back to byte loads for that row
+            const uint8_t* rowp = x + ((static_cast<int64_t>(img) * h + (2 * oy + ky)) * w + 2 * ox0) * 3;
+            float in[15];
+            const int nb = has2 ? 15 : 9;          // bytes under this thread's outputs; never read past them
+            if ((reinterpret_cast<uintptr_t>(rowp) & 1) == 0) {
+                const int n16 = nb >> 1;           // 7 or 4 aligned 16-bit loads, then the odd last byte
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const uint32_t v = j < n16 ? __ldg(reinterpret_cast<const unsigned short*>(rowp) + j) : 0u;
+                    in[2 * j] = static_cast<float>(v & 0xffu);
+                    in[2 * j + 1] = static_cast<float>(v >> 8);
+                }
+                const float last = static_cast<float>(__ldg(rowp + nb - 1));
+                if (has2) in[14] = last; else { in[8] = last; in[14] = 0.0f; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 15; ++j) in[j] = j < nb ? static_cast<float>(__ldg(rowp + j)) : 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {     // q = kx * 3 + ci
+                const float* wp = sw + (ky * 9 + q) * STEM_CO;
+                const float a0 = in[q], a1 = in[q + 6];
+#pragma unroll
+                for (int c = 0; c < STEM_CO; c += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + c);
+                    acc0[c] = fmaf(a0, wv.x, acc0[c]); acc0[c + 1] = fmaf(a0, wv.y, acc0[c + 1]);
+                    acc0[c + 2] = fmaf(a0, wv.z, acc0[c + 2]); acc0[c + 3] = fmaf(a0, wv.w, acc0[c + 3]);
+                    acc1[c] = fmaf(a1, wv.x, acc1[c]); acc1[c + 1] = fmaf(a1, wv.y, acc1[c + 1]);
+                    acc1[c + 2] = fmaf(a1, wv.z, acc1[c + 2]); acc1[c + 3] = fmaf(a1, wv.w, acc1[c + 3]);
+                }
+            }
+        }
+        T* yp = y + ((static_cast<int64_t>(img) * ho + oy) * wo + ox0) * STEM_CO;
+#pragma unroll
+        for (int c = 0; c < STEM_CO; c += 8) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaxf(acc0[c + e], 0.0f);
+            store8(yp + c, o);
+        }
+        if (has2) {
+#pragma unroll
+            for (int c = 0; c < STEM_CO; c += 8) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaxf(acc1[c + e], 0.0f);
+                store8(yp + STEM_CO + c, o);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // depthwise 3x3 pad 1, HBM-bound.  Persistent CTAs walk (image, channel-group, tile) work items; the
 // (TH+2) x (TW+2) x 64-channel halo tile of each item is fetched by ONE TMA load of a 4-D tensor map
 // (c, x, y, n) — the pad-1 border and ragged edges are the TMA's out-of-bounds zero fill — into a
@@ -348,6 +440,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
             const uint32_t rbase = static_cast<uint32_t>(st * DS_R - 2);
 #pragma unroll
             for (int i = 0; i < DS_R; ++i) {
+                if (st * DS_R + i >= static_cast<int>(rows_valid) + 2) break;   // slab rows past the segment's last input row (uniform)
                 float f[4][4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -532,6 +625,28 @@ static int conv_stem_launch(const float* x, const float* wt, const float* bias, 
 extern "C" int istvt_conv_stem_fwd(const float* x, const float* wt, const float* bias, void* y, int dtype, int n,
                                    int h, int w, int cout, istvt_stream_t stream) {
     return conv_stem_launch(x, wt, bias, y, dtype, n, h, w, cout, 1, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int istvt_conv_stem_u8_fwd(const uint8_t* x, const float* wt, const float* bias, void* y, int dtype, int n,
+                                      int h, int w, int cout, istvt_stream_t stream) {
+    ISTVT_REQUIRE(x && wt && bias && y);
+    ISTVT_REQUIRE(cout == STEM_CO && n > 0 && h >= 3 && w >= 3);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int ho = (h - 3) / 2 + 1, wo = (w - 3) / 2 + 1;
+    const int64_t total = static_cast<int64_t>(n) * ho * ((wo + 1) / 2);
+    int64_t blocks = (total + 127) / 128;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
+    if (blocks > cap) blocks = cap;
+    if (dtype == ISTVT_BF16)
+        conv_stem_u8_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 128, 0, st>>>(
+            x, wt, bias, static_cast<__nv_bfloat16*>(y), n, h, w, ho, wo);
+    else if (dtype == ISTVT_F32)
+        conv_stem_u8_kernel<float><<<static_cast<unsigned>(blocks), 128, 0, st>>>(x, wt, bias, static_cast<float*>(y), n,
+                                                                                    h, w, ho, wo);
+    else
+        return ISTVT_ERR_INVALID_ARG;
+    count_launch();
+    return launch_status();
 }
 
 // Training mode: the raw convolution (+ bias, normally zero) without the ReLU; BatchNorm batch statistics follow.

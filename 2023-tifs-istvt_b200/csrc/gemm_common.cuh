@@ -27,8 +27,6 @@ struct GemmParams {
     int kb_per_split; // every (tile, range) adds its partial product to the fp32 C with red.global (C pre-initialised)
     int mn_major;     // CTA-pair kernel: both operands are stored K-rows x MN-contiguous (A = dY [k, m], B = X [k, n]):
                       // the weight-gradient GEMM dW = dY^T X reads dY and X as they sit in HBM, no transposed copies
-    int prefetch_a;   // CTA-pair kernel, K-major, no split: while loading tile i the producer of the cluster whose NEXT
-                      // tile opens a new m-block (n_blk == 0) pulls that m-block's A rows into L2 with TMA prefetches
 };
 
 // ------------------------------------------------------------------------------------------

@@ -105,14 +105,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                 const int m0 = static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M);
                 const int n0 = n_blk * G2_BN + static_cast<int>(rank) * (tile_n_eff(n_blk) >> 1);
                 const int kb_end = (ks + 1) * kb_per < num_kb ? (ks + 1) * kb_per : num_kb;
-                // A rows are read from HBM exactly once (the other n-tiles of the m-block hit in L2), and that first
-                // touch used to stall the MMA warp at every tile start (profiles/r1h: 22 % of the stall samples on the
-                // full barrier while the producer was never blocked).  One tile ahead is ~4-7 us of lead.
-                const int64_t next = tile + n_clusters;
-                const bool pf = p.prefetch_a && next < total_tiles && next % n_tiles == 0;
-                const int m0_next = static_cast<int>((next / n_tiles) * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M);
                 for (int kb = ks * kb_per; kb < kb_end; ++kb) {
-                    if (pf) tma_prefetch_2d_l2(&tm_a, kb * G2_BK, m0_next);
                     mbar_wait_hot(&empty_bar[stage], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
                     if (!p.mn_major) {
@@ -272,6 +265,9 @@ int launch_gemm_2cta(const void* a, int64_t lda, const void* w, int64_t ldw, con
 
 static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmParams& p_in, cudaStream_t stream) {
     const GemmParams& p0 = p_in;
+    // (A TMA L2 prefetch of the next m-block's A rows one tile ahead was measured SLOWER — layer GEMM sum 2.42 ->
+    //  2.57 ms: the kernel is bound by L2->SM delivery, not by first-touch DRAM latency, and the prefetch requests
+    //  compete for the same L2 slices.  profiles/README.md r3a.)
     const int n_tiles = (p0.N + G2_BN - 1) / G2_BN;
     const int64_t m_tiles = (p0.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
     const int64_t total = m_tiles * n_tiles * (p0.split_k > 1 ? p0.split_k : 1);
@@ -284,12 +280,7 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
         const char* e = getenv("ISTVT_G2_EPI_WARPS");
         return e ? atoi(e) : 0;
     }();
-    static const int pf_env = []() {
-        const char* e = getenv("ISTVT_G2_PREFETCH");
-        return e ? atoi(e) : 1;
-    }();
-    GemmParams p = p_in;
-    p.prefetch_a = (pf_env && !p.mn_major && p.split_k <= 1) ? 1 : 0;
+    const GemmParams& p = p_in;
     const bool plain = !p.c_f32 && p.residual == nullptr;
     const int ew = ew_env == 8 || ew_env == 16 ? ew_env : (plain ? 16 : 8);
     const unsigned grid = static_cast<unsigned>(2 * clusters);

@@ -104,13 +104,6 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-// TMA prefetch of a 2-D box into L2 only (no smem destination, no barrier): hides the DRAM latency of operand rows
-// that nobody has touched yet (the first k-blocks of a new GEMM m-block).
-__device__ __forceinline__ void tma_prefetch_2d_l2(const CUtensorMap* m, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
-                 "r"(c0), "r"(c1)
-                 : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

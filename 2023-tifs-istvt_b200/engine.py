@@ -73,6 +73,9 @@ class _EntryPack:
     conv2_w: torch.Tensor
     conv2_b: torch.Tensor
     blocks: List[_BlockPack]
+    u8_key: Optional[tuple] = None        # (mean, std) the uint8-input stem weights below were folded for
+    u8_w: Optional[torch.Tensor] = None
+    u8_b: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -116,6 +119,18 @@ def pack_entry(xcep, dt: torch.dtype) -> _EntryPack:
     conv2_w = (xcep.conv2.weight.detach().float() * s2[:, None, None, None]).permute(0, 2, 3, 1).to(dt).contiguous()
     blocks = [_pack_block(b, dt) for b in (xcep.block1, xcep.block2, xcep.block3)]
     return _EntryPack(stem_w=stem_w, stem_b=b1.contiguous(), conv2_w=conv2_w, conv2_b=b2.contiguous(), blocks=blocks)
+
+
+def fold_input_norm(stem_w: torch.Tensor, stem_b: torch.Tensor, mean, std) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fold the per-channel input normalisation of decoded frames, x_norm = (u8 / 255 - mean_c) / std_c, into the
+    stem convolution: conv1 has no padding (xception.py:118), so conv(w, x_norm) + b == conv(w', u8) + b' with
+    w'[o, c] = w[o, c] / (255 std_c) and b'[o] = b[o] - sum_c (mean_c / std_c) sum_{ky,kx} w[o, c, ky, kx].
+    stem_w: fp32 [32, 3, 3, 3] (BN scale already folded), stem_b: fp32 [32]."""
+    mean_t = torch.as_tensor(mean, dtype=torch.float32, device=stem_w.device).reshape(3)
+    std_t = torch.as_tensor(std, dtype=torch.float32, device=stem_w.device).reshape(3)
+    w = stem_w / (255.0 * std_t)[None, :, None, None]
+    b = stem_b - (stem_w.sum(dim=(2, 3)) * (mean_t / std_t)[None, :]).sum(dim=1)
+    return w.contiguous(), b.contiguous()
 
 
 def _on_path_tensors(model) -> List[torch.Tensor]:
@@ -172,9 +187,18 @@ def _run_block(bp: _BlockPack, x: torch.Tensor, taps: Optional[dict], name: str)
     return y, skip.view(n, skip_in.shape[1], skip_in.shape[2], -1)
 
 
-def run_entry_flow(ep: _EntryPack, frames: torch.Tensor, dt: torch.dtype, taps: Optional[dict] = None):
-    """frames: fp32 NCHW [n, 3, H, W] -> (block-3 body [n, 37, 37, 728], block-3 skip [n, 19, 19, 728])."""
-    a = ops.conv_stem(frames, ep.stem_w, ep.stem_b, dt)                                # conv1+bn1+relu
+def run_entry_flow(ep: _EntryPack, frames: torch.Tensor, dt: torch.dtype, taps: Optional[dict] = None,
+                   input_norm=None):
+    """frames: fp32 NCHW [n, 3, H, W], or uint8 NHWC [n, H, W, 3] with `input_norm` = (mean, std)
+    -> (block-3 body [n, 37, 37, 728], block-3 skip [n, 19, 19, 728])."""
+    if frames.dtype == torch.uint8:
+        key = (tuple(float(v) for v in input_norm[0]), tuple(float(v) for v in input_norm[1]))
+        if ep.u8_key != key:
+            ep.u8_w, ep.u8_b = fold_input_norm(ep.stem_w, ep.stem_b, *key)
+            ep.u8_key = key
+        a = ops.conv_stem_u8(frames, ep.u8_w, ep.u8_b, dt)                             # normalise+conv1+bn1+relu
+    else:
+        a = ops.conv_stem(frames, ep.stem_w, ep.stem_b, dt)                            # conv1+bn1+relu
     a = ops.conv3x3(a, ep.conv2_w, ep.conv2_b, act=ops.ACT_RELU)                       # conv2+bn2+relu
     if taps is not None:
         taps["stem"] = a
@@ -219,13 +243,23 @@ class ISTVTEngine:
         vit = model.vit
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
-        if not isinstance(x, torch.Tensor) or x.dim() != 5 or x.shape[2] != 3:
+        is_u8 = isinstance(x, torch.Tensor) and x.dtype == torch.uint8
+        if is_u8:
+            # decoded frames, channels last: the normalisation is folded into the stem (fold_input_norm)
+            if x.dim() != 5 or x.shape[4] != 3:
+                raise ValueError("uint8 clips must be [B, T, H, W, 3] (decoded frames, channels last)")
+        elif not isinstance(x, torch.Tensor) or x.dim() != 5 or x.shape[2] != 3:
             raise ValueError("ISTVT expects a clip tensor [B, T, 3, H, W]")
         if not x.is_cuda:
             raise ValueError("ISTVT (istvt_b200) runs on CUDA tensors only: there is no CPU fallback by design")
-        b, t, _, hh, ww = x.shape
+        if is_u8:
+            b, t, hh, ww, _ = x.shape
+        else:
+            b, t, _, hh, ww = x.shape
         if t != vit.num_frames:
             raise ValueError(f"clip has {t} frames but the model was built with num_frames={vit.num_frames}")
+        if model.training and is_u8:
+            raise ValueError("uint8 clips are an inference-path input: normalise to fp32 [B, T, 3, H, W] for training")
         if model.training:
             # train mode without autograd (e.g. under torch.no_grad()): BatchNorm batch statistics, as the reference
             from .train import Trainer
@@ -252,16 +286,21 @@ class ISTVTEngine:
         f_tok = t + 1
         scale = 64 ** -0.5
 
-        frames = x.reshape(b * t, 3, hh, ww)
-        if frames.dtype != torch.float32 or not frames.is_contiguous():
-            frames = frames.float().contiguous()
+        input_norm = None
+        if is_u8:
+            frames = x.reshape(b * t, hh, ww, 3).contiguous()
+            input_norm = getattr(model, "input_norm", ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)))
+        else:
+            frames = x.reshape(b * t, 3, hh, ww)
+            if frames.dtype != torch.float32 or not frames.is_contiguous():
+                frames = frames.float().contiguous()
 
         # ---- Xception entry flow; block 3's pool+add lands in the token buffer ----
         if entry_precision is not None and entry_precision != precision:
             edt = PRECISIONS[entry_precision]
-            body, skip = run_entry_flow(self._pack(model, dev, entry_precision).entry, frames, edt, taps)
+            body, skip = run_entry_flow(self._pack(model, dev, entry_precision).entry, frames, edt, taps, input_norm)
         else:
-            body, skip = run_entry_flow(pk.entry, frames, dt, taps)
+            body, skip = run_entry_flow(pk.entry, frames, dt, taps, input_norm)
         tokens = torch.empty(b, f_tok, p_tok, dim, dtype=torch.float32, device=dev)
         ops.pool_add_tokens(body, skip, pk.pos_emb, tokens, b, t)
         ops.token_fill(tokens, pk.space_token, pk.temporal_token, pk.pos_emb)

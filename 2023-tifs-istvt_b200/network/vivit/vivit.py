@@ -56,7 +56,11 @@ class XceptionVidTr(nn.Module):
     """`XceptionVidTr()` as in the reference; `num_frames` / `precision` are additions with preserving defaults.
 
     forward(x: [B, T, 3, H, W] fp32 CUDA) -> logits [B, 1] fp32 (prediction = logit > 0, train_CNN.py:527).
+    Inference also accepts decoded frames, uint8 [B, T, H, W, 3]: the normalisation `input_norm` = (mean, std) per
+    channel on the [0, 1] scale — what the reference's (absent) `dataset.transform` does before the model,
+    train_CNN.py:18-21,172-173; xception.py:12-13 documents 0.5 / 0.5 — is folded into the stem convolution.
     """
+    input_norm = ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
 
     def __init__(self, num_frames: int = 6, precision: str = "bf16"):
         super().__init__()
@@ -80,6 +84,8 @@ class XceptionVidTr(nn.Module):
                 raise ValueError("attention maps are an inference-mode output")
             if not x.is_cuda:
                 raise ValueError("ISTVT (istvt_b200) runs on CUDA tensors only: there is no CPU fallback by design")
+            if x.dtype == torch.uint8:
+                raise ValueError("uint8 clips are an inference-path input: normalise to fp32 [B, T, 3, H, W] for training")
             from ...train import autograd_forward
             return autograd_forward(self, x)
         return self.engine().forward(self, x, precision=self.precision, return_attention=return_attention)

@@ -217,6 +217,22 @@ def conv_stem(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out_dtype: t
     return y
 
 
+def conv_stem_u8(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """x: uint8 NHWC [n, h, w, 3] (decoded frames); w: fp32 [32, 3, 3, 3] with BN scale AND the input normalisation
+    folded in (engine.fold_input_norm); -> NHWC [n, ho, wo, 32]."""
+    dev = _chk(x, w, bias)
+    if x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 3:
+        raise ValueError("conv_stem_u8 expects a uint8 NHWC [n, h, w, 3] input")
+    n, h, wd, _ = x.shape
+    cout = w.shape[0]
+    ho, wo = (h - 3) // 2 + 1, (wd - 3) // 2 + 1
+    y = torch.empty(n, ho, wo, cout, dtype=out_dtype, device=dev)
+    with _launch(dev, "conv_stem", 2.0 * y.numel() * 27, _nbytes(x, y)):
+        _lib.check(_lib.lib().istvt_conv_stem_u8_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), _dt(y), n, h, wd, cout,
+                                                     _stream(dev)), "istvt_conv_stem_u8_fwd")
+    return y
+
+
 def dwconv3x3(x: torch.Tensor, w: torch.Tensor, relu_in: bool) -> torch.Tensor:
     """x: NHWC; w: fp32 [3, 3, c]."""
     dev = _chk(x, w)

@@ -20,13 +20,13 @@ class ClipStream:
         self._bufs = None
         self._key = None
 
-    def _setup(self, shape, device):
-        key = (tuple(shape), str(device))
+    def _setup(self, shape, device, dtype=torch.float32):
+        key = (tuple(shape), str(device), dtype)
         if self._key == key:
             return
         self._key = key
         self._copy = torch.cuda.Stream(device)
-        self._bufs = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(self.depth)]
+        self._bufs = [torch.empty(shape, dtype=dtype, device=device) for _ in range(self.depth)]
         self._ready = [torch.cuda.Event() for _ in range(self.depth)]    # H2D of the slot finished
         self._free = [torch.cuda.Event() for _ in range(self.depth)]     # forward finished reading the slot
         self._done = [torch.cuda.Event() for _ in range(self.depth)]     # logits of the slot are on the host
@@ -51,7 +51,7 @@ class ClipStream:
             nxt = next(it)
         except StopIteration:
             return
-        self._setup(nxt.shape, device)
+        self._setup(nxt.shape, device, nxt.dtype)     # fp32 [B,T,3,H,W] or uint8 [B,T,H,W,3] batches
         main = torch.cuda.current_stream(device)
         self._prefetch(0, nxt, used_before=False)
         i = 0
@@ -63,8 +63,8 @@ class ClipStream:
             except StopIteration:
                 after = None
             if after is not None:
-                if tuple(after.shape) != self._key[0]:
-                    raise ValueError("ClipStream: all batches of one run must have the same shape")
+                if tuple(after.shape) != self._key[0] or after.dtype != self._key[2]:
+                    raise ValueError("ClipStream: all batches of one run must have the same shape and dtype")
                 self._prefetch((i + 1) % self.depth, after, used_before=(i + 1) >= self.depth)
             main.wait_event(self._ready[slot])
             logits = self.model(self._bufs[slot])

@@ -110,6 +110,17 @@ int istvt_conv_stem_fwd(const float* x, const float* wt, const float* bias, void
                         int w, int cout, istvt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Stem on decoded frames: the same convolution reading uint8 NHWC [n, h, w, 3] (the layout video decoders and
+ * the reference's absent `dataset.transform` input, train_CNN.py:18-21,172-173, start from).  The per-channel
+ * input normalisation (x / 255 - mean) / std — xception.py:12-13 documents mean = std = 0.5 — is affine and conv1
+ * has no padding, so the caller folds it into `wt` / `bias` together with the BN scale; the kernel converts bytes.
+ * cuts the host->device copy and the stem's HBM read 4x.
+ * x: uint8 [n, h, w, 3]; wt: fp32 [cout, 3, 3, 3]; bias fp32 [cout]; y: NHWC [n, (h-3)/2+1, (w-3)/2+1, cout].
+ * ------------------------------------------------------------------------------------------- */
+int istvt_conv_stem_u8_fwd(const uint8_t* x, const float* wt, const float* bias, void* y, int dtype, int n, int h,
+                           int w, int cout, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Depthwise 3x3 stride-1 pad-1 convolution, optional ReLU applied to the input on load.
  * Replaces: SeparableConv2d.conv1 (xception.py:43,47) and the ReLU that precedes it inside Block.rep
  * (xception.py:66-67,72-73,82-85).

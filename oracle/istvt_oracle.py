@@ -37,6 +37,19 @@ def _bn(sd: SD, prefix: str, x: torch.Tensor, training: bool = False) -> torch.T
                         sd[prefix + ".bias"], training=training, momentum=BN_MOMENTUM, eps=BN_EPS)
 
 
+def normalise_u8(frames_u8: torch.Tensor, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)) -> torch.Tensor:
+    """Decoded frames uint8 [B, T, H, W, 3] -> the model input fp32 [B, T, 3, H, W].
+
+    Restates the input transform that precedes the model in the reference: `transforms.ToTensor()` (u8 / 255, HWC ->
+    CHW) followed by `transforms.Normalize(mean, std)`.  The transform object itself lives in the absent `dataset`
+    package (train_CNN.py:18-21,172-173); xception.py:12-13 documents mean = std = [0.5, 0.5, 0.5] for this
+    backbone.  The CUDA path folds the same affine map into the stem convolution."""
+    x = frames_u8.to(torch.float32) / 255.0
+    m = torch.tensor(mean, dtype=torch.float32).view(1, 1, 1, 1, 3)
+    s = torch.tensor(std, dtype=torch.float32).view(1, 1, 1, 1, 3)
+    return ((x - m) / s).permute(0, 1, 4, 2, 3).contiguous()
+
+
 def _sep(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
     """SeparableConv2d.forward, xception.py:46-49: depthwise 3x3 pad 1 (groups = C) then pointwise 1x1."""
     x = F.conv2d(x, sd[prefix + ".conv1.weight"], None, 1, 1, 1, groups=x.shape[1])

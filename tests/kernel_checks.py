@@ -204,6 +204,27 @@ def check_conv_stem():
     return out
 
 
+def check_conv_stem_u8():
+    """uint8 NHWC stem (normalisation folded into the weights by the host) vs torch conv on the normalised clip."""
+    ops = _ops()
+    _noTF32()
+    import importlib
+    eng = importlib.import_module("2023-tifs-istvt_b200.engine")
+    out = {}
+    for (n, h, w) in ((2, 300, 300), (1, 299, 299), (3, 7, 9), (1, 8, 6), (2, 5, 5)):   # even / odd row pitch, ragged pairs
+        g = torch.Generator().manual_seed(h * 31 + w)
+        u8 = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8).to(DEV)
+        wt = _rand(32, 3, 3, 3, seed=1) * 0.2
+        b = _rand(32, seed=2) * 0.1
+        mean, std = (0.5, 0.4, 0.45), (0.5, 0.25, 0.3)
+        xn = (u8.float() / 255.0 - torch.tensor(mean, device=DEV)) / torch.tensor(std, device=DEV)
+        ref = F.relu(F.conv2d(xn.permute(0, 3, 1, 2), wt, b, stride=2)).permute(0, 2, 3, 1).contiguous()
+        w2, b2 = eng.fold_input_norm(wt, b, mean, std)
+        out[f"f32_{h}x{w}"] = _assert_close("stem u8 f32", ops.conv_stem_u8(u8, w2, b2, torch.float32), ref, 2e-5)
+        out[f"bf16_{h}x{w}"] = _assert_close("stem u8 bf16", ops.conv_stem_u8(u8, w2, b2, torch.bfloat16), ref, TOL_BF16)
+    return out
+
+
 def check_dwconv():
     ops = _ops()
     _noTF32()
@@ -632,6 +653,7 @@ CHECKS = {
     "gemm_f32": check_gemm_f32,
     "conv3x3": check_conv3x3,
     "conv_stem": check_conv_stem,
+    "conv_stem_u8": check_conv_stem_u8,
     "dwconv": check_dwconv,
     "pool_subsample_tokens": check_pool_subsample_tokens,
     "attn_temporal": check_attn_temporal,

@@ -122,6 +122,47 @@ def run_oracle_case(precision: str, batch: int = 2, seed: int = 99):
     return errs
 
 
+def run_uint8_input_check(batch: int = 2, seed: int = 7):
+    """decoded frames uint8 [B, T, H, W, 3] through `model(x_u8)` (normalisation
+    folded into the stem, 4x fewer H2D bytes) vs the CPU oracle on the normalised fp32 clip, in both precision
+    modes, and vs the CUDA fp32-input path on the same normalised clip."""
+    O = oracle()
+    case = {"seed": 0, "frames": 6, "sensitised": True}
+    model = build_model(case)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(seed)
+    u8 = torch.randint(0, 256, (batch, 6, 300, 300, 3), generator=g, dtype=torch.uint8)
+    mean, std = (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)
+    xn = O.normalise_u8(u8, mean, std)
+    with torch.no_grad():
+        want = O.forward(sd, xn)
+    model = model.cuda()
+    model.input_norm = (mean, std)
+    errs = {}
+    for precision in ("fp32", "bf16"):
+        model.precision = precision
+        got = model(u8.cuda())
+        got_f = model(xn.cuda())
+        torch.cuda.synchronize()
+        errs[f"u8_vs_oracle_{precision}"] = rel_err(got, want)
+        errs[f"u8_vs_float_{precision}"] = rel_err(got, got_f.cpu())
+        assert errs[f"u8_vs_oracle_{precision}"] <= TOL[precision], f"uint8/{precision}: {got.flatten().tolist()} vs {want.flatten().tolist()}"
+        assert errs[f"u8_vs_float_{precision}"] <= TOL[precision]
+        assert torch.equal(got.cpu() > 0, want > 0)
+    # another normalisation re-folds the stem weights
+    model.precision = "fp32"
+    model.input_norm = ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+    with torch.no_grad():
+        want2 = O.forward(sd, O.normalise_u8(u8, *model.input_norm))
+    errs["u8_imagenet_norm_fp32"] = rel_err(model(u8.cuda()), want2)
+    assert errs["u8_imagenet_norm_fp32"] <= TOL["fp32"]
+    # ClipStream with uint8 pinned batches
+    cs = pkg().ClipStream(model)
+    outs = [o.clone() for o in cs.run([u8.pin_memory(), u8.pin_memory()])]
+    assert len(outs) == 2 and rel_err(outs[1], want2) <= TOL["fp32"]
+    return errs
+
+
 def run_api_checks():
     """Boundary behaviour: errors raised up front, state_dict round trip, model_selection."""
     m = pkg()

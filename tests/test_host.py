@@ -69,3 +69,28 @@ def test_bn_folding_matches_torch(model):
         b3 = ep.blocks[2]
         assert b3.skip_w.shape == (728, 256) and b3.seps[1].pw.shape == (728, 728) and b3.seps[0].dw.shape == (3, 3, 256)
         assert b3.start_with_relu and not ep.blocks[0].start_with_relu
+
+
+def test_input_norm_folding_matches_torch(model):
+    """fold_input_norm: conv(w', u8) + b' == conv(w, (u8 / 255 - mean) / std) + b on CPU (the uint8 input stage's
+    host arithmetic; the kernel only converts bytes), checked through the oracle's normalise_u8."""
+    import importlib
+    from helpers import oracle
+    eng = importlib.import_module("2023-tifs-istvt_b200.engine")
+    O = oracle()
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(32, generator=g) * 0.1
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    u8 = torch.randint(0, 256, (1, 2, 21, 23, 3), generator=g, dtype=torch.uint8)
+    want = F.conv2d(O.normalise_u8(u8, mean, std).flatten(0, 1), w, b, stride=2)
+    w2, b2 = eng.fold_input_norm(w, b, mean, std)
+    got = F.conv2d(u8.flatten(0, 1).permute(0, 3, 1, 2).float(), w2, b2, stride=2)
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
+
+
+def test_uint8_clip_validation(model):
+    with pytest.raises(ValueError, match="uint8 clips must be"):
+        model(torch.zeros(1, 6, 3, 300, 300, dtype=torch.uint8))
+    with pytest.raises(ValueError, match="CUDA"):
+        model(torch.zeros(1, 6, 300, 300, 3, dtype=torch.uint8))

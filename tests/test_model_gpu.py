@@ -36,3 +36,8 @@ def test_relevance_pass_against_oracle():
 @pytest.mark.gpu
 def test_cuda_graph_forward():
     model_checks.run_graph_check()
+
+
+@pytest.mark.gpu
+def test_uint8_frames_against_oracle():
+    model_checks.run_uint8_input_check()

@@ -33,6 +33,7 @@ def all_checks():
     checks["train_golden"] = model_checks.run_train_golden
     checks["relevance"] = model_checks.run_relevance_check
     checks["cuda_graph"] = model_checks.run_graph_check
+    checks["uint8_input"] = model_checks.run_uint8_input_check
     return checks
 
 
