@@ -30,6 +30,7 @@ SOURCES = [
     "backward.cu",
     "entry_flow_bwd.cu",
     "entry_flow.cu",
+    "xception_tail.cu",
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -42,8 +42,8 @@ class _SepPack:
 
 @dataclass
 class _BlockPack:
-    skip_w: torch.Tensor
-    skip_b: torch.Tensor
+    skip_w: Optional[torch.Tensor]      # None: identity skip (middle flow)
+    skip_b: Optional[torch.Tensor]
     seps: List[_SepPack]
     start_with_relu: bool
 
@@ -96,9 +96,20 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().float().contiguous()
 
 
+def _pack_sep(sep, bn, dt: torch.dtype) -> _SepPack:
+    s, b = _bn_fold(bn)
+    dw = sep.conv1.weight.detach().float()[:, 0].permute(1, 2, 0).contiguous()            # [C,1,3,3] -> [3,3,C]
+    pw = (sep.pointwise.weight.detach().float().flatten(1) * s[:, None]).to(dt).contiguous()
+    return _SepPack(dw=dw, pw=pw, bias=b.contiguous())
+
+
 def _pack_block(block, dt: torch.dtype) -> _BlockPack:
-    sc, sh = _bn_fold(block.skipbn)
-    skip_w = (block.skip.weight.detach().float().flatten(1) * sc[:, None]).to(dt).contiguous()
+    if block.skip is None:      # middle-flow block: identity skip (xception.py:97-98)
+        skip_w = skip_b = None
+    else:
+        sc, sh = _bn_fold(block.skipbn)
+        skip_w = (block.skip.weight.detach().float().flatten(1) * sc[:, None]).to(dt).contiguous()
+        skip_b = sh.contiguous()
     seps = []
     mods = list(block.rep)
     for i, m in enumerate(mods):
@@ -108,7 +119,7 @@ def _pack_block(block, dt: torch.dtype) -> _BlockPack:
             dw = m.conv1.weight.detach().float()[:, 0].permute(1, 2, 0).contiguous()      # [C,1,3,3] -> [3,3,C]
             pw = (m.pointwise.weight.detach().float().flatten(1) * s[:, None]).to(dt).contiguous()
             seps.append(_SepPack(dw=dw, pw=pw, bias=b.contiguous()))
-    return _BlockPack(skip_w=skip_w, skip_b=sh.contiguous(), seps=seps, start_with_relu=block.start_with_relu)
+    return _BlockPack(skip_w=skip_w, skip_b=skip_b, seps=seps, start_with_relu=block.start_with_relu)
 
 
 def pack_entry(xcep, dt: torch.dtype) -> _EntryPack:
@@ -208,6 +219,110 @@ def run_entry_flow(ep: _EntryPack, frames: torch.Tensor, dt: torch.dtype, taps: 
         if taps is not None:
             taps[f"block{bi + 1}"] = a
     return _run_block(ep.blocks[2], a, taps, "block3")
+
+
+# ------------------------------------------------------------------------------------------------
+# the per-frame Xception baseline: entry flow + middle flow + exit flow + logits
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class _XceptionPack:
+    entry: _EntryPack
+    middle: List[_BlockPack]       # blocks 4-11
+    block12: _BlockPack
+    conv3: _SepPack
+    conv4: _SepPack
+    fc_w: torch.Tensor
+    fc_b: torch.Tensor
+    fingerprint: tuple = field(default_factory=tuple)
+
+
+def _xception_fingerprint(xcep) -> tuple:
+    return tuple((t.data_ptr(), t._version) for t in list(xcep.parameters()) + list(xcep.buffers()))
+
+
+def pack_xception(xcep, dt: torch.dtype) -> _XceptionPack:
+    fc = xcep.last_linear[-1] if isinstance(xcep.last_linear, torch.nn.Sequential) else xcep.last_linear
+    return _XceptionPack(
+        entry=pack_entry(xcep, dt),
+        middle=[_pack_block(getattr(xcep, f"block{i}"), dt) for i in range(4, 12)],
+        block12=_pack_block(xcep.block12, dt),
+        conv3=_pack_sep(xcep.conv3, xcep.bn3, dt), conv4=_pack_sep(xcep.conv4, xcep.bn4, dt),
+        fc_w=_f32(fc.weight), fc_b=_f32(fc.bias), fingerprint=_xception_fingerprint(xcep))
+
+
+def _run_identity_block(bp: _BlockPack, x: torch.Tensor) -> torch.Tensor:
+    """Middle-flow Block (728 -> 728, 3 separable convs, stride 1, xception.py:130-138): rep(inp) + inp.  The leading
+    ReLU is out of place (xception.py:82-85), so the residual adds the un-rectified block input."""
+    n, h, w, _ = x.shape
+    y = x
+    for i, sp in enumerate(bp.seps):
+        d = ops.dwconv3x3(y, sp.dw, relu_in=(bp.start_with_relu and i == 0))
+        last = i == len(bp.seps) - 1
+        y = ops.gemm(d, sp.pw, bias=sp.bias, act=ops.ACT_NONE if last else ops.ACT_RELU).view(n, h, w, -1)
+    return ops.add(y, x)
+
+
+def xception_features(xp: _XceptionPack, frames: torch.Tensor, dt: torch.dtype, input_norm=None,
+                      taps: Optional[dict] = None) -> torch.Tensor:
+    """Xception.features, xception.py:161-191: frames (fp32 NCHW or uint8 NHWC) -> NHWC [n, 10, 10, 2048] (bn4 output,
+    before the ReLU of `logits`)."""
+    body, skip = run_entry_flow(xp.entry, frames, dt, taps, input_norm)
+    a = ops.pool_add(body, skip)                                                        # block3 output
+    if taps is not None:
+        taps["block3"] = a
+    for i, bp in enumerate(xp.middle):
+        a = _run_identity_block(bp, a)                                                  # blocks 4-11
+        if taps is not None and i in (0, 7):
+            taps[f"block{i + 4}"] = a
+    body, skip = _run_block(xp.block12, a, None, "block12")
+    a = ops.pool_add(body, skip)                                                        # 19x19 -> 10x10, 1024 ch
+    if taps is not None:
+        taps["block12"] = a
+    n, h, w, _ = a.shape
+    d = ops.dwconv3x3(a, xp.conv3.dw, relu_in=False)
+    a = ops.gemm(d, xp.conv3.pw, bias=xp.conv3.bias, act=ops.ACT_RELU).view(n, h, w, -1)          # conv3+bn3+relu
+    d = ops.dwconv3x3(a, xp.conv4.dw, relu_in=False)
+    return ops.gemm(d, xp.conv4.pw, bias=xp.conv4.bias, act=ops.ACT_NONE).view(n, h, w, -1)       # conv4+bn4
+
+
+class XceptionEngine:
+    """Weight-pack cache + schedule of the per-frame Xception forward (`TransferModel('xception')`)."""
+
+    def __init__(self):
+        self._packs: Dict[Tuple[str, str], _XceptionPack] = {}
+
+    def pack(self, xcep, dev: torch.device, precision: str) -> _XceptionPack:
+        key = (str(dev), precision)
+        pk = self._packs.get(key)
+        fp = _xception_fingerprint(xcep)
+        if pk is None or pk.fingerprint != fp:
+            pk = pack_xception(xcep, PRECISIONS[precision])
+            self._packs[key] = pk
+        return pk
+
+    @torch.no_grad()
+    def forward(self, xcep, x: torch.Tensor, precision: str = "bf16", taps: Optional[dict] = None,
+                features_only: bool = False) -> torch.Tensor:
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        if xcep.training:
+            raise NotImplementedError("istvt_b200: the per-frame Xception baseline is an inference path (model.eval())")
+        is_u8 = isinstance(x, torch.Tensor) and x.dtype == torch.uint8
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or (x.shape[3] if is_u8 else x.shape[1]) != 3:
+            raise ValueError("Xception expects frames [N, 3, H, W] (fp32) or decoded frames [N, H, W, 3] (uint8)")
+        if not x.is_cuda:
+            raise ValueError("Xception (istvt_b200) runs on CUDA tensors only: there is no CPU fallback by design")
+        hh, ww = (x.shape[1], x.shape[2]) if is_u8 else (x.shape[2], x.shape[3])
+        if min(hh, ww) < 71:
+            raise ValueError(f"input {hh}x{ww} is too small for the Xception strides")
+        dt = PRECISIONS[precision]
+        xp = self.pack(xcep, x.device, precision)
+        frames = x.contiguous() if is_u8 else x.float().contiguous()
+        norm = getattr(xcep, "input_norm", ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))) if is_u8 else None
+        feats = xception_features(xp, frames, dt, norm, taps)
+        if features_only:
+            return feats
+        return ops.pool_linear(feats, xp.fc_w, xp.fc_b, relu=True)                     # logits, xception.py:208-221
 
 
 def entry_flow_features(xcep, x: torch.Tensor, precision: str = "fp32") -> torch.Tensor:

@@ -2,8 +2,9 @@
 
 Mirrors the attribute names of the reference's `network/xception.py` (`Xception` :104-149, `Block` :52-101,
 `SeparableConv2d` :39-49) so that checkpoints written by the reference load with `strict=True` (the key
-list is SURVEY.md Appendix A).  Only the entry flow (`low_level_features`, reference :193-206) is on the
-ISTVT path; blocks 4-12 / conv3 / conv4 / last_linear are kept as inert parameters.
+list is SURVEY.md Appendix A).  The entry flow (`low_level_features`, reference :193-206) is on the
+ISTVT path; the whole backbone (`features` / `logits` / `forward`, reference :161-226) serves the per-frame
+'xception' baseline of the same evaluation script (train_CNN.py:924-929) on the same kernels, inference only.
 
 The arithmetic lives in the CUDA library (see `engine.py`); nothing here computes with torch ops.
 """
@@ -88,7 +89,34 @@ class Xception(nn.Module):
         from ..engine import entry_flow_features
         return entry_flow_features(self, x)
 
-    def features(self, x):  # pragma: no cover - out of scope
-        raise NotImplementedError("Xception middle/exit flow is outside the ISTVT hot path (SURVEY.md §8f rank 2)")
+    # ---- the per-frame baseline: whole backbone ----
+    precision = "bf16"
+    input_norm = ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))      # used for uint8 [N, H, W, 3] inputs only
 
-    forward = features
+    def _xengine(self):
+        from ..engine import XceptionEngine
+        eng = self.__dict__.get("_xeng")
+        if eng is None:
+            eng = XceptionEngine()
+            self.__dict__["_xeng"] = eng
+        return eng
+
+    def features(self, x: torch.Tensor) -> torch.Tensor:
+        """reference :161-191 — fp32 NCHW [n, 2048, h', w'] (bn4 output), for parity with the reference layout."""
+        feats = self._xengine().forward(self, x, precision=self.precision, features_only=True)
+        return feats.float().permute(0, 3, 1, 2)
+
+    def logits(self, features: torch.Tensor) -> torch.Tensor:
+        """reference :208-221 on an NCHW feature tensor: ReLU, global average pool, last_linear."""
+        from .. import ops
+        fc = self.last_linear[-1] if isinstance(self.last_linear, nn.Sequential) else self.last_linear
+        x = features.permute(0, 2, 3, 1).contiguous()
+        return ops.pool_linear(x, fc.weight.detach().float().contiguous(), fc.bias.detach().float().contiguous())
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """reference :223-226 — frames [N, 3, H, W] fp32 (or uint8 [N, H, W, 3]) on CUDA -> logits fp32 [N, classes]."""
+        return self._xengine().forward(self, x, precision=self.precision)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_xeng", None)
+        return super()._apply(fn, *args, **kwargs)

@@ -233,6 +233,30 @@ def conv_stem_u8(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out_dtype
     return y
 
 
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a + b (same shape / dtype, numel % 8 == 0): identity-skip residual of the Xception middle-flow blocks."""
+    dev = _chk(a, b)
+    if a.shape != b.shape or a.dtype != b.dtype or a.numel() % 8:
+        raise ValueError("add: operands must have the same shape and dtype, numel % 8 == 0")
+    y = torch.empty_like(a)
+    with _launch(dev, "add", 0.0, _nbytes(a, b, y)):
+        _lib.check(_lib.lib().istvt_add_fwd(_ptr(a), _ptr(b), _ptr(y), _dt(a), a.numel(), _stream(dev)), "istvt_add_fwd")
+    return y
+
+
+def pool_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = True) -> torch.Tensor:
+    """x: NHWC [n, h, w, c] -> fp32 [n, ncls] = Linear(mean_hw(relu(x))) (Xception.logits, xception.py:208-221)."""
+    dev = _chk(x, w, bias)
+    n, h, wd, c = x.shape
+    if w.dtype != torch.float32 or w.dim() != 2 or w.shape[1] != c:
+        raise ValueError("pool_linear: weight must be fp32 [ncls, c]")
+    out = torch.empty(n, w.shape[0], dtype=torch.float32, device=dev)
+    with _launch(dev, "pool_linear", 2.0 * n * c * w.shape[0], _nbytes(x)):
+        _lib.check(_lib.lib().istvt_pool_linear_fwd(_ptr(x), _dt(x), _ptr(w), _ptr(bias), _ptr(out), n, h * wd, c,
+                                                    w.shape[0], int(relu), _stream(dev)), "istvt_pool_linear_fwd")
+    return out
+
+
 def dwconv3x3(x: torch.Tensor, w: torch.Tensor, relu_in: bool) -> torch.Tensor:
     """x: NHWC; w: fp32 [3, 3, c]."""
     dev = _chk(x, w)

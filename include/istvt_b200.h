@@ -187,6 +187,21 @@ int istvt_attn_spatial_fwd(const void* qkv, void* out, float* probs, int dtype, 
                            int heads, float scale, istvt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Per-frame Xception baseline (model_selection('xception'), train_CNN.py:924-929).
+ * The middle flow (blocks 4-11), block 12 and conv3 / conv4 reuse istvt_dwconv3x3_fwd, istvt_gemm_fwd (1x1 + folded
+ * BN + ReLU), istvt_subsample2_fwd and istvt_pool_add_fwd; these two entries are the only additions.
+ *
+ * istvt_add_fwd: y = a + b elementwise (count % 8 == 0) — the identity-skip residual `x += inp` of a Block without
+ * skip convolution, xception.py:92-101.
+ * istvt_pool_linear_fwd: logits, xception.py:208-221 — ReLU, adaptive_avg_pool2d(1, 1), last_linear (Dropout is
+ * the identity in eval mode).  x: NHWC [n, hw, c] (dtype); w: fp32 [ncls, c]; bias fp32 [ncls] or NULL;
+ * out: fp32 [n, ncls].
+ * ------------------------------------------------------------------------------------------- */
+int istvt_add_fwd(const void* a, const void* b, void* y, int dtype, int64_t count, istvt_stream_t stream);
+int istvt_pool_linear_fwd(const void* x, int dtype, const float* w, const float* bias, float* out, int n, int hw,
+                          int c, int ncls, int relu, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Classification head on token (0, 0) of every clip: final transformer LayerNorm (row-wise, so only
  * that row is needed), mlp_head LayerNorm, Linear(dim -> 1).
  * Replaces: vivit.py:101 (restricted to the rows read afterwards), vivit.py:144-148.

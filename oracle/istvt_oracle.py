@@ -91,6 +91,79 @@ def entry_flow(sd: SD, frames: torch.Tensor, taps: Optional[dict] = None, prefix
     return x
 
 
+# ------------------------------------------------------------------------------------------------
+# per-frame Xception baseline (model_selection('xception'), train_CNN.py:924-929): middle + exit flow + logits
+# ------------------------------------------------------------------------------------------------
+def _block_general(sd: SD, prefix: str, inp: torch.Tensor, reps: int, stride: int) -> torch.Tensor:
+    """Block.forward, xception.py:91-101, for the start_with_relu=True blocks 4-12 (eval mode).
+
+    rep = (ReLU Sep BN) x reps [+ MaxPool(3, stride, 1)] (xception.py:66-89; where the channel growth sits —
+    grow_first — only changes the weight shapes, which the state_dict carries).  The first ReLU is out of place
+    (xception.py:82-85): the skip path sees the un-rectified input.  Identity skip when there is no skip conv
+    (xception.py:97-98)."""
+    x = inp
+    for r in range(reps):
+        x = F.relu(x)
+        x = _bn(sd, f"{prefix}.rep.{3 * r + 2}", _sep(sd, f"{prefix}.rep.{3 * r + 1}", x))
+    if stride != 1:
+        x = F.max_pool2d(x, 3, stride, 1)
+    if f"{prefix}.skip.weight" in sd:
+        skip = _bn(sd, f"{prefix}.skipbn", F.conv2d(inp, sd[f"{prefix}.skip.weight"], None, stride))
+    else:
+        skip = inp
+    return x + skip
+
+
+def xception_features(sd: SD, frames: torch.Tensor, prefix: str = "model", taps: Optional[dict] = None) -> torch.Tensor:
+    """Xception.features, xception.py:161-191.  frames [n,3,H,W] -> [n,2048,h',w'] (bn4 output)."""
+    x = entry_flow(sd, frames, taps, prefix=prefix)                       # :162-172
+    for i in range(4, 12):                                                 # :173-180, Block(728,728,3,1) :130-138
+        x = _block_general(sd, f"{prefix}.block{i}", x, reps=3, stride=1)
+        if taps is not None and i in (4, 11):
+            taps[f"block{i}"] = x
+    x = _block_general(sd, f"{prefix}.block12", x, reps=2, stride=2)       # :181, Block(728,1024,2,2,grow_first=False) :140
+    if taps is not None:
+        taps["block12"] = x
+    x = F.relu(_bn(sd, f"{prefix}.bn3", _sep(sd, f"{prefix}.conv3", x)))    # :183-185
+    x = _bn(sd, f"{prefix}.bn4", _sep(sd, f"{prefix}.conv4", x))            # :187-188
+    if taps is not None:
+        taps["features"] = x
+    return x
+
+
+def xception_forward(sd: SD, frames: torch.Tensor, prefix: str = "model", taps: Optional[dict] = None) -> torch.Tensor:
+    """Xception.forward, xception.py:217-220 = features + logits (:208-215: ReLU, adaptive_avg_pool2d(1,1), flatten,
+    last_linear = Sequential(Dropout, Linear(2048, classes)) from TransferModel, models_copy.py:40-45; eval mode)."""
+    x = F.relu(xception_features(sd, frames, prefix, taps))
+    x = F.adaptive_avg_pool2d(x, (1, 1)).flatten(1)
+    key = f"{prefix}.last_linear.1" if f"{prefix}.last_linear.1.weight" in sd else f"{prefix}.last_linear"
+    return F.linear(x, sd[key + ".weight"], sd[key + ".bias"])
+
+
+def sensitise_xception_(sd: SD, prefix: str = "model", seed: int = 4321, gain: float = 1.85) -> SD:
+    """In place, deterministic: default init shrinks the signal by ~1/sqrt(3) per convolution (kaiming_uniform with
+    a = sqrt(5)), which would leave the logits of the 36-convolution backbone equal to the classifier bias.  Scale
+    every convolution by `gain` and randomise every BatchNorm (gamma, beta, running statistics) so that an error in
+    any block reaches the logits."""
+    g = torch.Generator().manual_seed(seed)
+    rnd = lambda shape: torch.rand(shape, generator=g)
+    for k in sorted(sd.keys()):
+        if not k.startswith(prefix + "."):
+            continue
+        v = sd[k]
+        if k.endswith("running_mean"):
+            v.copy_((rnd(v.shape) - 0.5) * 0.2)
+        elif k.endswith("running_var"):
+            v.copy_(0.5 + rnd(v.shape))
+        elif v.dim() == 4:
+            v.mul_(gain)
+        elif v.dim() == 1 and k.endswith(".weight") and k[: -len(".weight")] + ".running_mean" in sd:
+            v.copy_(0.7 + 0.6 * rnd(v.shape))
+        elif v.dim() == 1 and k.endswith(".bias") and k[: -len(".bias")] + ".running_mean" in sd:
+            v.copy_((rnd(v.shape) - 0.5) * 0.2)
+    return sd
+
+
 def build_tokens(sd: SD, feats: torch.Tensor, prefix: str = "vit") -> torch.Tensor:
     """DSTTr.forward up to the transformer, vivit.py:133-142.  feats [B,T,C,h,w] -> [B,(T+1)*362,C]."""
     b, t, c, h, w = feats.shape

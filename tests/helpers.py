@@ -13,6 +13,7 @@ if ROOT not in sys.path:
 
 PKG_NAME = "2023-tifs-istvt_b200"
 GOLDEN = os.path.join(ROOT, "tests", "golden", "istvt_golden.pt")
+GOLDEN_XCEPTION = os.path.join(ROOT, "tests", "golden", "xception_golden.pt")
 
 
 def pkg():
@@ -74,3 +75,23 @@ def rel_err(got: torch.Tensor, want: torch.Tensor) -> float:
     got = got.detach().double().cpu()
     want = want.detach().double().cpu()
     return ((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+
+def make_frames(n: int, side: int, seed: int = 77) -> torch.Tensor:
+    """Same recipe as oracle/make_golden_xception.py::make_frames."""
+    g = torch.Generator().manual_seed(seed + side)
+    x = torch.rand(n, 3, side, side, generator=g)
+    x[1::2] = 2 * x[1::2] - 1
+    return x
+
+
+def build_xception(seed: int = 0):
+    """The per-frame baseline `model_selection('xception', 2)` with the golden fixture's weights: seeded construction
+    (the Xception tree is the first thing the reference's XceptionVidTr() draws, so the same seed gives the same
+    values) + the deterministic `sensitise_xception_`."""
+    torch.manual_seed(seed)
+    model = pkg().model_selection("xception", num_out_classes=2, dropout=0.5)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    oracle().sensitise_xception_(sd, "model")
+    model.load_state_dict(sd)
+    return model.eval()

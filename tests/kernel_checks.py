@@ -225,6 +225,26 @@ def check_conv_stem_u8():
     return out
 
 
+def check_xception_tail():
+    ops = _ops()
+    _noTF32()
+    out = {}
+    for dt, tol in ((torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)):
+        a = _rand(3, 19, 19, 728, seed=1).to(dt)
+        b = _rand(3, 19, 19, 728, seed=2).to(dt)
+        out[f"add_{dt}"] = _assert_close("add", ops.add(a, b), a.float() + b.float(), tol)
+        x = _rand(5, 10, 10, 2048, seed=3).to(dt)
+        w = _rand(2, 2048, seed=4) * 0.05
+        bias = _rand(2, seed=5)
+        ref = F.linear(F.relu(x.float()).mean(dim=(1, 2)), w, bias)
+        out[f"pool_linear_{dt}"] = _assert_close("pool_linear", ops.pool_linear(x, w, bias), ref, 1e-5 if dt == torch.float32 else 2e-3)
+        x = _rand(2, 3, 7, 24, seed=6).to(dt)
+        w = _rand(5, 24, seed=7)
+        ref = F.linear(x.float().mean(dim=(1, 2)), w, None)
+        out[f"pool_linear_norelu_{dt}"] = _assert_close("pool_linear", ops.pool_linear(x, w, None, relu=False), ref, 1e-5 if dt == torch.float32 else 2e-3)
+    return out
+
+
 def check_dwconv():
     ops = _ops()
     _noTF32()
@@ -654,6 +674,7 @@ CHECKS = {
     "conv3x3": check_conv3x3,
     "conv_stem": check_conv_stem,
     "conv_stem_u8": check_conv_stem_u8,
+    "xception_tail": check_xception_tail,
     "dwconv": check_dwconv,
     "pool_subsample_tokens": check_pool_subsample_tokens,
     "attn_temporal": check_attn_temporal,

@@ -8,7 +8,8 @@ from __future__ import annotations
 
 import torch
 
-from helpers import GOLDEN, build_model, fingerprint_check, make_input, oracle, pkg, rel_err
+from helpers import (GOLDEN, GOLDEN_XCEPTION, build_model, build_xception, fingerprint_check, make_frames, make_input,
+                     oracle, pkg, rel_err)
 
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
 
@@ -160,6 +161,50 @@ def run_uint8_input_check(batch: int = 2, seed: int = 7):
     cs = pkg().ClipStream(model)
     outs = [o.clone() for o in cs.run([u8.pin_memory(), u8.pin_memory()])]
     assert len(outs) == 2 and rel_err(outs[1], want2) <= TOL["fp32"]
+    return errs
+
+
+def run_xception_golden(precision: str):
+    """the per-frame Xception baseline (`model_selection('xception', 2)`, whole backbone
+    on the entry flow's kernels) vs the golden vectors of the UNMODIFIED reference, block taps + logits, and uint8
+    frames through the same model."""
+    g = torch.load(GOLDEN_XCEPTION, weights_only=False)
+    model = build_xception(g["seed"])
+    sd = model.state_dict()
+    for k, want in g["weights"].items():
+        fingerprint_check(f"weights[{k}]", sd[k], want, 0.0)
+    model = model.cuda()
+    xc = model.model
+    xc.precision = precision
+    tol = TOL[precision]
+    errs = {}
+    nhwc = lambda a: a.float().permute(0, 3, 1, 2)
+    for name, case in g["cases"].items():
+        x = make_frames(case["n"], case["side"]).cuda()
+        taps = {}
+        logits = xc._xengine().forward(xc, x, precision=precision, taps=taps)
+        feats = xc._xengine().forward(xc, x, precision=precision, features_only=True)
+        torch.cuda.synchronize()
+        taps["features"] = feats
+        inf = float("inf")
+        for k, want in case["taps"].items():
+            errs[f"{name}.{k}"] = fingerprint_check(f"xception/{name}/{precision}/{k}", nhwc(taps[k]), want, inf)
+        errs[f"{name}.logits"] = rel_err(logits, case["logits"])
+        errs[f"{name}.api"] = rel_err(model(x), case["logits"])          # TransferModel.forward, the call the script makes
+        bad = {k: v for k, v in errs.items() if not v <= tol}
+        assert not bad, f"xception/{precision}: over tolerance {tol:.0e}: {bad}; all: {errs}"
+        assert torch.equal(logits.argmax(1).cpu(), case["logits"].argmax(1)), "predictions differ"
+    # features()/logits() in the reference's NCHW layout compose to forward()
+    x = make_frames(1, 300).cuda()
+    assert rel_err(xc.logits(xc.features(x)), model(x)) <= tol
+    # decoded uint8 frames: normalisation folded into the stem
+    O = oracle()
+    u8 = torch.randint(0, 256, (2, 300, 300, 3), generator=torch.Generator().manual_seed(3), dtype=torch.uint8)
+    xn = O.normalise_u8(u8.unsqueeze(0))[0]
+    with torch.no_grad():
+        want = O.xception_forward({k: v.cpu() for k, v in model.state_dict().items()}, xn, "model")
+    errs["uint8"] = rel_err(model(u8.cuda()), want)
+    assert errs["uint8"] <= tol, f"xception uint8 {errs['uint8']:.3e}"
     return errs
 
 

@@ -41,3 +41,9 @@ def test_cuda_graph_forward():
 @pytest.mark.gpu
 def test_uint8_frames_against_oracle():
     model_checks.run_uint8_input_check()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_xception_baseline_against_reference_golden(precision):
+    model_checks.run_xception_golden(precision)

@@ -10,7 +10,7 @@ import os
 import pytest
 import torch
 
-from helpers import GOLDEN, build_model, fingerprint_check, make_input, oracle
+from helpers import GOLDEN, GOLDEN_XCEPTION, build_model, build_xception, fingerprint_check, make_frames, make_input, oracle
 
 TIGHT = 2e-6   # fp32 CPU vs fp32 CPU: the only freedom is thread-count dependent summation order
 
@@ -132,3 +132,22 @@ def test_oracle_training_step_against_reference_golden():
         p = before[k].clone()
         O.adamw_update(p, gr, torch.zeros_like(p), torch.zeros_like(p), 1, g["lr"], weight_decay=g["weight_decay"])
         assert fp_err(p, g["params_after"][k]) <= 1e-5, k
+
+
+@pytest.mark.parametrize("name", ["b2_300", "b1_299"])
+def test_xception_oracle_matches_reference_golden(name):
+    """Per-frame Xception baseline: the oracle's xception_forward vs the golden vectors
+    oracle/make_golden_xception.py recorded from the UNMODIFIED reference TransferModel('xception')."""
+    O = oracle()
+    g = torch.load(GOLDEN_XCEPTION, weights_only=False)
+    case = g["cases"][name]
+    model = build_xception(g["seed"])
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    for k, want in g["weights"].items():
+        fingerprint_check(f"weights[{k}]", sd[k], want, 0.0)
+    taps = {}
+    with torch.no_grad():
+        logits = O.xception_forward(sd, make_frames(case["n"], case["side"]), "model", taps)
+    assert torch.allclose(logits, case["logits"], rtol=0, atol=TIGHT * max(1.0, case["logits"].abs().max().item()))
+    for key, want in case["taps"].items():
+        fingerprint_check(f"xception/{name}/{key}", taps[key], want, TIGHT)
