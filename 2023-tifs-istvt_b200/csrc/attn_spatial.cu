@@ -14,6 +14,8 @@
 #include "ptx.cuh"
 #include "simt_util.cuh"
 
+#include <stdlib.h>
+
 namespace istvt {
 
 constexpr int SA_DH = 64;
@@ -552,6 +554,317 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------------
+// bf16 production kernel, second generation: the pipelined kernel above with the 16 softmax warps split into
+// TWO GROUPS THAT ALTERNATE TILES (ping-pong).  ncu of the single-group version (profiles/README.md r1o/r1p) showed
+// the softmax warps as the critical path at ~8 100 clk per query tile against a MUFU floor of 3 072 (128 x 384
+// ex2 at 16 / clk / SM): max pass, CTA-wide barriers, the exp pass and the O epilogue ran back to back in every
+// warp, so the XU pipe idled 60 % of the time.  Here group g owns tiles t = g (mod 2): while it runs the exp pass of
+// tile t, the other group is already in the max pass of tile t+1 on the S chunks the tensor core re-filled behind
+// it (S(t+1).c is issued as soon as P(t).c has been consumed by PV(t).c), and its own O epilogue of tile t-2 falls
+// into the wait for S(t).  Each group has its own O accumulator (tile parity), its own named barrier and its own
+// s_full / p_full barrier sets (a waiter must not skip mbarrier phases, so the sets are indexed by tile parity).
+// Thread = (query row, 64-key half of every chunk), processed as two 32-key sub-blocks in the P layout the MMA
+// issuer already uses.
+// ------------------------------------------------------------------------------------------
+constexpr int PP_GROUP_WARPS = 8;
+constexpr int PP_THREADS = 128 + 32 * 2 * PP_GROUP_WARPS;          // 640
+constexpr int PP_SMEM = SP_MISC_OFF + 1024 /*align*/ + 256 /*barriers*/ + 2 * 2 * 2 * 128 * 4 /*[max,sum][group][half][row]*/;
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ lse, int tokens, int heads, int items, float scale_log2) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_q = smem + SP_Q_OFF;
+    uint8_t* s_k = smem + SP_K_OFF;
+    uint8_t* s_v = smem + SP_V_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_MISC_OFF);
+    uint64_t* q_full = bars;            // [4]
+    uint64_t* q_empty = bars + 4;       // [4]
+    uint64_t* k_full = bars + 8;        // [2]
+    uint64_t* k_empty = bars + 10;      // [2]
+    uint64_t* v_full = bars + 12;
+    uint64_t* v_empty = bars + 13;
+    uint64_t* s_full = bars + 14;       // [2 tile parities][3] S chunk c of tile t is in TMEM
+    uint64_t* p_full = bars + 20;       // [2][3] P chunk c of tile t written by all 8 warps of group t & 1
+    uint64_t* o_full = bars + 26;       // [2]
+    uint64_t* o_empty = bars + 28;      // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 30);
+    float* s_max = reinterpret_cast<float*>(smem + SP_MISC_OFF + 256);   // [2 groups][2 halves][128]
+    float* s_sum = s_max + 2 * 2 * 128;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int inner = heads * SA_DH;
+    const int q_tiles = (tokens + SA_BM - 1) / SA_BM;
+    const int k_chunks = q_tiles;
+    const int my_items = (items > static_cast<int>(blockIdx.x))
+                             ? (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                   static_cast<int>(gridDim.x)
+                             : 0;
+    const int n_tiles = my_items * q_tiles;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_qkv);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(q_full + i, 1); mbar_init(q_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
+            mbar_init(o_full + i, 1); mbar_init(o_empty + i, PP_GROUP_WARPS);
+        }
+        mbar_init(v_full, 1); mbar_init(v_empty, 1);
+        for (int i = 0; i < 6; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, PP_GROUP_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_holder, SA_TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t tmem_s = tmem_base;
+    const uint32_t tmem_o = tmem_base + SA_KMAX;    // + 64 * (tile parity)
+
+    if (warp == 0) {
+        // ================= TMA producer (unchanged) =================
+        if (lane == 0) {
+            for (int n = 0; n < my_items; ++n) {
+                const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+                const int h = item % heads;
+                const int bf = item / heads;
+                const int kb = n & 1;
+                mbar_wait_sleep(k_empty + kb, ((n >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(k_full + kb, k_chunks * SP_CHUNK_BYTES);
+                for (int c = 0; c < k_chunks; ++c)
+                    tma_load_3d(s_k + kb * SA_KV_BYTES + c * SP_CHUNK_BYTES, &tm_qkv, k_full + kb, inner + h * SA_DH,
+                                c * 128, bf);
+                for (int qt = 0; qt < q_tiles; ++qt) {
+                    const int t = n * q_tiles + qt;
+                    const int slot = t & 3;
+                    mbar_wait_sleep(q_empty + slot, ((t >> 2) & 1) ^ 1);
+                    mbar_arrive_expect_tx(q_full + slot, SP_CHUNK_BYTES);
+                    tma_load_3d(s_q + slot * SP_CHUNK_BYTES, &tm_qkv, q_full + slot, h * SA_DH, qt * SA_BM, bf);
+                }
+                mbar_wait_sleep(v_empty, (n & 1) ^ 1);
+                mbar_arrive_expect_tx(v_full, k_chunks * SP_CHUNK_BYTES);
+                for (int c = 0; c < k_chunks; ++c)
+                    tma_load_3d(s_v + c * SP_CHUNK_BYTES, &tm_qkv, v_full, 2 * inner + h * SA_DH, c * 128, bf);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer: same interleave, barrier sets indexed by tile parity =================
+        if (elect_one()) {
+            const uint32_t idesc_s = make_idesc_bf16(SA_BM, 128, 0, 0);
+            const uint32_t idesc_pv = make_idesc_bf16(SA_BM, SA_DH, 0, 1);   // B (= V) is MN-major
+            const uint64_t desc_kmaj = make_smem_desc(0, 0, 1024, SWZ_128B);
+            const uint64_t desc_v = make_smem_desc(smem_u32(s_v), 64 * 128, 1024, SWZ_128B);
+            const uint32_t q_field = (smem_u32(s_q) & 0x3FFFFu) >> 4;
+            const uint32_t k_field = (smem_u32(s_k) & 0x3FFFFu) >> 4;
+            const int last_ksteps = (tokens - (k_chunks - 1) * 128 + 15) / 16;
+            int qt = 0, n = 0;          // tile t = n * q_tiles + qt
+            int qp = 0, np = 0;         // tile t - 1
+            for (int t = 0; t <= n_tiles; ++t) {
+                const int slot = t & 3;
+                const int kb = n & 1;
+                const int tp = t - 1;
+                const int ob = tp & 1;
+                const uint64_t q_desc = desc_kmaj | (q_field + slot * (SP_CHUNK_BYTES >> 4));
+                const uint64_t k_desc = desc_kmaj | (k_field + kb * (SA_KV_BYTES >> 4));
+                const uint32_t d_o = tmem_o + ob * SA_DH;
+                for (int c = 0; c < k_chunks; ++c) {
+                    if (t > 0) {
+                        // ---- O(t-1) += P(t-1).c V.c ----
+                        if (c == 0) {
+                            if (qp == 0) mbar_wait(v_full, np & 1);
+                            mbar_wait(o_empty + ob, ((tp >> 1) & 1) ^ 1);
+                        }
+                        mbar_wait_hot(p_full + ob * 3 + c, (tp >> 1) & 1);
+                        tc_fence_after();
+                        const uint32_t a0 = tmem_s + c * 128;
+                        const uint64_t b0 = desc_v + static_cast<uint64_t>(c * 8 * (16 * 128 >> 4));
+                        if (c != k_chunks - 1) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                umma_f16_ts(d_o, a0 + (j >> 1) * 32 + (j & 1) * 8, b0 + j * (16 * 128 >> 4), idesc_pv,
+                                            (c | j) != 0 ? 1u : 0u);
+                        } else {
+                            for (int j = 0; j < last_ksteps; ++j)
+                                umma_f16_ts(d_o, a0 + (j >> 1) * 32 + (j & 1) * 8, b0 + j * (16 * 128 >> 4), idesc_pv,
+                                            (c | j) != 0 ? 1u : 0u);
+                            umma_commit(o_full + ob);
+                            if (qp == q_tiles - 1) umma_commit(v_empty);
+                        }
+                    }
+                    if (t < n_tiles) {
+                        // ---- S(t).c = Q(t) K.c^T ----
+                        if (c == 0) {
+                            mbar_wait_hot(q_full + slot, (t >> 2) & 1);
+                            if (qt == 0) mbar_wait_hot(k_full + kb, (n >> 1) & 1);
+                            tc_fence_after();
+                        }
+                        const uint64_t kc = k_desc + static_cast<uint64_t>(c * (SP_CHUNK_BYTES >> 4));
+                        umma_f16_ss(tmem_s + c * 128, q_desc, kc, idesc_s, 0u);
+                        umma_f16_ss(tmem_s + c * 128, q_desc + 2, kc + 2, idesc_s, 1u);
+                        umma_f16_ss(tmem_s + c * 128, q_desc + 4, kc + 4, idesc_s, 1u);
+                        umma_f16_ss(tmem_s + c * 128, q_desc + 6, kc + 6, idesc_s, 1u);
+                        umma_commit(s_full + (t & 1) * 3 + c);
+                        if (c == k_chunks - 1) {
+                            umma_commit(q_empty + slot);
+                            if (qt == q_tiles - 1) umma_commit(k_empty + kb);
+                        }
+                    }
+                }
+                qp = qt; np = n;
+                if (++qt == q_tiles) { qt = 0; ++n; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ================= softmax + epilogue, two groups alternating tiles =================
+        const int sw = warp - 4;
+        const int g = sw >> 3;                             // group = tile parity
+        const int quad = warp & 3;                         // TMEM lane quadrant of this warp
+        const int half = (sw >> 2) & 1;                    // 64-key half of every 128-key chunk
+        const int row = quad * 32 + lane;                  // row inside the q tile == TMEM lane
+        const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t t_row = tmem_s + lane_base + half * 64;   // this thread's 64 columns of chunk 0
+        float* g_max = s_max + g * 256;
+        float* g_sum = s_sum + g * 256;
+        const int bar_id = 1 + g;
+        float inv_prev = 0.0f;
+        int64_t out_prev = -1;                             // element offset of this thread's 32 outputs, -1 = no store
+
+        auto epilogue = [&](int tp) {                      // tp & 1 == g
+            mbar_wait(o_full + g, (tp >> 1) & 1);
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem_o + g * SA_DH + lane_base + half * 32, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty + g);
+            if (out_prev >= 0) {
+                __nv_bfloat16* op = out + out_prev;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 o;
+                    o.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * inv_prev, __uint_as_float(r[8 * q4 + 1]) * inv_prev);
+                    o.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * inv_prev, __uint_as_float(r[8 * q4 + 3]) * inv_prev);
+                    o.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * inv_prev, __uint_as_float(r[8 * q4 + 5]) * inv_prev);
+                    o.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * inv_prev, __uint_as_float(r[8 * q4 + 7]) * inv_prev);
+                    *reinterpret_cast<uint4*>(op + 8 * q4) = o;
+                }
+            }
+        };
+
+        int last_t = -1;
+        for (int t = g; t < n_tiles; t += 2) {
+            const int n = t / q_tiles;
+            const int qt = t - n * q_tiles;
+            const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+            const int h = item % heads;
+            const int bf = item / heads;
+            const int q_idx = qt * SA_BM + row;
+            const uint32_t par = (t >> 1) & 1;
+
+            // ---- O epilogue of this group's previous tile: its PV retired while the other group worked ----
+            if (last_t >= 0) epilogue(last_t);
+
+            // ---- pass 1: row max over the valid keys ----
+            float mx = -INFINITY;
+            for (int c = 0; c < k_chunks; ++c) {
+                mbar_wait(s_full + g * 3 + c, par);
+                tc_fence_after();
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int key0 = c * 128 + half * 64 + sub * 32;
+                    if (key0 >= tokens) continue;              // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_row + c * 128 + sub * 32, r);
+                    tmem_ld_wait();
+                    if (key0 + 32 <= tokens) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (key0 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    }
+                }
+            }
+            g_max[half * 128 + row] = mx;
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * PP_GROUP_WARPS) : "memory");
+            mx = fmaxf(g_max[row], g_max[128 + row]);
+            const float mxs = mx * scale_log2;
+
+            // ---- pass 2: P = exp2(S*c - max*c) -> bf16 -> TMEM (over the S columns just read), row sums ----
+            float sum = 0.0f;
+            for (int c = 0; c < k_chunks; ++c) {
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    uint32_t pk[16];
+                    const int key0 = c * 128 + half * 64 + sub * 32;
+                    if (key0 >= tokens) {                      // warp-uniform: fully masked
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                    } else {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(t_row + c * 128 + sub * 32, r);
+                        tmem_ld_wait();
+                        if (key0 + 32 <= tokens) {             // warp-uniform: no masking
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+                                const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
+                                sum += e0 + e1;
+                                pk[j] = pack_bf16x2_rne_alu(e0, e1);
+                            }
+                        } else {
+                            const int nvalid = tokens - key0;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+                                float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
+                                if (2 * j >= nvalid) e0 = 0.0f;
+                                if (2 * j + 1 >= nvalid) e1 = 0.0f;
+                                sum += e0 + e1;
+                                pk[j] = pack_bf16x2_rne_alu(e0, e1);
+                            }
+                        }
+                    }
+                    // keys [64*half + 32*sub, +32) of chunk c -> 16 packed columns at the same column offset
+                    tmem_st_32x32b_x16(t_row + c * 128 + sub * 32, pk);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full + g * 3 + c);
+            }
+            g_sum[half * 128 + row] = sum;
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * PP_GROUP_WARPS) : "memory");
+            const float total = g_sum[row] + g_sum[128 + row];
+            inv_prev = 1.0f / total;
+            out_prev = (q_idx < tokens)
+                           ? (static_cast<int64_t>(bf) * tokens + q_idx) * inner + h * SA_DH + half * 32
+                           : -1;
+            if (lse != nullptr && half == 0 && q_idx < tokens)
+                lse[(static_cast<int64_t>(bf) * heads + h) * tokens + q_idx] = mxs + log2f(total);
+            last_t = t;
+        }
+        if (last_t >= 0) epilogue(last_t);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, SA_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // fp32 validation kernel: one CTA per (frame, head); K and V in shared memory, one query per thread.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -659,13 +972,22 @@ static int attn_spatial_launch(const void* qkv, void* out, float* probs, float* 
     }
     const float scale_log2 = scale * 1.4426950408889634f;
     if (probs == nullptr) {
-        // production path: persistent pipelined kernel, one CTA per SM
-        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              SP_SMEM));
+        // production path: persistent pipelined kernel, one CTA per SM; two softmax groups alternating tiles
+        // (ISTVT_SA_PINGPONG=0 selects the single-group version, for A/B measurements)
+        static const bool pingpong = []() { const char* e = getenv("ISTVT_SA_PINGPONG"); return !e || atoi(e) != 0; }();
         const int items = batch_frames * heads;
         const int grid = items < sm_count() ? items : sm_count();
-        attn_spatial_pipe_kernel<<<grid, SP_THREADS, SP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
-                                                                   heads, items, scale_log2);
+        if (pingpong) {
+            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  PP_SMEM));
+            attn_spatial_pp_kernel<<<grid, PP_THREADS, PP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
+                                                                     heads, items, scale_log2);
+        } else {
+            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  SP_SMEM));
+            attn_spatial_pipe_kernel<<<grid, SP_THREADS, SP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
+                                                                       heads, items, scale_log2);
+        }
         count_launch();
         return launch_status();
     }
