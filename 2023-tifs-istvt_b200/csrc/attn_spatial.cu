@@ -554,25 +554,28 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------------
-// bf16 production kernel, second generation: the pipelined kernel above with the 16 softmax warps split into
-// TWO GROUPS THAT ALTERNATE TILES (ping-pong).  ncu of the single-group version (profiles/README.md r1o/r1p) showed
-// the softmax warps as the critical path at ~8 100 clk per query tile against a MUFU floor of 3 072 (128 x 384
-// ex2 at 16 / clk / SM): max pass, CTA-wide barriers, the exp pass and the O epilogue ran back to back in every
-// warp, so the XU pipe idled 60 % of the time.  Here group g owns tiles t = g (mod 2): while it runs the exp pass of
-// tile t, the other group is already in the max pass of tile t+1 on the S chunks the tensor core re-filled behind
-// it (S(t+1).c is issued as soon as P(t).c has been consumed by PV(t).c), and its own O epilogue of tile t-2 falls
-// into the wait for S(t).  Each group has its own O accumulator (tile parity), its own named barrier and its own
-// s_full / p_full barrier sets (a waiter must not skip mbarrier phases, so the sets are indexed by tile parity).
-// Thread = (query row, 64-key half of every chunk), processed as two 32-key sub-blocks in the P layout the MMA
-// issuer already uses.
+// bf16 production kernel, second generation: S is read from TMEM ONCE.
+//
+// The pipelined kernel above is bound by the TMEM read port, not by MUFU: tcgen05.ld moves 64 B/clk/SM
+// (B300_MICROARCH.md, TMEM table), and reading the 128 x 384 fp32 S tile twice (row-max pass + exp pass) plus the O
+// tile costs 6 650 clk per query tile — the measured 7 500 (a two-group ping-pong schedule of the softmax warps,
+// built and measured in round r3c, changed nothing for that reason).  Here every S element is loaded once and stays
+// in registers between its max and its exponential; the row maximum is maintained ONLINE per 128-key chunk:
+//   * chunk c: each of the row's 4 threads loads its 32 columns, publishes the local max (smem) and meets the other
+//     three on a 128-thread named barrier (the 4 warps that share a TMEM lane quadrant); the running max m is only
+//     raised when the chunk's max exceeds it by more than 2^8 in the exp2 domain ("lazy rescale", as in FA-4):
+//     exp2 arguments stay <= 8, bf16 P and the fp32 row sum have the range for that;
+//   * when m is raised for c >= 1 (rare), the row's O accumulator (128 x 64 fp32 in TMEM, 16 columns per thread) and
+//     partial sums are multiplied by exp2(m_old - m_new) after the PV MMAs of the previous chunks have retired
+//     (pv_done barriers, committed by the issuer after every chunk) and before P of chunk c is released.
+// LDTM per tile: 3 072 (S) + 512 (O) clk.  The result is the exact softmax (up to the usual fp32 / bf16 rounding).
 // ------------------------------------------------------------------------------------------
-constexpr int PP_GROUP_WARPS = 8;
-constexpr int PP_THREADS = 128 + 32 * 2 * PP_GROUP_WARPS;          // 640
-constexpr int PP_SMEM = SP_MISC_OFF + 1024 /*align*/ + 256 /*barriers*/ + 2 * 2 * 2 * 128 * 4 /*[max,sum][group][half][row]*/;
+constexpr float SO_TAU = 8.0f;      // lazy-rescale threshold, log2 domain
+constexpr int SO_SMEM = SP_MISC_OFF + 1024 /*align*/ + 256 /*barriers*/ + (2 + 1) * SP_PARTS * 128 * 4 /*max x2, sum*/;
 
-__global__ void __launch_bounds__(PP_THREADS, 1)
-attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                       float* __restrict__ lse, int tokens, int heads, int items, float scale_log2) {
+__global__ void __launch_bounds__(SP_THREADS, 1)
+attn_spatial_online_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
+                           float* __restrict__ lse, int tokens, int heads, int items, float scale_log2) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_q = smem + SP_Q_OFF;
@@ -585,13 +588,14 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
     uint64_t* k_empty = bars + 10;      // [2]
     uint64_t* v_full = bars + 12;
     uint64_t* v_empty = bars + 13;
-    uint64_t* s_full = bars + 14;       // [2 tile parities][3] S chunk c of tile t is in TMEM
-    uint64_t* p_full = bars + 20;       // [2][3] P chunk c of tile t written by all 8 warps of group t & 1
-    uint64_t* o_full = bars + 26;       // [2]
-    uint64_t* o_empty = bars + 28;      // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 30);
-    float* s_max = reinterpret_cast<float*>(smem + SP_MISC_OFF + 256);   // [2 groups][2 halves][128]
-    float* s_sum = s_max + 2 * 2 * 128;
+    uint64_t* s_full = bars + 14;       // [3] S chunk c of the current tile is in TMEM
+    uint64_t* p_full = bars + 17;       // [3] P chunk c written (S chunk c consumed, O rescaled if needed)
+    uint64_t* o_full = bars + 20;       // [2]
+    uint64_t* o_empty = bars + 22;      // [2]
+    uint64_t* pv_done = bars + 24;      // [2] PV MMAs of chunks 0..c of the current tile have retired (c = 0, 1)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 26);
+    float* s_max = reinterpret_cast<float*>(smem + SP_MISC_OFF + 256);   // [2 (chunk parity)][SP_PARTS][128]
+    float* s_sum = s_max + 2 * SP_PARTS * 128;                            // [SP_PARTS][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -609,10 +613,11 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
         for (int i = 0; i < 4; ++i) { mbar_init(q_full + i, 1); mbar_init(q_empty + i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
-            mbar_init(o_full + i, 1); mbar_init(o_empty + i, PP_GROUP_WARPS);
+            mbar_init(o_full + i, 1); mbar_init(o_empty + i, SP_SM_WARPS);
+            mbar_init(pv_done + i, 1);
         }
         mbar_init(v_full, 1); mbar_init(v_empty, 1);
-        for (int i = 0; i < 6; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, PP_GROUP_WARPS); }
+        for (int i = 0; i < 3; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, SP_SM_WARPS); }
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -624,10 +629,10 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const uint32_t tmem_s = tmem_base;
-    const uint32_t tmem_o = tmem_base + SA_KMAX;    // + 64 * (tile parity)
+    const uint32_t tmem_o = tmem_base + SA_KMAX;    // + 64 * buffer
 
     if (warp == 0) {
-        // ================= TMA producer (unchanged) =================
+        // ================= TMA producer =================
         if (lane == 0) {
             for (int n = 0; n < my_items; ++n) {
                 const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
@@ -654,7 +659,7 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ================= MMA issuer: same interleave, barrier sets indexed by tile parity =================
+        // ================= MMA issuer (as in the pipelined kernel, + pv_done commits) =================
         if (elect_one()) {
             const uint32_t idesc_s = make_idesc_bf16(SA_BM, 128, 0, 0);
             const uint32_t idesc_pv = make_idesc_bf16(SA_BM, SA_DH, 0, 1);   // B (= V) is MN-major
@@ -680,7 +685,7 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
                             if (qp == 0) mbar_wait(v_full, np & 1);
                             mbar_wait(o_empty + ob, ((tp >> 1) & 1) ^ 1);
                         }
-                        mbar_wait_hot(p_full + ob * 3 + c, (tp >> 1) & 1);
+                        mbar_wait_hot(p_full + c, tp & 1);
                         tc_fence_after();
                         const uint32_t a0 = tmem_s + c * 128;
                         const uint64_t b0 = desc_v + static_cast<uint64_t>(c * 8 * (16 * 128 >> 4));
@@ -689,12 +694,15 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
                             for (int j = 0; j < 8; ++j)
                                 umma_f16_ts(d_o, a0 + (j >> 1) * 32 + (j & 1) * 8, b0 + j * (16 * 128 >> 4), idesc_pv,
                                             (c | j) != 0 ? 1u : 0u);
+                            umma_commit(pv_done + c);          // c = 0, 1: lets a later chunk rescale O
                         } else {
                             for (int j = 0; j < last_ksteps; ++j)
                                 umma_f16_ts(d_o, a0 + (j >> 1) * 32 + (j & 1) * 8, b0 + j * (16 * 128 >> 4), idesc_pv,
                                             (c | j) != 0 ? 1u : 0u);
                             umma_commit(o_full + ob);
                             if (qp == q_tiles - 1) umma_commit(v_empty);
+                            // keep the pv_done phases in step with the tile index when there are fewer than 3 chunks
+                            for (int cc = c; cc < 2; ++cc) umma_commit(pv_done + cc);
                         }
                     }
                     if (t < n_tiles) {
@@ -709,7 +717,7 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
                         umma_f16_ss(tmem_s + c * 128, q_desc + 2, kc + 2, idesc_s, 1u);
                         umma_f16_ss(tmem_s + c * 128, q_desc + 4, kc + 4, idesc_s, 1u);
                         umma_f16_ss(tmem_s + c * 128, q_desc + 6, kc + 6, idesc_s, 1u);
-                        umma_commit(s_full + (t & 1) * 3 + c);
+                        umma_commit(s_full + c);
                         if (c == k_chunks - 1) {
                             umma_commit(q_empty + slot);
                             if (qt == q_tiles - 1) umma_commit(k_empty + kb);
@@ -722,138 +730,137 @@ attn_spatial_pp_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ================= softmax + epilogue, two groups alternating tiles =================
-        const int sw = warp - 4;
-        const int g = sw >> 3;                             // group = tile parity
-        const int quad = warp & 3;                         // TMEM lane quadrant of this warp
-        const int half = (sw >> 2) & 1;                    // 64-key half of every 128-key chunk
-        const int row = quad * 32 + lane;                  // row inside the q tile == TMEM lane
+        // ================= online softmax + epilogue =================
+        const int quad = warp & 3;
+        const int part = (warp - 4) >> 2;                 // which 32 columns of every 128-key chunk
+        const int row = quad * 32 + lane;                 // row inside the q tile == TMEM lane
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t t_row = tmem_s + lane_base + half * 64;   // this thread's 64 columns of chunk 0
-        float* g_max = s_max + g * 256;
-        float* g_sum = s_sum + g * 256;
-        const int bar_id = 1 + g;
+        const uint32_t t_row = tmem_s + lane_base + part * 32;   // this thread's 32 columns of chunk 0
+        const int qbar = 1 + quad;                         // named barrier of the 4 warps sharing this lane quadrant
         float inv_prev = 0.0f;
-        int64_t out_prev = -1;                             // element offset of this thread's 32 outputs, -1 = no store
+        int64_t out_prev = -1;                             // element offset of this thread's 16 outputs, -1 = no store
 
-        auto epilogue = [&](int tp) {                      // tp & 1 == g
-            mbar_wait(o_full + g, (tp >> 1) & 1);
+        auto epilogue = [&](int tp) {
+            const int ob = tp & 1;
+            mbar_wait(o_full + ob, (tp >> 1) & 1);
             tc_fence_after();
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_o + g * SA_DH + lane_base + half * 32, r);
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tmem_o + ob * SA_DH + lane_base + part * 16, r);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(o_empty + g);
+            if (lane == 0) mbar_arrive(o_empty + ob);
             if (out_prev >= 0) {
                 __nv_bfloat16* op = out + out_prev;
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
+                for (int g = 0; g < 2; ++g) {
                     uint4 o;
-                    o.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * inv_prev, __uint_as_float(r[8 * q4 + 1]) * inv_prev);
-                    o.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * inv_prev, __uint_as_float(r[8 * q4 + 3]) * inv_prev);
-                    o.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * inv_prev, __uint_as_float(r[8 * q4 + 5]) * inv_prev);
-                    o.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * inv_prev, __uint_as_float(r[8 * q4 + 7]) * inv_prev);
-                    *reinterpret_cast<uint4*>(op + 8 * q4) = o;
+                    o.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv_prev, __uint_as_float(r[8 * g + 1]) * inv_prev);
+                    o.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv_prev, __uint_as_float(r[8 * g + 3]) * inv_prev);
+                    o.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv_prev, __uint_as_float(r[8 * g + 5]) * inv_prev);
+                    o.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv_prev, __uint_as_float(r[8 * g + 7]) * inv_prev);
+                    *reinterpret_cast<uint4*>(op + 8 * g) = o;
                 }
             }
         };
 
-        int last_t = -1;
-        for (int t = g; t < n_tiles; t += 2) {
-            const int n = t / q_tiles;
-            const int qt = t - n * q_tiles;
+        int qt = 0, n = 0;
+        for (int t = 0; t < n_tiles; ++t) {
             const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
             const int h = item % heads;
             const int bf = item / heads;
             const int q_idx = qt * SA_BM + row;
-            const uint32_t par = (t >> 1) & 1;
+            const int ob = t & 1;
 
-            // ---- O epilogue of this group's previous tile: its PV retired while the other group worked ----
-            if (last_t >= 0) epilogue(last_t);
-
-            // ---- pass 1: row max over the valid keys ----
-            float mx = -INFINITY;
+            float m_run = -INFINITY;       // running row max (raw logits), identical in the row's 4 threads
+            float mxs = 0.0f;              // m_run * scale_log2
+            float sum = 0.0f;              // this thread's partial row sum, relative to m_run
             for (int c = 0; c < k_chunks; ++c) {
-                mbar_wait(s_full + g * 3 + c, par);
+                mbar_wait(s_full + c, t & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-                    const int key0 = c * 128 + half * 64 + sub * 32;
-                    if (key0 >= tokens) continue;              // warp-uniform
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_row + c * 128 + sub * 32, r);
+                const int key0 = c * 128 + part * 32;
+                const bool live = key0 < tokens;               // warp-uniform
+                const bool full = key0 + 32 <= tokens;         // warp-uniform
+                uint32_t r[32];
+                float lmax = -INFINITY;
+                if (live) {
+                    tmem_ld_32x32b_x32(t_row + c * 128, r);
                     tmem_ld_wait();
-                    if (key0 + 32 <= tokens) {
+                    if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        for (int j = 0; j < 32; ++j) lmax = fmaxf(lmax, __uint_as_float(r[j]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (key0 + j < tokens) mx = fmaxf(mx, __uint_as_float(r[j]));
+                            if (key0 + j < tokens) lmax = fmaxf(lmax, __uint_as_float(r[j]));
                     }
                 }
-            }
-            g_max[half * 128 + row] = mx;
-            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * PP_GROUP_WARPS) : "memory");
-            mx = fmaxf(g_max[row], g_max[128 + row]);
-            const float mxs = mx * scale_log2;
+                float* xch = s_max + (c & 1) * (SP_PARTS * 128);
+                xch[part * 128 + row] = lmax;
+                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+                const float cmax = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row]));
+                // raise the running max only when the chunk exceeds it by more than 2^SO_TAU (always for chunk 0)
+                const bool raise = (cmax - m_run) * scale_log2 > SO_TAU;      // -inf running max: +inf > tau
+                if (c > 0 && __any_sync(0xffffffffu, raise)) {
+                    // O(t) holds chunks 0..c-1 relative to the old max: rescale this thread's 16 columns of its row
+                    mbar_wait(pv_done + (c - 1), t & 1);
+                    tc_fence_after();
+                    const float f = raise ? ex2_approx((m_run - cmax) * scale_log2) : 1.0f;
+                    uint32_t o[16];
+                    tmem_ld_32x32b_x16(tmem_o + ob * SA_DH + lane_base + part * 16, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+                    tmem_st_32x32b_x16(tmem_o + ob * SA_DH + lane_base + part * 16, o);
+                    sum *= f;
+                }
+                if (raise) { m_run = cmax; mxs = cmax * scale_log2; }
 
-            // ---- pass 2: P = exp2(S*c - max*c) -> bf16 -> TMEM (over the S columns just read), row sums ----
-            float sum = 0.0f;
-            for (int c = 0; c < k_chunks; ++c) {
+                // deferred epilogue of the previous tile: its PV retired while chunk 0 of this tile was processed
+                if (c == 0 && t > 0) epilogue(t - 1);
+
+                uint32_t pk[16];
+                if (!live) {
 #pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-                    uint32_t pk[16];
-                    const int key0 = c * 128 + half * 64 + sub * 32;
-                    if (key0 >= tokens) {                      // warp-uniform: fully masked
+                    for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                } else if (full) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = 0u;
-                    } else {
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(t_row + c * 128 + sub * 32, r);
-                        tmem_ld_wait();
-                        if (key0 + 32 <= tokens) {             // warp-uniform: no masking
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
-                                const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
-                                sum += e0 + e1;
-                                pk[j] = pack_bf16x2_rne_alu(e0, e1);
-                            }
-                        } else {
-                            const int nvalid = tokens - key0;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
-                                float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
-                                if (2 * j >= nvalid) e0 = 0.0f;
-                                if (2 * j + 1 >= nvalid) e1 = 0.0f;
-                                sum += e0 + e1;
-                                pk[j] = pack_bf16x2_rne_alu(e0, e1);
-                            }
-                        }
+                    for (int j = 0; j < 16; ++j) {
+                        const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+                        const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
+                        sum += e0 + e1;
+                        pk[j] = pack_bf16x2_rne_alu(e0, e1);
                     }
-                    // keys [64*half + 32*sub, +32) of chunk c -> 16 packed columns at the same column offset
-                    tmem_st_32x32b_x16(t_row + c * 128 + sub * 32, pk);
+                } else {
+                    const int nvalid = tokens - key0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+                        float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
+                        if (2 * j >= nvalid) e0 = 0.0f;
+                        if (2 * j + 1 >= nvalid) e1 = 0.0f;
+                        sum += e0 + e1;
+                        pk[j] = pack_bf16x2_rne_alu(e0, e1);
+                    }
                 }
-                tmem_st_wait();
+                tmem_st_32x32b_x16(t_row + c * 128, pk);   // keys [32*part, 32*part+32) of chunk c -> 16 columns
+                tmem_st_wait();                              // also covers the O rescale stores above
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(p_full + g * 3 + c);
+                if (lane == 0) mbar_arrive(p_full + c);
             }
-            g_sum[half * 128 + row] = sum;
-            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * PP_GROUP_WARPS) : "memory");
-            const float total = g_sum[row] + g_sum[128 + row];
+            s_sum[part * 128 + row] = sum;
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+            const float total = (s_sum[row] + s_sum[128 + row]) + (s_sum[256 + row] + s_sum[384 + row]);
             inv_prev = 1.0f / total;
             out_prev = (q_idx < tokens)
-                           ? (static_cast<int64_t>(bf) * tokens + q_idx) * inner + h * SA_DH + half * 32
+                           ? (static_cast<int64_t>(bf) * tokens + q_idx) * inner + h * SA_DH + part * 16
                            : -1;
-            if (lse != nullptr && half == 0 && q_idx < tokens)
+            if (lse != nullptr && part == 0 && q_idx < tokens)
                 lse[(static_cast<int64_t>(bf) * heads + h) * tokens + q_idx] = mxs + log2f(total);
-            last_t = t;
+            if (++qt == q_tiles) { qt = 0; ++n; }
         }
-        if (last_t >= 0) epilogue(last_t);
+        if (n_tiles > 0) epilogue(n_tiles - 1);
     }
 
     tc_fence_before();
@@ -972,16 +979,16 @@ static int attn_spatial_launch(const void* qkv, void* out, float* probs, float* 
     }
     const float scale_log2 = scale * 1.4426950408889634f;
     if (probs == nullptr) {
-        // production path: persistent pipelined kernel, one CTA per SM; two softmax groups alternating tiles
-        // (ISTVT_SA_PINGPONG=0 selects the single-group version, for A/B measurements)
-        static const bool pingpong = []() { const char* e = getenv("ISTVT_SA_PINGPONG"); return !e || atoi(e) != 0; }();
+        // production path: persistent pipelined kernel, one CTA per SM, S read from TMEM once (online row max);
+        // ISTVT_SA_ONLINE=0 selects the two-pass predecessor, for A/B measurements
+        static const bool online = []() { const char* e = getenv("ISTVT_SA_ONLINE"); return !e || atoi(e) != 0; }();
         const int items = batch_frames * heads;
         const int grid = items < sm_count() ? items : sm_count();
-        if (pingpong) {
-            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  PP_SMEM));
-            attn_spatial_pp_kernel<<<grid, PP_THREADS, PP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
-                                                                     heads, items, scale_log2);
+        if (online) {
+            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_online_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  SO_SMEM));
+            attn_spatial_online_kernel<<<grid, SP_THREADS, SO_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
+                                                                         heads, items, scale_log2);
         } else {
             ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   SP_SMEM));
