@@ -14,8 +14,6 @@
 #include "ptx.cuh"
 #include "simt_util.cuh"
 
-#include <stdlib.h>
-
 namespace istvt {
 
 constexpr int SA_DH = 64;
@@ -553,323 +551,13 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// bf16 production kernel, second generation: S is read from TMEM ONCE.
-//
-// The pipelined kernel above is bound by the TMEM read port, not by MUFU: tcgen05.ld moves 64 B/clk/SM
-// (B300_MICROARCH.md, TMEM table), and reading the 128 x 384 fp32 S tile twice (row-max pass + exp pass) plus the O
-// tile costs 6 650 clk per query tile — the measured 7 500 (a two-group ping-pong schedule of the softmax warps,
-// built and measured in round r3c, changed nothing for that reason).  Here every S element is loaded once and stays
-// in registers between its max and its exponential; the row maximum is maintained ONLINE per 128-key chunk:
-//   * chunk c: each of the row's 4 threads loads its 32 columns, publishes the local max (smem) and meets the other
-//     three on a 128-thread named barrier (the 4 warps that share a TMEM lane quadrant); the running max m is only
-//     raised when the chunk's max exceeds it by more than 2^8 in the exp2 domain ("lazy rescale", as in FA-4):
-//     exp2 arguments stay <= 8, bf16 P and the fp32 row sum have the range for that;
-//   * when m is raised for c >= 1 (rare), the row's O accumulator (128 x 64 fp32 in TMEM, 16 columns per thread) and
-//     partial sums are multiplied by exp2(m_old - m_new) after the PV MMAs of the previous chunks have retired
-//     (pv_done barriers, committed by the issuer after every chunk) and before P of chunk c is released.
-// LDTM per tile: 3 072 (S) + 512 (O) clk.  The result is the exact softmax (up to the usual fp32 / bf16 rounding).
-// ------------------------------------------------------------------------------------------
-constexpr float SO_TAU = 8.0f;      // lazy-rescale threshold, log2 domain
-constexpr int SO_SMEM = SP_MISC_OFF + 1024 /*align*/ + 256 /*barriers*/ + (2 + 1) * SP_PARTS * 128 * 4 /*max x2, sum*/;
-
-__global__ void __launch_bounds__(SP_THREADS, 1)
-attn_spatial_online_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                           float* __restrict__ lse, int tokens, int heads, int items, float scale_log2) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* s_q = smem + SP_Q_OFF;
-    uint8_t* s_k = smem + SP_K_OFF;
-    uint8_t* s_v = smem + SP_V_OFF;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SP_MISC_OFF);
-    uint64_t* q_full = bars;            // [4]
-    uint64_t* q_empty = bars + 4;       // [4]
-    uint64_t* k_full = bars + 8;        // [2]
-    uint64_t* k_empty = bars + 10;      // [2]
-    uint64_t* v_full = bars + 12;
-    uint64_t* v_empty = bars + 13;
-    uint64_t* s_full = bars + 14;       // [3] S chunk c of the current tile is in TMEM
-    uint64_t* p_full = bars + 17;       // [3] P chunk c written (S chunk c consumed, O rescaled if needed)
-    uint64_t* o_full = bars + 20;       // [2]
-    uint64_t* o_empty = bars + 22;      // [2]
-    uint64_t* pv_done = bars + 24;      // [2] PV MMAs of chunks 0..c of the current tile have retired (c = 0, 1)
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 26);
-    float* s_max = reinterpret_cast<float*>(smem + SP_MISC_OFF + 256);   // [2 (chunk parity)][SP_PARTS][128]
-    float* s_sum = s_max + 2 * SP_PARTS * 128;                            // [SP_PARTS][128]
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int inner = heads * SA_DH;
-    const int q_tiles = (tokens + SA_BM - 1) / SA_BM;
-    const int k_chunks = q_tiles;
-    const int my_items = (items > static_cast<int>(blockIdx.x))
-                             ? (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                                   static_cast<int>(gridDim.x)
-                             : 0;
-    const int n_tiles = my_items * q_tiles;
-
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_qkv);
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(q_full + i, 1); mbar_init(q_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1);
-            mbar_init(o_full + i, 1); mbar_init(o_empty + i, SP_SM_WARPS);
-            mbar_init(pv_done + i, 1);
-        }
-        mbar_init(v_full, 1); mbar_init(v_empty, 1);
-        for (int i = 0; i < 3; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, SP_SM_WARPS); }
-        fence_mbar_init();
-    }
-    if (warp == 2) {
-        tmem_alloc(tmem_holder, SA_TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_s = tmem_base;
-    const uint32_t tmem_o = tmem_base + SA_KMAX;    // + 64 * buffer
-
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            for (int n = 0; n < my_items; ++n) {
-                const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-                const int h = item % heads;
-                const int bf = item / heads;
-                const int kb = n & 1;
-                mbar_wait_sleep(k_empty + kb, ((n >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(k_full + kb, k_chunks * SP_CHUNK_BYTES);
-                for (int c = 0; c < k_chunks; ++c)
-                    tma_load_3d(s_k + kb * SA_KV_BYTES + c * SP_CHUNK_BYTES, &tm_qkv, k_full + kb, inner + h * SA_DH,
-                                c * 128, bf);
-                for (int qt = 0; qt < q_tiles; ++qt) {
-                    const int t = n * q_tiles + qt;
-                    const int slot = t & 3;
-                    mbar_wait_sleep(q_empty + slot, ((t >> 2) & 1) ^ 1);
-                    mbar_arrive_expect_tx(q_full + slot, SP_CHUNK_BYTES);
-                    tma_load_3d(s_q + slot * SP_CHUNK_BYTES, &tm_qkv, q_full + slot, h * SA_DH, qt * SA_BM, bf);
-                }
-                mbar_wait_sleep(v_empty, (n & 1) ^ 1);
-                mbar_arrive_expect_tx(v_full, k_chunks * SP_CHUNK_BYTES);
-                for (int c = 0; c < k_chunks; ++c)
-                    tma_load_3d(s_v + c * SP_CHUNK_BYTES, &tm_qkv, v_full, 2 * inner + h * SA_DH, c * 128, bf);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ================= MMA issuer (as in the pipelined kernel, + pv_done commits) =================
-        if (elect_one()) {
-            const uint32_t idesc_s = make_idesc_bf16(SA_BM, 128, 0, 0);
-            const uint32_t idesc_pv = make_idesc_bf16(SA_BM, SA_DH, 0, 1);   // B (= V) is MN-major
-            const uint64_t desc_kmaj = make_smem_desc(0, 0, 1024, SWZ_128B);
-            const uint64_t desc_v = make_smem_desc(smem_u32(s_v), 64 * 128, 1024, SWZ_128B);
-            const uint32_t q_field = (smem_u32(s_q) & 0x3FFFFu) >> 4;
-            const uint32_t k_field = (smem_u32(s_k) & 0x3FFFFu) >> 4;
-            const int last_ksteps = (tokens - (k_chunks - 1) * 128 + 15) / 16;
-            int qt = 0, n = 0;          // tile t = n * q_tiles + qt
-            int qp = 0, np = 0;         // tile t - 1
-            for (int t = 0; t <= n_tiles; ++t) {
-                const int slot = t & 3;
-                const int kb = n & 1;
-                const int tp = t - 1;
-                const int ob = tp & 1;
-                const uint64_t q_desc = desc_kmaj | (q_field + slot * (SP_CHUNK_BYTES >> 4));
-                const uint64_t k_desc = desc_kmaj | (k_field + kb * (SA_KV_BYTES >> 4));
-                const uint32_t d_o = tmem_o + ob * SA_DH;
-                for (int c = 0; c < k_chunks; ++c) {
-                    if (t > 0) {
-                        // ---- O(t-1) += P(t-1).c V.c ----
-                        if (c == 0) {
-                            if (qp == 0) mbar_wait(v_full, np & 1);
-                            mbar_wait(o_empty + ob, ((tp >> 1) & 1) ^ 1);
-                        }
-                        mbar_wait_hot(p_full + c, tp & 1);
-                        tc_fence_after();
-                        const uint32_t a0 = tmem_s + c * 128;
-                        const uint64_t b0 = desc_v + static_cast<uint64_t>(c * 8 * (16 * 128 >> 4));
-                        if (c != k_chunks - 1) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                umma_f16_ts(d_o, a0 + (j >> 1) * 32 + (j & 1) * 8, b0 + j * (16 * 128 >> 4), idesc_pv,
-                                            (c | j) != 0 ? 1u : 0u);
-                            umma_commit(pv_done + c);          // c = 0, 1: lets a later chunk rescale O
-                        } else {
-                            for (int j = 0; j < last_ksteps; ++j)
-                                umma_f16_ts(d_o, a0 + (j >> 1) * 32 + (j & 1) * 8, b0 + j * (16 * 128 >> 4), idesc_pv,
-                                            (c | j) != 0 ? 1u : 0u);
-                            umma_commit(o_full + ob);
-                            if (qp == q_tiles - 1) umma_commit(v_empty);
-                            // keep the pv_done phases in step with the tile index when there are fewer than 3 chunks
-                            for (int cc = c; cc < 2; ++cc) umma_commit(pv_done + cc);
-                        }
-                    }
-                    if (t < n_tiles) {
-                        // ---- S(t).c = Q(t) K.c^T ----
-                        if (c == 0) {
-                            mbar_wait_hot(q_full + slot, (t >> 2) & 1);
-                            if (qt == 0) mbar_wait_hot(k_full + kb, (n >> 1) & 1);
-                            tc_fence_after();
-                        }
-                        const uint64_t kc = k_desc + static_cast<uint64_t>(c * (SP_CHUNK_BYTES >> 4));
-                        umma_f16_ss(tmem_s + c * 128, q_desc, kc, idesc_s, 0u);
-                        umma_f16_ss(tmem_s + c * 128, q_desc + 2, kc + 2, idesc_s, 1u);
-                        umma_f16_ss(tmem_s + c * 128, q_desc + 4, kc + 4, idesc_s, 1u);
-                        umma_f16_ss(tmem_s + c * 128, q_desc + 6, kc + 6, idesc_s, 1u);
-                        umma_commit(s_full + c);
-                        if (c == k_chunks - 1) {
-                            umma_commit(q_empty + slot);
-                            if (qt == q_tiles - 1) umma_commit(k_empty + kb);
-                        }
-                    }
-                }
-                qp = qt; np = n;
-                if (++qt == q_tiles) { qt = 0; ++n; }
-            }
-        }
-        __syncwarp();
-    } else if (warp >= 4) {
-        // ================= online softmax + epilogue =================
-        const int quad = warp & 3;
-        const int part = (warp - 4) >> 2;                 // which 32 columns of every 128-key chunk
-        const int row = quad * 32 + lane;                 // row inside the q tile == TMEM lane
-        const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t t_row = tmem_s + lane_base + part * 32;   // this thread's 32 columns of chunk 0
-        const int qbar = 1 + quad;                         // named barrier of the 4 warps sharing this lane quadrant
-        float inv_prev = 0.0f;
-        int64_t out_prev = -1;                             // element offset of this thread's 16 outputs, -1 = no store
-
-        auto epilogue = [&](int tp) {
-            const int ob = tp & 1;
-            mbar_wait(o_full + ob, (tp >> 1) & 1);
-            tc_fence_after();
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(tmem_o + ob * SA_DH + lane_base + part * 16, r);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(o_empty + ob);
-            if (out_prev >= 0) {
-                __nv_bfloat16* op = out + out_prev;
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    uint4 o;
-                    o.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv_prev, __uint_as_float(r[8 * g + 1]) * inv_prev);
-                    o.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv_prev, __uint_as_float(r[8 * g + 3]) * inv_prev);
-                    o.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv_prev, __uint_as_float(r[8 * g + 5]) * inv_prev);
-                    o.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv_prev, __uint_as_float(r[8 * g + 7]) * inv_prev);
-                    *reinterpret_cast<uint4*>(op + 8 * g) = o;
-                }
-            }
-        };
-
-        int qt = 0, n = 0;
-        for (int t = 0; t < n_tiles; ++t) {
-            const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-            const int h = item % heads;
-            const int bf = item / heads;
-            const int q_idx = qt * SA_BM + row;
-            const int ob = t & 1;
-
-            float m_run = -INFINITY;       // running row max (raw logits), identical in the row's 4 threads
-            float mxs = 0.0f;              // m_run * scale_log2
-            float sum = 0.0f;              // this thread's partial row sum, relative to m_run
-            for (int c = 0; c < k_chunks; ++c) {
-                mbar_wait(s_full + c, t & 1);
-                tc_fence_after();
-                const int key0 = c * 128 + part * 32;
-                const bool live = key0 < tokens;               // warp-uniform
-                const bool full = key0 + 32 <= tokens;         // warp-uniform
-                uint32_t r[32];
-                float lmax = -INFINITY;
-                if (live) {
-                    tmem_ld_32x32b_x32(t_row + c * 128, r);
-                    tmem_ld_wait();
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) lmax = fmaxf(lmax, __uint_as_float(r[j]));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (key0 + j < tokens) lmax = fmaxf(lmax, __uint_as_float(r[j]));
-                    }
-                }
-                float* xch = s_max + (c & 1) * (SP_PARTS * 128);
-                xch[part * 128 + row] = lmax;
-                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
-                const float cmax = fmaxf(fmaxf(xch[row], xch[128 + row]), fmaxf(xch[256 + row], xch[384 + row]));
-                // raise the running max only when the chunk exceeds it by more than 2^SO_TAU (always for chunk 0)
-                const bool raise = (cmax - m_run) * scale_log2 > SO_TAU;      // -inf running max: +inf > tau
-                if (c > 0 && __any_sync(0xffffffffu, raise)) {
-                    // O(t) holds chunks 0..c-1 relative to the old max: rescale this thread's 16 columns of its row
-                    mbar_wait(pv_done + (c - 1), t & 1);
-                    tc_fence_after();
-                    const float f = raise ? ex2_approx((m_run - cmax) * scale_log2) : 1.0f;
-                    uint32_t o[16];
-                    tmem_ld_32x32b_x16(tmem_o + ob * SA_DH + lane_base + part * 16, o);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
-                    tmem_st_32x32b_x16(tmem_o + ob * SA_DH + lane_base + part * 16, o);
-                    sum *= f;
-                }
-                if (raise) { m_run = cmax; mxs = cmax * scale_log2; }
-
-                // deferred epilogue of the previous tile: its PV retired while chunk 0 of this tile was processed
-                if (c == 0 && t > 0) epilogue(t - 1);
-
-                uint32_t pk[16];
-                if (!live) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) pk[j] = 0u;
-                } else if (full) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
-                        const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
-                        sum += e0 + e1;
-                        pk[j] = pack_bf16x2_rne_alu(e0, e1);
-                    }
-                } else {
-                    const int nvalid = tokens - key0;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
-                        float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
-                        if (2 * j >= nvalid) e0 = 0.0f;
-                        if (2 * j + 1 >= nvalid) e1 = 0.0f;
-                        sum += e0 + e1;
-                        pk[j] = pack_bf16x2_rne_alu(e0, e1);
-                    }
-                }
-                tmem_st_32x32b_x16(t_row + c * 128, pk);   // keys [32*part, 32*part+32) of chunk c -> 16 columns
-                tmem_st_wait();                              // also covers the O rescale stores above
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(p_full + c);
-            }
-            s_sum[part * 128 + row] = sum;
-            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
-            const float total = (s_sum[row] + s_sum[128 + row]) + (s_sum[256 + row] + s_sum[384 + row]);
-            inv_prev = 1.0f / total;
-            out_prev = (q_idx < tokens)
-                           ? (static_cast<int64_t>(bf) * tokens + q_idx) * inner + h * SA_DH + part * 16
-                           : -1;
-            if (lse != nullptr && part == 0 && q_idx < tokens)
-                lse[(static_cast<int64_t>(bf) * heads + h) * tokens + q_idx] = mxs + log2f(total);
-            if (++qt == q_tiles) { qt = 0; ++n; }
-        }
-        if (n_tiles > 0) epilogue(n_tiles - 1);
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, SA_TMEM_COLS);
-    }
-}
+// Two restructurings of the softmax side of this kernel were built, validated and measured in round 3 and did NOT
+// pay (profiles/README.md r3c / r3d; the code is in the git history):
+//   * two softmax groups alternating query tiles (ping-pong, barrier sets per tile parity): 0.289 vs 0.288 ms per
+//     launch at the C2 size — the softmax warps' serial max -> barrier -> exp chain is not the limiter;
+//   * S read from TMEM once (online row max per 128-key chunk, lazy O rescale, quad-level named barriers):
+//     0.338 ms — the per-chunk barrier puts the 4 warps of a scheduler in lockstep, so tcgen05.ld latency no longer
+//     overlaps the MUFU work of sibling warps; halving the TMEM reads (64 B/clk port) did not compensate.
 
 // ------------------------------------------------------------------------------------------
 // fp32 validation kernel: one CTA per (frame, head); K and V in shared memory, one query per thread.
@@ -979,22 +667,13 @@ static int attn_spatial_launch(const void* qkv, void* out, float* probs, float* 
     }
     const float scale_log2 = scale * 1.4426950408889634f;
     if (probs == nullptr) {
-        // production path: persistent pipelined kernel, one CTA per SM, S read from TMEM once (online row max);
-        // ISTVT_SA_ONLINE=0 selects the two-pass predecessor, for A/B measurements
-        static const bool online = []() { const char* e = getenv("ISTVT_SA_ONLINE"); return !e || atoi(e) != 0; }();
+        // production path: persistent pipelined kernel, one CTA per SM
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              SP_SMEM));
         const int items = batch_frames * heads;
         const int grid = items < sm_count() ? items : sm_count();
-        if (online) {
-            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_online_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  SO_SMEM));
-            attn_spatial_online_kernel<<<grid, SP_THREADS, SO_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
-                                                                         heads, items, scale_log2);
-        } else {
-            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  SP_SMEM));
-            attn_spatial_pipe_kernel<<<grid, SP_THREADS, SP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
-                                                                       heads, items, scale_log2);
-        }
+        attn_spatial_pipe_kernel<<<grid, SP_THREADS, SP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
+                                                                   heads, items, scale_log2);
         count_launch();
         return launch_status();
     }

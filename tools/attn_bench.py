@@ -1,7 +1,6 @@
 """Timing of the spatial / temporal attention kernels at the C2 sizes (64 clips: 448 frames x 362 tokens x 8 heads).
 
     python tools/attn_bench.py [--clips 64] [--iters 20]
-    ISTVT_SA_ONLINE=0 python tools/attn_bench.py       # the two-pass predecessor, for A/B
 """
 from __future__ import annotations
 
