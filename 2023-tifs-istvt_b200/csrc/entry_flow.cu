@@ -328,8 +328,7 @@ dwconv3x3_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __re
 // HBM floor: (2 + 2) B per output; the FMA pipe needs 9 of the ~14 issue slots.
 // ------------------------------------------------------------------------------------------
 constexpr int DS_CG = 64;            // channels per item (one 128-byte line per pixel)
-constexpr int DS_R = 6;              // input rows per ring stage (multiple of 3: accumulator roles realign)
-constexpr int DS_STAGES = 3;
+// input rows per ring stage (multiple of 3: the accumulator roles realign) x ring depth: 6 x 3 or 3 x 6 (same bytes)
 constexpr int DS_MAX_PAIRS = 19;     // column pairs per strip -> strips of <= 38 outputs
 constexpr int DS_MAX_THREADS = ((16 * DS_MAX_PAIRS + 31) / 32) * 32;   // 320 (a producer warp would cap the
                                                                         // kernel at 80 registers and spill)
@@ -347,7 +346,7 @@ struct DwStripPlan {
     int64_t items;
 };
 
-template <bool RELU>
+template <bool RELU, int DS_R, int DS_STAGES>
 __global__ void __launch_bounds__(DS_MAX_THREADS, 2)
 dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ wt,
                        __nv_bfloat16* __restrict__ y, int n, int h, int w, int c, const DwStripPlan plan) {
@@ -710,21 +709,28 @@ static int launch_dwconv_strips(const void* x, const float* wt, void* y, int n, 
                               static_cast<uint64_t>(n)};
     const uint64_t strides[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(w) * c * 2,
                                  static_cast<uint64_t>(h) * w * c * 2};
-    const uint32_t box[4] = {DS_CG, static_cast<uint32_t>(in_w), DS_R, 1};
+    // ISTVT_DW_R3=1: 3-row stages x 6 instead of 6-row stages x 3 (finer hand-off, same smem) — A/B measurements
+    static const bool r3 = []() { const char* e = getenv("ISTVT_DW_R3"); return e && atoi(e) != 0; }();
+    const int rows = r3 ? 3 : 6, stages = r3 ? 6 : 3;
+    const uint32_t box[4] = {DS_CG, static_cast<uint32_t>(in_w), static_cast<uint32_t>(rows), 1};
     int rc = encode_tmap(&tm, x, ISTVT_BF16, 4, dims, strides, box, 0);
     if (rc != ISTVT_OK) return rc;
-    const int smem = DS_STAGES * DS_R * in_w * DS_CG * 2 + 128 + 64;
+    const int smem = stages * rows * in_w * DS_CG * 2 + 128 + 64;
     const int threads = pl.warps * 32;
     const int64_t grid = pl.items < grid_max ? pl.items : grid_max;
-    if (relu_in) {
-        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        dwconv3x3_strip_kernel<true><<<static_cast<unsigned>(grid), threads, smem, st>>>(
-            tm, wt, static_cast<__nv_bfloat16*>(y), n, h, w, c, pl);
+#define ISTVT_DW_LAUNCH(RELU, R, S)                                                                                   \
+    do {                                                                                                              \
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<RELU, R, S>,                                     \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
+        dwconv3x3_strip_kernel<RELU, R, S><<<static_cast<unsigned>(grid), threads, smem, st>>>(                       \
+            tm, wt, static_cast<__nv_bfloat16*>(y), n, h, w, c, pl);                                                  \
+    } while (0)
+    if (r3) {
+        if (relu_in) ISTVT_DW_LAUNCH(true, 3, 6); else ISTVT_DW_LAUNCH(false, 3, 6);
     } else {
-        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        dwconv3x3_strip_kernel<false><<<static_cast<unsigned>(grid), threads, smem, st>>>(
-            tm, wt, static_cast<__nv_bfloat16*>(y), n, h, w, c, pl);
+        if (relu_in) ISTVT_DW_LAUNCH(true, 6, 3); else ISTVT_DW_LAUNCH(false, 6, 3);
     }
+#undef ISTVT_DW_LAUNCH
     count_launch();
     return launch_status();
 }
