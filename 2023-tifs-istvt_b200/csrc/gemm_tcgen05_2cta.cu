@@ -47,7 +47,6 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     uint64_t* tmem_full = bars + 2 * G2_STAGES;
     uint64_t* tmem_empty = bars + 2 * G2_STAGES + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
-    volatile int* prod_tile = reinterpret_cast<volatile int*>(bars + 2 * G2_STAGES + 5);   // producer's tile counter
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -76,7 +75,6 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             mbar_init(&tmem_full[s], 1);                    // one multicast commit
             mbar_init(&tmem_empty[s], 2 * G2_EPI_WARPS);    // epilogue warps of both CTAs
         }
-        *prod_tile = -1;
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -99,9 +97,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters, ++it) {
-                *prod_tile = it;
+            for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
                 const int ks = static_cast<int>(tile / mn_tiles);
                 const int64_t mn = tile - ks * mn_tiles;
                 const int64_t m_blk = mn / n_tiles;
@@ -189,23 +185,22 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         // the A rows of the tile two steps ahead into L2 with plain prefetch.global.L2 (LSU path: a TMA prefetch in the
         // producer's queue was measured slower, it holds TMA request slots for a DRAM round trip).  Only the cluster
         // whose tile opens the m-block (n_blk == 0) prefetches it.
-        // Paced by the producer's tile counter in smem (a plain value, not an mbarrier phase: if this warp falls behind
-        // it simply skips ahead instead of waiting for a parity that has already come round again).
+        int acc = 0;
+        uint32_t acc_phase = 0;
         const int lines_per_row = (p.K * 2 + 127) / 128;
         const uint8_t* a8 = static_cast<const uint8_t*>(p.a_ptr);
-        const uint8_t* a_end = a8 + p.M * p.lda * 2;
-        int it = 0;
-        for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters, ++it) {
-            while (*prod_tile < it) __nanosleep(256);
+        for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
+            mbar_wait(&tmem_full[acc], acc_phase);
             const int64_t ahead = tile + 2 * static_cast<int64_t>(n_clusters);
             if (ahead < total_tiles && ahead % n_tiles == 0) {
                 const int64_t m0 = (ahead / n_tiles) * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M;
                 for (int r = 0; r < GEMM_BLOCK_M && m0 + r < p.M; ++r) {
                     const uint8_t* row = a8 + (m0 + r) * p.lda * 2;
                     for (int l = lane; l < lines_per_row; l += 32)
-                        if (row + l * 128 < a_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + l * 128));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + l * 128));
                 }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4) {
         // ===================== epilogue (this CTA's 128 rows x 256 columns) =====================
