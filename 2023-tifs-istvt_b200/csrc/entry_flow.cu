@@ -709,28 +709,26 @@ static int launch_dwconv_strips(const void* x, const float* wt, void* y, int n, 
                               static_cast<uint64_t>(n)};
     const uint64_t strides[3] = {static_cast<uint64_t>(c) * 2, static_cast<uint64_t>(w) * c * 2,
                                  static_cast<uint64_t>(h) * w * c * 2};
-    // ISTVT_DW_R3=1: 3-row stages x 6 instead of 6-row stages x 3 (finer hand-off, same smem) — A/B measurements
-    static const bool r3 = []() { const char* e = getenv("ISTVT_DW_R3"); return e && atoi(e) != 0; }();
-    const int rows = r3 ? 3 : 6, stages = r3 ? 6 : 3;
+    // (3-row stages x 6 instead of 6-row stages x 3 — finer hand-off, same smem — measured slower: 3.30 vs 2.77 ms
+    //  over the six C2 layers, profiles/README.md r3f.)
+    constexpr int rows = 6, stages = 3;
     const uint32_t box[4] = {DS_CG, static_cast<uint32_t>(in_w), static_cast<uint32_t>(rows), 1};
     int rc = encode_tmap(&tm, x, ISTVT_BF16, 4, dims, strides, box, 0);
     if (rc != ISTVT_OK) return rc;
     const int smem = stages * rows * in_w * DS_CG * 2 + 128 + 64;
     const int threads = pl.warps * 32;
     const int64_t grid = pl.items < grid_max ? pl.items : grid_max;
-#define ISTVT_DW_LAUNCH(RELU, R, S)                                                                                   \
-    do {                                                                                                              \
-        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<RELU, R, S>,                                     \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
-        dwconv3x3_strip_kernel<RELU, R, S><<<static_cast<unsigned>(grid), threads, smem, st>>>(                       \
-            tm, wt, static_cast<__nv_bfloat16*>(y), n, h, w, c, pl);                                                  \
-    } while (0)
-    if (r3) {
-        if (relu_in) ISTVT_DW_LAUNCH(true, 3, 6); else ISTVT_DW_LAUNCH(false, 3, 6);
+    if (relu_in) {
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<true, rows, stages>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        dwconv3x3_strip_kernel<true, rows, stages><<<static_cast<unsigned>(grid), threads, smem, st>>>(
+            tm, wt, static_cast<__nv_bfloat16*>(y), n, h, w, c, pl);
     } else {
-        if (relu_in) ISTVT_DW_LAUNCH(true, 6, 3); else ISTVT_DW_LAUNCH(false, 6, 3);
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_strip_kernel<false, rows, stages>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        dwconv3x3_strip_kernel<false, rows, stages><<<static_cast<unsigned>(grid), threads, smem, st>>>(
+            tm, wt, static_cast<__nv_bfloat16*>(y), n, h, w, c, pl);
     }
-#undef ISTVT_DW_LAUNCH
     count_launch();
     return launch_status();
 }

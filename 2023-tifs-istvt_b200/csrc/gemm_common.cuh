@@ -27,8 +27,6 @@ struct GemmParams {
     int kb_per_split; // every (tile, range) adds its partial product to the fp32 C with red.global (C pre-initialised)
     int mn_major;     // CTA-pair kernel: both operands are stored K-rows x MN-contiguous (A = dY [k, m], B = X [k, n]):
                       // the weight-gradient GEMM dW = dY^T X reads dY and X as they sit in HBM, no transposed copies
-    const void* a_ptr;  // CTA-pair kernel, K-major, no split: A base / row pitch (elements) for the L2 prefetch warp
-    int64_t lda;        // (nullptr = no prefetch)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -177,31 +177,6 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             }
         }
         __syncwarp();
-    } else if (warp == 3 && p.a_ptr != nullptr) {
-        // ===================== L2 prefetch of first-touch A rows (otherwise idle warp) =====================
-        // ncu (profiles/r3e): the ring is latency bound — producer AND issuer both wait (48 % / 63 % of their samples)
-        // with 5 x 32 KB in flight per CTA at 66 GB/s/SM, i.e. 2.4 us per TMA stage; 26 % of the L2 sectors miss (A is
-        // read from HBM exactly once, by the n_tiles clusters that share the m-block at the same time).  This warp pulls
-        // the A rows of the tile two steps ahead into L2 with plain prefetch.global.L2 (LSU path: a TMA prefetch in the
-        // producer's queue was measured slower, it holds TMA request slots for a DRAM round trip).  Only the cluster
-        // whose tile opens the m-block (n_blk == 0) prefetches it.
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        const int lines_per_row = (p.K * 2 + 127) / 128;
-        const uint8_t* a8 = static_cast<const uint8_t*>(p.a_ptr);
-        for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
-            mbar_wait(&tmem_full[acc], acc_phase);
-            const int64_t ahead = tile + 2 * static_cast<int64_t>(n_clusters);
-            if (ahead < total_tiles && ahead % n_tiles == 0) {
-                const int64_t m0 = (ahead / n_tiles) * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M;
-                for (int r = 0; r < GEMM_BLOCK_M && m0 + r < p.M; ++r) {
-                    const uint8_t* row = a8 + (m0 + r) * p.lda * 2;
-                    for (int l = lane; l < lines_per_row; l += 32)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + l * 128));
-                }
-            }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
     } else if (warp >= 4) {
         // ===================== epilogue (this CTA's 128 rows x 256 columns) =====================
         const int ew = warp - 4;
@@ -285,17 +260,15 @@ int launch_gemm_2cta(const void* a, int64_t lda, const void* w, int64_t ldw, con
         int rc = encode_tmap(&tm_b, w, ISTVT_BF16, 2, dims, strides, box, 3);
         if (rc != ISTVT_OK) return rc;
     }
-    GemmParams q = p;
-    q.a_ptr = a;
-    q.lda = lda;
-    return launch_gemm_2cta_maps(tm_a, tm_b, q, stream);
+    return launch_gemm_2cta_maps(tm_a, tm_b, p, stream);
 }
 
 static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmParams& p_in, cudaStream_t stream) {
     const GemmParams& p0 = p_in;
     // (A TMA L2 prefetch of the next m-block's A rows one tile ahead was measured SLOWER — layer GEMM sum 2.42 ->
     //  2.57 ms: the kernel is bound by L2->SM delivery, not by first-touch DRAM latency, and the prefetch requests
-    //  compete for the same L2 slices.  profiles/README.md r3a.)
+    //  compete for the same L2 slices.  profiles/README.md r3a.  A second attempt on the LSU path — an otherwise idle
+    //  warp issuing prefetch.global.L2 for the m-block two tiles ahead — was worse still: 2.48 -> 3.08 ms, r3g.)
     const int n_tiles = (p0.N + G2_BN - 1) / G2_BN;
     const int64_t m_tiles = (p0.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
     const int64_t total = m_tiles * n_tiles * (p0.split_k > 1 ? p0.split_k : 1);
@@ -308,12 +281,7 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
         const char* e = getenv("ISTVT_G2_EPI_WARPS");
         return e ? atoi(e) : 0;
     }();
-    static const int pf_env = []() {
-        const char* e = getenv("ISTVT_G2_PREFETCH");
-        return e ? atoi(e) : 0;
-    }();
-    GemmParams p = p_in;
-    if (!pf_env || p.mn_major || p.split_k > 1) p.a_ptr = nullptr;
+    const GemmParams& p = p_in;
     const bool plain = !p.c_f32 && p.residual == nullptr;
     const int ew = ew_env == 8 || ew_env == 16 ? ew_env : (plain ? 16 : 8);
     const unsigned grid = static_cast<unsigned>(2 * clusters);
