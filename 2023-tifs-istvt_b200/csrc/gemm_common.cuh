@@ -43,6 +43,7 @@ struct GemmParams {
 //   fp32 output (+ residual) : raw accumulators staged 32 columns at a time; bias / residual / store on full lines.
 // ------------------------------------------------------------------------------------------
 constexpr int EPI_SLAB_BYTES = 32 * 128;   // per epilogue warp
+constexpr int EPI_SLAB_PLAIN_BYTES = 32 * 64;   // what the bf16-output path uses of it
 constexpr int EPI_COLS = 64;               // accumulator columns per epilogue warp
 
 // Output rows handled by this lane in the transposed phase: row (i*4 + lane/8) of the warp's 32, i = 0..7.
@@ -72,9 +73,10 @@ __device__ __forceinline__ float epi_act(float v, int act) {
 // column already applied).  `after_tmem_reads()` is invoked once all TMEM reads of the call have completed.
 // PLAIN_BF16 = bf16 output without residual (compile-time: keeps each kernel instantiation small — the first
 // version inlined both paths twice and the 147 KB of SASS missed in the instruction cache).
-// `slab` is the warp's 4 KB staging area as a shared-space address.
+// `slab` is the warp's staging area as a shared-space address; `drow_lane` = destination row of the accumulator row
+// this lane owns (-1: not stored), `drow_t` = the same for the rows of the 8-lanes-per-row transposed phase.
 template <bool PLAIN_BF16, typename F>
-__device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t taddr, uint32_t slab,
+__device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t taddr, uint32_t slab, int drow_lane,
                                                  const int (&drow_t)[8], int n0, int lane, F after_tmem_reads) {
     const int cchunk = lane & 7;
     const int sw = lane & 7;
@@ -83,18 +85,25 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
         return;
     }
     if constexpr (PLAIN_BF16) {
-        // ---------------- bf16 output: math first, packed staging ----------------
-        const uint32_t wrow = slab + lane * 128;
+        // ---------------- bf16 output: math first, packed staging, 32 columns (64 B per row) at a time ----------------
+        // Only EPI_SLAB_PLAIN_BYTES (2 KB) of the slab are used: the CTA-pair kernel spends the other half of the
+        // former 4 KB slabs on a sixth ring stage (its TMA ring is latency bound, profiles/README.md r3e).
+        // 16-byte chunk q of row r sits at r*64 + ((q ^ ((r >> 1) & 3)) << 4): conflict-free for the row-owner writes
+        // (8 lanes per phase, 64-byte pitch) and for the transposed reads (4 lanes per row).
+        const uint32_t wrow = slab + lane * 64;
+        const int wsw = (lane >> 1) & 3;
+        const int cchunk4 = lane & 3;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             const int nb = n0 + hh * 32;
-            uint32_t r[32];
-            if (nb < p.N) {   // warp-uniform
-                tmem_ld_32x32b_x32(taddr + hh * 32, r);
-                tmem_ld_wait();
+            if (nb >= p.N) {   // warp-uniform: ragged last N tile
+                if (hh == 1) after_tmem_reads();
+                break;
             }
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + hh * 32, r);
+            tmem_ld_wait();
             if (hh == 1) after_tmem_reads();
-            if (nb >= p.N) break;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {     // 8 columns -> one 16-byte chunk
                 const int n = nb + g * 8;
@@ -109,23 +118,23 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = epi_act(v[j], p.act);
-                const int c = hh * 4 + g;
-                sts_u4(wrow + ((c ^ sw) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                sts_u4(wrow + ((g ^ wsw) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                        pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
             }
-        }
-        __syncwarp();
-        const int n = n0 + cchunk * 8;
-        if (n < p.N) {
-            __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C) + n;
+            __syncwarp();
+            const int n = nb + cchunk4 * 8;
+            if (n < p.N) {
+                __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C) + n;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = i * 4 + (lane >> 3);
-                const uint4 v = lds_u4(slab + row * 128 + ((cchunk ^ (row & 7)) << 4));
-                if (drow_t[i] >= 0) *reinterpret_cast<uint4*>(cbase + static_cast<int64_t>(drow_t[i]) * p.ldc) = v;
+                for (int i = 0; i < 4; ++i) {
+                    const int row = i * 8 + (lane >> 2);
+                    const uint4 v = lds_u4(slab + row * 64 + ((cchunk4 ^ ((row >> 1) & 3)) << 4));
+                    const int drow = __shfl_sync(0xffffffffu, drow_lane, row);
+                    if (drow >= 0) *reinterpret_cast<uint4*>(cbase + static_cast<int64_t>(drow) * p.ldc) = v;
+                }
             }
+            __syncwarp();   // the slab is rewritten by the next half
         }
-        __syncwarp();
     } else {
         // ---------------- fp32 output and/or residual: raw staging, 32 columns per pass ----------------
 #pragma unroll

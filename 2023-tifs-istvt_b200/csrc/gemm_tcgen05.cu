@@ -188,7 +188,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             uint64_t* te = &tmem_empty[acc];
-            gemm_epilogue_64<PLAIN_BF16>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, slab, drow_t,
+            gemm_epilogue_64<PLAIN_BF16>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, slab, drow_lane, drow_t,
                              n_blk * BN + col0, lane, [&]() {
                                  tc_fence_before();
                                  __syncwarp();

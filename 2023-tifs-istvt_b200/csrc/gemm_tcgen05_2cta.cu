@@ -22,26 +22,29 @@ constexpr int G2_BK = 64;                     // 128-byte swizzle atom
 constexpr int G2_A_BYTES = GEMM_BLOCK_M * G2_BK * 2;   // 16 KB
 constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;    // 16 KB
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-template <int EW> struct G2Cfg {
+template <int EW, bool PLAIN> struct G2Cfg {
     static constexpr int THREADS = 128 + EW * 32;
-    static constexpr int STAGES = EW == 16 ? 5 : 6;
+    static constexpr int SLAB = PLAIN ? EPI_SLAB_PLAIN_BYTES : EPI_SLAB_BYTES;
+    // 6 ring stages whenever they fit: 16 warps with the 2 KB bf16 slabs, or 8 warps with the 4 KB fp32 slabs
+    static constexpr int STAGES = (EW == 16 && !PLAIN) ? 5 : 6;
     static constexpr int PASSES = (G2_BN / EPI_COLS) / (EW / 4);   // 64-column passes per epilogue warp per tile
-    static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + EW * EPI_SLAB_BYTES + 1024 + 256;
+    static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + EW * SLAB + 1024 + 256;
 };
 constexpr int G2_TMEM_COLS = 512;             // 2 accumulator buffers x 256 fp32 columns
 
 template <int EW, bool PLAIN_BF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Cfg<EW>::THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Cfg<EW, PLAIN_BF16>::THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const GemmParams p) {
-    constexpr int G2_STAGES = G2Cfg<EW>::STAGES;
+    using Cfg = G2Cfg<EW, PLAIN_BF16>;
+    constexpr int G2_STAGES = Cfg::STAGES;
     constexpr int G2_EPI_WARPS = EW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
     uint8_t* smem_epi = smem + G2_STAGES * G2_STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + G2_EPI_WARPS * EPI_SLAB_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + G2_EPI_WARPS * Cfg::SLAB);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + G2_STAGES;
     uint64_t* tmem_full = bars + 2 * G2_STAGES;
@@ -181,9 +184,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         // ===================== epilogue (this CTA's 128 rows x 256 columns) =====================
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-        constexpr int PASSES = G2Cfg<EW>::PASSES;
+        constexpr int PASSES = Cfg::PASSES;
         const int colw = (ew >> 2) * (EPI_COLS * PASSES);   // first tile column of this warp
-        const uint32_t slab = smem_u32(smem_epi + ew * EPI_SLAB_BYTES);
+        const uint32_t slab = smem_u32(smem_epi + ew * Cfg::SLAB);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
@@ -201,7 +204,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll 1
             for (int ps = 0; ps < PASSES; ++ps) {
                 const int col0 = colw + ps * EPI_COLS;
-                gemm_epilogue_64<PLAIN_BF16>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * G2_BN + col0, slab, drow_t,
+                gemm_epilogue_64<PLAIN_BF16>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * G2_BN + col0, slab, drow_lane, drow_t,
                                  n_blk * G2_BN + col0, lane, [&]() {
                                      if (ps != PASSES - 1) return;
                                      // all TMEM reads of this warp for this accumulator are done: tell the leader's MMA warp
@@ -288,8 +291,8 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
 #define ISTVT_G2_LAUNCH(EWV, PL)                                                                                   \
     do {                                                                                                           \
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<EWV, PL>,                                   \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<EWV>::SMEM_BYTES)); \
-        gemm_tcgen05_2cta_kernel<EWV, PL><<<grid, G2Cfg<EWV>::THREADS, G2Cfg<EWV>::SMEM_BYTES, stream>>>(tm_a, tm_b, p); \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<EWV, PL>::SMEM_BYTES)); \
+        gemm_tcgen05_2cta_kernel<EWV, PL><<<grid, G2Cfg<EWV, PL>::THREADS, G2Cfg<EWV, PL>::SMEM_BYTES, stream>>>(tm_a, tm_b, p); \
     } while (0)
     if (ew == 16) {
         if (plain) ISTVT_G2_LAUNCH(16, true); else ISTVT_G2_LAUNCH(16, false);
