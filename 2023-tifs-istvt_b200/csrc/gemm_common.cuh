@@ -123,14 +123,15 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
             }
             __syncwarp();
             const int n = nb + cchunk4 * 8;
-            if (n < p.N) {
-                __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C) + n;
+            const bool n_ok = n < p.N;                 // lane-dependent on the ragged last N tile: shuffles stay outside
+            __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(p.C) + n;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int row = i * 8 + (lane >> 2);
+            for (int i = 0; i < 4; ++i) {
+                const int row = i * 8 + (lane >> 2);
+                const int drow = __shfl_sync(0xffffffffu, drow_lane, row);
+                if (n_ok && drow >= 0) {
                     const uint4 v = lds_u4(slab + row * 64 + ((cchunk4 ^ ((row >> 1) & 3)) << 4));
-                    const int drow = __shfl_sync(0xffffffffu, drow_lane, row);
-                    if (drow >= 0) *reinterpret_cast<uint4*>(cbase + static_cast<int64_t>(drow) * p.ldc) = v;
+                    *reinterpret_cast<uint4*>(cbase + static_cast<int64_t>(drow) * p.ldc) = v;
                 }
             }
             __syncwarp();   // the slab is rewritten by the next half
