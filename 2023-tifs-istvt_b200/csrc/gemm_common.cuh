@@ -196,6 +196,58 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
     }
 }
 
+// In-place fp32 residual update  C[m, n] += act(acc + bias)  (s_out / ff2 of the inference path, where the GEMM output
+// IS the residual stream): the warp stages 32 rows x 32 fp32 columns in its slab in the TMA SWIZZLE_128B layout and one
+// elected lane issues a TMA reduce-add of the box — the addition is done by the L2, so the residual never travels to
+// the SM.  The register-path epilogue above was the bottleneck of s_out (profiles/README.md r3i: 8 batches of 4
+// dependent 16-byte loads per lane and tile, 2 KB in flight per warp, 3.8 TB/s).  Rows >= M and columns >= N are
+// clipped by the tensor map.  `row0` = first of the warp's 32 consecutive output rows.
+template <typename F>
+__device__ __forceinline__ void gemm_epilogue_reduce_64(const GemmParams& p, const CUtensorMap* tm_c, uint32_t taddr,
+                                                        uint32_t slab, int row0, int n0, int lane, F after_tmem_reads) {
+    if (n0 >= p.N) {
+        after_tmem_reads();
+        return;
+    }
+    const uint32_t wrow = slab + lane * 128;
+    const int sw = lane & 7;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int nb = n0 + hh * 32;
+        if (nb >= p.N) {   // warp-uniform
+            if (hh == 1) after_tmem_reads();
+            break;
+        }
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + hh * 32, r);
+        tmem_ld_wait();
+        if (hh == 1) after_tmem_reads();
+        if (lane == 0) tma_store_wait_read0();     // the previous box has left the slab
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[4 * c + j]);
+            const int n = nb + c * 4;
+            if (p.bias != nullptr && n < p.N) {
+                const float4 b = ldg_nc_f4_ordered(p.bias + n);
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = epi_act(v[j], p.act);
+            sts_u4(wrow + ((c ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                   __float_as_uint(v[3]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_reduce_add_2d(tm_c, slab, nb, row0);
+            tma_store_commit();
+        }
+    }
+}
+
 // host: launch the CTA-pair kernel (gemm_tcgen05_2cta.cu) for a plain GEMM with N >= 256
 int launch_gemm_2cta(const void* a, int64_t lda, const void* w, int64_t ldw, const GemmParams& p, cudaStream_t stream);
 // MN-major operands (p.mn_major = 1): a = [K rows, M] pitch lda, w = [K rows, N] pitch ldw

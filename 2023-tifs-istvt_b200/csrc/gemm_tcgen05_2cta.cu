@@ -22,21 +22,25 @@ constexpr int G2_BK = 64;                     // 128-byte swizzle atom
 constexpr int G2_A_BYTES = GEMM_BLOCK_M * G2_BK * 2;   // 16 KB
 constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;    // 16 KB
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-template <int EW, bool PLAIN> struct G2Cfg {
+// epilogue modes: bf16 output without residual / generic (fp32 output, residual through registers, split-K) /
+// in-place fp32 residual update by TMA reduce-add
+constexpr int EPI_PLAIN = 0, EPI_GENERIC = 1, EPI_REDUCE = 2;
+template <int EW, int EPI> struct G2Cfg {
     static constexpr int THREADS = 128 + EW * 32;
-    static constexpr int SLAB = PLAIN ? EPI_SLAB_PLAIN_BYTES : EPI_SLAB_BYTES;
+    static constexpr int SLAB = EPI == EPI_PLAIN ? EPI_SLAB_PLAIN_BYTES : EPI_SLAB_BYTES;
     // 6 ring stages whenever they fit: 16 warps with the 2 KB bf16 slabs, or 8 warps with the 4 KB fp32 slabs
-    static constexpr int STAGES = (EW == 16 && !PLAIN) ? 5 : 6;
+    static constexpr int STAGES = (EW == 16 && EPI != EPI_PLAIN) ? 5 : 6;
     static constexpr int PASSES = (G2_BN / EPI_COLS) / (EW / 4);   // 64-column passes per epilogue warp per tile
     static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + EW * SLAB + 1024 + 256;
 };
 constexpr int G2_TMEM_COLS = 512;             // 2 accumulator buffers x 256 fp32 columns
 
-template <int EW, bool PLAIN_BF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Cfg<EW, PLAIN_BF16>::THREADS, 1)
+template <int EW, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Cfg<EW, EPI>::THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                         const GemmParams p) {
-    using Cfg = G2Cfg<EW, PLAIN_BF16>;
+                         const __grid_constant__ CUtensorMap tm_c, const GemmParams p) {
+    constexpr bool PLAIN_BF16 = EPI == EPI_PLAIN;
+    using Cfg = G2Cfg<EW, EPI>;
     constexpr int G2_STAGES = Cfg::STAGES;
     constexpr int G2_EPI_WARPS = EW;
     extern __shared__ uint8_t smem_raw[];
@@ -197,26 +201,35 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             int drow_t[8];
             const int drow_lane = m < p.M ? static_cast<int>(m) : -1;
             epilogue_rows(drow_lane, lane, drow_t);
-            if constexpr (!PLAIN_BF16) epilogue_prefetch_residual(p, drow_lane, n_blk * G2_BN + colw, EPI_COLS * PASSES);
+            if constexpr (EPI == EPI_GENERIC) epilogue_prefetch_residual(p, drow_lane, n_blk * G2_BN + colw, EPI_COLS * PASSES);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             uint64_t* te = &tmem_empty[acc];
 #pragma unroll 1
             for (int ps = 0; ps < PASSES; ++ps) {
                 const int col0 = colw + ps * EPI_COLS;
-                gemm_epilogue_64<PLAIN_BF16>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * G2_BN + col0, slab, drow_lane, drow_t,
-                                 n_blk * G2_BN + col0, lane, [&]() {
-                                     if (ps != PASSES - 1) return;
-                                     // all TMEM reads of this warp for this accumulator are done: tell the leader's MMA warp
-                                     tc_fence_before();
-                                     __syncwarp();
-                                     if (lane == 0) mbar_arrive_cluster(te, 0);
-                                 });
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * G2_BN + col0;
+                auto release = [&]() {
+                    if (ps != PASSES - 1) return;
+                    // all TMEM reads of this warp for this accumulator are done: tell the leader's MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(te, 0);
+                };
+                if constexpr (EPI == EPI_REDUCE)
+                    gemm_epilogue_reduce_64(p, &tm_c, taddr, slab,
+                                            static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32),
+                                            n_blk * G2_BN + col0, lane, release);
+                else
+                    gemm_epilogue_64<PLAIN_BF16>(p, taddr, slab, drow_lane, drow_t, n_blk * G2_BN + col0, lane, release);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
+    if constexpr (EPI == EPI_REDUCE) {
+        if (warp >= 4 && lane == 0) tma_store_wait0();     // reduce-adds issued by this lane have completed
+    }
     // No CTA may exit (or free TMEM) while its peer can still multicast-arrive on its barriers or read its smem.
     tc_fence_before();
     cluster_sync_all();
@@ -286,18 +299,34 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
     }();
     const GemmParams& p = p_in;
     const bool plain = !p.c_f32 && p.residual == nullptr;
-    const int ew = ew_env == 8 || ew_env == 16 ? ew_env : (plain ? 16 : 8);
+    // In-place fp32 residual update (inference s_out / ff2): the addition is done by the L2 through a TMA reduce-add.
+    // ISTVT_G2_REDUCE=0 keeps the register-path epilogue (A/B measurements).
+    static const bool reduce_env = []() { const char* e = getenv("ISTVT_G2_REDUCE"); return !e || atoi(e) != 0; }();
+    const bool reduce = reduce_env && p.c_f32 && p.residual != nullptr && p.residual == p.C && p.ldr == p.ldc &&
+                        p.split_k <= 1 && !p.mn_major && (p.ldc * 4) % 16 == 0;
+    CUtensorMap tm_c = tm_a;     // placeholder for the modes that do not use it
+    if (reduce) {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(p.ldc) * 4};
+        const uint32_t box[2] = {32, 32};      // 32 fp32 columns (128 B, SW128) x the warp's 32 rows
+        int rc = encode_tmap(&tm_c, p.C, ISTVT_F32, 2, dims, strides, box, 3);
+        if (rc != ISTVT_OK) return rc;
+    }
+    const int ew = reduce ? 16 : (ew_env == 8 || ew_env == 16 ? ew_env : (plain ? 16 : 8));
     const unsigned grid = static_cast<unsigned>(2 * clusters);
-#define ISTVT_G2_LAUNCH(EWV, PL)                                                                                   \
+#define ISTVT_G2_LAUNCH(EWV, EPIV)                                                                                 \
     do {                                                                                                           \
-        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<EWV, PL>,                                   \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<EWV, PL>::SMEM_BYTES)); \
-        gemm_tcgen05_2cta_kernel<EWV, PL><<<grid, G2Cfg<EWV, PL>::THREADS, G2Cfg<EWV, PL>::SMEM_BYTES, stream>>>(tm_a, tm_b, p); \
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<EWV, EPIV>,                                 \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<EWV, EPIV>::SMEM_BYTES)); \
+        gemm_tcgen05_2cta_kernel<EWV, EPIV><<<grid, G2Cfg<EWV, EPIV>::THREADS, G2Cfg<EWV, EPIV>::SMEM_BYTES, stream>>>(   \
+            tm_a, tm_b, tm_c, p);                                                                                  \
     } while (0)
-    if (ew == 16) {
-        if (plain) ISTVT_G2_LAUNCH(16, true); else ISTVT_G2_LAUNCH(16, false);
+    if (reduce) {
+        ISTVT_G2_LAUNCH(16, EPI_REDUCE);
+    } else if (ew == 16) {
+        if (plain) ISTVT_G2_LAUNCH(16, EPI_PLAIN); else ISTVT_G2_LAUNCH(16, EPI_GENERIC);
     } else {
-        if (plain) ISTVT_G2_LAUNCH(8, true); else ISTVT_G2_LAUNCH(8, false);
+        if (plain) ISTVT_G2_LAUNCH(8, EPI_PLAIN); else ISTVT_G2_LAUNCH(8, EPI_GENERIC);
     }
 #undef ISTVT_G2_LAUNCH
     count_launch();

@@ -311,7 +311,8 @@ def run_ours(args) -> int:
         roofline = None
         traffic, traffic_src = None, None
         try:   # DRAM bytes per GEMM launch from the committed ncu capture of this same command
-            with open(os.path.join(ROOT, "profiles", "r1v_gemm_traffic.json")) as f:
+            cands = sorted(n for n in os.listdir(os.path.join(ROOT, "profiles")) if n.endswith("_gemm_traffic.json"))
+            with open(os.path.join(ROOT, "profiles", cands[-1])) as f:      # newest round's capture
                 tj = json.load(f)
             traffic, traffic_src = tj["gemm_dram_bytes_per_launch"], tj["source"]
         except Exception:  # noqa: BLE001
