@@ -75,7 +75,9 @@ __device__ __forceinline__ float epi_act(float v, int act) {
 // version inlined both paths twice and the 147 KB of SASS missed in the instruction cache).
 // `slab` is the warp's staging area as a shared-space address; `drow_lane` = destination row of the accumulator row
 // this lane owns (-1: not stored), `drow_t` = the same for the rows of the 8-lanes-per-row transposed phase.
-template <bool PLAIN_BF16, typename F>
+// HALVES = 1 (bf16 path only): the warp owns 32 columns instead of 64 — twice the epilogue warps per tile for the
+// short-K GEMMs whose tile period is the epilogue's latency chain.
+template <bool PLAIN_BF16, int HALVES = 2, typename F>
 __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t taddr, uint32_t slab, int drow_lane,
                                                  const int (&drow_t)[8], int n0, int lane, F after_tmem_reads) {
     const int cchunk = lane & 7;
@@ -94,16 +96,16 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
         const int wsw = (lane >> 1) & 3;
         const int cchunk4 = lane & 3;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+        for (int hh = 0; hh < HALVES; ++hh) {
             const int nb = n0 + hh * 32;
             if (nb >= p.N) {   // warp-uniform: ragged last N tile
-                if (hh == 1) after_tmem_reads();
+                if (hh == HALVES - 1) after_tmem_reads();
                 break;
             }
             uint32_t r[32];
             tmem_ld_32x32b_x32(taddr + hh * 32, r);
             tmem_ld_wait();
-            if (hh == 1) after_tmem_reads();
+            if (hh == HALVES - 1) after_tmem_reads();
 #pragma unroll
             for (int g = 0; g < 4; ++g) {     // 8 columns -> one 16-byte chunk
                 const int n = nb + g * 8;

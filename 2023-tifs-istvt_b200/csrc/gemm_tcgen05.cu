@@ -19,9 +19,14 @@
 namespace istvt {
 
 
-template <int BN, int BK>
+template <int BN, int BK, bool PLAIN>
 struct GemmCfg {
-    static constexpr int EPI_WARPS = 4 * (BN / EPI_COLS);   // lane quadrant x 64-column group
+    // epilogue warp = lane quadrant x column group.  bf16 output: 32-column groups (every GEMM on this kernel has
+    // K <= 256 or is the 9-tap conv: the tile period was the epilogue's latency chain — 2.5 us per 128 x 128 tile with
+    // 64-column warps, profiles/README.md r3k — so the tile is spread over twice the warps); fp32 / residual: 64.
+    static constexpr int WARP_COLS = PLAIN ? 32 : EPI_COLS;
+    static constexpr int EPI_WARPS = 4 * (BN / WARP_COLS);
+    static constexpr int SLAB = PLAIN ? EPI_SLAB_PLAIN_BYTES : EPI_SLAB_BYTES;
     static constexpr int THREADS = 128 + EPI_WARPS * 32;
     static constexpr int A_BYTES = GEMM_BLOCK_M * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
@@ -30,16 +35,16 @@ struct GemmCfg {
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * SLAB + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr uint32_t SWZ = (BK == 64) ? SWZ_128B : SWZ_64B;
     static constexpr uint32_t SBO = 8 * BK * 2;  // bytes between 8-row groups of a K-major swizzled tile
 };
 
 template <int BN, int BK, bool PLAIN_BF16>
-__global__ void __launch_bounds__(GemmCfg<BN, BK>::THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<BN, BK, PLAIN_BF16>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                     const GemmParams p) {
-    using Cfg = GemmCfg<BN, BK>;
+    using Cfg = GemmCfg<BN, BK, PLAIN_BF16>;
     constexpr int STAGES = Cfg::STAGES;
 
     extern __shared__ uint8_t smem_raw[];
@@ -48,7 +53,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
     uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_WARPS * EPI_SLAB_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_WARPS * Cfg::SLAB);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
     uint64_t* tmem_full = bars + 2 * STAGES;
@@ -160,8 +165,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         // ===================== epilogue =====================
         const int ew = warp - 4;
         const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-        const int col0 = (ew >> 2) * EPI_COLS;
-        const uint32_t slab = smem_u32(smem_epi + ew * EPI_SLAB_BYTES);
+        const int col0 = (ew >> 2) * Cfg::WARP_COLS;
+        const uint32_t slab = smem_u32(smem_epi + ew * Cfg::SLAB);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -184,11 +189,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             int drow_t[8];
             const int drow_lane = row_ok ? static_cast<int>(drow) : -1;
             epilogue_rows(drow_lane, lane, drow_t);
-            if constexpr (!PLAIN_BF16) epilogue_prefetch_residual(p, drow_lane, n_blk * BN + col0, EPI_COLS);
+            if constexpr (!PLAIN_BF16) epilogue_prefetch_residual(p, drow_lane, n_blk * BN + col0, Cfg::WARP_COLS);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             uint64_t* te = &tmem_empty[acc];
-            gemm_epilogue_64<PLAIN_BF16>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, slab, drow_lane, drow_t,
+            gemm_epilogue_64<PLAIN_BF16, PLAIN_BF16 ? 1 : 2>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, slab, drow_lane, drow_t,
                              n_blk * BN + col0, lane, [&]() {
                                  tc_fence_before();
                                  __syncwarp();
@@ -208,17 +213,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 
 template <int BN, int BK>
 static int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, BK>;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int64_t m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
     const int64_t total = m_tiles * n_tiles;
     int grid = sm_count();
     if (total < grid) grid = static_cast<int>(total);
     if (!p.c_f32 && p.residual == nullptr) {
+        using Cfg = GemmCfg<BN, BK, true>;
         auto kern = gemm_tcgen05_kernel<BN, BK, true>;
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
     } else {
+        using Cfg = GemmCfg<BN, BK, false>;
         auto kern = gemm_tcgen05_kernel<BN, BK, false>;
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);

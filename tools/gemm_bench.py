@@ -31,6 +31,43 @@ SHAPES = {
 }
 
 
+# name: (pixels per frame, N, K) — 1x1 convolutions + folded BN (+ ReLU) as GEMMs over NHWC pixels
+ENTRY = {
+    "b1_pw1": (147 * 147, 128, 64), "b1_pw2": (147 * 147, 128, 128), "b1_skip": (74 * 74, 128, 64),
+    "b2_pw1": (74 * 74, 256, 128), "b2_pw2": (74 * 74, 256, 256), "b2_skip": (37 * 37, 256, 128),
+    "b3_pw1": (37 * 37, 728, 256), "b3_pw2": (37 * 37, 728, 728), "b3_skip": (19 * 19, 728, 256),
+}
+
+
+def entry_flow(args) -> None:
+    dev = "cuda"
+    frames = 384
+    tot_ms = tot_by = 0.0
+    for name, (px, n, k) in ENTRY.items():
+        m = frames * px
+        a = [torch.randn(m, k, device=dev).to(torch.bfloat16) for _ in range(2)]
+        w = (torch.randn(n, k, device=dev) * k ** -0.5).to(torch.bfloat16)
+        b = torch.randn(n, device=dev)
+        outs = [torch.empty(m, n, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+        for i in range(3):
+            ops.gemm(a[i % 2], w, bias=b, act=1, out=outs[i % 2])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.iters):
+            ops.gemm(a[i % 2], w, bias=b, act=1, out=outs[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        by = (m * k + m * n + n * k) * 2
+        tot_ms += ms
+        tot_by += by
+        print(f"{name:8s} M={m:8d} N={n:4d} K={k:4d} {ms:7.3f} ms  {2.0 * m * n * k / ms / 1e9:7.1f} TFLOP/s  "
+              f"{by / ms / 1e6:6.0f} GB/s", flush=True)
+        del a, outs
+    print(f"entry-flow GEMM sum {tot_ms:7.3f} ms  {tot_by / tot_ms / 1e6:6.0f} GB/s")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
@@ -39,7 +76,11 @@ def main() -> None:
     ap.add_argument("--custom", default="", help="extra shapes 'N,K;N,K' (bf16 out, no bias)")
     ap.add_argument("--cublas", action="store_true", help="also time torch.matmul (cuBLAS) on the same operands: a "
                                                           "yardstick for what the shape can reach, not a product path")
+    ap.add_argument("--entry", action="store_true", help="the 9 pointwise / skip GEMMs of the Xception entry flow at "
+                                                         "the C2 size (384 frames) instead of the transformer's")
     args = ap.parse_args()
+    if args.entry:
+        return entry_flow(args)
     for i, nk in enumerate(filter(None, args.custom.split(";"))):
         n_, k_ = (int(v) for v in nk.split(","))
         SHAPES[f"c{n_}x{k_}"] = (n_, k_, False, False, 0, torch.bfloat16)
