@@ -27,8 +27,6 @@ struct GemmParams {
     int kb_per_split; // every (tile, range) adds its partial product to the fp32 C with red.global (C pre-initialised)
     int mn_major;     // CTA-pair kernel: both operands are stored K-rows x MN-contiguous (A = dY [k, m], B = X [k, n]):
                       // the weight-gradient GEMM dW = dY^T X reads dY and X as they sit in HBM, no transposed copies
-    int b_resident;   // 1-CTA kernel: one N tile and <= STAGES k-blocks (conv2, block-1 pointwise): the weight k-blocks
-                      // are loaded into the ring's B slots ONCE per CTA and every tile streams only A
 };
 
 // ------------------------------------------------------------------------------------------

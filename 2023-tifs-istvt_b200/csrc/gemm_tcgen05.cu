@@ -16,8 +16,6 @@
 // input's W_in-wide grid; the epilogue drops the two junk columns/rows and compacts the row index).
 #include "gemm_common.cuh"
 
-#include <stdlib.h>
-
 namespace istvt {
 
 
@@ -35,11 +33,9 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BUDGET = 192 * 1024;
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
-    // up to 16 stages: the 9-tap conv has 12 KB stages (K = 32 per tap) and its ring is latency bound — with the
-    // former cap of 8 it ran at one k-block per 0.25 us (8 stages / ~2 us TMA latency), profiles/README.md r3n
-    static constexpr int STAGES = STAGES_RAW > 16 ? 16 : STAGES_RAW;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * SLAB + 1024 /*align slack*/ + 512 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * SLAB + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr uint32_t SWZ = (BK == 64) ? SWZ_128B : SWZ_64B;
     static constexpr uint32_t SBO = 8 * BK * 2;  // bytes between 8-row groups of a K-major swizzled tile
 };
@@ -63,7 +59,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    uint64_t* b_full = bars + 2 * STAGES + 5;     // resident-B mode: all weight k-blocks have landed
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -87,7 +82,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], Cfg::EPI_WARPS);
         }
-        mbar_init(b_full, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -104,15 +98,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            if (p.b_resident) {
-                // the TMA unit works per box row (64-128 B each): with 1-9 tiny k-blocks per tile the weight rows were
-                // a third to a half of all requests.  k-block j of W lives in B slot j for the whole kernel.
-                mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(num_kb) * Cfg::B_BYTES);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int tap = kb / kb_per_tap;
-                    tma_load_2d(smem_b + kb * Cfg::B_BYTES, &tm_b, b_full, tap * p.K + (kb - tap * kb_per_tap) * BK, 0);
-                }
-            }
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int64_t m_blk = tile / n_tiles;
                 const int n_blk = static_cast<int>(tile % n_tiles);
@@ -123,10 +108,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const int tap = kb / kb_per_tap;
                     const int kcol = (kb - tap * kb_per_tap) * BK;
                     const int64_t shift = (p.taps == 1) ? 0 : (int64_t)(tap / 3) * p.conv_w_in + (tap % 3);
-                    mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tm_a, &full_bar[stage], kcol, static_cast<int>(m0 + shift));
-                    if (!p.b_resident)
-                        tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tm_b, &full_bar[stage], tap * p.K + kcol, n0);
+                    tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tm_b, &full_bar[stage], tap * p.K + kcol, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -145,10 +129,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            if (p.b_resident) {
-                mbar_wait(b_full, 0);
-                tc_fence_after();
-            }
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_blk = static_cast<int>(tile % n_tiles);
                 int n_eff = p.N - n_blk * BN;
@@ -162,7 +142,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     mbar_wait_hot(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t a_desc = desc_hi | (a_field0 + stage * (Cfg::A_BYTES >> 4));
-                    const uint64_t b_desc = desc_hi | (b_field0 + (p.b_resident ? kb : stage) * (Cfg::B_BYTES >> 4));
+                    const uint64_t b_desc = desc_hi | (b_field0 + stage * (Cfg::B_BYTES >> 4));
                     const bool tap_end = (++kb_in_tap == kb_per_tap);
                     if (tap_end) kb_in_tap = 0;
                     if (!tap_end || last_steps == KSTEPS) {
@@ -238,21 +218,16 @@ static int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const G
     const int64_t total = m_tiles * n_tiles;
     int grid = sm_count();
     if (total < grid) grid = static_cast<int>(total);
-    static const bool bres_env = []() { const char* e = getenv("ISTVT_G1_BRESIDENT"); return !e || atoi(e) != 0; }();
-    const int num_kb = ((p.K + BK - 1) / BK) * p.taps;
-    GemmParams q = p;
     if (!p.c_f32 && p.residual == nullptr) {
         using Cfg = GemmCfg<BN, BK, true>;
-        q.b_resident = (bres_env && n_tiles == 1 && num_kb <= Cfg::STAGES) ? 1 : 0;
         auto kern = gemm_tcgen05_kernel<BN, BK, true>;
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, q);
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
     } else {
         using Cfg = GemmCfg<BN, BK, false>;
-        q.b_resident = (bres_env && n_tiles == 1 && num_kb <= Cfg::STAGES) ? 1 : 0;
         auto kern = gemm_tcgen05_kernel<BN, BK, false>;
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, q);
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
     }
     count_launch();
     return launch_status();
