@@ -117,11 +117,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def use_all_host_threads() -> int:
+    """The CPU legs use every host core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which would silently turn the reference arm into a single-thread run; torch.set_num_threads overrides it."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_oracle_clips_per_s(batch: int, frames: int, budget_s: float, min_iters: int = 2):
     """Reference algorithm on the host cores (oracle port), fp32, eval, no_grad (SURVEY.md §8d CPU baseline)."""
     import torch
     from oracle import istvt_oracle as O
     pkg = importlib.import_module(PKG)
+    use_all_host_threads()
     torch.manual_seed(0)
     model = pkg.XceptionVidTr(num_frames=frames).eval()
     sd = {k: v.detach() for k, v in model.state_dict().items()}
@@ -147,6 +160,7 @@ def run_reference(args) -> int:
     import torch
     from oracle import istvt_oracle as O
     pkg = importlib.import_module(PKG)
+    use_all_host_threads()
     torch.manual_seed(0)
     model = pkg.XceptionVidTr(num_frames=args.frames).eval()
     sd = {k: v.detach() for k, v in model.state_dict().items()}
