@@ -11,6 +11,7 @@
 #include "simt_util.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace istvt {
 
@@ -143,6 +144,57 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
         atomicAdd(dgamma + i, s_acc[i]);
         atomicAdd(dbeta + i, s_acc[c + i]);
+    }
+}
+
+// dx, row-loop form: thread = (row lane, 8-channel group) with the per-channel coefficients in registers, two rows in
+// flight.  dx = sc*dz + B*x + C with B = -sc*dgamma*rstd/m, C = -sc*dbeta/m - B*mean (the same expression as below,
+// regrouped).  The flat form below re-loaded six 32-byte parameter vectors per 16-byte data vector: 12 of its 15
+// load instructions were parameters, and it ran at ~3 TB/s.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const float* __restrict__ dgamma, const float* __restrict__ dbeta, bf16* __restrict__ dx,
+                         int64_t m, int c, float inv_m, int relu) {
+    const ChanLayout L(c);
+    if (!L.active) return;
+    float sc[8], sh[8], cb[8], cc[8];
+    {
+        float mu[8], rs[8], dg[8], db[8];
+        load8(scale + L.cg * 8, sc); load8(shift + L.cg * 8, sh);
+        load8(mean + L.cg * 8, mu);  load8(rstd + L.cg * 8, rs);
+        load8(dgamma + L.cg * 8, dg); load8(dbeta + L.cg * 8, db);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            cb[e] = -sc[e] * dg[e] * rs[e] * inv_m;
+            cc[e] = -sc[e] * db[e] * inv_m - cb[e] * mu[e];
+        }
+    }
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * L.lanes;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * L.lanes + L.rl; r < m; r += 2 * stride) {
+        const int64_t r1 = r + stride;
+        const bool two = r1 < m;
+        float v0[8], d0[8], v1[8], d1[8];
+        load8(x + r * c + L.cg * 8, v0);
+        load8(dy + r * c + L.cg * 8, d0);
+        if (two) {
+            load8(x + r1 * c + L.cg * 8, v1);
+            load8(dy + r1 * c + L.cg * 8, d1);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float dz = (relu && fmaf(v0[e], sc[e], sh[e]) <= 0.f) ? 0.f : d0[e];
+            d0[e] = fmaf(sc[e], dz, fmaf(cb[e], v0[e], cc[e]));
+        }
+        store8(dx + r * c + L.cg * 8, d0);
+        if (two) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float dz = (relu && fmaf(v1[e], sc[e], sh[e]) <= 0.f) ? 0.f : d1[e];
+                d1[e] = fmaf(sc[e], dz, fmaf(cb[e], v1[e], cc[e]));
+            }
+            store8(dx + r1 * c + L.cg * 8, d1);
+        }
     }
 }
 
@@ -583,10 +635,23 @@ extern "C" int istvt_bn_bwd(const void* dy, const void* x, const float* scale, c
     bn_bwd_reduce_kernel<<<static_cast<unsigned>(blocks), chan_threads(c), 2 * c * sizeof(float), st>>>(
         static_cast<const bf16*>(dy), static_cast<const bf16*>(x), scale, shift, mean, rstd, dgamma, dbeta, m, c, relu);
     count_launch();
-    const int64_t n8 = m * (c / 8);
-    bn_bwd_apply_kernel<<<nblk2(n8, 256), 256, 0, st>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), scale,
-                                                        shift, mean, rstd, dgamma, dbeta, static_cast<bf16*>(dx), n8,
-                                                        c / 8, 1.0f / static_cast<float>(m), relu);
+    // ISTVT_BN_FLAT=1: the flat one-vector-per-thread apply kernel (A/B measurements)
+    static const bool flat = []() { const char* e = getenv("ISTVT_BN_FLAT"); return e && atoi(e) != 0; }();
+    if (flat) {
+        const int64_t n8 = m * (c / 8);
+        bn_bwd_apply_kernel<<<nblk2(n8, 256), 256, 0, st>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), scale,
+                                                            shift, mean, rstd, dgamma, dbeta, static_cast<bf16*>(dx), n8,
+                                                            c / 8, 1.0f / static_cast<float>(m), relu);
+    } else {
+        const int threads = chan_threads(c);
+        const int lanes = (256 / (c / 8)) < 1 ? 1 : 256 / (c / 8);
+        int64_t ablocks = (m + 4 * lanes - 1) / (4 * lanes);          // >= 4 rows per thread
+        const int64_t acap = static_cast<int64_t>(sm_count()) * 16;
+        if (ablocks > acap) ablocks = acap;
+        bn_bwd_apply_rows_kernel<<<static_cast<unsigned>(ablocks), threads, 0, st>>>(
+            static_cast<const bf16*>(dy), static_cast<const bf16*>(x), scale, shift, mean, rstd, dgamma, dbeta,
+            static_cast<bf16*>(dx), m, c, 1.0f / static_cast<float>(m), relu);
+    }
     count_launch();
     return launch_status();
 }
