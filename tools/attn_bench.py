@@ -35,6 +35,7 @@ def main() -> None:
     ap.add_argument("--clips", type=int, default=64)
     ap.add_argument("--frames", type=int, default=6)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--bwd", action="store_true", help="also time the spatial-attention backward (training)")
     args = ap.parse_args()
     b, f, p, heads = args.clips, args.frames + 1, 362, 8
     dev = "cuda"
@@ -48,6 +49,12 @@ def main() -> None:
     fl = 4.0 * b * f * heads * p * p * 64
     print(f"attn_spatial  {b * f} frames x {p} tokens  {ms:7.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s  "
           f"{(qkvs[0].numel() * 2 + b * f * p * 512 * 2) / ms / 1e6:7.0f} GB/s", flush=True)
+    if args.bwd:
+        o, lse = ops.attn_spatial_lse(qkvs[0], b * f, p, heads, 0.125)
+        dout = torch.randn_like(o)
+        scratch = torch.empty(b * f * p, 512, dtype=torch.float32, device=dev)
+        ms = timed(lambda: ops.attn_spatial_bwd(qkvs[0], o, dout, lse, b * f, p, heads, 0.125, scratch=scratch), args.iters)
+        print(f"attn_spatial_bwd {b * f} frames x {p} tokens  {ms:7.3f} ms  {2.5 * fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
     qk = torch.randn(b * f * p, 1024, device=dev).to(torch.bfloat16)
     v = torch.randn(b * f * p, 512, device=dev).to(torch.bfloat16)
     ms = timed(lambda: ops.attn_temporal(qk, v, b, f, p, heads, 0.125), args.iters)
