@@ -37,7 +37,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--cudart", "static",
-]
+] + os.environ.get("ISTVT_BUILD_DEFS", "").split()      # e.g. -DISTVT_GEMM_TRACE for tools/gemm_trace.py (debug only)
 
 
 def _nvcc() -> str:

@@ -17,6 +17,25 @@
 
 namespace istvt {
 
+// Debug timeline (compiled only with -DISTVT_GEMM_TRACE, see tools/gemm_trace.py): cluster 0 records globaltimer
+// stamps of its first tiles — [tile][0] producer: first TMA of the tile issued, [1] last TMA issued, [2] issuer: accumulator
+// free, [3] first k-block landed, [4] last MMA + commits issued, [5] epilogue warp 4: tmem_full seen, [6] its TMEM reads
+// done (arrive on tmem_empty), [7] its last store issued.
+#ifdef ISTVT_GEMM_TRACE
+__device__ unsigned long long* g_gemm_trace = nullptr;
+constexpr int TRACE_TILES = 24;
+__device__ __forceinline__ void trace_stamp(bool on, int tile_it, int slot) {
+    if (on && tile_it < TRACE_TILES && g_gemm_trace != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_gemm_trace[tile_it * 8 + slot] = t;
+    }
+}
+#define ISTVT_TRACE(on, it, slot) trace_stamp(on, it, slot)
+#else
+#define ISTVT_TRACE(on, it, slot) ((void)0)
+#endif
+
 constexpr int G2_BN = 256;                    // cluster tile N (UMMA N), 128 W rows staged per CTA
 constexpr int G2_BK = 64;                     // 128-byte swizzle atom
 constexpr int G2_A_BYTES = GEMM_BLOCK_M * G2_BK * 2;   // 16 KB
@@ -34,6 +53,38 @@ template <int EW, int EPI> struct G2Cfg {
     static constexpr int SMEM_BYTES = STAGES * G2_STAGE_BYTES + EW * SLAB + 1024 + 256;
 };
 constexpr int G2_TMEM_COLS = 512;             // 2 accumulator buffers x 256 fp32 columns
+
+// Static tile schedule of one cluster, tile = ks * (m_tiles * n_tiles) + m_blk * n_tiles + n_blk, advanced by the
+// cluster count with 32-bit adds.  The first version recomputed (ks, m_blk, n_blk) from the 64-bit tile index with two
+// 64-bit divisions per tile in every role: on the single MMA-issuing thread that was 0.57 us between the last MMA of
+// one tile and the first of the next — 9 % of a K = 728 tile (tools/gemm_trace.py, profiles/README.md r3u).
+struct TileIter {
+    int ks, m_blk, n_blk;          // current tile
+    int s_ks, s_m, s_n;            // decomposition of the step (number of clusters)
+    int m_tiles, n_tiles;
+    int64_t tile, total, step;
+    __device__ __forceinline__ TileIter(int64_t start, int64_t step_, int m_tiles_, int n_tiles_, int64_t total_)
+        : m_tiles(m_tiles_), n_tiles(n_tiles_), tile(start), total(total_), step(step_) {
+        const int64_t mn = static_cast<int64_t>(m_tiles) * n_tiles;
+        ks = static_cast<int>(start / mn);
+        const int64_t r = start - ks * mn;
+        m_blk = static_cast<int>(r / n_tiles);
+        n_blk = static_cast<int>(r - static_cast<int64_t>(m_blk) * n_tiles);
+        s_ks = static_cast<int>(step / mn);
+        const int64_t sr = step - s_ks * mn;
+        s_m = static_cast<int>(sr / n_tiles);
+        s_n = static_cast<int>(sr - static_cast<int64_t>(s_m) * n_tiles);
+    }
+    __device__ __forceinline__ bool valid() const { return tile < total; }
+    __device__ __forceinline__ void next() {
+        tile += step;
+        n_blk += s_n;
+        if (n_blk >= n_tiles) { n_blk -= n_tiles; ++m_blk; }
+        m_blk += s_m;
+        if (m_blk >= m_tiles) { m_blk -= m_tiles; ++ks; }
+        ks += s_ks;
+    }
+};
 
 template <int EW, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Cfg<EW, EPI>::THREADS, 1)
@@ -63,10 +114,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 
     const int num_kb = (p.K + G2_BK - 1) / G2_BK;
     const int n_tiles = (p.N + G2_BN - 1) / G2_BN;
-    const int64_t m_tiles = (p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M);
+    const int m_tiles = static_cast<int>((p.M + 2 * GEMM_BLOCK_M - 1) / (2 * GEMM_BLOCK_M));
     const int splits = p.split_k > 1 ? p.split_k : 1;
     const int kb_per = p.split_k > 1 ? p.kb_per_split : num_kb;
-    const int64_t mn_tiles = m_tiles * n_tiles;
+    const int64_t mn_tiles = static_cast<int64_t>(m_tiles) * n_tiles;
     const int64_t total_tiles = mn_tiles * splits;     // tile = split * mn_tiles + (m_blk * n_tiles + n_blk)
 
     if (warp == 0 && lane == 0) {
@@ -104,16 +155,17 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
-                const int ks = static_cast<int>(tile / mn_tiles);
-                const int64_t mn = tile - ks * mn_tiles;
-                const int64_t m_blk = mn / n_tiles;
-                const int n_blk = static_cast<int>(mn % n_tiles);
-                const int m0 = static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M);
+            [[maybe_unused]] int trace_it = 0;
+            for (TileIter ti(cluster, n_clusters, m_tiles, n_tiles, total_tiles); ti.valid(); ti.next(), ++trace_it) {
+                const int ks = ti.ks;
+                const int n_blk = ti.n_blk;
+                const int m0 = ti.m_blk * (2 * GEMM_BLOCK_M) + static_cast<int>(rank) * GEMM_BLOCK_M;
                 const int n0 = n_blk * G2_BN + static_cast<int>(rank) * (tile_n_eff(n_blk) >> 1);
                 const int kb_end = (ks + 1) * kb_per < num_kb ? (ks + 1) * kb_per : num_kb;
                 for (int kb = ks * kb_per; kb < kb_end; ++kb) {
                     mbar_wait_hot(&empty_bar[stage], phase ^ 1);
+                    if (kb == ks * kb_per) ISTVT_TRACE(cluster == 0 && rank == 0, trace_it, 0);
+                    if (kb == kb_end - 1) ISTVT_TRACE(cluster == 0 && rank == 0, trace_it, 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
                     if (!p.mn_major) {
                         tma_load_2d_2cta(smem_a + stage * G2_A_BYTES, &tm_a, &full_bar[stage], kb * G2_BK, m0);
@@ -149,13 +201,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
-                const int ks = static_cast<int>(tile / mn_tiles);
-                const int n_blk = static_cast<int>((tile - ks * mn_tiles) % n_tiles);
+            [[maybe_unused]] int trace_it = 0;
+            for (TileIter ti(cluster, n_clusters, m_tiles, n_tiles, total_tiles); ti.valid(); ti.next(), ++trace_it) {
+                const int ks = ti.ks;
+                const int n_blk = ti.n_blk;
                 const uint32_t mnm = p.mn_major ? 1u : 0u;
                 const uint32_t idesc = make_idesc_bf16(2 * GEMM_BLOCK_M, static_cast<uint32_t>(tile_n_eff(n_blk)), mnm, mnm);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
+                ISTVT_TRACE(cluster == 0, trace_it, 2);
                 const uint32_t d_tmem = tmem_base + acc * G2_BN;
                 const int kb_begin = ks * kb_per;
                 const int kb_end = (ks + 1) * kb_per < num_kb ? (ks + 1) * kb_per : num_kb;
@@ -163,6 +217,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait_hot(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (kb == kb_begin) ISTVT_TRACE(cluster == 0, trace_it, 3);
                     const uint64_t a_desc = desc_hi | (a_field0 + stage * (G2_A_BYTES >> 4));
                     const uint64_t b_desc = desc_hi | (b_field0 + stage * (G2_B_BYTES >> 4));
                     if (kb != kb_end - 1) {
@@ -177,6 +232,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                                              (kb != kb_begin || k != 0) ? 1u : 0u);
                         umma_commit_2cta(&empty_bar[stage], 3);
                         umma_commit_2cta(&tmem_full[acc], 3);                    // accumulator ready in both CTAs
+                        ISTVT_TRACE(cluster == 0, trace_it, 4);
                     }
                     if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -193,17 +249,19 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         const uint32_t slab = smem_u32(smem_epi + ew * Cfg::SLAB);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int64_t tile = cluster; tile < total_tiles; tile += n_clusters) {
-            const int64_t mn = tile % mn_tiles;
-            const int64_t m_blk = mn / n_tiles;
-            const int n_blk = static_cast<int>(mn % n_tiles);
-            const int64_t m = m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32 + lane;
+        [[maybe_unused]] int trace_it = 0;
+        [[maybe_unused]] const bool tracer = cluster == 0 && rank == 0 && ew == 0 && lane == 0;
+        for (TileIter ti(cluster, n_clusters, m_tiles, n_tiles, total_tiles); ti.valid(); ti.next(), ++trace_it) {
+            const int m_blk = ti.m_blk;
+            const int n_blk = ti.n_blk;
+            const int64_t m = static_cast<int64_t>(m_blk) * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32 + lane;
             int drow_t[8];
             const int drow_lane = m < p.M ? static_cast<int>(m) : -1;
             epilogue_rows(drow_lane, lane, drow_t);
             if constexpr (EPI == EPI_GENERIC) epilogue_prefetch_residual(p, drow_lane, n_blk * G2_BN + colw, EPI_COLS * PASSES);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
+            ISTVT_TRACE(tracer, trace_it, 5);
             uint64_t* te = &tmem_empty[acc];
 #pragma unroll 1
             for (int ps = 0; ps < PASSES; ++ps) {
@@ -215,6 +273,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(te, 0);
+                    ISTVT_TRACE(tracer, trace_it, 6);
                 };
                 if constexpr (EPI == EPI_REDUCE)
                     gemm_epilogue_reduce_64(p, &tm_c, taddr, slab,
@@ -223,6 +282,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                 else
                     gemm_epilogue_64<PLAIN_BF16>(p, taddr, slab, drow_lane, drow_t, n_blk * G2_BN + col0, lane, release);
             }
+            ISTVT_TRACE(tracer, trace_it, 7);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -334,3 +394,9 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
 }
 
 }  // namespace istvt
+
+#ifdef ISTVT_GEMM_TRACE
+extern "C" int istvt_debug_gemm_trace(unsigned long long* buf) {   // debug builds only; not part of the ABI header
+    return static_cast<int>(cudaMemcpyToSymbol(istvt::g_gemm_trace, &buf, sizeof(buf)));
+}
+#endif
