@@ -27,6 +27,9 @@ struct GemmParams {
     int kb_per_split; // every (tile, range) adds its partial product to the fp32 C with red.global (C pre-initialised)
     int mn_major;     // CTA-pair kernel: both operands are stored K-rows x MN-contiguous (A = dY [k, m], B = X [k, n]):
                       // the weight-gradient GEMM dW = dY^T X reads dY and X as they sit in HBM, no transposed copies
+#ifdef ISTVT_GEMM_TRACE
+    int trace_no_tma; // debug builds only (tools/gemm_trace.py)
+#endif
 };
 
 // ------------------------------------------------------------------------------------------

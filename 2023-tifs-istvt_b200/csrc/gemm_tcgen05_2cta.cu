@@ -166,6 +166,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                     mbar_wait_hot(&empty_bar[stage], phase ^ 1);
                     if (kb == ks * kb_per) ISTVT_TRACE(cluster == 0 && rank == 0, trace_it, 0);
                     if (kb == kb_end - 1) ISTVT_TRACE(cluster == 0 && rank == 0, trace_it, 1);
+#ifdef ISTVT_GEMM_TRACE
+                    // experiment (results are garbage): after the ring's first fill, signal the slots full WITHOUT loading,
+                    // so that the MMAs re-read stale shared memory with no concurrent TMA fills (ISTVT_TRACE_NOTMA=1)
+                    if (p.trace_no_tma && (trace_it > 0 || kb >= G2_STAGES)) {
+                        if (rank == 0) mbar_arrive(&full_bar[stage]);
+                        if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+#endif
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
                     if (!p.mn_major) {
                         tma_load_2d_2cta(smem_a + stage * G2_A_BYTES, &tm_a, &full_bar[stage], kb * G2_BK, m0);
@@ -357,7 +366,15 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
         const char* e = getenv("ISTVT_G2_EPI_WARPS");
         return e ? atoi(e) : 0;
     }();
+#ifdef ISTVT_GEMM_TRACE
+    GemmParams p = p_in;
+    {
+        const char* e = getenv("ISTVT_TRACE_NOTMA");
+        p.trace_no_tma = e && atoi(e) != 0;
+    }
+#else
     const GemmParams& p = p_in;
+#endif
     const bool plain = !p.c_f32 && p.residual == nullptr;
     // In-place fp32 residual update (inference s_out / ff2): the addition is done by the L2 through a TMA reduce-add.
     // ISTVT_G2_REDUCE=0 keeps the register-path epilogue (A/B measurements).
