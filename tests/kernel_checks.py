@@ -363,6 +363,38 @@ def check_attn_spatial_bf16():
     return out
 
 
+def check_attn_spatial_spiky():
+    """The production kernel's softmax stabiliser is the maximum over a SAMPLE of the keys (columns 0-7 of every
+    32-column block), which is exact as long as exp2 stays in range; logits that beat every sampled key by a wide
+    margin at an UNSAMPLED key must still give the reference result: margin ~30 nats (inside the range) and ~200 nats
+    (clamped; the softmax is one-hot there)."""
+    ops = _ops()
+    out = {}
+    heads, scale = 8, 0.125
+    for (bf, p, key, boost) in ((3, 362, 13, 30.0), (3, 362, 300, 30.0), (2, 362, 13, 200.0), (2, 200, 77, 200.0),
+                                (2, 362, 361, 60.0)):
+        assert key % 32 >= 8, "the spiked key must not be one of the sampled columns"
+        qkv = _rand(bf * p, 1536, seed=key + p).reshape(bf, p, 3, heads, 64)
+        # every query gets the component 8 along dim 0; the spiked key gets boost / (8 * scale) there:
+        # logit(query, key) = 8 * boost / (8 * scale) * scale + noise = boost nats above the rest
+        qkv[:, :, 0, :, 0] = 8.0
+        qkv[:, :, 1, :, 0] = 0.0
+        qkv[:, key, 1, :, 0] = boost / (8.0 * scale)
+        qkv = qkv.reshape(bf * p, 1536).to(torch.bfloat16)
+        split = lambda t: t.float().reshape(bf, p, heads, 64).permute(0, 2, 1, 3)
+        oref, _ = _attn_ref(split(qkv[:, :512]), split(qkv[:, 512:1024]), split(qkv[:, 1024:]), scale)
+        o, none = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=False)
+        torch.cuda.synchronize()
+        assert torch.isfinite(o.float()).all(), "non-finite attention output"
+        out[f"spike_{p}_{key}_{int(boost)}"] = _assert_close(
+            f"attn_s spiky key={key} boost={boost}", o, oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 1.5e-2)
+        o2, lse = ops.attn_spatial_lse(qkv, bf, p, heads, scale)          # training forward: same kernel + LSE
+        s = torch.einsum("bhid,bhjd->bhij", split(qkv[:, :512]), split(qkv[:, 512:1024])) * scale
+        lse_ref = torch.logsumexp(s, dim=-1) * 1.4426950408889634       # log2 domain
+        out[f"lse_{p}_{key}_{int(boost)}"] = _assert_close("attn_s spiky lse", lse, lse_ref, 2e-3)
+    return out
+
+
 def check_head():
     ops = _ops()
     b, f, p, d = 3, 7, 362, 728
@@ -675,6 +707,7 @@ CHECKS = {
     "conv3x3": check_conv3x3,
     "conv_stem": check_conv_stem,
     "conv_stem_u8": check_conv_stem_u8,
+    "attn_spatial_spiky": check_attn_spatial_spiky,
     "xception_tail": check_xception_tail,
     "dwconv": check_dwconv,
     "pool_subsample_tokens": check_pool_subsample_tokens,
