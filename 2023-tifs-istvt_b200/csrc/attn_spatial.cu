@@ -14,8 +14,6 @@
 #include "ptx.cuh"
 #include "simt_util.cuh"
 
-#include <stdlib.h>
-
 namespace istvt {
 
 constexpr int SA_DH = 64;
@@ -257,7 +255,6 @@ attn_spatial_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfl
 // tile t (O is double buffered).  Bound: MUFU (ex2) — 128 x 362 exponentials per tile at 16/clk/SM.
 // Optional `lse` output (training): log2-domain log-sum-exp of every query row, consumed by the backward.
 // ------------------------------------------------------------------------------------------
-constexpr float SP_EXP_CLAMP = 100.0f;                            // exp2 argument bound (sampled stabiliser)
 constexpr int SP_QSLOTS = 4;
 constexpr int SP_PARTS = 4;                                      // softmax threads per query row
 constexpr int SP_SM_WARPS = 4 * SP_PARTS;                        // 16 softmax warps
@@ -271,7 +268,7 @@ constexpr int SP_SMEM = SP_MISC_OFF + 1024 /*align*/ + 256 /*barriers*/ + 2 * SP
 
 __global__ void __launch_bounds__(SP_THREADS, 1)
 attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                         float* __restrict__ lse, int tokens, int heads, int items, float scale_log2, int sampled_max) {
+                         float* __restrict__ lse, int tokens, int heads, int items, float scale_log2) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_q = smem + SP_Q_OFF;
@@ -463,29 +460,13 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
             const int bf = item / heads;
             const int q_idx = qt * SA_BM + row;
 
-            // ---- pass 1: softmax stabiliser ----
-            // The kernel is bound by the TMEM read port (64 B/clk/SM: reading the 128 x 384 fp32 S tile twice plus O is
-            // 6 650 of the 7 300 clk per tile, profiles/README.md r3y).  softmax(s) = exp(s - m) / sum exp(s - m) for ANY
-            // m, and fp32 / bf16 hold exp2 arguments up to +100 without overflow, so m does not have to be the exact
-            // row maximum: with `sampled_max` it is the maximum over the first 8 of every thread's 32 columns per
-            // chunk (a quarter of the keys, a quarter of the TMEM bytes), and pass 2 clamps the exponent at +100 —
-            // reached only if some key beats every sampled key of its row by more than 69 nats, where the softmax is
-            // one-hot anyway.  sampled_max == 0: the exact maximum over all keys.
+            // ---- pass 1: row max over the valid keys ----
             float mx = -INFINITY;
             for (int c = 0; c < k_chunks; ++c) {
                 mbar_wait(s_full + c, t & 1);
                 tc_fence_after();
                 const int key0 = c * 128 + part * 32;
                 if (key0 >= tokens) continue;              // warp-uniform
-                if (sampled_max) {
-                    uint32_t r8[8];
-                    tmem_ld_32x32b_x8(t_row + c * 128, r8);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (key0 + j < tokens) mx = fmaxf(mx, __uint_as_float(r8[j]));
-                    continue;
-                }
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(t_row + c * 128, r);
                 tmem_ld_wait();
@@ -524,8 +505,8 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
                     if (key0 + 32 <= tokens) {             // warp-uniform: no masking
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float e0 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs), SP_EXP_CLAMP));
-                            const float e1 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs), SP_EXP_CLAMP));
+                            const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+                            const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
                             sum += e0 + e1;
                             pk[j] = pack_bf16x2_rne_alu(e0, e1);
                         }
@@ -533,8 +514,8 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
                         const int nvalid = tokens - key0;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            float e0 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs), SP_EXP_CLAMP));
-                            float e1 = ex2_approx(fminf(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs), SP_EXP_CLAMP));
+                            float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), scale_log2, -mxs));
+                            float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), scale_log2, -mxs));
                             if (2 * j >= nvalid) e0 = 0.0f;
                             if (2 * j + 1 >= nvalid) e1 = 0.0f;
                             sum += e0 + e1;
@@ -691,13 +672,8 @@ static int attn_spatial_launch(const void* qkv, void* out, float* probs, float* 
                                               SP_SMEM));
         const int items = batch_frames * heads;
         const int grid = items < sm_count() ? items : sm_count();
-        // ISTVT_SA_SAMPLED_MAX=0: exact row maximum over all keys (the stabiliser is then never below the maximum)
-        static const int sampled = []() { const char* e = getenv("ISTVT_SA_SAMPLED_MAX"); return e ? atoi(e) : 1; }();
         attn_spatial_pipe_kernel<<<grid, SP_THREADS, SP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
-                                                                   heads, items, scale_log2,
-                                                                   // the training forward hands lse to the backward, which
-                                                                   // recomputes P from it: no clamped rows there
-                                                                   (sampled && lse == nullptr) ? 1 : 0);
+                                                                   heads, items, scale_log2);
         count_launch();
         return launch_status();
     }

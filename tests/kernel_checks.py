@@ -364,16 +364,15 @@ def check_attn_spatial_bf16():
 
 
 def check_attn_spatial_spiky():
-    """The production kernel's softmax stabiliser is the maximum over a SAMPLE of the keys (columns 0-7 of every
-    32-column block), which is exact as long as exp2 stays in range; logits that beat every sampled key by a wide
-    margin at an UNSAMPLED key must still give the reference result: margin ~30 nats (inside the range) and ~200 nats
-    (clamped; the softmax is one-hot there)."""
+    """Rows whose softmax is dominated by ONE key by a wide margin (~30, ~60 and ~200 nats: near one-hot to exactly
+    one-hot in fp32): the two-pass kernel subtracts the exact row maximum, so these must match the reference and the
+    log-sum-exp handed to the backward must stay exact.  (A variant that took the stabiliser from a sample of the keys
+    was measured and dropped, profiles/README.md r3y; this check is what it had to pass.)"""
     ops = _ops()
     out = {}
     heads, scale = 8, 0.125
     for (bf, p, key, boost) in ((3, 362, 13, 30.0), (3, 362, 300, 30.0), (2, 362, 13, 200.0), (2, 200, 77, 200.0),
                                 (2, 362, 361, 60.0)):
-        assert key % 32 >= 8, "the spiked key must not be one of the sampled columns"
         qkv = _rand(bf * p, 1536, seed=key + p).reshape(bf, p, 3, heads, 64)
         # every query gets the component 8 along dim 0; the spiked key gets boost / (8 * scale) there:
         # logit(query, key) = 8 * boost / (8 * scale) * scale + noise = boost nats above the rest
