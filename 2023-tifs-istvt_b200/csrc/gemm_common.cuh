@@ -30,6 +30,7 @@ struct GemmParams {
 #ifdef ISTVT_GEMM_TRACE
     int trace_no_tma; // debug builds only (tools/gemm_trace.py)
 #endif
+    int split_producer;  // 1-CTA kernel: warp 0 loads the A boxes and warp 3 the B boxes (two issuing threads)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -16,6 +16,8 @@
 // input's W_in-wide grid; the epilogue drops the two junk columns/rows and compacts the row index).
 #include "gemm_common.cuh"
 
+#include <stdlib.h>
+
 namespace istvt {
 
 
@@ -75,7 +77,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], p.split_producer ? 2 : 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -103,15 +105,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 const int n_blk = static_cast<int>(tile % n_tiles);
                 const int64_t m0 = m_blk * GEMM_BLOCK_M;
                 const int n0 = n_blk * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait_hot(&empty_bar[stage], phase ^ 1);
-                    const int tap = kb / kb_per_tap;
-                    const int kcol = (kb - tap * kb_per_tap) * BK;
-                    const int64_t shift = (p.taps == 1) ? 0 : (int64_t)(tap / 3) * p.conv_w_in + (tap % 3);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tm_a, &full_bar[stage], kcol, static_cast<int>(m0 + shift));
-                    tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tm_b, &full_bar[stage], tap * p.K + kcol, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                // taps x k-blocks as nested counters: this single thread issues every TMA of the CTA, and for the 9-tap
+                // conv (one 12 KB stage per tap) its instruction count per stage — not the ring, not the MMAs — set the
+                // tile period (r4a: a second producer thread for the B boxes alone gave 10 %)
+                int row = static_cast<int>(m0), bcol = 0, kx = 0;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    for (int kcol = 0; kcol < p.K; kcol += BK) {
+                        mbar_wait_hot(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], p.split_producer ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
+                        tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tm_a, &full_bar[stage], kcol, row);
+                        if (!p.split_producer)
+                            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tm_b, &full_bar[stage], bcol + kcol, n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    bcol += p.K;
+                    if (++kx == 3) { kx = 0; row += p.conv_w_in - 2; } else { ++row; }     // next tap: (ky, kx) row shift
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3 && p.split_producer) {
+        // ===================== second TMA producer: the B (weight) boxes =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = static_cast<int>(tile % n_tiles) * BN;
+                int bcol = 0;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    for (int kcol = 0; kcol < p.K; kcol += BK) {
+                        mbar_wait_hot(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES);
+                        tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tm_b, &full_bar[stage], bcol + kcol, n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    bcol += p.K;
                 }
             }
         }
@@ -218,16 +246,20 @@ static int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const G
     const int64_t total = m_tiles * n_tiles;
     int grid = sm_count();
     if (total < grid) grid = static_cast<int>(total);
+    // 9-tap conv: A and B boxes issued by two threads (warp 0 / warp 3); ISTVT_G1_SPLIT_PRODUCER=0/1 forces it off / on
+    static const int split_env = []() { const char* e = getenv("ISTVT_G1_SPLIT_PRODUCER"); return e ? atoi(e) : -1; }();
+    GemmParams q = p;
+    q.split_producer = split_env >= 0 ? split_env : (p.taps > 1 ? 1 : 0);
     if (!p.c_f32 && p.residual == nullptr) {
         using Cfg = GemmCfg<BN, BK, true>;
         auto kern = gemm_tcgen05_kernel<BN, BK, true>;
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, q);
     } else {
         using Cfg = GemmCfg<BN, BK, false>;
         auto kern = gemm_tcgen05_kernel<BN, BK, false>;
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, p);
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, q);
     }
     count_launch();
     return launch_status();
