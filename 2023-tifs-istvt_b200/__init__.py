@@ -15,9 +15,10 @@ from .train import Trainer  # noqa: F401
 from .relevance import LRP, relevance_maps  # noqa: F401
 from .graph import GraphedForward  # noqa: F401
 from .network.models import TransferModel, model_selection  # noqa: F401
-from .network.vivit.vivit import DSTTr, STTransformer, XceptionVidTr  # noqa: F401
+from .network.vivit.vivit import DSTTr, STTransformer, Transformer, VanillaTr, ViViT, XceptionVidTr  # noqa: F401
+from .network.vivit.module import Attention, TemporalOnlyAttention  # noqa: F401
 
 ISTVT = XceptionVidTr
 
 __all__ = ["ISTVT", "XceptionVidTr", "DSTTr", "STTransformer", "TransferModel", "model_selection", "ISTVTEngine",
-           "entry_flow_features", "ops", "ClipStream", "Trainer", "LRP", "relevance_maps", "GraphedForward"]
+           "entry_flow_features", "ops", "Transformer", "ViViT", "VanillaTr", "Attention", "TemporalOnlyAttention", "ClipStream", "Trainer", "LRP", "relevance_maps", "GraphedForward"]

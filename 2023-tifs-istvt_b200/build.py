@@ -26,6 +26,8 @@ SOURCES = [
     "gemm_f32.cu",
     "attn_temporal.cu",
     "attn_spatial.cu",
+    "attn_joint.cu",
+    "token_build.cu",
     "attn_spatial_bwd.cu",
     "backward.cu",
     "entry_flow_bwd.cu",

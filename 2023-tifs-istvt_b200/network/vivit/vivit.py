@@ -1,7 +1,7 @@
 """ISTVT model = Xception entry flow + decomposed spatial-temporal transformer (B200-native forward).
 
 API mirror of the reference's `network/vivit/vivit.py`: `STTransformer` (:85-101), `DSTTr` (:103-148),
-`XceptionVidTr` (:193-208).  Constructor signatures, attribute paths (`xcep.model.*`,
+`XceptionVidTr` (:193-208), and the ablation models `Transformer` (:10-25), `ViViT` (:29-81), `VanillaTr` (:150-191).  Constructor signatures, attribute paths (`xcep.model.*`,
 `vit.transformer.layers[i][{0,1,2}].{norm,fn}`, `vit.mlp_head`) and therefore `state_dict` keys are the
 reference's.  `forward` hands the clip to `engine.ISTVTEngine`, which runs the hand-written sm_100a
 kernels through the C ABI; there is no torch-op or CPU fallback.
@@ -11,7 +11,101 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .module import FeedForward, PreNorm, SpatialOnlyAttention, TemporalResidualAttention
+from .module import Attention, FeedForward, PreNorm, SpatialOnlyAttention, TemporalResidualAttention
+
+
+class Transformer(nn.Module):
+    """depth x (PreNorm(Attention) + residual, PreNorm(FeedForward) + residual), final LayerNorm (reference
+    vivit.py:10-25).  `forward(x: [b, n, dim] CUDA) -> [b, n, dim] fp32`, inference only."""
+
+    def __init__(self, dim: int, depth: int, heads: int, dim_head: int, mlp_dim: int, dropout: float = 0.0):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        self.norm = nn.LayerNorm(dim)
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([
+                PreNorm(dim, Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout)),
+                PreNorm(dim, FeedForward(dim, mlp_dim, dropout=dropout)),
+            ]))
+        self.precision = "bf16"
+
+    def forward(self, x):
+        from ...ablation import transformer_forward
+        return transformer_forward(self, x, self.precision)
+
+
+def _check_vit_args(pool, image_size, patch_size, in_channels, dim, dim_head, num_classes, patch_linear):
+    if pool not in ("cls", "mean"):
+        raise ValueError("pool type must be either cls (cls token) or mean (mean pooling)")
+    if image_size % patch_size != 0:
+        raise ValueError("Image dimensions must be divisible by the patch size.")
+    if patch_size != 1 or dim_head != 64 or (in_channels != dim and not patch_linear):
+        raise ValueError("the B200 path supports patch size 1, head dimension 64 and dim == channels")
+    if num_classes != 1:
+        raise ValueError("the B200 head kernel emits one logit (num_classes=1, vivit.py:201)")
+
+
+class ViViT(nn.Module):
+    """Factorised-encoder ablation (reference vivit.py:29-81): a `Transformer` over the 362 tokens of every frame, then a
+    `Transformer` over the T+1 frame tokens of every clip.  Constructor signature and attribute names are the
+    reference's; `forward(x: [b, t, 728, 19, 19] CUDA feature maps) -> logits [b, 1]` (inference only)."""
+
+    def __init__(self, image_size: int, patch_size: int, num_classes: int, num_frames: int, dim: int = 728,
+                 depth: int = 12, heads: int = 8, pool: str = "cls", in_channels: int = 728, dim_head: int = 64,
+                 dropout: float = 0.0, emb_dropout: float = 0.0, scale_dim: int = 4):
+        super().__init__()
+        _check_vit_args(pool, image_size, patch_size, in_channels, dim, dim_head, num_classes, False)
+        if pool != "cls":
+            raise NotImplementedError("istvt_b200: ViViT mean pooling (vivit.py:79) is not built; use pool='cls'")
+        self.image_size, self.num_frames, self.dim, self.depth, self.heads = image_size, num_frames, dim, depth, heads
+        num_patches = (image_size // patch_size) ** 2
+        self.num_patches = num_patches
+        # construction order of the reference (vivit.py:45-59), so that a seeded init draws the same values
+        self.to_patch_embedding = nn.Sequential(nn.Identity())         # Rearrange only: no parameters (vivit.py:40-43)
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_frames, num_patches + 1, dim))
+        self.space_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.space_transformer = Transformer(dim, depth, heads, dim_head, dim * scale_dim, dropout)
+        self.temporal_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.temporal_transformer = Transformer(dim, depth, heads, dim_head, dim * scale_dim, dropout)
+        self.dropout = nn.Dropout(emb_dropout)
+        self.pool = pool
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
+        self.precision = "bf16"
+
+    def forward(self, x):
+        from ...ablation import features_forward
+        return features_forward(self, x, self.precision)
+
+
+class VanillaTr(nn.Module):
+    """Joint-attention ablation (reference vivit.py:150-191): per-patch Linear, then one `Transformer` over the
+    T*361+1 tokens of a clip (2167 at T=6: the key-streaming attention kernel).
+    `forward(x: [b, t, 728, 19, 19] CUDA feature maps) -> logits [b, 1]` (inference only)."""
+
+    def __init__(self, image_size: int, patch_size: int, num_classes: int, num_frames: int, dim: int = 728,
+                 depth: int = 12, heads: int = 8, pool: str = "cls", in_channels: int = 728, dim_head: int = 64,
+                 dropout: float = 0.0, emb_dropout: float = 0.0, scale_dim: int = 4):
+        super().__init__()
+        _check_vit_args(pool, image_size, patch_size, in_channels, dim, dim_head, num_classes, True)
+        if in_channels % 8 or dim % 8:
+            raise ValueError("in_channels and dim must be multiples of 8")
+        self.image_size, self.num_frames, self.dim, self.depth, self.heads = image_size, num_frames, dim, depth, heads
+        num_patches = (image_size // patch_size) ** 2
+        self.num_patches = num_patches
+        patch_dim = in_channels * patch_size ** 2
+        # index 1 carries the weights, like the reference's Sequential(Rearrange, Linear, Rearrange) (vivit.py:161-165)
+        self.to_patch_embedding = nn.Sequential(nn.Identity(), nn.Linear(patch_dim, dim), nn.Identity())
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_frames * num_patches + 1, dim))
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.transformer = Transformer(dim, depth, heads, dim_head, dim * scale_dim, dropout)
+        self.dropout = nn.Dropout(emb_dropout)
+        self.pool = pool
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
+        self.precision = "bf16"
+
+    def forward(self, x):
+        from ...ablation import features_forward
+        return features_forward(self, x, self.precision)
 
 
 class STTransformer(nn.Module):
@@ -62,11 +156,17 @@ class XceptionVidTr(nn.Module):
     """
     input_norm = ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))
 
-    def __init__(self, num_frames: int = 6, precision: str = "bf16"):
+    VARIANTS = {"dsttr": DSTTr, "vivit": ViViT, "vanilla": VanillaTr}
+
+    def __init__(self, num_frames: int = 6, precision: str = "bf16", variant: str = "dsttr"):
         super().__init__()
         from ..models import model_selection
+        if variant not in self.VARIANTS:
+            raise ValueError(f"variant must be one of {sorted(self.VARIANTS)}")
         self.xcep = model_selection(modelname="xception", num_out_classes=2, dropout=0.5, batch_size=1)
-        self.vit = DSTTr(19, 1, 1, num_frames)
+        # vivit.py:201 builds DSTTr(19, 1, 1, 6); the ablation transformers take the same arguments (vivit.py:30,151)
+        self.vit = self.VARIANTS[variant](19, 1, 1, num_frames)
+        self.variant = variant
         self.num_frames = num_frames
         self.precision = precision
         self._engine = None
@@ -78,6 +178,11 @@ class XceptionVidTr(nn.Module):
         return self._engine
 
     def forward(self, x: torch.Tensor, return_attention: bool = False):
+        if not isinstance(self.vit, DSTTr):      # ablation transformer behind the same entry flow (inference only)
+            if return_attention:
+                raise ValueError("attention maps are an output of the ISTVT model (variant='dsttr') only")
+            from ...ablation import clip_forward
+            return clip_forward(self, x, self.precision)
         if self.training and torch.is_grad_enabled():
             # model.train() (train_CNN.py:226): BatchNorm batch statistics + activations kept for loss.backward()
             if return_attention:

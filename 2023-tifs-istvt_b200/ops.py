@@ -350,6 +350,39 @@ def attn_spatial(qkv: torch.Tensor, batch_frames: int, tokens: int, heads: int, 
     return out, probs
 
 
+def attn_joint(qkv: torch.Tensor, batch: int, tokens: int, heads: int, scale: float) -> torch.Tensor:
+    """Joint self-attention over all `tokens` of each of the `batch` sequences, any sequence length (module.py:53-63).
+    qkv: [batch*tokens, 3*heads*64] -> [batch*tokens, heads*64]; keys are streamed with an online softmax."""
+    dev = _chk(qkv)
+    inner = heads * 64
+    rows = batch * tokens
+    if qkv.numel() != rows * 3 * inner:
+        raise ValueError("attn_joint: qkv must be [batch*tokens, 3*heads*64]")
+    out = torch.empty(rows, inner, dtype=qkv.dtype, device=dev)
+    with _launch(dev, "attn_joint", 4.0 * batch * heads * tokens * tokens * 64, _nbytes(qkv, out)):
+        _lib.check(_lib.lib().istvt_attn_joint_fwd(_ptr(qkv), _ptr(out), _dt(qkv), batch, tokens, heads, scale,
+                                                   _stream(dev)), "istvt_attn_joint_fwd")
+    return out
+
+
+def token_build(src: torch.Tensor, cls: torch.Tensor, pos: Optional[torch.Tensor], sequences: int, n: int,
+                pos_period: int = 1) -> torch.Tensor:
+    """Class token + n patch rows (+ positional embedding) per sequence -> fp32 tokens [sequences, n+1, dim]
+    (vivit.py:64-66, :73-74, :183-185).  src: [sequences*n, dim] bf16/fp32; cls fp32 [dim]; pos fp32
+    [pos_period, n+1, dim] or None."""
+    dev = _chk(src, cls, pos)
+    dim = src.shape[-1]
+    if src.numel() != sequences * n * dim or cls.numel() != dim or cls.dtype != torch.float32:
+        raise ValueError("token_build: src must be [sequences*n, dim] and cls fp32 [dim]")
+    if pos is not None and (pos.dtype != torch.float32 or pos.numel() != pos_period * (n + 1) * dim):
+        raise ValueError("token_build: pos must be fp32 [pos_period, n+1, dim]")
+    tokens = torch.empty(sequences, n + 1, dim, dtype=torch.float32, device=dev)
+    with _launch(dev, "token_build", 0.0, _nbytes(src, tokens) + (0 if pos is None else tokens.numel() * 4)):
+        _lib.check(_lib.lib().istvt_token_build_fwd(_ptr(src), _dt(src), _ptr(cls), _ptr(pos), _ptr(tokens), sequences,
+                                                    n, dim, pos_period, _stream(dev)), "istvt_token_build_fwd")
+    return tokens
+
+
 def head(tokens: torch.Tensor, norm_g, norm_b, head_g, head_b, head_w, head_bias, eps: float = 1e-5) -> torch.Tensor:
     """tokens: fp32 [B, F, P, D] -> logits fp32 [B, 1] from token (0, 0)."""
     dev = _chk(tokens, norm_g, norm_b, head_g, head_b, head_w, head_bias)

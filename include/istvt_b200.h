@@ -187,6 +187,31 @@ int istvt_attn_spatial_fwd(const void* qkv, void* out, float* probs, int dtype, 
                            int heads, float scale, istvt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Joint self-attention over all tokens of a sequence, ANY sequence length (the
+ * ablation transformers).  Replaces: module.py:53-63 (`Attention.forward`: chunk, rearranges, einsum, softmax,
+ * einsum, rearrange), as used by `Transformer` (vivit.py:10-25) inside `ViViT` (vivit.py:29-81) and `VanillaTr`
+ * (vivit.py:150-191; 6*361+1 = 2167 tokens per clip).
+ * bf16: tcgen05 QK^T / PV with the keys streamed in blocks of 128 and an online softmax (the score matrix of a long
+ * sequence does not fit TMEM); q/k/v tiles fetched by TMA from the packed projection output, no permute copies.
+ * qkv: [batch*tokens, 3*heads*64] (q | k | v columns, head-major); out: [batch*tokens, heads*64].
+ * dim_head is fixed at 64; scale > 0.  fp32 dtype runs the SIMT validation kernel.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_attn_joint_fwd(const void* qkv, void* out, int dtype, int batch, int tokens, int heads, float scale,
+                         istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Token-sequence assembly of the ablation transformers: class token in slot 0, the n patch rows behind it, positional
+ * embedding added, in one pass.  Replaces the repeat / torch.cat / `x += pos_embedding` triples at vivit.py:64-66
+ * (ViViT, per frame: pos_period = T), vivit.py:73-74 (ViViT, per clip: pos = NULL) and vivit.py:183-185 (VanillaTr,
+ * per clip: pos_period = 1).
+ * tokens[s, 0, :] = cls + pos[s % pos_period, 0, :];  tokens[s, 1+i, :] = src[s*n + i, :] + pos[s % pos_period, 1+i, :].
+ * src: [sequences*n, dim] (src_dtype bf16 or fp32); cls: fp32 [dim]; pos: fp32 [pos_period, n+1, dim] or NULL;
+ * tokens: fp32 [sequences, n+1, dim].  dim % 4 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_token_build_fwd(const void* src, int src_dtype, const float* cls, const float* pos, float* tokens,
+                          int sequences, int n, int dim, int pos_period, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Per-frame Xception baseline (model_selection('xception'), train_CNN.py:924-929).
  * The middle flow (blocks 4-11), block 12 and conv3 / conv4 reuse istvt_dwconv3x3_fwd, istvt_gemm_fwd (1x1 + folded
  * BN + ReLU), istvt_subsample2_fwd and istvt_pool_add_fwd; these two entries are the only additions.

@@ -14,6 +14,7 @@ if ROOT not in sys.path:
 PKG_NAME = "2023-tifs-istvt_b200"
 GOLDEN = os.path.join(ROOT, "tests", "golden", "istvt_golden.pt")
 GOLDEN_XCEPTION = os.path.join(ROOT, "tests", "golden", "xception_golden.pt")
+GOLDEN_ABLATION = os.path.join(ROOT, "tests", "golden", "ablation_golden.pt")
 
 
 def pkg():
@@ -95,3 +96,24 @@ def build_xception(seed: int = 0):
     oracle().sensitise_xception_(sd, "model")
     model.load_state_dict(sd)
     return model.eval()
+
+
+def ablation_oracle():
+    from oracle import ablation_oracle as A
+    return A
+
+
+def build_ablation_model(case: dict):
+    """Rebuild an ablation model of tests/golden/ablation_golden.pt from its seed with the B200 package's classes (same
+    construction order as the reference, oracle/make_golden_ablation.py::build) + the deterministic sensitisation."""
+    torch.manual_seed(case["seed"])
+    model = getattr(pkg(), case["cls"])(19, 1, 1, 6, depth=case["depth"]).eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    ablation_oracle().sensitise_ablation_(sd)
+    model.load_state_dict(sd)
+    return model
+
+
+def build_ablation_block(case: dict):
+    torch.manual_seed(case["seed"])
+    return getattr(pkg(), case["kind"])(728).eval()

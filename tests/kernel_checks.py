@@ -394,6 +394,76 @@ def check_attn_spatial_spiky():
     return out
 
 
+def check_attn_joint():
+    """Key-streaming joint attention (istvt_attn_joint_fwd, module.py:53-63) vs an fp64 softmax(QK^T)V: sequences of
+    1 .. 17 key blocks, ragged last blocks, a single-token sequence, near-one-hot logits, and a dominant key that sits
+    in a LATE block (every earlier block's partial result must be rescaled away)."""
+    ops = _ops()
+    out = {}
+    heads, scale = 8, 0.125
+    split = lambda t, b, n: t.float().reshape(b, n, heads, 64).permute(0, 2, 1, 3)
+    def ref(qkv, b, n):
+        o, _ = _attn_ref(split(qkv[:, :512], b, n), split(qkv[:, 512:1024], b, n), split(qkv[:, 1024:], b, n), scale)
+        return o.permute(0, 2, 1, 3).reshape(b * n, 512)
+    kept = {}
+    for (b, n, amp) in ((1, 2167, 1.0), (2, 300, 1.0), (3, 128, 1.0), (2, 129, 2.0), (2, 7, 1.0), (1, 1, 1.0),
+                        (2, 1000, 3.0), (1, 256, 1.0), (20, 362, 1.5), (1, 4096, 1.0)):
+        qkv = (_rand(b * n, 1536, seed=n + b) * amp).to(torch.bfloat16)
+        o = ops.attn_joint(qkv, b, n, heads, scale)
+        torch.cuda.synchronize()
+        assert torch.isfinite(o.float()).all(), f"non-finite joint attention output at {b}x{n}"
+        want = ref(qkv, b, n)
+        out[f"bf16_{b}x{n}"] = _assert_close(f"attn_joint bf16 {b}x{n}", o, want, 1.5e-2)
+        kept[(b, n)] = (qkv, o)
+    # a dominant key in block 11 of 17 (and one in block 0): online rescaling across blocks
+    for (n, key, boost) in ((2167, 1500, 40.0), (2167, 5, 40.0), (700, 699, 200.0)):
+        qkv = _rand(2 * n, 1536, seed=key).reshape(2, n, 3, heads, 64)
+        qkv[:, :, 0, :, 0] = 8.0
+        qkv[:, :, 1, :, 0] = 0.0
+        qkv[:, key, 1, :, 0] = boost / (8.0 * scale)
+        qkv = qkv.reshape(2 * n, 1536).to(torch.bfloat16)
+        o = ops.attn_joint(qkv, 2, n, heads, scale)
+        torch.cuda.synchronize()
+        assert torch.isfinite(o.float()).all(), "non-finite joint attention output (spiky)"
+        out[f"spike_{n}_{key}"] = _assert_close(f"attn_joint spiky n={n} key={key}", o, ref(qkv, 2, n), 1.5e-2)
+    # fp32 validation kernel
+    for (b, n) in ((1, 2167), (2, 300), (2, 7), (1, 65)):
+        qkv = _rand(b * n, 1536, seed=n) * 1.5
+        o = ops.attn_joint(qkv, b, n, heads, scale)
+        out[f"f32_{b}x{n}"] = _assert_close(f"attn_joint f32 {b}x{n}", o, ref(qkv, b, n), 5e-5)
+    # same math as the all-keys-resident spatial kernel wherever that one applies
+    for (b, n), (qkv, o) in kept.items():
+        if 7 <= n <= 384:
+            o2, _ = ops.attn_spatial(qkv, b, n, heads, scale)
+            out[f"vs_spatial_{b}x{n}"] = _assert_close(f"attn_joint vs attn_spatial {b}x{n}", o, o2, 8e-3)
+    # short sequences through the spatial kernels (ViViT's temporal transformer: 7 tokens per clip)
+    for dt, tol in ((torch.float32, 5e-5), (torch.bfloat16, 1.5e-2)):
+        qkv = (_rand(5 * 7, 1536, seed=77) * 1.5).to(dt)
+        o, _ = ops.attn_spatial(qkv, 5, 7, heads, scale)
+        out[f"spatial_7tok_{dt}"] = _assert_close(f"attn_spatial 7 tokens {dt}", o, ref(qkv, 5, 7), tol)
+    return out
+
+
+def check_token_build():
+    """Class token + patches (+ positional embedding) assembly of the ablation transformers vs torch cat / add."""
+    ops = _ops()
+    out = {}
+    dim = 728
+    for (seqs, n, period, with_pos, dt) in ((12, 361, 6, True, torch.bfloat16), (4, 361, 2, True, torch.float32),
+                                            (2, 2166, 1, True, torch.float32), (3, 6, 1, False, torch.float32),
+                                            (2, 2166, 1, True, torch.bfloat16)):
+        src = _rand(seqs * n, dim, seed=n).to(dt)
+        cls = _rand(dim, seed=1)
+        pos = _rand(period, n + 1, dim, seed=2) if with_pos else None
+        tok = ops.token_build(src, cls, pos, seqs, n, pos_period=period)
+        ref = torch.cat((cls.reshape(1, 1, dim).expand(seqs, 1, dim), src.float().reshape(seqs, n, dim)), dim=1)
+        if with_pos:
+            ref = ref + pos[torch.arange(seqs, device=DEV) % period]
+        assert tok.dtype == torch.float32 and tuple(tok.shape) == (seqs, n + 1, dim)
+        out[f"{seqs}x{n}_{dt}"] = _assert_close(f"token_build {seqs}x{n}", tok.reshape(-1, dim), ref.reshape(-1, dim), 1e-6)
+    return out
+
+
 def check_head():
     ops = _ops()
     b, f, p, d = 3, 7, 362, 728
@@ -713,6 +783,8 @@ CHECKS = {
     "attn_temporal": check_attn_temporal,
     "attn_spatial_f32": check_attn_spatial_f32,
     "attn_spatial_bf16": check_attn_spatial_bf16,
+    "attn_joint": check_attn_joint,
+    "token_build": check_token_build,
     "head": check_head,
     "layernorm_bwd": check_layernorm_bwd,
     "gelu_cast_transpose": check_gelu_cast_transpose,

@@ -8,7 +8,8 @@ from __future__ import annotations
 
 import torch
 
-from helpers import (GOLDEN, GOLDEN_XCEPTION, build_model, build_xception, fingerprint_check, make_frames, make_input,
+from helpers import (GOLDEN, GOLDEN_ABLATION, GOLDEN_XCEPTION, ablation_oracle, build_ablation_block,
+                     build_ablation_model, build_model, build_xception, fingerprint_check, make_frames, make_input,
                      oracle, pkg, rel_err)
 
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
@@ -383,3 +384,104 @@ def run_graph_check():
     print(f"batch-1 latency: eager {eager_ms:.3f} ms, CUDA graph {graph_ms:.3f} ms")
     assert graph_ms < eager_ms
     return {"eager_ms": eager_ms, "graph_ms": graph_ms}
+
+
+# ------------------------------------------------------------------------------------------------
+# ablation transformers
+# ------------------------------------------------------------------------------------------------
+def _abs_floor_err(got: torch.Tensor, want: torch.Tensor) -> float:
+    """max|got - want| / max(1, max|want|): logits of a single clip can sit near zero."""
+    got = got.detach().double().cpu()
+    want = want.detach().double().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1.0)).item()
+
+
+def run_ablation_golden(name: str, precision: str):
+    """`ViViT` / `VanillaTr` on seeded feature maps vs the golden logits of the UNMODIFIED reference
+    (tests/golden/ablation_golden.pt) and, layer by layer, vs the CPU oracle's residual stream."""
+    A = ablation_oracle()
+    case = torch.load(GOLDEN_ABLATION, weights_only=False)["models"][name]
+    model = build_ablation_model(case)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    for k, want in case["weights"].items():
+        fingerprint_check(f"weights[{k}]", sd[k], want, 0.0)
+    model = model.cuda()
+    model.precision = precision
+    tol = TOL[precision]
+    x = A.make_features(case["batch"], 6)
+    from importlib import import_module
+    ablation = import_module(pkg().__name__ + ".ablation")
+    taps = {}
+    logits = ablation.features_forward(model, x.cuda(), precision, taps)
+    torch.cuda.synchronize()
+    errs = {"logits": _abs_floor_err(logits, case["logits"]), "api": _abs_floor_err(model(x.cuda()), case["logits"])}
+    variant = "vivit" if case["cls"] == "ViViT" else "vanilla"
+    otaps = {}
+    with torch.no_grad():
+        A.FORWARDS[variant](sd, x, "", otaps)
+    last = case["depth"] - 1
+    for key in ([f"space.layer0", f"space.layer{last}", f"temporal.layer{last}"] if variant == "vivit"
+                else ["layer0", f"layer{last}"]):
+        errs[key] = rel_err(taps[key].reshape(-1), otaps[key].reshape(-1))
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f"ablation/{name}/{precision}: over tolerance {tol:.0e}: {bad}; all: {errs}"
+    assert torch.equal(logits.cpu() > 0, case["logits"] > 0), "predictions differ"
+    return errs
+
+
+def run_ablation_blocks(precision: str):
+    """Stand-alone `Attention` (2167 and 300 tokens) and `TemporalOnlyAttention` vs the reference's golden outputs."""
+    A = ablation_oracle()
+    g = torch.load(GOLDEN_ABLATION, weights_only=False)["blocks"]
+    errs = {}
+    for name, case in g.items():
+        blk = build_ablation_block(case).cuda()
+        blk.precision = precision
+        y = blk(A.make_tokens(case["batch"], case["n"]).cuda())
+        torch.cuda.synchronize()
+        assert y.dtype == torch.float32
+        errs[name] = fingerprint_check(f"ablation/{name}/{precision}", y, case["out"], TOL[precision])
+    # Transformer.forward on a token tensor == the oracle's plain_transformer
+    torch.manual_seed(5)
+    tr = pkg().Transformer(728, 2, 8, 64, 2912).eval()
+    sd = {"t." + k: v.clone() for k, v in tr.state_dict().items()}
+    x = A.make_tokens(2, 500)
+    with torch.no_grad():
+        want = A.plain_transformer(sd, "t", x)
+    tr = tr.cuda()
+    tr.precision = precision
+    errs["transformer_n500"] = rel_err(tr(x.cuda()), want)
+    assert errs["transformer_n500"] <= TOL[precision], errs
+    return errs
+
+
+def run_ablation_clip_check(variant: str, precision: str = "bf16"):
+    """`XceptionVidTr(variant=...)`: clips through the entry flow + ViViT / VanillaTr vs the CPU oracle; boundary
+    behaviour of the variant models."""
+    import pytest
+    A = ablation_oracle()
+    torch.manual_seed(3)
+    model = pkg().XceptionVidTr(variant=variant, precision=precision).eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    oracle().sensitise_(sd)                       # BatchNorm statistics of the entry flow, LayerNorms under "vit."
+    model.load_state_dict(sd)
+    x = make_input(2, 6, seed=41)
+    with torch.no_grad():
+        want = A.clip_forward(sd, x, variant)
+    with pytest.raises(ValueError, match="CUDA"):
+        model(x)
+    model = model.cuda()
+    got = model(x.cuda())
+    torch.cuda.synchronize()
+    errs = {"logits": _abs_floor_err(got, want)}
+    assert errs["logits"] <= TOL[precision], f"{variant}/{precision}: {errs}; got {got.flatten().tolist()} want {want.flatten().tolist()}"
+    with pytest.raises(ValueError):
+        model(x.cuda(), return_attention=True)
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(x.cuda())
+    with torch.no_grad():                          # train-mode modules under no_grad are still the inference path
+        model.eval()
+        errs["repeat"] = _abs_floor_err(model(x.cuda()), got)
+    assert errs["repeat"] == 0.0
+    return errs

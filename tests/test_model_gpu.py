@@ -47,3 +47,22 @@ def test_uint8_frames_against_oracle():
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_xception_baseline_against_reference_golden(precision):
     model_checks.run_xception_golden(precision)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", ["vivit_d2_b2", "vivit_d12_b1", "vanilla_d2_b1", "vanilla_d12_b1"])
+def test_ablation_models_against_reference_golden(case, precision):
+    model_checks.run_ablation_golden(case, precision)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ablation_blocks_against_reference_golden(precision):
+    model_checks.run_ablation_blocks(precision)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["vivit", "vanilla"])
+def test_ablation_variants_behind_the_entry_flow(variant):
+    model_checks.run_ablation_clip_check(variant)
