@@ -575,6 +575,125 @@ def run_relevance(args) -> int:
     return 0
 
 
+def run_ablation(args) -> int:
+    """--mode ablation --variant vivit|vanilla: SURVEY.md section 8(f) rank 3 — the ablation transformers behind the same
+    entry flow (`XceptionVidTr(variant=...)`), clips sharded over GPUs, no collective.  Not BASELINE.json's headline
+    metric: a side line for the widened scope, same JSON shape."""
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module(PKG)
+    ops = pkg.ops
+    torch.manual_seed(0)
+    model = pkg.XceptionVidTr(num_frames=args.frames, precision=args.precision, variant=args.variant).eval()
+    sd_cpu = {k: v.clone() for k, v in model.state_dict().items()} if rank == 0 and not args.no_cpu_baseline else None
+    model = model.to(dev)
+    x_host = torch.rand(args.batch, args.frames, 3, 300, 300, generator=torch.Generator().manual_seed(1234 + rank)).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        model(x_dev)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.25)
+    rec = ops.LaunchRecorder()
+    ops.set_recorder(rec)
+    n0 = pkg._lib.launch_count()
+    barrier()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        logits = model(x_dev)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler is not None else None
+    launches = pkg._lib.launch_count() - n0
+    ops.set_recorder(None)
+    ms = e0.elapsed_time(e1)
+    out = torch.empty(logits.shape).pin_memory()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        out.copy_(model(x_host.to(dev, non_blocking=True)))
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank == 0:
+        total = args.batch * world * args.steps
+        fam = rec.summary()
+        peaks, peak_source = load_peaks()
+        kernels = {}
+        for n, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+            k = {"launches": d["launches"], "ms_per_step": d["ms"] / args.steps, "share": d["ms"] / ms}
+            if d["flops"]:
+                k["tflops"] = d["flops"] / d["ms"] / 1e9
+            if d["bytes"]:
+                k["gbs"] = d["bytes"] / d["ms"] / 1e6
+            kernels[n] = k
+        top = "attn_joint" if "attn_joint" in fam else "gemm_bf16"
+        d = fam.get(top)
+        roof = None
+        if d is not None and d["flops"]:
+            ach = d["flops"] / d["ms"] / 1e9
+            roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "peak_source": peak_source + ", sustained bf16 (kernel timed inside a long step)",
+                    "share_of_step": d["ms"] / ms}
+        line = {"metric": f"clips/sec forward ({args.variant} ablation)", "value": total / (ms / 1e3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+                "data": "synthetic",
+                "config": {"workload": f"8(f)-3 ablation: Xception entry flow + {type(model.vit).__name__} "
+                                       f"({args.precision} inference), {args.batch} clips x {args.frames} frames x 300x300 "
+                                       "per GPU, random-init weights seed 0",
+                           "batch_per_gpu": args.batch, "variant": args.variant,
+                           "l2_policy": "no flush needed: the per-step input and every activation tensor exceed the L2"},
+                "e2e": {"value": total / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": out.numel() * 4 * world},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels}
+        if sd_cpu is not None:
+            from oracle import ablation_oracle as A
+            threads = use_all_host_threads()
+            xs = x_host[:1].clone()
+            with torch.no_grad():
+                A.clip_forward(sd_cpu, xs, args.variant)
+                n_it, t0 = 0, time.perf_counter()
+                while n_it < 2 or time.perf_counter() - t0 < args.cpu_budget:
+                    A.clip_forward(sd_cpu, xs, args.variant)
+                    n_it += 1
+                dt_s = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n_it / dt_s, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{n_it} forwards of 1 clip (oracle/ablation_oracle.py clip_forward, fp32)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -587,7 +706,8 @@ def main() -> int:
     ap.add_argument("--ref-clips", type=int, default=2, help="--impl reference: clips per CPU step")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="infer", choices=["infer", "train", "relevance"],
+    ap.add_argument("--variant", default="vanilla", choices=["vivit", "vanilla"], help="--mode ablation: which transformer")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "relevance", "ablation"],
                     help="infer: BASELINE.json's headline metric (C2, default; --frames 32 --batch 8 = C5); "
                          "train: the DP training step (C3); relevance: the relevance pass (C4, use --batch 32)")
     args = ap.parse_args()
@@ -599,6 +719,8 @@ def main() -> int:
         return run_train(args)
     if args.mode == "relevance":
         return run_relevance(args)
+    if args.mode == "ablation":
+        return run_ablation(args)
     return run_ours(args)
 
 

@@ -30,13 +30,35 @@ def timed(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
+def joint(args) -> None:
+    heads, dev = 8, "cuda"
+    for clips, n in ((args.clips, args.frames * 361 + 1), (args.clips * (args.frames + 1), 362)):
+        qkvs = [torch.randn(clips * n, 1536, device=dev).to(torch.bfloat16) for _ in range(2)]
+        i = [0]
+
+        def run():
+            i[0] ^= 1
+            ops.attn_joint(qkvs[i[0]], clips, n, heads, 0.125)
+        ms = timed(run, args.iters)
+        fl = 4.0 * clips * heads * n * n * 64
+        print(f"attn_joint   {clips} sequences x {n} tokens  {ms:7.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s  "
+              f"{(qkvs[0].numel() * 2 + clips * n * 512 * 2) / ms / 1e6:7.0f} GB/s (qkv + out once)", flush=True)
+        if n <= 384:
+            ms = timed(lambda: ops.attn_spatial(qkvs[0], clips, n, heads, 0.125), args.iters)
+            print(f"attn_spatial {clips} sequences x {n} tokens  {ms:7.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s", flush=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--clips", type=int, default=64)
     ap.add_argument("--frames", type=int, default=6)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--bwd", action="store_true", help="also time the spatial-attention backward (training)")
+    ap.add_argument("--joint", action="store_true",
+                    help="only the key-streaming joint attention at VanillaTr's sequence length (frames*361+1 tokens)")
     args = ap.parse_args()
+    if args.joint:
+        return joint(args)
     b, f, p, heads = args.clips, args.frames + 1, 362, 8
     dev = "cuda"
     qkvs = [torch.randn(b * f * p, 1536, device=dev).to(torch.bfloat16) for _ in range(2)]
