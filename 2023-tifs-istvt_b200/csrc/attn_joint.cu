@@ -4,7 +4,7 @@
 // key columns resident), so this kernel streams the keys in blocks of 128 with an online softmax.
 //
 // bf16 path (tcgen05): one CTA = one (sequence b, head h, 128-query tile).
-//   warp 0     TMA producer: Q once, then K / V blocks of 128 keys through a 2-stage ring, read in place from the
+//   warp 0     TMA producer: Q once, then K / V blocks of 128 keys through a 4-stage ring, read in place from the
 //              packed projection output [rows, 3*heads*64] (3-D tensor map: col, token, sequence; OOB rows zero-filled)
 //   warp 1     MMA issuer:   S_j[128 x 128] = Q K_j^T      (both operands K-major SW128, accumulator in TMEM)
 //                            O_j[128 x 64]  = P_j V_j       (P_j bf16 in smem, V_j the MN-major B operand)
@@ -15,8 +15,10 @@
 //              accumulator o = o * exp2((m_old - m_new) c) + O_j one block late (while S_{j+1} / PV_j run), so no
 //              accumulator in TMEM ever needs rescaling.
 //   TMEM: S0 S1 [128 x 128] fp32 (cols 0-255), O0 O1 [128 x 64] fp32 (cols 256-383).
-//   smem: Q 16 KB, K 2 x 16 KB, V 2 x 16 KB, P 2 x 32 KB.
+//   smem: Q 16 KB, K 4 x 16 KB, V 4 x 16 KB (ring of 4 key blocks), P 2 x 32 KB.
 // fp32 path: SIMT validation kernel, one query per thread, K / V streamed through shared memory in blocks of 64.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "simt_util.cuh"
@@ -26,30 +28,80 @@ namespace istvt {
 constexpr int JA_DH = 64;
 constexpr int JA_BM = 128;         // queries per CTA
 constexpr int JA_BN = 128;         // keys per block
-constexpr int JA_THREADS = 384;    // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: softmax + accumulate
+// warps 0-3: TMA / MMA / TMEM alloc / spare; then SPLIT x 4 softmax warps (SPLIT threads per query row)
+constexpr int ja_threads(int split) { return 128 + split * 128; }
 constexpr int JA_TILE_BYTES = 128 * JA_DH * 2;       // 16 KB: a Q tile, a K block or a V block
 constexpr int JA_P_BYTES = JA_BM * JA_BN * 2;        // 32 KB: two 64-key SW128 atoms of 128 rows
-constexpr int JA_SMEM = 5 * JA_TILE_BYTES + 2 * JA_P_BYTES + 4096 + 1024;
+constexpr int JA_STAGES = 4;       // K / V ring: the fetch of block j+3 starts when PV_{j-1} retires (a 2-stage ring left
+                                   // the TMA latency of K_{j+1} exposed: the softmax warps' top stall was the wait for S)
+constexpr int JA_SMEM = (1 + 2 * JA_STAGES) * JA_TILE_BYTES + 2 * JA_P_BYTES + 8192 + 1024;
 constexpr int JA_TMEM_COLS = 512;
 
-__global__ void __launch_bounds__(JA_THREADS, 1)
+__device__ __forceinline__ void tmem_ld_32x32b(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_32x32b(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
+
+// row maximum of this thread's slice of a score block (MASK: columns >= valid are past the sequence's last key)
+template <int NLD, bool MASK>
+__device__ __forceinline__ float block_max(const uint32_t (&r)[NLD][32], int valid) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int l = 0; l < NLD; ++l)
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (!MASK || l * 32 + c < valid) mx = fmaxf(mx, __uint_as_float(r[l][c]));
+    return mx;
+}
+
+// p = exp2(s * c - m * c) for this thread's slice, rounded to bf16 and stored as the PV MMA's A operand; returns the
+// slice's contribution to the row denominator, accumulated from the SAME rounded values the MMA consumes.
+template <int NLD, bool MASK>
+__device__ __forceinline__ float block_exp_store(const uint32_t (&r)[NLD][32], int valid, float scale_log2, float mxs,
+                                                 uint8_t* prow, int chunk0, int row) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int l = 0; l < NLD; ++l) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int c = l * 32 + 2 * i;
+            float e0 = ex2_approx(fmaf(__uint_as_float(r[l][2 * i]), scale_log2, -mxs));
+            float e1 = ex2_approx(fmaf(__uint_as_float(r[l][2 * i + 1]), scale_log2, -mxs));
+            if (MASK) {
+                e0 = (c < valid) ? e0 : 0.0f;
+                e1 = (c + 1 < valid) ? e1 : 0.0f;
+            }
+            pk[i] = pack_bf16x2(e0, e1);
+            const float2 f = unpack_bf16x2(pk[i]);
+            sum += f.x + f.y;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int chunk = (chunk0 + l * 4 + g) ^ (row & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+    }
+    return sum;
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(ja_threads(SPLIT), 1)
 attn_joint_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, int tokens,
                           int heads, float scale_log2) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_q = smem;
-    uint8_t* s_k = s_q + JA_TILE_BYTES;            // [2][16 KB]
-    uint8_t* s_v = s_k + 2 * JA_TILE_BYTES;        // [2][16 KB]
-    uint8_t* s_p = s_v + 2 * JA_TILE_BYTES;        // [2][32 KB]
+    uint8_t* s_k = s_q + JA_TILE_BYTES;                    // [JA_STAGES][16 KB]
+    uint8_t* s_v = s_k + JA_STAGES * JA_TILE_BYTES;        // [JA_STAGES][16 KB]
+    uint8_t* s_p = s_v + JA_STAGES * JA_TILE_BYTES;        // [2][32 KB]
     uint8_t* s_misc = s_p + 2 * JA_P_BYTES;
     uint64_t* bar_q = reinterpret_cast<uint64_t*>(s_misc);
-    uint64_t* kv_full = bar_q + 1;                 // [2]
-    uint64_t* kv_empty = bar_q + 3;                // [2]
-    uint64_t* bar_s = bar_q + 5;                   // [2]
-    uint64_t* bar_p = bar_q + 7;                   // [2]
-    uint64_t* bar_o = bar_q + 9;                   // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_q + 11);
-    float* s_red = reinterpret_cast<float*>(s_misc + 128);   // [2 block parities][2 halves][128 rows]
+    uint64_t* kv_full = bar_q + 1;                         // [JA_STAGES]
+    uint64_t* kv_empty = kv_full + JA_STAGES;              // [JA_STAGES]
+    uint64_t* bar_s = kv_empty + JA_STAGES;                // [2]
+    uint64_t* bar_p = bar_s + 2;                           // [2]
+    uint64_t* bar_o = bar_p + 2;                           // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_o + 2);
+    float* s_red = reinterpret_cast<float*>(s_misc + 256);   // [2 block parities][SPLIT slices][128 rows], then sums
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -64,11 +116,13 @@ attn_joint_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_qkv);
     if (warp == 1 && lane == 0) {
         mbar_init(bar_q, 1);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < JA_STAGES; ++s) {
             mbar_init(kv_full + s, 1);
             mbar_init(kv_empty + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(bar_s + s, 1);
-            mbar_init(bar_p + s, 8);   // one arrive per softmax warp
+            mbar_init(bar_p + s, SPLIT * 4);   // one arrive per softmax warp
             mbar_init(bar_o + s, 1);
         }
         fence_mbar_init();
@@ -89,8 +143,8 @@ attn_joint_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
             mbar_arrive_expect_tx(bar_q, JA_TILE_BYTES);
             tma_load_3d(s_q, &tm_qkv, bar_q, h * JA_DH, qt * JA_BM, b);
             for (int j = 0; j < nblk; ++j) {
-                const int s = j & 1;
-                if (j >= 2) mbar_wait_sleep(kv_empty + s, ((j >> 1) - 1) & 1);
+                const int s = j % JA_STAGES;
+                if (j >= JA_STAGES) mbar_wait_sleep(kv_empty + s, ((j / JA_STAGES) - 1) & 1);
                 mbar_arrive_expect_tx(kv_full + s, 2 * JA_TILE_BYTES);
                 tma_load_3d(s_k + s * JA_TILE_BYTES, &tm_qkv, kv_full + s, inner + h * JA_DH, j * JA_BN, b);
                 tma_load_3d(s_v + s * JA_TILE_BYTES, &tm_qkv, kv_full + s, 2 * inner + h * JA_DH, j * JA_BN, b);
@@ -116,10 +170,11 @@ attn_joint_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
         for (int j = 0; j < nblk; ++j) {
             if (j + 1 < nblk) {   // S_{j+1}: its TMEM buffer was released by bar_p of block j-1 (waited last iteration)
                 const int s1 = (j + 1) & 1;
-                mbar_wait(kv_full + s1, ((j + 1) >> 1) & 1);
+                const int st1 = (j + 1) % JA_STAGES;
+                mbar_wait(kv_full + st1, ((j + 1) / JA_STAGES) & 1);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t k_addr = smem_u32(s_k + s1 * JA_TILE_BYTES);
+                    const uint32_t k_addr = smem_u32(s_k + st1 * JA_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < JA_DH / 16; ++k)
                         umma_f16_ss(tmem_s + s1 * JA_BN, make_smem_desc(q_addr + k * 32, 0, 1024, SWZ_128B),
@@ -133,7 +188,7 @@ attn_joint_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t p_addr = smem_u32(s_p + s * JA_P_BYTES);
-                const uint32_t v_addr = smem_u32(s_v + s * JA_TILE_BYTES);
+                const uint32_t v_addr = smem_u32(s_v + (j % JA_STAGES) * JA_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < JA_BN / 16; ++k) {
                     const uint64_t a_desc =
@@ -142,72 +197,61 @@ attn_joint_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
                     umma_f16_ss(tmem_o + s * JA_DH, a_desc, b_desc, idesc_o, k != 0 ? 1u : 0u);
                 }
                 umma_commit(bar_o + s);
-                umma_commit(kv_empty + s);        // K_j (read by S_j) and V_j are free once PV_j retires
+                umma_commit(kv_empty + (j % JA_STAGES));   // K_j (read by S_j) and V_j are free once PV_j retires
             }
             __syncwarp();
         }
     } else if (warp >= 4) {
+        constexpr int COLS = JA_BN / SPLIT;             // key columns of a block per thread: 64 | 32
+        constexpr int NLD = COLS / 32;                  // 32-column TMEM loads per block: 2 | 1
+        constexpr int OC = JA_DH / SPLIT;               // output columns per thread: 32 | 16
         const int quad = warp & 3;
-        const int half = (warp - 4) >> 2;
+        const int part = (warp - 4) >> 2;               // which column slice of the row this thread owns
         const int row = quad * 32 + lane;               // row inside the q tile == TMEM lane
         const int q_idx = qt * JA_BM + row;
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
 
         float m_run = -INFINITY, l_part = 0.0f, corr_prev = 0.0f;
-        float o[32];
+        float o[OC];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.0f;
+        for (int i = 0; i < OC; ++i) o[i] = 0.0f;
+
+        auto add_block = [&](int sp) {                  // o = o * corr_prev + O_sp
+            uint32_t ro[OC];
+            tmem_ld_32x32b(tmem_o + lane_base + sp * JA_DH + part * OC, ro);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < OC; ++i) o[i] = fmaf(o[i], corr_prev, __uint_as_float(ro[i]));
+        };
 
         for (int j = 0; j < nblk; ++j) {
             const int s = j & 1;
             mbar_wait(bar_s + s, (j >> 1) & 1);
             tc_fence_after();
-            uint32_t r0[32], r1[32];
-            const uint32_t t_s = tmem_s + lane_base + s * JA_BN + half * 64;
-            tmem_ld_32x32b_x32(t_s, r0);
-            tmem_ld_32x32b_x32(t_s + 32, r1);
-            tmem_ld_wait();
-            const int key0 = j * JA_BN + half * 64;     // key index of r0[0]
-            const int valid = tokens - key0;            // columns [0, valid) of this thread's 64 are real keys
-            float mx = -INFINITY;
+            uint32_t r[NLD][32];
+            const uint32_t t_s = tmem_s + lane_base + s * JA_BN + part * COLS;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                if (c < valid) mx = fmaxf(mx, __uint_as_float(r0[c]));
-                if (c + 32 < valid) mx = fmaxf(mx, __uint_as_float(r1[c]));
-            }
-            float* red = s_red + s * 256;
-            red[half * 128 + row] = mx;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float m_new = fmaxf(m_run, fmaxf(red[row], red[128 + row]));
+            for (int l = 0; l < NLD; ++l) tmem_ld_32x32b_x32(t_s + l * 32, r[l]);
+            tmem_ld_wait();
+            const int valid = tokens - (j * JA_BN + part * COLS);   // columns [0, valid) of this slice are real keys
+            // only the sequence's last key block has columns past the last token: everything else skips the masks
+            const bool ragged = valid < COLS;            // warp-uniform
+            const float mx = ragged ? block_max<NLD, true>(r, valid) : block_max<NLD, false>(r, valid);
+            float* red = s_red + s * (SPLIT * 128);
+            red[part * 128 + row] = mx;
+            asm volatile("bar.sync 1, %0;" ::"n"(SPLIT * 128) : "memory");
+            float m_new = m_run;
+#pragma unroll
+            for (int p = 0; p < SPLIT; ++p) m_new = fmaxf(m_new, red[p * 128 + row]);
             const float corr = ex2_approx((m_run - m_new) * scale_log2);
             const float mxs = m_new * scale_log2;
 
-            float sum = 0.0f;
-            uint8_t* prow = s_p + s * JA_P_BYTES + half * (JA_BM * 128) + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = part * 32 + 2 * i;
-                    const uint32_t u0 = part == 0 ? r0[2 * i] : r1[2 * i];
-                    const uint32_t u1 = part == 0 ? r0[2 * i + 1] : r1[2 * i + 1];
-                    float e0 = ex2_approx(fmaf(__uint_as_float(u0), scale_log2, -mxs));
-                    float e1 = ex2_approx(fmaf(__uint_as_float(u1), scale_log2, -mxs));
-                    e0 = (c < valid) ? e0 : 0.0f;
-                    e1 = (c + 1 < valid) ? e1 : 0.0f;
-                    // the PV MMA consumes bf16 P: the denominator is accumulated from the same rounded values
-                    pk[i] = pack_bf16x2(e0, e1);
-                    const float2 f = unpack_bf16x2(pk[i]);
-                    sum += f.x + f.y;
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int chunk = (part * 4 + g) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(prow + chunk * 16) =
-                        make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-                }
-            }
+            // P_j, bf16, K-major SW128: atom = 64 keys (128 B per row), 16-byte chunks XOR-swizzled by row & 7
+            uint8_t* prow = s_p + s * JA_P_BYTES + ((part * COLS) >> 6) * (JA_BM * 128) + (row >> 3) * 1024 +
+                            (row & 7) * 128;
+            const int chunk0 = ((part * COLS) & 63) >> 3;
+            const float sum = ragged ? block_exp_store<NLD, true>(r, valid, scale_log2, mxs, prow, chunk0, row)
+                                     : block_exp_store<NLD, false>(r, valid, scale_log2, mxs, prow, chunk0, row);
             l_part = fmaf(l_part, corr, sum);
             fence_proxy_async_smem();   // st.shared P -> visible to the tensor core (async proxy)
             tc_fence_before();
@@ -215,37 +259,28 @@ attn_joint_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
             if (lane == 0) mbar_arrive(bar_p + s);
 
             if (j > 0) {   // deferred: o = o * corr_{j-1} + O_{j-1}
-                const int sp = (j - 1) & 1;
-                mbar_wait(bar_o + sp, ((j - 1) >> 1) & 1);
+                mbar_wait(bar_o + ((j - 1) & 1), ((j - 1) >> 1) & 1);
                 tc_fence_after();
-                uint32_t ro[32];
-                tmem_ld_32x32b_x32(tmem_o + lane_base + sp * JA_DH + half * 32, ro);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], corr_prev, __uint_as_float(ro[i]));
+                add_block((j - 1) & 1);
             }
             corr_prev = corr;
             m_run = m_new;
         }
-        {
-            const int sp = (nblk - 1) & 1;
-            mbar_wait(bar_o + sp, ((nblk - 1) >> 1) & 1);
-            tc_fence_after();
-            uint32_t ro[32];
-            tmem_ld_32x32b_x32(tmem_o + lane_base + sp * JA_DH + half * 32, ro);
-            tmem_ld_wait();
+        mbar_wait(bar_o + ((nblk - 1) & 1), ((nblk - 1) >> 1) & 1);
+        tc_fence_after();
+        add_block((nblk - 1) & 1);
+        // denominators of the column slices (each already in the scale of the final maximum)
+        float* sums = s_red + 2 * SPLIT * 128;
+        sums[part * 128 + row] = l_part;
+        asm volatile("bar.sync 1, %0;" ::"n"(SPLIT * 128) : "memory");
+        float total = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], corr_prev, __uint_as_float(ro[i]));
-        }
-        // denominators of the two column halves (each already in the scale of the final maximum)
-        float* sums = s_red + 512;
-        sums[half * 128 + row] = l_part;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float inv = 1.0f / (sums[row] + sums[128 + row]);
+        for (int p = 0; p < SPLIT; ++p) total += sums[p * 128 + row];
+        const float inv = 1.0f / total;
         if (q_idx < tokens) {
-            __nv_bfloat16* op = out + (static_cast<int64_t>(b) * tokens + q_idx) * inner + h * JA_DH + half * 32;
+            __nv_bfloat16* op = out + (static_cast<int64_t>(b) * tokens + q_idx) * inner + h * JA_DH + part * OC;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < OC / 8; ++g) {
                 uint4 v;
                 v.x = pack_bf16x2(o[8 * g + 0] * inv, o[8 * g + 1] * inv);
                 v.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
@@ -341,6 +376,16 @@ attn_joint_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, in
 
 using namespace istvt;
 
+// softmax threads per query row: 2 (default: 0.385 ms at 16 x 2167 tokens) or 4 (ISTVT_JA_SPLIT=4: 0.390 ms — more
+// warps do not help, the block loop is a latency chain, not an issue-slot shortage; kept for A/B measurements)
+static int joint_split() {
+    static const int v = [] {
+        const char* e = getenv("ISTVT_JA_SPLIT");
+        return (e != nullptr && atoi(e) == 4) ? 4 : 2;
+    }();
+    return v;
+}
+
 extern "C" int istvt_attn_joint_fwd(const void* qkv, void* out, int dtype, int batch, int tokens, int heads,
                                     float scale, istvt_stream_t stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -367,10 +412,19 @@ extern "C" int istvt_attn_joint_fwd(const void* qkv, void* out, int dtype, int b
         int rc = encode_tmap(&tm, qkv, ISTVT_BF16, 3, dims, strides, box, 3);
         if (rc != ISTVT_OK) return rc;
     }
-    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          JA_SMEM));
-    attn_joint_tcgen05_kernel<<<batch * heads * q_tiles, JA_THREADS, JA_SMEM, st>>>(
-        tm, static_cast<__nv_bfloat16*>(out), tokens, heads, scale * 1.4426950408889634f);
+    const float scale_log2 = scale * 1.4426950408889634f;
+    const int grid = batch * heads * q_tiles;
+    if (joint_split() == 2) {
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              JA_SMEM));
+        attn_joint_tcgen05_kernel<2><<<grid, ja_threads(2), JA_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), tokens,
+                                                                          heads, scale_log2);
+    } else {
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              JA_SMEM));
+        attn_joint_tcgen05_kernel<4><<<grid, ja_threads(4), JA_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), tokens,
+                                                                          heads, scale_log2);
+    }
     count_launch();
     return launch_status();
 }

@@ -48,10 +48,15 @@ def test_argument_validation_without_gpu(lib):
     assert lib.istvt_gemm_fwd(None, 8, None, 8, None, 8, 0, 128, 128, 64, None, None, 0, 0, None) == -1
     assert lib.istvt_attn_spatial_fwd(None, None, None, 0, 1, 362, 8, 0.125, None) == -1
     assert lib.istvt_dwconv3x3_fwd(None, None, None, 0, 1, 8, 8, 8, 0, None) == -1
+    assert lib.istvt_attn_joint_fwd(None, None, 0, 1, 2167, 8, 0.125, None) == -1
+    assert lib.istvt_token_build_fwd(None, 0, None, None, None, 1, 361, 728, 1, None) == -1
     buf = ctypes.create_string_buffer(64)
     p = ctypes.cast(buf, ctypes.c_void_p)
     assert lib.istvt_layernorm_fwd(p, 1, p, p, p, 0, 4, 730, 1e-5, None) == -1      # dim % 4
     assert lib.istvt_gemm_fwd(p, 7, p, 8, p, 8, 0, 128, 128, 64, None, None, 0, 0, None) == -1   # lda % 8
+    assert lib.istvt_attn_joint_fwd(p, p, 0, 1, 0, 8, 0.125, None) == -1                         # no tokens
+    assert lib.istvt_attn_joint_fwd(p, p, 0, 1, 64, 8, -1.0, None) == -1                         # scale <= 0
+    assert lib.istvt_token_build_fwd(p, 0, p, None, p, 1, 361, 730, 1, None) == -1               # dim % 4
 
 
 def test_missing_library_fails_loudly(monkeypatch):

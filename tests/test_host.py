@@ -94,3 +94,49 @@ def test_uint8_clip_validation(model):
         model(torch.zeros(1, 6, 3, 300, 300, dtype=torch.uint8))
     with pytest.raises(ValueError, match="CUDA"):
         model(torch.zeros(1, 6, 300, 300, 3, dtype=torch.uint8))
+
+
+# ------------------------------------------------------------------------------------------------
+# ablation transformers: module tree, constructor contract, error behaviour
+# ------------------------------------------------------------------------------------------------
+def test_ablation_module_trees():
+    m = pkg()
+    v = m.ViViT(19, 1, 1, 6, depth=1)
+    sd = v.state_dict()
+    assert sd["pos_embedding"].shape == (1, 6, 362, 728)
+    assert sd["space_transformer.layers.0.0.fn.to_qkv.weight"].shape == (1536, 728)
+    assert sd["temporal_transformer.layers.0.1.fn.net.0.weight"].shape == (2912, 728)
+    assert "temporal_token" in sd and "space_token" in sd and sd["mlp_head.1.weight"].shape == (1, 728)
+    w = m.VanillaTr(19, 1, 1, 6, depth=1)
+    sd = w.state_dict()
+    assert sd["pos_embedding"].shape == (1, 6 * 361 + 1, 728) and sd["cls_token"].shape == (1, 1, 728)
+    assert sd["to_patch_embedding.1.weight"].shape == (728, 728)
+    assert sd["transformer.layers.0.0.fn.to_out.0.bias"].shape == (728,)
+    a = m.TemporalOnlyAttention(728)
+    assert a.to_qkv.weight.shape == (1536, 728) and a.scale == 0.125
+
+
+def test_ablation_constructor_contract():
+    m = pkg()
+    with pytest.raises(ValueError):
+        m.ViViT(19, 1, 1, 6, pool="max")
+    with pytest.raises(NotImplementedError):
+        m.ViViT(19, 1, 1, 6, depth=1, pool="mean")
+    with pytest.raises(ValueError):
+        m.VanillaTr(19, 2, 1, 6)                  # 19 % 2
+    with pytest.raises(ValueError):
+        m.Attention(728, dim_head=32)
+    with pytest.raises(ValueError):
+        m.XceptionVidTr(variant="joint")
+
+
+def test_ablation_no_cpu_fallback():
+    m = pkg()
+    v = m.ViViT(19, 1, 1, 6, depth=1).eval()
+    with pytest.raises(ValueError, match="CUDA"):
+        v(torch.zeros(1, 6, 728, 19, 19))
+    with pytest.raises(ValueError):
+        v(torch.zeros(1, 6, 19, 19))
+    for blk in (m.Attention(728).eval(), m.TemporalOnlyAttention(728).eval(), m.Transformer(728, 1, 8, 64, 2912).eval()):
+        with pytest.raises(ValueError, match="CUDA"):
+            blk(torch.zeros(1, 362, 728))
