@@ -37,6 +37,7 @@ SIGNATURES = {
     "istvt_attn_spatial_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "istvt_attn_joint_fwd": [_P, _P, _I, _I, _I, _I, _F, _P],
     "istvt_token_build_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P],
+    "istvt_mean_rows_fwd": [_P, _P, _I, _I, _I, _P],
     "istvt_add_fwd": [_P, _P, _P, _I, _L, _P],
     "istvt_pool_linear_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "istvt_head_fwd": [_P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],

@@ -235,6 +235,12 @@ def vivit_forward_rows(vit, rows: torch.Tensor, b: int, t: int, precision: str, 
         taps["space_cls"] = cls_rows.clone()
     tok2 = ops.token_build(cls_rows, _f32(vit.temporal_token.reshape(-1)), None, b, t)        # vivit.py:73-74
     run_transformer(tp, tok2.view(b * (t + 1), dim), b, t + 1, dt, taps, "temporal.")          # vivit.py:76
+    if vit.pool == "mean":
+        # norm over every frame token, mean over the T+1 tokens of a clip, mlp_head (vivit.py:25, 79-81)
+        normed = ops.layernorm(tok2.view(b * (t + 1), dim), tp.norm[0], tp.norm[1], torch.float32)
+        pooled = ops.layernorm(ops.mean_rows(normed, b, t + 1), *_ln(vit.mlp_head[0]), torch.float32)
+        return ops.pool_linear(pooled.view(b, 1, 1, dim), _f32(vit.mlp_head[1].weight), _f32(vit.mlp_head[1].bias),
+                               relu=False)
     # norm, x[:, 0], mlp_head (vivit.py:25, 79-81)
     return ops.head(tok2.view(b, t + 1, 1, dim), tp.norm[0], tp.norm[1], *_ln(vit.mlp_head[0]),
                     _f32(vit.mlp_head[1].weight.reshape(-1)), _f32(vit.mlp_head[1].bias))

@@ -38,9 +38,45 @@ token_build_kernel(const T* __restrict__ src, const float* __restrict__ cls, con
     }
 }
 
+// out[seq, :] = mean over the n rows of x[seq, :, :] (fp32): ViViT's `x.mean(dim = 1)` pooling, vivit.py:79.
+// One thread per 4 channels of one sequence; n is small (T + 1 frame tokens).
+__global__ void __launch_bounds__(256)
+mean_rows_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t total4, int n, int dim4) {
+    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total4;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c4 = static_cast<int>(idx % dim4);
+        const int64_t seq = idx / dim4;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int r = 0; r < n; ++r) {
+            float v[4];
+            load4(x + ((seq * n + r) * dim4 + c4) * 4, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] += v[e];
+        }
+        const float inv = 1.0f / static_cast<float>(n);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] *= inv;
+        store4(out + idx * 4, acc);
+    }
+}
+
 }  // namespace istvt
 
 using namespace istvt;
+
+extern "C" int istvt_mean_rows_fwd(const float* x, float* out, int sequences, int n, int dim, istvt_stream_t stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ISTVT_REQUIRE(x && out);
+    ISTVT_REQUIRE(sequences > 0 && n > 0 && dim > 0 && dim % 4 == 0);
+    const int dim4 = dim / 4;
+    const int64_t total4 = static_cast<int64_t>(sequences) * dim4;
+    int64_t blocks = (total4 + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    mean_rows_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(x, out, total4, n, dim4);
+    count_launch();
+    return launch_status();
+}
 
 extern "C" int istvt_token_build_fwd(const void* src, int src_dtype, const float* cls, const float* pos, float* tokens,
                                      int sequences, int n, int dim, int pos_period, istvt_stream_t stream) {

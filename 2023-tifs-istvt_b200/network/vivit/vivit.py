@@ -55,8 +55,6 @@ class ViViT(nn.Module):
                  dropout: float = 0.0, emb_dropout: float = 0.0, scale_dim: int = 4):
         super().__init__()
         _check_vit_args(pool, image_size, patch_size, in_channels, dim, dim_head, num_classes, False)
-        if pool != "cls":
-            raise NotImplementedError("istvt_b200: ViViT mean pooling (vivit.py:79) is not built; use pool='cls'")
         self.image_size, self.num_frames, self.dim, self.depth, self.heads = image_size, num_frames, dim, depth, heads
         num_patches = (image_size // patch_size) ** 2
         self.num_patches = num_patches

@@ -383,6 +383,19 @@ def token_build(src: torch.Tensor, cls: torch.Tensor, pos: Optional[torch.Tensor
     return tokens
 
 
+def mean_rows(x: torch.Tensor, sequences: int, n: int) -> torch.Tensor:
+    """x fp32 [sequences, n, dim] -> fp32 [sequences, dim], the mean over the n token rows (vivit.py:79)."""
+    dev = _chk(x)
+    dim = x.shape[-1]
+    if x.dtype != torch.float32 or x.numel() != sequences * n * dim:
+        raise ValueError("mean_rows: x must be fp32 [sequences, n, dim]")
+    out = torch.empty(sequences, dim, dtype=torch.float32, device=dev)
+    with _launch(dev, "mean_rows", 0.0, _nbytes(x, out)):
+        _lib.check(_lib.lib().istvt_mean_rows_fwd(_ptr(x), _ptr(out), sequences, n, dim, _stream(dev)),
+                   "istvt_mean_rows_fwd")
+    return out
+
+
 def head(tokens: torch.Tensor, norm_g, norm_b, head_g, head_b, head_w, head_bias, eps: float = 1e-5) -> torch.Tensor:
     """tokens: fp32 [B, F, P, D] -> logits fp32 [B, 1] from token (0, 0)."""
     dev = _chk(tokens, norm_g, norm_b, head_g, head_b, head_w, head_bias)

@@ -211,6 +211,10 @@ int istvt_attn_joint_fwd(const void* qkv, void* out, int dtype, int batch, int t
 int istvt_token_build_fwd(const void* src, int src_dtype, const float* cls, const float* pos, float* tokens,
                           int sequences, int n, int dim, int pos_period, istvt_stream_t stream);
 
+/* Mean over the n token rows of every sequence: out[s, :] = mean_r x[s, r, :] (fp32 in, fp32 out; dim % 4 == 0).
+ * Replaces: vivit.py:79 (`x.mean(dim = 1)`, ViViT with pool = 'mean'). */
+int istvt_mean_rows_fwd(const float* x, float* out, int sequences, int n, int dim, istvt_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Per-frame Xception baseline (model_selection('xception'), train_CNN.py:924-929).
  * The middle flow (blocks 4-11), block 12 and conv3 / conv4 reuse istvt_dwconv3x3_fwd, istvt_gemm_fwd (1x1 + folded

@@ -72,8 +72,9 @@ def _p(prefix: str, name: str) -> str:
     return f"{prefix}.{name}" if prefix else name
 
 
-def vivit_forward(sd: SD, feats: torch.Tensor, prefix: str = "", taps: Optional[dict] = None) -> torch.Tensor:
-    """ViViT.forward, vivit.py:60-81 (pool = 'cls').  feats [b, t, C, h, w] -> logits [b, num_classes]."""
+def vivit_forward(sd: SD, feats: torch.Tensor, prefix: str = "", taps: Optional[dict] = None,
+                  pool: str = "cls") -> torch.Tensor:
+    """ViViT.forward, vivit.py:60-81.  feats [b, t, C, h, w] -> logits [b, num_classes]."""
     b, t, c, h, w = feats.shape
     x = feats.permute(0, 1, 3, 4, 2).reshape(b, t, h * w, c)                              # Rearrange :41 (patch size 1), :61
     n = h * w
@@ -90,7 +91,7 @@ def vivit_forward(sd: SD, feats: torch.Tensor, prefix: str = "", taps: Optional[
     x = plain_transformer(sd, _p(prefix, "temporal_transformer"), x, taps, "temporal.")   # :76
     if taps is not None:
         taps["temporal_out"] = x
-    x = x[:, 0]                                                                           # :79 (pool == 'cls')
+    x = x.mean(dim=1) if pool == "mean" else x[:, 0]                                        # :79
     return F.linear(_ln(sd, _p(prefix, "mlp_head.0"), x), sd[_p(prefix, "mlp_head.1.weight")],
                     sd[_p(prefix, "mlp_head.1.bias")])                                    # :81
 

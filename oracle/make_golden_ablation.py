@@ -24,9 +24,10 @@ from oracle.make_golden import fp  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "ablation_golden.pt")
 
-# name -> (class, depth, batch, seed)
+# name -> (class, depth, batch, seed[, pool])
 MODEL_CASES = {
     "vivit_d2_b2": ("ViViT", 2, 2, 11),
+    "vivit_mean_d2_b2": ("ViViT", 2, 2, 15, "mean"),
     "vivit_d12_b1": ("ViViT", 12, 1, 12),
     "vanilla_d2_b1": ("VanillaTr", 2, 1, 13),
     "vanilla_d12_b1": ("VanillaTr", 12, 1, 14),
@@ -39,17 +40,17 @@ WEIGHT_KEYS = {
 }
 
 
-def build(vv, cls_name: str, depth: int, seed: int):
+def build(vv, cls_name: str, depth: int, seed: int, pool: str = "cls"):
     torch.manual_seed(seed)
-    m = getattr(vv, cls_name)(19, 1, 1, 6, depth=depth).eval()
+    m = getattr(vv, cls_name)(19, 1, 1, 6, depth=depth, pool=pool).eval()
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     A.sensitise_ablation_(sd)
     m.load_state_dict(sd)
     return m, sd
 
 
-def run_model_case(vv, cls_name: str, depth: int, batch: int, seed: int) -> dict:
-    m, sd = build(vv, cls_name, depth, seed)
+def run_model_case(vv, cls_name: str, depth: int, batch: int, seed: int, pool: str = "cls") -> dict:
+    m, sd = build(vv, cls_name, depth, seed, pool)
     x = A.make_features(batch, 6)
     taps = {}
     hooks = []
@@ -63,9 +64,9 @@ def run_model_case(vv, cls_name: str, depth: int, batch: int, seed: int) -> dict
         h.remove()
     variant = "vivit" if cls_name == "ViViT" else "vanilla"
     with torch.no_grad():
-        want = A.FORWARDS[variant](sd, x)
+        want = A.FORWARDS[variant](sd, x, pool=pool) if variant == "vivit" else A.FORWARDS[variant](sd, x)
     print(f"   oracle vs reference: {(want - logits).abs().max().item():.3e}")
-    return {"cls": cls_name, "depth": depth, "batch": batch, "seed": seed, "logits": logits.detach().clone(),
+    return {"cls": cls_name, "depth": depth, "batch": batch, "seed": seed, "pool": pool, "logits": logits.detach().clone(),
             "taps": {k: fp(v) for k, v in taps.items()}, "weights": {k: fp(sd[k]) for k in WEIGHT_KEYS[cls_name]}}
 
 
@@ -99,9 +100,9 @@ def main() -> None:
     torch.set_num_threads(os.cpu_count() or 8)
     vv = reference_shim.load()
     golden = {"torch_version": torch.__version__, "models": {}, "blocks": run_block_cases(vv)}
-    for name, (cls_name, depth, batch, seed) in MODEL_CASES.items():
+    for name, spec in MODEL_CASES.items():
         print(name)
-        c = run_model_case(vv, cls_name, depth, batch, seed)
+        c = run_model_case(vv, *spec)
         golden["models"][name] = c
         print("   logits", c["logits"].flatten().tolist(), {k: round(v["absmax"], 3) for k, v in c["taps"].items()})
     torch.save(golden, OUT)

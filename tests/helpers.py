@@ -107,7 +107,7 @@ def build_ablation_model(case: dict):
     """Rebuild an ablation model of tests/golden/ablation_golden.pt from its seed with the B200 package's classes (same
     construction order as the reference, oracle/make_golden_ablation.py::build) + the deterministic sensitisation."""
     torch.manual_seed(case["seed"])
-    model = getattr(pkg(), case["cls"])(19, 1, 1, 6, depth=case["depth"]).eval()
+    model = getattr(pkg(), case["cls"])(19, 1, 1, 6, depth=case["depth"], pool=case.get("pool", "cls")).eval()
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     ablation_oracle().sensitise_ablation_(sd)
     model.load_state_dict(sd)

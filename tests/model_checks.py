@@ -418,7 +418,7 @@ def run_ablation_golden(name: str, precision: str):
     variant = "vivit" if case["cls"] == "ViViT" else "vanilla"
     otaps = {}
     with torch.no_grad():
-        A.FORWARDS[variant](sd, x, "", otaps)
+        A.FORWARDS[variant](sd, x, "", otaps, **({"pool": case.get("pool", "cls")} if variant == "vivit" else {}))
     last = case["depth"] - 1
     for key in ([f"space.layer0", f"space.layer{last}", f"temporal.layer{last}"] if variant == "vivit"
                 else ["layer0", f"layer{last}"]):

@@ -50,6 +50,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.istvt_dwconv3x3_fwd(None, None, None, 0, 1, 8, 8, 8, 0, None) == -1
     assert lib.istvt_attn_joint_fwd(None, None, 0, 1, 2167, 8, 0.125, None) == -1
     assert lib.istvt_token_build_fwd(None, 0, None, None, None, 1, 361, 728, 1, None) == -1
+    assert lib.istvt_mean_rows_fwd(None, None, 1, 7, 728, None) == -1
     buf = ctypes.create_string_buffer(64)
     p = ctypes.cast(buf, ctypes.c_void_p)
     assert lib.istvt_layernorm_fwd(p, 1, p, p, p, 0, 4, 730, 1e-5, None) == -1      # dim % 4

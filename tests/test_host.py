@@ -120,8 +120,7 @@ def test_ablation_constructor_contract():
     m = pkg()
     with pytest.raises(ValueError):
         m.ViViT(19, 1, 1, 6, pool="max")
-    with pytest.raises(NotImplementedError):
-        m.ViViT(19, 1, 1, 6, depth=1, pool="mean")
+    assert m.ViViT(19, 1, 1, 6, depth=1, pool="mean").pool == "mean"
     with pytest.raises(ValueError):
         m.VanillaTr(19, 2, 1, 6)                  # 19 % 2
     with pytest.raises(ValueError):

@@ -51,7 +51,7 @@ def test_xception_baseline_against_reference_golden(precision):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("case", ["vivit_d2_b2", "vivit_d12_b1", "vanilla_d2_b1", "vanilla_d12_b1"])
+@pytest.mark.parametrize("case", ["vivit_d2_b2", "vivit_mean_d2_b2", "vivit_d12_b1", "vanilla_d2_b1", "vanilla_d12_b1"])
 def test_ablation_models_against_reference_golden(case, precision):
     model_checks.run_ablation_golden(case, precision)
 

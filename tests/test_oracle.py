@@ -157,7 +157,7 @@ def test_xception_oracle_matches_reference_golden(name):
 # ------------------------------------------------------------------------------------------------
 # ablation transformers
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["vivit_d2_b2", "vanilla_d2_b1"])
+@pytest.mark.parametrize("name", ["vivit_d2_b2", "vivit_mean_d2_b2", "vanilla_d2_b1"])
 def test_ablation_oracle_matches_reference_golden(name):
     """oracle/ablation_oracle.py vs the golden vectors oracle/make_golden_ablation.py recorded from the UNMODIFIED
     reference `ViViT` / `VanillaTr`; the weights are rebuilt from the seed with the B200 package's classes, so this
@@ -171,7 +171,8 @@ def test_ablation_oracle_matches_reference_golden(name):
     taps = {}
     variant = "vivit" if case["cls"] == "ViViT" else "vanilla"
     with torch.no_grad():
-        logits = A.FORWARDS[variant](sd, A.make_features(case["batch"], 6), "", taps)
+        kw = {"pool": case.get("pool", "cls")} if variant == "vivit" else {}
+        logits = A.FORWARDS[variant](sd, A.make_features(case["batch"], 6), "", taps, **kw)
     assert torch.allclose(logits, case["logits"], rtol=0, atol=TIGHT * max(1.0, case["logits"].abs().max().item()))
     rename = {"space_transformer_out": "space_out", "temporal_transformer_out": "temporal_out",
               "transformer_out": "transformer_out"}

@@ -37,7 +37,7 @@ def all_checks():
     checks["xception_fp32"] = lambda: model_checks.run_xception_golden("fp32")
     checks["xception_bf16"] = lambda: model_checks.run_xception_golden("bf16")
     for prec in ("fp32", "bf16"):
-        for case in ("vivit_d2_b2", "vivit_d12_b1", "vanilla_d2_b1", "vanilla_d12_b1"):
+        for case in ("vivit_d2_b2", "vivit_mean_d2_b2", "vivit_d12_b1", "vanilla_d2_b1", "vanilla_d12_b1"):
             checks[f"ablation_{case}_{prec}"] = lambda c=case, p=prec: model_checks.run_ablation_golden(c, p)
         checks[f"ablation_blocks_{prec}"] = lambda p=prec: model_checks.run_ablation_blocks(p)
     for variant in ("vivit", "vanilla"):
