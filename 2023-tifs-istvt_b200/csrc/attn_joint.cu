@@ -56,7 +56,7 @@ __device__ __forceinline__ float block_max(const uint32_t (&r)[NLD][32], int val
 
 // p = exp2(s * c - m * c) for this thread's slice, rounded to bf16 and stored as the PV MMA's A operand; returns the
 // slice's contribution to the row denominator, accumulated from the SAME rounded values the MMA consumes.
-template <int NLD, bool MASK, bool ALUPACK>
+template <int NLD, bool MASK, bool ALUPACK, bool ROUNDED_SUM = true>
 __device__ __forceinline__ float block_exp_store(const uint32_t (&r)[NLD][32], int valid, float scale_log2, float mxs,
                                                  uint8_t* prow, int chunk0, int row) {
     float sum = 0.0f;
@@ -74,7 +74,8 @@ __device__ __forceinline__ float block_exp_store(const uint32_t (&r)[NLD][32], i
             }
             if (ALUPACK) {   // round on the integer pipe: F2FP shares the XU pipe with the exponentials
                 pk[i] = pack_bf16x2_rne_alu(e0, e1);
-                sum += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
+                if (ROUNDED_SUM) sum += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
+                else sum += e0 + e1;   // round-to-nearest is unbiased: the spatial kernel sums the unrounded values too
             } else {
                 pk[i] = pack_bf16x2(e0, e1);
                 const float2 f = unpack_bf16x2(pk[i]);
@@ -310,6 +311,12 @@ attn_joint_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloa
     }
 }
 
+}  // namespace istvt
+
+#include "attn_joint_pp.cuh"
+
+namespace istvt {
+
 // ------------------------------------------------------------------------------------------
 // fp32 validation kernel: one CTA per (sequence, head, 128 queries); K and V stream through shared memory in
 // blocks of 64 keys, one query per thread with an online softmax.
@@ -408,6 +415,17 @@ static int joint_variant() {
     return v;
 }
 
+// ISTVT_JA_PP: two query tiles per CTA in ping-pong (attn_joint_pp.cuh) for sequences of at least two tiles: default (1);
+// 0 = the one-tile-per-CTA kernel above (0.365 vs 0.340 ms at 16 x 2167 tokens), 2 = ping-pong with the denominator
+// summed from the bf16-rounded P values (A/B)
+static int joint_pingpong() {
+    static const int v = [] {
+        const char* e = getenv("ISTVT_JA_PP");
+        return e != nullptr ? atoi(e) : 1;
+    }();
+    return v;
+}
+
 extern "C" int istvt_attn_joint_fwd(const void* qkv, void* out, int dtype, int batch, int tokens, int heads,
                                     float scale, istvt_stream_t stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -437,6 +455,20 @@ extern "C" int istvt_attn_joint_fwd(const void* qkv, void* out, int dtype, int b
     const float scale_log2 = scale * 1.4426950408889634f;
     const int grid = batch * heads * q_tiles;
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+    if (joint_pingpong() && q_tiles >= 2) {
+        const int pp_grid = batch * heads * ((q_tiles + 1) / 2);
+        if (joint_pingpong() == 2) {   // A/B: denominator from the bf16-rounded P values
+            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  PP_SMEM));
+            attn_joint_pp_kernel<true><<<pp_grid, PP_THREADS, PP_SMEM, st>>>(tm, o, tokens, heads, scale_log2);
+        } else {
+            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  PP_SMEM));
+            attn_joint_pp_kernel<false><<<pp_grid, PP_THREADS, PP_SMEM, st>>>(tm, o, tokens, heads, scale_log2);
+        }
+        count_launch();
+        return launch_status();
+    }
 #define ISTVT_JA_LAUNCH(SPLIT, QB, AP)                                                                                  \
     do {                                                                                                               \
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_tcgen05_kernel<SPLIT, QB, AP>,                                \
