@@ -76,15 +76,30 @@ def attention(qkv: torch.Tensor, sequences: int, tokens: int, heads: int, scale:
 
 
 def run_transformer(tp: _TransformerPack, tok: torch.Tensor, sequences: int, tokens: int, dt: torch.dtype,
-                    taps: Optional[dict] = None, tag: str = "") -> torch.Tensor:
+                    taps: Optional[dict] = None, tag: str = "", cls_only: bool = False) -> torch.Tensor:
     """`Transformer.forward` WITHOUT its final LayerNorm (vivit.py:22-24): tok fp32 [sequences*tokens, dim], updated
-    in place.  The caller applies `norm` to the rows it reads (LayerNorm is row-wise)."""
+    in place.  The caller applies `norm` to the rows it reads (LayerNorm is row-wise).
+
+    `cls_only`: the caller reads only token 0 of every sequence (vivit.py:71, :79, :189).  Everything after the last
+    layer's attention is row-wise, so that layer's output projection, residual adds and MLP then run on the class rows
+    alone and the function returns them as fp32 [sequences, dim] (`tok` is left one layer behind).  Attention itself and
+    the layers before it need every row.  Not used when intermediates are tapped."""
     rows, dim = tok.shape
     scale = 64 ** -0.5
+    prune = cls_only and taps is None and tokens > 1
     for li, lp in enumerate(tp.layers):
         xn = ops.layernorm(tok, lp.ln1[0], lp.ln1[1], dt)                               # PreNorm, module.py:21
         qkv = ops.gemm(xn, lp.w_qkv)                                                    # to_qkv, module.py:54
         a = attention(qkv, sequences, tokens, tp.heads, scale)
+        if prune and li == len(tp.layers) - 1:
+            inner = tp.heads * 64
+            a_cls = ops.gather_rows(a, sequences, tokens * inner, 1, inner, inner)      # query 0 of every sequence
+            x_cls = ops.gather_rows(tok, sequences, tokens * dim, 1, dim, dim)          # fp32 residual rows
+            ops.gemm(a_cls, lp.w_o, bias=lp.b_o, residual=x_cls, out=x_cls)
+            zn = ops.layernorm(x_cls, lp.ln2[0], lp.ln2[1], dt)
+            hid = ops.gemm(zn, lp.w_1, bias=lp.b_1, act=ops.ACT_GELU, out_dtype=dt)
+            ops.gemm(hid, lp.w_2, bias=lp.b_2, residual=x_cls, out=x_cls)
+            return x_cls
         ops.gemm(a, lp.w_o, bias=lp.b_o, residual=tok, out=tok)                         # to_out + residual, vivit.py:23
         zn = ops.layernorm(tok, lp.ln2[0], lp.ln2[1], dt)
         hid = ops.gemm(zn, lp.w_1, bias=lp.b_1, act=ops.ACT_GELU, out_dtype=dt)         # module.py:33-34
@@ -92,6 +107,8 @@ def run_transformer(tp: _TransformerPack, tok: torch.Tensor, sequences: int, tok
         if taps is not None:
             taps[f"{tag}layer{li}"] = tok.clone()
         del xn, qkv, a, zn, hid
+    if cls_only:
+        return ops.gather_rows(tok, sequences, tokens * dim, 1, dim, dim)
     return tok
 
 
@@ -142,18 +159,39 @@ def _inference_only(fn):
 # ------------------------------------------------------------------------------------------------
 # standalone blocks
 # ------------------------------------------------------------------------------------------------
+@dataclass
+class _BlockPack:
+    w_qkv: torch.Tensor
+    w_o: torch.Tensor
+    b_o: torch.Tensor
+    fingerprint: tuple = field(default_factory=tuple)
+
+
+def _pack_block(mod, dt: torch.dtype) -> _BlockPack:
+    return _BlockPack(w_qkv=mod.to_qkv.weight.detach().to(dt).contiguous(),
+                      w_o=mod.to_out[0].weight.detach().to(dt).contiguous(), b_o=_f32(mod.to_out[0].bias),
+                      fingerprint=_fingerprint(mod))
+
+
+def _block_pack(mod, dev: torch.device, precision: str) -> _BlockPack:
+    cache = mod.__dict__.get("_pack_cache")
+    if cache is None:
+        cache = _PackCache(_pack_block)
+        object.__setattr__(mod, "_pack_cache", cache)
+    return cache.get(mod, dev, precision)
+
+
 @_inference_only
 def attention_forward(mod, x: torch.Tensor, precision: str = "bf16") -> torch.Tensor:
     """`Attention.forward`, module.py:52-63: x [b, n, dim] -> [b, n, dim] fp32."""
     dt = _check_precision(precision)
     _check_tokens(x, mod.to_qkv.in_features, "Attention")
     b, n, dim = x.shape
+    bp = _block_pack(mod, x.device, precision)
     xa = x.reshape(b * n, dim).to(dt).contiguous()
-    qkv = ops.gemm(xa, mod.to_qkv.weight.detach().to(dt).contiguous())
+    qkv = ops.gemm(xa, bp.w_qkv)
     a = attention(qkv, b, n, mod.heads, mod.scale)
-    out = ops.gemm(a, mod.to_out[0].weight.detach().to(dt).contiguous(), bias=_f32(mod.to_out[0].bias),
-                   out_dtype=torch.float32)
-    return out.view(b, n, dim)
+    return ops.gemm(a, bp.w_o, bias=bp.b_o, out_dtype=torch.float32).view(b, n, dim)
 
 
 @_inference_only
@@ -167,14 +205,12 @@ def temporal_only_attention_forward(mod, x: torch.Tensor, precision: str = "bf16
     if n % p_tok:
         raise ValueError(f"TemporalOnlyAttention needs a multiple of {p_tok} tokens per clip, got {n}")
     inner = mod.heads * 64
-    w = mod.to_qkv.weight.detach().to(dt)
+    bp = _block_pack(mod, x.device, precision)
     xa = x.reshape(b * n, dim).to(dt).contiguous()
-    qk = ops.gemm(xa, w[: 2 * inner].contiguous())
-    v = ops.gemm(xa, w[2 * inner:].contiguous())
+    qk = ops.gemm(xa, bp.w_qkv[: 2 * inner])             # row slices of a contiguous [3*inner, dim] weight are contiguous
+    v = ops.gemm(xa, bp.w_qkv[2 * inner:])
     a, _ = ops.attn_temporal(qk, v, b, n // p_tok, p_tok, mod.heads, mod.scale)
-    out = ops.gemm(a, mod.to_out[0].weight.detach().to(dt).contiguous(), bias=_f32(mod.to_out[0].bias),
-                   out_dtype=torch.float32)
-    return out.view(b, n, dim)
+    return ops.gemm(a, bp.w_o, bias=bp.b_o, out_dtype=torch.float32).view(b, n, dim)
 
 
 def _tpack(tr, dev: torch.device, precision: str) -> _TransformerPack:
@@ -227,23 +263,22 @@ def vivit_forward_rows(vit, rows: torch.Tensor, b: int, t: int, precision: str, 
     tok = ops.token_build(rows, _f32(vit.space_token.reshape(-1)), _f32(vit.pos_embedding[0]), b * t, n, pos_period=t)
     if taps is not None:
         taps["tokens"] = tok.clone()
-    run_transformer(sp, tok.view(b * t * (n + 1), dim), b * t, n + 1, dt, taps, "space.")     # vivit.py:69-70
-    # x[:, 0] of the normalised output: LayerNorm is row-wise, so only the class rows are normalised (vivit.py:25,71)
-    cls_rows = ops.gather_rows(tok, b * t, (n + 1) * dim, 1, dim, dim)
+    # x[:, 0] of the normalised output: LayerNorm is row-wise, so only the class rows are normalised (vivit.py:25,70-71)
+    cls_rows = run_transformer(sp, tok.view(b * t * (n + 1), dim), b * t, n + 1, dt, taps, "space.", cls_only=True)
     cls_rows = ops.layernorm(cls_rows, sp.norm[0], sp.norm[1], torch.float32)
     if taps is not None:
         taps["space_cls"] = cls_rows.clone()
     tok2 = ops.token_build(cls_rows, _f32(vit.temporal_token.reshape(-1)), None, b, t)        # vivit.py:73-74
-    run_transformer(tp, tok2.view(b * (t + 1), dim), b, t + 1, dt, taps, "temporal.")          # vivit.py:76
+    head_w, head_b = _f32(vit.mlp_head[1].weight.reshape(-1)), _f32(vit.mlp_head[1].bias)
     if vit.pool == "mean":
         # norm over every frame token, mean over the T+1 tokens of a clip, mlp_head (vivit.py:25, 79-81)
+        run_transformer(tp, tok2.view(b * (t + 1), dim), b, t + 1, dt, taps, "temporal.")          # vivit.py:76
         normed = ops.layernorm(tok2.view(b * (t + 1), dim), tp.norm[0], tp.norm[1], torch.float32)
         pooled = ops.layernorm(ops.mean_rows(normed, b, t + 1), *_ln(vit.mlp_head[0]), torch.float32)
-        return ops.pool_linear(pooled.view(b, 1, 1, dim), _f32(vit.mlp_head[1].weight), _f32(vit.mlp_head[1].bias),
-                               relu=False)
+        return ops.pool_linear(pooled.view(b, 1, 1, dim), _f32(vit.mlp_head[1].weight), head_b, relu=False)
+    cls = run_transformer(tp, tok2.view(b * (t + 1), dim), b, t + 1, dt, taps, "temporal.", cls_only=True)
     # norm, x[:, 0], mlp_head (vivit.py:25, 79-81)
-    return ops.head(tok2.view(b, t + 1, 1, dim), tp.norm[0], tp.norm[1], *_ln(vit.mlp_head[0]),
-                    _f32(vit.mlp_head[1].weight.reshape(-1)), _f32(vit.mlp_head[1].bias))
+    return ops.head(cls.view(b, 1, 1, dim), tp.norm[0], tp.norm[1], *_ln(vit.mlp_head[0]), head_w, head_b)
 
 
 def vanilla_forward_rows(vit, rows: torch.Tensor, b: int, t: int, precision: str, taps: Optional[dict] = None
@@ -261,8 +296,8 @@ def vanilla_forward_rows(vit, rows: torch.Tensor, b: int, t: int, precision: str
     if taps is not None:
         taps["tokens"] = tok.clone()
     seq = t * n + 1
-    run_transformer(tp, tok.view(b * seq, dim), b, seq, dt, taps, "")                          # vivit.py:187
-    return ops.head(tok.view(b, seq, 1, dim), tp.norm[0], tp.norm[1], *_ln(vit.mlp_head[0]),   # vivit.py:189-191
+    cls = run_transformer(tp, tok.view(b * seq, dim), b, seq, dt, taps, "", cls_only=True)     # vivit.py:187, 189
+    return ops.head(cls.view(b, 1, 1, dim), tp.norm[0], tp.norm[1], *_ln(vit.mlp_head[0]),     # vivit.py:25, 191
                     _f32(vit.mlp_head[1].weight.reshape(-1)), _f32(vit.mlp_head[1].bias))
 
 
