@@ -20,6 +20,8 @@ One JSON line on rank 0:
                measured bf16 peak in MEASURED_PEAKS.json (or the profiling guide's fallback)
   cpu_baseline the CPU oracle port of the reference forward (oracle/istvt_oracle.py, fp32, all host threads)
                on a bounded sample of the same workload — rank 0, N=1 only
+  gpu_eager_baseline  the same op sequence as eager PyTorch on the GPU (TF32 and bf16 autocast): SURVEY.md 8(d)'s
+               "kernel to beat"; N=1 only, skipped with --no-eager-baseline
   kernels      per-kernel-family share of the step (launches, ms, TFLOP/s or GB/s) — explains `value`
 
 `--impl reference` times the reference's own algorithm on the host cores (the oracle port: the reference
@@ -150,6 +152,46 @@ def cpu_oracle_clips_per_s(batch: int, frames: int, budget_s: float, min_iters: 
                 break
         dt = time.perf_counter() - t0
     return batch * iters / dt, iters, torch.get_num_threads()
+
+
+def gpu_eager_clips_per_s(frames: int, dev, batch: int = 16, iters: int = 3):
+    """The reference's algorithm as plain eager PyTorch ops ON THE SAME B200 ("the real kernel to
+    beat"): the oracle port (same F.conv2d / F.linear / matmul / softmax / LayerNorm sequence, same permute copies and
+    materialised score tensors as the reference) with its state_dict on the GPU, (a) fp32 with TF32 tensor cores allowed,
+    (b) under torch.autocast(bfloat16).  cuDNN / cuBLAS / ATen do the work: library baselines, device-timed, inputs resident
+    in HBM.  Reported next to cpu_baseline; never part of the product path."""
+    import torch
+    from oracle import istvt_oracle as O
+    pkg = importlib.import_module(PKG)
+    torch.manual_seed(0)
+    model = pkg.XceptionVidTr(num_frames=frames).eval()
+    sd = {k: v.detach().to(dev) for k, v in model.state_dict().items()}
+    x = torch.rand(batch, frames, 3, 300, 300, generator=torch.Generator().manual_seed(1234)).to(dev)
+    out = {}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        for name, ctx in (("fp32_tf32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            def step():
+                with torch.no_grad():
+                    if ctx is None:
+                        return O.forward(sd, x)
+                    with ctx:
+                        return O.forward(sd, x)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            out[name] = batch * iters / (e0.elapsed_time(e1) / 1e3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return out, batch, iters
 
 
 def run_reference(args) -> int:
@@ -377,6 +419,16 @@ def run_ours(args) -> int:
                                     "sample": f"{iters} forwards of 1 clip x {args.frames} frames x 300x300 "
                                               f"(oracle/istvt_oracle.py, fp32, {threads} torch threads of "
                                               f"{os.cpu_count()} logical CPUs)"}
+        if world == 1 and not args.no_eager_baseline:
+            try:
+                vals, eb, ei = gpu_eager_clips_per_s(args.frames, dev, batch=min(args.batch, 64))
+                line["gpu_eager_baseline"] = {
+                    "fp32_tf32": vals["fp32_tf32"], "bf16_autocast": vals["bf16_autocast"], "unit": UNIT, "kind": "port",
+                    "sample": f"{ei} forwards of {eb} clips x {args.frames} frames x 300x300, the oracle port of the "
+                              "reference's op sequence run as eager PyTorch (cuDNN / cuBLAS / ATen) on this GPU, inputs "
+                              "resident, CUDA events"}
+            except Exception as e:  # noqa: BLE001 — a baseline must never take the bench line down
+                line["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -706,6 +758,8 @@ def main() -> int:
     ap.add_argument("--ref-clips", type=int, default=2, help="--impl reference: clips per CPU step")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip timing the reference's op sequence as eager PyTorch on the GPU (gpu_eager_baseline)")
     ap.add_argument("--variant", default="vanilla", choices=["vivit", "vanilla"], help="--mode ablation: which transformer")
     ap.add_argument("--mode", default="infer", choices=["infer", "train", "relevance", "ablation"],
                     help="infer: BASELINE.json's headline metric (C2, default; --frames 32 --batch 8 = C5); "

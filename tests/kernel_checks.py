@@ -407,7 +407,7 @@ def check_attn_joint():
         return o.permute(0, 2, 1, 3).reshape(b * n, 512)
     kept = {}
     for (b, n, amp) in ((1, 2167, 1.0), (2, 300, 1.0), (3, 128, 1.0), (2, 129, 2.0), (2, 7, 1.0), (1, 1, 1.0),
-                        (2, 1000, 3.0), (1, 256, 1.0), (20, 362, 1.5), (1, 4096, 1.0)):
+                        (2, 1000, 3.0), (1, 256, 1.0), (20, 362, 1.5), (1, 4096, 1.0), (1, 32 * 361 + 1, 1.0)):
         qkv = (_rand(b * n, 1536, seed=n + b) * amp).to(torch.bfloat16)
         o = ops.attn_joint(qkv, b, n, heads, scale)
         torch.cuda.synchronize()
