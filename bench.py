@@ -194,6 +194,56 @@ def gpu_eager_clips_per_s(frames: int, dev, batch: int = 16, iters: int = 3):
     return out, batch, iters
 
 
+def gpu_eager_train_clips_per_s(frames: int, dev, batch: int = 16, iters: int = 2):
+    """The reference's TRAINING iteration (train-mode forward with BatchNorm batch statistics, BCE-with-logits,
+    autograd backward, AdamW on the 252 trained tensors; train_CNN.py:513-533) as eager PyTorch on the same B200: the
+    oracle port (`loss_and_grads` + `adamw_update`) with its state_dict on the GPU, fp32 with TF32 allowed and under
+    torch.autocast(bfloat16).  Device-timed, inputs resident.  A reported baseline only."""
+    import torch
+    from oracle import istvt_oracle as O
+    pkg = importlib.import_module(PKG)
+    out = {}
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        for name in ("fp32_tf32", "bf16_autocast"):
+            torch.manual_seed(0)
+            model = pkg.XceptionVidTr(num_frames=frames)
+            sd = {k: v.detach().clone().to(dev) for k, v in model.state_dict().items()}
+            del model
+            x = torch.rand(batch, frames, 3, 300, 300, generator=torch.Generator().manual_seed(1234)).to(dev)
+            y = torch.randint(0, 2, (batch,), generator=torch.Generator().manual_seed(99)).to(dev)
+            mom, var = {}, {}
+
+            def step(i):
+                if name == "bf16_autocast":
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        _, _, grads = O.loss_and_grads(sd, x, y)
+                else:
+                    _, _, grads = O.loss_and_grads(sd, x, y)
+                with torch.no_grad():
+                    for k, g in grads.items():
+                        if k not in mom:
+                            mom[k], var[k] = torch.zeros_like(sd[k]), torch.zeros_like(sd[k])
+                        O.adamw_update(sd[k], g.float(), mom[k], var[k], i + 1, 1e-4)
+
+            step(0)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(iters):
+                step(i + 1)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            out[name] = batch * iters / (e0.elapsed_time(e1) / 1e3)
+            del sd, x, y, mom, var
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return out, batch, iters
+
+
 def run_reference(args) -> int:
     """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -541,6 +591,25 @@ def run_train(args) -> int:
             "whole_step": {"algorithmic_tflop_per_step": 3 * GFLOP_PER_CLIP_T6 * args.batch / 1e3,
                            "achieved_tflops_per_gpu": 3 * GFLOP_PER_CLIP_T6 * args.batch / 1e3 / (ms / args.steps * 1e-3)},
         }
+        if world == 1 and not args.no_eager_baseline:
+            try:
+                vals = None
+                for eb_try in (32, 16):      # the eager autograd graph of 64 fp32 clips does not fit 180 GB
+                    try:
+                        torch.cuda.empty_cache()
+                        vals, eb, ei = gpu_eager_train_clips_per_s(args.frames, dev, batch=eb_try)
+                        break
+                    except torch.cuda.OutOfMemoryError:
+                        continue
+                if vals is None:
+                    raise RuntimeError("out of memory at 16 clips")
+                line["gpu_eager_baseline"] = {
+                    "fp32_tf32": vals["fp32_tf32"], "bf16_autocast": vals["bf16_autocast"], "unit": UNIT, "kind": "port",
+                    "sample": f"{ei} training iterations of {eb} clips x {args.frames} frames x 300x300, the oracle port of "
+                              "the reference's train-mode forward + BCE + autograd backward + AdamW as eager PyTorch on "
+                              "this GPU, inputs resident, CUDA events"}
+            except Exception as e:  # noqa: BLE001 — a baseline must never take the bench line down
+                line["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
