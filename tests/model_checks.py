@@ -475,6 +475,15 @@ def run_ablation_clip_check(variant: str, precision: str = "bf16"):
     torch.cuda.synchronize()
     errs = {"logits": _abs_floor_err(got, want)}
     assert errs["logits"] <= TOL[precision], f"{variant}/{precision}: {errs}; got {got.flatten().tolist()} want {want.flatten().tolist()}"
+    # decoded uint8 frames through the same variant (normalisation folded into the stem convolution)
+    u8 = torch.randint(0, 256, (2, 6, 300, 300, 3), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
+    with torch.no_grad():
+        want_u8 = A.clip_forward(sd, oracle().normalise_u8(u8), variant)
+    errs["uint8"] = _abs_floor_err(model(u8.cuda()), want_u8)
+    assert errs["uint8"] <= TOL[precision], f"{variant}/{precision} uint8: {errs}"
+    # ClipStream feeds the variant model like the ISTVT model
+    outs = [o.clone() for o in pkg().ClipStream(model).run([x.pin_memory(), x.pin_memory()])]
+    assert len(outs) == 2 and _abs_floor_err(outs[1], got) == 0.0
     with pytest.raises(ValueError):
         model(x.cuda(), return_attention=True)
     model.train()
