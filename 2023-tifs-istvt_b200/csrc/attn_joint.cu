@@ -394,30 +394,12 @@ attn_joint_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, in
 
 using namespace istvt;
 
-// softmax threads per query row: 2 (default: 0.385 ms at 16 x 2167 tokens) or 4 (ISTVT_JA_SPLIT=4: 0.390 ms — more
-// warps do not help, the block loop is a latency chain, not an issue-slot shortage; kept for A/B measurements)
-static int joint_split() {
-    static const int v = [] {
-        const char* e = getenv("ISTVT_JA_SPLIT");
-        return (e != nullptr && atoi(e) == 4) ? 4 : 2;
-    }();
-    return v;
-}
-
-// A/B switch, ISTVT_JA_VARIANT: bit 0 = the row maximum is exchanged inside the row's warp group only (named barrier
-// per quad) instead of across all softmax warps, bit 1 = P rounded to bf16 on the integer pipe (F2FP shares the XU pipe
-// with the exponentials).  Measured at 16 x 2167 tokens: 0 -> 0.385 ms, 1 -> 0.368, 2 -> 0.378, 3 -> 0.365 (default).
-static int joint_variant() {
-    static const int v = [] {
-        const char* e = getenv("ISTVT_JA_VARIANT");
-        return e != nullptr ? (atoi(e) & 3) : 3;
-    }();
-    return v;
-}
-
-// ISTVT_JA_PP: two query tiles per CTA in ping-pong (attn_joint_pp.cuh) for sequences of at least two tiles: default (1);
-// 0 = the one-tile-per-CTA kernel above (0.365 vs 0.340 ms at 16 x 2167 tokens), 2 = ping-pong with the denominator
-// summed from the bf16-rounded P values (A/B)
+// Kernel choice.  Sequences of at least two query tiles run the ping-pong kernel (attn_joint_pp.cuh: 0.339 ms at 16 x 2167
+// tokens); single-tile sequences, or ISTVT_JA_PP=0 (A/B switch), the one-tile-per-CTA kernel above (0.365 ms).
+// Alternatives of the one-tile kernel that were measured through its template parameters and are not instantiated
+// (profiles/README.md r5b-r5d): 4 softmax threads per row (0.390 ms), CTA-wide instead of per-quad exchange of the row
+// maximum (0.378), F2FP instead of integer-pipe rounding of P (0.368), neither (0.385); of the ping-pong kernel: the
+// denominator summed from the bf16-rounded P (0.340 vs 0.339), paired TMEM loads (0.338, r5q).
 static int joint_pingpong() {
     static const int v = [] {
         const char* e = getenv("ISTVT_JA_PP");
@@ -456,33 +438,15 @@ extern "C" int istvt_attn_joint_fwd(const void* qkv, void* out, int dtype, int b
     const int grid = batch * heads * q_tiles;
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
     if (joint_pingpong() && q_tiles >= 2) {
-        const int pp_grid = batch * heads * ((q_tiles + 1) / 2);
-        if (joint_pingpong() == 2) {   // A/B: denominator from the bf16-rounded P values
-            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  PP_SMEM));
-            attn_joint_pp_kernel<true><<<pp_grid, PP_THREADS, PP_SMEM, st>>>(tm, o, tokens, heads, scale_log2);
-        } else {
-            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  PP_SMEM));
-            attn_joint_pp_kernel<false><<<pp_grid, PP_THREADS, PP_SMEM, st>>>(tm, o, tokens, heads, scale_log2);
-        }
-        count_launch();
-        return launch_status();
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              PP_SMEM));
+        attn_joint_pp_kernel<false><<<batch * heads * ((q_tiles + 1) / 2), PP_THREADS, PP_SMEM, st>>>(tm, o, tokens, heads,
+                                                                                                     scale_log2);
+    } else {
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_tcgen05_kernel<2, true, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, JA_SMEM));
+        attn_joint_tcgen05_kernel<2, true, true><<<grid, ja_threads(2), JA_SMEM, st>>>(tm, o, tokens, heads, scale_log2);
     }
-#define ISTVT_JA_LAUNCH(SPLIT, QB, AP)                                                                                  \
-    do {                                                                                                               \
-        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_joint_tcgen05_kernel<SPLIT, QB, AP>,                                \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, JA_SMEM));                  \
-        attn_joint_tcgen05_kernel<SPLIT, QB, AP><<<grid, ja_threads(SPLIT), JA_SMEM, st>>>(tm, o, tokens, heads,        \
-                                                                                           scale_log2);               \
-    } while (0)
-    const int variant = joint_variant();
-    if (joint_split() == 4) ISTVT_JA_LAUNCH(4, false, false);
-    else if (variant == 0) ISTVT_JA_LAUNCH(2, false, false);
-    else if (variant == 1) ISTVT_JA_LAUNCH(2, true, false);
-    else if (variant == 2) ISTVT_JA_LAUNCH(2, false, true);
-    else ISTVT_JA_LAUNCH(2, true, true);
-#undef ISTVT_JA_LAUNCH
     count_launch();
     return launch_status();
 }
