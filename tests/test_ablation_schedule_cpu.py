@@ -13,90 +13,15 @@ import importlib
 
 import pytest
 import torch
-import torch.nn.functional as F
 
+import torch_ops as tops
 from helpers import (GOLDEN_ABLATION, ablation_oracle, build_ablation_block, build_ablation_model, fingerprint_check, pkg)
-
-
-def _gemm(a, w, bias=None, residual=None, act=0, out_dtype=None, out=None):
-    y = F.linear(a.float().reshape(-1, a.shape[-1]), w.float(), bias)
-    if act == 2:
-        y = F.gelu(y)
-    elif act == 1:
-        y = F.relu(y)
-    if residual is not None:
-        y = y + residual.reshape(y.shape)
-    if out is not None:
-        out.copy_(y.reshape(out.shape))
-        return out
-    if out_dtype is None:
-        out_dtype = torch.float32 if (residual is not None or a.dtype == torch.float32) else a.dtype
-    return y.to(out_dtype).reshape(*a.shape[:-1], w.shape[0])
-
-
-def _layernorm(x, g, b, out_dtype, eps=1e-5, out=None):
-    return F.layer_norm(x.float(), (x.shape[-1],), g, b, eps).to(out_dtype)
-
-
-def _attn(qkv, seqs, n, heads, scale):
-    q, k, v = qkv.float().reshape(seqs, n, 3, heads, 64).permute(2, 0, 3, 1, 4)
-    a = torch.softmax(q @ k.transpose(-1, -2) * scale, -1)
-    return (a @ v).permute(0, 2, 1, 3).reshape(seqs * n, heads * 64).to(qkv.dtype)
-
-
-def _attn_temporal(qk, v, b, f, p, heads, scale, want_probs=False):
-    sp = lambda t: t.float().reshape(b, f, p, heads, 64).permute(0, 3, 2, 1, 4)
-    q, k, vv = sp(qk[:, :512]), sp(qk[:, 512:]), sp(v)
-    a = torch.softmax(q @ k.transpose(-1, -2) * scale, -1)
-    return (a @ vv).permute(0, 3, 2, 1, 4).reshape(b * f * p, 512).to(qk.dtype), None
-
-
-def _token_build(src, cls, pos, seqs, n, pos_period=1):
-    dim = src.shape[-1]
-    t = torch.cat((cls.reshape(1, 1, dim).expand(seqs, 1, dim), src.float().reshape(seqs, n, dim)), 1)
-    if pos is not None:
-        t = t + pos.reshape(pos_period, n + 1, dim)[torch.arange(seqs) % pos_period]
-    return t.contiguous()
-
-
-def _gather_rows(src, n_outer, outer_stride, rows, row_stride, width):
-    flat = src.reshape(-1)
-    return torch.stack([flat[o * outer_stride + r * row_stride: o * outer_stride + r * row_stride + width]
-                        for o in range(n_outer) for r in range(rows)])
-
-
-def _head(tokens, ng, nb, hg, hb, hw, hbias, eps=1e-5):
-    x = tokens[:, 0, 0]
-    x = F.layer_norm(x, (x.shape[-1],), ng, nb, eps)
-    x = F.layer_norm(x, (x.shape[-1],), hg, hb, eps)
-    return x @ hw.reshape(-1, 1) + hbias
-
-
-def _pool_linear(x, w, bias, relu=True):
-    m = x.float().reshape(x.shape[0], -1, x.shape[-1])
-    m = (F.relu(m) if relu else m).mean(1)
-    return m @ w.t() + bias
 
 
 @pytest.fixture
 def torch_ops(monkeypatch):
-    """Substitute the C-ABI wrappers by their torch definitions and let CPU tensors pass the CUDA-only guards."""
-    ops = pkg().ops
-    calls = []
-
-    def rec(name, fn):
-        def wrapped(*a, **k):
-            calls.append(name)
-            return fn(*a, **k)
-        return wrapped
-
-    for name, fn in dict(gemm=_gemm, layernorm=_layernorm, attn_joint=_attn, attn_temporal=_attn_temporal,
-                         attn_spatial=lambda qkv, bf, n, heads, scale, want_probs=False: (_attn(qkv, bf, n, heads, scale), None),
-                         token_build=_token_build, gather_rows=_gather_rows, head=_head, pool_linear=_pool_linear,
-                         mean_rows=lambda x, seqs, n: x.reshape(seqs, n, -1).mean(1)).items():
-        monkeypatch.setattr(ops, name, rec(name, fn))
-    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
-    return calls
+    """Substitute the C-ABI wrappers by their torch definitions (tests/torch_ops.py) for one test."""
+    return tops.install(monkeypatch, pkg().ops)
 
 
 @pytest.mark.parametrize("name", ["vivit_d2_b2", "vivit_mean_d2_b2", "vanilla_d2_b1"])
