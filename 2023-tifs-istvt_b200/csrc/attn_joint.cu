@@ -1,9 +1,11 @@
 // Joint self-attention over ALL tokens of a sequence, any sequence length (network/vivit/module.py:53-63,
 // `Attention.forward`: the ablation transformers `Transformer` / `ViViT` / `VanillaTr`, vivit.py:10-25,29-81,150-191).
 // At VanillaTr's 6*361+1 = 2167 tokens the score matrix no longer fits TMEM (the spatial kernel keeps all 384
-// key columns resident), so this kernel streams the keys in blocks of 128 with an online softmax.
+// key columns resident), so these kernels stream the keys in blocks of 128 with an online softmax.
 //
-// bf16 path (tcgen05): one CTA = one (sequence b, head h, 128-query tile).
+// Two bf16 kernels (tcgen05).  Sequences of at least two query tiles run attn_joint_pp_kernel (attn_joint_pp.cuh: two
+// tiles per CTA in ping-pong, the faster one); this file holds the one-tile-per-CTA kernel it grew out of, which serves
+// single-tile sequences: one CTA = one (sequence b, head h, 128-query tile).
 //   warp 0     TMA producer: Q once, then K / V blocks of 128 keys through a 4-stage ring, read in place from the
 //              packed projection output [rows, 3*heads*64] (3-D tensor map: col, token, sequence; OOB rows zero-filled)
 //   warp 1     MMA issuer:   S_j[128 x 128] = Q K_j^T      (both operands K-major SW128, accumulator in TMEM)
