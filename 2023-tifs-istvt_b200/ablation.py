@@ -43,6 +43,7 @@ class _TransformerPack:
     layers: List[_TLayerPack]
     norm: Tuple[torch.Tensor, torch.Tensor]
     heads: int
+    scale: float = 64 ** -0.5          # Attention.scale = dim_head ** -0.5 (module.py:41)
     fingerprint: tuple = field(default_factory=tuple)
 
 
@@ -58,14 +59,14 @@ def pack_transformer(tr, dt: torch.dtype) -> _TransformerPack:
     """tr: `Transformer` parameter tree (layers[i] = [PreNorm(Attention), PreNorm(FeedForward)], vivit.py:16-19)."""
     wt = lambda m: m.weight.detach().to(dt).contiguous()
     layers = []
-    heads = 8
+    heads, scale = 8, 64 ** -0.5
     for attn, ff in tr.layers:
-        heads = attn.fn.heads
+        heads, scale = attn.fn.heads, float(attn.fn.scale)
         layers.append(_TLayerPack(
             ln1=_ln(attn.norm), w_qkv=wt(attn.fn.to_qkv), w_o=wt(attn.fn.to_out[0]), b_o=_f32(attn.fn.to_out[0].bias),
             ln2=_ln(ff.norm), w_1=wt(ff.fn.net[0]), b_1=_f32(ff.fn.net[0].bias),
             w_2=wt(ff.fn.net[3]), b_2=_f32(ff.fn.net[3].bias)))
-    return _TransformerPack(layers=layers, norm=_ln(tr.norm), heads=heads, fingerprint=_fingerprint(tr))
+    return _TransformerPack(layers=layers, norm=_ln(tr.norm), heads=heads, scale=scale, fingerprint=_fingerprint(tr))
 
 
 def attention(qkv: torch.Tensor, sequences: int, tokens: int, heads: int, scale: float) -> torch.Tensor:
@@ -85,7 +86,7 @@ def run_transformer(tp: _TransformerPack, tok: torch.Tensor, sequences: int, tok
     alone and the function returns them as fp32 [sequences, dim] (`tok` is left one layer behind).  Attention itself and
     the layers before it need every row.  Not used when intermediates are tapped."""
     rows, dim = tok.shape
-    scale = 64 ** -0.5
+    scale = tp.scale
     prune = cls_only and taps is None and tokens > 1
     for li, lp in enumerate(tp.layers):
         xn = ops.layernorm(tok, lp.ln1[0], lp.ln1[1], dt)                               # PreNorm, module.py:21
@@ -142,14 +143,18 @@ def _check_tokens(x: torch.Tensor, dim: int, what: str) -> None:
 
 
 def _inference_only(fn):
-    """Public entry points: refuse a training-mode call that expects autograd (the backward kernels are built for the
-    ISTVT model only), then run without recording a graph."""
+    """Public entry points: refuse ANY training-mode call, then run without recording a graph.  In train mode the
+    reference uses BatchNorm batch statistics (and updates the running ones) and applies dropout; these paths fold the
+    running statistics into the convolutions and have no dropout kernel, so a `module.train()` call — with or without
+    `torch.no_grad()` — would silently compute something else.  The backward kernels are built for the ISTVT model
+    (DSTTr) only."""
 
     @functools.wraps(fn)
     def wrapper(module, *args, **kwargs):
-        if module.training and torch.is_grad_enabled():
-            raise NotImplementedError(f"istvt_b200: {type(module).__name__} is an inference path here (model.eval() / "
-                                      "torch.no_grad()); the training step is built for the ISTVT model (DSTTr) only")
+        if module.training:
+            raise NotImplementedError(f"istvt_b200: {type(module).__name__} is an inference path here: call "
+                                      "model.eval() first (train mode means BatchNorm batch statistics and dropout in "
+                                      "the reference; the training step is built for the ISTVT model, DSTTr, only)")
         with torch.no_grad():
             return fn(module, *args, **kwargs)
 
@@ -240,8 +245,12 @@ def _features_nhwc(x: torch.Tensor, vit, dt: torch.dtype) -> Tuple[torch.Tensor,
     """[b, t, C, h, w] feature maps (the reference's layout, vivit.py:41 / :162) -> patch rows [b*t*h*w, C].  The
     layout change is the reference's own `Rearrange('b t c h w -> b t (h w) c')`; inside `XceptionVidTr` the entry
     flow already produces this layout and nothing is permuted."""
-    if not isinstance(x, torch.Tensor) or x.dim() != 5 or x.shape[2] != vit.dim:
-        raise ValueError(f"{type(vit).__name__} expects feature maps [b, t, {vit.dim}, h, w]")
+    # ViViT consumes the channels as tokens directly (in_channels == dim); VanillaTr projects them with its patch
+    # Linear first (vivit.py:162-167), so its channel count is that layer's in_features, not `dim`
+    emb = vit.to_patch_embedding[1] if len(vit.to_patch_embedding) > 1 else None
+    chans = emb.in_features if isinstance(emb, torch.nn.Linear) else vit.dim
+    if not isinstance(x, torch.Tensor) or x.dim() != 5 or x.shape[2] != chans:
+        raise ValueError(f"{type(vit).__name__} expects feature maps [b, t, {chans}, h, w]")
     if not x.is_cuda:
         raise ValueError(f"{type(vit).__name__} (istvt_b200) runs on CUDA tensors only: there is no CPU fallback by design")
     b, t, c, h, w = x.shape

@@ -10,6 +10,7 @@
 // online softmax over the F key frames (all lanes of a warp with the same head read K/V by broadcast;
 // the +8 element row padding keeps different heads on different banks).
 #include "common.cuh"
+#include "ptx.cuh"
 #include "simt_util.cuh"
 
 namespace istvt {
@@ -240,6 +241,192 @@ attn_temporal_mma_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------------
+// bf16 production kernel for 8 < F <= 16 * MT frames (MT = 2, 3: the long-clip configuration C5 has F = 33), the same
+// one-warp-per-(clip, position, head), registers-only mma.sync scheme as above with the frame axis tiled:
+//   * K is held as B fragments of Q.K^T for every 8-key n-tile (row 8 nj + g, 16-byte chunks t and t + 4), V as B
+//     fragments of P.V for every 16-key k-step (rows 16 kk + 2t, + 1, + 8, + 9, chunk g; byte-permuted per n-tile);
+//   * the query frames are walked in m16 tiles: Q rows 16 mi + g and + 8 (A fragments), S = 16 x 8 NT scores, softmax
+//     over the NT n-tiles and the quad, and the score accumulators ARE the A fragments of P.V (c0,c1 / c2,c3 of n-tiles
+//     2 kk and 2 kk + 1 = a0 / a1 and a2 / a3 of k-step kk) — no shuffles, no shared memory;
+//   * the head-dim permutations are those of the F <= 8 kernel, so every global access is a 16-byte vector and every
+//     lane stores 2 x 16 contiguous bytes per output row.
+// HBM traffic = q, k, v once + the output once (4 KB per token row); 4 warps per CTA so that 2-3 CTAs overlap their
+// load and compute phases on one SM.
+// ------------------------------------------------------------------------------------------
+template <int MT>
+__global__ void __launch_bounds__(128)
+attn_temporal_mma_wide_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
+                              __nv_bfloat16* __restrict__ out, float* __restrict__ probs, int frames, int tokens,
+                              int heads, float scale_log2, int64_t units) {
+    constexpr int NT = 2 * MT;        // 8-key n-tiles of Q.K^T
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int64_t unit = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+    if (unit >= units) return;
+    const int h = static_cast<int>(unit % heads);
+    const int64_t bp = unit / heads;
+    const int64_t b = bp / tokens;
+    const int pos = static_cast<int>(bp - b * tokens);
+    const int inner = heads * TA_DH;
+    const int64_t row0 = b * frames * tokens + pos;
+    const int64_t qk_pitch = static_cast<int64_t>(tokens) * (2 * inner);      // elements between consecutive frames
+    const int64_t v_pitch = static_cast<int64_t>(tokens) * inner;
+    const __nv_bfloat16* qbase = qk + row0 * (2 * inner) + h * TA_DH;
+    const __nv_bfloat16* vbase = v + row0 * inner + h * TA_DH;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+
+    // ---- K fragments: key 8 nj + g, head-dim chunks t and t + 4 ----
+    uint4 kf[NT][2];
+#pragma unroll
+    for (int nj = 0; nj < NT; ++nj) {
+        const int key = 8 * nj + g;
+        kf[nj][0] = kf[nj][1] = zero;
+        if (key < frames) {
+            const __nv_bfloat16* kp = qbase + key * qk_pitch + inner;
+            kf[nj][0] = ldg_nc_u4(kp + 8 * t);
+            kf[nj][1] = ldg_nc_u4(kp + 8 * (t + 4));
+        }
+    }
+    // ---- V fragments: keys 16 kk + {2t, 2t+1, 2t+8, 2t+9}, head-dim chunk g ----
+    uint4 vf[MT][4];
+#pragma unroll
+    for (int kk = 0; kk < MT; ++kk)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int key = 16 * kk + 2 * t + (r & 1) + 8 * (r >> 1);
+            vf[kk][r] = zero;
+            if (key < frames) vf[kk][r] = ldg_nc_u4(vbase + key * v_pitch + 8 * g);
+        }
+
+    auto pk = [](float x, float y) {
+        const __nv_bfloat162 r = __floats2bfloat162_rn(x, y);
+        return *reinterpret_cast<const uint32_t*>(&r);
+    };
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+        if (16 * mi >= frames) break;                    // warp-uniform
+        const int r0 = 16 * mi + g, r1 = r0 + 8;         // the two query frames of this lane
+        uint4 qa[2][2] = {{zero, zero}, {zero, zero}};
+        if (r0 < frames) {
+            qa[0][0] = ldg_nc_u4(qbase + r0 * qk_pitch + 8 * t);
+            qa[0][1] = ldg_nc_u4(qbase + r0 * qk_pitch + 8 * (t + 4));
+        }
+        if (r1 < frames) {
+            qa[1][0] = ldg_nc_u4(qbase + r1 * qk_pitch + 8 * t);
+            qa[1][1] = ldg_nc_u4(qbase + r1 * qk_pitch + 8 * (t + 4));
+        }
+        // ---- S = Q K^T: s[nj] = {S[r0][8nj+2t], S[r0][8nj+2t+1], S[r1][8nj+2t], S[r1][8nj+2t+1]} ----
+        float s[NT][4];
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj) {
+            s[nj][0] = s[nj][1] = s[nj][2] = s[nj][3] = 0.f;
+            if (8 * nj < frames) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    mma_bf16_16816(s[nj], qa[0][c].x, qa[1][c].x, qa[0][c].y, qa[1][c].y, kf[nj][c].x, kf[nj][c].y);
+                    mma_bf16_16816(s[nj], qa[0][c].z, qa[1][c].z, qa[0][c].w, qa[1][c].w, kf[nj][c].z, kf[nj][c].w);
+                }
+            }
+        }
+        // ---- softmax over the keys (n-tiles x quad lanes) ----
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const bool ok = 8 * nj + 2 * t + e < frames;
+                s[nj][e] = ok ? s[nj][e] * scale_log2 : -INFINITY;
+                s[nj][2 + e] = ok ? s[nj][2 + e] * scale_log2 : -INFINITY;
+                mx0 = fmaxf(mx0, s[nj][e]);
+                mx1 = fmaxf(mx1, s[nj][2 + e]);
+            }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        uint32_t pa[NT][2];            // bf16 P: [nj][0] = row r0, [nj][1] = row r1
+        float sum0 = 0.f, sum1 = 0.f, sum0_32 = 0.f, sum1_32 = 0.f;
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float pe;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(s[nj][e] - (e < 2 ? mx0 : mx1)));
+                s[nj][e] = pe;
+            }
+            sum0_32 += s[nj][0] + s[nj][1];
+            sum1_32 += s[nj][2] + s[nj][3];
+            // the P.V MMA consumes bf16 P: normalise by the sum of the rounded values
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(s[nj][0], s[nj][1]);
+            const __nv_bfloat162 p1 = __floats2bfloat162_rn(s[nj][2], s[nj][3]);
+            pa[nj][0] = *reinterpret_cast<const uint32_t*>(&p0);
+            pa[nj][1] = *reinterpret_cast<const uint32_t*>(&p1);
+            const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+            sum0 += f0.x + f0.y;
+            sum1 += f1.x + f1.y;
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+
+        if (probs != nullptr) {    // probs[b, h, pos, i, j], fp32, from the unrounded exponentials
+            sum0_32 += __shfl_xor_sync(0xffffffffu, sum0_32, 1);
+            sum0_32 += __shfl_xor_sync(0xffffffffu, sum0_32, 2);
+            sum1_32 += __shfl_xor_sync(0xffffffffu, sum1_32, 1);
+            sum1_32 += __shfl_xor_sync(0xffffffffu, sum1_32, 2);
+            const float i0 = 1.0f / sum0_32, i1 = 1.0f / sum1_32;
+            float* pr = probs + (((b * heads + h) * tokens + pos) * frames) * frames;
+#pragma unroll
+            for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int key = 8 * nj + 2 * t + e;
+                    if (key < frames) {
+                        if (r0 < frames) pr[static_cast<int64_t>(r0) * frames + key] = s[nj][e] * i0;
+                        if (r1 < frames) pr[static_cast<int64_t>(r1) * frames + key] = s[nj][2 + e] * i1;
+                    }
+                }
+        }
+
+        // ---- O = P V: lane owns dims [16t, 16t+16) of rows r0 and r1 ----
+        float o[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < MT; ++kk) {
+            if (16 * kk >= frames) break;               // warp-uniform
+            const uint32_t w0[4] = {vf[kk][0].x, vf[kk][0].y, vf[kk][0].z, vf[kk][0].w};
+            const uint32_t w1[4] = {vf[kk][1].x, vf[kk][1].y, vf[kk][1].z, vf[kk][1].w};
+            const uint32_t w2[4] = {vf[kk][2].x, vf[kk][2].y, vf[kk][2].z, vf[kk][2].w};
+            const uint32_t w3[4] = {vf[kk][3].x, vf[kk][3].y, vf[kk][3].z, vf[kk][3].w};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const uint32_t sel = (nt & 1) ? 0x7632 : 0x5410;
+                const uint32_t b0 = __byte_perm(w0[nt >> 1], w1[nt >> 1], sel);
+                const uint32_t b1 = __byte_perm(w2[nt >> 1], w3[nt >> 1], sel);
+                mma_bf16_16816(o[nt], pa[2 * kk][0], pa[2 * kk][1], pa[2 * kk + 1][0], pa[2 * kk + 1][1], b0, b1);
+            }
+        }
+        auto store_row = [&](int r, float inv, int e0) {
+            __nv_bfloat16* op = out + (row0 + static_cast<int64_t>(r) * tokens) * inner + h * TA_DH + 16 * t;
+            uint4 a, c;
+            a.x = pk(o[0][e0] * inv, o[1][e0] * inv); a.y = pk(o[2][e0] * inv, o[3][e0] * inv);
+            a.z = pk(o[4][e0] * inv, o[5][e0] * inv); a.w = pk(o[6][e0] * inv, o[7][e0] * inv);
+            c.x = pk(o[0][e0 + 1] * inv, o[1][e0 + 1] * inv); c.y = pk(o[2][e0 + 1] * inv, o[3][e0 + 1] * inv);
+            c.z = pk(o[4][e0 + 1] * inv, o[5][e0 + 1] * inv); c.w = pk(o[6][e0 + 1] * inv, o[7][e0 + 1] * inv);
+            *reinterpret_cast<uint4*>(op) = a;
+            *reinterpret_cast<uint4*>(op + 8) = c;
+        };
+        if (r0 < frames) store_row(r0, inv0, 0);
+        if (r1 < frames) store_row(r1, inv1, 2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Backward of the temporal attention for F <= 8 frames, same one-warp-per-(clip, position, head) mma.sync
 // scheme as the forward (everything stays in registers; probabilities are recomputed):
 //   S = Q K^T, P = softmax(S * scale), dP = dO V^T, D_i = sum_j P_ij dP_ij, dS = P o (dP - D) * scale
@@ -257,8 +444,8 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
 __global__ void __launch_bounds__(256)
 attn_temporal_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
                              const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqk,
-                             __nv_bfloat16* __restrict__ dv, float* __restrict__ cam, int frames, int tokens, int heads,
-                             float scale, int64_t units) {
+                             __nv_bfloat16* __restrict__ dv, float* __restrict__ cam, int frames, int tokens,
+                             int heads, float scale, int64_t units) {
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2;
     const int t = lane & 3;
@@ -377,6 +564,249 @@ attn_temporal_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bf
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward of the temporal attention for 8 < F <= 16 * MT frames (MT = 2, 3): one warp per (clip, position, head) on
+// mma.sync again, but with the four operand matrices of the unit (Q, K, V, dO: RP = 16 MT rows x 64 dims, rows >= F
+// zero-filled) staged ONCE in shared memory by cp.async (16-byte chunks XOR-swizzled by row) and read back with
+// ldmatrix — every tensor is needed in two fragment roles here (K: B of Q.K^T with k = dim, and B of dS.K with
+// k = key; Q: A of Q.K^T, and B of dS^T.Q; ...), which the registers-only scheme of the forward cannot hold.
+//   phase A, per 16-query tile mi:  S = Q K^T, dP = dO V^T, P = softmax(S scale), D = rowsum(P o dP),
+//                                   dS = P o (dP - D) scale, dQ[mi] = dS K; P and dS stay in registers as bf16 pairs
+//   phase B, per 16-key tile kj:    dV[kj] = sum_mi P[mi, kj]^T dO[mi], dK[kj] = sum_mi dS[mi, kj]^T Q[mi]
+//                                   (A fragments = movmatrix transposes of the 8x8 blocks of P / dS)
+// Zero rows are inert: a padded query row has dO = 0, hence dP = D = dS = 0 and no contribution to dV / dK.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// byte offset of 16-byte chunk `chunk` of row `row` in a [rows][64] bf16 tile (128-byte rows)
+__device__ __forceinline__ uint32_t tw_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+template <int MT>
+__global__ void __launch_bounds__(128)
+attn_temporal_bwd_wide_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
+                              const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dqk,
+                              __nv_bfloat16* __restrict__ dv, float* __restrict__ cam, int frames, int tokens,
+                              int heads, float scale, int64_t units) {
+    constexpr int NT = 2 * MT;
+    constexpr int RP = 16 * MT;                      // padded rows per tensor
+    constexpr int TILE_BYTES = RP * 128;
+    extern __shared__ __align__(128) uint8_t tw_smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int64_t unit = static_cast<int64_t>(blockIdx.x) * 4 + warp;
+    if (unit >= units) return;
+    const int h = static_cast<int>(unit % heads);
+    const int64_t bp = unit / heads;
+    const int64_t b = bp / tokens;
+    const int pos = static_cast<int>(bp - b * tokens);
+    const int inner = heads * TA_DH;
+    const int64_t row0 = b * frames * tokens + pos;
+    const float scale_log2 = scale * 1.4426950408889634f;
+
+    const uint32_t sq = smem_u32(tw_smem) + warp * (4 * TILE_BYTES);
+    const uint32_t sk = sq + TILE_BYTES, sv = sk + TILE_BYTES, sdo = sv + TILE_BYTES;
+
+    // ---- stage Q, K, V, dO (zero-fill rows >= frames) ----
+    {
+        const __nv_bfloat16* qb = qk + row0 * (2 * inner) + h * TA_DH;
+        const __nv_bfloat16* vb = v + row0 * inner + h * TA_DH;
+        const __nv_bfloat16* ob = dout + row0 * inner + h * TA_DH;
+        for (int i = lane; i < RP * 8; i += 32) {
+            const int row = i >> 3, chunk = i & 7;
+            const bool ok = row < frames;
+            const int64_t r = ok ? row : 0;
+            const uint32_t n = ok ? 16u : 0u;
+            const uint32_t off = tw_off(row, chunk);
+            const __nv_bfloat16* qp = qb + r * tokens * (2 * inner) + chunk * 8;
+            const __nv_bfloat16* vp = vb + r * tokens * inner + chunk * 8;
+            const __nv_bfloat16* op = ob + r * tokens * inner + chunk * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sq + off), "l"(qp), "r"(n) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sk + off), "l"(qp + inner), "r"(n) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sv + off), "l"(vp), "r"(n) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdo + off), "l"(op), "r"(n) : "memory");
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+    }
+
+    auto pk = [](float x, float y) {
+        const __nv_bfloat162 r = __floats2bfloat162_rn(x, y);
+        return *reinterpret_cast<const uint32_t*>(&r);
+    };
+    // ldmatrix lane addressing (see the fragment maps in the kernel comment)
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_chunk = lane >> 4;     // A tiles and transposed B tiles
+    const int b_row = lane & 7, b_chunk = lane >> 3;                               // B tiles of X.Y^T (k = head dim)
+
+    uint32_t pp[MT][NT][2], dsp[MT][NT][2];       // bf16 pairs: [..][0] = row 16 mi + g, [..][1] = row 16 mi + g + 8
+
+    // ================= phase A =================
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+        uint32_t qa[4][4], da[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            ldsm_x4(sq + tw_off(16 * mi + a_row, 2 * ks + a_chunk), qa[ks]);
+            ldsm_x4(sdo + tw_off(16 * mi + a_row, 2 * ks + a_chunk), da[ks]);
+        }
+        float s[NT][4], dp[NT][4];
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj) {
+            s[nj][0] = s[nj][1] = s[nj][2] = s[nj][3] = 0.f;
+            dp[nj][0] = dp[nj][1] = dp[nj][2] = dp[nj][3] = 0.f;
+#pragma unroll
+            for (int hk = 0; hk < 2; ++hk) {          // 32 head dims per ldmatrix.x4
+                uint32_t kb[4], vb4[4];
+                ldsm_x4(sk + tw_off(8 * nj + b_row, 4 * hk + b_chunk), kb);
+                ldsm_x4(sv + tw_off(8 * nj + b_row, 4 * hk + b_chunk), vb4);
+                mma_bf16_16816(s[nj], qa[2 * hk][0], qa[2 * hk][1], qa[2 * hk][2], qa[2 * hk][3], kb[0], kb[1]);
+                mma_bf16_16816(s[nj], qa[2 * hk + 1][0], qa[2 * hk + 1][1], qa[2 * hk + 1][2], qa[2 * hk + 1][3], kb[2], kb[3]);
+                mma_bf16_16816(dp[nj], da[2 * hk][0], da[2 * hk][1], da[2 * hk][2], da[2 * hk][3], vb4[0], vb4[1]);
+                mma_bf16_16816(dp[nj], da[2 * hk + 1][0], da[2 * hk + 1][1], da[2 * hk + 1][2], da[2 * hk + 1][3], vb4[2], vb4[3]);
+            }
+        }
+        // ---- softmax rows r0 = 16 mi + g (elements 0, 1) and r1 = r0 + 8 (elements 2, 3) ----
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const bool ok = 8 * nj + 2 * t + e < frames;
+                s[nj][e] = ok ? s[nj][e] * scale_log2 : -INFINITY;
+                s[nj][2 + e] = ok ? s[nj][2 + e] * scale_log2 : -INFINITY;
+                mx0 = fmaxf(mx0, s[nj][e]);
+                mx1 = fmaxf(mx1, s[nj][2 + e]);
+            }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float pe;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(s[nj][e] - (e < 2 ? mx0 : mx1)));
+                s[nj][e] = pe;
+                if (e < 2) sum0 += pe; else sum1 += pe;
+            }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj) {
+            s[nj][0] *= inv0; s[nj][1] *= inv0; s[nj][2] *= inv1; s[nj][3] *= inv1;
+            d0 += s[nj][0] * dp[nj][0] + s[nj][1] * dp[nj][1];
+            d1 += s[nj][2] * dp[nj][2] + s[nj][3] * dp[nj][3];
+        }
+        d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+        d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+        const int r0 = 16 * mi + g, r1 = r0 + 8;
+        if (cam != nullptr) {
+            // relevance pass: cam[b, pos, i, j] += relu(dA o A) / heads
+            float* cr = cam + (b * tokens + pos) * frames * frames;
+            const float ih = 1.0f / static_cast<float>(heads);
+#pragma unroll
+            for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int key = 8 * nj + 2 * t + e;
+                    if (key < frames) {
+                        if (r0 < frames) atomicAdd(cr + r0 * frames + key, fmaxf(s[nj][e] * dp[nj][e], 0.f) * ih);
+                        if (r1 < frames) atomicAdd(cr + r1 * frames + key, fmaxf(s[nj][2 + e] * dp[nj][2 + e], 0.f) * ih);
+                    }
+                }
+        }
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj) {
+            pp[mi][nj][0] = pk(s[nj][0], s[nj][1]);
+            pp[mi][nj][1] = pk(s[nj][2], s[nj][3]);
+            dsp[mi][nj][0] = pk(s[nj][0] * (dp[nj][0] - d0) * scale, s[nj][1] * (dp[nj][1] - d0) * scale);
+            dsp[mi][nj][1] = pk(s[nj][2] * (dp[nj][2] - d1) * scale, s[nj][3] * (dp[nj][3] - d1) * scale);
+        }
+        // ---- dQ[mi] = dS[mi] K ----
+        float dq[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < MT; ++kk)
+#pragma unroll
+            for (int n2 = 0; n2 < 4; ++n2) {           // 16 head dims per ldmatrix.x4.trans
+                uint32_t kb[4];
+                ldsm_x4_trans(sk + tw_off(16 * kk + a_row, 2 * n2 + a_chunk), kb);
+                mma_bf16_16816(dq[2 * n2], dsp[mi][2 * kk][0], dsp[mi][2 * kk][1], dsp[mi][2 * kk + 1][0],
+                               dsp[mi][2 * kk + 1][1], kb[0], kb[1]);
+                mma_bf16_16816(dq[2 * n2 + 1], dsp[mi][2 * kk][0], dsp[mi][2 * kk][1], dsp[mi][2 * kk + 1][0],
+                               dsp[mi][2 * kk + 1][1], kb[2], kb[3]);
+            }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            if (r0 < frames)
+                *reinterpret_cast<uint32_t*>(dqk + (row0 + static_cast<int64_t>(r0) * tokens) * (2 * inner) + h * TA_DH + 8 * nt + 2 * t) =
+                    pk(dq[nt][0], dq[nt][1]);
+            if (r1 < frames)
+                *reinterpret_cast<uint32_t*>(dqk + (row0 + static_cast<int64_t>(r1) * tokens) * (2 * inner) + h * TA_DH + 8 * nt + 2 * t) =
+                    pk(dq[nt][2], dq[nt][3]);
+        }
+    }
+
+    // ================= phase B =================
+#pragma unroll
+    for (int kj = 0; kj < MT; ++kj) {
+        if (16 * kj >= frames) break;          // warp-uniform
+        float dvv[8][4], dkk[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            dvv[nt][0] = dvv[nt][1] = dvv[nt][2] = dvv[nt][3] = 0.f;
+            dkk[nt][0] = dkk[nt][1] = dkk[nt][2] = dkk[nt][3] = 0.f;
+        }
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+            const uint32_t pa0 = movmatrix_trans(pp[mi][2 * kj][0]), pa1 = movmatrix_trans(pp[mi][2 * kj + 1][0]);
+            const uint32_t pa2 = movmatrix_trans(pp[mi][2 * kj][1]), pa3 = movmatrix_trans(pp[mi][2 * kj + 1][1]);
+            const uint32_t sa0 = movmatrix_trans(dsp[mi][2 * kj][0]), sa1 = movmatrix_trans(dsp[mi][2 * kj + 1][0]);
+            const uint32_t sa2 = movmatrix_trans(dsp[mi][2 * kj][1]), sa3 = movmatrix_trans(dsp[mi][2 * kj + 1][1]);
+#pragma unroll
+            for (int n2 = 0; n2 < 4; ++n2) {
+                uint32_t ob[4], qb4[4];
+                ldsm_x4_trans(sdo + tw_off(16 * mi + a_row, 2 * n2 + a_chunk), ob);
+                ldsm_x4_trans(sq + tw_off(16 * mi + a_row, 2 * n2 + a_chunk), qb4);
+                mma_bf16_16816(dvv[2 * n2], pa0, pa1, pa2, pa3, ob[0], ob[1]);
+                mma_bf16_16816(dvv[2 * n2 + 1], pa0, pa1, pa2, pa3, ob[2], ob[3]);
+                mma_bf16_16816(dkk[2 * n2], sa0, sa1, sa2, sa3, qb4[0], qb4[1]);
+                mma_bf16_16816(dkk[2 * n2 + 1], sa0, sa1, sa2, sa3, qb4[2], qb4[3]);
+            }
+        }
+        const int r0 = 16 * kj + g, r1 = r0 + 8;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            if (r0 < frames) {
+                const int64_t r = row0 + static_cast<int64_t>(r0) * tokens;
+                *reinterpret_cast<uint32_t*>(dqk + r * (2 * inner) + inner + h * TA_DH + 8 * nt + 2 * t) = pk(dkk[nt][0], dkk[nt][1]);
+                *reinterpret_cast<uint32_t*>(dv + r * inner + h * TA_DH + 8 * nt + 2 * t) = pk(dvv[nt][0], dvv[nt][1]);
+            }
+            if (r1 < frames) {
+                const int64_t r = row0 + static_cast<int64_t>(r1) * tokens;
+                *reinterpret_cast<uint32_t*>(dqk + r * (2 * inner) + inner + h * TA_DH + 8 * nt + 2 * t) = pk(dkk[nt][2], dkk[nt][3]);
+                *reinterpret_cast<uint32_t*>(dv + r * inner + h * TA_DH + 8 * nt + 2 * t) = pk(dvv[nt][2], dvv[nt][3]);
+            }
+        }
+    }
+}
+
 template <typename T>
 static int launch_temporal(const void* qk, const void* v, void* out, float* probs, int batch, int frames,
                            int tokens, int heads, float scale, cudaStream_t st) {
@@ -413,6 +843,24 @@ extern "C" int istvt_attn_temporal_fwd(const void* qk, const void* v, void* out,
         count_launch();
         return launch_status();
     }
+    if (dtype == ISTVT_BF16 && frames <= 48) {
+        ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(v) |
+                        reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+        const int64_t units = static_cast<int64_t>(batch) * tokens * heads;
+        const int64_t grid = (units + 3) / 4;
+        ISTVT_REQUIRE(grid < (int64_t(1) << 31));
+        const float sl2 = scale * 1.4426950408889634f;
+        if (frames <= 32)
+            attn_temporal_mma_wide_kernel<2><<<static_cast<unsigned>(grid), 128, 0, st>>>(
+                static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v),
+                static_cast<__nv_bfloat16*>(out), probs, frames, tokens, heads, sl2, units);
+        else
+            attn_temporal_mma_wide_kernel<3><<<static_cast<unsigned>(grid), 128, 0, st>>>(
+                static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v),
+                static_cast<__nv_bfloat16*>(out), probs, frames, tokens, heads, sl2, units);
+        count_launch();
+        return launch_status();
+    }
     ISTVT_REQUIRE(heads * frames <= 288);
     ISTVT_REQUIRE(static_cast<int64_t>(batch) * tokens < (int64_t(1) << 31));
     if (dtype == ISTVT_BF16)
@@ -421,17 +869,40 @@ extern "C" int istvt_attn_temporal_fwd(const void* qk, const void* v, void* out,
     return ISTVT_ERR_INVALID_ARG;
 }
 
+template <int MT>
+static int launch_temporal_bwd_wide(const void* qk, const void* v, const void* dout, void* dqk, void* dv, float* cam,
+                                    int frames, int tokens, int heads, float scale, int64_t units,
+                                    cudaStream_t st) {
+    const int smem = 4 * 4 * (16 * MT) * 128;      // 4 warps x {Q, K, V, dO} x padded rows x 128 B
+    auto kern = attn_temporal_bwd_wide_kernel<MT>;
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t grid = (units + 3) / 4;
+    ISTVT_REQUIRE(grid < (int64_t(1) << 31));
+    kern<<<static_cast<unsigned>(grid), 128, smem, st>>>(
+        static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v),
+        static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), cam,
+        frames, tokens, heads, scale, units);
+    count_launch();
+    return launch_status();
+}
+
 static int attn_temporal_bwd_launch(const void* qk, const void* v, const void* dout, void* dqk, void* dv, float* cam,
-                                    int batch, int frames, int tokens, int heads, float scale, istvt_stream_t stream) {
+                                    int batch, int frames, int tokens, int heads, float scale,
+                                    istvt_stream_t stream) {
     ISTVT_REQUIRE(qk && v && dout && dqk && dv);
     ISTVT_REQUIRE(batch > 0 && frames > 0 && tokens > 0 && heads > 0);
-    if (frames > 8) return ISTVT_ERR_UNSUPPORTED;   // training is built for the ISTVT configuration (T = 6, F = 7)
+    if (frames > 48) return ISTVT_ERR_UNSUPPORTED;   // mma.sync kernels cover T <= 47 frames (C5: T = 32)
     ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(qk) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(dout) |
                     reinterpret_cast<uintptr_t>(dqk) | reinterpret_cast<uintptr_t>(dv)) & 15) == 0);
     const int64_t units = static_cast<int64_t>(batch) * tokens * heads;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (frames > 32)
+        return launch_temporal_bwd_wide<3>(qk, v, dout, dqk, dv, cam, frames, tokens, heads, scale, units, st);
+    if (frames > 8)
+        return launch_temporal_bwd_wide<2>(qk, v, dout, dqk, dv, cam, frames, tokens, heads, scale, units, st);
     const int64_t grid = (units + 7) / 8;
     ISTVT_REQUIRE(grid < (int64_t(1) << 31));
-    attn_temporal_bwd_mma_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    attn_temporal_bwd_mma_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v),
         static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), cam,
         frames, tokens, heads, scale, units);

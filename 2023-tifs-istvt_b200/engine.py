@@ -14,6 +14,7 @@ BatchNorm (eval mode) is folded: scale into the bf16 weights, shift into the GEM
 """
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -337,15 +338,30 @@ def entry_flow_features(xcep, x: torch.Tensor, precision: str = "fp32") -> torch
 
 
 class ISTVTEngine:
+    """Packed-weight cache + forward schedule.  One engine serves a model AND its `nn.DataParallel` replicas
+    (train_CNN.py:185-186): packs are cached per (device, precision) and validated against the OWNER's parameters
+    (storage pointer + version counter of every on-path tensor), not against the replica's — a replica's parameters
+    are fresh broadcast copies on every forward, so a fingerprint of those would force a full re-pack per replica per
+    step.  The pack itself is built from the tensors of the module it is asked for (they live on that module's device
+    and hold the owner's values)."""
+
     def __init__(self, model):
+        self._owner = weakref.ref(model)
         self._packs: Dict[Tuple[str, str], _Pack] = {}
+
+    def _fingerprint(self, model) -> tuple:
+        owner = self._owner()
+        if owner is None or not getattr(model, "_is_replica", False):
+            owner = model
+        return _fingerprint(owner)
 
     def _pack(self, model, dev: torch.device, precision: str) -> _Pack:
         key = (str(dev), precision)
         pack = self._packs.get(key)
-        fp = _fingerprint(model)
+        fp = self._fingerprint(model)
         if pack is None or pack.fingerprint != fp:
             pack = pack_model(model, PRECISIONS[precision])
+            pack.fingerprint = fp
             self._packs[key] = pack
         return pack
 
@@ -377,14 +393,10 @@ class ISTVTEngine:
             raise ValueError("uint8 clips are an inference-path input: normalise to fp32 [B, T, 3, H, W] for training")
         if model.training:
             # train mode without autograd (e.g. under torch.no_grad()): BatchNorm batch statistics, as the reference
-            from .train import Trainer
-            tr = model.__dict__.get("_autograd_trainer")
-            if tr is None:
-                tr = Trainer(model)
-                object.__setattr__(model, "_autograd_trainer", tr)
+            from .train import bridge_trainer
             if return_attention:
                 raise ValueError("attention maps are an inference-mode output")
-            return tr.forward_train(x)[0]
+            return bridge_trainer(model, x.device).forward_train(x)[0]
         side = vit.image_size
         feat = lambda s: (((((s - 3) // 2 + 1) - 2) - 1) // 2 + 1)      # stem: 3x3 s2, 3x3 s1; then three s2 stages
         fh, fw = feat(hh), feat(ww)

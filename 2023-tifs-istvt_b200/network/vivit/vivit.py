@@ -8,6 +8,8 @@ kernels through the C ABI; there is no torch-op or CPU fallback.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 from torch import nn
 
@@ -144,6 +146,25 @@ class DSTTr(nn.Module):
         self.mlp_head = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, num_classes))
 
 
+class _Shared:
+    """Derived state of one `XceptionVidTr` that its `nn.DataParallel` replicas must see too.  `replicate()` gives every
+    replica a shallow copy of the module's `__dict__` (torch/nn/modules/module.py, `_replicate_for_data_parallel`) and
+    rebuilds the replicas on EVERY forward, so anything cached on a replica is lost and anything keyed on the replica's
+    parameter copies (fresh broadcast tensors each step) never hits.  This object is referenced, not copied: the engine
+    (packed weights per device, keyed on the OWNER's parameter versions) and the per-device training state live here."""
+
+    def __init__(self, owner):
+        self.owner = weakref.ref(owner)
+        self.engine = None
+        self.trainer = None             # torch.autograd bridge of the owner (train.autograd_forward)
+        self.replica_trainers = {}      # device index -> train.Trainer in replica mode
+
+    def reset(self) -> None:
+        self.engine = None
+        self.trainer = None
+        self.replica_trainers.clear()
+
+
 class XceptionVidTr(nn.Module):
     """`XceptionVidTr()` as in the reference; `num_frames` / `precision` are additions with preserving defaults.
 
@@ -167,13 +188,33 @@ class XceptionVidTr(nn.Module):
         self.variant = variant
         self.num_frames = num_frames
         self.precision = precision
-        self._engine = None
+        self._shared = _Shared(self)
+
+    # `_engine` is kept as an attribute name (train.py resets it after an optimizer step); it lives in `_shared`
+    @property
+    def _engine(self):
+        return self._shared.engine
+
+    @_engine.setter
+    def _engine(self, value):
+        self._shared.engine = value
 
     def engine(self):
         from ...engine import ISTVTEngine
-        if self._engine is None:
-            self._engine = ISTVTEngine(self)
-        return self._engine
+        sh = self._shared
+        if sh.engine is None:
+            owner = sh.owner()
+            sh.engine = ISTVTEngine(owner if owner is not None else self)
+        return sh.engine
+
+    def __getstate__(self):              # torch.save(model) / copy.deepcopy: derived state is rebuilt, never serialised
+        state = self.__dict__.copy()
+        state.pop("_shared", None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.__dict__["_shared"] = _Shared(self)
 
     def forward(self, x: torch.Tensor, return_attention: bool = False):
         if not isinstance(self.vit, DSTTr):      # ablation transformer behind the same entry flow (inference only)
@@ -194,11 +235,9 @@ class XceptionVidTr(nn.Module):
         return self.engine().forward(self, x, precision=self.precision, return_attention=return_attention)
 
     def _apply(self, fn, *args, **kwargs):  # .cuda() / .to(): drop the packed-weight cache and the flat train state
-        self._engine = None
-        if "_autograd_trainer" in self.__dict__:
-            del self.__dict__["_autograd_trainer"]
+        self._shared.reset()
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
-        self._engine = None
+        self._shared.engine = None
         return super().load_state_dict(*args, **kwargs)

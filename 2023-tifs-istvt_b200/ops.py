@@ -624,12 +624,18 @@ def batchnorm_train(x: torch.Tensor, bn, relu: bool, update_running: bool = True
 
 def batchnorm_bwd(dy: torch.Tensor, x: torch.Tensor, st: BNState, dgamma: torch.Tensor, dbeta: torch.Tensor,
                   relu: bool) -> torch.Tensor:
+    """dgamma / dbeta are ACCUMULATED into (gradient accumulation over micro-batches keeps working): the kernel reduces
+    this layer's sums into a zeroed per-call scratch — it derives dx from exactly those sums — and the scratch is then
+    added to the caller's slots."""
     dev = _chk(dy, x, dgamma, dbeta)
     dx = torch.empty_like(x)
+    sums = torch.zeros(2, st.c, dtype=torch.float32, device=dev)
     with _launch(dev, "bn_bwd", 0.0, 2 * _nbytes(dy, x) + _nbytes(dx)):
         _lib.check(_lib.lib().istvt_bn_bwd(_ptr(dy), _ptr(x), _ptr(st.scale), _ptr(st.shift), _ptr(st.mean), _ptr(st.rstd),
-                                           _ptr(dgamma), _ptr(dbeta), _ptr(dx), st.m, st.c, int(relu), _stream(dev)),
+                                           _ptr(sums[0]), _ptr(sums[1]), _ptr(dx), st.m, st.c, int(relu), _stream(dev)),
                    "istvt_bn_bwd")
+    dgamma.add_(sums[0])
+    dbeta.add_(sums[1])
     return dx
 
 

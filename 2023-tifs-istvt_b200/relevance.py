@@ -61,8 +61,8 @@ def relevance_maps(model, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, 
         raise ValueError("ISTVT (istvt_b200) runs on CUDA tensors only: there is no CPU fallback by design")
     vit = model.vit
     b, t = x.shape[:2]
-    if t != vit.num_frames or t + 1 > 8:
-        raise ValueError("relevance pass: clip length must equal num_frames (<= 7)")
+    if t != vit.num_frames or t + 1 > 48:
+        raise ValueError("relevance pass: clip length must equal num_frames (<= 47)")
     f32 = lambda z: z.detach().float().contiguous()
     frames = x.reshape(b * t, *x.shape[2:]).float().contiguous()
     body, skip = run_entry_flow(pack_entry(model.xcep.model, BF16), frames, BF16)

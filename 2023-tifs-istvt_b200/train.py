@@ -36,39 +36,58 @@ BF16 = torch.bfloat16
 # ------------------------------------------------------------------------------------------------
 # parameters on the path, flat buffers
 # ------------------------------------------------------------------------------------------------
-def on_path_named_parameters(model, train_entry_flow: bool) -> List[Tuple[str, torch.nn.Parameter]]:
+def _named_parameters(module):
+    """`module.named_parameters()` that also works on an `nn.DataParallel` replica: `replicate()` empties
+    `_parameters` and keeps the broadcast copies (non-leaf tensors whose autograd history reduces the gradients back
+    to the source device) as plain attributes, listed in `_former_parameters` — same order as named_parameters()."""
+    if not getattr(module, "_is_replica", False):
+        yield from module.named_parameters()
+        return
+    for mname, m in module.named_modules():
+        for k, p in getattr(m, "_former_parameters", {}).items():
+            if p is not None:
+                yield (f"{mname}.{k}" if mname else k), p
+
+
+def on_path_named_parameters(model, train_entry_flow: bool) -> List[Tuple[str, torch.Tensor]]:
     """Parameters that receive a gradient (117 Xception-tail tensors never do)."""
     out = []
     if train_entry_flow:
         x = model.xcep.model
         for name in ("conv1", "bn1", "conv2", "bn2", "block1", "block2", "block3"):
-            for n, p in getattr(x, name).named_parameters():
+            for n, p in _named_parameters(getattr(x, name)):
                 out.append((f"xcep.model.{name}.{n}", p))
-    for n, p in model.vit.named_parameters():
+    for n, p in _named_parameters(model.vit):
         out.append((f"vit.{n}", p))
     return out
 
 
 class FlatState:
     """fp32 parameters / gradients / Adam moments of the path in four flat buffers; every `nn.Parameter.data`
-    becomes a view into `params`, so state_dict(), the packing code and external optimizers keep working."""
+    becomes a view into `params`, so state_dict(), the packing code and external optimizers keep working.
 
-    def __init__(self, model, train_entry_flow: bool):
+    `grads_only` (an `nn.DataParallel` replica: its parameters are per-step broadcast copies owned by autograd, the
+    optimizer runs on the source module): only the flat gradient buffer and its per-parameter views exist."""
+
+    def __init__(self, model, train_entry_flow: bool, grads_only: bool = False):
         named = on_path_named_parameters(model, train_entry_flow)
         dev = named[0][1].device
         sizes = [(p.numel() + 3) // 4 * 4 for _, p in named]       # 16-byte aligned slots
         total = sum(sizes)
-        self.params = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros_like(self.params)
-        self.exp_avg = torch.zeros_like(self.params)
-        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.params = self.exp_avg = self.exp_avg_sq = None
+        if not grads_only:
+            self.params = torch.zeros_like(self.grads)
+            self.exp_avg = torch.zeros_like(self.grads)
+            self.exp_avg_sq = torch.zeros_like(self.grads)
         self.grad: Dict[str, torch.Tensor] = {}
         self.names = [n for n, _ in named]
         off = 0
         for (name, p), sz in zip(named, sizes):
-            view = self.params[off:off + p.numel()].view(p.shape)
-            view.copy_(p.data)
-            p.data = view
+            if not grads_only:
+                view = self.params[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
             self.grad[name] = self.grads[off:off + p.numel()].view(p.shape)
             off += sz
         self.step = 0
@@ -277,20 +296,20 @@ class Trainer:
                  train_entry_flow: bool = True, process_group=None):
         if model.precision != "bf16":
             raise ValueError("istvt_b200 training runs in bf16 mode (fp32 master weights, fp32 gradients)")
-        if next(model.parameters()).device.type != "cuda":
+        # an nn.DataParallel replica (train_CNN.py:185-186): forward / backward only, gradients flow back to the
+        # source module through autograd's Broadcast node; the optimizer belongs to the source module
+        self.replica = bool(getattr(model, "_is_replica", False))
+        if on_path_named_parameters(model, True)[0][1].device.type != "cuda":
             raise ValueError("move the model to a CUDA device first: there is no CPU training path")
-        if model.vit.num_frames + 1 > 8:
-            raise NotImplementedError("training is built for the ISTVT configuration (T <= 7 frames)")
+        if model.vit.num_frames + 1 > 48:
+            raise NotImplementedError("training covers clips of up to 47 frames (temporal-attention backward kernels)")
         self.model = model
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.train_entry_flow = train_entry_flow
         self.pg = process_group
-        self.state = FlatState(model, train_entry_flow)
-        model._engine = None
-        self._entry = None
-        if train_entry_flow:
-            from .train_entry import EntryFlowTrainer
-            self._entry = EntryFlowTrainer(model.xcep.model)
+        self.state = FlatState(model, train_entry_flow, grads_only=self.replica)
+        if not self.replica:
+            model._engine = None
 
     # -- pieces (also used by the autograd.Function wrapper) --
     def forward_train(self, x: torch.Tensor):
@@ -302,8 +321,11 @@ class Trainer:
         f32 = lambda z: z.detach().float().contiguous()
         pos = f32(vit.pos_embedding[0])
         tokens = torch.empty(b, t + 1, vit.num_patches + 1, vit.dim, dtype=torch.float32, device=x.device)
-        if self._entry is not None:
-            body, skip, ectx = self._entry.forward(frames)
+        entry = None
+        if self.train_entry_flow:
+            from .train_entry import EntryFlowTrainer
+            entry = EntryFlowTrainer(model.xcep.model)       # stateless: binds the module tree this forward ran on
+            body, skip, ectx = entry.forward(frames)
             _, amax3 = ops.pool_add_idx(body, skip, tokens=tokens, pos_emb=pos, t_frames=t)
         else:
             body, skip = run_entry_flow(pack_entry(model.xcep.model, BF16), frames, BF16)
@@ -313,21 +335,25 @@ class Trainer:
         ops.token_fill(tokens, f32(vit.space_token.reshape(-1)), f32(vit.temporal_token.reshape(-1)), pos)
         layers = _pack_layers(vit)
         logits, ctxs, x_final, head = transformer_forward_train(vit, layers, tokens)
-        saved = SimpleNamespace(layers=layers, ctxs=ctxs, x_final=x_final, head=head, ectx=ectx, amax3=amax3, b=b, t=t)
+        saved = SimpleNamespace(layers=layers, ctxs=ctxs, x_final=x_final, head=head, ectx=ectx, amax3=amax3, b=b, t=t,
+                                vit=vit, entry=entry)
         return logits, saved
 
     def backward(self, saved, dlogits: torch.Tensor) -> None:
-        vit = self.model.vit
+        """Accumulates into the flat gradient buffer — call zero_grad() first unless accumulation is intended (every
+        kernel on this path adds into its slot or reduces into a per-call scratch first, see istvt_bn_bwd)."""
         G = self.state.grad
-        g = transformer_backward(vit, saved.layers, saved.ctxs, saved.x_final, saved.head, dlogits, G)
+        g = transformer_backward(saved.vit, saved.layers, saved.ctxs, saved.x_final, saved.head, dlogits, G)
         ops.token_bwd(g, G["vit.pos_embedding"][0], G["vit.space_token"].view(-1), G["vit.temporal_token"].view(-1))
-        if self._entry is not None:
-            self._entry.backward(saved.ectx, saved.amax3, g, G)
+        if saved.entry is not None:
+            saved.entry.backward(saved.ectx, saved.amax3, g, G)
 
     def zero_grad(self) -> None:
         self.state.grads.zero_()
 
     def optimizer_step(self, world: int = 1) -> None:
+        if self.replica:
+            raise RuntimeError("an nn.DataParallel replica has no optimizer state: step the source module's optimizer")
         st = self.state
         st.step += 1
         ops.adamw_step(st.params, st.grads, st.exp_avg, st.exp_avg_sq, self.lr, self.betas, self.eps,
@@ -372,12 +398,28 @@ class _ISTVTTrainFunction(torch.autograd.Function):
         return (None, None) + tuple(tr.state.grad[n].clone() for n in tr.state.names)
 
 
+def bridge_trainer(model, dev: torch.device) -> "Trainer":
+    """The Trainer behind `model(x)` in train mode, cached in the state a model shares with its `nn.DataParallel`
+    replicas (network/vivit/vivit.py::_Shared): one for the module itself, one per device for replicas — replicas are
+    rebuilt by every DataParallel.forward, so the cached Trainer is re-bound to the replica it is asked for."""
+    sh = model._shared
+    if getattr(model, "_is_replica", False):
+        tr = sh.replica_trainers.get(dev.index)
+        if tr is None:
+            tr = Trainer(model)
+            sh.replica_trainers[dev.index] = tr
+        tr.model = model
+        return tr
+    if sh.trainer is None:
+        sh.trainer = Trainer(model)
+    return sh.trainer
+
+
 def autograd_forward(model, x: torch.Tensor) -> torch.Tensor:
     """Training-mode `XceptionVidTr.forward`: the CUDA forward that keeps activations, differentiable through the
-    hand-written backward.  Any torch optimizer over `model.parameters()` then works as in the reference."""
-    tr = getattr(model, "_autograd_trainer", None)
-    if tr is None:
-        tr = Trainer(model)
-        object.__setattr__(model, "_autograd_trainer", tr)
+    hand-written backward.  Any torch optimizer over `model.parameters()` then works as in the reference, and so does
+    `nn.DataParallel(model)` (train_CNN.py:185-186): on a replica the parameters handed to autograd are the broadcast
+    copies, whose history reduces the per-replica gradients onto the source module."""
+    tr = bridge_trainer(model, x.device)
     params = [p for _, p in on_path_named_parameters(model, tr.train_entry_flow)]
     return _ISTVTTrainFunction.apply(x, tr, *params)

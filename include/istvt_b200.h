@@ -170,6 +170,8 @@ int istvt_token_fill_fwd(float* tokens, const float* space_token, const float* t
  * qk: [batch*frames*tokens, 2*heads*64] (q columns then k columns, head-major); v: [rows, heads*64];
  * out: [rows, heads*64]; probs (optional, may be NULL): fp32 [batch, heads, tokens, frames, frames].
  * q/k/v are read in place: consecutive frames of one position are `tokens` rows apart.
+ * bf16: one warp per (clip, position, head) on mma.sync, registers only — frames <= 8 (T = 6) in one m16 tile,
+ * frames <= 48 (the long-clip configuration, T = 32) with the frame axis tiled; fp32 and frames > 48: SIMT kernel.
  * ------------------------------------------------------------------------------------------- */
 int istvt_attn_temporal_fwd(const void* qk, const void* v, void* out, float* probs, int dtype, int batch,
                             int frames, int tokens, int heads, float scale, istvt_stream_t stream);
@@ -259,7 +261,8 @@ int istvt_attn_spatial_bwd(const void* qkv, const void* o, const void* dout, con
                            float* dq_scratch, int batch_frames, int tokens, int heads, float scale,
                            istvt_stream_t stream);
 
-/* Backward of module.py:197-205 (frames <= 8).  dqk: bf16 [rows, 2*heads*64], dv: bf16 [rows, heads*64]. */
+/* Backward of module.py:197-205 (frames <= 48; ISTVT_ERR_UNSUPPORTED beyond).  dqk: bf16 [rows, 2*heads*64], dv: bf16
+ * [rows, heads*64].  frames <= 8: registers only; 9..48: operands staged once in shared memory, ldmatrix fragments. */
 int istvt_attn_temporal_bwd(const void* qk, const void* v, const void* dout, void* dqk, void* dv, int batch,
                             int frames, int tokens, int heads, float scale, istvt_stream_t stream);
 

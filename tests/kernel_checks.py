@@ -304,8 +304,10 @@ def check_attn_temporal():
     ops = _ops()
     out = {}
     heads, scale = 8, 0.125
-    # f <= 8 in bf16 runs the warp-per-(clip, position, head) mma.sync kernel; f = 33 / fp32 the SIMT kernel
-    for (b, f, p) in ((2, 7, 362), (1, 33, 362), (1, 2, 5), (3, 8, 101), (1, 1, 9)):
+    # bf16: f <= 8 runs the one-tile warp-per-(clip, position, head) mma.sync kernel, 9 <= f <= 48 the frame-tiled one
+    # (2 or 3 m16 tiles; f = 33 is the long-clip configuration), f > 48 and fp32 the SIMT kernel
+    for (b, f, p) in ((2, 7, 362), (1, 33, 362), (1, 2, 5), (3, 8, 101), (1, 1, 9), (2, 9, 37), (1, 16, 50), (1, 17, 19),
+                      (2, 32, 21), (1, 47, 11), (1, 48, 13), (1, 49, 7)):
         for dt, tol in ((torch.float32, 5e-5), (torch.bfloat16, TOL_BF16)):
             rows = b * f * p
             qk = (_rand(rows, 1024, seed=f) * 1.5).to(dt)
@@ -580,7 +582,9 @@ def check_attn_temporal_bwd():
     ops = _ops()
     out = {}
     heads, scale = 8, 0.125
-    for (b, f, p) in ((2, 7, 362), (1, 2, 5), (3, 8, 33)):
+    # f <= 8: registers-only kernel; 9 <= f <= 48: shared-memory / ldmatrix kernel (2 or 3 frame tiles)
+    for (b, f, p) in ((2, 7, 362), (1, 2, 5), (3, 8, 33), (1, 33, 362), (2, 9, 21), (1, 16, 17), (1, 17, 30), (1, 32, 9),
+                      (1, 48, 5)):
         rows = b * f * p
         qk = (_rand(rows, 1024, seed=f) * 1.5).to(torch.bfloat16)
         v = _rand(rows, 512, seed=f + 1).to(torch.bfloat16)

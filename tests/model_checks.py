@@ -316,6 +316,116 @@ def run_train_golden():
     return errs
 
 
+def run_batch64_parity():
+    """Parity AT THE BENCHMARK SHAPE (C2: 64 clips x 6 frames, bf16, the pruned last block — 162 176 token rows, the
+    8 704-CTA grids): the oracle's logits for the clips at batch positions 0 / 21 / 42 / 63, and the same 64 clips run
+    8 at a time through the same kernels (every position of the big batch is covered by that comparison)."""
+    O = oracle()
+    model = build_model({"seed": 0, "frames": 6, "sensitised": True})
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = make_input(64, 6, seed=64)
+    picks = [0, 21, 42, 63]
+    with torch.no_grad():
+        want = torch.cat([O.forward(sd, x[i:i + 1]) for i in picks])
+    model = model.cuda().eval()
+    xg = x.cuda()
+    with torch.no_grad():
+        got = model(xg)
+        chunks = torch.cat([model(xg[i:i + 8]) for i in range(0, 64, 8)])
+    torch.cuda.synchronize()
+    errs = {"oracle_picks": rel_err(got[picks], want), "vs_batches_of_8": rel_err(got, chunks)}
+    assert bool(((got[picks] > 0) == (want.cuda() > 0)).all()), "predictions differ from the oracle"
+    assert errs["oracle_picks"] <= 2e-2, errs
+    assert errs["vs_batches_of_8"] <= 2e-3, errs
+    return errs
+
+
+def run_data_parallel_check():
+    """`nn.DataParallel(model)` on two devices (train_CNN.py:185-186), eval and train:
+    eval  — logits equal the single-device forward; the second step re-uses the per-device weight packs (the engine
+            validates them against the owner's parameters, so replicas — rebuilt every step — do not re-pack);
+    train — `loss.backward()` through the per-replica hand-written backward + autograd's gradient reduction gives the
+            gradients of the oracle on the CONCATENATED batch up to the per-replica BatchNorm statistics (each replica
+            normalises with its own half, exactly like the reference under DataParallel), so the comparison is against
+            the oracle run per half and averaged."""
+    assert torch.cuda.device_count() >= 2, "needs two visible GPUs"
+    O = oracle()
+    m = pkg()
+    model = build_model({"seed": 0, "frames": 6, "sensitised": True}).cuda()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    x = make_input(4, 6, seed=91).cuda()
+    with torch.no_grad():
+        want = model(x)
+    dp = torch.nn.DataParallel(model, device_ids=[0, 1])
+    n0 = m._lib.launch_count()
+    with torch.no_grad():
+        got = dp(x)
+    n1 = m._lib.launch_count()
+    packs = {k: id(v) for k, v in model.engine()._packs.items()}
+    with torch.no_grad():
+        got2 = dp(x)
+    n2 = m._lib.launch_count()
+    errs = {"eval_vs_single": rel_err(got, want), "eval_repeat": rel_err(got2, got)}
+    assert got.device == x.device and errs["eval_vs_single"] <= 1e-3 and errs["eval_repeat"] == 0.0, errs
+    assert {k: id(v) for k, v in model.engine()._packs.items()} == packs and len(packs) == 2, "replicas re-packed"
+    assert n2 - n1 == n1 - n0 > 300, "both replicas must launch the CUDA path"
+    # ---- training through DataParallel ----
+    dp.train()
+    labels = torch.tensor([1.0, 0.0, 0.0, 1.0], device="cuda")
+    model.zero_grad()
+    out = dp(x)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out.view(-1), labels)
+    loss.backward()
+    torch.cuda.synchronize()
+    xc, lc = x.cpu(), labels.cpu()
+    l0, _, g0 = O.loss_and_grads({k: v.clone() for k, v in sd.items()}, xc[:2], lc[:2])
+    l1, _, g1 = O.loss_and_grads({k: v.clone() for k, v in sd.items()}, xc[2:], lc[2:])
+    errs["train_loss"] = abs(float(loss) - 0.5 * float(l0 + l1)) / abs(0.5 * float(l0 + l1))
+    named = dict(model.named_parameters())
+    gerr = {k: rel_err(named[k].grad, 0.5 * (g0[k] + g1[k])) for k in g0}
+    errs["grad_worst_vit"] = max(v for k, v in gerr.items() if k.startswith("vit."))
+    errs["grad_worst_entry"] = max(v for k, v in gerr.items() if k.startswith("xcep."))
+    assert named["xcep.model.block4.rep.1.conv1.weight"].grad is None
+    assert errs["train_loss"] <= TOL_TRAIN["loss"], errs
+    assert errs["grad_worst_vit"] <= TOL_TRAIN["grad_vit"] and errs["grad_worst_entry"] <= TOL_TRAIN["grad_entry"], errs
+    return errs
+
+
+def run_train_t32_oracle():
+    """Long-clip configuration (T = 32, F = 33 frames incl. the temporal class frame): one train-mode forward + backward
+    on the GPU vs the CPU oracle's autograd on the same clip (the oracle's train mode is pinned to the unmodified
+    reference at T = 6, tests/test_oracle.py; DSTTr(19,1,1,32) is the same code path with a longer frame axis).
+    Covers the frame-tiled temporal-attention forward / backward kernels inside the whole schedule."""
+    O = oracle()
+    model = build_model({"seed": 0, "vit_seed": 1, "frames": 32, "sensitised": True})
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = make_input(1, 32, seed=55)
+    labels = torch.tensor([1])
+    want_loss, want_logits, want = O.loss_and_grads(sd, x, labels)
+    model = model.cuda().train()
+    tr = pkg().Trainer(model, lr=1e-4, weight_decay=0.0)
+    tr.zero_grad()
+    logits, saved = tr.forward_train(x.cuda())
+    z = logits.view(-1)
+    y = labels.cuda().float()
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(z, y)
+    tr.backward(saved, (torch.sigmoid(z) - y) / z.numel())
+    torch.cuda.synchronize()
+    errs = {"loss": abs(float(loss) - float(want_loss)) / abs(float(want_loss)), "logits": rel_err(logits, want_logits)}
+    gerr = {k: rel_err(tr.state.grad[k], g) for k, g in want.items()}
+    errs["grad_worst_vit"] = max(v for k, v in gerr.items() if k.startswith("vit."))
+    errs["grad_worst_entry"] = max(v for k, v in gerr.items() if k.startswith("xcep."))
+    errs["grad_median"] = sorted(gerr.values())[len(gerr) // 2]
+    worst = sorted(gerr.items(), key=lambda kv: -kv[1])[:6]
+    profile = "; ".join(f"{k}={v:.3e}" for k, v in errs.items()) + " | worst grads: " + \
+        ", ".join(f"{k}={v:.2e}" for k, v in worst)
+    print("train T=32 profile:", profile)
+    assert errs["loss"] <= TOL_TRAIN["loss"] and errs["logits"] <= 2e-2, profile
+    assert errs["grad_worst_vit"] <= TOL_TRAIN["grad_vit"], profile
+    assert errs["grad_worst_entry"] <= TOL_TRAIN["grad_entry"], profile
+    return errs
+
+
 def run_relevance_check(batch: int = 2):
     """Relevance pass (BASELINE config 4) on the GPU vs oracle/relevance_oracle.py — PARITY UNPINNED: the reference's
     own implementation is absent from its tree, the oracle restates the rule the product implements."""
@@ -350,6 +460,25 @@ def run_relevance_check(batch: int = 2):
     # same clip in a batch of 1 and of 2: equal up to the run-to-run noise of the floating-point atomics (dQ, cam)
     assert rel_err(cs, cam_s[0]) <= 2e-2 and rel_err(ct, cam_t[0]) <= 2e-2
     print("relevance profile:", profile)
+    return errs
+
+
+def run_relevance_t32_check():
+    """Relevance pass on a 32-frame clip (F = 33: the frame-tiled temporal-attention backward accumulates the 33 x 33
+    relu(dA o A) maps) vs oracle/relevance_oracle.py — PARITY UNPINNED like run_relevance_check."""
+    from oracle import relevance_oracle as R
+    m = pkg()
+    model = build_model({"seed": 0, "vit_seed": 1, "frames": 32, "sensitised": True})
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    x = make_input(1, 32, seed=78)
+    want_s, want_t, want_logits = R.relevance_maps(sd, x)
+    cam_s, cam_t, logits = m.relevance_maps(model.cuda().eval(), x.cuda())
+    torch.cuda.synchronize()
+    assert cam_s.shape == (1, 32, 361) and cam_t.shape == (1, 32, 361)
+    errs = {"logits": rel_err(logits, want_logits), "cam_s": rel_err(cam_s, want_s), "cam_t": rel_err(cam_t, want_t)}
+    profile = ", ".join(f"{k}={v:.3e}" for k, v in errs.items())
+    print("relevance T=32 profile:", profile)
+    assert errs["logits"] <= 2e-2 and errs["cam_s"] <= 1e-1 and errs["cam_t"] <= 1e-1, profile
     return errs
 
 

@@ -139,3 +139,120 @@ def test_ablation_no_cpu_fallback():
     for blk in (m.Attention(728).eval(), m.TemporalOnlyAttention(728).eval(), m.Transformer(728, 1, 8, 64, 2912).eval()):
         with pytest.raises(ValueError, match="CUDA"):
             blk(torch.zeros(1, 362, 728))
+
+
+def test_shadow_mode_import_runs_forward():
+    """with the package directory itself on sys.path, `from network.models import model_selection`
+    must give a model whose forward reaches the device check (ValueError on a CPU tensor), not an ImportError from
+    relative imports that climb above a re-rooted `network` package; eval, train and ablation entries all resolve."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {os.path.join(root, '2023-tifs-istvt_b200')!r})\n"
+        "from network.models import model_selection\n"
+        "import network.vivit.vivit as vv, network.vivit.module as mod, network.xception as xc\n"
+        "m = model_selection('resnet_3d', num_out_classes=1)\n"
+        "assert type(m) is vv.XceptionVidTr\n"
+        "x = torch.zeros(1, 6, 3, 300, 300)\n"
+        "for mode in (m.eval(), m.train()):\n"
+        "    try:\n"
+        "        mode(x)\n"
+        "    except ValueError as e:\n"
+        "        assert 'CUDA' in str(e), e\n"
+        "    else:\n"
+        "        raise SystemExit('no ValueError')\n"
+        "for ctor in (lambda: vv.XceptionVidTr(variant='vivit'), lambda: mod.Attention(728), lambda: model_selection('xception', 2)):\n"
+        "    a = ctor().eval()\n"
+        "    inp = x if not isinstance(a, mod.Attention) else torch.zeros(1, 10, 728)\n"
+        "    if hasattr(a, 'model') and not hasattr(a, 'vit'): inp = torch.zeros(1, 3, 299, 299)\n"
+        "    try:\n"
+        "        a(inp)\n"
+        "    except ValueError as e:\n"
+        "        assert 'CUDA' in str(e), e\n"
+        "    else:\n"
+        "        raise SystemExit('no ValueError')\n"
+        "print('shadow ok')\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert r.returncode == 0 and "shadow ok" in r.stdout, r.stdout + r.stderr
+
+
+def _fake_replicate(model):
+    """What torch.nn.parallel.replicate() does to a module tree (torch/nn/parallel/replicate.py), on CPU: shallow
+    __dict__ copies, `_parameters` emptied, the parameter copies (non-leaf tensors) set as plain attributes and listed
+    in `_former_parameters`."""
+    from collections import OrderedDict
+    modules = list(model.modules())
+    index = {m: i for i, m in enumerate(modules)}
+    copies = [m._replicate_for_data_parallel() for m in modules]
+    for r in copies:
+        r._former_parameters = OrderedDict()
+    for i, m in enumerate(modules):
+        for k, child in m._modules.items():
+            if child is not None:
+                setattr(copies[i], k, copies[index[child]])
+        for k, p in m._parameters.items():
+            if p is not None:
+                c = p * 1.0          # non-leaf, like the output of Broadcast.apply
+                setattr(copies[i], k, c)
+                copies[i]._former_parameters[k] = c
+        for k, b in m._buffers.items():
+            if b is not None:
+                setattr(copies[i], k, b.clone())
+    return copies[0]
+
+
+def test_data_parallel_replica_shares_engine_and_lists_parameters(model):
+    """nn.DataParallel (train_CNN.py:185-186): a replica must (a) reach the owner's engine, whose pack cache is
+    validated against the OWNER's parameters — the replica's are fresh copies every step — and (b) expose the on-path
+    parameter copies, in named_parameters() order, to the training bridge."""
+    train = __import__("importlib").import_module("2023-tifs-istvt_b200.train")
+    eng_owner = model.engine()
+    rep = _fake_replicate(model)
+    assert getattr(rep, "_is_replica", False) and len(list(rep.parameters())) == 0
+    assert rep._shared is model._shared and rep.engine() is eng_owner
+    assert eng_owner._fingerprint(rep) == eng_owner._fingerprint(model)
+    rep2 = _fake_replicate(model)                       # next step's replica: new tensors, same fingerprint
+    assert eng_owner._fingerprint(rep2) == eng_owner._fingerprint(model)
+    before = eng_owner._fingerprint(rep)
+    with torch.no_grad():
+        model.vit.mlp_head[1].bias.add_(1.0)            # an optimizer step on the owner invalidates it
+    assert eng_owner._fingerprint(_fake_replicate(model)) != before
+    want = train.on_path_named_parameters(model, True)
+    got = train.on_path_named_parameters(rep, True)
+    assert [n for n, _ in got] == [n for n, _ in want] and len(got) == 252
+    assert all(g.shape == w.shape and not g.is_leaf for (_, g), (_, w) in zip(got, want))
+    st = train.FlatState(rep, True, grads_only=True)
+    assert st.params is None and st.grads.numel() >= 89467761 and set(st.grad) == {n for n, _ in want}
+
+
+def test_model_pickles_without_shared_state(model):
+    import copy
+    m2 = copy.deepcopy(model)
+    assert m2._shared is not model._shared and m2._shared.owner() is m2 and m2._engine is None
+
+
+def test_ablation_paths_refuse_train_mode():
+    """train mode means BatchNorm batch statistics + dropout in the reference; the ablation paths fold the
+    running statistics, so they must refuse `module.train()` even under torch.no_grad()."""
+    m = pkg()
+    vivit = m.XceptionVidTr(variant="vivit").train()
+    with torch.no_grad(), pytest.raises(NotImplementedError, match="eval"):
+        vivit(torch.zeros(1, 6, 3, 300, 300))
+    attn = m.Attention(728).train()
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        attn(torch.zeros(1, 10, 728))
+
+
+def test_vanilla_tr_checks_patch_linear_channels():
+    """VanillaTr(in_channels != dim) is a valid model (patch Linear, vivit.py:162-167): the channel check must follow
+    the Linear's in_features — the error for a wrong channel count names it, the right count passes to the device check."""
+    m = pkg()
+    v = m.VanillaTr(19, 1, 1, 6, dim=128, depth=1, in_channels=64).eval()
+    with pytest.raises(ValueError, match="64"):
+        v(torch.zeros(1, 6, 128, 19, 19))
+    with pytest.raises(ValueError, match="CUDA"):
+        v(torch.zeros(1, 6, 64, 19, 19))

@@ -19,6 +19,19 @@ def test_against_cpu_oracle(precision):
 
 
 @pytest.mark.gpu
+def test_benchmark_shape_batch64_against_oracle():
+    model_checks.run_batch64_parity()
+
+
+@pytest.mark.gpu
+def test_data_parallel_two_devices():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("nn.DataParallel check needs two visible GPUs (run under gpurun --gpus 2)")
+    model_checks.run_data_parallel_check()
+
+
+@pytest.mark.gpu
 def test_api_boundary():
     model_checks.run_api_checks()
 
@@ -29,8 +42,18 @@ def test_training_step_against_reference_golden():
 
 
 @pytest.mark.gpu
+def test_training_step_long_clip_against_oracle():
+    model_checks.run_train_t32_oracle()
+
+
+@pytest.mark.gpu
 def test_relevance_pass_against_oracle():
     model_checks.run_relevance_check()
+
+
+@pytest.mark.gpu
+def test_relevance_pass_long_clip_against_oracle():
+    model_checks.run_relevance_t32_check()
 
 
 @pytest.mark.gpu

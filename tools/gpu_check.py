@@ -30,8 +30,14 @@ def all_checks():
         checks[f"oracle_{prec}"] = lambda p=prec: model_checks.run_oracle_case(p)
     checks["golden_t32_bf16"] = lambda: model_checks.run_golden_case("sensitised_t32_b1", "bf16")
     checks["golden_t32_fp32"] = lambda: model_checks.run_golden_case("sensitised_t32_b1", "fp32")
+    checks["batch64"] = model_checks.run_batch64_parity
+    import torch
+    if torch.cuda.is_available() and torch.cuda.device_count() >= 2:
+        checks["data_parallel"] = model_checks.run_data_parallel_check
     checks["train_golden"] = model_checks.run_train_golden
+    checks["train_t32_oracle"] = model_checks.run_train_t32_oracle
     checks["relevance"] = model_checks.run_relevance_check
+    checks["relevance_t32"] = model_checks.run_relevance_t32_check
     checks["cuda_graph"] = model_checks.run_graph_check
     checks["uint8_input"] = model_checks.run_uint8_input_check
     checks["xception_fp32"] = lambda: model_checks.run_xception_golden("fp32")

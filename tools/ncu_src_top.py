@@ -14,7 +14,8 @@ def main() -> None:
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hi]
     ci = {h: i for i, h in enumerate(hdr)}
-    body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    end = next((i for i in range(hi + 1, len(rows)) if rows[i] and rows[i][0] == "Kernel Name"), len(rows))
+    body = [r for r in rows[hi + 1:end] if len(r) == len(hdr)]       # first captured launch only
     sk, ex = ci["# Samples"], ci["Instructions Executed"]
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(float(r[sk] or 0) for r in body)
