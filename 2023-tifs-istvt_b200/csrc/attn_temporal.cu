@@ -13,6 +13,9 @@
 #include "ptx.cuh"
 #include "simt_util.cuh"
 
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 namespace istvt {
 
 constexpr int TA_DH = 64;       // head dim
@@ -241,24 +244,85 @@ attn_temporal_mma_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------------
-// bf16 production kernel for 8 < F <= 16 * MT frames (MT = 2, 3: the long-clip configuration C5 has F = 33), the same
+// bf16 production kernels for 8 < F <= 48 frames (the long-clip configuration C5 has F = 33), the same
 // one-warp-per-(clip, position, head), registers-only mma.sync scheme as above with the frame axis tiled:
 //   * K is held as B fragments of Q.K^T for every 8-key n-tile (row 8 nj + g, 16-byte chunks t and t + 4), V as B
 //     fragments of P.V for every 16-key k-step (rows 16 kk + 2t, + 1, + 8, + 9, chunk g; byte-permuted per n-tile);
 //   * the query frames are walked in m16 tiles: Q rows 16 mi + g and + 8 (A fragments), S = 16 x 8 NT scores, softmax
-//     over the NT n-tiles and the quad, and the score accumulators ARE the A fragments of P.V (c0,c1 / c2,c3 of n-tiles
+//     over the n-tiles and the quad, and the score accumulators ARE the A fragments of P.V (c0,c1 / c2,c3 of n-tiles
 //     2 kk and 2 kk + 1 = a0 / a1 and a2 / a3 of k-step kk) — no shuffles, no shared memory;
-//   * the head-dim permutations are those of the F <= 8 kernel, so every global access is a 16-byte vector and every
-//     lane stores 2 x 16 contiguous bytes per output row.
-// HBM traffic = q, k, v once + the output once (4 KB per token row); 4 warps per CTA so that 2-3 CTAs overlap their
+//   * P.V runs in fp16: with 33 keys the 8-bit mantissa of a bf16 P cost 2.9e-2 on the T = 32 golden logit (the SIMT
+//     kernel it replaces: 1.4e-2); P in [0, 1] rounds to fp16 with 11 bits and V (bf16, 8 bits) converts exactly
+//     (saturating at +-65504: V is a projection of LayerNorm output);
+//   * legacy mma.sync peaks near 512 FLOP/clk/SM on sm_100a (profiles/README.md r1x), i.e. one m16n8k16 per 8 clk and
+//     SM: the generic kernel's 132 MMAs per unit at F = 33 (3 m16 tiles x 5 n8 tiles, of which the third tile and the
+//     fifth n-tile hold ONE frame) are 1056 clk per unit, above the unit's HBM time.  F = 16 MT + 1 (T = 16, 32: the
+//     extra frame is the temporal class token) therefore has its own kernel: the 16 MT x 16 MT core on 64 MMAs
+//     (MT = 2), the last KEY folded into the softmax / output of every row with fp32 FMAs on the lane's own fragments
+//     (16 head dims per lane, quad reduction), and the last QUERY row done entirely on the FMA pipe from the K / V
+//     fragments the lane already holds.
+// HBM traffic = q, k, v once + the output once (4 KB per token row); 4 warps per CTA so that 3 CTAs overlap their
 // load and compute phases on one SM.
 // ------------------------------------------------------------------------------------------
-template <int MT>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                              uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float bf16lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t x) { return pack_f16x2(bf16lo(x), bf16hi(x)); }
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t x) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&x));
+}
+// partial dot product over the 16 head dims a lane holds (two 16-byte chunks of a bf16 row each)
+__device__ __forceinline__ float dot16_bf16(const uint4 (&a)[2], const uint4 (&b)[2]) {
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const uint32_t aw[4] = {a[c].x, a[c].y, a[c].z, a[c].w}, bw[4] = {b[c].x, b[c].y, b[c].z, b[c].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc = fmaf(bf16lo(aw[i]), bf16lo(bw[i]), acc);
+            acc = fmaf(bf16hi(aw[i]), bf16hi(bw[i]), acc);
+        }
+    }
+    return acc;
+}
+__device__ __forceinline__ float quad_sum(float x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    return x + __shfl_xor_sync(0xffffffffu, x, 2);
+}
+__device__ __forceinline__ float quad_max(float x) {
+    x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+    return fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 2));
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float x, float y) {
+    const __nv_bfloat162 r = __floats2bfloat162_rn(x, y);
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// TAIL = false: any 8 < F <= 16 MT (rows / keys >= F masked).  TAIL = true: F == 16 MT + 1 exactly.
+template <int MT, bool TAIL>
+__global__ void __launch_bounds__(128, TAIL ? 3 : 2)
 attn_temporal_mma_wide_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
                               __nv_bfloat16* __restrict__ out, float* __restrict__ probs, int frames, int tokens,
                               int heads, float scale_log2, int64_t units) {
     constexpr int NT = 2 * MT;        // 8-key n-tiles of Q.K^T
+    constexpr int R = 16 * MT;        // TAIL: index of the last frame
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2;
     const int t = lane & 3;
@@ -275,6 +339,7 @@ attn_temporal_mma_wide_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_b
     const __nv_bfloat16* qbase = qk + row0 * (2 * inner) + h * TA_DH;
     const __nv_bfloat16* vbase = v + row0 * inner + h * TA_DH;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const int fmain = TAIL ? R : frames;       // frames covered by the MMA tiles
 
     // ---- K fragments: key 8 nj + g, head-dim chunks t and t + 4 ----
     uint4 kf[NT][2];
@@ -282,46 +347,149 @@ attn_temporal_mma_wide_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_b
     for (int nj = 0; nj < NT; ++nj) {
         const int key = 8 * nj + g;
         kf[nj][0] = kf[nj][1] = zero;
-        if (key < frames) {
+        if (key < fmain) {
             const __nv_bfloat16* kp = qbase + key * qk_pitch + inner;
             kf[nj][0] = ldg_nc_u4(kp + 8 * t);
             kf[nj][1] = ldg_nc_u4(kp + 8 * (t + 4));
         }
     }
     // ---- V fragments: keys 16 kk + {2t, 2t+1, 2t+8, 2t+9}, head-dim chunk g ----
-    uint4 vf[MT][4];
+    uint4 vraw[MT][4];
 #pragma unroll
     for (int kk = 0; kk < MT; ++kk)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int key = 16 * kk + 2 * t + (r & 1) + 8 * (r >> 1);
-            vf[kk][r] = zero;
-            if (key < frames) vf[kk][r] = ldg_nc_u4(vbase + key * v_pitch + 8 * g);
+            vraw[kk][r] = zero;
+            if (key < fmain) vraw[kk][r] = ldg_nc_u4(vbase + key * v_pitch + 8 * g);
         }
-
-    auto pk = [](float x, float y) {
-        const __nv_bfloat162 r = __floats2bfloat162_rn(x, y);
-        return *reinterpret_cast<const uint32_t*>(&r);
+    // ---- TAIL: the last frame's q / k (this lane's 16 head dims) and v (this lane's 16 OUTPUT dims; chunk g) ----
+    uint4 qt[2] = {zero, zero}, kt[2] = {zero, zero}, vt[2] = {zero, zero}, vtg = zero;
+    if constexpr (TAIL) {
+        const __nv_bfloat16* qp = qbase + R * qk_pitch;
+        qt[0] = ldg_nc_u4(qp + 8 * t);         qt[1] = ldg_nc_u4(qp + 8 * (t + 4));
+        kt[0] = ldg_nc_u4(qp + inner + 8 * t); kt[1] = ldg_nc_u4(qp + inner + 8 * (t + 4));
+        vt[0] = ldg_nc_u4(vbase + R * v_pitch + 16 * t);
+        vt[1] = ldg_nc_u4(vbase + R * v_pitch + 16 * t + 8);
+        vtg = ldg_nc_u4(vbase + R * v_pitch + 8 * g);
+    }
+    // first query tile
+    uint4 qa[2][2], qn[2][2];
+    auto load_q = [&](int mi, uint4 (&q)[2][2]) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 16 * mi + g + 8 * rr;
+            q[rr][0] = q[rr][1] = zero;
+            if (r < fmain) {
+                q[rr][0] = ldg_nc_u4(qbase + r * qk_pitch + 8 * t);
+                q[rr][1] = ldg_nc_u4(qbase + r * qk_pitch + 8 * (t + 4));
+            }
+        }
     };
+    load_q(0, qa);
+
+    // ---- B fragments of P.V in fp16: vb[kk][nt] = {V[16kk+2t][8g+nt], V[16kk+2t+1][.]}, {V[16kk+2t+8][.], V[16kk+2t+9][.]} ----
+    uint32_t vb[MT][8][2];
+#pragma unroll
+    for (int kk = 0; kk < MT; ++kk) {
+        const uint32_t w0[4] = {vraw[kk][0].x, vraw[kk][0].y, vraw[kk][0].z, vraw[kk][0].w};
+        const uint32_t w1[4] = {vraw[kk][1].x, vraw[kk][1].y, vraw[kk][1].z, vraw[kk][1].w};
+        const uint32_t w2[4] = {vraw[kk][2].x, vraw[kk][2].y, vraw[kk][2].z, vraw[kk][2].w};
+        const uint32_t w3[4] = {vraw[kk][3].x, vraw[kk][3].y, vraw[kk][3].z, vraw[kk][3].w};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const uint32_t sel = (nt & 1) ? 0x7632 : 0x5410;
+            vb[kk][nt][0] = bf16x2_to_f16x2(__byte_perm(w0[nt >> 1], w1[nt >> 1], sel));
+            vb[kk][nt][1] = bf16x2_to_f16x2(__byte_perm(w2[nt >> 1], w3[nt >> 1], sel));
+        }
+    }
+    float* pr_base = probs != nullptr ? probs + (((b * heads + h) * tokens + pos) * frames) * frames : nullptr;
+
+    // ================= TAIL: the last query row, entirely on the FMA pipe =================
+    if constexpr (TAIL) {
+        float st[NT];                                 // S[R][8 nj + g] (log2 domain), the same in the 4 lanes of a quad
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj) {
+            st[nj] = quad_sum(dot16_bf16(qt, kf[nj])) * scale_log2;
+            mx = fmaxf(mx, st[nj]);
+        }
+        const float stt = quad_sum(dot16_bf16(qt, kt)) * scale_log2;       // S[R][R]
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        mx = fmaxf(mx, stt);
+        float sum = 0.f;
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj) {
+            st[nj] = ex2f(st[nj] - mx);
+            sum += st[nj];
+        }
+        const float ptt = ex2f(stt - mx);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        sum += ptt;
+        const float inv = 1.0f / sum;
+        if (pr_base != nullptr && t == 0) {
+            float* pr = pr_base + static_cast<int64_t>(R) * frames;
+#pragma unroll
+            for (int nj = 0; nj < NT; ++nj) pr[8 * nj + g] = st[nj] * inv;
+            if (g == 0) pr[R] = ptt * inv;
+        }
+        // O[R][8g + nt]: this lane's keys 16 kk + 2t + {0, 1, 8, 9}, then the quad (t) reduction and the last key
+        float acc[8];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) acc[nt] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < MT; ++kk) {
+            // P[R][key] sits in every lane of quad g' = key & 7 as st[key >> 3]
+            const float p0 = __shfl_sync(0xffffffffu, st[2 * kk], ((2 * t) << 2) | t);
+            const float p1 = __shfl_sync(0xffffffffu, st[2 * kk], ((2 * t + 1) << 2) | t);
+            const float p8 = __shfl_sync(0xffffffffu, st[2 * kk + 1], ((2 * t) << 2) | t);
+            const float p9 = __shfl_sync(0xffffffffu, st[2 * kk + 1], ((2 * t + 1) << 2) | t);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float2 a = unpack_f16x2(vb[kk][nt][0]), c = unpack_f16x2(vb[kk][nt][1]);
+                acc[nt] = fmaf(p0, a.x, fmaf(p1, a.y, fmaf(p8, c.x, fmaf(p9, c.y, acc[nt]))));
+            }
+        }
+        const uint32_t vw[4] = {vtg.x, vtg.y, vtg.z, vtg.w};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            acc[nt] = quad_sum(acc[nt]);
+            acc[nt] = fmaf(ptt, (nt & 1) ? bf16hi(vw[nt >> 1]) : bf16lo(vw[nt >> 1]), acc[nt]) * inv;
+        }
+        if (t == 0) {
+            uint4 a;
+            a.x = pack_bf16x2_rn(acc[0], acc[1]); a.y = pack_bf16x2_rn(acc[2], acc[3]);
+            a.z = pack_bf16x2_rn(acc[4], acc[5]); a.w = pack_bf16x2_rn(acc[6], acc[7]);
+            *reinterpret_cast<uint4*>(out + (row0 + static_cast<int64_t>(R) * tokens) * inner + h * TA_DH + 8 * g) = a;
+        }
+    }
+    // the lane's 16 output dims of the last frame's V, for the last key's contribution to every row
+    float vtf[16];
+    if constexpr (TAIL) {
+        const uint32_t w[8] = {vt[0].x, vt[0].y, vt[0].z, vt[0].w, vt[1].x, vt[1].y, vt[1].z, vt[1].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            vtf[2 * i] = bf16lo(w[i]);
+            vtf[2 * i + 1] = bf16hi(w[i]);
+        }
+    }
+
+    // ================= the query tiles =================
 #pragma unroll
     for (int mi = 0; mi < MT; ++mi) {
-        if (16 * mi >= frames) break;                    // warp-uniform
+        if (16 * mi >= fmain) break;                     // warp-uniform
+        if (mi + 1 < MT && 16 * (mi + 1) < fmain) load_q(mi + 1, qn);      // prefetch the next tile's rows
         const int r0 = 16 * mi + g, r1 = r0 + 8;         // the two query frames of this lane
-        uint4 qa[2][2] = {{zero, zero}, {zero, zero}};
-        if (r0 < frames) {
-            qa[0][0] = ldg_nc_u4(qbase + r0 * qk_pitch + 8 * t);
-            qa[0][1] = ldg_nc_u4(qbase + r0 * qk_pitch + 8 * (t + 4));
-        }
-        if (r1 < frames) {
-            qa[1][0] = ldg_nc_u4(qbase + r1 * qk_pitch + 8 * t);
-            qa[1][1] = ldg_nc_u4(qbase + r1 * qk_pitch + 8 * (t + 4));
-        }
         // ---- S = Q K^T: s[nj] = {S[r0][8nj+2t], S[r0][8nj+2t+1], S[r1][8nj+2t], S[r1][8nj+2t+1]} ----
         float s[NT][4];
 #pragma unroll
         for (int nj = 0; nj < NT; ++nj) {
             s[nj][0] = s[nj][1] = s[nj][2] = s[nj][3] = 0.f;
-            if (8 * nj < frames) {
+            if (8 * nj < fmain) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     mma_bf16_16816(s[nj], qa[0][c].x, qa[1][c].x, qa[0][c].y, qa[1][c].y, kf[nj][c].x, kf[nj][c].y);
@@ -329,100 +497,99 @@ attn_temporal_mma_wide_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_b
                 }
             }
         }
-        // ---- softmax over the keys (n-tiles x quad lanes) ----
+        float sl0 = -INFINITY, sl1 = -INFINITY;          // TAIL: scores against the last key (log2 domain)
+        if constexpr (TAIL) {
+            sl0 = quad_sum(dot16_bf16(qa[0], kt)) * scale_log2;
+            sl1 = quad_sum(dot16_bf16(qa[1], kt)) * scale_log2;
+        }
+        // ---- softmax over the keys (n-tiles x quad lanes [+ the last key]) ----
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int nj = 0; nj < NT; ++nj) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const bool ok = 8 * nj + 2 * t + e < frames;
+                const bool ok = TAIL || 8 * nj + 2 * t + e < frames;
                 s[nj][e] = ok ? s[nj][e] * scale_log2 : -INFINITY;
                 s[nj][2 + e] = ok ? s[nj][2 + e] * scale_log2 : -INFINITY;
                 mx0 = fmaxf(mx0, s[nj][e]);
                 mx1 = fmaxf(mx1, s[nj][2 + e]);
             }
         }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        uint32_t pa[NT][2];            // bf16 P: [nj][0] = row r0, [nj][1] = row r1
+        mx0 = fmaxf(quad_max(mx0), sl0);
+        mx1 = fmaxf(quad_max(mx1), sl1);
+        uint32_t pa[NT][2];            // fp16 P: [nj][0] = row r0, [nj][1] = row r1
         float sum0 = 0.f, sum1 = 0.f, sum0_32 = 0.f, sum1_32 = 0.f;
 #pragma unroll
         for (int nj = 0; nj < NT; ++nj) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float pe;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(s[nj][e] - (e < 2 ? mx0 : mx1)));
-                s[nj][e] = pe;
-            }
+            for (int e = 0; e < 4; ++e) s[nj][e] = ex2f(s[nj][e] - (e < 2 ? mx0 : mx1));
             sum0_32 += s[nj][0] + s[nj][1];
             sum1_32 += s[nj][2] + s[nj][3];
-            // the P.V MMA consumes bf16 P: normalise by the sum of the rounded values
-            const __nv_bfloat162 p0 = __floats2bfloat162_rn(s[nj][0], s[nj][1]);
-            const __nv_bfloat162 p1 = __floats2bfloat162_rn(s[nj][2], s[nj][3]);
-            pa[nj][0] = *reinterpret_cast<const uint32_t*>(&p0);
-            pa[nj][1] = *reinterpret_cast<const uint32_t*>(&p1);
-            const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+            // the P.V MMA consumes fp16 P: normalise by the sum of the rounded values
+            pa[nj][0] = pack_f16x2(s[nj][0], s[nj][1]);
+            pa[nj][1] = pack_f16x2(s[nj][2], s[nj][3]);
+            const float2 f0 = unpack_f16x2(pa[nj][0]), f1 = unpack_f16x2(pa[nj][1]);
             sum0 += f0.x + f0.y;
             sum1 += f1.x + f1.y;
         }
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const float pl0 = TAIL ? ex2f(sl0 - mx0) : 0.f, pl1 = TAIL ? ex2f(sl1 - mx1) : 0.f;
+        sum0 = quad_sum(sum0) + pl0;
+        sum1 = quad_sum(sum1) + pl1;
         const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
 
-        if (probs != nullptr) {    // probs[b, h, pos, i, j], fp32, from the unrounded exponentials
-            sum0_32 += __shfl_xor_sync(0xffffffffu, sum0_32, 1);
-            sum0_32 += __shfl_xor_sync(0xffffffffu, sum0_32, 2);
-            sum1_32 += __shfl_xor_sync(0xffffffffu, sum1_32, 1);
-            sum1_32 += __shfl_xor_sync(0xffffffffu, sum1_32, 2);
-            const float i0 = 1.0f / sum0_32, i1 = 1.0f / sum1_32;
-            float* pr = probs + (((b * heads + h) * tokens + pos) * frames) * frames;
+        if (pr_base != nullptr) {    // probs[b, h, pos, i, j], fp32, from the unrounded exponentials
+            const float i0 = 1.0f / (quad_sum(sum0_32) + pl0), i1 = 1.0f / (quad_sum(sum1_32) + pl1);
 #pragma unroll
             for (int nj = 0; nj < NT; ++nj)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int key = 8 * nj + 2 * t + e;
-                    if (key < frames) {
-                        if (r0 < frames) pr[static_cast<int64_t>(r0) * frames + key] = s[nj][e] * i0;
-                        if (r1 < frames) pr[static_cast<int64_t>(r1) * frames + key] = s[nj][2 + e] * i1;
+                    if (key < fmain) {
+                        if (r0 < fmain) pr_base[static_cast<int64_t>(r0) * frames + key] = s[nj][e] * i0;
+                        if (r1 < fmain) pr_base[static_cast<int64_t>(r1) * frames + key] = s[nj][2 + e] * i1;
                     }
                 }
+            if (TAIL && t == 0) {
+                pr_base[static_cast<int64_t>(r0) * frames + R] = pl0 * i0;
+                pr_base[static_cast<int64_t>(r1) * frames + R] = pl1 * i1;
+            }
         }
 
         // ---- O = P V: lane owns dims [16t, 16t+16) of rows r0 and r1 ----
         float o[8][4];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+        for (int nt = 0; nt < 8; ++nt) {
+            if constexpr (TAIL) {        // the last key's contribution, fp32
+                o[nt][0] = pl0 * vtf[nt]; o[nt][1] = pl0 * vtf[8 + nt];
+                o[nt][2] = pl1 * vtf[nt]; o[nt][3] = pl1 * vtf[8 + nt];
+            } else {
+                o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+            }
+        }
 #pragma unroll
         for (int kk = 0; kk < MT; ++kk) {
-            if (16 * kk >= frames) break;               // warp-uniform
-            const uint32_t w0[4] = {vf[kk][0].x, vf[kk][0].y, vf[kk][0].z, vf[kk][0].w};
-            const uint32_t w1[4] = {vf[kk][1].x, vf[kk][1].y, vf[kk][1].z, vf[kk][1].w};
-            const uint32_t w2[4] = {vf[kk][2].x, vf[kk][2].y, vf[kk][2].z, vf[kk][2].w};
-            const uint32_t w3[4] = {vf[kk][3].x, vf[kk][3].y, vf[kk][3].z, vf[kk][3].w};
+            if (16 * kk >= fmain) break;               // warp-uniform
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const uint32_t sel = (nt & 1) ? 0x7632 : 0x5410;
-                const uint32_t b0 = __byte_perm(w0[nt >> 1], w1[nt >> 1], sel);
-                const uint32_t b1 = __byte_perm(w2[nt >> 1], w3[nt >> 1], sel);
-                mma_bf16_16816(o[nt], pa[2 * kk][0], pa[2 * kk][1], pa[2 * kk + 1][0], pa[2 * kk + 1][1], b0, b1);
-            }
+            for (int nt = 0; nt < 8; ++nt)
+                mma_f16_16816(o[nt], pa[2 * kk][0], pa[2 * kk][1], pa[2 * kk + 1][0], pa[2 * kk + 1][1], vb[kk][nt][0],
+                              vb[kk][nt][1]);
         }
         auto store_row = [&](int r, float inv, int e0) {
             __nv_bfloat16* op = out + (row0 + static_cast<int64_t>(r) * tokens) * inner + h * TA_DH + 16 * t;
             uint4 a, c;
-            a.x = pk(o[0][e0] * inv, o[1][e0] * inv); a.y = pk(o[2][e0] * inv, o[3][e0] * inv);
-            a.z = pk(o[4][e0] * inv, o[5][e0] * inv); a.w = pk(o[6][e0] * inv, o[7][e0] * inv);
-            c.x = pk(o[0][e0 + 1] * inv, o[1][e0 + 1] * inv); c.y = pk(o[2][e0 + 1] * inv, o[3][e0 + 1] * inv);
-            c.z = pk(o[4][e0 + 1] * inv, o[5][e0 + 1] * inv); c.w = pk(o[6][e0 + 1] * inv, o[7][e0 + 1] * inv);
+            a.x = pack_bf16x2_rn(o[0][e0] * inv, o[1][e0] * inv); a.y = pack_bf16x2_rn(o[2][e0] * inv, o[3][e0] * inv);
+            a.z = pack_bf16x2_rn(o[4][e0] * inv, o[5][e0] * inv); a.w = pack_bf16x2_rn(o[6][e0] * inv, o[7][e0] * inv);
+            c.x = pack_bf16x2_rn(o[0][e0 + 1] * inv, o[1][e0 + 1] * inv); c.y = pack_bf16x2_rn(o[2][e0 + 1] * inv, o[3][e0 + 1] * inv);
+            c.z = pack_bf16x2_rn(o[4][e0 + 1] * inv, o[5][e0 + 1] * inv); c.w = pack_bf16x2_rn(o[6][e0 + 1] * inv, o[7][e0 + 1] * inv);
             *reinterpret_cast<uint4*>(op) = a;
             *reinterpret_cast<uint4*>(op + 8) = c;
         };
-        if (r0 < frames) store_row(r0, inv0, 0);
-        if (r1 < frames) store_row(r1, inv1, 2);
+        if (r0 < fmain) store_row(r0, inv0, 0);
+        if (r1 < fmain) store_row(r1, inv1, 2);
+        if (mi + 1 < MT) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) { qa[rr][0] = qn[rr][0]; qa[rr][1] = qn[rr][1]; }
+        }
     }
 }
 
@@ -850,18 +1017,26 @@ extern "C" int istvt_attn_temporal_fwd(const void* qk, const void* v, void* out,
         const int64_t grid = (units + 3) / 4;
         ISTVT_REQUIRE(grid < (int64_t(1) << 31));
         const float sl2 = scale * 1.4426950408889634f;
-        if (frames <= 32)
-            attn_temporal_mma_wide_kernel<2><<<static_cast<unsigned>(grid), 128, 0, st>>>(
-                static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v),
-                static_cast<__nv_bfloat16*>(out), probs, frames, tokens, heads, sl2, units);
+        const __nv_bfloat16* qkp = static_cast<const __nv_bfloat16*>(qk);
+        const __nv_bfloat16* vp = static_cast<const __nv_bfloat16*>(v);
+        __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
+        const unsigned gr = static_cast<unsigned>(grid);
+        // F = 16 MT + 1 (T = 16 / 32 frames + the temporal class frame): core tiles on mma.sync, last frame on the FMA pipe
+        static const bool tail_env = []() { const char* e = getenv("ISTVT_TA_TAIL"); return !e || atoi(e) != 0; }();
+        if (frames == 33 && tail_env)
+            attn_temporal_mma_wide_kernel<2, true><<<gr, 128, 0, st>>>(qkp, vp, op, probs, frames, tokens, heads, sl2, units);
+        else if (frames == 17 && tail_env)
+            attn_temporal_mma_wide_kernel<1, true><<<gr, 128, 0, st>>>(qkp, vp, op, probs, frames, tokens, heads, sl2, units);
+        else if (frames <= 16)
+            attn_temporal_mma_wide_kernel<1, false><<<gr, 128, 0, st>>>(qkp, vp, op, probs, frames, tokens, heads, sl2, units);
+        else if (frames <= 32)
+            attn_temporal_mma_wide_kernel<2, false><<<gr, 128, 0, st>>>(qkp, vp, op, probs, frames, tokens, heads, sl2, units);
         else
-            attn_temporal_mma_wide_kernel<3><<<static_cast<unsigned>(grid), 128, 0, st>>>(
-                static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v),
-                static_cast<__nv_bfloat16*>(out), probs, frames, tokens, heads, sl2, units);
+            attn_temporal_mma_wide_kernel<3, false><<<gr, 128, 0, st>>>(qkp, vp, op, probs, frames, tokens, heads, sl2, units);
         count_launch();
         return launch_status();
     }
-    ISTVT_REQUIRE(heads * frames <= 288);
+    if (heads * frames > 288) return ISTVT_ERR_UNSUPPORTED;    // SIMT kernel (fp32 validation mode): F <= 36
     ISTVT_REQUIRE(static_cast<int64_t>(batch) * tokens < (int64_t(1) << 31));
     if (dtype == ISTVT_BF16)
         return launch_temporal<__nv_bfloat16>(qk, v, out, probs, batch, frames, tokens, heads, scale, st);

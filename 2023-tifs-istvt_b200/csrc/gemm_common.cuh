@@ -29,8 +29,10 @@ struct GemmParams {
                       // the weight-gradient GEMM dW = dY^T X reads dY and X as they sit in HBM, no transposed copies
 #ifdef ISTVT_GEMM_TRACE
     int trace_no_tma; // debug builds only (tools/gemm_trace.py)
+    int trace_no_epi;
 #endif
     int split_producer;  // 1-CTA kernel: warp 0 loads the A boxes and warp 3 the B boxes (two issuing threads)
+    int epi_tma;         // CTA-pair kernel, bf16 output: the epilogue's global stores are TMA box stores from the slabs
 };
 
 // ------------------------------------------------------------------------------------------
@@ -198,6 +200,65 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
                 }
             }
             __syncwarp();   // slab is rewritten by the next pass
+        }
+    }
+}
+
+// bf16 output stored by TMA: the warp stages act(acc + bias) as packed bf16, 32 rows x 32 columns (64-byte rows) at a
+// time, in its 2 KB slab — the row-owner writes of the transpose path above, whose chunk swizzle (q ^ ((r >> 1) & 3)) IS
+// the TMA SWIZZLE_64B pattern for a 512-byte-aligned slab — and one lane issues cp.async.bulk.tensor of the box: no
+// LDS / STG / address arithmetic per lane, ragged M / N edges clipped by the tensor map.  (Storing straight from
+// registers with 32-byte vectors, one output row per lane, measured SLOWER: ff1 0.74 -> 0.79-0.89 ms, to_v 0.132 ->
+// 0.154 ms, profiles/README.md r6d — 32 scattered sectors per store instruction cost more than the staging.)
+// `row0` = first of the warp's 32 consecutive output rows.
+template <typename F>
+__device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, const CUtensorMap* tm_c, uint32_t taddr,
+                                                          uint32_t slab, int row0, int n0, int lane, F after_tmem_reads) {
+    if (n0 >= p.N) {
+        after_tmem_reads();
+        return;
+    }
+    const uint32_t wrow = slab + lane * 64;
+    const int wsw = (lane >> 1) & 3;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int nb = n0 + hh * 32;
+        if (nb >= p.N) {   // warp-uniform: ragged last N tile
+            if (hh == 1) after_tmem_reads();
+            break;
+        }
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + hh * 32, r);
+        // the bias of these 32 columns is fetched while the TMEM load is in flight (the same 128 B for every lane)
+        float4 bv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            bv[q] = (p.bias != nullptr && nb + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + q)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        tmem_ld_wait();
+        if (hh == 1) after_tmem_reads();
+        uint32_t o[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {     // 8 columns -> one 16-byte chunk
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+            v[0] += bv[2 * g].x; v[1] += bv[2 * g].y; v[2] += bv[2 * g].z; v[3] += bv[2 * g].w;
+            v[4] += bv[2 * g + 1].x; v[5] += bv[2 * g + 1].y; v[6] += bv[2 * g + 1].z; v[7] += bv[2 * g + 1].w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = epi_act(v[j], p.act);
+            o[4 * g] = pack_bf16x2(v[0], v[1]); o[4 * g + 1] = pack_bf16x2(v[2], v[3]);
+            o[4 * g + 2] = pack_bf16x2(v[4], v[5]); o[4 * g + 3] = pack_bf16x2(v[6], v[7]);
+        }
+        if (lane == 0) tma_store_wait_read0();     // the previous box has left the slab
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) sts_u4(wrow + ((g ^ wsw) << 4), o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tm_c, slab, nb, row0);
+            tma_store_commit();
         }
     }
 }

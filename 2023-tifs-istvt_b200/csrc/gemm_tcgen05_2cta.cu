@@ -140,6 +140,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         tmem_relinquish_2cta();
     }
     tc_fence_before();
+    __syncthreads();       // CTA-level ordering of the tmem_holder write (compute-sanitizer racecheck does not model
+                           // barrier.cluster as a shared-memory barrier; once per kernel)
     cluster_sync_all();    // barrier inits + TMEM allocation visible in both CTAs before any remote arrive / TMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
@@ -169,8 +171,20 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #ifdef ISTVT_GEMM_TRACE
                     // experiment (results are garbage): after the ring's first fill, signal the slots full WITHOUT loading,
                     // so that the MMAs re-read stale shared memory with no concurrent TMA fills (ISTVT_TRACE_NOTMA=1)
-                    if (p.trace_no_tma && (trace_it > 0 || kb >= G2_STAGES)) {
+                    if (p.trace_no_tma == 1 && (trace_it > 0 || kb >= G2_STAGES)) {
                         if (rank == 0) mbar_arrive(&full_bar[stage]);
+                        if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+#endif
+#ifdef ISTVT_GEMM_TRACE
+                    // ISTVT_TRACE_NOTMA=2 / 3: after the first ring fill only the A / only the B boxes are fetched (the
+                    // other operand is re-read stale): how much of the k-block time is the fill of each operand
+                    if (p.trace_no_tma >= 2 && !p.mn_major && (trace_it > 0 || kb >= G2_STAGES)) {
+                        const bool only_a = p.trace_no_tma == 2;
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (only_a ? G2_A_BYTES : G2_B_BYTES));
+                        if (only_a) tma_load_2d_2cta(smem_a + stage * G2_A_BYTES, &tm_a, &full_bar[stage], kb * G2_BK, m0);
+                        else        tma_load_2d_2cta(smem_b + stage * G2_B_BYTES, &tm_b, &full_bar[stage], kb * G2_BK, n0);
                         if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
@@ -272,6 +286,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             tc_fence_after();
             ISTVT_TRACE(tracer, trace_it, 5);
             uint64_t* te = &tmem_empty[acc];
+#ifdef ISTVT_GEMM_TRACE
+            if (p.trace_no_epi) {     // timing experiment: no TMEM reads, no math, no stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(te, 0);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
+#endif
 #pragma unroll 1
             for (int ps = 0; ps < PASSES; ++ps) {
                 const int col0 = colw + ps * EPI_COLS;
@@ -288,6 +311,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                     gemm_epilogue_reduce_64(p, &tm_c, taddr, slab,
                                             static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32),
                                             n_blk * G2_BN + col0, lane, release);
+                else if (PLAIN_BF16 && p.epi_tma)
+                    gemm_epilogue_tma_bf16_64(p, &tm_c, taddr, slab,
+                                              static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32),
+                                              n_blk * G2_BN + col0, lane, release);
                 else
                     gemm_epilogue_64<PLAIN_BF16>(p, taddr, slab, drow_lane, drow_t, n_blk * G2_BN + col0, lane, release);
             }
@@ -296,8 +323,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         }
     }
 
-    if constexpr (EPI == EPI_REDUCE) {
-        if (warp >= 4 && lane == 0) tma_store_wait0();     // reduce-adds issued by this lane have completed
+    if (EPI == EPI_REDUCE || (EPI == EPI_PLAIN && p.epi_tma)) {
+        if (warp >= 4 && lane == 0) tma_store_wait0();     // TMA stores / reduce-adds issued by this lane have completed
     }
     // No CTA may exit (or free TMEM) while its peer can still multicast-arrive on its barriers or read its smem.
     tc_fence_before();
@@ -366,14 +393,16 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
         const char* e = getenv("ISTVT_G2_EPI_WARPS");
         return e ? atoi(e) : 0;
     }();
-#ifdef ISTVT_GEMM_TRACE
+    // ISTVT_G2_TMASTORE=0: bf16 epilogue with per-lane LDS + STG instead of TMA box stores (A/B measurements)
+    static const int tma_env = []() { const char* e = getenv("ISTVT_G2_TMASTORE"); return e ? atoi(e) : 1; }();
     GemmParams p = p_in;
+#ifdef ISTVT_GEMM_TRACE
     {
         const char* e = getenv("ISTVT_TRACE_NOTMA");
-        p.trace_no_tma = e && atoi(e) != 0;
+        p.trace_no_tma = e ? atoi(e) : 0;
+        const char* f = getenv("ISTVT_TRACE_NOEPI");      // 1: the epilogue warps only release the accumulator
+        p.trace_no_epi = f ? atoi(f) : 0;
     }
-#else
-    const GemmParams& p = p_in;
 #endif
     const bool plain = !p.c_f32 && p.residual == nullptr;
     // In-place fp32 residual update (inference s_out / ff2): the addition is done by the L2 through a TMA reduce-add.
@@ -390,6 +419,14 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
         if (rc != ISTVT_OK) return rc;
     }
     const int ew = reduce ? 16 : (ew_env == 8 || ew_env == 16 ? ew_env : (plain ? 16 : 8));
+    p.epi_tma = plain && ew == 16 && tma_env && !p.mn_major && p.split_k <= 1 && (p.ldc * 2) % 16 == 0;
+    if (p.epi_tma) {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(p.ldc) * 2};
+        const uint32_t box[2] = {32, 32};      // 32 bf16 columns (64 B, SW64) x the warp's 32 rows
+        int rc = encode_tmap(&tm_c, p.C, ISTVT_BF16, 2, dims, strides, box, 2);
+        if (rc != ISTVT_OK) return rc;
+    }
     const unsigned grid = static_cast<unsigned>(2 * clusters);
 #define ISTVT_G2_LAUNCH(EWV, EPIV)                                                                                 \
     do {                                                                                                           \

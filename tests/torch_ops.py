@@ -150,10 +150,232 @@ def token_fill(tokens, space_token, temporal_token, pos_emb):
     tokens[:, 1:, 0] = space_token.reshape(1, 1, d) + pos[None, :, 0]
 
 
+# ---- training step: forward variants that keep what the backward needs, and the backward of every op ----
+def conv_stem_raw(x, w):
+    return _nhwc(F.conv2d(x, w, None, stride=2), x.dtype)
+
+
+class _BNState:
+    pass
+
+
+def batchnorm_train(x, bn, relu, update_running=True):
+    """nn.BatchNorm2d in train mode on NHWC rows: batch statistics, running statistics updated with the UNBIASED variance."""
+    c = x.shape[-1]
+    xf = x.float().reshape(-1, c)
+    m = xf.shape[0]
+    mean, var = xf.mean(0), xf.var(0, unbiased=False)
+    st = _BNState()
+    st.m, st.c, st.mean, st.rstd = m, c, mean, torch.rsqrt(var + bn.eps)
+    st.scale = bn.weight.detach().float() * st.rstd
+    st.shift = bn.bias.detach().float() - mean * st.scale
+    if update_running:
+        with torch.no_grad():
+            bn.running_mean.mul_(1 - bn.momentum).add_(bn.momentum * mean)
+            bn.running_var.mul_(1 - bn.momentum).add_(bn.momentum * var * m / (m - 1))
+            bn.num_batches_tracked += 1
+    y = xf * st.scale + st.shift
+    return (F.relu(y) if relu else y).reshape(x.shape).to(x.dtype), st
+
+
+def batchnorm_bwd(dy, x, st, dgamma, dbeta, relu):
+    c = st.c
+    xf, g = x.float().reshape(-1, c), dy.float().reshape(-1, c)
+    if relu:
+        g = g * ((xf * st.scale + st.shift) > 0)
+    xhat = (xf - st.mean) * st.rstd
+    sb, sg = g.sum(0), (g * xhat).sum(0)
+    dbeta += sb
+    dgamma += sg
+    return (st.scale * (g - sb / st.m - xhat * sg / st.m)).reshape(x.shape).to(x.dtype)
+
+
+def pool_add_idx(x, skip, tokens=None, pos_emb=None, t_frames=1):
+    """max-pool 3x3 s2 p1 + skip; the arg-max is kept as torch's flat window index (private to pool_bwd below)."""
+    y, idx = F.max_pool2d(_nchw(x), 3, 2, 1, return_indices=True)
+    y = _nhwc(y, torch.float32) + skip.float().reshape(x.shape[0], y.shape[2], y.shape[3], x.shape[3])
+    if tokens is None:
+        return y.to(x.dtype), idx
+    n, ho, wo, c = y.shape
+    pos = pos_emb.reshape(t_frames, ho * wo + 1, c)
+    tokens[:, 1:, 1:, :] = y.reshape(n // t_frames, t_frames, ho * wo, c) + pos[None, :, 1:, :]
+    return None, idx
+
+
+def pool_bwd(dy, amax, h, wd):
+    g = _nchw(dy)                                  # overlapping 3x3 / stride-2 windows can share an arg-max: accumulate
+    dx = torch.zeros(g.shape[0], g.shape[1], h * wd)
+    dx.scatter_add_(2, amax.flatten(2), g.flatten(2))
+    return _nhwc(dx.view(g.shape[0], g.shape[1], h, wd), dy.dtype)
+
+
+def token_grad_gather(g):
+    b, f, p, c = g.shape
+    side = int(round((p - 1) ** 0.5))
+    return g[:, 1:, 1:, :].reshape(b * (f - 1), side, side, c).contiguous()
+
+
+def token_bwd(g, d_pos, d_space, d_temporal):
+    d_pos += g[:, 1:].sum(0)                       # pos_embedding is added to every row of the real frames (vivit.py:138)
+    d_space += g[:, 1:, 0].sum((0, 1))
+    d_temporal += g[:, 0].sum((0, 1))
+
+
+def dwconv3x3_wgrad(x, dy, dw, relu_in):
+    xi = F.pad(F.relu(_nchw(x)) if relu_in else _nchw(x), (1, 1, 1, 1))
+    g = _nchw(dy)
+    h, w = g.shape[2:]
+    for ky in range(3):
+        for kx in range(3):
+            dw[ky, kx] += (xi[:, :, ky:ky + h, kx:kx + w] * g).sum((0, 2, 3))
+
+
+def block_input_grad(d_main, x_in, d_skip, relu_in):
+    dx = d_main.float() * (x_in > 0) if relu_in else d_main.float().clone()
+    dx[:, ::2, ::2, :] += d_skip.float()
+    return dx.to(d_main.dtype)
+
+
+def transpose(x, colsum=None):
+    if colsum is not None:
+        colsum += x.float().sum(0)
+    m = x.shape[0]
+    return F.pad(x.t(), (0, (m + 7) // 8 * 8 - m)).contiguous()
+
+
+def im2col_t(x):
+    n, h, w, cin = x.shape
+    cols = torch.stack([x[:, ky:ky + h - 2, kx:kx + w - 2, :] for ky in range(3) for kx in range(3)])   # [9, n, ho, wo, cin]
+    out = cols.permute(0, 4, 1, 2, 3).reshape(9 * cin, -1)
+    return F.pad(out, (0, (out.shape[1] + 7) // 8 * 8 - out.shape[1])).contiguous()
+
+
+def im2col_t_stem(x):
+    n, _, h, w = x.shape
+    ho, wo = (h - 3) // 2 + 1, (w - 3) // 2 + 1
+    rows = [x[:, c, ky:ky + 2 * ho - 1:2, kx:kx + 2 * wo - 1:2].reshape(-1) for c in range(3) for ky in range(3) for kx in range(3)]
+    out = torch.cat((torch.stack(rows), torch.zeros(5, rows[0].numel())))
+    return F.pad(out, (0, (out.shape[1] + 7) // 8 * 8 - out.shape[1])).contiguous()
+
+
+def gemm_wgrad(dyt, xt, rows, dw):
+    dw += (dyt[:, :rows].float() @ xt[:, :rows].float().t()).reshape(dw.shape)
+
+
+def colsum(x, out):
+    out += x.float().sum(0)
+
+
+def wgrad(dy, x, dw, bias_grad=None):
+    dw += (dy.float().t() @ x.float()).reshape(dw.shape)
+    if bias_grad is not None:
+        bias_grad += dy.float().sum(0)
+
+
+def gelu(x):
+    return F.gelu(x.float()).to(x.dtype)
+
+
+def gelu_bwd(dy, x):
+    xf = x.float()
+    cdf = 0.5 * (1 + torch.erf(xf * 0.7071067811865476))
+    pdf = torch.exp(-0.5 * xf * xf) * 0.3989422804014327
+    return (dy.float() * (cdf + xf * pdf)).to(x.dtype)
+
+
+def cast_bf16(x, out=None):
+    if out is None:
+        return x.clone()
+    out.copy_(x)
+    return out
+
+
+def layernorm_bwd(dy, x, gamma, dgamma, dbeta, g_accum=None, g_bf16=None, dy2=None, frames=0, tokens_per_frame=0, eps=1e-5):
+    d = x.shape[-1]
+    xf = x.float().reshape(-1, d)
+    g = dy.float().reshape(-1, d).clone()
+    if dy2 is not None:      # backward of the self-subtract (module.py:192) folded in: diff[f] = xn[f] - xn[f-1] for f >= 2
+        gv, d2 = g.view(-1, frames, tokens_per_frame, d), dy2.float().reshape(-1, frames, tokens_per_frame, d)
+        gv += d2
+        gv[:, 1:frames - 1] -= d2[:, 2:frames]
+    mean = xf.mean(-1, keepdim=True)
+    rstd = torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + eps)
+    xhat = (xf - mean) * rstd
+    dgamma += (g * xhat).sum(0)
+    dbeta += g.sum(0)
+    gg = g * gamma
+    dx = rstd * (gg - gg.mean(-1, keepdim=True) - xhat * (gg * xhat).mean(-1, keepdim=True))
+    if g_accum is None:
+        return dx.reshape(x.shape).to(dy.dtype)
+    g_accum += dx.reshape(g_accum.shape)
+    if g_bf16 is not None:
+        g_bf16.copy_(g_accum.reshape(g_bf16.shape))
+    return None
+
+
+def head_bwd(tokens, dlogits, ng, nb, hg, hb, hw, g, d_ng, d_nb, d_hg, d_hb, d_hw, d_hbias, eps=1e-5):
+    with torch.enable_grad():
+        leaves = [t.detach().clone().requires_grad_(True) for t in (tokens[:, 0, 0], ng, nb, hg, hb, hw)]
+        x, a, b, c, e, w = leaves
+        y = F.layer_norm(F.layer_norm(x, (x.shape[-1],), a, b, eps), (x.shape[-1],), c, e, eps)
+        grads = torch.autograd.grad(y @ w.reshape(-1, 1), leaves, dlogits.reshape(-1, 1))
+    g[:, 0, 0] += grads[0]
+    for dst, src in zip((d_ng, d_nb, d_hg, d_hb, d_hw), grads[1:]):
+        dst += src.reshape(dst.shape)
+    d_hbias += dlogits.sum()
+
+
+def attn_spatial_lse(qkv, batch_frames, tokens, heads, scale):
+    return attention(qkv, batch_frames, tokens, heads, scale)[0], torch.zeros(batch_frames, heads, tokens)
+
+
+def _attn_bwd(q, k, v, do, scale):
+    """q, k, v, do: [..., n, 64] -> (dq, dk, dv, a, da)."""
+    a = torch.softmax(q @ k.transpose(-1, -2) * scale, -1)
+    da = do @ v.transpose(-1, -2)
+    ds = a * (da - (a * da).sum(-1, keepdim=True)) * scale
+    return ds @ k, ds.transpose(-1, -2) @ q, a.transpose(-1, -2) @ do, a, da
+
+
+def attn_spatial_bwd(qkv, o, dout, lse, batch_frames, tokens, heads, scale, scratch=None, cam=None):
+    q, k, v = qkv.float().reshape(batch_frames, tokens, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    do = dout.float().reshape(batch_frames, tokens, heads, 64).permute(0, 2, 1, 3)
+    dq, dk, dv, a, da = _attn_bwd(q, k, v, do, scale)
+    if cam is not None:
+        cam += (a * da).clamp(min=0).mean(1).reshape(cam.shape)
+    return torch.stack((dq, dk, dv)).permute(1, 3, 0, 2, 4).reshape(qkv.shape).to(qkv.dtype)
+
+
+def attn_temporal_bwd(qk, v, dout, b, f, p, heads, scale, cam=None):
+    sp = lambda t: t.float().reshape(b, f, p, heads, 64).permute(0, 3, 2, 1, 4)      # b h p f d
+    inner = heads * 64
+    dq, dk, dv, a, da = _attn_bwd(sp(qk[:, :inner]), sp(qk[:, inner:]), sp(v), sp(dout), scale)
+    if cam is not None:
+        cam += (a * da).clamp(min=0).mean(1).reshape(cam.shape)
+    back = lambda t: t.permute(0, 3, 2, 1, 4).reshape(b * f * p, inner)
+    return torch.cat((back(dq), back(dk)), 1).to(qk.dtype), back(dv).to(v.dtype)
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step=1, grad_scale=1.0):
+    """torch.optim.AdamW (decoupled weight decay), one step on flat buffers."""
+    g = grads * grad_scale
+    params.mul_(1 - lr * weight_decay)
+    exp_avg.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+    exp_avg_sq.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    denom = (exp_avg_sq / (1 - betas[1] ** step)).sqrt_().add_(eps)
+    params.addcdiv_(exp_avg / (1 - betas[0] ** step), denom, value=-lr)
+
+
 ALL = dict(gemm=gemm, layernorm=layernorm, layernorm_diff=layernorm_diff, attn_joint=attn_joint, attn_spatial=attn_spatial,
            attn_temporal=attn_temporal, token_build=token_build, gather_rows=gather_rows, head=head, pool_linear=pool_linear,
            mean_rows=mean_rows, conv_stem=conv_stem, conv_stem_u8=conv_stem_u8, conv3x3=conv3x3, dwconv3x3=dwconv3x3,
-           subsample2=subsample2, pool_add=pool_add, pool_add_tokens=pool_add_tokens, token_fill=token_fill)
+           subsample2=subsample2, pool_add=pool_add, pool_add_tokens=pool_add_tokens, token_fill=token_fill,
+           conv_stem_raw=conv_stem_raw, batchnorm_train=batchnorm_train, batchnorm_bwd=batchnorm_bwd, pool_add_idx=pool_add_idx,
+           pool_bwd=pool_bwd, token_grad_gather=token_grad_gather, token_bwd=token_bwd, dwconv3x3_wgrad=dwconv3x3_wgrad,
+           block_input_grad=block_input_grad, transpose=transpose, im2col_t=im2col_t, im2col_t_stem=im2col_t_stem,
+           gemm_wgrad=gemm_wgrad, colsum=colsum, wgrad=wgrad, gelu=gelu, gelu_bwd=gelu_bwd, cast_bf16=cast_bf16,
+           layernorm_bwd=layernorm_bwd, head_bwd=head_bwd, attn_spatial_lse=attn_spatial_lse, attn_spatial_bwd=attn_spatial_bwd,
+           attn_temporal_bwd=attn_temporal_bwd, adamw_step=adamw_step)
 
 
 def install(monkeypatch, ops_module):
