@@ -72,7 +72,7 @@ class FlatState:
     def __init__(self, model, train_entry_flow: bool, grads_only: bool = False):
         named = on_path_named_parameters(model, train_entry_flow)
         dev = named[0][1].device
-        sizes = [(p.numel() + 3) // 4 * 4 for _, p in named]       # 16-byte aligned slots
+        sizes = [(p.numel() + 7) // 8 * 8 for _, p in named]       # slots 16-byte aligned in fp32 AND in the bf16 mirror
         total = sum(sizes)
         self.grads = torch.zeros(total, dtype=torch.float32, device=dev)
         self.params = self.exp_avg = self.exp_avg_sq = None
@@ -91,6 +91,22 @@ class FlatState:
             self.grad[name] = self.grads[off:off + p.numel()].view(p.shape)
             off += sz
         self.step = 0
+        self._offsets = {}
+        off = 0
+        for (name, p), sz in zip(named, sizes):
+            self._offsets[name] = (off, p.shape)
+            off += sz
+        self.params_bf16: Optional[torch.Tensor] = None
+
+    def bf16_weights(self) -> Optional[Dict[str, torch.Tensor]]:
+        """bf16 mirror of every on-path parameter, refreshed by ONE cast kernel over the flat master buffer (the
+        optimizer moves the weights every step); views share the fp32 slots' offsets.  None for a replica."""
+        if self.params is None:
+            return None
+        if self.params_bf16 is None:
+            self.params_bf16 = torch.empty(self.params.shape, dtype=BF16, device=self.params.device)
+        ops.cast_bf16(self.params, out=self.params_bf16)
+        return {n: self.params_bf16[o:o + torch.Size(shape).numel()].view(shape) for n, (o, shape) in self._offsets.items()}
 
     def attach_grads(self, model, train_entry_flow: bool) -> None:
         """Expose the flat gradient views as `.grad` (for inspection / external optimizers)."""
@@ -101,16 +117,28 @@ class FlatState:
 # ------------------------------------------------------------------------------------------------
 # weight packs for training (bf16 forward weights + their transposes for the data-gradient GEMMs)
 # ------------------------------------------------------------------------------------------------
-def _pack_layers(vit) -> List[SimpleNamespace]:
+def bf16_weight(w: torch.Tensor, mirror: Optional[Dict[str, torch.Tensor]], name: str) -> torch.Tensor:
+    """bf16 copy of an fp32 weight: the view of the flat mirror when there is one, else one cast kernel."""
+    if mirror is not None and name in mirror:
+        return mirror[name]
+    return ops.cast_bf16(w.detach().float().contiguous())
+
+
+def _pack_layers(vit, mirror: Optional[Dict[str, torch.Tensor]] = None) -> List[SimpleNamespace]:
+    """Per-layer bf16 weights [N, K] and their transposes [K, N] (B operand of the data-gradient GEMMs); `mirror` =
+    FlatState.bf16_weights().  The transposes are produced by istvt_transpose_colsum — no ATen kernel on the path."""
     layers = []
     f32 = lambda t: t.detach().float().contiguous()
-    for attn_t, attn_s, ff in vit.transformer.layers:
+    for li, (attn_t, attn_s, ff) in enumerate(vit.transformer.layers):
         L = SimpleNamespace()
-        for key, lin in (("qk", attn_t.fn.to_qk), ("v", attn_t.fn.to_v), ("to", attn_t.fn.to_out[0]),
-                         ("qkv", attn_s.fn.to_qkv), ("so", attn_s.fn.to_out[0]), ("1", ff.fn.net[0]), ("2", ff.fn.net[3])):
-            w = lin.weight.detach().to(BF16).contiguous()
+        pre = f"vit.transformer.layers.{li}"
+        for key, lin, name in (("qk", attn_t.fn.to_qk, f"{pre}.0.fn.to_qk"), ("v", attn_t.fn.to_v, f"{pre}.0.fn.to_v"),
+                               ("to", attn_t.fn.to_out[0], f"{pre}.0.fn.to_out.0"), ("qkv", attn_s.fn.to_qkv, f"{pre}.1.fn.to_qkv"),
+                               ("so", attn_s.fn.to_out[0], f"{pre}.1.fn.to_out.0"), ("1", ff.fn.net[0], f"{pre}.2.fn.net.0"),
+                               ("2", ff.fn.net[3], f"{pre}.2.fn.net.3")):
+            w = bf16_weight(lin.weight, mirror, name + ".weight")
             setattr(L, "w_" + key, w)
-            setattr(L, "wT_" + key, w.t().contiguous())
+            setattr(L, "wT_" + key, ops.transpose(w))
             if lin.bias is not None:
                 setattr(L, "b_" + key, f32(lin.bias))
         L.ln1 = (f32(attn_t.norm.weight), f32(attn_t.norm.bias))
@@ -321,10 +349,11 @@ class Trainer:
         f32 = lambda z: z.detach().float().contiguous()
         pos = f32(vit.pos_embedding[0])
         tokens = torch.empty(b, t + 1, vit.num_patches + 1, vit.dim, dtype=torch.float32, device=x.device)
+        mirror = self.state.bf16_weights()
         entry = None
         if self.train_entry_flow:
             from .train_entry import EntryFlowTrainer
-            entry = EntryFlowTrainer(model.xcep.model)       # stateless: binds the module tree this forward ran on
+            entry = EntryFlowTrainer(model.xcep.model, mirror)   # stateless: binds the module tree this forward ran on
             body, skip, ectx = entry.forward(frames)
             _, amax3 = ops.pool_add_idx(body, skip, tokens=tokens, pos_emb=pos, t_frames=t)
         else:
@@ -333,7 +362,7 @@ class Trainer:
             ops.pool_add_tokens(body, skip, pos, tokens, b, t)
         del body, skip
         ops.token_fill(tokens, f32(vit.space_token.reshape(-1)), f32(vit.temporal_token.reshape(-1)), pos)
-        layers = _pack_layers(vit)
+        layers = _pack_layers(vit, mirror)
         logits, ctxs, x_final, head = transformer_forward_train(vit, layers, tokens)
         saved = SimpleNamespace(layers=layers, ctxs=ctxs, x_final=x_final, head=head, ectx=ectx, amax3=amax3, b=b, t=t,
                                 vit=vit, entry=entry)

@@ -32,26 +32,32 @@ def _seps(block):
 
 
 class EntryFlowTrainer:
-    def __init__(self, xcep):
+    def __init__(self, xcep, mirror=None):
+        """mirror: FlatState.bf16_weights() — bf16 views of the parameters by state_dict name, or None."""
         self.x = xcep
+        self.mirror = mirror
+
+    def _w(self, weight, name: str):
+        from .train import bf16_weight
+        return bf16_weight(weight, self.mirror, "xcep.model." + name)
 
     # ------------------------------------------------------------------ forward
-    def _block_fwd(self, blk, xin: torch.Tensor) -> SimpleNamespace:
+    def _block_fwd(self, blk, xin: torch.Tensor, prefix: str) -> SimpleNamespace:
         n, h, w, cin = xin.shape
         bc = SimpleNamespace(xin=xin)
         bc.skip_in = ops.subsample2(xin)
         ho, wo = bc.skip_in.shape[1:3]
-        wsk = blk.skip.weight.detach().flatten(1).to(BF16).contiguous()
-        bc.wskT = wsk.t().contiguous()
+        wsk = self._w(blk.skip.weight, f"{prefix}.skip.weight").flatten(1)
+        bc.wskT = ops.transpose(wsk)
         bc.s_raw = ops.gemm(bc.skip_in.view(-1, cin), wsk).view(n, ho, wo, -1)
         bc.s, bc.bn_s = ops.batchnorm_train(bc.s_raw, blk.skipbn, relu=False)
         (sep1, bn_a, i1), (sep2, bn_b, i2) = _seps(blk)
         bc.idx = (i1, i2)
         bc.dw1 = sep1.conv1.weight.detach().float()[:, 0].permute(1, 2, 0).contiguous()      # [3, 3, C]
         bc.dw2 = sep2.conv1.weight.detach().float()[:, 0].permute(1, 2, 0).contiguous()
-        pw1 = sep1.pointwise.weight.detach().flatten(1).to(BF16).contiguous()
-        pw2 = sep2.pointwise.weight.detach().flatten(1).to(BF16).contiguous()
-        bc.pw1T, bc.pw2T = pw1.t().contiguous(), pw2.t().contiguous()
+        pw1 = self._w(sep1.pointwise.weight, f"{prefix}.rep.{i1}.pointwise.weight").flatten(1)
+        pw2 = self._w(sep2.pointwise.weight, f"{prefix}.rep.{i2}.pointwise.weight").flatten(1)
+        bc.pw1T, bc.pw2T = ops.transpose(pw1), ops.transpose(pw2)
         bc.d1 = ops.dwconv3x3(xin, bc.dw1, relu_in=blk.start_with_relu)
         bc.p1_raw = ops.gemm(bc.d1.view(-1, cin), pw1).view(n, h, w, -1)
         bc.y1, bc.bn_a = ops.batchnorm_train(bc.p1_raw, bn_a, relu=True)
@@ -73,7 +79,7 @@ class EntryFlowTrainer:
         xin = a2
         c.blocks = []
         for bi, blk in enumerate((x.block1, x.block2, x.block3)):
-            bc = self._block_fwd(blk, xin)
+            bc = self._block_fwd(blk, xin, f"block{bi + 1}")
             c.blocks.append(bc)
             if bi < 2:
                 xin, bc.amax = ops.pool_add_idx(bc.y2, bc.s)
