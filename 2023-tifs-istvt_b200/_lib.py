@@ -73,6 +73,9 @@ SIGNATURES = {
     "istvt_gather_rows": [_P, _P, _L, _L, _L, _L, _L, _P],
     "istvt_gemm_wgrad_accum": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P],
     "istvt_colsum": [_P, _P, _L, _I, _P],
+    "istvt_gemm_rowstats_fwd": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _P, _P],
+    "istvt_ln_stats_finalize": [_P, _P, _L, _I, _F, _P],
+    "istvt_gemm_lnfold_fwd": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _P, _P, _P],
 }
 _RESTYPES = {"istvt_error_string": c_char_p, "istvt_launch_count": c_int64}
 

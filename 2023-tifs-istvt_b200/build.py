@@ -32,6 +32,7 @@ SOURCES = [
     "backward.cu",
     "entry_flow_bwd.cu",
     "entry_flow.cu",
+    "conv_stem_tc.cu",
     "xception_tail.cu",
 ]
 NVCC_FLAGS = [

@@ -282,7 +282,7 @@ constexpr int TB_THREADS = 384;
 constexpr int TB_TILE = 128 * 64 * 2;                 // 16 KB: 128 rows x 64 bf16
 constexpr int TB_K_OFF = 0, TB_V_OFF = TB_TILE, TB_Q_OFF = 2 * TB_TILE, TB_DO_OFF = 4 * TB_TILE;
 constexpr int TB_P_OFF = 6 * TB_TILE, TB_DS_OFF = 8 * TB_TILE, TB_MISC_OFF = 10 * TB_TILE;      // 160 KB
-constexpr int TB_SMEM = TB_MISC_OFF + 1024 + 256 + 2 * 128 * 4 + 128 * 4;
+constexpr int TB_SMEM = TB_MISC_OFF + 1024 + 256 + 2 * (2 * 128 * 4 + 128 * 4);
 
 __global__ void __launch_bounds__(TB_THREADS, 1)
 attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
@@ -301,8 +301,11 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
     uint64_t* dq_empty = bars + 8;
     uint64_t* fin = bars + 9;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
-    float* s_dpart = reinterpret_cast<float*>(smem + TB_MISC_OFF + 256);    // [2][128] partial D
-    float* s_lse = s_dpart + 256;                                            // [128]
+    // double-buffered by the parity of the query tile: the reads of tile t and the writes of tile t + 1 are ordered by
+    // the mbarrier chain p_ready -> MMA -> dq_full, which compute-sanitizer's racecheck does not model (r6a); with two
+    // copies every reuse is also separated by the named barrier of the tile in between
+    float* s_dpart0 = reinterpret_cast<float*>(smem + TB_MISC_OFF + 256);   // [2 tiles][2][128] partial D
+    float* s_lse0 = s_dpart0 + 512;                                          // [2 tiles][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k_chunks = (tokens + 127) / 128;
@@ -411,6 +414,8 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
                     for (int e = 0; e < 8; ++e) dpart = fmaf(a[e], b[e], dpart);
                 }
             }
+            float* s_dpart = s_dpart0 + (t & 1) * 256;
+            float* s_lse = s_lse0 + (t & 1) * 128;
             s_dpart[half * 128 + row] = dpart;
             if (half == 0) s_lse[row] = row_ok ? lse[(static_cast<int64_t>(bf) * heads + h) * tokens + q_idx] : INFINITY;
             asm volatile("bar.sync 1, 256;" ::: "memory");

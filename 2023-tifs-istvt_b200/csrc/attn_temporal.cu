@@ -316,6 +316,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(float x, float y) {
 }
 
 // TAIL = false: any 8 < F <= 16 MT (rows / keys >= F masked).  TAIL = true: F == 16 MT + 1 exactly.
+// (4 CTAs per SM at 128 registers, ~0.5 KB of spills per thread, measured slower: 1.44 vs 1.20 ms per C5 step, r6g.)
 template <int MT, bool TAIL>
 __global__ void __launch_bounds__(128, TAIL ? 3 : 2)
 attn_temporal_mma_wide_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,

@@ -596,9 +596,19 @@ static inline unsigned blocks_for(int64_t total, int threads) {
     return static_cast<unsigned>((total + threads - 1) / threads);
 }
 
+// conv_stem_tc.cu: the bf16-output stem as a TF32 implicit GEMM on tcgen05
+int conv_stem_tc_launch(const void* x, bool u8, const float* wt, const float* bias, void* y, int n, int h, int w,
+                        int relu, cudaStream_t st);
+
 }  // namespace istvt
 
 using namespace istvt;
+
+// ISTVT_STEM_TC=0: the SIMT stem kernels also for bf16 output (A/B measurements)
+static bool stem_tc_enabled() {
+    static const bool on = []() { const char* e = getenv("ISTVT_STEM_TC"); return !e || atoi(e) != 0; }();
+    return on;
+}
 
 static int conv_stem_launch(const float* x, const float* wt, const float* bias, void* y, int dtype, int n, int h, int w,
                             int cout, int relu, cudaStream_t st) {
@@ -609,6 +619,7 @@ static int conv_stem_launch(const float* x, const float* wt, const float* bias, 
     int64_t blocks = (total + 127) / 128;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
     if (blocks > cap) blocks = cap;
+    if (dtype == ISTVT_BF16 && stem_tc_enabled()) return conv_stem_tc_launch(x, false, wt, bias, y, n, h, w, relu, st);
     if (dtype == ISTVT_BF16)
         conv_stem_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 128, 0, st>>>(
             x, wt, bias, static_cast<__nv_bfloat16*>(y), n, h, w, ho, wo, relu);
@@ -636,6 +647,7 @@ extern "C" int istvt_conv_stem_u8_fwd(const uint8_t* x, const float* wt, const f
     int64_t blocks = (total + 127) / 128;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 32;
     if (blocks > cap) blocks = cap;
+    if (dtype == ISTVT_BF16 && stem_tc_enabled()) return conv_stem_tc_launch(x, true, wt, bias, y, n, h, w, 1, st);
     if (dtype == ISTVT_BF16)
         conv_stem_u8_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 128, 0, st>>>(
             x, wt, bias, static_cast<__nv_bfloat16*>(y), n, h, w, ho, wo);

@@ -33,6 +33,13 @@ struct GemmParams {
 #endif
     int split_producer;  // 1-CTA kernel: warp 0 loads the A boxes and warp 3 the B boxes (two issuing threads)
     int epi_tma;         // CTA-pair kernel, bf16 output: the epilogue's global stores are TMA box stores from the slabs
+    // LayerNorm folded around a GEMM pair (CTA-pair kernel, bf16 output, TMA-store epilogue; engine.py, LN2).
+    // Row statistics travel as one (sum, M2) pair per row and 64-column group — M2 = sum of squared deviations from the
+    // GROUP mean — and are combined with Chan's formula: no atomics (bitwise reproducible), no E[x^2] - mu^2 cancellation.
+    float2* row_stats_out;   // producer: fp32 [M, ceil(N / 64), 2], every slot written exactly once
+    const float2* ln_stats;  // consumer: (mu, rstd) of ITS A rows, fp32 [M, 2];  C = rstd_m (acc - mu_m ln_c[n]) + ln_d[n]
+    const float* ln_c;       //   fp32 [N]: row sums of the gamma-folded bf16 weight
+    const float* ln_d;       //   fp32 [N]: W beta
 };
 
 // ------------------------------------------------------------------------------------------
@@ -220,6 +227,15 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
     }
     const uint32_t wrow = slab + lane * 64;
     const int wsw = (lane >> 1) & 3;
+    const bool row_ok = row0 + lane < p.M;
+    // LayerNorm fold, consumer side: this lane's row statistics (mu, rstd), finalized by istvt_ln_stats_finalize
+    float ln_a = 1.f, ln_b = 0.f;             // C = ln_a * acc + ln_b * c[n] + d[n],  ln_b = -rstd * mu
+    if (p.ln_stats != nullptr && row_ok) {
+        const float2 st = __ldg(p.ln_stats + row0 + lane);
+        ln_a = st.y;
+        ln_b = -st.y * st.x;
+    }
+    float st_n = 0.f, st_sum = 0.f, st_m2 = 0.f, st_shift = 0.f;   // producer side: shifted sums of this warp's columns
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
         const int nb = n0 + hh * 32;
@@ -230,11 +246,12 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + hh * 32, r);
         // the bias of these 32 columns is fetched while the TMEM load is in flight (the same 128 B for every lane)
+        const float* bsrc = p.ln_stats != nullptr ? p.ln_d : p.bias;
         float4 bv[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-            bv[q] = (p.bias != nullptr && nb + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + nb) + q)
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            bv[q] = (bsrc != nullptr && nb + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(bsrc + nb) + q)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
         tmem_ld_wait();
         if (hh == 1) after_tmem_reads();
         uint32_t o[16];
@@ -243,12 +260,37 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-            v[0] += bv[2 * g].x; v[1] += bv[2 * g].y; v[2] += bv[2 * g].z; v[3] += bv[2 * g].w;
-            v[4] += bv[2 * g + 1].x; v[5] += bv[2 * g + 1].y; v[6] += bv[2 * g + 1].z; v[7] += bv[2 * g + 1].w;
+            if (p.ln_stats != nullptr) {
+                float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                if (nb + 8 * g < p.N) {
+                    c0 = __ldg(reinterpret_cast<const float4*>(p.ln_c + nb) + 2 * g);
+                    c1 = __ldg(reinterpret_cast<const float4*>(p.ln_c + nb) + 2 * g + 1);
+                }
+                v[0] = fmaf(ln_a, v[0], fmaf(ln_b, c0.x, bv[2 * g].x)); v[1] = fmaf(ln_a, v[1], fmaf(ln_b, c0.y, bv[2 * g].y));
+                v[2] = fmaf(ln_a, v[2], fmaf(ln_b, c0.z, bv[2 * g].z)); v[3] = fmaf(ln_a, v[3], fmaf(ln_b, c0.w, bv[2 * g].w));
+                v[4] = fmaf(ln_a, v[4], fmaf(ln_b, c1.x, bv[2 * g + 1].x)); v[5] = fmaf(ln_a, v[5], fmaf(ln_b, c1.y, bv[2 * g + 1].y));
+                v[6] = fmaf(ln_a, v[6], fmaf(ln_b, c1.z, bv[2 * g + 1].z)); v[7] = fmaf(ln_a, v[7], fmaf(ln_b, c1.w, bv[2 * g + 1].w));
+            } else {
+                v[0] += bv[2 * g].x; v[1] += bv[2 * g].y; v[2] += bv[2 * g].z; v[3] += bv[2 * g].w;
+                v[4] += bv[2 * g + 1].x; v[5] += bv[2 * g + 1].y; v[6] += bv[2 * g + 1].z; v[7] += bv[2 * g + 1].w;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = epi_act(v[j], p.act);
             o[4 * g] = pack_bf16x2(v[0], v[1]); o[4 * g + 1] = pack_bf16x2(v[2], v[3]);
             o[4 * g + 2] = pack_bf16x2(v[4], v[5]); o[4 * g + 3] = pack_bf16x2(v[6], v[7]);
+            if (p.row_stats_out != nullptr && nb + 8 * g < p.N) {
+                // LayerNorm statistics of the output row (fp32 values: rounding to bf16 moves mean and variance of 728
+                // features by ~1e-5 relative).  Sums are taken about a per-row shift — the row's first value in this
+                // column group — so that sum of squares does not cancel when |mean| >> sigma.
+                if (hh == 0 && g == 0) st_shift = v[0];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float dv = v[j] - st_shift;
+                    st_sum += dv;
+                    st_m2 = fmaf(dv, dv, st_m2);
+                }
+                st_n += 8.f;
+            }
         }
         if (lane == 0) tma_store_wait_read0();     // the previous box has left the slab
         __syncwarp();
@@ -260,6 +302,12 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
             tma_store_2d(tm_c, slab, nb, row0);
             tma_store_commit();
         }
+    }
+    if (p.row_stats_out != nullptr && row_ok) {
+        // (sum, M2 about the group mean) of this 64-column group: M2 = sum (x - s)^2 - n (mean - s)^2
+        const float dmean = st_sum / st_n;
+        p.row_stats_out[static_cast<int64_t>(row0 + lane) * ((p.N + 63) >> 6) + (n0 >> 6)] =
+            make_float2(fmaf(st_n, st_shift, st_sum), fmaxf(st_m2 - st_sum * dmean, 0.f));
     }
 }
 

@@ -340,6 +340,67 @@ extern "C" int istvt_gemm_fwd(const void* a, int64_t lda, const void* w, int64_t
     return gemm_bf16_dispatch(a, m, lda, w, ldw, k, p, static_cast<cudaStream_t>(stream));
 }
 
+// LayerNorm folded around a GEMM pair (see include/istvt_b200.h): both halves run on the CTA-pair kernel's TMA-store
+// epilogue, so N >= 256, bf16 output, 16-byte row pitch.
+extern "C" int istvt_gemm_rowstats_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c, int64_t ldc,
+                                       int64_t m, int n, int k, const float* bias, float* row_stats,
+                                       istvt_stream_t stream) {
+    ISTVT_REQUIRE(row_stats != nullptr && n >= 256 && (ldc * 2) % 16 == 0);
+    ISTVT_REQUIRE((reinterpret_cast<uintptr_t>(row_stats) & 7) == 0);
+    GemmParams p{};
+    p.M = m; p.N = n; p.K = k;
+    p.taps = 1;
+    p.C = c; p.ldc = ldc;
+    p.bias = bias;
+    p.act = ISTVT_ACT_NONE;
+    p.row_stats_out = reinterpret_cast<float2*>(row_stats);
+    return gemm_bf16_dispatch(a, m, lda, w, ldw, k, p, static_cast<cudaStream_t>(stream));
+}
+
+// (mu, rstd) per row from the per-group partials of istvt_gemm_rowstats_fwd, Chan's parallel-variance combination.
+__global__ void __launch_bounds__(256)
+ln_stats_finalize_kernel(const float2* __restrict__ partials, float2* __restrict__ out, int64_t m, int groups, int dim,
+                         float eps) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= m) return;
+    const float2* st = partials + row * groups;
+    float tot = 0.f;
+    for (int g = 0; g < groups; ++g) tot += st[g].x;
+    const float mu = tot / static_cast<float>(dim);
+    float m2 = 0.f;
+    for (int g = 0; g < groups; ++g) {
+        const float ng = static_cast<float>(min(64, dim - 64 * g));
+        const float dm = st[g].x / ng - mu;
+        m2 += st[g].y + ng * dm * dm;
+    }
+    out[row] = make_float2(mu, rsqrtf(m2 / static_cast<float>(dim) + eps));
+}
+
+extern "C" int istvt_ln_stats_finalize(const float* partials, float* mu_rstd, int64_t m, int dim, float eps,
+                                       istvt_stream_t stream) {
+    ISTVT_REQUIRE(partials && mu_rstd && m > 0 && dim > 0);
+    ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(mu_rstd)) & 7) == 0);
+    ln_stats_finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(partials), reinterpret_cast<float2*>(mu_rstd), m, (dim + 63) / 64, dim, eps);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_gemm_lnfold_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c, int64_t ldc,
+                                     int64_t m, int n, int k, const float* mu_rstd, const float* w_rowsum,
+                                     const float* shift, istvt_stream_t stream) {
+    ISTVT_REQUIRE(mu_rstd != nullptr && w_rowsum != nullptr && shift != nullptr && n >= 256 && (ldc * 2) % 16 == 0);
+    ISTVT_REQUIRE(((reinterpret_cast<uintptr_t>(mu_rstd) & 7) | (reinterpret_cast<uintptr_t>(w_rowsum) & 15) |
+                   (reinterpret_cast<uintptr_t>(shift) & 15)) == 0);
+    GemmParams p{};
+    p.M = m; p.N = n; p.K = k;
+    p.taps = 1;
+    p.C = c; p.ldc = ldc;
+    p.act = ISTVT_ACT_NONE;
+    p.ln_stats = reinterpret_cast<const float2*>(mu_rstd); p.ln_c = w_rowsum; p.ln_d = shift;
+    return gemm_bf16_dispatch(a, m, lda, w, ldw, k, p, static_cast<cudaStream_t>(stream));
+}
+
 // split-K plan shared by the two weight-gradient entry points
 static void plan_splitk(GemmParams& p, int64_t m, int n) {
     const int num_kb = (p.K + 63) / 64;

@@ -14,6 +14,7 @@ BatchNorm (eval mode) is folded: scale into the bf16 weights, shift into the GEM
 """
 from __future__ import annotations
 
+import os
 import weakref
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
@@ -23,6 +24,7 @@ import torch
 from . import ops
 
 PRECISIONS = {"bf16": torch.bfloat16, "fp32": torch.float32}
+_LN2_FOLD = os.environ.get("ISTVT_LN2_FOLD", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -65,6 +67,17 @@ class _LayerPack:
     b_1: torch.Tensor
     w_2: torch.Tensor
     b_2: torch.Tensor
+    # LayerNorm 2 folded into to_qkv (bf16 mode): LN(y) W^T = rstd (y (gamma o W)^T - mu rowsum(gamma o W)) + W beta
+    w_qkv_f: Optional[torch.Tensor] = None      # bf16 [1536, 728] = gamma o W
+    ln2_c: Optional[torch.Tensor] = None        # fp32 [1536]: row sums of the ROUNDED folded weight
+    ln2_d: Optional[torch.Tensor] = None        # fp32 [1536]: W beta
+
+
+def fold_layernorm(weight: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dt: torch.dtype):
+    """(gamma o W in `dt`, its fp32 row sums, W beta) for ops.gemm_lnfold; weight [N, K] fp32, gamma / beta [K]."""
+    w = weight.detach().float()
+    wf = (w * gamma.detach().float()[None, :]).to(dt).contiguous()
+    return wf, wf.float().sum(dim=1).contiguous(), (w @ beta.detach().float()).contiguous()
 
 
 @dataclass
@@ -164,13 +177,17 @@ def pack_model(model, dt: torch.dtype) -> _Pack:
     wt = lambda m: m.weight.detach().to(dt).contiguous()
     layers = []
     for attn_t, attn_s, ff in vit.transformer.layers:
-        layers.append(_LayerPack(
+        lp = _LayerPack(
             ln1=ln(attn_t.norm), w_qk=wt(attn_t.fn.to_qk), w_v=wt(attn_t.fn.to_v),
             w_to=wt(attn_t.fn.to_out[0]), b_to=_f32(attn_t.fn.to_out[0].bias),
             ln2=ln(attn_s.norm), w_qkv=wt(attn_s.fn.to_qkv),
             w_so=wt(attn_s.fn.to_out[0]), b_so=_f32(attn_s.fn.to_out[0].bias),
             ln3=ln(ff.norm), w_1=wt(ff.fn.net[0]), b_1=_f32(ff.fn.net[0].bias),
-            w_2=wt(ff.fn.net[3]), b_2=_f32(ff.fn.net[3].bias)))
+            w_2=wt(ff.fn.net[3]), b_2=_f32(ff.fn.net[3].bias))
+        if dt == torch.bfloat16:
+            lp.w_qkv_f, lp.ln2_c, lp.ln2_d = fold_layernorm(attn_s.fn.to_qkv.weight, attn_s.norm.weight,
+                                                            attn_s.norm.bias, dt)
+        layers.append(lp)
     return _Pack(
         entry=pack_entry(model.xcep.model, dt),
         pos_emb=_f32(vit.pos_embedding[0]), space_token=_f32(vit.space_token.reshape(-1)),
@@ -446,6 +463,10 @@ class ISTVTEngine:
         # work actually executed.
         prune_last = not return_attention and taps is None and not ln2_input_fp32
         cls_stream = None
+        # LayerNorm 2 never runs as a pass in bf16 mode: to_out's epilogue emits the row sums of y1, to_qkv consumes
+        # y1 with gamma folded into its weight and applies mu / rstd / beta in its epilogue (ISTVT_LN2_FOLD=0: A/B)
+        fold_ln2 = dt == torch.bfloat16 and not ln2_input_fp32 and _LN2_FOLD
+        row_stats = torch.empty(rows, (dim + 63) // 64, 2, dtype=torch.float32, device=dev) if fold_ln2 else None
         for li, lp in enumerate(pk.layers):
             # temporal self-subtract attention (module.py:190-208), no residual of its own (vivit.py:99)
             ops.layernorm_diff(tokens, lp.ln1[0], lp.ln1[1], dt, out=(xn, diff))
@@ -465,10 +486,14 @@ class ISTVTEngine:
                 ops.gemm(hid, lp.w_2, bias=lp.b_2, residual=x_cls, out=x_cls)
                 cls_stream = x_cls.view(b, 1, 1, dim)
                 break
-            y1 = ops.gemm(at, lp.w_to, bias=lp.b_to, out_dtype=torch.float32 if ln2_input_fp32 else dt)
             # spatial attention (module.py:81-93) + the residual spanning both attentions (vivit.py:99)
-            yn = ops.layernorm(y1, lp.ln2[0], lp.ln2[1], dt, out=xn.view(rows, dim))
-            qkv = ops.gemm(yn, lp.w_qkv)
+            if fold_ln2:
+                y1 = ops.gemm_rowstats(at, lp.w_to, lp.b_to, row_stats)
+                qkv = ops.gemm_lnfold(y1, lp.w_qkv_f, ops.ln_stats_finalize(row_stats, dim), lp.ln2_c, lp.ln2_d)
+            else:
+                y1 = ops.gemm(at, lp.w_to, bias=lp.b_to, out_dtype=torch.float32 if ln2_input_fp32 else dt)
+                yn = ops.layernorm(y1, lp.ln2[0], lp.ln2[1], dt, out=xn.view(rows, dim))
+                qkv = ops.gemm(yn, lp.w_qkv)
             as_, p_s = ops.attn_spatial(qkv, b * f_tok, p_tok, heads, scale, want_probs=return_attention)
             tok2d = tokens.view(rows, dim)
             ops.gemm(as_, lp.w_so, bias=lp.b_so, residual=tok2d, out=tok2d)

@@ -232,7 +232,21 @@ class XceptionVidTr(nn.Module):
                 raise ValueError("uint8 clips are an inference-path input: normalise to fp32 [B, T, 3, H, W] for training")
             from ...train import autograd_forward
             return autograd_forward(self, x)
+        if self.keep_relprop_input and not self.training:
+            self.__dict__["_relprop_clips"] = x if x.shape[0] == 1 else None
         return self.engine().forward(self, x, precision=self.precision, return_attention=return_attention)
+
+    keep_relprop_input = False      # True: eval-mode forwards remember their batch-1 clip for a following relprop()
+
+    def relprop(self, cam=None, method: str = "transformer_attribution", is_ablation: bool = False,
+                start_layer: int = 0, alpha: float = 1, clips=None):
+        """Relevance maps (cam_s, cam_t) of the last decision — the call the reference's relevance generator makes on
+        its model (visualize_rel.py:206,257; the model class itself, `tfe...ViT_LRP.VisionTransformer`, models.py:26,180,
+        is absent from the reference tree).  See relevance.relprop."""
+        if not isinstance(self.vit, DSTTr):
+            raise NotImplementedError("relprop is built for the ISTVT model (variant='dsttr')")
+        from ...relevance import relprop
+        return relprop(self, cam, method=method, is_ablation=is_ablation, start_layer=start_layer, alpha=alpha, clips=clips)
 
     def _apply(self, fn, *args, **kwargs):  # .cuda() / .to(): drop the packed-weight cache and the flat train state
         self._shared.reset()

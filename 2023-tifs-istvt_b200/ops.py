@@ -188,6 +188,60 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     return out
 
 
+def gemm_rowstats(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], row_stats: torch.Tensor) -> torch.Tensor:
+    """out = a . w^T + bias (bf16) and row_stats[m, g] = (sum, sum of squared deviations from the group mean) of every
+    64-column group of the output row — the producer half of the LayerNorm fold (istvt_gemm_rowstats_fwd).
+    row_stats: fp32 [M, ceil(N / 64), 2], fully overwritten."""
+    dev = _chk(a, w, bias, row_stats)
+    k = a.shape[-1]
+    m = a.numel() // k
+    n = w.shape[0]
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or w.shape[1] != k:
+        raise ValueError("gemm_rowstats: bf16 a [M, K] and w [N, K]")
+    if row_stats.dtype != torch.float32 or row_stats.numel() != 2 * m * ((n + 63) // 64):
+        raise ValueError("gemm_rowstats: row_stats must be fp32 [M, ceil(N / 64), 2]")
+    out = torch.empty(*a.shape[:-1], n, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "gemm_bf16", 2.0 * m * n * k, _nbytes(a, w, out)):
+        _lib.check(_lib.lib().istvt_gemm_rowstats_fwd(_ptr(a), k, _ptr(w), k, _ptr(out), n, m, n, k, _ptr(bias),
+                                                      _ptr(row_stats), _stream(dev)), "istvt_gemm_rowstats_fwd")
+    return out
+
+
+def ln_stats_finalize(row_stats: torch.Tensor, dim: int, eps: float = 1e-5) -> torch.Tensor:
+    """(mean, rstd) per row, fp32 [M, 2], from gemm_rowstats' per-group partials (istvt_ln_stats_finalize)."""
+    dev = _chk(row_stats)
+    groups = (dim + 63) // 64
+    if row_stats.dtype != torch.float32 or row_stats.numel() % (2 * groups):
+        raise ValueError("ln_stats_finalize: row_stats must be fp32 [M, ceil(dim / 64), 2]")
+    m = row_stats.numel() // (2 * groups)
+    out = torch.empty(m, 2, dtype=torch.float32, device=dev)
+    with _launch(dev, "layernorm", 0.0, _nbytes(row_stats, out)):
+        _lib.check(_lib.lib().istvt_ln_stats_finalize(_ptr(row_stats), _ptr(out), m, dim, eps, _stream(dev)),
+                   "istvt_ln_stats_finalize")
+    return out
+
+
+def gemm_lnfold(a: torch.Tensor, w_folded: torch.Tensor, mu_rstd: torch.Tensor, w_rowsum: torch.Tensor,
+                shift: torch.Tensor) -> torch.Tensor:
+    """LayerNorm(a) . W^T without the LayerNorm pass — the consumer half of the fold (istvt_gemm_lnfold_fwd):
+    out = rstd (a . w_folded^T - mu w_rowsum) + shift with (mu, rstd) per row from ln_stats_finalize."""
+    dev = _chk(a, w_folded, mu_rstd, w_rowsum, shift)
+    k = a.shape[-1]
+    m = a.numel() // k
+    n = w_folded.shape[0]
+    if a.dtype != torch.bfloat16 or w_folded.dtype != torch.bfloat16 or w_folded.shape[1] != k:
+        raise ValueError("gemm_lnfold: bf16 a [M, K] and w_folded [N, K]")
+    if mu_rstd.numel() != 2 * m or w_rowsum.numel() != n or shift.numel() != n or \
+            any(t.dtype != torch.float32 for t in (mu_rstd, w_rowsum, shift)):
+        raise ValueError("gemm_lnfold: mu_rstd fp32 [M, 2], w_rowsum / shift fp32 [N]")
+    out = torch.empty(*a.shape[:-1], n, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "gemm_bf16", 2.0 * m * n * k, _nbytes(a, w_folded, out)):
+        _lib.check(_lib.lib().istvt_gemm_lnfold_fwd(_ptr(a), k, _ptr(w_folded), k, _ptr(out), n, m, n, k, _ptr(mu_rstd),
+                                                    _ptr(w_rowsum), _ptr(shift), _stream(dev)),
+                   "istvt_gemm_lnfold_fwd")
+    return out
+
+
 def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int = ACT_RELU) -> torch.Tensor:
     """x: NHWC [n, h, w, cin]; w: [cout, 3, 3, cin] (same dtype); -> NHWC [n, h-2, w-2, cout]."""
     dev = _chk(x, w, bias)

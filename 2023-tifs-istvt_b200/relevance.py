@@ -30,8 +30,9 @@ from .train import BF16, _pack_layers, transformer_backward, transformer_forward
 
 
 class _Rollout:
-    def __init__(self, b: int, f: int, p: int, dev):
+    def __init__(self, b: int, f: int, p: int, dev, start_layer: int = 0):
         self.b, self.f, self.p = b, f, p
+        self.start_layer = start_layer       # rollout over layers start_layer .. L-1 (upstream `start_layer` argument)
         self.cam_s = torch.empty(b * f, p, p, dtype=torch.float32, device=dev)
         self.cam_t = torch.empty(b * p, f, f, dtype=torch.float32, device=dev)
         self.v_s = torch.zeros(b * f, p, dtype=torch.float32, device=dev)
@@ -53,8 +54,11 @@ class _Rollout:
 
 
 @torch.no_grad()
-def relevance_maps(model, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """x: [B, T, 3, H, W] CUDA clips -> (cam_s [B, T, 361], cam_t [B, T, 361], logits [B, 1]); model in eval mode."""
+def relevance_maps(model, x: torch.Tensor, start_layer: int = 0, seed: torch.Tensor = None
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """x: [B, T, 3, H, W] CUDA clips -> (cam_s [B, T, 361], cam_t [B, T, 361], logits [B, 1]); model in eval mode.
+    `start_layer`: first transformer layer included in the rollout; `seed`: d(target)/d(logit) per clip (the upstream
+    one-hot vector; default 1 = the only logit, class index 0)."""
     if model.training:
         raise ValueError("relevance maps are computed in eval mode (visualize_rel.py:201)")
     if not x.is_cuda:
@@ -74,8 +78,14 @@ def relevance_maps(model, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, 
     del body, skip
     layers = _pack_layers(vit)
     logits, ctxs, x_final, head = transformer_forward_train(vit, layers, tokens)
-    roll = _Rollout(b, t + 1, p, x.device)
-    dlogits = torch.ones(b, dtype=torch.float32, device=x.device)          # d logit[b, index 0] / d logit[b]
+    depth = len(layers)
+    if not 0 <= start_layer < depth:
+        raise ValueError(f"start_layer must be in [0, {depth})")
+    roll = _Rollout(b, t + 1, p, x.device, start_layer)
+    if seed is None:
+        dlogits = torch.ones(b, dtype=torch.float32, device=x.device)      # d logit[b, index 0] / d logit[b]
+    else:
+        dlogits = seed.to(x.device).reshape(b).float().contiguous()
     transformer_backward(vit, layers, ctxs, x_final, head, dlogits, None, relevance=roll)
     cam_s = roll.v_s.view(b, t + 1, p)[:, 1:, 1:].contiguous()                       # [B, T, 361]
     cam_t = roll.v_t.view(b, p, t + 1)[:, 1:, 1:].transpose(1, 2).contiguous()       # [B, 361, T] -> [B, T, 361]
@@ -90,14 +100,43 @@ class LRP:
     def __init__(self, model):
         self.model = model
 
-    def generate_LRP(self, x: torch.Tensor, method: str = "transformer_attribution", index=None, **_):
-        if method not in ("transformer_attribution", "attn_grad_rollout"):
-            raise NotImplementedError(f"relevance method {method!r} is not built")
+    def generate_LRP(self, x: torch.Tensor, method: str = "transformer_attribution", is_ablation: bool = False,
+                     start_layer: int = 0, index=None, **_):
+        """The upstream generator's sequence (the public Transformer-Explainability `LRP.generate_LRP`, of which the
+        reference's absent `tfe` package is a fork): forward, one-hot vector for `index` (None = the predicted class;
+        ISTVT has ONE logit), then `model.relprop(one_hot, method=..., is_ablation=..., start_layer=..., alpha=1)`."""
         if index not in (None, 0):
             raise ValueError("ISTVT has one logit: index must be 0")
         if x.shape[0] != 1:
             raise ValueError("generate_LRP follows the reference call site (batch 1); use relevance_maps() for batches")
-        cam_s, cam_t, _ = relevance_maps(self.model, x)
-        seq_s: List[torch.Tensor] = [cam_s[0, i:i + 1] for i in range(cam_s.shape[1])]              # T x [1, 361]
-        seq_t: List[torch.Tensor] = [cam_t[0, :, j:j + 1].t() for j in range(cam_t.shape[2])]       # 361 x [1, T]
-        return seq_s, seq_t
+        one_hot = torch.ones(1, 1, dtype=torch.float32, device=x.device)
+        return self.model.relprop(one_hot, method=method, is_ablation=is_ablation, start_layer=start_layer, alpha=1,
+                                  clips=x)
+
+
+RELPROP_METHODS = ("transformer_attribution", "attn_grad_rollout")
+
+
+def relprop(model, cam: torch.Tensor = None, method: str = "transformer_attribution", is_ablation: bool = False,
+            start_layer: int = 0, alpha: float = 1, clips: torch.Tensor = None):
+    """`model.relprop(one_hot, method=..., is_ablation=..., start_layer=..., alpha=1)` of the upstream convention
+    (SURVEY.md section 8(b)): returns (cam_s, cam_t) as sequences such that `torch.cat(cam_s, 0)` is [T, 361] and
+    `torch.cat(cam_t, 0).transpose(0, 1)` is [T, 361] — exactly what visualize_rel.py:258-262 indexes.  `clips`: the
+    batch-1 input; without it the clip of the model's last eval-mode forward is used (`model.keep_relprop_input`)."""
+    if method not in RELPROP_METHODS:
+        raise NotImplementedError(f"relevance method {method!r} is not built (available: {RELPROP_METHODS})")
+    if is_ablation:
+        raise NotImplementedError("is_ablation is an option of the absent upstream package; not built")
+    if alpha != 1:
+        raise NotImplementedError("only alpha = 1 (the reference call sites' value) is built")
+    if clips is None:
+        clips = getattr(model, "_relprop_clips", None)
+        if clips is None:
+            raise ValueError("relprop needs the clip: pass clips=..., or set model.keep_relprop_input = True before the "
+                             "forward whose decision is to be explained")
+    if clips.shape[0] != 1:
+        raise ValueError("relprop follows the reference call site (batch 1); use relevance_maps() for batches")
+    cam_s, cam_t, _ = relevance_maps(model, clips, start_layer=start_layer, seed=cam)
+    seq_s: List[torch.Tensor] = [cam_s[0, i:i + 1] for i in range(cam_s.shape[1])]              # T x [1, 361]
+    seq_t: List[torch.Tensor] = [cam_t[0, :, j:j + 1].t() for j in range(cam_t.shape[2])]       # 361 x [1, T]
+    return seq_s, seq_t

@@ -85,6 +85,28 @@ int istvt_gemm_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void*
                    int64_t m, int n, int k, const float* bias, const float* residual, int64_t ldr, int act,
                    istvt_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm folded around a pair of GEMMs:  Z = LN(Y) W2^T  with  Y = A W1^T + b1  computed WITHOUT the LN pass.
+ * Replaces: PreNorm of the spatial attention, module.py:15-21 on vivit.py:93,99 — `norm(y1)` between the temporal
+ * attention's to_out (module.py:185-188,206) and the spatial to_qkv (module.py:74,83).  LN's input is the bf16 GEMM
+ * output, so folding is precision-neutral:
+ *   LN(y) W^T = rstd (y (gamma o W)^T - mu rowsum(gamma o W)) + W beta
+ * istvt_gemm_rowstats_fwd: C = A W^T + bias (bf16), and for every row m and 64-column group g of the output
+ *   row_stats[m, g] = {sum, sum of squared deviations from the group mean} (fp32 [m, ceil(n / 64), 2]; every slot is
+ *   written exactly once: no atomics, bitwise reproducible; taken from the fp32 values before the bf16 rounding).
+ * istvt_ln_stats_finalize: mu_rstd[m] = {mean, 1 / sqrt(var + eps)} over `dim` features from the ceil(dim / 64)
+ *   partials of row m, combined with Chan's parallel-variance formula (no E[x^2] - mu^2 cancellation).
+ * istvt_gemm_lnfold_fwd: C[m,n] = rstd_m (acc[m,n] - mu_m w_rowsum[n]) + shift[n];
+ *   w = bf16(gamma o W) [n, k], w_rowsum = its fp32 row sums, shift = W beta (fp32 [n]), mu_rstd fp32 [m, 2].
+ * GEMMs: n >= 256, bf16 output, the usual alignment rules of istvt_gemm_fwd.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_gemm_rowstats_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c, int64_t ldc, int64_t m,
+                            int n, int k, const float* bias, float* row_stats, istvt_stream_t stream);
+int istvt_ln_stats_finalize(const float* partials, float* mu_rstd, int64_t m, int dim, float eps, istvt_stream_t stream);
+int istvt_gemm_lnfold_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c, int64_t ldc, int64_t m,
+                          int n, int k, const float* mu_rstd, const float* w_rowsum, const float* shift,
+                          istvt_stream_t stream);
+
 /* Same contract in fp32 (SIMT FFMA kernel; the 1e-4 validation mode, not the performance path).
  * A, W, C, residual all fp32. */
 int istvt_gemm_f32_fwd(const float* a, int64_t lda, const float* w, int64_t ldw, float* c, int64_t ldc, int64_t m,

@@ -18,8 +18,9 @@ import torch
 from . import istvt_oracle as O
 
 
-def relevance_maps(sd, clips: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """clips [B, T, 3, H, W] -> (cam_s [B, T, 361], cam_t [B, T, 361], logits [B, 1]); eval mode, fp32."""
+def relevance_maps(sd, clips: torch.Tensor, start_layer: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """clips [B, T, 3, H, W] -> (cam_s [B, T, 361], cam_t [B, T, 361], logits [B, 1]); eval mode, fp32.
+    `start_layer`: first layer of the rollout (the upstream generator's argument of the same name)."""
     b, t = clips.shape[:2]
     depth = O.num_layers(sd)
     with torch.no_grad():
@@ -37,7 +38,7 @@ def relevance_maps(sd, clips: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor,
     p, f = O.TOKENS_PER_FRAME, t + 1
     r_s = torch.eye(p).expand(b, f, p, p).clone()
     r_t = torch.eye(f).expand(b, p, f, f).clone()
-    for l in range(depth):
+    for l in range(start_layer, depth):
         c_s = (g_s[l] * a_s[l]).clamp(min=0).mean(dim=1).detach()
         c_t = (g_t[l] * a_t[l]).clamp(min=0).mean(dim=1).detach()
         r_s = r_s + c_s @ r_s

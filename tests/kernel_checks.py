@@ -7,6 +7,7 @@ Tolerances (norm-wise: max|a-b| / max|ref|): 1e-5 for fp32 SIMT kernels (5e-5 wh
 """
 from __future__ import annotations
 
+import importlib
 import math
 
 import torch
@@ -156,6 +157,40 @@ def check_gemm_shapes():
     # ff1): exercises the TMEM double-buffer hand-off on every path (a missed tmem_empty arrival deadlocks here)
     out["ragged_n_many_tiles"] = _check_gemm_case(256 * 40 + 3, 2912, 128, True, False, 2, torch.bfloat16, 11)
     out["ragged_n_many_tiles_f32"] = _check_gemm_case(256 * 120 + 3, 1120, 64, True, True, 0, torch.float32, 12)
+    return out
+
+
+def check_gemm_lnfold():
+    """LayerNorm folded around a GEMM pair (istvt_gemm_rowstats_fwd + istvt_gemm_lnfold_fwd, engine.fold_layernorm)
+    vs the unfused definition Linear(LayerNorm(y)) evaluated in fp64 on the same bf16-rounded y; ragged M, the path's
+    shapes (to_out 512 -> 728, to_qkv 728 -> 1536), a row-mean several sigma away from zero, near-constant rows."""
+    ops = _ops()
+    eng = importlib.import_module("2023-tifs-istvt_b200.engine")
+    out = {}
+    for m, shift in ((1000, 0.0), (257, 3.0), (4099, -1.5)):
+        a = _rand(m, 512, seed=m).to(torch.bfloat16)
+        w1 = (_rand(728, 512, seed=m + 1) * 512 ** -0.5).to(torch.bfloat16)
+        b1 = _rand(728, seed=m + 2) * 0.5 + shift
+        gamma, beta = _rand(728, seed=m + 3).abs() + 0.3, _rand(728, seed=m + 4) * 0.4
+        w2 = _rand(1536, 728, seed=m + 5) * 728 ** -0.5
+        a[-3:] *= 1e-3                      # rows whose variance is tiny next to their mean (= the bias)
+        stats = torch.full((m, 12, 2), float("nan"), device="cuda")
+        y = ops.gemm_rowstats(a, w1, b1, stats)
+        yref = _gemm_ref(a, w1, b1, None, 0)
+        out[f"y_{m}"] = _assert_close("lnfold y", y, yref, TOL_BF16)
+        yd = yref.double()                 # the statistics are taken before the bf16 rounding
+        blocks = [yd[:, 64 * g: 64 * g + 64] for g in range(12)]
+        want_stats = torch.stack([torch.stack((b.sum(1), ((b - b.mean(1, keepdim=True)) ** 2).sum(1)), 1) for b in blocks], 1)
+        out[f"stats_{m}"] = _assert_close("lnfold stats", stats, want_stats.float(), 2e-5)
+        mr = ops.ln_stats_finalize(stats, 728)
+        want_mr = torch.stack((yd.mean(1), torch.rsqrt(yd.var(1, unbiased=False) + 1e-5)), 1)
+        out[f"mu_rstd_{m}"] = _assert_close("lnfold mu/rstd", mr, want_mr.float(), 2e-5)
+        y2 = ops.gemm_rowstats(a, w1, b1, torch.empty_like(stats))
+        assert torch.equal(y, y2), "the statistics output must not change the GEMM result"
+        wf, c, d = eng.fold_layernorm(w2, gamma, beta, torch.bfloat16)
+        z = ops.gemm_lnfold(y, wf, mr, c, d)
+        zref = torch.nn.functional.layer_norm(y.double(), (728,), gamma.double(), beta.double(), 1e-5) @ w2.double().t()
+        out[f"z_{m}"] = _assert_close("lnfold z", z, zref.float(), TOL_BF16)
     return out
 
 
@@ -785,6 +820,7 @@ CHECKS = {
     "layernorm_diff": check_layernorm_diff,
     "gemm_basic": check_gemm_basic,
     "gemm_shapes": check_gemm_shapes,
+    "gemm_lnfold": check_gemm_lnfold,
     "gemm_f32": check_gemm_f32,
     "conv3x3": check_conv3x3,
     "conv_stem": check_conv_stem,

@@ -42,6 +42,23 @@ def _worker(rank: int, world: int, port: int, out):
         p_scaled = state.params.clone()
         O.adamw_update(p_scaled, state.grads * (1.0 / world), torch.zeros(n), torch.zeros(n), 1, 1e-3, weight_decay=0.01)
         assert torch.allclose(p_ref, p_scaled, rtol=0, atol=1e-5)
+        # Trainer.step's two gradient buckets (transformer slots reduced asynchronously while the entry-flow backward
+        # runs, entry-flow slots at the end) == one all-reduce of the whole flat buffer
+        x = torch.nn.Module()
+        for nm in ("conv1", "bn1", "conv2", "bn2", "block1", "block2", "block3"):
+            setattr(x, nm, torch.nn.Linear(3, 5))
+        model.xcep = torch.nn.Module()
+        model.xcep.model = x
+        st2 = train.FlatState(model, train_entry_flow=True)
+        assert st2.vit_offset == 7 * (16 + 8) and st2.names[0].startswith("xcep.") and st2.names[-1].startswith("vit.")
+        n2 = st2.grads.numel()
+        st2.grads.copy_(torch.arange(n2, dtype=torch.float32) * 1e-6 - rank)
+        whole = st2.grads.clone()
+        dist.all_reduce(whole)
+        work = dist.all_reduce(st2.grads[st2.vit_offset:], async_op=True)
+        dist.all_reduce(st2.grads[:st2.vit_offset])
+        work.wait()
+        assert torch.equal(st2.grads, whole)
         # layouts agree across ranks
         gathered = [None] * world
         dist.all_gather_object(gathered, (names, n))

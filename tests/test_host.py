@@ -256,3 +256,20 @@ def test_vanilla_tr_checks_patch_linear_channels():
         v(torch.zeros(1, 6, 128, 19, 19))
     with pytest.raises(ValueError, match="CUDA"):
         v(torch.zeros(1, 6, 64, 19, 19))
+
+
+def test_layernorm_fold_algebra():
+    """engine.fold_layernorm + the definitions of the two fold GEMMs reproduce Linear(LayerNorm(y)) (module.py:21, :83)."""
+    import torch_ops as tops
+    eng = __import__("importlib").import_module("2023-tifs-istvt_b200.engine")
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(37, 512, generator=g)
+    w1, b1 = torch.randn(728, 512, generator=g) * 0.05, torch.randn(728, generator=g)
+    gamma, beta = torch.rand(728, generator=g) + 0.5, torch.randn(728, generator=g)
+    w2 = torch.randn(1536, 728, generator=g) * 0.04
+    stats = torch.zeros(37, 12, 2)
+    y = tops.gemm_rowstats(a, w1, b1, stats)
+    wf, c, d = eng.fold_layernorm(w2, gamma, beta, torch.float32)
+    got = tops.gemm_lnfold(y, wf, tops.ln_stats_finalize(stats, 728), c, d)
+    want = F.linear(F.layer_norm(F.linear(a, w1, b1), (728,), gamma, beta), w2)
+    assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()

@@ -150,6 +150,32 @@ def token_fill(tokens, space_token, temporal_token, pos_emb):
     tokens[:, 1:, 0] = space_token.reshape(1, 1, d) + pos[None, :, 0]
 
 
+def gemm_rowstats(a, w, bias, row_stats):
+    y = gemm(a, w, bias=bias)
+    yr = y.float().reshape(-1, y.shape[-1])
+    n = yr.shape[1]
+    for g in range((n + 63) // 64):
+        blk = yr[:, 64 * g: 64 * g + 64]
+        row_stats.view(yr.shape[0], -1, 2)[:, g, 0] = blk.sum(1)
+        row_stats.view(yr.shape[0], -1, 2)[:, g, 1] = ((blk - blk.mean(1, keepdim=True)) ** 2).sum(1)
+    return y
+
+
+def ln_stats_finalize(row_stats, dim, eps=1e-5):
+    st = row_stats.reshape(-1, (dim + 63) // 64, 2)
+    ng = torch.tensor([min(64, dim - 64 * g) for g in range(st.shape[1])], dtype=torch.float32)
+    mu = st[:, :, 0].sum(1) / dim
+    m2 = (st[:, :, 1] + ng * (st[:, :, 0] / ng - mu[:, None]) ** 2).sum(1)      # Chan's parallel-variance combination
+    return torch.stack((mu, torch.rsqrt(m2 / dim + eps)), 1)
+
+
+def gemm_lnfold(a, w_folded, mu_rstd, w_rowsum, shift):
+    k = a.shape[-1]
+    mu, rstd = mu_rstd.reshape(-1, 2).unbind(1)
+    acc = a.float().reshape(-1, k) @ w_folded.float().t()
+    return (rstd[:, None] * (acc - mu[:, None] * w_rowsum[None, :]) + shift[None, :]).to(a.dtype).reshape(*a.shape[:-1], -1)
+
+
 # ---- training step: forward variants that keep what the backward needs, and the backward of every op ----
 def conv_stem_raw(x, w):
     return _nhwc(F.conv2d(x, w, None, stride=2), x.dtype)
@@ -370,7 +396,7 @@ ALL = dict(gemm=gemm, layernorm=layernorm, layernorm_diff=layernorm_diff, attn_j
            attn_temporal=attn_temporal, token_build=token_build, gather_rows=gather_rows, head=head, pool_linear=pool_linear,
            mean_rows=mean_rows, conv_stem=conv_stem, conv_stem_u8=conv_stem_u8, conv3x3=conv3x3, dwconv3x3=dwconv3x3,
            subsample2=subsample2, pool_add=pool_add, pool_add_tokens=pool_add_tokens, token_fill=token_fill,
-           conv_stem_raw=conv_stem_raw, batchnorm_train=batchnorm_train, batchnorm_bwd=batchnorm_bwd, pool_add_idx=pool_add_idx,
+           gemm_rowstats=gemm_rowstats, ln_stats_finalize=ln_stats_finalize, gemm_lnfold=gemm_lnfold, conv_stem_raw=conv_stem_raw, batchnorm_train=batchnorm_train, batchnorm_bwd=batchnorm_bwd, pool_add_idx=pool_add_idx,
            pool_bwd=pool_bwd, token_grad_gather=token_grad_gather, token_bwd=token_bwd, dwconv3x3_wgrad=dwconv3x3_wgrad,
            block_input_grad=block_input_grad, transpose=transpose, im2col_t=im2col_t, im2col_t_stem=im2col_t_stem,
            gemm_wgrad=gemm_wgrad, colsum=colsum, wgrad=wgrad, gelu=gelu, gelu_bwd=gelu_bwd, cast_bf16=cast_bf16,
