@@ -33,6 +33,7 @@ SOURCES = [
     "entry_flow_bwd.cu",
     "entry_flow.cu",
     "conv_stem_tc.cu",
+    "conv3x3_tc.cu",
     "xception_tail.cu",
 ]
 NVCC_FLAGS = [

@@ -309,9 +309,22 @@ int gemm_bf16_dispatch(const void* a, int64_t a_rows, int64_t lda, const void* w
     }
 }
 
+// conv3x3_tc.cu: conv2's shape (32 -> 64 channels) with the A operand gathered by the SIMT threads
+int conv3x3_c32_tc_launch(const void* x, const void* wt, const float* bias, void* y, int n, int h, int w, int act,
+                          cudaStream_t st);
+
 // bf16 dense 3x3 stride-1 pad-0 convolution (conv2 of the stem) on the implicit-GEMM path.
 int conv3x3_bf16(const void* x, const void* wt, const float* bias, void* y, int n, int h, int w, int cin, int cout,
                  int act, cudaStream_t stream) {
+    // ISTVT_CONV2_TC=1: conv2's shape on the gathered-operand kernel.  Measured SLOWER than the 9-tap TMA formulation
+    // (1.23 vs 0.91 ms stand-alone, 1.52 vs 1.13 ms inside the C2 step, profiles/README.md r6l), so it is off by default
+    // and kept as the A/B alternative.
+    // (read per call — one getenv per conv2 launch — so that a check can exercise both kernels in one process)
+    const char* gather_e = getenv("ISTVT_CONV2_TC");
+    const bool gather_env = gather_e != nullptr && atoi(gather_e) != 0;
+    if (gather_env && cin == 32 && cout == 64 && (act == ISTVT_ACT_NONE || act == ISTVT_ACT_RELU) && h >= 3 && w >= 3 &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wt) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+        return conv3x3_c32_tc_launch(x, wt, bias, y, n, h, w, act, stream);
     GemmParams p{};
     p.M = static_cast<int64_t>(n) * h * w;  // outputs on the input's grid; junk rows/cols dropped in the epilogue
     p.N = cout; p.K = cin;

@@ -419,7 +419,7 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
         if (rc != ISTVT_OK) return rc;
     }
     const int ew = reduce ? 16 : (ew_env == 8 || ew_env == 16 ? ew_env : (plain ? 16 : 8));
-    p.epi_tma = plain && ew == 16 && tma_env && !p.mn_major && p.split_k <= 1 && (p.ldc * 2) % 16 == 0;
+    p.epi_tma = plain && tma_env && !p.mn_major && p.split_k <= 1 && (p.ldc * 2) % 16 == 0;
     if ((p.row_stats_out != nullptr || p.ln_stats != nullptr) && !p.epi_tma) return ISTVT_ERR_UNSUPPORTED;
     if (p.epi_tma) {
         const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};

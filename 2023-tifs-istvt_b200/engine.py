@@ -107,7 +107,7 @@ class _Pack:
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
-    return t.detach().float().contiguous()
+    return ops.f32_aligned(t)
 
 
 def _pack_sep(sep, bn, dt: torch.dtype) -> _SepPack:

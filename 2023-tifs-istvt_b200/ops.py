@@ -45,6 +45,14 @@ def _chk(*tensors: Optional[torch.Tensor]) -> torch.device:
     return dev
 
 
+def f32_aligned(t: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous, 16-byte aligned view or copy of a parameter.  Parameters of an `nn.DataParallel` replica are
+    views into one coalesced broadcast buffer (torch's `broadcast_coalesced` packs them back to back), so their start
+    is only element-aligned; the kernels read vectors of 16 bytes."""
+    t = t.detach().float().contiguous()
+    return t.clone() if t.data_ptr() % 16 else t
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 

@@ -67,7 +67,7 @@ def relevance_maps(model, x: torch.Tensor, start_layer: int = 0, seed: torch.Ten
     b, t = x.shape[:2]
     if t != vit.num_frames or t + 1 > 48:
         raise ValueError("relevance pass: clip length must equal num_frames (<= 47)")
-    f32 = lambda z: z.detach().float().contiguous()
+    f32 = ops.f32_aligned
     frames = x.reshape(b * t, *x.shape[2:]).float().contiguous()
     body, skip = run_entry_flow(pack_entry(model.xcep.model, BF16), frames, BF16)
     pos = f32(vit.pos_embedding[0])

@@ -123,14 +123,14 @@ def bf16_weight(w: torch.Tensor, mirror: Optional[Dict[str, torch.Tensor]], name
     """bf16 copy of an fp32 weight: the view of the flat mirror when there is one, else one cast kernel."""
     if mirror is not None and name in mirror:
         return mirror[name]
-    return ops.cast_bf16(w.detach().float().contiguous())
+    return ops.cast_bf16(ops.f32_aligned(w))
 
 
 def _pack_layers(vit, mirror: Optional[Dict[str, torch.Tensor]] = None) -> List[SimpleNamespace]:
     """Per-layer bf16 weights [N, K] and their transposes [K, N] (B operand of the data-gradient GEMMs); `mirror` =
     FlatState.bf16_weights().  The transposes are produced by istvt_transpose_colsum — no ATen kernel on the path."""
     layers = []
-    f32 = lambda t: t.detach().float().contiguous()
+    f32 = ops.f32_aligned
     for li, (attn_t, attn_s, ff) in enumerate(vit.transformer.layers):
         L = SimpleNamespace()
         pre = f"vit.transformer.layers.{li}"
@@ -174,7 +174,7 @@ def transformer_forward_train(vit, layers: List[SimpleNamespace], tokens: torch.
     rows = b * f * p
     heads = vit.heads
     scale = 64 ** -0.5
-    f32 = lambda t: t.detach().float().contiguous()
+    f32 = ops.f32_aligned
     ctxs = []
     x = tokens
     for L in layers:
@@ -350,7 +350,7 @@ class Trainer:
         if t != vit.num_frames:
             raise ValueError(f"clip has {t} frames but the model was built with num_frames={vit.num_frames}")
         frames = x.reshape(b * t, *x.shape[2:]).float().contiguous()
-        f32 = lambda z: z.detach().float().contiguous()
+        f32 = ops.f32_aligned
         pos = f32(vit.pos_embedding[0])
         tokens = torch.empty(b, t + 1, vit.num_patches + 1, vit.dim, dtype=torch.float32, device=x.device)
         mirror = self.state.bf16_weights()

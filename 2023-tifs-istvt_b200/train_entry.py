@@ -71,7 +71,7 @@ class EntryFlowTrainer:
         x = self.x
         dev = frames.device
         c = SimpleNamespace(frames=frames)
-        c.c1 = ops.conv_stem_raw(frames, x.conv1.weight.detach().float().contiguous())
+        c.c1 = ops.conv_stem_raw(frames, ops.f32_aligned(x.conv1.weight))
         c.a1, c.bn1 = ops.batchnorm_train(c.c1, x.bn1, relu=True)
         w2 = x.conv2.weight.detach().permute(0, 2, 3, 1).to(BF16).contiguous()                 # [64, 3, 3, 32]
         c.c2 = ops.conv3x3(c.a1, w2, torch.zeros(w2.shape[0], device=dev), act=ops.ACT_NONE)
