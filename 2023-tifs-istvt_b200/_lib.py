@@ -23,6 +23,8 @@ SIGNATURES = {
     "istvt_launch_count": [],
     "istvt_layernorm_fwd": [_P, _I, _P, _P, _P, _I, _L, _I, _F, _P],
     "istvt_layernorm_diff_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "istvt_layernorm_fwd_ld": [_P, _I, _L, _P, _P, _P, _I, _L, _L, _I, _F, _P],
+    "istvt_layernorm_diff_fwd_ld": [_P, _L, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _F, _P],
     "istvt_gemm_fwd": [_P, _L, _P, _L, _P, _L, _I, _L, _I, _I, _P, _P, _L, _I, _P],
     "istvt_gemm_f32_fwd": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _P, _L, _I, _P],
     "istvt_conv3x3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

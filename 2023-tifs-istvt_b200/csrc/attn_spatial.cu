@@ -289,7 +289,7 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
     float* s_max = reinterpret_cast<float*>(smem + SP_MISC_OFF + 256);   // [SP_PARTS][128]
     float* s_sum = s_max + SP_PARTS * 128;                                // [SP_PARTS][128]
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;   // (roles in the four highest warp ids instead: neutral, 0.286 ms both ways, r6o)
     const int lane = threadIdx.x & 31;
     const int inner = heads * SA_DH;
     const int q_tiles = (tokens + SA_BM - 1) / SA_BM;

@@ -218,15 +218,18 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
 // registers with 32-byte vectors, one output row per lane, measured SLOWER: ff1 0.74 -> 0.79-0.89 ms, to_v 0.132 ->
 // 0.154 ms, profiles/README.md r6d — 32 scattered sectors per store instruction cost more than the staging.)
 // `row0` = first of the warp's 32 consecutive output rows.
-template <typename F>
+// BOXC = 64: both 32-column halves are staged in one 4 KB slab (128-byte rows, SWIZZLE_128B) and leave as ONE box —
+// half as many box rows for the TMA unit, which serves the operand fills of the same CTA (profiles/README.md r6m: the
+// TMA stores, not the TMEM reads, the math or the staging, are what the epilogue costs the main loop).
+template <int BOXC = 32, typename F>
 __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, const CUtensorMap* tm_c, uint32_t taddr,
                                                           uint32_t slab, int row0, int n0, int lane, F after_tmem_reads) {
     if (n0 >= p.N) {
         after_tmem_reads();
         return;
     }
-    const uint32_t wrow = slab + lane * 64;
-    const int wsw = (lane >> 1) & 3;
+    const uint32_t wrow = slab + lane * (2 * BOXC);
+    const int wsw = BOXC == 64 ? (lane & 7) : ((lane >> 1) & 3);
     const bool row_ok = row0 + lane < p.M;
     // LayerNorm fold, consumer side: this lane's row statistics (mu, rstd), finalized by istvt_ln_stats_finalize
     float ln_a = 1.f, ln_b = 0.f;             // C = ln_a * acc + ln_b * c[n] + d[n],  ln_b = -rstd * mu
@@ -244,6 +247,15 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
             break;
         }
         uint32_t r[32];
+#ifdef ISTVT_GEMM_TRACE
+        // timing experiments (results are garbage): trace_no_epi = 2 TMEM reads only; 3 reads + math + staging, no TMA
+        // store; 4 staging + TMA store without the TMEM reads; 5 reads + math, nothing staged or stored
+        const int tmode = p.trace_no_epi;
+        if (tmode == 4) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = static_cast<uint32_t>(lane + j);
+        } else
+#endif
         tmem_ld_32x32b_x32(taddr + hh * 32, r);
         // the bias of these 32 columns is fetched while the TMEM load is in flight (the same 128 B for every lane)
         const float* bsrc = p.ln_stats != nullptr ? p.ln_d : p.bias;
@@ -254,6 +266,15 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
         tmem_ld_wait();
         if (hh == 1) after_tmem_reads();
+#ifdef ISTVT_GEMM_TRACE
+        if (tmode == 2) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x ^= r[j];
+            if (x == 0x7fc12345u) sts_u4(wrow, x, x, x, x);     // keeps the loads alive
+            continue;
+        }
+#endif
         uint32_t o[16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {     // 8 columns -> one 16-byte chunk
@@ -292,14 +313,30 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
                 st_n += 8.f;
             }
         }
-        if (lane == 0) tma_store_wait_read0();     // the previous box has left the slab
-        __syncwarp();
+#ifdef ISTVT_GEMM_TRACE
+        if (tmode == 5) {
+            uint32_t x = 0;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) sts_u4(wrow + ((g ^ wsw) << 4), o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+            for (int j = 0; j < 16; ++j) x ^= o[j];
+            if (x == 0x7fc12345u) sts_u4(wrow, x, x, x, x);
+            continue;
+        }
+#endif
+        if (BOXC == 32 || hh == 0) {
+            if (lane == 0) tma_store_wait_read0();     // the previous box has left the slab
+            __syncwarp();
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            sts_u4(wrow + (((BOXC == 64 ? hh * 4 + g : g) ^ wsw) << 4), o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+        if (BOXC == 64 && hh == 0 && nb + 32 < p.N) continue;      // the box leaves after the second half
         fence_proxy_async_smem();
         __syncwarp();
+#ifdef ISTVT_GEMM_TRACE
+        if (tmode == 3) continue;
+#endif
         if (lane == 0) {
-            tma_store_2d(tm_c, slab, nb, row0);
+            tma_store_2d(tm_c, slab, BOXC == 64 ? n0 : nb, row0);
             tma_store_commit();
         }
     }

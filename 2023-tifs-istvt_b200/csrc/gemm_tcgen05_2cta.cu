@@ -43,10 +43,11 @@ constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;    // 16 KB
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 // epilogue modes: bf16 output without residual / generic (fp32 output, residual through registers, split-K) /
 // in-place fp32 residual update by TMA reduce-add
-constexpr int EPI_PLAIN = 0, EPI_GENERIC = 1, EPI_REDUCE = 2;
+// in-place fp32 residual update by TMA reduce-add / bf16 output whose TMA-store boxes are 64 columns (128 bytes) wide
+constexpr int EPI_PLAIN = 0, EPI_GENERIC = 1, EPI_REDUCE = 2, EPI_PLAIN128 = 3;
 template <int EW, int EPI> struct G2Cfg {
     static constexpr int THREADS = 128 + EW * 32;
-    static constexpr int SLAB = EPI == EPI_PLAIN ? EPI_SLAB_PLAIN_BYTES : EPI_SLAB_BYTES;
+    static constexpr int SLAB = EPI == EPI_PLAIN ? EPI_SLAB_PLAIN_BYTES : EPI_SLAB_BYTES;   // PLAIN128: 32 rows x 128 B
     // 6 ring stages whenever they fit: 16 warps with the 2 KB bf16 slabs, or 8 warps with the 4 KB fp32 slabs
     static constexpr int STAGES = (EW == 16 && EPI != EPI_PLAIN) ? 5 : 6;
     static constexpr int PASSES = (G2_BN / EPI_COLS) / (EW / 4);   // 64-column passes per epilogue warp per tile
@@ -90,7 +91,7 @@ template <int EW, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Cfg<EW, EPI>::THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const __grid_constant__ CUtensorMap tm_c, const GemmParams p) {
-    constexpr bool PLAIN_BF16 = EPI == EPI_PLAIN;
+    constexpr bool PLAIN_BF16 = EPI == EPI_PLAIN || EPI == EPI_PLAIN128;
     using Cfg = G2Cfg<EW, EPI>;
     constexpr int G2_STAGES = Cfg::STAGES;
     constexpr int G2_EPI_WARPS = EW;
@@ -106,8 +107,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     uint64_t* tmem_empty = bars + 2 * G2_STAGES + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
 
-    const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // (Placing the single-thread roles in the four HIGHEST warp ids — the issue arbiter is said to prefer the highest
+    //  eligible warp id — measured neutral: layer GEMM sum 2.322-2.326 vs 2.315-2.319 ms, profiles/README.md r6o.)
+    const int warp = threadIdx.x >> 5;
     const uint32_t rank = cluster_ctarank();          // 0 = leader
     const uint32_t cluster = cluster_id_x();
     const uint32_t n_clusters = num_clusters_x();
@@ -287,7 +290,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             ISTVT_TRACE(tracer, trace_it, 5);
             uint64_t* te = &tmem_empty[acc];
 #ifdef ISTVT_GEMM_TRACE
-            if (p.trace_no_epi) {     // timing experiment: no TMEM reads, no math, no stores
+            if (p.trace_no_epi == 1) {     // timing experiment: no TMEM reads, no math, no stores
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(te, 0);
@@ -312,9 +315,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                                             static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32),
                                             n_blk * G2_BN + col0, lane, release);
                 else if (PLAIN_BF16 && p.epi_tma)
-                    gemm_epilogue_tma_bf16_64(p, &tm_c, taddr, slab,
-                                              static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32),
-                                              n_blk * G2_BN + col0, lane, release);
+                    gemm_epilogue_tma_bf16_64<EPI == EPI_PLAIN128 ? 64 : 32>(
+                        p, &tm_c, taddr, slab, static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32),
+                        n_blk * G2_BN + col0, lane, release);
                 else
                     gemm_epilogue_64<PLAIN_BF16>(p, taddr, slab, drow_lane, drow_t, n_blk * G2_BN + col0, lane, release);
             }
@@ -323,7 +326,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         }
     }
 
-    if (EPI == EPI_REDUCE || (EPI == EPI_PLAIN && p.epi_tma)) {
+    if (EPI == EPI_REDUCE || (PLAIN_BF16 && p.epi_tma)) {
         if (warp >= 4 && lane == 0) tma_store_wait0();     // TMA stores / reduce-adds issued by this lane have completed
     }
     // No CTA may exit (or free TMEM) while its peer can still multicast-arrive on its barriers or read its smem.
@@ -421,11 +424,16 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
     const int ew = reduce ? 16 : (ew_env == 8 || ew_env == 16 ? ew_env : (plain ? 16 : 8));
     p.epi_tma = plain && tma_env && !p.mn_major && p.split_k <= 1 && (p.ldc * 2) % 16 == 0;
     if ((p.row_stats_out != nullptr || p.ln_stats != nullptr) && !p.epi_tma) return ISTVT_ERR_UNSUPPORTED;
+    // ISTVT_G2_STORE128=0: 32-column store boxes (2 KB slabs, six ring stages) instead of 64-column ones (4 KB slabs,
+    // five stages) — A/B measurements
+    static const bool store128_env = []() { const char* e = getenv("ISTVT_G2_STORE128"); return !e || atoi(e) != 0; }();
+    const bool store128 = p.epi_tma && store128_env;
     if (p.epi_tma) {
         const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
         const uint64_t strides[1] = {static_cast<uint64_t>(p.ldc) * 2};
-        const uint32_t box[2] = {32, 32};      // 32 bf16 columns (64 B, SW64) x the warp's 32 rows
-        int rc = encode_tmap(&tm_c, p.C, ISTVT_BF16, 2, dims, strides, box, 2);
+        // the warp's 32 rows x 32 bf16 columns (64 B, SW64) or x 64 columns (128 B, SW128)
+        const uint32_t box[2] = {store128 ? 64u : 32u, 32};
+        int rc = encode_tmap(&tm_c, p.C, ISTVT_BF16, 2, dims, strides, box, store128 ? 3 : 2);
         if (rc != ISTVT_OK) return rc;
     }
     const unsigned grid = static_cast<unsigned>(2 * clusters);
@@ -439,9 +447,13 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
     if (reduce) {
         ISTVT_G2_LAUNCH(16, EPI_REDUCE);
     } else if (ew == 16) {
-        if (plain) ISTVT_G2_LAUNCH(16, EPI_PLAIN); else ISTVT_G2_LAUNCH(16, EPI_GENERIC);
+        if (store128) ISTVT_G2_LAUNCH(16, EPI_PLAIN128);
+        else if (plain) ISTVT_G2_LAUNCH(16, EPI_PLAIN);
+        else ISTVT_G2_LAUNCH(16, EPI_GENERIC);
     } else {
-        if (plain) ISTVT_G2_LAUNCH(8, EPI_PLAIN); else ISTVT_G2_LAUNCH(8, EPI_GENERIC);
+        if (store128) ISTVT_G2_LAUNCH(8, EPI_PLAIN128);
+        else if (plain) ISTVT_G2_LAUNCH(8, EPI_PLAIN);
+        else ISTVT_G2_LAUNCH(8, EPI_GENERIC);
     }
 #undef ISTVT_G2_LAUNCH
     count_launch();

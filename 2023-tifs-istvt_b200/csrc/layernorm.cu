@@ -69,14 +69,14 @@ __device__ __forceinline__ void ln_store_row(TO* row, int dim, int lane, const f
 template <int ITERS, typename TI, typename TO>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, TO* __restrict__ y,
-                                                        int64_t rows, int dim, float eps) {
+                                                        int64_t rows, int dim, int64_t ldx, int64_t ldy, float eps) {
     const int lane = threadIdx.x & 31;
     const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     float v[ITERS][4];
-    ln_load_row<ITERS>(x + row * dim, dim, lane, v);
+    ln_load_row<ITERS>(x + row * ldx, dim, lane, v);
     ln_normalize<ITERS>(v, dim, lane, gamma, beta, eps);
-    ln_store_row<ITERS>(y + row * dim, dim, lane, v);
+    ln_store_row<ITERS>(y + row * ldy, dim, lane, v);
 }
 
 // One warp per (clip, position): walks the frames, keeps the previous frame's normalised row in
@@ -85,25 +85,25 @@ template <int ITERS, typename TO>
 __global__ void __launch_bounds__(256)
 layernorm_diff_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                       TO* __restrict__ xn, TO* __restrict__ diff, int batch, int frames, int tokens, int dim,
-                      float eps) {
+                      int64_t ldx, int64_t ldo, float eps) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= static_cast<int64_t>(batch) * tokens) return;
     const int b = static_cast<int>(wid / tokens);
     const int pos = static_cast<int>(wid - static_cast<int64_t>(b) * tokens);
-    const int64_t frame_stride = static_cast<int64_t>(tokens) * dim;
-    const int64_t base = (static_cast<int64_t>(b) * frames * tokens + pos) * dim;
+    const int64_t row0 = static_cast<int64_t>(b) * frames * tokens + pos;      // token row of frame 0; + f * tokens
 
     float prev[ITERS][4], cur[ITERS][4], nxt[ITERS][4];
-    ln_load_row<ITERS>(x + base, dim, lane, nxt);
+    ln_load_row<ITERS>(x + row0 * ldx, dim, lane, nxt);
     for (int f = 0; f < frames; ++f) {
 #pragma unroll
         for (int j = 0; j < ITERS; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) cur[j][e] = nxt[j][e];
-        if (f + 1 < frames) ln_load_row<ITERS>(x + base + (f + 1) * frame_stride, dim, lane, nxt);  // prefetch
+        if (f + 1 < frames)
+            ln_load_row<ITERS>(x + (row0 + static_cast<int64_t>(f + 1) * tokens) * ldx, dim, lane, nxt);  // prefetch
         ln_normalize<ITERS>(cur, dim, lane, gamma, beta, eps);
-        const int64_t off = base + f * frame_stride;
+        const int64_t off = (row0 + static_cast<int64_t>(f) * tokens) * ldo;
         ln_store_row<ITERS>(xn + off, dim, lane, cur);
         if (f < 2) {
             ln_store_row<ITERS>(diff + off, dim, lane, cur);
@@ -178,38 +178,39 @@ head_kernel(const float* __restrict__ tokens, int64_t rows_per_clip, const float
 
 template <int ITERS>
 static int launch_ln(const void* x, int x_dtype, const float* g, const float* b, void* y, int y_dtype, int64_t rows,
-                     int dim, float eps, cudaStream_t st) {
+                     int dim, int64_t ldx, int64_t ldy, float eps, cudaStream_t st) {
     const int warps = 8;
     const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
     if (x_dtype == ISTVT_F32 && y_dtype == ISTVT_BF16)
         layernorm_kernel<ITERS, float, __nv_bfloat16><<<grid, warps * 32, 0, st>>>(
-            static_cast<const float*>(x), g, b, static_cast<__nv_bfloat16*>(y), rows, dim, eps);
+            static_cast<const float*>(x), g, b, static_cast<__nv_bfloat16*>(y), rows, dim, ldx, ldy, eps);
     else if (x_dtype == ISTVT_F32 && y_dtype == ISTVT_F32)
         layernorm_kernel<ITERS, float, float><<<grid, warps * 32, 0, st>>>(static_cast<const float*>(x), g, b,
-                                                                          static_cast<float*>(y), rows, dim, eps);
+                                                                          static_cast<float*>(y), rows, dim, ldx, ldy, eps);
     else if (x_dtype == ISTVT_BF16 && y_dtype == ISTVT_BF16)
         layernorm_kernel<ITERS, __nv_bfloat16, __nv_bfloat16><<<grid, warps * 32, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(x), g, b, static_cast<__nv_bfloat16*>(y), rows, dim, eps);
+            static_cast<const __nv_bfloat16*>(x), g, b, static_cast<__nv_bfloat16*>(y), rows, dim, ldx, ldy, eps);
     else
         layernorm_kernel<ITERS, __nv_bfloat16, float><<<grid, warps * 32, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(x), g, b, static_cast<float*>(y), rows, dim, eps);
+            static_cast<const __nv_bfloat16*>(x), g, b, static_cast<float*>(y), rows, dim, ldx, ldy, eps);
     count_launch();
     return launch_status();
 }
 
 template <int ITERS>
 static int launch_ln_diff(const float* x, const float* g, const float* b, void* xn, void* diff, int out_dtype,
-                          int batch, int frames, int tokens, int dim, float eps, cudaStream_t st) {
+                          int batch, int frames, int tokens, int dim, int64_t ldx, int64_t ldo, float eps,
+                          cudaStream_t st) {
     const int warps = 8;
     const int64_t work = static_cast<int64_t>(batch) * tokens;
     const unsigned grid = static_cast<unsigned>((work + warps - 1) / warps);
     if (out_dtype == ISTVT_BF16)
         layernorm_diff_kernel<ITERS, __nv_bfloat16><<<grid, warps * 32, 0, st>>>(
             x, g, b, static_cast<__nv_bfloat16*>(xn), static_cast<__nv_bfloat16*>(diff), batch, frames, tokens, dim,
-            eps);
+            ldx, ldo, eps);
     else
         layernorm_diff_kernel<ITERS, float><<<grid, warps * 32, 0, st>>>(
-            x, g, b, static_cast<float*>(xn), static_cast<float*>(diff), batch, frames, tokens, dim, eps);
+            x, g, b, static_cast<float*>(xn), static_cast<float*>(diff), batch, frames, tokens, dim, ldx, ldo, eps);
     count_launch();
     return launch_status();
 }
@@ -230,14 +231,35 @@ static int launch_ln_diff(const float* x, const float* g, const float* b, void* 
 
 using namespace istvt;
 
-extern "C" int istvt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
-                                   int y_dtype, int64_t rows, int dim, float eps, istvt_stream_t stream) {
+extern "C" int istvt_layernorm_fwd_ld(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta,
+                                      void* y, int y_dtype, int64_t ldy, int64_t rows, int dim, float eps,
+                                      istvt_stream_t stream) {
     ISTVT_REQUIRE(x && y && gamma && beta);
     ISTVT_REQUIRE(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_ITERS * 128);
     ISTVT_REQUIRE((x_dtype | 1) == 1 && (y_dtype | 1) == 1);
+    ISTVT_REQUIRE(ldx >= dim && ldy >= dim && ldx % 4 == 0 && ldy % 4 == 0);      // 8-byte (bf16) / 16-byte vectors
     const int iters = (dim + 127) / 128;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CALL(I) launch_ln<I>(x, x_dtype, gamma, beta, y, y_dtype, rows, dim, eps, st)
+#define CALL(I) launch_ln<I>(x, x_dtype, gamma, beta, y, y_dtype, rows, dim, ldx, ldy, eps, st)
+    ISTVT_DISPATCH_ITERS(iters, CALL)
+#undef CALL
+}
+
+extern "C" int istvt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
+                                   int y_dtype, int64_t rows, int dim, float eps, istvt_stream_t stream) {
+    return istvt_layernorm_fwd_ld(x, x_dtype, dim, gamma, beta, y, y_dtype, dim, rows, dim, eps, stream);
+}
+
+extern "C" int istvt_layernorm_diff_fwd_ld(const float* x, int64_t ldx, const float* gamma, const float* beta, void* xn,
+                                           void* diff, int out_dtype, int64_t ld_out, int batch, int frames, int tokens,
+                                           int dim, float eps, istvt_stream_t stream) {
+    ISTVT_REQUIRE(x && xn && diff && gamma && beta);
+    ISTVT_REQUIRE(batch > 0 && frames > 0 && tokens > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_ITERS * 128);
+    ISTVT_REQUIRE((out_dtype | 1) == 1);
+    ISTVT_REQUIRE(ldx >= dim && ld_out >= dim && ldx % 4 == 0 && ld_out % 4 == 0);
+    const int iters = (dim + 127) / 128;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL(I) launch_ln_diff<I>(x, gamma, beta, xn, diff, out_dtype, batch, frames, tokens, dim, ldx, ld_out, eps, st)
     ISTVT_DISPATCH_ITERS(iters, CALL)
 #undef CALL
 }
@@ -245,14 +267,8 @@ extern "C" int istvt_layernorm_fwd(const void* x, int x_dtype, const float* gamm
 extern "C" int istvt_layernorm_diff_fwd(const float* x, const float* gamma, const float* beta, void* xn, void* diff,
                                         int out_dtype, int batch, int frames, int tokens, int dim, float eps,
                                         istvt_stream_t stream) {
-    ISTVT_REQUIRE(x && xn && diff && gamma && beta);
-    ISTVT_REQUIRE(batch > 0 && frames > 0 && tokens > 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAX_ITERS * 128);
-    ISTVT_REQUIRE((out_dtype | 1) == 1);
-    const int iters = (dim + 127) / 128;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CALL(I) launch_ln_diff<I>(x, gamma, beta, xn, diff, out_dtype, batch, frames, tokens, dim, eps, st)
-    ISTVT_DISPATCH_ITERS(iters, CALL)
-#undef CALL
+    return istvt_layernorm_diff_fwd_ld(x, dim, gamma, beta, xn, diff, out_dtype, dim, batch, frames, tokens, dim, eps,
+                                       stream);
 }
 
 extern "C" int istvt_token_fill_fwd(float* tokens, const float* space_token, const float* temporal_token,

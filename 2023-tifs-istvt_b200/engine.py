@@ -25,6 +25,7 @@ from . import ops
 
 PRECISIONS = {"bf16": torch.bfloat16, "fp32": torch.float32}
 _LN2_FOLD = os.environ.get("ISTVT_LN2_FOLD", "1") != "0"
+_ROW_PITCH = os.environ.get("ISTVT_ROW_PITCH", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -174,7 +175,10 @@ def _fingerprint(model) -> tuple:
 def pack_model(model, dt: torch.dtype) -> _Pack:
     vit = model.vit
     ln = lambda m: (_f32(m.weight), _f32(m.bias))
-    wt = lambda m: m.weight.detach().to(dt).contiguous()
+    # bf16 weights sit at the 128-byte aligned row pitch (K = 728 -> 768 elements; ops.pad_rows): a TMA box row of the
+    # operand is then one line, not two — 13-25 % on the K = 728 GEMMs (profiles/README.md r6n).  ISTVT_ROW_PITCH=0: A/B.
+    pad = ops.pad_rows if (dt == torch.bfloat16 and _ROW_PITCH) else (lambda t: t)
+    wt = lambda m: pad(m.weight.detach().to(dt).contiguous())
     layers = []
     for attn_t, attn_s, ff in vit.transformer.layers:
         lp = _LayerPack(
@@ -187,6 +191,7 @@ def pack_model(model, dt: torch.dtype) -> _Pack:
         if dt == torch.bfloat16:
             lp.w_qkv_f, lp.ln2_c, lp.ln2_d = fold_layernorm(attn_s.fn.to_qkv.weight, attn_s.norm.weight,
                                                             attn_s.norm.bias, dt)
+            lp.w_qkv_f = pad(lp.w_qkv_f)
         layers.append(lp)
     return _Pack(
         entry=pack_entry(model.xcep.model, dt),
@@ -454,8 +459,10 @@ class ISTVTEngine:
 
         attn: List[Tuple[torch.Tensor, torch.Tensor]] = []
         rows = b * f_tok * p_tok
-        xn = torch.empty(b, f_tok, p_tok, dim, dtype=dt, device=dev)
-        diff = torch.empty_like(xn)
+        # GEMM A operands at the aligned row pitch in bf16 mode (see pack_model)
+        alloc = ops.empty_rows if (dt == torch.bfloat16 and _ROW_PITCH) else torch.empty
+        xn = alloc((b, f_tok, p_tok, dim), dtype=dt, device=dev)
+        diff = alloc((b, f_tok, p_tok, dim), dtype=dt, device=dev)
         # After the last block only token (0, 0) of every clip is read (vivit.py:144-148).  Unless intermediates
         # were asked for, the last block therefore runs its temporal attention in full (frame-0 queries need every
         # frame's K / V) and everything after it on the rows that can reach that token: frame-0 rows for the
@@ -470,8 +477,8 @@ class ISTVTEngine:
         for li, lp in enumerate(pk.layers):
             # temporal self-subtract attention (module.py:190-208), no residual of its own (vivit.py:99)
             ops.layernorm_diff(tokens, lp.ln1[0], lp.ln1[1], dt, out=(xn, diff))
-            qk = ops.gemm(diff.view(rows, dim), lp.w_qk)
-            v = ops.gemm(xn.view(rows, dim), lp.w_v)
+            qk = ops.gemm(diff, lp.w_qk).view(rows, -1)
+            v = ops.gemm(xn, lp.w_v).view(rows, -1)
             at, p_t = ops.attn_temporal(qk, v, b, f_tok, p_tok, heads, scale, want_probs=return_attention)
             if prune_last and li == len(pk.layers) - 1:
                 inner = heads * 64
@@ -492,14 +499,14 @@ class ISTVTEngine:
                 qkv = ops.gemm_lnfold(y1, lp.w_qkv_f, ops.ln_stats_finalize(row_stats, dim), lp.ln2_c, lp.ln2_d)
             else:
                 y1 = ops.gemm(at, lp.w_to, bias=lp.b_to, out_dtype=torch.float32 if ln2_input_fp32 else dt)
-                yn = ops.layernorm(y1, lp.ln2[0], lp.ln2[1], dt, out=xn.view(rows, dim))
+                yn = ops.layernorm(y1, lp.ln2[0], lp.ln2[1], dt, out=xn)
                 qkv = ops.gemm(yn, lp.w_qkv)
             as_, p_s = ops.attn_spatial(qkv, b * f_tok, p_tok, heads, scale, want_probs=return_attention)
             tok2d = tokens.view(rows, dim)
             ops.gemm(as_, lp.w_so, bias=lp.b_so, residual=tok2d, out=tok2d)
             # MLP (module.py:33-34) + residual (vivit.py:100)
-            zn = ops.layernorm(tok2d, lp.ln3[0], lp.ln3[1], dt, out=xn.view(rows, dim))
-            hid = ops.gemm(zn, lp.w_1, bias=lp.b_1, act=ops.ACT_GELU, out_dtype=dt)
+            zn = ops.layernorm(tokens, lp.ln3[0], lp.ln3[1], dt, out=xn)
+            hid = ops.gemm(zn, lp.w_1, bias=lp.b_1, act=ops.ACT_GELU, out_dtype=dt).view(rows, -1)
             ops.gemm(hid, lp.w_2, bias=lp.b_2, residual=tok2d, out=tok2d)
             if return_attention:
                 attn.append((p_t, p_s.view(b, f_tok, heads, p_tok, p_tok)))

@@ -45,6 +45,61 @@ def _chk(*tensors: Optional[torch.Tensor]) -> torch.device:
     return dev
 
 
+def _ld(t: torch.Tensor) -> int:
+    """Row pitch (elements) of a row-pitched matrix: last axis dense, all leading axes collapse to one row index with a
+    uniform pitch >= shape[-1] (a contiguous tensor, or a `[..., :dim]` view of one whose rows are padded)."""
+    if t.dim() < 2:
+        return t.shape[-1]
+    if t.stride(-1) != 1 or t.stride(-2) < t.shape[-1]:
+        raise ValueError("istvt_b200: the last axis must be dense")
+    ld = t.stride(-2)
+    step = ld
+    for i in range(t.dim() - 2, 0, -1):
+        step *= t.shape[i]
+        if t.shape[i - 1] > 1 and t.stride(i - 1) != step:
+            raise ValueError("istvt_b200: rows must have a uniform pitch")
+    return ld
+
+
+def _chk_rows(*tensors: Optional[torch.Tensor]) -> torch.device:
+    """_chk for row-pitched matrices (see _ld) instead of contiguous tensors."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise ValueError("istvt_b200: tensors must live on a CUDA device (no CPU fallback by design)")
+        _ld(t)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError("istvt_b200: all tensors of one call must be on the same device")
+    assert dev is not None
+    return dev
+
+
+def row_pitch(dim: int, dtype: torch.dtype = torch.bfloat16) -> int:
+    """Pitch (elements) that makes every row of a [rows, dim] matrix start on a 128-byte line: 728 bf16 -> 768."""
+    per_line = 128 // torch.empty((), dtype=dtype).element_size()
+    return (dim + per_line - 1) // per_line * per_line
+
+
+def empty_rows(shape, dtype: torch.dtype, device) -> torch.Tensor:
+    """torch.empty(shape) whose rows (last axis) sit at the 128-byte aligned pitch row_pitch(shape[-1]): returned as
+    the `[..., :dim]` view.  TMA box rows of such an operand never straddle two lines (profiles/README.md r6n)."""
+    dim = shape[-1]
+    ld = row_pitch(dim, dtype)
+    full = torch.empty(*shape[:-1], ld, dtype=dtype, device=device)
+    return full if ld == dim else full[..., :dim]
+
+
+def pad_rows(t: torch.Tensor) -> torch.Tensor:
+    """Copy of a [rows, dim] matrix at the aligned pitch (weights, at pack time)."""
+    out = empty_rows(tuple(t.shape), t.dtype, t.device)
+    out.copy_(t)
+    return out
+
+
 def f32_aligned(t: torch.Tensor) -> torch.Tensor:
     """fp32, contiguous, 16-byte aligned view or copy of a parameter.  Parameters of an `nn.DataParallel` replica are
     views into one coalesced broadcast buffer (torch's `broadcast_coalesced` packs them back to back), so their start
@@ -126,14 +181,16 @@ def _nbytes(*ts: Optional[torch.Tensor]) -> int:
 # ----------------------------------------------------------------------------------------------
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out_dtype: torch.dtype,
               eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    dev = _chk(x, gamma, beta, out)
+    dev = _chk(gamma, beta)
+    _chk_rows(x, out)
     dim = x.shape[-1]
     rows = x.numel() // dim
     if out is None:
         out = torch.empty(x.shape, dtype=out_dtype, device=dev)
     with _launch(dev, "layernorm", 0.0, _nbytes(x, out)):
-        _lib.check(_lib.lib().istvt_layernorm_fwd(_ptr(x), _dt(x), _ptr(gamma), _ptr(beta), _ptr(out), _dt(out),
-                                                  rows, dim, eps, _stream(dev)), "istvt_layernorm_fwd")
+        _lib.check(_lib.lib().istvt_layernorm_fwd_ld(_ptr(x), _dt(x), _ld(x), _ptr(gamma), _ptr(beta), _ptr(out),
+                                                     _dt(out), _ld(out), rows, dim, eps, _stream(dev)),
+                   "istvt_layernorm_fwd_ld")
     return out
 
 
@@ -141,7 +198,8 @@ def layernorm_diff(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out
                    eps: float = 1e-5, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
                    ) -> Tuple[torch.Tensor, torch.Tensor]:
     """x: fp32 [B, F, P, D] -> (LN(x), self-subtract difference), both [B, F, P, D] in out_dtype."""
-    dev = _chk(x, gamma, beta)
+    dev = _chk(gamma, beta)
+    _chk_rows(x)
     if x.dtype != torch.float32 or x.dim() != 4:
         raise ValueError("layernorm_diff expects an fp32 [B, F, P, D] token tensor")
     b, f, p, d = x.shape
@@ -150,11 +208,13 @@ def layernorm_diff(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out
         diff = torch.empty(x.shape, dtype=out_dtype, device=dev)
     else:
         xn, diff = out
-        _chk(xn, diff)
+        _chk_rows(xn, diff)
+        if _ld(xn) != _ld(diff):
+            raise ValueError("layernorm_diff: xn and diff must have the same row pitch")
     with _launch(dev, "layernorm_diff", 0.0, _nbytes(x, xn, diff)):
-        _lib.check(_lib.lib().istvt_layernorm_diff_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(xn), _ptr(diff),
-                                                       _dt(xn), b, f, p, d, eps, _stream(dev)),
-                   "istvt_layernorm_diff_fwd")
+        _lib.check(_lib.lib().istvt_layernorm_diff_fwd_ld(_ptr(x), _ld(x), _ptr(gamma), _ptr(beta), _ptr(xn), _ptr(diff),
+                                                          _dt(xn), _ld(xn), b, f, p, d, eps, _stream(dev)),
+                   "istvt_layernorm_diff_fwd_ld")
     return xn, diff
 
 
@@ -166,7 +226,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     bf16 operands run the tcgen05 kernel, fp32 operands the SIMT validation kernel.
     `residual` must be fp32; pass `out=residual` for the in-place residual update.
     """
-    dev = _chk(a, w, bias, residual, out)
+    dev = _chk(bias) if bias is not None else a.device
+    _chk_rows(a, w, residual, out)
     k = a.shape[-1]
     m = a.numel() // k
     n = w.shape[0]
@@ -186,13 +247,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     with _launch(dev, "gemm_bf16" if a.dtype == torch.bfloat16 else "gemm_f32", 2.0 * m * n * k,
                  _nbytes(a, w, out, residual)):
         if a.dtype == torch.bfloat16:
-            _lib.check(_lib.lib().istvt_gemm_fwd(_ptr(a), k, _ptr(w), k, _ptr(out), n, _dt(out), m, n, k, _ptr(bias),
-                                                 _ptr(residual), n, act, st), "istvt_gemm_fwd")
+            _lib.check(_lib.lib().istvt_gemm_fwd(_ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(out), _ld(out), _dt(out), m, n, k,
+                                                 _ptr(bias), _ptr(residual), _ld(residual) if residual is not None else n,
+                                                 act, st), "istvt_gemm_fwd")
         else:
             if out.dtype != torch.float32:
                 raise ValueError("gemm: fp32 operands need an fp32 output")
-            _lib.check(_lib.lib().istvt_gemm_f32_fwd(_ptr(a), k, _ptr(w), k, _ptr(out), n, m, n, k, _ptr(bias),
-                                                     _ptr(residual), n, act, st), "istvt_gemm_f32_fwd")
+            _lib.check(_lib.lib().istvt_gemm_f32_fwd(_ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(out), _ld(out), m, n, k,
+                                                     _ptr(bias), _ptr(residual),
+                                                     _ld(residual) if residual is not None else n, act, st),
+                       "istvt_gemm_f32_fwd")
     return out
 
 
@@ -200,7 +264,8 @@ def gemm_rowstats(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     """out = a . w^T + bias (bf16) and row_stats[m, g] = (sum, sum of squared deviations from the group mean) of every
     64-column group of the output row — the producer half of the LayerNorm fold (istvt_gemm_rowstats_fwd).
     row_stats: fp32 [M, ceil(N / 64), 2], fully overwritten."""
-    dev = _chk(a, w, bias, row_stats)
+    dev = _chk(bias, row_stats)
+    _chk_rows(a, w)
     k = a.shape[-1]
     m = a.numel() // k
     n = w.shape[0]
@@ -208,10 +273,11 @@ def gemm_rowstats(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
         raise ValueError("gemm_rowstats: bf16 a [M, K] and w [N, K]")
     if row_stats.dtype != torch.float32 or row_stats.numel() != 2 * m * ((n + 63) // 64):
         raise ValueError("gemm_rowstats: row_stats must be fp32 [M, ceil(N / 64), 2]")
-    out = torch.empty(*a.shape[:-1], n, dtype=torch.bfloat16, device=dev)
+    out = empty_rows((*a.shape[:-1], n), torch.bfloat16, dev)      # the next GEMM's A operand: aligned pitch
     with _launch(dev, "gemm_bf16", 2.0 * m * n * k, _nbytes(a, w, out)):
-        _lib.check(_lib.lib().istvt_gemm_rowstats_fwd(_ptr(a), k, _ptr(w), k, _ptr(out), n, m, n, k, _ptr(bias),
-                                                      _ptr(row_stats), _stream(dev)), "istvt_gemm_rowstats_fwd")
+        _lib.check(_lib.lib().istvt_gemm_rowstats_fwd(_ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(out), _ld(out), m, n, k,
+                                                      _ptr(bias), _ptr(row_stats), _stream(dev)),
+                   "istvt_gemm_rowstats_fwd")
     return out
 
 
@@ -233,7 +299,8 @@ def gemm_lnfold(a: torch.Tensor, w_folded: torch.Tensor, mu_rstd: torch.Tensor, 
                 shift: torch.Tensor) -> torch.Tensor:
     """LayerNorm(a) . W^T without the LayerNorm pass — the consumer half of the fold (istvt_gemm_lnfold_fwd):
     out = rstd (a . w_folded^T - mu w_rowsum) + shift with (mu, rstd) per row from ln_stats_finalize."""
-    dev = _chk(a, w_folded, mu_rstd, w_rowsum, shift)
+    dev = _chk(mu_rstd, w_rowsum, shift)
+    _chk_rows(a, w_folded)
     k = a.shape[-1]
     m = a.numel() // k
     n = w_folded.shape[0]
@@ -244,8 +311,8 @@ def gemm_lnfold(a: torch.Tensor, w_folded: torch.Tensor, mu_rstd: torch.Tensor, 
         raise ValueError("gemm_lnfold: mu_rstd fp32 [M, 2], w_rowsum / shift fp32 [N]")
     out = torch.empty(*a.shape[:-1], n, dtype=torch.bfloat16, device=dev)
     with _launch(dev, "gemm_bf16", 2.0 * m * n * k, _nbytes(a, w_folded, out)):
-        _lib.check(_lib.lib().istvt_gemm_lnfold_fwd(_ptr(a), k, _ptr(w_folded), k, _ptr(out), n, m, n, k, _ptr(mu_rstd),
-                                                    _ptr(w_rowsum), _ptr(shift), _stream(dev)),
+        _lib.check(_lib.lib().istvt_gemm_lnfold_fwd(_ptr(a), _ld(a), _ptr(w_folded), _ld(w_folded), _ptr(out), n, m, n, k,
+                                                    _ptr(mu_rstd), _ptr(w_rowsum), _ptr(shift), _stream(dev)),
                    "istvt_gemm_lnfold_fwd")
     return out
 

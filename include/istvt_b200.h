@@ -56,6 +56,11 @@ int64_t istvt_launch_count(void);
  * ------------------------------------------------------------------------------------------- */
 int istvt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
                         int y_dtype, int64_t rows, int dim, float eps, istvt_stream_t stream);
+/* The same with row pitches ldx / ldy (elements, >= dim, % 4 == 0).  The engine keeps its [rows, 728] bf16 GEMM
+ * operands at a pitch of 768 elements: every 128-byte TMA box row of an operand is then ONE 128-byte line instead of
+ * straddling two (7 rows of 8 at pitch 728), which is worth 13-25 % on the K = 728 GEMMs (profiles/README.md r6n). */
+int istvt_layernorm_fwd_ld(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* y,
+                           int y_dtype, int64_t ldy, int64_t rows, int dim, float eps, istvt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm fused with the temporal self-subtract of TemporalResidualAttention.
@@ -68,6 +73,10 @@ int istvt_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const fl
 int istvt_layernorm_diff_fwd(const float* x, const float* gamma, const float* beta, void* xn, void* diff,
                              int out_dtype, int batch, int frames, int tokens, int dim, float eps,
                              istvt_stream_t stream);
+/* The same with row pitches: ldx of x, ld_out of xn AND diff (elements, >= dim, % 4 == 0). */
+int istvt_layernorm_diff_fwd_ld(const float* x, int64_t ldx, const float* gamma, const float* beta, void* xn, void* diff,
+                                int out_dtype, int64_t ld_out, int batch, int frames, int tokens, int dim, float eps,
+                                istvt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * C[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] ) + residual[m, n]

@@ -68,6 +68,82 @@ def entry_flow(args) -> None:
     print(f"entry-flow GEMM sum {tot_ms:7.3f} ms  {tot_by / tot_ms / 1e6:6.0f} GB/s")
 
 
+def pitch_experiment(args) -> None:
+    """Does the row pitch of the K-major operands matter?  K = 728 rows are 1456 B apart, so 7 of every 8 box rows
+    (128 B of one operand row) straddle two 128-byte lines; with a pitch of 768 elements every box row is one line."""
+    from importlib import import_module
+    _lib = import_module("2023-tifs-istvt_b200._lib")
+    lib = _lib.lib()
+    dev = "cuda"
+    m = args.m
+    st = torch.cuda.current_stream().cuda_stream
+    for (n, k) in ((1536, 728), (2912, 728), (1024, 728), (728, 2912)):
+        for (lda, ldw, ldc) in ((k, k, n), (k + 40 if k == 728 else k + 32, k, n), (k, k + 40 if k == 728 else k + 32, n),
+                                (k + 40 if k == 728 else k + 32, k + 40 if k == 728 else k + 32, n),
+                                (k, k, (n + 63) // 64 * 64)):
+            nbuf = 3
+            a = [torch.randn(m, lda, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+            w = torch.randn(n, ldw, device=dev, dtype=torch.bfloat16) * k ** -0.5
+            outs = [torch.zeros(m, ldc, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+
+            def run(i):
+                _lib.check(lib.istvt_gemm_fwd(a[i % nbuf].data_ptr(), lda, w.data_ptr(), ldw, outs[i % nbuf].data_ptr(), ldc,
+                                              ops.BF16, m, n, k, None, None, n, 0, st),
+                           "istvt_gemm_fwd")
+            for i in range(3):
+                run(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.iters):
+                run(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.iters
+            ref = (a[(args.iters - 1) % nbuf][:4096, :k].float() @ w[:, :k].float().t())
+            err = ((outs[(args.iters - 1) % nbuf][:4096, :n].float() - ref).abs().max() / ref.abs().max()).item()
+            print(f"N={n:5d} K={k:5d} lda={lda:5d} ldw={ldw:5d} ldc={ldc:5d} {ms:7.3f} ms  {2.0 * m * n * k / ms / 1e9:7.1f} TFLOP/s"
+                  f"  rel_err {err:.1e}", flush=True)
+            del a, outs
+
+
+def residual_pitch_experiment(args) -> None:
+    """In-place fp32 residual update (s_out / ff2: TMA reduce-add of 128-byte box rows) with the residual stream at
+    pitch 728 (2912 B: 3 box rows of 4 straddle two lines) vs 768 (3072 B)."""
+    from importlib import import_module
+    _lib = import_module("2023-tifs-istvt_b200._lib")
+    lib = _lib.lib()
+    dev = "cuda"
+    m = args.m
+    st = torch.cuda.current_stream().cuda_stream
+    for (n, k) in ((728, 512), (728, 2912)):
+        for ldc in (728, 768):
+            nbuf = 3
+            a = [torch.randn(m, k, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+            w = torch.randn(n, k, device=dev, dtype=torch.bfloat16) * k ** -0.5
+            bias = torch.randn(n, device=dev)
+            outs = [torch.zeros(m, ldc, device=dev, dtype=torch.float32) for _ in range(nbuf)]
+
+            def run(i):
+                o = outs[i % nbuf]
+                _lib.check(lib.istvt_gemm_fwd(a[i % nbuf].data_ptr(), k, w.data_ptr(), k, o.data_ptr(), ldc, ops.F32, m, n, k,
+                                              bias.data_ptr(), o.data_ptr(), ldc, 0, st), "istvt_gemm_fwd")
+            for i in range(3):
+                run(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.iters):
+                run(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.iters
+            by = m * k * 2 + n * k * 2 + 2 * m * n * 4
+            print(f"residual in place N={n:5d} K={k:5d} ldc={ldc:5d} {ms:7.3f} ms  {2.0 * m * n * k / ms / 1e9:7.1f} TFLOP/s"
+                  f"  {by / ms / 1e6:6.0f} GB/s", flush=True)
+            del a, outs
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
@@ -78,9 +154,15 @@ def main() -> None:
                                                           "yardstick for what the shape can reach, not a product path")
     ap.add_argument("--entry", action="store_true", help="the 9 pointwise / skip GEMMs of the Xception entry flow at "
                                                          "the C2 size (384 frames) instead of the transformer's")
+    ap.add_argument("--residual-pitch", action="store_true", help="s_out / ff2 in place with the fp32 stream at pitch 728 vs 768")
+    ap.add_argument("--pitch", action="store_true", help="row-pitch experiment: K = 728 operands with pitch 728 vs 768")
     args = ap.parse_args()
     if args.entry:
         return entry_flow(args)
+    if args.pitch:
+        return pitch_experiment(args)
+    if args.residual_pitch:
+        return residual_pitch_experiment(args)
     for i, nk in enumerate(filter(None, args.custom.split(";"))):
         n_, k_ = (int(v) for v in nk.split(","))
         SHAPES[f"c{n_}x{k_}"] = (n_, k_, False, False, 0, torch.bfloat16)
