@@ -31,6 +31,9 @@ _ROW_PITCH = os.environ.get("ISTVT_ROW_PITCH", "1") != "0"
 # ------------------------------------------------------------------------------------------------
 # weight packing
 # ------------------------------------------------------------------------------------------------
+PACK_FORMAT = 2      # bump when the layout of a packed tensor changes (v2: K = 728 weights at the aligned row pitch)
+
+
 def _bn_fold(bn) -> Tuple[torch.Tensor, torch.Tensor]:
     scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
     shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
@@ -357,6 +360,73 @@ def entry_flow_features(xcep, x: torch.Tensor, precision: str = "fp32") -> torch
     body, skip = run_entry_flow(ep, x.contiguous().float(), dt)
     y = ops.pool_add(body, skip)
     return y.float().permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# packed weights persisted beside the checkpoint (train_CNN.py:998-1011 writes best.pkl)
+# ------------------------------------------------------------------------------------------------
+def state_digest(model) -> str:
+    """sha256 over the bytes of every on-path parameter / buffer, in module order: the key a persisted pack is valid for."""
+    import hashlib
+    h = hashlib.sha256()
+    for t in _on_path_tensors(model):
+        c = t.detach().contiguous().cpu()
+        h.update(str((tuple(c.shape), str(c.dtype))).encode())
+        h.update(c.reshape(-1).view(torch.uint8).numpy().tobytes() if c.numel() else b"")
+    return h.hexdigest()
+
+
+def _pack_to_plain(obj):
+    """dataclass tree -> nested dict / list / tuple of CPU tensors (row-pitched views are saved dense, flagged)."""
+    from dataclasses import fields, is_dataclass
+    if is_dataclass(obj):
+        return {"__dc__": type(obj).__name__, **{f.name: _pack_to_plain(getattr(obj, f.name)) for f in fields(obj)
+                                                 if f.name != "fingerprint"}}
+    if isinstance(obj, torch.Tensor):
+        pitched = obj.dim() >= 2 and obj.stride(-2) != obj.shape[-1]
+        return {"__t__": obj.detach().contiguous().cpu(), "pitched": pitched}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_pack_to_plain(v) for v in obj)
+    return obj
+
+
+def _pack_from_plain(obj, dev):
+    classes = {c.__name__: c for c in (_SepPack, _BlockPack, _LayerPack, _EntryPack, _Pack)}
+    if isinstance(obj, dict) and "__dc__" in obj:
+        kw = {k: _pack_from_plain(v, dev) for k, v in obj.items() if k != "__dc__"}
+        return classes[obj["__dc__"]](**kw)
+    if isinstance(obj, dict) and "__t__" in obj:
+        t = obj["__t__"].to(dev)
+        return ops.pad_rows(t) if obj["pitched"] else t
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_pack_from_plain(v, dev) for v in obj)
+    return obj
+
+
+def save_pack(model, path: str, precision: Optional[str] = None) -> str:
+    """Write the packed weights of `model` (BatchNorm folded, bf16 casts, LayerNorm-2 fold, aligned row pitch) to
+    `path`, keyed by state_digest(model).  Typical use: next to the checkpoint, `save_pack(model, "best.pkl.pack")`."""
+    precision = precision or model.precision
+    pack = pack_model(model, PRECISIONS[precision])
+    blob = {"format": PACK_FORMAT, "precision": precision, "row_pitch": _ROW_PITCH, "digest": state_digest(model),
+            "pack": _pack_to_plain(pack)}
+    torch.save(blob, path)
+    return blob["digest"]
+
+
+def load_pack(model, path: str) -> bool:
+    """Install a persisted pack into the model's engine cache for the model's current device.  Returns False — and
+    leaves the engine to pack on the first forward as usual — when the file was written for other weights, another
+    format, or another pitch setting; a stale pack is never used."""
+    blob = torch.load(path, map_location="cpu", weights_only=True)
+    if blob.get("format") != PACK_FORMAT or blob.get("row_pitch") != _ROW_PITCH or blob.get("digest") != state_digest(model):
+        return False
+    dev = _on_path_tensors(model)[0].device
+    pack = _pack_from_plain(blob["pack"], dev)
+    pack.fingerprint = _fingerprint(model)
+    eng = model.engine()
+    eng._packs[(str(dev), blob["precision"])] = pack
+    return True
 
 
 class ISTVTEngine:

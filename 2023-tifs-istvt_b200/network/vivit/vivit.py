@@ -248,6 +248,16 @@ class XceptionVidTr(nn.Module):
         from ...relevance import relprop
         return relprop(self, cam, method=method, is_ablation=is_ablation, start_layer=start_layer, alpha=alpha, clips=clips)
 
+    def save_packed_weights(self, path: str) -> str:
+        """Persist the packed inference weights beside a checkpoint; see engine.save_pack."""
+        from ...engine import save_pack
+        return save_pack(self, path)
+
+    def load_packed_weights(self, path: str) -> bool:
+        """Install a persisted pack (False if it does not belong to the current weights); see engine.load_pack."""
+        from ...engine import load_pack
+        return load_pack(self, path)
+
     def _apply(self, fn, *args, **kwargs):  # .cuda() / .to(): drop the packed-weight cache and the flat train state
         self._shared.reset()
         return super()._apply(fn, *args, **kwargs)

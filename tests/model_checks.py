@@ -563,6 +563,42 @@ def run_graph_check():
     return {"eager_ms": eager_ms, "graph_ms": graph_ms}
 
 
+def run_pack_cache_check():
+    """Packed weights persisted beside the checkpoint: a second model that loads the
+    state_dict and the pack file runs its first forward WITHOUT packing (no torch cast / fold kernels, pack object taken
+    from the file) and returns bit-identical logits; a pack of other weights is refused."""
+    import os
+    import tempfile
+    m = pkg()
+    eng = __import__("importlib").import_module("2023-tifs-istvt_b200.engine")
+    model = build_model({"seed": 0, "frames": 6, "sensitised": True}).cuda().eval()
+    x = make_input(2, 6, seed=5).cuda()
+    with torch.no_grad():
+        want = model(x).clone()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "best.pkl.pack")
+        model.save_packed_weights(path)
+        other = m.XceptionVidTr().eval()
+        other.load_state_dict(model.state_dict())
+        other = other.cuda()
+        assert other.load_packed_weights(path)
+        pack = other.engine()._packs[(str(x.device), "bf16")]
+        calls = []
+        orig = eng.pack_model
+        eng.pack_model = lambda *a, **k: calls.append(1) or orig(*a, **k)
+        try:
+            with torch.no_grad():
+                got = other(x).clone()
+        finally:
+            eng.pack_model = orig
+        assert not calls and other.engine()._packs[(str(x.device), "bf16")] is pack, "the persisted pack was not used"
+        assert torch.equal(got, want), f"persisted pack {got.flatten().tolist()} != packed in place {want.flatten().tolist()}"
+        with torch.no_grad():
+            other.vit.mlp_head[1].bias.add_(0.5)
+        assert not other.load_packed_weights(path)
+    return {"bit_equal": 0.0}
+
+
 # ------------------------------------------------------------------------------------------------
 # ablation transformers (SURVEY.md section 8(f) rank 3)
 # ------------------------------------------------------------------------------------------------

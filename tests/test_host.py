@@ -273,3 +273,41 @@ def test_layernorm_fold_algebra():
     got = tops.gemm_lnfold(y, wf, tops.ln_stats_finalize(stats, 728), c, d)
     want = F.linear(F.layer_norm(F.linear(a, w1, b1), (728,), gamma, beta), w2)
     assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+
+
+def test_persisted_pack_round_trip_and_staleness(tmp_path):
+    """packed weights written beside a checkpoint come back bit-identical (row-pitched
+    tensors at their pitch), and a pack written for other weights is refused."""
+    eng = __import__("importlib").import_module("2023-tifs-istvt_b200.engine")
+    ops = __import__("importlib").import_module("2023-tifs-istvt_b200.ops")
+    torch.manual_seed(3)
+    m = pkg().XceptionVidTr().eval()
+    path = str(tmp_path / "best.pkl.pack")
+    digest = m.save_packed_weights(path)
+    assert digest == eng.state_digest(m)
+    assert m.load_packed_weights(path)
+    got = m.engine()._packs[("cpu", "bf16")]
+    want = eng.pack_model(m, torch.bfloat16)
+
+    def leaves(o, out):
+        from dataclasses import fields, is_dataclass
+        if is_dataclass(o):
+            for f in fields(o):
+                if f.name != "fingerprint":
+                    leaves(getattr(o, f.name), out)
+        elif isinstance(o, torch.Tensor):
+            out.append(o)
+        elif isinstance(o, (list, tuple)):
+            for v in o:
+                leaves(v, out)
+        return out
+    a, b = leaves(got, []), leaves(want, [])
+    assert len(a) == len(b) > 200
+    for x, y in zip(a, b):
+        assert x.dtype == y.dtype and x.shape == y.shape and x.stride() == y.stride() and torch.equal(x, y)
+    lp = got.layers[0]
+    assert lp.w_qkv_f.stride(0) == ops.row_pitch(728) == 768 and lp.w_2.stride(0) == 2912
+    assert got.fingerprint == eng._fingerprint(m)
+    with torch.no_grad():
+        m.vit.transformer.layers[3][2].fn.net[0].bias.add_(1e-3)      # any on-path change invalidates the file
+    assert not m.load_packed_weights(path)

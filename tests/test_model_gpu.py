@@ -62,6 +62,11 @@ def test_cuda_graph_forward():
 
 
 @pytest.mark.gpu
+def test_persisted_pack_cache():
+    model_checks.run_pack_cache_check()
+
+
+@pytest.mark.gpu
 def test_uint8_frames_against_oracle():
     model_checks.run_uint8_input_check()
 

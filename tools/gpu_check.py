@@ -39,6 +39,7 @@ def all_checks():
     checks["relevance"] = model_checks.run_relevance_check
     checks["relevance_t32"] = model_checks.run_relevance_t32_check
     checks["cuda_graph"] = model_checks.run_graph_check
+    checks["pack_cache"] = model_checks.run_pack_cache_check
     checks["uint8_input"] = model_checks.run_uint8_input_check
     checks["xception_fp32"] = lambda: model_checks.run_xception_golden("fp32")
     checks["xception_bf16"] = lambda: model_checks.run_xception_golden("bf16")
