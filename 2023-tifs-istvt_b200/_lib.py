@@ -27,6 +27,8 @@ SIGNATURES = {
     "istvt_layernorm_diff_fwd_ld": [_P, _L, _P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _F, _P],
     "istvt_gemm_fwd": [_P, _L, _P, _L, _P, _L, _I, _L, _I, _I, _P, _P, _L, _I, _P],
     "istvt_gemm_f32_fwd": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _P, _L, _I, _P],
+    "istvt_gemm_act_dual_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _I, _P],
+    "istvt_gemm_dgelu_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _P],
     "istvt_conv3x3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "istvt_conv_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "istvt_conv_stem_u8_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -48,6 +50,9 @@ SIGNATURES = {
     "istvt_attn_spatial_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "istvt_attn_temporal_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "istvt_layernorm_bwd": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
+    "istvt_layernorm_bwd_ld": [_P, _P, _L, _I, _I, _P, _I, _L, _P, _P, _L, _P, _L, _P, _L, _P, _P, _L, _I, _F, _P],
+    "istvt_cast_f32_bf16_rows": [_P, _L, _P, _L, _L, _I, _P],
+    "istvt_colsum_ld": [_P, _L, _P, _L, _I, _P],
     "istvt_gelu_fwd": [_P, _P, _L, _P],
     "istvt_gelu_bwd": [_P, _P, _P, _L, _P],
     "istvt_cast_f32_bf16": [_P, _P, _L, _P],

@@ -9,6 +9,7 @@
 #include "simt_util.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace istvt {
 
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, int frames, int tokens_pf,
                      const TX* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ g,
                      bf16* __restrict__ g_bf, bf16* __restrict__ dx_out, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, int64_t rows, int dim, float eps) {
+                     float* __restrict__ dbeta, int64_t rows, int dim, int64_t ld_dy, int64_t ld_x, int64_t ld_g,
+                     int64_t ld_gb, int64_t ld_dx, float eps, int p_prefetch) {
     // dgamma / dbeta partials live in a per-warp slab of shared memory (each lane owns its columns, no atomics):
     // keeping them in registers cost 48 registers per thread and held the kernel to one CTA per SM (1.4 TB/s).
     extern __shared__ __align__(16) float s_part[];          // [warps][2][dim]
@@ -62,7 +64,26 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
 
     const int64_t wid = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t wstride = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+    // Two dependent DRAM round trips per row (x / dy, then the read-modify-write of g) with one row per warp in flight
+    // held the kernel at 3.4 TB/s (profiles/README.md r6f).  Each lane now pulls one 128-byte line of THIS row's g and
+    // of the NEXT row's x / dy / dy2 / g into L2 before the row's own loads: no registers, the later loads hit in L2.
+    auto prefetch_row = [&](int64_t r, bool with_inputs) {
+        if (r >= rows) return;
+        if (with_inputs) {
+            if (lane * (128 / static_cast<int>(sizeof(TX))) < dim)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(x + r * ld_x + lane * (128 / sizeof(TX))));
+            if (lane * 64 < dim) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + r * ld_dy + lane * 64));
+                if (dy2 != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(dy2 + r * ld_dy + lane * 64));
+            }
+        }
+        if (ACCUM && lane * 32 < dim) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + r * ld_g + lane * 32));
+    };
     for (int64_t row = wid; row < rows; row += wstride) {
+        if (p_prefetch) {
+            prefetch_row(row, false);
+            prefetch_row(row + wstride, true);
+        }
         float xv[LNB_MAXC][4], dv[LNB_MAXC][4];
         bool sub_next = false;
         if (dy2 != nullptr) {
@@ -76,8 +97,8 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
         for (int i = 0; i < LNB_MAXC; ++i) {
             const int c = lane + 32 * i;
             if (c < nch) {
-                ld4(x + row * dim + 4 * c, xv[i]);
-                ld4(dy + row * dim + 4 * c, dv[i]);
+                ld4(x + row * ld_x + 4 * c, xv[i]);
+                ld4(dy + row * ld_dy + 4 * c, dv[i]);
             } else {
                 xv[i][0] = xv[i][1] = xv[i][2] = xv[i][3] = 0.f;
                 dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
@@ -89,11 +110,11 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
                 const int c = lane + 32 * i;
                 if (c < nch) {
                     float t[4];
-                    ld4(dy2 + row * dim + 4 * c, t);
+                    ld4(dy2 + row * ld_dy + 4 * c, t);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) dv[i][e] += t[e];
                     if (sub_next) {
-                        ld4(dy2 + (row + tokens_pf) * dim + 4 * c, t);
+                        ld4(dy2 + (row + tokens_pf) * ld_dy + 4 * c, t);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) dv[i][e] -= t[e];
                     }
@@ -148,13 +169,13 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
                 for (int e = 0; e < 4; ++e) dx[e] = rstd * (dv[i][e] - s1 - xv[i][e] * s2);
                 if (ACCUM) {
                     float gv[4];
-                    ld4(g + row * dim + 4 * c, gv);
+                    ld4(g + row * ld_g + 4 * c, gv);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) gv[e] += dx[e];
-                    st4(g + row * dim + 4 * c, gv);
-                    if (g_bf != nullptr) st4(g_bf + row * dim + 4 * c, gv);
+                    st4(g + row * ld_g + 4 * c, gv);
+                    if (g_bf != nullptr) st4(g_bf + row * ld_gb + 4 * c, gv);
                 } else {
-                    st4(dx_out + row * dim + 4 * c, dx);
+                    st4(dx_out + row * ld_dx + 4 * c, dx);
                 }
             }
         }
@@ -218,6 +239,18 @@ gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* _
         d[e] *= fmaf(v[e], pdf, cdf);
     }
     store8(dx + i * 8, d);
+}
+
+// the same for a [rows, cols] matrix with row pitches (cols % 4 == 0): thread = 4 consecutive elements of one row
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_rows_kernel(const float* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy, int64_t rows, int c4) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows * c4) return;
+    const int64_t r = i / c4;
+    const int c = static_cast<int>(i - r * c4) * 4;
+    float v[4];
+    ld4(x + r * ldx + c, v);
+    st4(y + r * ldy + c, v);
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n4) {
@@ -438,7 +471,7 @@ rollout_row_kernel(float* __restrict__ v, const float* __restrict__ cmat, int le
 // thread = (row lane, 8-column group), groups fastest; per-CTA partials through shared memory.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-colsum_kernel(const bf16* __restrict__ x, float* __restrict__ colsum, int64_t m, int c) {
+colsum_kernel(const bf16* __restrict__ x, float* __restrict__ colsum, int64_t m, int c, int64_t ld) {
     extern __shared__ float s_cs[];
     for (int i = threadIdx.x; i < c; i += blockDim.x) s_cs[i] = 0.f;
     __syncthreads();
@@ -451,7 +484,7 @@ colsum_kernel(const bf16* __restrict__ x, float* __restrict__ colsum, int64_t m,
         for (int e = 0; e < 8; ++e) s[e] = 0.f;
         for (int64_t r = static_cast<int64_t>(blockIdx.x) * lanes + rl; r < m; r += static_cast<int64_t>(gridDim.x) * lanes) {
             float v[8];
-            load8(x + r * c + cg * 8, v);
+            load8(x + r * ld + cg * 8, v);
 #pragma unroll
             for (int e = 0; e < 8; ++e) s[e] += v[e];
         }
@@ -486,12 +519,16 @@ static inline unsigned nblk(int64_t total, int threads) { return static_cast<uns
 
 using namespace istvt;
 
-extern "C" int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, int tokens_per_frame, const void* x,
-                                   int x_dtype, const float* gamma, float* g_accum, void* g_bf16, void* dx_out,
-                                   float* dgamma, float* dbeta, int64_t rows, int dim, float eps,
-                                   istvt_stream_t stream) {
+extern "C" int istvt_layernorm_bwd_ld(const void* dy, const void* dy2, int64_t ld_dy, int frames, int tokens_per_frame,
+                                      const void* x, int x_dtype, int64_t ld_x, const float* gamma, float* g_accum,
+                                      int64_t ld_g, void* g_bf16, int64_t ld_gb, void* dx_out, int64_t ld_dx,
+                                      float* dgamma, float* dbeta, int64_t rows, int dim, float eps,
+                                      istvt_stream_t stream) {
     ISTVT_REQUIRE(dy && x && gamma && dgamma && dbeta && rows > 0);
     ISTVT_REQUIRE(dim % 4 == 0 && dim <= 768);
+    ISTVT_REQUIRE(ld_dy >= dim && ld_x >= dim && ld_dy % 4 == 0 && ld_x % 4 == 0);
+    ISTVT_REQUIRE(g_accum == nullptr || (ld_g >= dim && ld_g % 4 == 0 && (g_bf16 == nullptr || (ld_gb >= dim && ld_gb % 4 == 0))));
+    ISTVT_REQUIRE(dx_out == nullptr || (ld_dx >= dim && ld_dx % 4 == 0));
     ISTVT_REQUIRE((g_accum != nullptr) != (dx_out != nullptr));
     ISTVT_REQUIRE(dy2 == nullptr || (frames > 0 && tokens_per_frame > 0));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -504,6 +541,8 @@ extern "C" int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, 
     bf16* dxo = static_cast<bf16*>(dx_out);
     const unsigned gr = static_cast<unsigned>(blocks);
     const size_t smem = 8 * 2 * static_cast<size_t>(dim) * sizeof(float);
+    // ISTVT_LNB_PREFETCH=0: without the L2 prefetches of the next row (A/B measurements)
+    static const int pf = []() { const char* e = getenv("ISTVT_LNB_PREFETCH"); return e ? atoi(e) : 1; }();
     ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
     ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
     ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
@@ -512,23 +551,31 @@ extern "C" int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, 
         const float* xx = static_cast<const float*>(x);
         if (g_accum)
             layernorm_bwd_kernel<float, true><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
-                                                                   nullptr, dgamma, dbeta, rows, dim, eps);
+                                                                   nullptr, dgamma, dbeta, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
         else
             layernorm_bwd_kernel<float, false><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
-                                                                    nullptr, dxo, dgamma, dbeta, rows, dim, eps);
+                                                                    nullptr, dxo, dgamma, dbeta, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
     } else if (x_dtype == ISTVT_BF16) {
         const bf16* xx = static_cast<const bf16*>(x);
         if (g_accum)
             layernorm_bwd_kernel<bf16, true><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
-                                                                  nullptr, dgamma, dbeta, rows, dim, eps);
+                                                                  nullptr, dgamma, dbeta, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
         else
             layernorm_bwd_kernel<bf16, false><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
-                                                                   nullptr, dxo, dgamma, dbeta, rows, dim, eps);
+                                                                   nullptr, dxo, dgamma, dbeta, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
     } else {
         return ISTVT_ERR_INVALID_ARG;
     }
     count_launch();
     return launch_status();
+}
+
+extern "C" int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, int tokens_per_frame, const void* x,
+                                   int x_dtype, const float* gamma, float* g_accum, void* g_bf16, void* dx_out,
+                                   float* dgamma, float* dbeta, int64_t rows, int dim, float eps,
+                                   istvt_stream_t stream) {
+    return istvt_layernorm_bwd_ld(dy, dy2, dim, frames, tokens_per_frame, x, x_dtype, dim, gamma, g_accum, dim, g_bf16, dim,
+                                  dx_out, dim, dgamma, dbeta, rows, dim, eps, stream);
 }
 
 extern "C" int istvt_gelu_fwd(const void* x, void* y, int64_t n, istvt_stream_t stream) {
@@ -622,8 +669,8 @@ extern "C" int istvt_gather_rows(const void* src, void* dst, int64_t n_outer, in
     return launch_status();
 }
 
-extern "C" int istvt_colsum(const void* x, float* colsum, int64_t m, int c, istvt_stream_t stream) {
-    ISTVT_REQUIRE(x && colsum && m > 0 && c > 0 && c % 8 == 0 && c <= 8192);
+extern "C" int istvt_colsum_ld(const void* x, int64_t ld, float* colsum, int64_t m, int c, istvt_stream_t stream) {
+    ISTVT_REQUIRE(x && colsum && m > 0 && c > 0 && c % 8 == 0 && c <= 8192 && ld >= c && ld % 8 == 0);
     const int c8 = c / 8;
     int lanes = 256 / c8;
     if (lanes < 1) lanes = 1;
@@ -634,7 +681,21 @@ extern "C" int istvt_colsum(const void* x, float* colsum, int64_t m, int c, istv
     const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
     colsum_kernel<<<static_cast<unsigned>(blocks), threads, c * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const bf16*>(x), colsum, m, c);
+        static_cast<const bf16*>(x), colsum, m, c, ld);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_colsum(const void* x, float* colsum, int64_t m, int c, istvt_stream_t stream) {
+    return istvt_colsum_ld(x, c, colsum, m, c, stream);
+}
+
+extern "C" int istvt_cast_f32_bf16_rows(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int cols,
+                                        istvt_stream_t stream) {
+    ISTVT_REQUIRE(x && y && rows > 0 && cols > 0 && cols % 4 == 0 && ldx >= cols && ldy >= cols && ldx % 4 == 0 && ldy % 4 == 0);
+    const int64_t n4 = rows * (cols / 4);
+    cast_f32_bf16_rows_kernel<<<nblk(n4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, static_cast<bf16*>(y), ldy, rows, cols / 4);
     count_launch();
     return launch_status();
 }

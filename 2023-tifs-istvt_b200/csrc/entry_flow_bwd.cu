@@ -288,16 +288,16 @@ pool_add_idx_kernel(const bf16* __restrict__ x, const bf16* __restrict__ skip, b
 __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ amax, bf16* __restrict__ dx, int n, int h, int w,
                 int c, int ho, int wo) {
+    // grid = (ceil(w * c/8 / 256), h, n): one 32-bit division per thread (the flat 64-bit index cost three 64-bit
+    // divisions per thread and held the kernel at 1.4 TB/s, profiles/README.md r6f)
     const int c8 = c >> 3;
-    const int64_t total = static_cast<int64_t>(n) * h * w * c8;
-    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int cg = static_cast<int>(idx % c8);
-    int64_t t = idx / c8;
-    const int ix = static_cast<int>(t % w);
-    t /= w;
-    const int iy = static_cast<int>(t % h);
-    const int img = static_cast<int>(t / h);
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;        // ix * c8 + cg
+    if (col >= w * c8) return;
+    const int ix = col / c8;
+    const int cg = col - ix * c8;
+    const int iy = blockIdx.y;
+    const int img = blockIdx.z;
+    const int64_t idx = (static_cast<int64_t>(img) * h + iy) * (static_cast<int64_t>(w) * c8) + col;
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -680,8 +680,9 @@ extern "C" int istvt_pool_bwd(const void* dy, const void* argmax, void* dx, int 
                               istvt_stream_t stream) {
     ISTVT_REQUIRE(dy && argmax && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0);
     const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
-    const int64_t total = static_cast<int64_t>(n) * h * w * (c / 8);
-    pool_bwd_kernel<<<nblk2(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    ISTVT_REQUIRE(h <= 65535 && n <= 65535);
+    const dim3 grid(static_cast<unsigned>((w * (c / 8) + 255) / 256), static_cast<unsigned>(h), static_cast<unsigned>(n));
+    pool_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16*>(dy), static_cast<const uint8_t*>(argmax), static_cast<bf16*>(dx), n, h, w, c, ho, wo);
     count_launch();
     return launch_status();

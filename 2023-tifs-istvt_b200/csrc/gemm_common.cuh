@@ -36,6 +36,11 @@ struct GemmParams {
     // LayerNorm folded around a GEMM pair (CTA-pair kernel, bf16 output, TMA-store epilogue; engine.py, LN2).
     // Row statistics travel as one (sum, M2) pair per row and 64-column group — M2 = sum of squared deviations from the
     // GROUP mean — and are combined with Chan's formula: no atomics (bitwise reproducible), no E[x^2] - mu^2 cancellation.
+    // Training-step fusions of the MLP (CTA-pair kernel, bf16 output, TMA-store epilogue):
+    void* C2;                // ff1: second output, the PRE-activation acc + bias (bf16 [M, N], pitch ldc2) next to
+    int64_t ldc2;            //      C = act(acc + bias): replaces the stand-alone GELU pass of the training forward
+    const void* mul_pre;     // ff2 data gradient: C = acc * gelu'(mul_pre[m, n]) (bf16 [M, N], pitch ld_pre): replaces
+    int64_t ld_pre;          //      the stand-alone GELU backward pass
     float2* row_stats_out;   // producer: fp32 [M, ceil(N / 64), 2], every slot written exactly once
     const float2* ln_stats;  // consumer: (mu, rstd) of ITS A rows, fp32 [M, 2];  C = rstd_m (acc - mu_m ln_c[n]) + ln_d[n]
     const float* ln_c;       //   fp32 [N]: row sums of the gamma-folded bf16 weight
@@ -221,9 +226,14 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
 // BOXC = 64: both 32-column halves are staged in one 4 KB slab (128-byte rows, SWIZZLE_128B) and leave as ONE box —
 // half as many box rows for the TMA unit, which serves the operand fills of the same CTA (profiles/README.md r6m: the
 // TMA stores, not the TMEM reads, the math or the staging, are what the epilogue costs the main loop).
-template <int BOXC = 32, typename F>
-__device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, const CUtensorMap* tm_c, uint32_t taddr,
-                                                          uint32_t slab, int row0, int n0, int lane, F after_tmem_reads) {
+// DUAL (BOXC = 32, 4 KB slab): the pre-activation goes out through `tm_c2` from the slab's first half and the activated
+// value through `tm_c` from its second half (GemmParams::C2).  MULPRE: the accumulator is multiplied by gelu'(mul_pre).
+// Both are compile-time so that the inference instantiations keep their register budget (102 at 640 threads).
+template <int BOXC = 32, bool DUAL = false, bool MULPRE = false, typename F>
+__device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, const CUtensorMap* tm_c,
+                                                          const CUtensorMap* tm_c2, uint32_t taddr, uint32_t slab,
+                                                          int row0, int n0, int lane, F after_tmem_reads) {
+    static_assert(!DUAL || BOXC == 32, "dual output stages two 32-column boxes");
     if (n0 >= p.N) {
         after_tmem_reads();
         return;
@@ -264,6 +274,15 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
         for (int q = 0; q < 8; ++q)
             bv[q] = (bsrc != nullptr && nb + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4*>(bsrc + nb) + q)
                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        // ff2 data gradient: the pre-activations under this lane's 32 accumulator columns (64 contiguous bytes)
+        [[maybe_unused]] uint4 pre[MULPRE ? 4 : 1];
+        if constexpr (MULPRE) {
+            const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.mul_pre) +
+                                                              static_cast<int64_t>(row0 + lane) * p.ld_pre + nb);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                pre[g] = (row_ok && nb + 8 * g < p.N) ? __ldg(src + g) : make_uint4(0u, 0u, 0u, 0u);
+        }
         tmem_ld_wait();
         if (hh == 1) after_tmem_reads();
 #ifdef ISTVT_GEMM_TRACE
@@ -276,11 +295,20 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
         }
 #endif
         uint32_t o[16];
+        [[maybe_unused]] uint32_t o_pre[DUAL ? 16 : 1];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {     // 8 columns -> one 16-byte chunk
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+            if constexpr (MULPRE) {
+                const uint32_t w[4] = {pre[g].x, pre[g].y, pre[g].z, pre[g].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[2 * j] *= gelu_grad_fast(__uint_as_float(w[j] << 16));
+                    v[2 * j + 1] *= gelu_grad_fast(__uint_as_float(w[j] & 0xffff0000u));
+                }
+            }
             if (p.ln_stats != nullptr) {
                 float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
                 if (nb + 8 * g < p.N) {
@@ -294,6 +322,10 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
             } else {
                 v[0] += bv[2 * g].x; v[1] += bv[2 * g].y; v[2] += bv[2 * g].z; v[3] += bv[2 * g].w;
                 v[4] += bv[2 * g + 1].x; v[5] += bv[2 * g + 1].y; v[6] += bv[2 * g + 1].z; v[7] += bv[2 * g + 1].w;
+            }
+            if constexpr (DUAL) {
+                o_pre[4 * g] = pack_bf16x2(v[0], v[1]); o_pre[4 * g + 1] = pack_bf16x2(v[2], v[3]);
+                o_pre[4 * g + 2] = pack_bf16x2(v[4], v[5]); o_pre[4 * g + 3] = pack_bf16x2(v[6], v[7]);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = epi_act(v[j], p.act);
@@ -328,7 +360,13 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-            sts_u4(wrow + (((BOXC == 64 ? hh * 4 + g : g) ^ wsw) << 4), o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+            sts_u4(wrow + (DUAL ? 2048 : 0) + (((BOXC == 64 ? hh * 4 + g : g) ^ wsw) << 4), o[4 * g], o[4 * g + 1],
+                   o[4 * g + 2], o[4 * g + 3]);
+        if constexpr (DUAL) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                sts_u4(wrow + ((g ^ wsw) << 4), o_pre[4 * g], o_pre[4 * g + 1], o_pre[4 * g + 2], o_pre[4 * g + 3]);
+        }
         if (BOXC == 64 && hh == 0 && nb + 32 < p.N) continue;      // the box leaves after the second half
         fence_proxy_async_smem();
         __syncwarp();
@@ -336,7 +374,8 @@ __device__ __forceinline__ void gemm_epilogue_tma_bf16_64(const GemmParams& p, c
         if (tmode == 3) continue;
 #endif
         if (lane == 0) {
-            tma_store_2d(tm_c, slab, BOXC == 64 ? n0 : nb, row0);
+            if constexpr (DUAL) tma_store_2d(tm_c2, slab, nb, row0);
+            tma_store_2d(tm_c, slab + (DUAL ? 2048 : 0), BOXC == 64 ? n0 : nb, row0);
             tma_store_commit();
         }
     }

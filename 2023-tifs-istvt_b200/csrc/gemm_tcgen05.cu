@@ -414,6 +414,36 @@ extern "C" int istvt_gemm_lnfold_fwd(const void* a, int64_t lda, const void* w, 
     return gemm_bf16_dispatch(a, m, lda, w, ldw, k, p, static_cast<cudaStream_t>(stream));
 }
 
+// MLP fusions of the training step (see include/istvt_b200.h)
+extern "C" int istvt_gemm_act_dual_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c_act, int64_t ldc,
+                                       void* c_pre, int64_t ldc_pre, int64_t m, int n, int k, const float* bias, int act,
+                                       istvt_stream_t stream) {
+    ISTVT_REQUIRE(c_pre != nullptr && n >= 256 && (ldc * 2) % 16 == 0 && (ldc_pre * 2) % 16 == 0);
+    ISTVT_REQUIRE((reinterpret_cast<uintptr_t>(c_pre) & 15) == 0);
+    ISTVT_REQUIRE(act >= ISTVT_ACT_NONE && act <= ISTVT_ACT_GELU);
+    GemmParams p{};
+    p.M = m; p.N = n; p.K = k;
+    p.taps = 1;
+    p.C = c_act; p.ldc = ldc;
+    p.C2 = c_pre; p.ldc2 = ldc_pre;
+    p.bias = bias;
+    p.act = act;
+    return gemm_bf16_dispatch(a, m, lda, w, ldw, k, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int istvt_gemm_dgelu_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c, int64_t ldc,
+                                    const void* pre, int64_t ld_pre, int64_t m, int n, int k, istvt_stream_t stream) {
+    ISTVT_REQUIRE(pre != nullptr && n >= 256 && (ldc * 2) % 16 == 0 && ld_pre % 8 == 0 && ld_pre >= n);
+    ISTVT_REQUIRE((reinterpret_cast<uintptr_t>(pre) & 15) == 0);
+    GemmParams p{};
+    p.M = m; p.N = n; p.K = k;
+    p.taps = 1;
+    p.C = c; p.ldc = ldc;
+    p.mul_pre = pre; p.ld_pre = ld_pre;
+    p.act = ISTVT_ACT_NONE;
+    return gemm_bf16_dispatch(a, m, lda, w, ldw, k, p, static_cast<cudaStream_t>(stream));
+}
+
 // split-K plan shared by the two weight-gradient entry points
 static void plan_splitk(GemmParams& p, int64_t m, int n) {
     const int num_kb = (p.K + 63) / 64;

@@ -44,7 +44,9 @@ constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 // epilogue modes: bf16 output without residual / generic (fp32 output, residual through registers, split-K) /
 // in-place fp32 residual update by TMA reduce-add
 // in-place fp32 residual update by TMA reduce-add / bf16 output whose TMA-store boxes are 64 columns (128 bytes) wide
-constexpr int EPI_PLAIN = 0, EPI_GENERIC = 1, EPI_REDUCE = 2, EPI_PLAIN128 = 3;
+// EPI_DUAL: bf16 output twice (pre-activation and activated), two 32-column boxes per half from a 4 KB slab
+// EPI_DGELU: EPI_PLAIN128 whose accumulator is multiplied by gelu'(mul_pre) first
+constexpr int EPI_PLAIN = 0, EPI_GENERIC = 1, EPI_REDUCE = 2, EPI_PLAIN128 = 3, EPI_DUAL = 4, EPI_DGELU = 5;
 template <int EW, int EPI> struct G2Cfg {
     static constexpr int THREADS = 128 + EW * 32;
     static constexpr int SLAB = EPI == EPI_PLAIN ? EPI_SLAB_PLAIN_BYTES : EPI_SLAB_BYTES;   // PLAIN128: 32 rows x 128 B
@@ -90,8 +92,9 @@ struct TileIter {
 template <int EW, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Cfg<EW, EPI>::THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                         const __grid_constant__ CUtensorMap tm_c, const GemmParams p) {
-    constexpr bool PLAIN_BF16 = EPI == EPI_PLAIN || EPI == EPI_PLAIN128;
+                         const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_c2,
+                         const GemmParams p) {
+    constexpr bool PLAIN_BF16 = EPI == EPI_PLAIN || EPI == EPI_PLAIN128 || EPI == EPI_DUAL || EPI == EPI_DGELU;
     using Cfg = G2Cfg<EW, EPI>;
     constexpr int G2_STAGES = Cfg::STAGES;
     constexpr int G2_EPI_WARPS = EW;
@@ -285,6 +288,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             const int drow_lane = m < p.M ? static_cast<int>(m) : -1;
             epilogue_rows(drow_lane, lane, drow_t);
             if constexpr (EPI == EPI_GENERIC) epilogue_prefetch_residual(p, drow_lane, n_blk * G2_BN + colw, EPI_COLS * PASSES);
+            if (EPI == EPI_DGELU && drow_lane >= 0) {
+                // ff2 data gradient: this lane's 64 pre-activations of the tile (128 bytes) into L2 before the wait
+                const int nf = n_blk * G2_BN + colw;
+                for (int n = nf; n < nf + EPI_COLS * PASSES && n < p.N; n += 32)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const __nv_bfloat16*>(p.mul_pre) +
+                                                                  static_cast<int64_t>(drow_lane) * p.ld_pre + n));
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             ISTVT_TRACE(tracer, trace_it, 5);
@@ -315,8 +325,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
                                             static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32),
                                             n_blk * G2_BN + col0, lane, release);
                 else if (PLAIN_BF16 && p.epi_tma)
-                    gemm_epilogue_tma_bf16_64<EPI == EPI_PLAIN128 ? 64 : 32>(
-                        p, &tm_c, taddr, slab, static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32),
+                    gemm_epilogue_tma_bf16_64<(EPI == EPI_PLAIN128 || EPI == EPI_DGELU) ? 64 : 32, EPI == EPI_DUAL, EPI == EPI_DGELU>(
+                        p, &tm_c, &tm_c2, taddr, slab,
+                        static_cast<int>(m_blk * (2 * GEMM_BLOCK_M) + rank * GEMM_BLOCK_M + quad * 32),
                         n_blk * G2_BN + col0, lane, release);
                 else
                     gemm_epilogue_64<PLAIN_BF16>(p, taddr, slab, drow_lane, drow_t, n_blk * G2_BN + col0, lane, release);
@@ -427,7 +438,19 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
     // ISTVT_G2_STORE128=0: 32-column store boxes (2 KB slabs, six ring stages) instead of 64-column ones (4 KB slabs,
     // five stages) — A/B measurements
     static const bool store128_env = []() { const char* e = getenv("ISTVT_G2_STORE128"); return !e || atoi(e) != 0; }();
-    const bool store128 = p.epi_tma && store128_env;
+    const bool dual = p.C2 != nullptr;
+    if (dual && !(p.epi_tma && (p.ldc2 * 2) % 16 == 0)) return ISTVT_ERR_UNSUPPORTED;
+    const bool dgelu = p.mul_pre != nullptr;
+    if (dgelu && (!p.epi_tma || dual)) return ISTVT_ERR_UNSUPPORTED;
+    const bool store128 = p.epi_tma && (store128_env || dgelu) && !dual;
+    CUtensorMap tm_c2 = tm_a;    // placeholder unless dual
+    if (dual) {
+        const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
+        const uint64_t strides[1] = {static_cast<uint64_t>(p.ldc2) * 2};
+        const uint32_t box[2] = {32, 32};
+        int rc = encode_tmap(&tm_c2, p.C2, ISTVT_BF16, 2, dims, strides, box, 2);
+        if (rc != ISTVT_OK) return rc;
+    }
     if (p.epi_tma) {
         const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
         const uint64_t strides[1] = {static_cast<uint64_t>(p.ldc) * 2};
@@ -442,10 +465,14 @@ static int launch_gemm_2cta_maps(const CUtensorMap& tm_a, const CUtensorMap& tm_
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<EWV, EPIV>,                                 \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<EWV, EPIV>::SMEM_BYTES)); \
         gemm_tcgen05_2cta_kernel<EWV, EPIV><<<grid, G2Cfg<EWV, EPIV>::THREADS, G2Cfg<EWV, EPIV>::SMEM_BYTES, stream>>>(   \
-            tm_a, tm_b, tm_c, p);                                                                                  \
+            tm_a, tm_b, tm_c, tm_c2, p);                                                                           \
     } while (0)
     if (reduce) {
         ISTVT_G2_LAUNCH(16, EPI_REDUCE);
+    } else if (dual) {
+        ISTVT_G2_LAUNCH(16, EPI_DUAL);
+    } else if (dgelu) {
+        ISTVT_G2_LAUNCH(16, EPI_DGELU);
     } else if (ew == 16) {
         if (store128) ISTVT_G2_LAUNCH(16, EPI_PLAIN128);
         else if (plain) ISTVT_G2_LAUNCH(16, EPI_PLAIN);

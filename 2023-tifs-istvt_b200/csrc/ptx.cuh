@@ -425,4 +425,22 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
     return fmaf(h, erf_x, h);
 }
 
+// gelu'(x) = Phi(x) + x phi(x) with the same erf approximation (one rcp, one ex2): the factor the ff2 data-gradient GEMM
+// applies in its epilogue (istvt_gemm_dgelu_fwd) and the stand-alone istvt_gelu_bwd kernel.
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(z, 0.3275911f, 1.0f)));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));   // exp(-x^2 / 2)
+    const float erf_abs = fmaf(-p, e, 1.0f);
+    const float cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
+    return fmaf(x, 0.3989422804014327f * e, cdf);
+}
+
 }  // namespace istvt

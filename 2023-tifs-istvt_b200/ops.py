@@ -6,6 +6,7 @@ stream to libistvt_b200.so.  Non-CUDA tensors are rejected (there is no CPU path
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -14,6 +15,7 @@ from . import _lib
 
 BF16, F32 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+_ROW_PITCH = os.environ.get("ISTVT_ROW_PITCH", "1") != "0"      # 0: every matrix dense (A/B measurements)
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -83,7 +85,7 @@ def row_pitch(dim: int, dtype: torch.dtype = torch.bfloat16) -> int:
     Rows that already start on 64-byte boundaries are left alone (dim 2912: a 128-byte box row then spans two lines
     on odd rows but the same four 32-byte sectors; padding to 2944 measured +1 % on A and -3 % on W, r6n)."""
     size = torch.empty((), dtype=dtype).element_size()
-    if dim * size % 64 == 0:
+    if dim * size % 64 == 0 or not _ROW_PITCH:
         return dim
     per_line = 128 // size
     return (dim + per_line - 1) // per_line * per_line
@@ -262,6 +264,43 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
                                                      _ptr(bias), _ptr(residual),
                                                      _ld(residual) if residual is not None else n, act, st),
                        "istvt_gemm_f32_fwd")
+    return out
+
+
+def gemm_act_dual(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_GELU
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(act(a . w^T + bias), a . w^T + bias), both bf16 [rows, N], from one accumulator (istvt_gemm_act_dual_fwd): the
+    training forward of FeedForward.net[0:2] keeps the pre-activation for the backward without a GELU pass."""
+    dev = _chk(bias) if bias is not None else a.device
+    _chk_rows(a, w)
+    k = a.shape[-1]
+    m = a.numel() // k
+    n = w.shape[0]
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or w.shape[1] != k:
+        raise ValueError("gemm_act_dual: bf16 a [M, K] and w [N, K]")
+    out = torch.empty(*a.shape[:-1], n, dtype=torch.bfloat16, device=dev)
+    pre = torch.empty(*a.shape[:-1], n, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "gemm_bf16", 2.0 * m * n * k, _nbytes(a, w, out, pre)):
+        _lib.check(_lib.lib().istvt_gemm_act_dual_fwd(_ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(out), n, _ptr(pre), n, m, n, k,
+                                                      _ptr(bias), act, _stream(dev)), "istvt_gemm_act_dual_fwd")
+    return out, pre
+
+
+def gemm_dgelu(a: torch.Tensor, w: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    """(a . w^T) o gelu'(pre), bf16 [rows, N] (istvt_gemm_dgelu_fwd): the data gradient through FeedForward.net[3] and
+    the GELU in one kernel."""
+    dev = a.device
+    _chk_rows(a, w, pre)
+    k = a.shape[-1]
+    m = a.numel() // k
+    n = w.shape[0]
+    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or w.shape[1] != k or pre.dtype != torch.bfloat16 or \
+            pre.numel() != m * n:
+        raise ValueError("gemm_dgelu: bf16 a [M, K], w [N, K], pre [M, N]")
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "gemm_bf16", 2.0 * m * n * k, _nbytes(a, w, out, pre)):
+        _lib.check(_lib.lib().istvt_gemm_dgelu_fwd(_ptr(a), _ld(a), _ptr(w), _ld(w), _ptr(out), n, _ptr(pre), _ld(pre), m, n,
+                                                   k, _stream(dev)), "istvt_gemm_dgelu_fwd")
     return out
 
 
@@ -617,16 +656,25 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dgamma
                   dy2: Optional[torch.Tensor] = None, frames: int = 0, tokens_per_frame: int = 0,
                   eps: float = 1e-5) -> Optional[torch.Tensor]:
     """Returns dx (bf16) unless `g_accum` (fp32, += dx) is given."""
-    dev = _chk(dy, x, gamma, dgamma, dbeta, g_accum, g_bf16, dy2)
+    dev = _chk(gamma, dgamma, dbeta)
+    _chk_rows(dy, x, g_accum, g_bf16, dy2)
     dim = x.shape[-1]
     rows = x.numel() // dim
     if dy.dtype != torch.bfloat16 or dy.numel() != x.numel():
         raise ValueError("layernorm_bwd: dy must be bf16 with x's shape")
-    dx = None if g_accum is not None else torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
+    if dy2 is not None and _ld(dy2) != _ld(dy):
+        raise ValueError("layernorm_bwd: dy and dy2 must have the same row pitch")
+    # dx is the A operand of the next GEMM / weight-gradient GEMM: 128-byte aligned row pitch when dy has one
+    dx = None
+    if g_accum is None:
+        dx = empty_rows((rows, dim), torch.bfloat16, dev) if _ld(dy) != dim else torch.empty(rows, dim, dtype=torch.bfloat16,
+                                                                                             device=dev)
     with _launch(dev, "layernorm_bwd", 0.0, _nbytes(dy, x, dx, dy2, g_bf16) + 2 * _nbytes(g_accum)):
-        _lib.check(_lib.lib().istvt_layernorm_bwd(_ptr(dy), _ptr(dy2), frames, tokens_per_frame, _ptr(x), _dt(x),
-                                                  _ptr(gamma), _ptr(g_accum), _ptr(g_bf16), _ptr(dx), _ptr(dgamma),
-                                                  _ptr(dbeta), rows, dim, eps, _stream(dev)), "istvt_layernorm_bwd")
+        _lib.check(_lib.lib().istvt_layernorm_bwd_ld(
+            _ptr(dy), _ptr(dy2), _ld(dy), frames, tokens_per_frame, _ptr(x), _dt(x), _ld(x), _ptr(gamma), _ptr(g_accum),
+            _ld(g_accum) if g_accum is not None else dim, _ptr(g_bf16), _ld(g_bf16) if g_bf16 is not None else dim,
+            _ptr(dx), _ld(dx) if dx is not None else dim, _ptr(dgamma), _ptr(dbeta), rows, dim, eps, _stream(dev)),
+            "istvt_layernorm_bwd_ld")
     return dx
 
 
@@ -647,24 +695,31 @@ def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 
 
 def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    dev = _chk(x, out)
+    """fp32 -> bf16; `out` (or x) may be a row-pitched matrix (ops.empty_rows)."""
+    dev = _chk_rows(x, out)
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=dev)
     with _launch(dev, "cast", 0.0, _nbytes(x, out)):
-        _lib.check(_lib.lib().istvt_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream(dev)), "istvt_cast_f32_bf16")
+        if x.is_contiguous() and out.is_contiguous():
+            _lib.check(_lib.lib().istvt_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream(dev)), "istvt_cast_f32_bf16")
+        else:
+            cols = x.shape[-1]
+            _lib.check(_lib.lib().istvt_cast_f32_bf16_rows(_ptr(x), _ld(x), _ptr(out), _ld(out), x.numel() // cols, cols,
+                                                           _stream(dev)), "istvt_cast_f32_bf16_rows")
     return out
 
 
-def transpose(x: torch.Tensor, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x: bf16 [M, C] -> bf16 [C, ld] with ld = M rounded up to 8 (pad zero); colsum (fp32 [C]) += column sums."""
+def transpose(x: torch.Tensor, colsum: Optional[torch.Tensor] = None, aligned: bool = False) -> torch.Tensor:
+    """x: bf16 [M, C] -> bf16 [C, ld] with ld = M rounded up to 8 (pad zero); colsum (fp32 [C]) += column sums.
+    aligned: ld = the 128-byte aligned row pitch of M instead (the result is a GEMM operand with K = M)."""
     dev = _chk(x, colsum)
     m, c = x.shape
-    ld = (m + 7) // 8 * 8
+    ld = max(row_pitch(m), (m + 7) // 8 * 8) if aligned else (m + 7) // 8 * 8
     out = torch.empty(c, ld, dtype=torch.bfloat16, device=dev)
     with _launch(dev, "transpose", 0.0, 2 * _nbytes(x)):
         _lib.check(_lib.lib().istvt_transpose_colsum(_ptr(x), _ptr(out), _ptr(colsum), m, c, ld, _stream(dev)),
                    "istvt_transpose_colsum")
-    return out
+    return out[:, :m] if aligned and ld != m else out
 
 
 def gemm_wgrad(dyt: torch.Tensor, xt: torch.Tensor, rows: int, dw: torch.Tensor) -> None:
@@ -876,25 +931,27 @@ def gather_rows(src: torch.Tensor, n_outer: int, outer_stride: int, rows: int, r
 
 def colsum(x: torch.Tensor, out: torch.Tensor) -> None:
     """out (fp32 [C]) += column sums of x (bf16 [M, C])."""
-    dev = _chk(x, out)
+    dev = _chk(out)
+    _chk_rows(x)
     m, c = x.shape
     with _launch(dev, "colsum", 0.0, _nbytes(x)):
-        _lib.check(_lib.lib().istvt_colsum(_ptr(x), _ptr(out), m, c, _stream(dev)), "istvt_colsum")
+        _lib.check(_lib.lib().istvt_colsum_ld(_ptr(x), _ld(x), _ptr(out), m, c, _stream(dev)), "istvt_colsum_ld")
 
 
 def wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, bias_grad: Optional[torch.Tensor] = None) -> None:
     """dw[N, K] (fp32) += dy[rows, N]^T x[rows, K]; bias_grad (fp32 [N]) += column sums of dy.
     Operands are read in place (MN-major tcgen05 tiles); tiny problems (rows <= 64) take the transposed-copy path."""
-    dev = _chk(dy, x, dw, bias_grad)
+    dev = _chk(dw, bias_grad)
+    _chk_rows(dy, x)
     rows, n = dy.shape
     k = x.shape[1]
     if x.shape[0] != rows or dw.numel() != n * k or dw.dtype != torch.float32:
         raise ValueError("wgrad: operand shapes do not match")
     if rows <= 64:
-        gemm_wgrad(transpose(dy, colsum=bias_grad), transpose(x), rows, dw)
+        gemm_wgrad(transpose(dy.contiguous(), colsum=bias_grad), transpose(x.contiguous()), rows, dw)
         return
     if bias_grad is not None:
         colsum(dy, bias_grad)
     with _launch(dev, "gemm_wgrad", 2.0 * n * k * rows, _nbytes(dy, x) + 2 * _nbytes(dw)):
-        _lib.check(_lib.lib().istvt_gemm_wgrad_accum(_ptr(dy), n, _ptr(x), k, _ptr(dw), k, rows, n, k, _stream(dev)),
-                   "istvt_gemm_wgrad_accum")
+        _lib.check(_lib.lib().istvt_gemm_wgrad_accum(_ptr(dy), _ld(dy), _ptr(x), _ld(x), _ptr(dw), k, rows, n, k,
+                                                     _stream(dev)), "istvt_gemm_wgrad_accum")

@@ -21,6 +21,7 @@ Weight gradients are split-K tcgen05 GEMMs that read dY and X in place as MN-maj
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
 
@@ -31,6 +32,7 @@ from . import ops
 from .engine import pack_entry, run_entry_flow
 
 BF16 = torch.bfloat16
+_MLP_FUSE = os.environ.get("ISTVT_MLP_FUSE", "1") != "0"      # 0: stand-alone GELU forward / backward passes (A/B)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -139,8 +141,13 @@ def _pack_layers(vit, mirror: Optional[Dict[str, torch.Tensor]] = None) -> List[
                                ("so", attn_s.fn.to_out[0], f"{pre}.1.fn.to_out.0"), ("1", ff.fn.net[0], f"{pre}.2.fn.net.0"),
                                ("2", ff.fn.net[3], f"{pre}.2.fn.net.3")):
             w = bf16_weight(lin.weight, mirror, name + ".weight")
-            setattr(L, "w_" + key, w)
-            setattr(L, "wT_" + key, ops.transpose(w))
+            # GEMM operands whose K rows are not 64-byte aligned (K = 728) sit at the 128-byte aligned pitch: the forward
+            # weight as a pitched cast of the fp32 master, the transposed weight through the transpose kernel's ldo
+            wf = w
+            if ops.row_pitch(w.shape[1]) != w.shape[1]:
+                wf = ops.cast_bf16(f32(lin.weight), out=ops.empty_rows(tuple(w.shape), BF16, w.device))
+            setattr(L, "w_" + key, wf)
+            setattr(L, "wT_" + key, ops.transpose(w, aligned=True))
             if lin.bias is not None:
                 setattr(L, "b_" + key, f32(lin.bias))
         L.ln1 = (f32(attn_t.norm.weight), f32(attn_t.norm.bias))
@@ -175,25 +182,32 @@ def transformer_forward_train(vit, layers: List[SimpleNamespace], tokens: torch.
     heads = vit.heads
     scale = 64 ** -0.5
     f32 = ops.f32_aligned
+    act = lambda: ops.empty_rows((rows, d), BF16, tokens.device)
+    act4 = lambda: ops.empty_rows((b, f, p, d), BF16, tokens.device)
     ctxs = []
     x = tokens
     for L in layers:
         c = SimpleNamespace()
         c.x0 = x
-        c.xn, c.diff = ops.layernorm_diff(x, L.ln1[0], L.ln1[1], BF16)
-        c.qk = ops.gemm(c.diff.view(rows, d), L.w_qk)
-        c.v = ops.gemm(c.xn.view(rows, d), L.w_v)
+        # every bf16 [rows, 728] activation is a GEMM / weight-gradient operand: 128-byte aligned row pitch (act())
+        c.xn, c.diff = ops.layernorm_diff(x, L.ln1[0], L.ln1[1], BF16, out=(act4(), act4()))
+        c.xn, c.diff = c.xn.view(rows, d), c.diff.view(rows, d)
+        c.qk = ops.gemm(c.diff, L.w_qk)
+        c.v = ops.gemm(c.xn, L.w_v)
         c.at, _ = ops.attn_temporal(c.qk, c.v, b, f, p, heads, scale)
-        c.y1 = ops.gemm(c.at, L.w_to, bias=L.b_to, out_dtype=BF16)
-        c.yn = ops.layernorm(c.y1, L.ln2[0], L.ln2[1], BF16)
+        c.y1 = ops.gemm(c.at, L.w_to, bias=L.b_to, out=act())
+        c.yn = ops.layernorm(c.y1, L.ln2[0], L.ln2[1], BF16, out=act())
         c.qkv = ops.gemm(c.yn, L.w_qkv)
         c.as_, c.lse = ops.attn_spatial_lse(c.qkv, b * f, p, heads, scale)
         x1 = torch.empty_like(x)
         ops.gemm(c.as_, L.w_so, bias=L.b_so, residual=x.view(rows, d), out=x1.view(rows, d))
         c.x1 = x1
-        c.zn = ops.layernorm(x1.view(rows, d), L.ln3[0], L.ln3[1], BF16)
-        c.hpre = ops.gemm(c.zn, L.w_1, bias=L.b_1, out_dtype=BF16)
-        c.hid = ops.gelu(c.hpre)
+        c.zn = ops.layernorm(x1.view(rows, d), L.ln3[0], L.ln3[1], BF16, out=act())
+        if _MLP_FUSE:      # GELU in ff1's epilogue, both the activated value and the pre-activation are written
+            c.hid, c.hpre = ops.gemm_act_dual(c.zn, L.w_1, L.b_1, ops.ACT_GELU)
+        else:
+            c.hpre = ops.gemm(c.zn, L.w_1, bias=L.b_1, out_dtype=BF16)
+            c.hid = ops.gelu(c.hpre)
         x2 = torch.empty_like(x)
         ops.gemm(c.hid, L.w_2, bias=L.b_2, residual=x1.view(rows, d), out=x2.view(rows, d))
         x = x2
@@ -237,7 +251,8 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
                  head.w, g, G["vit.transformer.norm.weight"], G["vit.transformer.norm.bias"],
                  G["vit.mlp_head.0.weight"], G["vit.mlp_head.0.bias"], G["vit.mlp_head.1.weight"].view(-1)[:d],
                  G["vit.mlp_head.1.bias"])
-    g_bf = ops.cast_bf16(g2)
+    act = lambda: ops.empty_rows((rows, d), BF16, g.device)      # bf16 [rows, 728] operands at the aligned row pitch
+    g_bf = ops.cast_bf16(g2, out=act())
     scratch = torch.empty(rows, heads * 64, dtype=torch.float32, device=g.device)
     for li in range(len(layers) - 1, -1, -1):
         L, c = layers[li], ctxs[li]
@@ -250,11 +265,12 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
             continue
         # ---- MLP (module.py:27-34) ----
         ops.wgrad(g_bf, c.hid, N["w_2"], bias_grad=N["b_2"])
-        dhid = ops.gemm(g_bf, L.wT_2)
-        dhpre = ops.gelu_bwd(dhid, c.hpre)
-        del dhid
+        if _MLP_FUSE:      # gelu'(hpre) applied in the data-gradient GEMM's epilogue
+            dhpre = ops.gemm_dgelu(g_bf, L.wT_2, c.hpre)
+        else:
+            dhpre = ops.gelu_bwd(ops.gemm(g_bf, L.wT_2), c.hpre)
         ops.wgrad(dhpre, c.zn, N["w_1"], bias_grad=N["b_1"])
-        dzn = ops.gemm(dhpre, L.wT_1)
+        dzn = ops.gemm(dhpre, L.wT_1, out=act())
         del dhpre
         ops.layernorm_bwd(dzn, c.x1.view(rows, d), L.ln3[0], N["ln3_w"], N["ln3_b"], g_accum=g2, g_bf16=g_bf)
         del dzn
@@ -264,7 +280,7 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
         dqkv = ops.attn_spatial_bwd(c.qkv, c.as_, das, c.lse, b * f, p, heads, scale, scratch)
         del das
         ops.wgrad(dqkv, c.yn, N["w_qkv"])
-        dyn = ops.gemm(dqkv, L.wT_qkv)
+        dyn = ops.gemm(dqkv, L.wT_qkv, out=act())
         del dqkv
         dy1 = ops.layernorm_bwd(dyn, c.y1, L.ln2[0], N["ln2_w"], N["ln2_b"])
         del dyn
@@ -274,10 +290,10 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
         del dy1
         dqk, dv = ops.attn_temporal_bwd(c.qk, c.v, dat, b, f, p, heads, scale)
         del dat
-        ops.wgrad(dqk, c.diff.view(rows, d), N["w_qk"])
-        ops.wgrad(dv, c.xn.view(rows, d), N["w_v"])
-        ddiff = ops.gemm(dqk, L.wT_qk)
-        dxn_v = ops.gemm(dv, L.wT_v)
+        ops.wgrad(dqk, c.diff, N["w_qk"])
+        ops.wgrad(dv, c.xn, N["w_v"])
+        ddiff = ops.gemm(dqk, L.wT_qk, out=act())
+        dxn_v = ops.gemm(dv, L.wT_v, out=act())
         del dqk, dv
         ops.layernorm_bwd(dxn_v, c.x0.view(rows, d), L.ln1[0], N["ln1_w"], N["ln1_b"], g_accum=g2, g_bf16=g_bf,
                           dy2=ddiff, frames=f, tokens_per_frame=p)
@@ -289,8 +305,9 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
 def _transformer_layer_backward_acts(L, c, N, g2, g_bf, scratch, b, f, p, d, heads, scale, relevance, li) -> None:
     """One block's backward without the weight-gradient GEMMs (same data path as transformer_backward)."""
     rows = b * f * p
-    dhpre = ops.gelu_bwd(ops.gemm(g_bf, L.wT_2), c.hpre)
-    dzn = ops.gemm(dhpre, L.wT_1)
+    act = lambda: ops.empty_rows((rows, d), BF16, g2.device)
+    dhpre = ops.gemm_dgelu(g_bf, L.wT_2, c.hpre) if _MLP_FUSE else ops.gelu_bwd(ops.gemm(g_bf, L.wT_2), c.hpre)
+    dzn = ops.gemm(dhpre, L.wT_1, out=act())
     del dhpre
     ops.layernorm_bwd(dzn, c.x1.view(rows, d), L.ln3[0], N["ln3_w"], N["ln3_b"], g_accum=g2, g_bf16=g_bf)
     del dzn
@@ -298,15 +315,15 @@ def _transformer_layer_backward_acts(L, c, N, g2, g_bf, scratch, b, f, p, d, hea
     cam_s = relevance.spatial_buffer() if relevance is not None else None
     dqkv = ops.attn_spatial_bwd(c.qkv, c.as_, das, c.lse, b * f, p, heads, scale, scratch, cam=cam_s)
     del das
-    dy1 = ops.layernorm_bwd(ops.gemm(dqkv, L.wT_qkv), c.y1, L.ln2[0], N["ln2_w"], N["ln2_b"])
+    dy1 = ops.layernorm_bwd(ops.gemm(dqkv, L.wT_qkv, out=act()), c.y1, L.ln2[0], N["ln2_w"], N["ln2_b"])
     del dqkv
     dat = ops.gemm(dy1, L.wT_to)
     del dy1
     cam_t = relevance.temporal_buffer() if relevance is not None else None
     dqk, dv = ops.attn_temporal_bwd(c.qk, c.v, dat, b, f, p, heads, scale, cam=cam_t)
     del dat
-    ddiff = ops.gemm(dqk, L.wT_qk)
-    dxn_v = ops.gemm(dv, L.wT_v)
+    ddiff = ops.gemm(dqk, L.wT_qk, out=act())
+    dxn_v = ops.gemm(dv, L.wT_v, out=act())
     del dqk, dv
     ops.layernorm_bwd(dxn_v, c.x0.view(rows, d), L.ln1[0], N["ln1_w"], N["ln1_b"], g_accum=g2, g_bf16=g_bf,
                       dy2=ddiff, frames=f, tokens_per_frame=p)

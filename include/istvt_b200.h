@@ -95,6 +95,19 @@ int istvt_gemm_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void*
                    istvt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * MLP fusions of the training step (FeedForward, module.py:27-34; train_CNN.py:532 `loss.backward()`), CTA-pair kernel,
+ * bf16, n >= 256:
+ *   istvt_gemm_act_dual_fwd: c_pre = A W^T + bias (what the backward of the activation needs) AND c_act = act(c_pre)
+ *     (the next Linear's operand) from one accumulator — no stand-alone GELU pass in the training forward;
+ *   istvt_gemm_dgelu_fwd:    c = (A W^T) o gelu'(pre) — the data gradient of the second Linear multiplied by the
+ *     activation's derivative in the epilogue (pre: bf16 [m, n], pitch ld_pre) — no stand-alone GELU backward pass.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_gemm_act_dual_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c_act, int64_t ldc, void* c_pre,
+                            int64_t ldc_pre, int64_t m, int n, int k, const float* bias, int act, istvt_stream_t stream);
+int istvt_gemm_dgelu_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c, int64_t ldc, const void* pre,
+                         int64_t ld_pre, int64_t m, int n, int k, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * LayerNorm folded around a pair of GEMMs:  Z = LN(Y) W2^T  with  Y = A W1^T + b1  computed WITHOUT the LN pass.
  * Replaces: PreNorm of the spatial attention, module.py:15-21 on vivit.py:93,99 — `norm(y1)` between the temporal
  * attention's to_out (module.py:185-188,206) and the spatial to_qkv (module.py:74,83).  LN's input is the bf16 GEMM
@@ -307,6 +320,12 @@ int istvt_attn_temporal_bwd(const void* qk, const void* v, const void* dout, voi
 int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, int tokens_per_frame, const void* x, int x_dtype,
                         const float* gamma, float* g_accum, void* g_bf16, void* dx_out, float* dgamma, float* dbeta,
                         int64_t rows, int dim, float eps, istvt_stream_t stream);
+/* The same with row pitches (elements, >= dim, % 4 == 0): ld_dy of dy AND dy2, ld_x of x, ld_g of g_accum, ld_gb of
+ * g_bf16, ld_dx of dx_out (the pitches of absent operands are ignored). */
+int istvt_layernorm_bwd_ld(const void* dy, const void* dy2, int64_t ld_dy, int frames, int tokens_per_frame,
+                           const void* x, int x_dtype, int64_t ld_x, const float* gamma, float* g_accum, int64_t ld_g,
+                           void* g_bf16, int64_t ld_gb, void* dx_out, int64_t ld_dx, float* dgamma, float* dbeta,
+                           int64_t rows, int dim, float eps, istvt_stream_t stream);
 
 /* exact-erf GELU (module.py:28) on bf16, elementwise: forward (training keeps the pre-activation) and backward. */
 int istvt_gelu_fwd(const void* x, void* y, int64_t n, istvt_stream_t stream);
@@ -314,6 +333,10 @@ int istvt_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, istvt_str
 
 /* fp32 -> bf16 cast (gradient of the fp32 residual stream as a GEMM operand). */
 int istvt_cast_f32_bf16(const float* x, void* y, int64_t n, istvt_stream_t stream);
+/* The same for a [rows, cols] matrix with row pitches (elements; cols, ldx, ldy % 4 == 0): bf16 GEMM operands of the
+ * training step at the 128-byte aligned pitch (see istvt_layernorm_fwd_ld). */
+int istvt_cast_f32_bf16_rows(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int cols,
+                             istvt_stream_t stream);
 
 /* out[c, m] = in[m, c] (bf16; out row pitch ldo >= m, multiple of 8, pad zero-filled); colsum (optional, fp32 [c])
  * += column sums of `in` — the bias gradient of the nn.Linear whose output gradient is being transposed.
@@ -414,6 +437,8 @@ int istvt_gemm_wgrad_accum(const void* dy, int64_t ld_dy, const void* x, int64_t
                            int64_t rows, int n_out, int k_in, istvt_stream_t stream);
 /* colsum[c] (fp32, +=) = sum_m x[m, c] (bf16): the bias gradient from an output gradient. */
 int istvt_colsum(const void* x, float* colsum, int64_t m, int c, istvt_stream_t stream);
+/* The same with a row pitch ld (elements, >= c, % 8 == 0). */
+int istvt_colsum_ld(const void* x, int64_t ld, float* colsum, int64_t m, int c, istvt_stream_t stream);
 
 #ifdef __cplusplus
 }

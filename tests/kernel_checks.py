@@ -195,6 +195,34 @@ def check_gemm_lnfold():
     return out
 
 
+def check_gemm_mlp_fusions():
+    """Training-step MLP fusions vs fp64: istvt_gemm_act_dual_fwd (pre-activation and GELU from one accumulator) and
+    istvt_gemm_dgelu_fwd ((A W^T) o gelu'(pre)); ragged M and N, row-pitched A / W operands (K = 728 at pitch 768)."""
+    ops = _ops()
+    out = {}
+    for m in (1000, 257, 4099):
+        a = ops.empty_rows((m, 728), torch.bfloat16, "cuda")
+        a.copy_(_rand(m, 728, seed=m))
+        w1 = ops.pad_rows((_rand(2912, 728, seed=m + 1) * 728 ** -0.5).to(torch.bfloat16))
+        b1 = _rand(2912, seed=m + 2) * 0.5
+        hid, pre = ops.gemm_act_dual(a, w1, b1, ops.ACT_GELU)
+        pre_ref = a.double() @ w1.double().t() + b1.double()
+        out[f"pre_{m}"] = _assert_close("dual pre", pre, pre_ref.float(), TOL_BF16)
+        out[f"hid_{m}"] = _assert_close("dual gelu", hid, torch.nn.functional.gelu(pre_ref).float(), TOL_BF16)
+        plain = ops.gemm(a, w1, bias=b1, act=ops.ACT_GELU)
+        assert torch.equal(plain, hid), "dual-output GELU differs from the single-output epilogue"
+        # data gradient through Linear(2912 -> 728)^T and the GELU: g [m, 728] . W2 [728, 2912] o gelu'(pre)
+        g = ops.empty_rows((m, 728), torch.bfloat16, "cuda")
+        g.copy_(_rand(m, 728, seed=m + 3))
+        w2t = ops.pad_rows((_rand(2912, 728, seed=m + 4) * 728 ** -0.5).to(torch.bfloat16))     # = W2^T, [2912, 728]
+        got = ops.gemm_dgelu(g, w2t, pre)
+        x = pre.double()
+        dg = 0.5 * (1 + torch.erf(x * 0.7071067811865476)) + x * torch.exp(-0.5 * x * x) * 0.3989422804014327
+        ref = (g.double() @ w2t.double().t()) * dg
+        out[f"dgelu_{m}"] = _assert_close("dgelu", got, ref.float(), TOL_BF16)
+    return out
+
+
 def check_gemm_f32():
     ops = _ops()
     out = {}
@@ -850,6 +878,7 @@ CHECKS = {
     "gemm_basic": check_gemm_basic,
     "gemm_shapes": check_gemm_shapes,
     "gemm_lnfold": check_gemm_lnfold,
+    "gemm_mlp_fusions": check_gemm_mlp_fusions,
     "gemm_f32": check_gemm_f32,
     "conv3x3": check_conv3x3,
     "conv_stem": check_conv_stem,

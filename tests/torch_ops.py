@@ -150,6 +150,21 @@ def token_fill(tokens, space_token, temporal_token, pos_emb):
     tokens[:, 1:, 0] = space_token.reshape(1, 1, d) + pos[None, :, 0]
 
 
+def gemm_act_dual(a, w, bias, act=2):
+    pre = F.linear(a.float().reshape(-1, a.shape[-1]), w.float(), bias)
+    out = F.gelu(pre) if act == 2 else (F.relu(pre) if act == 1 else pre)
+    shape = (*a.shape[:-1], w.shape[0])
+    return out.to(a.dtype).reshape(shape), pre.to(a.dtype).reshape(shape)
+
+
+def gemm_dgelu(a, w, pre):
+    y = F.linear(a.float().reshape(-1, a.shape[-1]), w.float())
+    xf = pre.float().reshape(y.shape)
+    cdf = 0.5 * (1 + torch.erf(xf * 0.7071067811865476))
+    pdf = torch.exp(-0.5 * xf * xf) * 0.3989422804014327
+    return (y * (cdf + xf * pdf)).to(a.dtype)
+
+
 def gemm_rowstats(a, w, bias, row_stats):
     y = gemm(a, w, bias=bias)
     yr = y.float().reshape(-1, y.shape[-1])
@@ -262,10 +277,12 @@ def block_input_grad(d_main, x_in, d_skip, relu_in):
     return dx.to(d_main.dtype)
 
 
-def transpose(x, colsum=None):
+def transpose(x, colsum=None, aligned=False):
     if colsum is not None:
         colsum += x.float().sum(0)
     m = x.shape[0]
+    if aligned:        # the product returns the [:, :m] view of a row-pitched buffer
+        return x.t().contiguous()
     return F.pad(x.t(), (0, (m + 7) // 8 * 8 - m)).contiguous()
 
 
@@ -401,7 +418,7 @@ ALL = dict(gemm=gemm, layernorm=layernorm, layernorm_diff=layernorm_diff, attn_j
            block_input_grad=block_input_grad, transpose=transpose, im2col_t=im2col_t, im2col_t_stem=im2col_t_stem,
            gemm_wgrad=gemm_wgrad, colsum=colsum, wgrad=wgrad, gelu=gelu, gelu_bwd=gelu_bwd, cast_bf16=cast_bf16,
            layernorm_bwd=layernorm_bwd, head_bwd=head_bwd, attn_spatial_lse=attn_spatial_lse, attn_spatial_bwd=attn_spatial_bwd,
-           attn_temporal_bwd=attn_temporal_bwd, adamw_step=adamw_step)
+           attn_temporal_bwd=attn_temporal_bwd, adamw_step=adamw_step, gemm_act_dual=gemm_act_dual, gemm_dgelu=gemm_dgelu)
 
 
 def install(monkeypatch, ops_module):
