@@ -278,15 +278,17 @@ attn_spatial_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o
 //   roles: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM alloc, warps 4-11: D = rowsum(dO o O), P = exp2(S c - lse),
 //          dS = P o (dP - D) * scale -> smem, dQ tile -> red.global.add (summed over the key chunks), final dK / dV.
 // ------------------------------------------------------------------------------------------
-constexpr int TB_THREADS = 384;
+constexpr int TB_PARTS = 4;                           // softmax threads per query row (32 of the 128 key columns each)
+constexpr int TB_SM_WARPS = 4 * TB_PARTS;             // 16 (8 until r6r: 64 columns per thread at 168 registers)
+constexpr int TB_THREADS = 128 + 32 * TB_SM_WARPS;
 constexpr int TB_TILE = 128 * 64 * 2;                 // 16 KB: 128 rows x 64 bf16
 constexpr int TB_K_OFF = 0, TB_V_OFF = TB_TILE, TB_Q_OFF = 2 * TB_TILE, TB_DO_OFF = 4 * TB_TILE;
 constexpr int TB_P_OFF = 6 * TB_TILE, TB_DS_OFF = 8 * TB_TILE, TB_MISC_OFF = 10 * TB_TILE;      // 160 KB
-constexpr int TB_SMEM = TB_MISC_OFF + 1024 + 256 + 2 * (2 * 128 * 4 + 128 * 4);
+constexpr int TB_SMEM = TB_MISC_OFF + 1024 + 256;
 
 __global__ void __launch_bounds__(TB_THREADS, 1)
 attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                           const bf16* __restrict__ o, const bf16* __restrict__ dout, const float* __restrict__ lse,
+                           const float* __restrict__ d_rows, const float* __restrict__ lse,
                            bf16* __restrict__ dqkv, float* __restrict__ dq_acc, float* __restrict__ cam, int tokens,
                            int heads, float scale) {
     extern __shared__ uint8_t tb_raw[];
@@ -301,11 +303,6 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
     uint64_t* dq_empty = bars + 8;
     uint64_t* fin = bars + 9;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
-    // double-buffered by the parity of the query tile: the reads of tile t and the writes of tile t + 1 are ordered by
-    // the mbarrier chain p_ready -> MMA -> dq_full, which compute-sanitizer's racecheck does not model (r6a); with two
-    // copies every reuse is also separated by the named barrier of the tile in between
-    float* s_dpart0 = reinterpret_cast<float*>(smem + TB_MISC_OFF + 256);   // [2 tiles][2][128] partial D
-    float* s_lse0 = s_dpart0 + 512;                                          // [2 tiles][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k_chunks = (tokens + 127) / 128;
@@ -321,7 +318,8 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
     if (warp == 1 && lane == 0) {
         mbar_init(kv_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(q_full + i, 1); mbar_init(q_empty + i, 1); }
-        mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(dq_full, 1); mbar_init(dq_empty, 8); mbar_init(fin, 1);
+        mbar_init(s_full, 1); mbar_init(p_ready, TB_SM_WARPS); mbar_init(dq_full, 1); mbar_init(dq_empty, TB_SM_WARPS);
+        mbar_init(fin, 1);
         fence_mbar_init();
     }
     if (warp == 2) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
@@ -393,40 +391,24 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
         __syncwarp();
     } else if (warp >= 4) {
         // ================= softmax / dS / epilogues =================
-        const int quad = warp & 3, half = (warp - 4) >> 2;
+        const int quad = warp & 3, part = (warp - 4) >> 2;
         const int row = quad * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
         const float ih = 1.0f / static_cast<float>(heads);
         for (int t = 0; t < q_tiles; ++t) {
             const int q_idx = t * 128 + row;
             const bool row_ok = q_idx < tokens;
-            // D = rowsum(dO o O): this thread's 32 of the 64 dims (overlaps the S / dP MMAs)
-            float dpart = 0.f;
-            if (row_ok) {
-                const bf16* dop = dout + (row0 + q_idx) * inner + h * SB_DH + half * 32;
-                const bf16* op = o + (row0 + q_idx) * inner + h * SB_DH + half * 32;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float a[8], b[8];
-                    load8(dop + c * 8, a);
-                    load8(op + c * 8, b);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) dpart = fmaf(a[e], b[e], dpart);
-                }
-            }
-            float* s_dpart = s_dpart0 + (t & 1) * 256;
-            float* s_lse = s_lse0 + (t & 1) * 128;
-            s_dpart[half * 128 + row] = dpart;
-            if (half == 0) s_lse[row] = row_ok ? lse[(static_cast<int64_t>(bf) * heads + h) * tokens + q_idx] : INFINITY;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float dsum = s_dpart[row] + s_dpart[128 + row];
-            const float l = s_lse[row];
+            // D = rowsum(dO o O) of this query row and head: computed once per row by attn_spatial_bwd_d_kernel into the
+            // (not yet written) dQ columns of dqkv.  The first version recomputed it in every key-chunk CTA from 2 x 64
+            // bytes of uncoalesced global loads per thread and exchanged halves through shared memory + a named barrier —
+            // 11 % of the stall samples (profiles/r3s_attn_spatial_bwd_ncu_source.txt).
+            const float dsum = row_ok ? __ldg(d_rows + (row0 + q_idx) * (3 * inner / 2) + h) : 0.f;
+            const float l = row_ok ? __ldg(lse + (static_cast<int64_t>(bf) * heads + h) * tokens + q_idx) : INFINITY;
 
             mbar_wait(s_full, t & 1);
             tc_fence_after();
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int col0 = half * 64 + b * 32;               // key column inside the chunk
+            {
+                const int col0 = part * 32;                        // key column inside the chunk
                 uint32_t rs[32], rd[32];
                 tmem_ld_32x32b_x32(t_s + lane_base + col0, rs);
                 tmem_ld_32x32b_x32(t_dp + lane_base + col0, rd);
@@ -468,16 +450,16 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
             mbar_wait(dq_full, t & 1);
             tc_fence_after();
             {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_dq + lane_base + half * 32, r);
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(t_dq + lane_base + part * 16, r);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(dq_empty);
                 if (row_ok) {
-                    float* dst = dq_acc + (row0 + q_idx) * inner + h * SB_DH + half * 32;
+                    float* dst = dq_acc + (row0 + q_idx) * inner + h * SB_DH + part * 16;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g)
+                    for (int g = 0; g < 4; ++g)
                         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
                                      "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
                                      "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3]))
@@ -490,14 +472,14 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
         tc_fence_after();
         {
             const int key = kc * 128 + row;
-            uint32_t rk[32], rv[32];
-            tmem_ld_32x32b_x32(t_dk + lane_base + half * 32, rk);
-            tmem_ld_32x32b_x32(t_dv + lane_base + half * 32, rv);
+            uint32_t rk[16], rv[16];
+            tmem_ld_32x32b_x16(t_dk + lane_base + part * 16, rk);
+            tmem_ld_32x32b_x16(t_dv + lane_base + part * 16, rv);
             tmem_ld_wait();
             if (key < tokens) {
-                bf16* base = dqkv + (row0 + key) * (3 * inner) + h * SB_DH + half * 32;
+                bf16* base = dqkv + (row0 + key) * (3 * inner) + h * SB_DH + part * 16;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 2; ++g) {
                     uint4 a, b;
                     a.x = pack_bf16x2(__uint_as_float(rk[8 * g]), __uint_as_float(rk[8 * g + 1]));
                     a.y = pack_bf16x2(__uint_as_float(rk[8 * g + 2]), __uint_as_float(rk[8 * g + 3]));
@@ -518,6 +500,33 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
+    }
+}
+
+// D[row, head] = sum_d dO[row, head, d] * O[row, head, d] (fp32), one warp per token row, written to the first `heads`
+// floats of the row's dQ columns in dqkv — scratch until attn_spatial_bwd_dq_kernel overwrites them at the end.
+__global__ void __launch_bounds__(256)
+attn_spatial_bwd_d_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, bf16* __restrict__ dqkv, int64_t rows,
+                          int heads) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int inner = heads * SB_DH;
+    float* dst = reinterpret_cast<float*>(dqkv + row * (3 * inner));
+    for (int c0 = 0; c0 < inner; c0 += 256) {          // 32 lanes x 8 elements: 4 heads per pass, 8 lanes per head
+        const int c = c0 + lane * 8;
+        float acc = 0.f;
+        if (c < inner) {
+            float a[8], b[8];
+            load8(dout + row * inner + c, a);
+            load8(o + row * inner + c, b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fmaf(a[e], b[e], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if ((lane & 7) == 0 && c < inner) dst[c >> 6] = acc;
     }
 }
 
@@ -579,10 +588,13 @@ static int attn_spatial_bwd_launch(const void* qkv, const void* o, const void* d
             int rc = encode_tmap(&tm_do, dout, ISTVT_BF16, 3, dims, strides, box, 3);
             if (rc != ISTVT_OK) return rc;
         }
+        attn_spatial_bwd_d_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(
+            static_cast<const bf16*>(o), static_cast<const bf16*>(dout), static_cast<bf16*>(dqkv), rows, heads);
+        count_launch();
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM));
         attn_spatial_bwd_tc_kernel<<<static_cast<unsigned>(grid), TB_THREADS, TB_SMEM, st>>>(
-            tm_qkv, tm_do, static_cast<const bf16*>(o), static_cast<const bf16*>(dout), lse, static_cast<bf16*>(dqkv),
-            dq_scratch, cam, tokens, heads, scale);
+            tm_qkv, tm_do, reinterpret_cast<const float*>(dqkv), lse, static_cast<bf16*>(dqkv), dq_scratch, cam, tokens,
+            heads, scale);
     }
     count_launch();
     const int64_t n = rows * (inner / 8);

@@ -32,7 +32,11 @@ from . import ops
 from .engine import pack_entry, run_entry_flow
 
 BF16 = torch.bfloat16
-_MLP_FUSE = os.environ.get("ISTVT_MLP_FUSE", "1") != "0"      # 0: stand-alone GELU forward / backward passes (A/B)
+# ISTVT_MLP_FUSE=1: GELU (+ pre-activation) in ff1's epilogue and gelu' in the ff2 data-gradient epilogue instead of the
+# stand-alone GELU passes.  Measured on the C3 step (profiles/README.md r6q): the passes cost 4.4 + 5.9 ms, the fused
+# epilogues add 8.8 ms to the GEMMs (twice the TMA store boxes; per-lane loads of the pre-activation) — 208.5 -> 207.0 ms,
+# not enough to make it the default.
+_MLP_FUSE = os.environ.get("ISTVT_MLP_FUSE", "0") != "0"
 
 
 # ------------------------------------------------------------------------------------------------
