@@ -282,44 +282,65 @@ constexpr int TB_PARTS = 4;                           // softmax threads per que
 constexpr int TB_SM_WARPS = 4 * TB_PARTS;             // 16 (8 until r6r: 64 columns per thread at 168 registers)
 constexpr int TB_THREADS = 128 + 32 * TB_SM_WARPS;
 constexpr int TB_TILE = 128 * 64 * 2;                 // 16 KB: 128 rows x 64 bf16
-constexpr int TB_K_OFF = 0, TB_V_OFF = TB_TILE, TB_Q_OFF = 2 * TB_TILE, TB_DO_OFF = 4 * TB_TILE;
-constexpr int TB_P_OFF = 6 * TB_TILE, TB_DS_OFF = 8 * TB_TILE, TB_MISC_OFF = 10 * TB_TILE;      // 160 KB
+// K / V chunk double buffered by item parity, Q / dO tile double buffered by tile parity, P and dS single
+constexpr int TB_K_OFF = 0, TB_V_OFF = 2 * TB_TILE, TB_Q_OFF = 4 * TB_TILE, TB_DO_OFF = 6 * TB_TILE;
+constexpr int TB_P_OFF = 8 * TB_TILE, TB_DS_OFF = 10 * TB_TILE, TB_MISC_OFF = 12 * TB_TILE;      // 192 KB
 constexpr int TB_SMEM = TB_MISC_OFF + 1024 + 256;
+
+// PERSISTENT (r6s): one CTA per SM walks items = (frame, head, 128-key chunk); the producer fetches the next item's
+// K / V chunk and first Q / dO tile while the current item computes, TMEM is allocated once, and the dK / dV epilogue
+// of item n overlaps the S / dP MMAs of item n + 1.  The one-item-per-CTA version paid launch, barrier set-up, TMEM
+// allocation and the first TMA round trip 10 752 times per layer: 24.8 us per item against ~12 us of work.
+__device__ __forceinline__ int tb_item(int n, int k_chunks, int grouped) {
+    if (!grouped) return static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+    const int grp = n / k_chunks;
+    return (static_cast<int>(blockIdx.x) + grp * static_cast<int>(gridDim.x)) * k_chunks + (n - grp * k_chunks);
+}
 
 __global__ void __launch_bounds__(TB_THREADS, 1)
 attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                            const float* __restrict__ d_rows, const float* __restrict__ lse,
                            bf16* __restrict__ dqkv, float* __restrict__ dq_acc, float* __restrict__ cam, int tokens,
-                           int heads, float scale) {
+                           int heads, int items, float scale, int grouped, int no_red) {
     extern __shared__ uint8_t tb_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tb_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TB_MISC_OFF);
-    uint64_t* kv_full = bars;
-    uint64_t* q_full = bars + 1;      // [2]
-    uint64_t* q_empty = bars + 3;     // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_ready = bars + 6;
-    uint64_t* dq_full = bars + 7;
-    uint64_t* dq_empty = bars + 8;
-    uint64_t* fin = bars + 9;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* kv_full = bars;         // [2]
+    uint64_t* kv_empty = bars + 2;    // [2]
+    uint64_t* q_full = bars + 4;      // [2]
+    uint64_t* q_empty = bars + 6;     // [2]
+    uint64_t* s_full = bars + 8;
+    uint64_t* p_ready = bars + 9;
+    uint64_t* dq_full = bars + 10;
+    uint64_t* dq_empty = bars + 11;
+    uint64_t* fin = bars + 12;        // dK / dV of the item complete in TMEM
+    uint64_t* dkv_empty = bars + 13;  // ... and read out by the epilogue warps
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k_chunks = (tokens + 127) / 128;
     const int q_tiles = k_chunks;
-    const int kc = blockIdx.x % k_chunks;
-    const int h = (blockIdx.x / k_chunks) % heads;
-    const int bf = blockIdx.x / (k_chunks * heads);
     const int inner = heads * SB_DH;
-    const int64_t row0 = static_cast<int64_t>(bf) * tokens;
     const float scale_log2 = scale * 1.4426950408889634f;
+    // grouped: a CTA takes the k_chunks key chunks of one (frame, head) back to back, so the three read-modify-writes of
+    // that (frame, head)'s dQ rows and the three reads of its Q / dO tiles hit in L2 instead of going to HBM
+    const int groups = items / k_chunks;
+    const int my_groups = groups > static_cast<int>(blockIdx.x)
+                              ? (groups - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                              : 0;
+    const int my_items = grouped ? my_groups * k_chunks
+                                 : (items > static_cast<int>(blockIdx.x)
+                                        ? (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                                        : 0);
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do); }
     if (warp == 1 && lane == 0) {
-        mbar_init(kv_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(q_full + i, 1); mbar_init(q_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(kv_full + i, 1); mbar_init(kv_empty + i, 1);
+            mbar_init(q_full + i, 1); mbar_init(q_empty + i, 1);
+        }
         mbar_init(s_full, 1); mbar_init(p_ready, TB_SM_WARPS); mbar_init(dq_full, 1); mbar_init(dq_empty, TB_SM_WARPS);
-        mbar_init(fin, 1);
+        mbar_init(fin, 1); mbar_init(dkv_empty, TB_SM_WARPS);
         fence_mbar_init();
     }
     if (warp == 2) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
@@ -332,15 +353,22 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            mbar_arrive_expect_tx(kv_full, 2 * TB_TILE);
-            tma_load_3d(smem + TB_K_OFF, &tm_qkv, kv_full, inner + h * SB_DH, kc * 128, bf);
-            tma_load_3d(smem + TB_V_OFF, &tm_qkv, kv_full, 2 * inner + h * SB_DH, kc * 128, bf);
-            for (int t = 0; t < q_tiles; ++t) {
-                const int slot = t & 1;
-                mbar_wait_sleep(q_empty + slot, ((t >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(q_full + slot, 2 * TB_TILE);
-                tma_load_3d(smem + TB_Q_OFF + slot * TB_TILE, &tm_qkv, q_full + slot, h * SB_DH, t * 128, bf);
-                tma_load_3d(smem + TB_DO_OFF + slot * TB_TILE, &tm_do, q_full + slot, h * SB_DH, t * 128, bf);
+            for (int n = 0; n < my_items; ++n) {
+                const int item = tb_item(n, k_chunks, grouped);
+                const int kc = item % k_chunks, h = (item / k_chunks) % heads, bf = item / (k_chunks * heads);
+                const int ks = n & 1;
+                mbar_wait_sleep(kv_empty + ks, ((n >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(kv_full + ks, 2 * TB_TILE);
+                tma_load_3d(smem + TB_K_OFF + ks * TB_TILE, &tm_qkv, kv_full + ks, inner + h * SB_DH, kc * 128, bf);
+                tma_load_3d(smem + TB_V_OFF + ks * TB_TILE, &tm_qkv, kv_full + ks, 2 * inner + h * SB_DH, kc * 128, bf);
+                for (int t = 0; t < q_tiles; ++t) {
+                    const int g = n * q_tiles + t;
+                    const int slot = g & 1;
+                    mbar_wait_sleep(q_empty + slot, ((g >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(q_full + slot, 2 * TB_TILE);
+                    tma_load_3d(smem + TB_Q_OFF + slot * TB_TILE, &tm_qkv, q_full + slot, h * SB_DH, t * 128, bf);
+                    tma_load_3d(smem + TB_DO_OFF + slot * TB_TILE, &tm_do, q_full + slot, h * SB_DH, t * 128, bf);
+                }
             }
         }
         __syncwarp();
@@ -354,39 +382,46 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
             const uint64_t d_mn_a = make_smem_desc(0, 128 * 128, 1024, SWZ_128B);   // atoms of 64 keys are 16 KB apart
             const uint64_t d_mn_b = make_smem_desc(0, 128 * 128, 1024, SWZ_128B);   // N = 64: a single atom
             auto fld = [&](int off) { return static_cast<uint64_t>((smem_u32(smem + off) & 0x3FFFFu) >> 4); };
-            const uint64_t k_f = fld(TB_K_OFF), v_f = fld(TB_V_OFF), p_f = fld(TB_P_OFF), ds_f = fld(TB_DS_OFF);
-            mbar_wait(kv_full, 0);
-            for (int t = 0; t < q_tiles; ++t) {
-                const int slot = t & 1;
-                const uint64_t q_f = fld(TB_Q_OFF + slot * TB_TILE), do_f = fld(TB_DO_OFF + slot * TB_TILE);
-                mbar_wait(q_full + slot, (t >> 1) & 1);
-                tc_fence_after();
+            const uint64_t p_f = fld(TB_P_OFF), ds_f = fld(TB_DS_OFF);
+            for (int n = 0; n < my_items; ++n) {
+                const int ks = n & 1;
+                const uint64_t k_f = fld(TB_K_OFF + ks * TB_TILE), v_f = fld(TB_V_OFF + ks * TB_TILE);
+                mbar_wait(kv_full + ks, (n >> 1) & 1);
+                for (int t = 0; t < q_tiles; ++t) {
+                    const int g = n * q_tiles + t;
+                    const int slot = g & 1;
+                    const uint64_t q_f = fld(TB_Q_OFF + slot * TB_TILE), do_f = fld(TB_DO_OFF + slot * TB_TILE);
+                    mbar_wait(q_full + slot, (g >> 1) & 1);
+                    tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 4; ++k)      // S = Q K^T
-                    umma_f16_ss(t_s, d_kmaj | (q_f + 2 * k), d_kmaj | (k_f + 2 * k), id_s, k != 0 ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k)      // S = Q K^T
+                        umma_f16_ss(t_s, d_kmaj | (q_f + 2 * k), d_kmaj | (k_f + 2 * k), id_s, k != 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)      // dP = dO V^T
-                    umma_f16_ss(t_dp, d_kmaj | (do_f + 2 * k), d_kmaj | (v_f + 2 * k), id_s, k != 0 ? 1u : 0u);
-                umma_commit(s_full);
-                mbar_wait(p_ready, t & 1);                       // P, dS in smem; S / dP TMEM consumed
-                mbar_wait(dq_empty, (t & 1) ^ 1);                // previous dQ tile drained
-                tc_fence_after();
+                    for (int k = 0; k < 4; ++k)      // dP = dO V^T
+                        umma_f16_ss(t_dp, d_kmaj | (do_f + 2 * k), d_kmaj | (v_f + 2 * k), id_s, k != 0 ? 1u : 0u);
+                    umma_commit(s_full);
+                    mbar_wait(p_ready, g & 1);                       // P, dS in smem; S / dP TMEM consumed
+                    mbar_wait(dq_empty, (g & 1) ^ 1);                // previous dQ tile drained
+                    if (t == 0) mbar_wait(dkv_empty, (n & 1) ^ 1);   // previous item's dK / dV read out
+                    tc_fence_after();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)      // dQ = dS K   (A K-major: key atom j>>2, 32 B per k-step; B = K MN-major)
-                    umma_f16_ss(t_dq, d_kmaj | (ds_f + (j >> 2) * (128 * 128 >> 4) + (j & 3) * 2),
-                                d_mn_b | (k_f + j * (16 * 128 >> 4)), id_q, j != 0 ? 1u : 0u);
-                umma_commit(dq_full);
+                    for (int j = 0; j < 8; ++j)      // dQ = dS K   (A K-major: key atom j>>2, 32 B per k-step; B = K MN-major)
+                        umma_f16_ss(t_dq, d_kmaj | (ds_f + (j >> 2) * (128 * 128 >> 4) + (j & 3) * 2),
+                                    d_mn_b | (k_f + j * (16 * 128 >> 4)), id_q, j != 0 ? 1u : 0u);
+                    umma_commit(dq_full);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)      // dV += P^T dO   (k-step = 16 queries = 2048 B in both operands)
-                    umma_f16_ss(t_dv, d_mn_a | (p_f + j * (16 * 128 >> 4)), d_mn_b | (do_f + j * (16 * 128 >> 4)), id_t,
-                                (t | j) != 0 ? 1u : 0u);
+                    for (int j = 0; j < 8; ++j)      // dV += P^T dO   (k-step = 16 queries = 2048 B in both operands)
+                        umma_f16_ss(t_dv, d_mn_a | (p_f + j * (16 * 128 >> 4)), d_mn_b | (do_f + j * (16 * 128 >> 4)), id_t,
+                                    (t | j) != 0 ? 1u : 0u);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)      // dK += dS^T Q
-                    umma_f16_ss(t_dk, d_mn_a | (ds_f + j * (16 * 128 >> 4)), d_mn_b | (q_f + j * (16 * 128 >> 4)), id_t,
-                                (t | j) != 0 ? 1u : 0u);
-                umma_commit(q_empty + slot);
+                    for (int j = 0; j < 8; ++j)      // dK += dS^T Q
+                        umma_f16_ss(t_dk, d_mn_a | (ds_f + j * (16 * 128 >> 4)), d_mn_b | (q_f + j * (16 * 128 >> 4)), id_t,
+                                    (t | j) != 0 ? 1u : 0u);
+                    umma_commit(q_empty + slot);
+                }
+                umma_commit(kv_empty + ks);
+                umma_commit(fin);
             }
-            umma_commit(fin);
         }
         __syncwarp();
     } else if (warp >= 4) {
@@ -395,17 +430,43 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
         const int row = quad * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
         const float ih = 1.0f / static_cast<float>(heads);
+        float dsum_next = 0.f, l_next = INFINITY;       // D and log-sum-exp of this thread's row in the NEXT tile
+        if (my_items > 0) {
+            const int item0 = tb_item(0, k_chunks, grouped);
+            const int h0 = (item0 / k_chunks) % heads, bf0 = item0 / (k_chunks * heads);
+            if (row < tokens) {
+                dsum_next = __ldg(d_rows + (static_cast<int64_t>(bf0) * tokens + row) * (3 * inner / 2) + h0);
+                l_next = __ldg(lse + (static_cast<int64_t>(bf0) * heads + h0) * tokens + row);
+            }
+        }
+        for (int n = 0; n < my_items; ++n) {
+        const int item = tb_item(n, k_chunks, grouped);
+        const int kc = item % k_chunks, h = (item / k_chunks) % heads, bf = item / (k_chunks * heads);
+        const int64_t row0 = static_cast<int64_t>(bf) * tokens;
         for (int t = 0; t < q_tiles; ++t) {
+            const int g = n * q_tiles + t;
             const int q_idx = t * 128 + row;
             const bool row_ok = q_idx < tokens;
             // D = rowsum(dO o O) of this query row and head: computed once per row by attn_spatial_bwd_d_kernel into the
             // (not yet written) dQ columns of dqkv.  The first version recomputed it in every key-chunk CTA from 2 x 64
             // bytes of uncoalesced global loads per thread and exchanged halves through shared memory + a named barrier —
             // 11 % of the stall samples (profiles/r3s_attn_spatial_bwd_ncu_source.txt).
-            const float dsum = row_ok ? __ldg(d_rows + (row0 + q_idx) * (3 * inner / 2) + h) : 0.f;
-            const float l = row_ok ? __ldg(lse + (static_cast<int64_t>(bf) * heads + h) * tokens + q_idx) : INFINITY;
+            // (loaded one tile ahead, below: the two L2 round trips were exposed at the top of every tile, r6u ncu)
+            const float dsum = dsum_next, l = l_next;
+            {
+                int t2 = t + 1, n2 = n;
+                if (t2 == q_tiles) { t2 = 0; ++n2; }
+                if (n2 < my_items) {
+                    const int item2 = tb_item(n2, k_chunks, grouped);
+                    const int h2 = (item2 / k_chunks) % heads, bf2 = item2 / (k_chunks * heads);
+                    const int q2 = t2 * 128 + row;
+                    const bool ok2 = q2 < tokens;
+                    dsum_next = ok2 ? __ldg(d_rows + (static_cast<int64_t>(bf2) * tokens + q2) * (3 * inner / 2) + h2) : 0.f;
+                    l_next = ok2 ? __ldg(lse + (static_cast<int64_t>(bf2) * heads + h2) * tokens + q2) : INFINITY;
+                }
+            }
 
-            mbar_wait(s_full, t & 1);
+            mbar_wait(s_full, g & 1);
             tc_fence_after();
             {
                 const int col0 = part * 32;                        // key column inside the chunk
@@ -447,7 +508,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
             if (lane == 0) mbar_arrive(p_ready);
 
             // dQ tile: this thread's 32 of the 64 dims of its query row, accumulated over the key chunks in global
-            mbar_wait(dq_full, t & 1);
+            mbar_wait(dq_full, g & 1);
             tc_fence_after();
             {
                 uint32_t r[16];
@@ -456,7 +517,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(dq_empty);
-                if (row_ok) {
+                if (row_ok && !no_red) {
                     float* dst = dq_acc + (row0 + q_idx) * inner + h * SB_DH + part * 16;
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
@@ -468,7 +529,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
             }
         }
         // ---- dK, dV of this key chunk ----
-        mbar_wait(fin, 0);
+        mbar_wait(fin, n & 1);
         tc_fence_after();
         {
             const int key = kc * 128 + row;
@@ -476,6 +537,9 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
             tmem_ld_32x32b_x16(t_dk + lane_base + part * 16, rk);
             tmem_ld_32x32b_x16(t_dv + lane_base + part * 16, rv);
             tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dkv_empty);      // the next item's dV / dK MMAs may overwrite the accumulators
             if (key < tokens) {
                 bf16* base = dqkv + (row0 + key) * (3 * inner) + h * SB_DH + part * 16;
 #pragma unroll
@@ -494,6 +558,7 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
                 }
             }
         }
+        }   // items
     }
     tc_fence_before();
     __syncthreads();
@@ -592,9 +657,14 @@ static int attn_spatial_bwd_launch(const void* qkv, const void* o, const void* d
             static_cast<const bf16*>(o), static_cast<const bf16*>(dout), static_cast<bf16*>(dqkv), rows, heads);
         count_launch();
         ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM));
-        attn_spatial_bwd_tc_kernel<<<static_cast<unsigned>(grid), TB_THREADS, TB_SMEM, st>>>(
+        // ISTVT_SAB_GROUPED=0: items round-robin over the CTAs instead of one (frame, head) per CTA at a time (A/B);
+        // ISTVT_SAB_NORED=1 (timing experiment, wrong dQ): without the red.global accumulation of dQ
+        static const int grouped_env = []() { const char* e = getenv("ISTVT_SAB_GROUPED"); return e ? atoi(e) : 1; }();
+        static const int nored_env = []() { const char* e = getenv("ISTVT_SAB_NORED"); return e ? atoi(e) : 0; }();
+        const int64_t ctas = grid < sm_count() ? grid : sm_count();       // persistent: one CTA per SM walks the items
+        attn_spatial_bwd_tc_kernel<<<static_cast<unsigned>(ctas), TB_THREADS, TB_SMEM, st>>>(
             tm_qkv, tm_do, reinterpret_cast<const float*>(dqkv), lse, static_cast<bf16*>(dqkv), dq_scratch, cam, tokens,
-            heads, scale);
+            heads, static_cast<int>(grid), scale, grouped_env, nored_env);
     }
     count_launch();
     const int64_t n = rows * (inner / 8);

@@ -154,6 +154,7 @@ def main() -> None:
                                                           "yardstick for what the shape can reach, not a product path")
     ap.add_argument("--entry", action="store_true", help="the 9 pointwise / skip GEMMs of the Xception entry flow at "
                                                          "the C2 size (384 frames) instead of the transformer's")
+    ap.add_argument("--aligned", action="store_true", help="operands / bf16 outputs at the engine's aligned row pitch")
     ap.add_argument("--residual-pitch", action="store_true", help="s_out / ff2 in place with the fp32 stream at pitch 728 vs 768")
     ap.add_argument("--pitch", action="store_true", help="row-pitch experiment: K = 728 operands with pitch 728 vs 768")
     args = ap.parse_args()
@@ -175,8 +176,13 @@ def main() -> None:
         nbuf = 3
         a = [torch.randn(m, k, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
         w = torch.randn(n, k, device=dev, dtype=torch.bfloat16) * k ** -0.5
+        if args.aligned:      # the engine's layout: K = 728 operands at the 128-byte aligned row pitch (768 elements)
+            a = [ops.pad_rows(t) for t in a]
+            w = ops.pad_rows(w)
         b = torch.randn(n, device=dev) if bias else None
         outs = [torch.zeros(m, n, device=dev, dtype=odt) for _ in range(nbuf)]
+        if args.aligned and odt == torch.bfloat16:
+            outs = [ops.pad_rows(t) for t in outs]
         for i in range(3):
             ops.gemm(a[i % nbuf], w, bias=b, residual=outs[i % nbuf] if res else None, act=act, out=outs[i % nbuf])
         torch.cuda.synchronize()
@@ -193,6 +199,9 @@ def main() -> None:
         tot_fl += fl
         extra = ""
         if args.cublas:
+            if args.aligned:      # cuBLAS on the dense operands (torch.matmul would copy a strided view anyway)
+                a = [t.contiguous() for t in a]
+                w = w.contiguous()
             wt = w.t()
             for i in range(3):
                 torch.matmul(a[i % nbuf], wt)
