@@ -18,14 +18,16 @@ One JSON line on rank 0:
   roofline     the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs of its launches / their summed
                CUDA-event durations, measured live in the timed region (ops.LaunchRecorder), against the
                measured bf16 peak in MEASURED_PEAKS.json (or the profiling guide's fallback)
-  cpu_baseline the CPU oracle port of the reference forward (oracle/istvt_oracle.py, fp32, all host threads)
-               on a bounded sample of the same workload — rank 0, N=1 only
+  cpu_baseline the reference forward on the host cores (fp32, all host threads) on a bounded sample of the same
+               workload — rank 0, N=1 only.  kind "reference": the UNMODIFIED reference modules staged under
+               oracle/_ref by oracle/make_ref.py (they travel with the gpurun snapshot); kind "port": the oracle
+               restatement oracle/istvt_oracle.py when oracle/_ref is absent or the clip length is not 6
   gpu_eager_baseline  the same op sequence as eager PyTorch on the GPU (TF32 and bf16 autocast): SURVEY.md 8(d)'s
                "kernel to beat"; N=1 only, skipped with --no-eager-baseline
   kernels      per-kernel-family share of the step (launches, ms, TFLOP/s or GB/s) — explains `value`
 
-`--impl reference` times the reference's own algorithm on the host cores (the oracle port: the reference
-is Python and /root/reference does not exist on the GPU box) and prints the same line with "impl": "reference".
+`--impl reference` times the reference's own CPU implementation on the host cores (oracle/_ref when staged, else the
+oracle port — /root/reference itself does not exist on the GPU box) and prints the same line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -131,27 +133,52 @@ def use_all_host_threads() -> int:
     return torch.get_num_threads()
 
 
-def cpu_oracle_clips_per_s(batch: int, frames: int, budget_s: float, min_iters: int = 2):
-    """Reference algorithm on the host cores (oracle port), fp32, eval, no_grad (SURVEY.md §8d CPU baseline)."""
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")       # unmodified reference modules staged by oracle/make_ref.py
+
+
+def cpu_forward_fn(frames: int):
+    """(forward(x) on the host cores, kind, description).  kind "reference": the UNMODIFIED reference `XceptionVidTr`
+    staged under oracle/_ref (oracle/make_ref.py; its constructor hard-codes 6 frames, vivit.py:201, so other clip
+    lengths fall back); kind "port": the oracle restatement, pinned to the reference by tests/test_oracle.py."""
     import torch
+    use_all_host_threads()
+    if frames == 6 and os.path.isfile(os.path.join(REF_DIR, "network", "vivit", "vivit.py")):
+        os.environ["ISTVT_REFERENCE_ROOT"] = REF_DIR
+        from oracle import reference_shim as shim
+        shim.REFERENCE_ROOT = REF_DIR
+        product_network = {k: v for k, v in sys.modules.items() if k == "network" or k.startswith("network.")}
+        try:
+            model = shim.build_reference_model(seed=0)
+        finally:      # the shim imports the reference's `network` package: put the product's aliases back
+            for k in [k for k in sys.modules if k == "network" or k.startswith("network.")]:
+                del sys.modules[k]
+            sys.modules.update(product_network)
+        return (lambda x: model(x)), "reference", "the unmodified reference XceptionVidTr (oracle/_ref via oracle/reference_shim.py)"
     from oracle import istvt_oracle as O
     pkg = importlib.import_module(PKG)
-    use_all_host_threads()
     torch.manual_seed(0)
     model = pkg.XceptionVidTr(num_frames=frames).eval()
     sd = {k: v.detach() for k, v in model.state_dict().items()}
+    return (lambda x: O.forward(sd, x)), "port", "oracle/istvt_oracle.py"
+
+
+def cpu_oracle_clips_per_s(batch: int, frames: int, budget_s: float, min_iters: int = 2):
+    """Reference algorithm on the host cores, fp32, eval, no_grad (SURVEY.md §8d CPU baseline).
+    Returns (clips/s, iterations, threads, kind, what)."""
+    import torch
+    fwd, kind, what = cpu_forward_fn(frames)
     x = torch.rand(batch, frames, 3, 300, 300, generator=torch.Generator().manual_seed(1234))
     with torch.no_grad():
-        O.forward(sd, x)  # warm-up
+        fwd(x)  # warm-up
         t0 = time.perf_counter()
         iters = 0
         while iters < min_iters or (time.perf_counter() - t0) < budget_s:
-            O.forward(sd, x)
+            fwd(x)
             iters += 1
             if time.perf_counter() - t0 > 3 * budget_s:
                 break
         dt = time.perf_counter() - t0
-    return batch * iters / dt, iters, torch.get_num_threads()
+    return batch * iters / dt, iters, torch.get_num_threads(), kind, what
 
 
 def gpu_eager_clips_per_s(frames: int, dev, batch: int = 16, iters: int = 3):
@@ -250,20 +277,15 @@ def run_reference(args) -> int:
     if rank != 0:
         return 0
     import torch
-    from oracle import istvt_oracle as O
-    pkg = importlib.import_module(PKG)
-    use_all_host_threads()
-    torch.manual_seed(0)
-    model = pkg.XceptionVidTr(num_frames=args.frames).eval()
-    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    fwd, kind, what = cpu_forward_fn(args.frames)
     sample = args.ref_clips
     x = torch.rand(sample, args.frames, 3, 300, 300, generator=torch.Generator().manual_seed(1234))
     with torch.no_grad():
         for _ in range(args.warmup):
-            O.forward(sd, x)
+            fwd(x)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.forward(sd, x)
+            fwd(x)
         dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     threads = torch.get_num_threads()
@@ -272,9 +294,9 @@ def run_reference(args) -> int:
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, note=f"CPU arm: each step is a bounded sample of {sample} clip(s) of the workload"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"{sample} clip(s) x {args.frames} frames x 300x300 per step, {args.steps} steps, "
-                                   f"fp32, torch CPU ops, {threads} threads of {os.cpu_count()} logical CPUs"},
+                                   f"fp32, {what}, {threads} threads of {os.cpu_count()} logical CPUs"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -464,10 +486,10 @@ def run_ours(args) -> int:
                                   "frac_of_bf16_sustained": executed / (ms / args.steps * 1e-3) / 1e12
                                                             / peaks["bf16_tflops_sustained"]}
         if world == 1 and not args.no_cpu_baseline:
-            v, iters, threads = cpu_oracle_clips_per_s(1, args.frames, args.cpu_budget)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            v, iters, threads, kind, what = cpu_oracle_clips_per_s(1, args.frames, args.cpu_budget)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                                     "sample": f"{iters} forwards of 1 clip x {args.frames} frames x 300x300 "
-                                              f"(oracle/istvt_oracle.py, fp32, {threads} torch threads of "
+                                              f"({what}, fp32, {threads} torch threads of "
                                               f"{os.cpu_count()} logical CPUs)"}
         if world == 1 and not args.no_eager_baseline:
             try:
