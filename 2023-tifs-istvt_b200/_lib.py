@@ -34,6 +34,7 @@ SIGNATURES = {
     "istvt_conv_stem_u8_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "istvt_dwconv3x3_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "istvt_subsample2_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "istvt_sepconv_fused_fwd": [_P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "istvt_pool_add_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "istvt_pool_add_tokens_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "istvt_token_fill_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],

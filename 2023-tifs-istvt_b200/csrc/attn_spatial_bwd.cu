@@ -430,15 +430,6 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
         const int row = quad * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
         const float ih = 1.0f / static_cast<float>(heads);
-        float dsum_next = 0.f, l_next = INFINITY;       // D and log-sum-exp of this thread's row in the NEXT tile
-        if (my_items > 0) {
-            const int item0 = tb_item(0, k_chunks, grouped);
-            const int h0 = (item0 / k_chunks) % heads, bf0 = item0 / (k_chunks * heads);
-            if (row < tokens) {
-                dsum_next = __ldg(d_rows + (static_cast<int64_t>(bf0) * tokens + row) * (3 * inner / 2) + h0);
-                l_next = __ldg(lse + (static_cast<int64_t>(bf0) * heads + h0) * tokens + row);
-            }
-        }
         for (int n = 0; n < my_items; ++n) {
         const int item = tb_item(n, k_chunks, grouped);
         const int kc = item % k_chunks, h = (item / k_chunks) % heads, bf = item / (k_chunks * heads);
@@ -451,20 +442,10 @@ attn_spatial_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __g
             // (not yet written) dQ columns of dqkv.  The first version recomputed it in every key-chunk CTA from 2 x 64
             // bytes of uncoalesced global loads per thread and exchanged halves through shared memory + a named barrier —
             // 11 % of the stall samples (profiles/r3s_attn_spatial_bwd_ncu_source.txt).
-            // (loaded one tile ahead, below: the two L2 round trips were exposed at the top of every tile, r6u ncu)
-            const float dsum = dsum_next, l = l_next;
-            {
-                int t2 = t + 1, n2 = n;
-                if (t2 == q_tiles) { t2 = 0; ++n2; }
-                if (n2 < my_items) {
-                    const int item2 = tb_item(n2, k_chunks, grouped);
-                    const int h2 = (item2 / k_chunks) % heads, bf2 = item2 / (k_chunks * heads);
-                    const int q2 = t2 * 128 + row;
-                    const bool ok2 = q2 < tokens;
-                    dsum_next = ok2 ? __ldg(d_rows + (static_cast<int64_t>(bf2) * tokens + q2) * (3 * inner / 2) + h2) : 0.f;
-                    l_next = ok2 ? __ldg(lse + (static_cast<int64_t>(bf2) * heads + h2) * tokens + q2) : INFINITY;
-                }
-            }
+            // (Loading these one tile ahead measured SLOWER — 1.476 vs 1.356 ms per launch, r6w: the two extra live values
+            //  and the item arithmetic cost more than the L2 round trip they hide.)
+            const float dsum = row_ok ? __ldg(d_rows + (row0 + q_idx) * (3 * inner / 2) + h) : 0.f;
+            const float l = row_ok ? __ldg(lse + (static_cast<int64_t>(bf) * heads + h) * tokens + q_idx) : INFINITY;
 
             mbar_wait(s_full, g & 1);
             tc_fence_after();

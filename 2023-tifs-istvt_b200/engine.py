@@ -26,6 +26,7 @@ from . import ops
 PRECISIONS = {"bf16": torch.bfloat16, "fp32": torch.float32}
 _LN2_FOLD = os.environ.get("ISTVT_LN2_FOLD", "1") != "0"
 _ROW_PITCH = os.environ.get("ISTVT_ROW_PITCH", "1") != "0"
+_SEP_FUSE = os.environ.get("ISTVT_SEP_FUSE", "1") != "0"      # 0: depthwise and pointwise as two kernels everywhere (A/B)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -216,10 +217,16 @@ def _run_block(bp: _BlockPack, x: torch.Tensor, taps: Optional[dict], name: str)
     y = x
     for i, sp in enumerate(bp.seps):
         relu_in = bp.start_with_relu and i == 0                        # leading ReLU reads the block input (:82-85)
-        d = ops.dwconv3x3(y, sp.dw, relu_in=relu_in)                   # depthwise (:47)
         last = i == len(bp.seps) - 1
+        act = ops.ACT_NONE if last else ops.ACT_RELU
+        c_in, c_out = y.shape[-1], sp.pw.shape[0]
+        if _SEP_FUSE and y.dtype == torch.bfloat16 and ops.sepconv_fused_supported(c_in, c_out, w):
+            # depthwise + pointwise + BN (+ ReLU) in one kernel: the depthwise result stays on chip (blocks 1 and 2)
+            y = ops.sepconv_fused(y, sp.dw, sp.pw, sp.bias, relu_in, act)
+            continue
+        d = ops.dwconv3x3(y, sp.dw, relu_in=relu_in)                   # depthwise (:47)
         # pointwise + BN (+ the ReLU that precedes the next separable conv) (:48, :69-75)
-        y = ops.gemm(d, sp.pw, bias=sp.bias, act=ops.ACT_NONE if last else ops.ACT_RELU)
+        y = ops.gemm(d, sp.pw, bias=sp.bias, act=act)
         y = y.view(n, h, w, -1)
     return y, skip.view(n, skip_in.shape[1], skip_in.shape[2], -1)
 

@@ -375,6 +375,35 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int = ACT
     return y
 
 
+def sepconv_fused_supported(c: int, n_out: int, w: int) -> bool:
+    """Whether istvt_sepconv_fused_fwd takes this SeparableConv2d (same arithmetic as its host planner): 64-channel
+    groups, <= 256 output channels, and the pointwise weights + two input ring stages within 227 KB of shared memory."""
+    if c % 64 or c > 256 or n_out % 64 or not 64 <= n_out <= 256:
+        return False
+    strips = (w + 37) // 38
+    pairs = ((w + strips - 1) // strips + 1) // 2
+    stage = 5 * (2 * pairs + 2) * 128
+    fixed = 2 * 16384 + 16384 + (c // 64) * n_out * 128 + 1024 + 256
+    return (227 * 1024 - fixed) // stage >= 2
+
+
+def sepconv_fused(x: torch.Tensor, dw: torch.Tensor, pw: torch.Tensor, bias: torch.Tensor, relu_in: bool,
+                  act: int = ACT_NONE) -> torch.Tensor:
+    """act(pointwise(depthwise3x3(relu_in ? relu(x) : x)) + bias) in one kernel (istvt_sepconv_fused_fwd).
+    x: bf16 NHWC [n, h, w, c]; dw: fp32 [3, 3, c]; pw: bf16 [n_out, c]; -> bf16 NHWC [n, h, w, n_out]."""
+    dev = _chk(x, dw, bias)
+    _chk_rows(pw)
+    n, h, w, c = x.shape
+    n_out = pw.shape[0]
+    if x.dtype != torch.bfloat16 or pw.dtype != torch.bfloat16 or pw.shape[1] != c or dw.numel() != 9 * c:
+        raise ValueError("sepconv_fused: bf16 x [n, h, w, c], fp32 dw [3, 3, c], bf16 pw [n_out, c]")
+    y = torch.empty(n, h, w, n_out, dtype=torch.bfloat16, device=dev)
+    with _launch(dev, "sepconv_fused", 2.0 * n * h * w * c * (9 + n_out), _nbytes(x, y, pw)):
+        _lib.check(_lib.lib().istvt_sepconv_fused_fwd(_ptr(x), _ptr(dw), _ptr(pw), _ld(pw), _ptr(bias), _ptr(y), n, h, w, c,
+                                                      n_out, int(relu_in), act, _stream(dev)), "istvt_sepconv_fused_fwd")
+    return y
+
+
 def conv_stem(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     """x: fp32 NCHW [n, 3, h, w]; w: fp32 [32, 3, 3, 3]; -> NHWC [n, ho, wo, 32]."""
     dev = _chk(x, w, bias)

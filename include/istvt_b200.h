@@ -174,6 +174,22 @@ int istvt_dwconv3x3_fwd(const void* x, const float* wt, void* y, int dtype, int 
                         int relu_in, istvt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SeparableConv2d + folded BatchNorm (+ ReLU) in ONE kernel: the depthwise result is produced straight into the
+ * pointwise tensor-core GEMM's shared-memory A tiles and never goes to HBM.
+ * Replaces: SeparableConv2d.forward (xception.py:46-49: conv1 = depthwise 3x3 pad 1 groups=C, pointwise = 1x1) together
+ * with the BatchNorm2d after it (xception.py:69-75, eval mode: scale folded into pw, shift = bias) and the ReLU that
+ * precedes the next separable conv; relu_in = the ReLU in front of THIS one (xception.py:82-85).
+ *   y = act( pw . depthwise3x3( relu_in ? relu(x) : x ) + bias )
+ * x: bf16 NHWC [n, h, w, c]; dw: fp32 [3, 3, c]; pw: bf16 [n_out, c], row pitch ld_pw; bias: fp32 [n_out];
+ * y: bf16 NHWC [n, h, w, n_out]; act: ISTVT_ACT_NONE or ISTVT_ACT_RELU.
+ * Supported: c in {64, 128, 192, 256}, n_out in {64, 128, 192, 256}, weights + rings within 227 KB of shared memory
+ * (every separable conv of entry-flow blocks 1 and 2 except 256 -> 256); otherwise ISTVT_ERR_UNSUPPORTED and the
+ * caller runs istvt_dwconv3x3_fwd + istvt_gemm_fwd.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_sepconv_fused_fwd(const void* x, const float* dw, const void* pw, int64_t ld_pw, const float* bias, void* y,
+                            int n, int h, int w, int c, int n_out, int relu_in, int act, istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Pixel subsampling by 2 in both axes (rows/cols 0, 2, 4, ...): the gather of a stride-2 1x1 convolution.
  * Replaces the stride of Block.skip (xception.py:57, 94); the 1x1 itself is istvt_gemm_fwd.
  * x: NHWC [n, h, w, c]; y: NHWC [n, (h-1)/2+1, (w-1)/2+1, c].

@@ -358,6 +358,37 @@ def check_dwconv():
     return out
 
 
+def check_sepconv_fused():
+    """istvt_sepconv_fused_fwd (depthwise 3x3 + pointwise 1x1 + bias + ReLU, depthwise result kept on chip) vs the two-kernel
+    path it replaces (istvt_dwconv3x3_fwd + istvt_gemm_fwd: same bf16 rounding of the depthwise result, so the two must
+    agree to the last bits of the fp32 accumulation order) and vs an fp32 torch reference; the entry flow's shapes, ragged
+    strips / row blocks, several items per CTA, image borders, all four (relu_in, act) combinations."""
+    ops = _ops()
+    _noTF32()
+    out = {}
+    cases = ((2, 147, 147, 64, 128, False, 1), (1, 147, 147, 128, 128, False, 0), (2, 74, 74, 128, 256, True, 1),
+             (1, 13, 12, 64, 64, True, 0), (3, 20, 17, 192, 192, False, 1), (1, 7, 40, 256, 128, True, 1),
+             (5, 37, 37, 128, 256, True, 0), (1, 1, 1, 64, 128, False, 1), (40, 74, 74, 64, 128, True, 1))
+    for (n, h, w, c, n_out, relu_in, act) in cases:
+        assert ops.sepconv_fused_supported(c, n_out, w)
+        x = _rand(n, h, w, c, seed=c + h).to(torch.bfloat16)
+        dw = _rand(3, 3, c, seed=7) * 0.3
+        pw = (_rand(n_out, c, seed=8) * c ** -0.5).to(torch.bfloat16)
+        bias = _rand(n_out, seed=9) * 0.2
+        got = ops.sepconv_fused(x, dw, pw, bias, relu_in, act)
+        two = ops.gemm(ops.dwconv3x3(x, dw, relu_in), pw, bias=bias, act=act).view(n, h, w, n_out)
+        xin = F.relu(x.float()) if relu_in else x.float()
+        d = F.conv2d(xin.permute(0, 3, 1, 2), dw.permute(2, 0, 1).unsqueeze(1), None, 1, 1, 1, groups=c)
+        d = d.permute(0, 2, 3, 1).to(torch.bfloat16).float()             # the depthwise result is a bf16 operand
+        ref = d.reshape(-1, c) @ pw.float().t() + bias
+        ref = (F.relu(ref) if act else ref).view(n, h, w, n_out)
+        tag = f"{n}x{h}x{w}_{c}_{n_out}"
+        out["ref_" + tag] = _assert_close("sepconv_fused vs torch " + tag, got, ref, TOL_BF16)
+        out["two_" + tag] = _assert_close("sepconv_fused vs dwconv + gemm " + tag, got, two.float(), 4e-3)
+    assert not ops.sepconv_fused_supported(256, 256, 74) and not ops.sepconv_fused_supported(728, 728, 37)
+    return out
+
+
 def check_pool_subsample_tokens():
     ops = _ops()
     out = {}
@@ -886,6 +917,7 @@ CHECKS = {
     "attn_spatial_spiky": check_attn_spatial_spiky,
     "xception_tail": check_xception_tail,
     "dwconv": check_dwconv,
+    "sepconv_fused": check_sepconv_fused,
     "pool_subsample_tokens": check_pool_subsample_tokens,
     "attn_temporal": check_attn_temporal,
     "attn_spatial_f32": check_attn_spatial_f32,

@@ -127,6 +127,12 @@ def dwconv3x3(x, w, relu_in):
     return _nhwc(F.conv2d(xi, w.permute(2, 0, 1)[:, None].contiguous(), None, 1, 1, 1, groups=c), x.dtype)
 
 
+def sepconv_fused(x, dw, pw, bias, relu_in, act=0):
+    d = dwconv3x3(x, dw, relu_in)
+    n, h, w, _ = x.shape
+    return gemm(d, pw, bias=bias, act=act).reshape(n, h, w, -1)
+
+
 def subsample2(x):
     return x[:, ::2, ::2, :].contiguous()
 
@@ -418,7 +424,8 @@ ALL = dict(gemm=gemm, layernorm=layernorm, layernorm_diff=layernorm_diff, attn_j
            block_input_grad=block_input_grad, transpose=transpose, im2col_t=im2col_t, im2col_t_stem=im2col_t_stem,
            gemm_wgrad=gemm_wgrad, colsum=colsum, wgrad=wgrad, gelu=gelu, gelu_bwd=gelu_bwd, cast_bf16=cast_bf16,
            layernorm_bwd=layernorm_bwd, head_bwd=head_bwd, attn_spatial_lse=attn_spatial_lse, attn_spatial_bwd=attn_spatial_bwd,
-           attn_temporal_bwd=attn_temporal_bwd, adamw_step=adamw_step, gemm_act_dual=gemm_act_dual, gemm_dgelu=gemm_dgelu)
+           attn_temporal_bwd=attn_temporal_bwd, adamw_step=adamw_step, gemm_act_dual=gemm_act_dual, gemm_dgelu=gemm_dgelu,
+           sepconv_fused=sepconv_fused)
 
 
 def install(monkeypatch, ops_module):
