@@ -13,9 +13,14 @@
 //   * one thread issues tcgen05.mma (M 128, N = Cout <= 256, K 64 per group) against the pointwise weights, which stay
 //     in shared memory for the life of the CTA; the A tile is double buffered, so the MMAs of group g overlap the
 //     depthwise arithmetic of group g + 1;
+//   * the bias is added by the tensor core: every accumulator starts as ones[128 x 16] . B_bias[N x 16]^T, where the
+//     first two k columns of B_bias hold the bf16 head and tail of the fp32 bias (hi + lo: 16 mantissa bits, far below
+//     the bf16 rounding of the output) — no bias loads or adds in the epilogue;
 //   * 4 epilogue warps (lane = pixel) read the accumulator (double buffered in TMEM: the epilogue of item i overlaps
-//     item i + 1), add the bias, apply the ReLU, and stage 64 output channels at a time in a swizzled slab that ONE 4-D
+//     item i + 1), apply the ReLU, and stage 64 output channels at a time in one of two swizzled slabs that ONE 4-D
 //     TMA store (channels, x, y, image) writes back — image borders and ragged strips are clipped by the tensor map.
+//     (First version: bias through 32 loads + 64 adds per thread and group, one slab, two barriers per group — the
+//     epilogue, not the depthwise arithmetic, set the pace: profiles/r6x_sepconv_fused_ncu_source.txt.)
 // HBM traffic = the input read once (+ 2 halo rows of 5, served by L2) and the output written once.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -34,6 +39,7 @@ constexpr int SF_WARP_PROD = SF_DW_WARPS, SF_WARP_MMA = SF_DW_WARPS + 1, SF_WARP
 constexpr int SF_THREADS = 32 * (SF_DW_WARPS + 2 + SF_EPI_WARPS);      // 512
 constexpr int SF_A_BYTES = 128 * SF_CG * 2;                            // 16 KB: 128 pixels x 64 bf16
 constexpr int SF_SLAB_BYTES = 128 * 128;                               // 16 KB: 128 pixels x 64 bf16 output channels
+constexpr int SF_ONES_BYTES = 128 * 32;                                // 4 KB: A tile of the bias MMA, [128 x 16] SW32
 constexpr int SF_MAX_STAGES = 4;
 
 struct SepFusedPlan {
@@ -59,8 +65,10 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const uint32_t stage_bytes = static_cast<uint32_t>(SF_IN_ROWS * in_w * SF_CG * 2);
     const uint32_t w_chunk = static_cast<uint32_t>(n_out) * 128u;                    // one K group of the weights
     uint8_t* s_a = smem;                                          // 2 x 16 KB
-    uint8_t* s_slab = s_a + 2 * SF_A_BYTES;                       // 16 KB
-    uint8_t* s_w = s_slab + SF_SLAB_BYTES;                        // cgroups x n_out x 128 B
+    uint8_t* s_slab = s_a + 2 * SF_A_BYTES;                       // 2 x 16 KB
+    uint8_t* s_ones = s_slab + 2 * SF_SLAB_BYTES;                 // 4 KB: [128 x 16] K-major SW32, k columns 0 and 1 = 1.0
+    uint8_t* s_bias = s_ones + SF_ONES_BYTES;                     // n_out x 32 B: [n_out x 16] SW32, k 0 / 1 = bias hi / lo
+    uint8_t* s_w = s_bias + 256 * 32;                             // cgroups x n_out x 128 B
     uint8_t* s_in = s_w + plan.cgroups * w_chunk;                 // stages x stage_bytes (128-byte aligned)
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_in + plan.stages * stage_bytes);
     uint64_t* in_full = bars;                        // [SF_MAX_STAGES]
@@ -89,6 +97,23 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         fence_mbar_init();
     }
     if (warp == SF_WARP_MMA) { tmem_alloc(tmem_holder, 512); tmem_relinquish(); }
+    // operands of the bias MMA.  SWIZZLE_32B K-major: row r at r * 32, its 16-byte chunk q at ((q ^ ((r >> 2) & 1)) << 4);
+    // only chunk 0 (k = 0 .. 7) is non-zero
+    for (int r = threadIdx.x; r < 128 + n_out; r += SF_THREADS) {
+        uint32_t first = 0x3F803F80u;                                  // (1.0, 1.0) in bf16
+        uint8_t* row = s_ones + r * 32;
+        if (r >= 128) {
+            const float b = bias[r - 128];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+            first = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+            row = s_bias + (r - 128) * 32;
+        }
+        const int sw = (r >> 2) & 1;                                   // same for both tiles: both start 256-byte aligned
+        *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = make_uint4(first, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -130,6 +155,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             const uint32_t idesc = make_idesc_bf16(128, static_cast<uint32_t>(n_out), 0, 0);
             const uint64_t desc = make_smem_desc(0, 0, 1024, SWZ_128B);
             const uint64_t a_f = (smem_u32(s_a) & 0x3FFFFu) >> 4, w_f = (smem_u32(s_w) & 0x3FFFFu) >> 4;
+            const uint64_t ones_d = make_smem_desc(smem_u32(s_ones), 0, 256, SWZ_32B);
+            const uint64_t bias_d = make_smem_desc(smem_u32(s_bias), 0, 256, SWZ_32B);
             mbar_wait(w_full, 0);
             int ab = 0;
             uint32_t a_phase = 0;
@@ -138,13 +165,14 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 mbar_wait(&acc_empty[acc], ((k >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + acc * 256;
+                umma_f16_ss(d_tmem, ones_d, bias_d, idesc, 0u);          // accumulator = bias (hi + lo)
                 for (int g = 0; g < plan.cgroups; ++g) {
                     mbar_wait_hot(&a_full[ab], a_phase);
                     tc_fence_after();
                     const uint64_t ad = desc | (a_f + ab * (SF_A_BYTES >> 4));
                     const uint64_t bd = desc | (w_f + g * (w_chunk >> 4));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) umma_f16_ss(d_tmem, ad + 2 * j, bd + 2 * j, idesc, (g | j) != 0 ? 1u : 0u);
+                    for (int j = 0; j < 4; ++j) umma_f16_ss(d_tmem, ad + 2 * j, bd + 2 * j, idesc, 1u);
                     umma_commit(&a_empty[ab]);
                     if (++ab == 2) { ab = 0; a_phase ^= 1; }
                 }
@@ -162,15 +190,19 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int wpix = 2 * plan.pairs;               // pixels per tile row
         int slot = 0, ab = 0;
         uint32_t phase = 0, a_phase = 0;
+        float wk[9][4];
+        auto load_weights = [&](int g) {      // this thread's 4 channels of the 3x3 filters of channel group g
+            const int ch = g * SF_CG + cq * 4;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(dw + q * c + ch));
+                wk[q][0] = t.x; wk[q][1] = t.y; wk[q][2] = t.z; wk[q][3] = t.w;
+            }
+        };
+        if (plan.cgroups == 1) load_weights(0);       // one group: the filters stay in registers for the whole kernel
         for (int k = 0; k < my_items; ++k) {
             for (int g = 0; g < plan.cgroups; ++g) {
-                const int ch = g * SF_CG + cq * 4;
-                float wk[9][4];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(dw + q * c + ch));
-                    wk[q][0] = t.x; wk[q][1] = t.y; wk[q][2] = t.z; wk[q][3] = t.w;
-                }
+                if (plan.cgroups > 1) load_weights(g);
                 float acc[SF_ROWS][2][4];
 #pragma unroll
                 for (int r = 0; r < SF_ROWS; ++r)
@@ -218,7 +250,10 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 if (lane == 0) mbar_arrive(&in_empty[slot]);          // the slab has been read by this warp
                 if (++slot == plan.stages) { slot = 0; phase ^= 1; }
                 // A tile: row = pixel (r * wpix + column), 16-byte chunk (cq / 2) ^ (row & 7), 8 bytes per thread
-                mbar_wait(&a_empty[ab], a_phase ^ 1);                 // the MMAs that read this buffer have retired
+                // the MMAs that read this buffer have retired.  (Backing off between polls — nanosleep instead of spinning
+                // next to the epilogue warp that shares the scheduler — measured neutral: 0.813 / 1.164 / 0.457 vs
+                // 0.814 / 1.211 / 0.441 ms on the three layers, r7b.)
+                mbar_wait(&a_empty[ab], a_phase ^ 1);
                 if (active) {
                     const uint32_t abase = smem_u32(s_a) + ab * SF_A_BYTES + (cq & 1) * 8;
 #pragma unroll
@@ -244,8 +279,7 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int quad = warp & 3;                      // TMEM lane quadrant of this warp (warps 12-15 -> 0-3)
         const int p = quad * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t slab = smem_u32(s_slab);
-        const uint32_t srow = slab + p * 128;
+        const uint32_t slab0 = smem_u32(s_slab);
         const bool issuer = warp == SF_WARP_EPI0 && lane == 0;
         for (int k = 0; k < my_items; ++k) {
             int img, x0, y0;
@@ -253,35 +287,51 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             const int acc = k & 1;
             mbar_wait(&acc_full[acc], (k >> 1) & 1);
             tc_fence_after();
-            for (int n0 = 0; n0 < n_out; n0 += 64) {
-                uint32_t o[32];
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tmem + lane_base + acc * 256 + n0 + hh * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float2 b = __ldg(reinterpret_cast<const float2*>(bias + n0 + hh * 32) + j);
-                        float v0 = __uint_as_float(r[2 * j]) + b.x, v1 = __uint_as_float(r[2 * j + 1]) + b.y;
-                        if (act == ISTVT_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                        o[hh * 16 + j] = pack_bf16x2(v0, v1);
-                    }
-                }
-                if (n0 + 64 >= n_out) {       // all TMEM reads of this accumulator are done
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
-                }
-                if (issuer) tma_store_wait_read0();                      // the previous store has left the slab
+            // 128 output channels per round (n_out = 64: one round of 64): two TMEM loads in flight per wait, both slabs
+            // staged, ONE proxy fence + barrier, then one TMA store per slab.  (One 64-channel group per round cost
+            // ~1700 clk per group in fences / barrier latency and made the epilogue the pacing stage, r6y.)
+            for (int n0 = 0; n0 < n_out; n0 += 128) {
+                const int halves = n_out - n0 >= 128 ? 2 : 1;            // 64-channel groups in this round
+                // both slabs were handed to the TMA unit in the previous round; the issuer waits until those stores have
+                // been read out of shared memory, then everybody may overwrite them
+                if (issuer) tma_store_wait_read0();
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * SF_EPI_WARPS) : "memory");
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    sts_u4(srow + ((q ^ (p & 7)) << 4), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                for (int gq = 0; gq < 2; ++gq) {
+                    if (gq >= halves) break;
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(tmem + lane_base + acc * 256 + n0 + gq * 64, r0);
+                    tmem_ld_32x32b_x32(tmem + lane_base + acc * 256 + n0 + gq * 64 + 32, r1);
+                    tmem_ld_wait();
+                    if (n0 + 128 >= n_out && gq == halves - 1) {      // all TMEM reads of this accumulator are done
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    }
+                    uint32_t o[32];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        uint32_t v0 = pack_bf16x2(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+                        uint32_t v1 = pack_bf16x2(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+                        if (act == ISTVT_ACT_RELU) {       // on the rounded pair: max(round(x), 0) == round(max(x, 0))
+                            const __nv_bfloat162 z = __float2bfloat162_rn(0.0f);
+                            const __nv_bfloat162 m0 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&v0), z);
+                            const __nv_bfloat162 m1 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&v1), z);
+                            v0 = *reinterpret_cast<const uint32_t*>(&m0);
+                            v1 = *reinterpret_cast<const uint32_t*>(&m1);
+                        }
+                        o[j] = v0;
+                        o[16 + j] = v1;
+                    }
+                    const uint32_t srow = slab0 + gq * SF_SLAB_BYTES + p * 128;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        sts_u4(srow + ((q ^ (p & 7)) << 4), o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                }
                 fence_proxy_async_smem();
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * SF_EPI_WARPS) : "memory");
                 if (issuer) {
-                    tma_store_4d(&tm_y, slab, n0, x0, y0, img);
+                    for (int gq = 0; gq < halves; ++gq) tma_store_4d(&tm_y, slab0 + gq * SF_SLAB_BYTES, n0 + gq * 64, x0, y0, img);
                     tma_store_commit();
                 }
             }
@@ -307,7 +357,8 @@ static int sepconv_fused_launch(const void* x, const float* dw, const void* pw, 
     pl.items = static_cast<int64_t>(n) * pl.strips * pl.rblocks;
     const int in_w = 2 * pl.pairs + 2;
     const int stage_bytes = SF_IN_ROWS * in_w * SF_CG * 2;
-    const int fixed = 2 * SF_A_BYTES + SF_SLAB_BYTES + pl.cgroups * n_out * 128 + 1024 /*align*/ + 256 /*barriers*/;
+    const int fixed = 2 * SF_A_BYTES + 2 * SF_SLAB_BYTES + SF_ONES_BYTES + 256 * 32 + pl.cgroups * n_out * 128 +
+                      1024 /*align*/ + 256 /*barriers*/;
     pl.stages = (227 * 1024 - fixed) / stage_bytes;
     if (pl.stages > SF_MAX_STAGES) pl.stages = SF_MAX_STAGES;
     if (pl.stages < 2) return ISTVT_ERR_UNSUPPORTED;

@@ -383,7 +383,7 @@ def sepconv_fused_supported(c: int, n_out: int, w: int) -> bool:
     strips = (w + 37) // 38
     pairs = ((w + strips - 1) // strips + 1) // 2
     stage = 5 * (2 * pairs + 2) * 128
-    fixed = 2 * 16384 + 16384 + (c // 64) * n_out * 128 + 1024 + 256
+    fixed = 2 * 16384 + 2 * 16384 + 4096 + 8192 + (c // 64) * n_out * 128 + 1024 + 256
     return (227 * 1024 - fixed) // stage >= 2
 
 
