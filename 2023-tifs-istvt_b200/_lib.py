@@ -51,7 +51,8 @@ SIGNATURES = {
     "istvt_attn_spatial_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "istvt_attn_temporal_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "istvt_layernorm_bwd": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
-    "istvt_layernorm_bwd_ld": [_P, _P, _L, _I, _I, _P, _I, _L, _P, _P, _L, _P, _L, _P, _L, _P, _P, _L, _I, _F, _P],
+    "istvt_layernorm_bwd_ld": [_P, _P, _L, _I, _I, _P, _I, _L, _P, _P, _L, _P, _L, _P, _L, _P, _P, _P, _L, _I, _F, _P],
+    "istvt_gelu_bwd_colsum": [_P, _P, _P, _P, _L, _I, _P],
     "istvt_cast_f32_bf16_rows": [_P, _L, _P, _L, _L, _I, _P],
     "istvt_colsum_ld": [_P, _L, _P, _L, _I, _P],
     "istvt_gelu_fwd": [_P, _P, _L, _P],

@@ -49,17 +49,24 @@ __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, int frames, int tokens_pf,
                      const TX* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ g,
                      bf16* __restrict__ g_bf, bf16* __restrict__ dx_out, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, int64_t rows, int dim, int64_t ld_dy, int64_t ld_x, int64_t ld_g,
-                     int64_t ld_gb, int64_t ld_dx, float eps, int p_prefetch) {
+                     float* __restrict__ dbeta, float* __restrict__ out_colsum, int64_t rows, int dim, int64_t ld_dy,
+                     int64_t ld_x, int64_t ld_g, int64_t ld_gb, int64_t ld_dx, float eps, int p_prefetch) {
     // dgamma / dbeta partials live in a per-warp slab of shared memory (each lane owns its columns, no atomics):
     // keeping them in registers cost 48 registers per thread and held the kernel to one CTA per SM (1.4 TB/s).
-    extern __shared__ __align__(16) float s_part[];          // [warps][2][dim]
+    // out_colsum (optional): column sums of the OUTPUT rows (the updated g, or dx) — the bias gradient of the nn.Linear
+    // whose output gradient this kernel produces (b_2 / b_so / b_to): a third per-warp slab instead of a separate pass
+    // over the rows this kernel has just written (istvt_colsum: 4 launches and 1.6 GB of re-reads per layer).
+    extern __shared__ __align__(16) float s_part[];          // [warps][2 or 3][dim]
     const int lane = threadIdx.x & 31;
     const int nch = dim >> 2;
     const float inv_dim = 1.0f / static_cast<float>(dim);
-    float* s_dg = s_part + (threadIdx.x >> 5) * 2 * dim;
+    const int slabs = out_colsum != nullptr ? 3 : 2;
+    float* s_dg = s_part + (threadIdx.x >> 5) * slabs * dim;
     float* s_db = s_dg + dim;
+    float* s_cs = s_db + dim;                                // only touched when out_colsum != nullptr
     for (int i = lane; i < dim; i += 32) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+    if (out_colsum != nullptr)
+        for (int i = lane; i < dim; i += 32) s_cs[i] = 0.f;
     __syncwarp();
 
     const int64_t wid = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -174,8 +181,17 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
                     for (int e = 0; e < 4; ++e) gv[e] += dx[e];
                     st4(g + row * ld_g + 4 * c, gv);
                     if (g_bf != nullptr) st4(g_bf + row * ld_gb + 4 * c, gv);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dx[e] = gv[e];       // what the column sums take below
                 } else {
                     st4(dx_out + row * ld_dx + 4 * c, dx);
+                }
+                if (out_colsum != nullptr) {
+                    float pc[4];
+                    ld4(s_cs + 4 * c, pc);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pc[e] += dx[e];
+                    st4(s_cs + 4 * c, pc);
                 }
             }
         }
@@ -183,13 +199,15 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
     __syncthreads();
     const int warps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-        float a = 0.f, b = 0.f;
+        float a = 0.f, b = 0.f, cs = 0.f;
         for (int w = 0; w < warps; ++w) {
-            a += s_part[w * 2 * dim + i];
-            b += s_part[w * 2 * dim + dim + i];
+            a += s_part[w * slabs * dim + i];
+            b += s_part[w * slabs * dim + dim + i];
+            if (out_colsum != nullptr) cs += s_part[w * slabs * dim + 2 * dim + i];
         }
         atomicAdd(dgamma + i, a);
         atomicAdd(dbeta + i, b);
+        if (out_colsum != nullptr) atomicAdd(out_colsum + i, cs);
     }
 }
 
@@ -251,6 +269,57 @@ cast_f32_bf16_rows_kernel(const float* __restrict__ x, int64_t ldx, bf16* __rest
     float v[4];
     ld4(x + r * ldx + c, v);
     st4(y + r * ldy + c, v);
+}
+
+// dx = dy * gelu'(x) AND colsum[c] += sum_rows dx[r, c] (the bias gradient of the Linear in front of the GELU, b_1):
+// thread = 8 fixed columns, walking rows with the grid stride, sums in registers -> shared memory -> one atomic per
+// column and CTA.  Replaces istvt_gelu_bwd + istvt_colsum (a second pass over the 944 MB it has just written).
+__global__ void __launch_bounds__(1024)
+gelu_bwd_colsum_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx,
+                       float* __restrict__ colsum, int64_t rows, int cols) {
+    extern __shared__ float s_gc[];                      // [cols]
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) s_gc[i] = 0.f;
+    __syncthreads();
+    const int c8 = cols >> 3;
+    const int rows_per_cta = blockDim.x / c8 > 0 ? blockDim.x / c8 : 1;   // cols / 8 <= 256 is required by the host
+    const int cg = threadIdx.x % c8, rl = threadIdx.x / c8;
+    if (rl < rows_per_cta) {
+        float s[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = 0.f;
+        // four rows in flight per thread (one row at a time was latency bound: 3.2 TB/s against the flat kernel's 5.9)
+        const int64_t rstep = static_cast<int64_t>(gridDim.x) * rows_per_cta;
+        for (int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta + rl; r0 < rows; r0 += 4 * rstep) {
+            uint4 xv[4], dv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = r0 + u * rstep;
+                if (r < rows) {
+                    xv[u] = *reinterpret_cast<const uint4*>(x + r * cols + cg * 8);
+                    dv[u] = *reinterpret_cast<const uint4*>(dy + r * cols + cg * 8);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = r0 + u * rstep;
+                if (r >= rows) break;
+                const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+                float d[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    d[2 * j] = __uint_as_float(dw[j] << 16) * gelu_grad_fast(__uint_as_float(xw[j] << 16));
+                    d[2 * j + 1] = __uint_as_float(dw[j] & 0xffff0000u) * gelu_grad_fast(__uint_as_float(xw[j] & 0xffff0000u));
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s[e] += d[e];
+                store8(dx + r * cols + cg * 8, d);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_gc[cg * 8 + e], s[e]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) atomicAdd(colsum + i, s_gc[i]);
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n4) {
@@ -522,7 +591,7 @@ using namespace istvt;
 extern "C" int istvt_layernorm_bwd_ld(const void* dy, const void* dy2, int64_t ld_dy, int frames, int tokens_per_frame,
                                       const void* x, int x_dtype, int64_t ld_x, const float* gamma, float* g_accum,
                                       int64_t ld_g, void* g_bf16, int64_t ld_gb, void* dx_out, int64_t ld_dx,
-                                      float* dgamma, float* dbeta, int64_t rows, int dim, float eps,
+                                      float* dgamma, float* dbeta, float* out_colsum, int64_t rows, int dim, float eps,
                                       istvt_stream_t stream) {
     ISTVT_REQUIRE(dy && x && gamma && dgamma && dbeta && rows > 0);
     ISTVT_REQUIRE(dim % 4 == 0 && dim <= 768);
@@ -540,29 +609,29 @@ extern "C" int istvt_layernorm_bwd_ld(const void* dy, const void* dy2, int64_t l
     bf16* gb = static_cast<bf16*>(g_bf16);
     bf16* dxo = static_cast<bf16*>(dx_out);
     const unsigned gr = static_cast<unsigned>(blocks);
-    const size_t smem = 8 * 2 * static_cast<size_t>(dim) * sizeof(float);
+    const size_t smem = 8 * (out_colsum != nullptr ? 3 : 2) * static_cast<size_t>(dim) * sizeof(float);
     // ISTVT_LNB_PREFETCH=0: without the L2 prefetches of the next row (A/B measurements)
     static const int pf = []() { const char* e = getenv("ISTVT_LNB_PREFETCH"); return e ? atoi(e) : 1; }();
-    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
-    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
-    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
-    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 768 * 4));
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * 4));
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * 4));
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * 4));
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 768 * 4));
     if (x_dtype == ISTVT_F32) {
         const float* xx = static_cast<const float*>(x);
         if (g_accum)
             layernorm_bwd_kernel<float, true><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
-                                                                   nullptr, dgamma, dbeta, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
+                                                                   nullptr, dgamma, dbeta, out_colsum, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
         else
             layernorm_bwd_kernel<float, false><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
-                                                                    nullptr, dxo, dgamma, dbeta, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
+                                                                    nullptr, dxo, dgamma, dbeta, out_colsum, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
     } else if (x_dtype == ISTVT_BF16) {
         const bf16* xx = static_cast<const bf16*>(x);
         if (g_accum)
             layernorm_bwd_kernel<bf16, true><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, g_accum, gb,
-                                                                  nullptr, dgamma, dbeta, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
+                                                                  nullptr, dgamma, dbeta, out_colsum, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
         else
             layernorm_bwd_kernel<bf16, false><<<gr, 256, smem, st>>>(d1, d2, frames, tokens_per_frame, xx, gamma, nullptr,
-                                                                   nullptr, dxo, dgamma, dbeta, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
+                                                                   nullptr, dxo, dgamma, dbeta, out_colsum, rows, dim, ld_dy, ld_x, ld_g, ld_gb, ld_dx, eps, pf);
     } else {
         return ISTVT_ERR_INVALID_ARG;
     }
@@ -575,7 +644,7 @@ extern "C" int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, 
                                    float* dgamma, float* dbeta, int64_t rows, int dim, float eps,
                                    istvt_stream_t stream) {
     return istvt_layernorm_bwd_ld(dy, dy2, dim, frames, tokens_per_frame, x, x_dtype, dim, gamma, g_accum, dim, g_bf16, dim,
-                                  dx_out, dim, dgamma, dbeta, rows, dim, eps, stream);
+                                  dx_out, dim, dgamma, dbeta, nullptr, rows, dim, eps, stream);
 }
 
 extern "C" int istvt_gelu_fwd(const void* x, void* y, int64_t n, istvt_stream_t stream) {
@@ -590,6 +659,23 @@ extern "C" int istvt_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n
     ISTVT_REQUIRE(dy && x && dx && n > 0 && n % 8 == 0);
     gelu_bwd_kernel<<<nblk(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16*>(dy), static_cast<const bf16*>(x), static_cast<bf16*>(dx), n / 8);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_gelu_bwd_colsum(const void* dy, const void* x, void* dx, float* colsum, int64_t rows, int cols,
+                                     istvt_stream_t stream) {
+    ISTVT_REQUIRE(dy && x && dx && colsum && rows > 0 && cols > 0 && cols % 8 == 0);
+    const int c8 = cols / 8;
+    // thread = 8 columns: up to 1024 threads per CTA so that one CTA covers whole rows (cols <= 8192)
+    ISTVT_REQUIRE(c8 <= 1024);
+    int threads = (c8 <= 256) ? (256 / c8) * c8 : c8;
+    threads = (threads + 31) / 32 * 32;
+    int64_t blocks = static_cast<int64_t>(sm_count()) * (threads <= 512 ? 4 : 2);
+    ISTVT_CHECK_CUDA(cudaFuncSetAttribute(gelu_bwd_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(cols * sizeof(float))));
+    gelu_bwd_colsum_kernel<<<static_cast<unsigned>(blocks), threads, cols * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(dy), static_cast<const bf16*>(x), static_cast<bf16*>(dx), colsum, rows, cols);
     count_launch();
     return launch_status();
 }

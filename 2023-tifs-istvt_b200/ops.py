@@ -683,9 +683,10 @@ def attn_temporal_bwd(qk: torch.Tensor, v: torch.Tensor, dout: torch.Tensor, bat
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
                   g_accum: Optional[torch.Tensor] = None, g_bf16: Optional[torch.Tensor] = None,
                   dy2: Optional[torch.Tensor] = None, frames: int = 0, tokens_per_frame: int = 0,
-                  eps: float = 1e-5) -> Optional[torch.Tensor]:
-    """Returns dx (bf16) unless `g_accum` (fp32, += dx) is given."""
-    dev = _chk(gamma, dgamma, dbeta)
+                  eps: float = 1e-5, out_colsum: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """Returns dx (bf16) unless `g_accum` (fp32, += dx) is given.  `out_colsum` (fp32 [dim], +=): column sums of the
+    rows produced (updated g_accum, or dx) — the bias gradient of the Linear whose output gradient they are."""
+    dev = _chk(gamma, dgamma, dbeta, out_colsum)
     _chk_rows(dy, x, g_accum, g_bf16, dy2)
     dim = x.shape[-1]
     rows = x.numel() // dim
@@ -702,7 +703,8 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dgamma
         _lib.check(_lib.lib().istvt_layernorm_bwd_ld(
             _ptr(dy), _ptr(dy2), _ld(dy), frames, tokens_per_frame, _ptr(x), _dt(x), _ld(x), _ptr(gamma), _ptr(g_accum),
             _ld(g_accum) if g_accum is not None else dim, _ptr(g_bf16), _ld(g_bf16) if g_bf16 is not None else dim,
-            _ptr(dx), _ld(dx) if dx is not None else dim, _ptr(dgamma), _ptr(dbeta), rows, dim, eps, _stream(dev)),
+            _ptr(dx), _ld(dx) if dx is not None else dim, _ptr(dgamma), _ptr(dbeta), _ptr(out_colsum), rows, dim, eps,
+            _stream(dev)),
             "istvt_layernorm_bwd_ld")
     return dx
 
@@ -715,11 +717,17 @@ def gelu(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def gelu_bwd(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    dev = _chk(dy, x)
+def gelu_bwd(dy: torch.Tensor, x: torch.Tensor, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = dy * gelu'(x); `colsum` (fp32 [cols], +=): column sums of dx (x: [rows, cols]) from the same pass."""
+    dev = _chk(dy, x, colsum)
     dx = torch.empty_like(x)
     with _launch(dev, "gelu_bwd", 0.0, _nbytes(dy, x, dx)):
-        _lib.check(_lib.lib().istvt_gelu_bwd(_ptr(dy), _ptr(x), _ptr(dx), x.numel(), _stream(dev)), "istvt_gelu_bwd")
+        if colsum is None:
+            _lib.check(_lib.lib().istvt_gelu_bwd(_ptr(dy), _ptr(x), _ptr(dx), x.numel(), _stream(dev)), "istvt_gelu_bwd")
+        else:
+            cols = x.shape[-1]
+            _lib.check(_lib.lib().istvt_gelu_bwd_colsum(_ptr(dy), _ptr(x), _ptr(dx), _ptr(colsum), x.numel() // cols, cols,
+                                                        _stream(dev)), "istvt_gelu_bwd_colsum")
     return dx
 
 

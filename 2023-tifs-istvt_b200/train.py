@@ -258,6 +258,11 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
     act = lambda: ops.empty_rows((rows, d), BF16, g.device)      # bf16 [rows, 728] operands at the aligned row pitch
     g_bf = ops.cast_bf16(g2, out=act())
     scratch = torch.empty(rows, heads * 64, dtype=torch.float32, device=g.device)
+    # Bias gradients = column sums of the output gradients.  They are taken by the kernel that PRODUCES each gradient
+    # (layernorm_bwd for g / dy1, gelu_bwd for dhpre) instead of by a column-sum pass over what it has just written;
+    # only the very first g (from the head) needs the stand-alone kernel.
+    if wgrad:
+        ops.colsum(g_bf, G[_layer_grad_names(len(layers) - 1)["b_2"]])
     for li in range(len(layers) - 1, -1, -1):
         L, c = layers[li], ctxs[li]
         N = {k: G[v] for k, v in _layer_grad_names(li).items()}
@@ -268,28 +273,30 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
             ctxs[li] = None
             continue
         # ---- MLP (module.py:27-34) ----
-        ops.wgrad(g_bf, c.hid, N["w_2"], bias_grad=N["b_2"])
+        ops.wgrad(g_bf, c.hid, N["w_2"])                    # db_2: column sums of g, taken where g was produced
         if _MLP_FUSE:      # gelu'(hpre) applied in the data-gradient GEMM's epilogue
             dhpre = ops.gemm_dgelu(g_bf, L.wT_2, c.hpre)
+            ops.colsum(dhpre, N["b_1"])
         else:
-            dhpre = ops.gelu_bwd(ops.gemm(g_bf, L.wT_2), c.hpre)
-        ops.wgrad(dhpre, c.zn, N["w_1"], bias_grad=N["b_1"])
+            dhpre = ops.gelu_bwd(ops.gemm(g_bf, L.wT_2), c.hpre, colsum=N["b_1"])
+        ops.wgrad(dhpre, c.zn, N["w_1"])
         dzn = ops.gemm(dhpre, L.wT_1, out=act())
         del dhpre
-        ops.layernorm_bwd(dzn, c.x1.view(rows, d), L.ln3[0], N["ln3_w"], N["ln3_b"], g_accum=g2, g_bf16=g_bf)
+        ops.layernorm_bwd(dzn, c.x1.view(rows, d), L.ln3[0], N["ln3_w"], N["ln3_b"], g_accum=g2, g_bf16=g_bf,
+                          out_colsum=N["b_so"])
         del dzn
         # ---- spatial attention (module.py:81-93) ----
-        ops.wgrad(g_bf, c.as_, N["w_so"], bias_grad=N["b_so"])
+        ops.wgrad(g_bf, c.as_, N["w_so"])
         das = ops.gemm(g_bf, L.wT_so)
         dqkv = ops.attn_spatial_bwd(c.qkv, c.as_, das, c.lse, b * f, p, heads, scale, scratch)
         del das
         ops.wgrad(dqkv, c.yn, N["w_qkv"])
         dyn = ops.gemm(dqkv, L.wT_qkv, out=act())
         del dqkv
-        dy1 = ops.layernorm_bwd(dyn, c.y1, L.ln2[0], N["ln2_w"], N["ln2_b"])
+        dy1 = ops.layernorm_bwd(dyn, c.y1, L.ln2[0], N["ln2_w"], N["ln2_b"], out_colsum=N["b_to"])
         del dyn
         # ---- temporal self-subtract attention (module.py:190-208) ----
-        ops.wgrad(dy1, c.at, N["w_to"], bias_grad=N["b_to"])
+        ops.wgrad(dy1, c.at, N["w_to"])
         dat = ops.gemm(dy1, L.wT_to)
         del dy1
         dqk, dv = ops.attn_temporal_bwd(c.qk, c.v, dat, b, f, p, heads, scale)
@@ -300,7 +307,8 @@ def transformer_backward(vit, layers, ctxs, x_final: torch.Tensor, head, dlogits
         dxn_v = ops.gemm(dv, L.wT_v, out=act())
         del dqk, dv
         ops.layernorm_bwd(dxn_v, c.x0.view(rows, d), L.ln1[0], N["ln1_w"], N["ln1_b"], g_accum=g2, g_bf16=g_bf,
-                          dy2=ddiff, frames=f, tokens_per_frame=p)
+                          dy2=ddiff, frames=f, tokens_per_frame=p,
+                          out_colsum=G[_layer_grad_names(li - 1)["b_2"]] if li > 0 else None)   # db_2 of the layer below
         del ddiff, dxn_v
         ctxs[li] = None     # release this layer's activations
     return g

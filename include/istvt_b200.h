@@ -341,11 +341,17 @@ int istvt_layernorm_bwd(const void* dy, const void* dy2, int frames, int tokens_
 int istvt_layernorm_bwd_ld(const void* dy, const void* dy2, int64_t ld_dy, int frames, int tokens_per_frame,
                            const void* x, int x_dtype, int64_t ld_x, const float* gamma, float* g_accum, int64_t ld_g,
                            void* g_bf16, int64_t ld_gb, void* dx_out, int64_t ld_dx, float* dgamma, float* dbeta,
-                           int64_t rows, int dim, float eps, istvt_stream_t stream);
+                           float* out_colsum, int64_t rows, int dim, float eps, istvt_stream_t stream);
+/* out_colsum (optional, fp32 [dim], +=): column sums of the rows this call produces (the updated g_accum, or dx_out) —
+ * the bias gradient of the nn.Linear whose output gradient they are (net.3 / spatial to_out / temporal to_out). */
 
 /* exact-erf GELU (module.py:28) on bf16, elementwise: forward (training keeps the pre-activation) and backward. */
 int istvt_gelu_fwd(const void* x, void* y, int64_t n, istvt_stream_t stream);
 int istvt_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, istvt_stream_t stream);
+/* The same on a [rows, cols] matrix, also accumulating colsum[c] (fp32, +=) = sum_r dx[r, c]: the bias gradient of
+ * FeedForward.net[0] (module.py:27) without a second pass over dx.  cols % 8 == 0, cols <= 8192. */
+int istvt_gelu_bwd_colsum(const void* dy, const void* x, void* dx, float* colsum, int64_t rows, int cols,
+                          istvt_stream_t stream);
 
 /* fp32 -> bf16 cast (gradient of the fp32 residual stream as a GEMM operand). */
 int istvt_cast_f32_bf16(const float* x, void* y, int64_t n, istvt_stream_t stream);

@@ -643,6 +643,19 @@ def check_layernorm_bwd():
         assert ops.layernorm_bwd(dy, x, g, dg, db, g_accum=acc, g_bf16=gbf) is None
         out[f"acc_{rows}"] = _assert_close("ln_bwd accumulate", acc, want, 5e-3)
         out[f"accbf_{rows}"] = _assert_close("ln_bwd accumulate bf16 copy", gbf, want, TOL_BF16)
+        # fused bias gradient: column sums of the rows produced (dx, or the updated g), added to what is there; row-pitched
+        # operands (the training step's layout)
+        cs = torch.ones(dim, device=DEV)
+        dyp, dxw = ops.pad_rows(dy), xr.grad
+        dg.zero_(); db.zero_()
+        dxp = ops.layernorm_bwd(dyp, x, g, dg, db, out_colsum=cs)
+        assert dxp.stride(0) == ops.row_pitch(dim) and torch.equal(dxp, dx), "pitched operands must not change dx"
+        out[f"cs_dx_{rows}"] = _assert_close("ln_bwd column sums of dx", cs, 1 + dxw.sum(0), 5e-4)
+        acc2, cs2 = _rand(rows, dim, seed=9), torch.zeros(dim, device=DEV)
+        gbp = ops.empty_rows((rows, dim), torch.bfloat16, DEV)
+        ops.layernorm_bwd(dyp, x, g, dg, db, g_accum=acc2, g_bf16=gbp, out_colsum=cs2)
+        assert torch.equal(acc2, acc) and torch.equal(gbp, gbf)
+        out[f"cs_acc_{rows}"] = _assert_close("ln_bwd column sums of g", cs2, want.sum(0), 5e-4)
     # fused self-subtract backward (module.py:192): x [B, F, P, D]
     bsz, f, p = 2, 7, 11
     x = _rand(bsz, f, p, dim, seed=5) * 1.5
@@ -675,6 +688,18 @@ def check_gelu_cast_transpose():
     y.backward(dy.float())
     out["gelu"] = _assert_close("gelu fwd", ops.gelu(x), y, TOL_BF16)
     out["gelu_bwd"] = _assert_close("gelu bwd", ops.gelu_bwd(dy, x), xr.grad, TOL_BF16)
+    for rows in (1000, 37):      # with the fused column sums (bias gradient of net[0]); several / one row per CTA slot
+        cs = torch.ones(2912, device=DEV)
+        got = ops.gelu_bwd(dy[:rows], x[:rows], colsum=cs)
+        assert torch.equal(got, ops.gelu_bwd(dy[:rows], x[:rows])), "the column sums must not change dx"
+        out[f"gelu_bwd_colsum_{rows}"] = _assert_close("gelu bwd column sums", cs, 1 + xr.grad[:rows].sum(0), 1e-3)
+    xs = (_rand(300, 64, seed=4) * 2).to(torch.bfloat16)      # narrow matrix: many rows per CTA
+    dys = _rand(300, 64, seed=5).to(torch.bfloat16)
+    xsr = xs.float().requires_grad_(True)
+    F.gelu(xsr).backward(dys.float())
+    cs = torch.zeros(64, device=DEV)
+    out["gelu_bwd_narrow"] = _assert_close("gelu bwd narrow", ops.gelu_bwd(dys, xs, colsum=cs), xsr.grad, TOL_BF16)
+    out["gelu_bwd_narrow_cs"] = _assert_close("gelu bwd narrow column sums", cs, xsr.grad.sum(0), 1e-3)
     f = _rand(333, 728, seed=3)
     out["cast"] = _assert_close("cast", ops.cast_bf16(f), f, TOL_BF16)
     for (m, c) in ((5068, 728), (64, 64), (1001, 2912), (77, 8)):

@@ -325,11 +325,14 @@ def gelu(x):
     return F.gelu(x.float()).to(x.dtype)
 
 
-def gelu_bwd(dy, x):
+def gelu_bwd(dy, x, colsum=None):
     xf = x.float()
     cdf = 0.5 * (1 + torch.erf(xf * 0.7071067811865476))
     pdf = torch.exp(-0.5 * xf * xf) * 0.3989422804014327
-    return (dy.float() * (cdf + xf * pdf)).to(x.dtype)
+    dx = dy.float() * (cdf + xf * pdf)
+    if colsum is not None:
+        colsum += dx.reshape(-1, x.shape[-1]).sum(0)
+    return dx.to(x.dtype)
 
 
 def cast_bf16(x, out=None):
@@ -339,7 +342,8 @@ def cast_bf16(x, out=None):
     return out
 
 
-def layernorm_bwd(dy, x, gamma, dgamma, dbeta, g_accum=None, g_bf16=None, dy2=None, frames=0, tokens_per_frame=0, eps=1e-5):
+def layernorm_bwd(dy, x, gamma, dgamma, dbeta, g_accum=None, g_bf16=None, dy2=None, frames=0, tokens_per_frame=0, eps=1e-5,
+                  out_colsum=None):
     d = x.shape[-1]
     xf = x.float().reshape(-1, d)
     g = dy.float().reshape(-1, d).clone()
@@ -355,8 +359,12 @@ def layernorm_bwd(dy, x, gamma, dgamma, dbeta, g_accum=None, g_bf16=None, dy2=No
     gg = g * gamma
     dx = rstd * (gg - gg.mean(-1, keepdim=True) - xhat * (gg * xhat).mean(-1, keepdim=True))
     if g_accum is None:
+        if out_colsum is not None:
+            out_colsum += dx.sum(0)
         return dx.reshape(x.shape).to(dy.dtype)
     g_accum += dx.reshape(g_accum.shape)
+    if out_colsum is not None:
+        out_colsum += g_accum.reshape(-1, d).sum(0)
     if g_bf16 is not None:
         g_bf16.copy_(g_accum.reshape(g_bf16.shape))
     return None
