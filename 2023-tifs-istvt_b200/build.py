@@ -34,6 +34,7 @@ SOURCES = [
     "entry_flow.cu",
     "conv_stem_tc.cu",
     "conv3x3_tc.cu",
+    "conv3x3_strip.cu",
     "sepconv_fused.cu",
     "xception_tail.cu",
 ]

@@ -309,22 +309,29 @@ int gemm_bf16_dispatch(const void* a, int64_t a_rows, int64_t lda, const void* w
     }
 }
 
-// conv3x3_tc.cu: conv2's shape (32 -> 64 channels) with the A operand gathered by the SIMT threads
+// conv3x3_tc.cu / conv3x3_strip.cu: conv2's shape (32 -> 64 channels) on dedicated kernels
 int conv3x3_c32_tc_launch(const void* x, const void* wt, const float* bias, void* y, int n, int h, int w, int act,
                           cudaStream_t st);
+int conv3x3_c32_strip_launch(const void* x, const void* wt, const float* bias, void* y, int n, int h, int w, int act,
+                             cudaStream_t st);
 
 // bf16 dense 3x3 stride-1 pad-0 convolution (conv2 of the stem) on the implicit-GEMM path.
 int conv3x3_bf16(const void* x, const void* wt, const float* bias, void* y, int n, int h, int w, int cin, int cout,
                  int act, cudaStream_t stream) {
-    // ISTVT_CONV2_TC=1: conv2's shape on the gathered-operand kernel.  Measured SLOWER than the 9-tap TMA formulation
-    // (1.23 vs 0.91 ms stand-alone, 1.52 vs 1.13 ms inside the C2 step, profiles/README.md r6l), so it is off by default
-    // and kept as the A/B alternative.
-    // (read per call — one getenv per conv2 launch — so that a check can exercise both kernels in one process)
-    const char* gather_e = getenv("ISTVT_CONV2_TC");
-    const bool gather_env = gather_e != nullptr && atoi(gather_e) != 0;
-    if (gather_env && cin == 32 && cout == 64 && (act == ISTVT_ACT_NONE || act == ISTVT_ACT_RELU) && h >= 3 && w >= 3 &&
-        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wt) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
-        return conv3x3_c32_tc_launch(x, wt, bias, y, n, h, w, act, stream);
+    // conv2's shape (32 -> 64): ISTVT_CONV2_KERNEL = taps (default: the 9-tap TMA formulation below, the path of every
+    // other shape; 0.91 ms at the C2 size) | strip (TMA slab -> shared-memory im2col -> tcgen05, conv3x3_strip.cu: 1.01 ms,
+    // r7h — the im2col moves 9x the input through the shared-memory port) | gather (per-thread global loads,
+    // conv3x3_tc.cu: 1.23 ms, r6l).  Read per call so that a check can exercise all three in one process.
+    const char* ke = getenv("ISTVT_CONV2_KERNEL");
+    const char* legacy = getenv("ISTVT_CONV2_TC");
+    const bool shape_ok = cin == 32 && cout == 64 && (act == ISTVT_ACT_NONE || act == ISTVT_ACT_RELU) && h >= 3 && w >= 3 &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wt) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (shape_ok) {
+        const bool gather = (ke != nullptr && ke[0] == 'g') || (ke == nullptr && legacy != nullptr && atoi(legacy) != 0);
+        const bool strip = ke != nullptr && ke[0] == 's';
+        if (gather) return conv3x3_c32_tc_launch(x, wt, bias, y, n, h, w, act, stream);
+        if (strip) return conv3x3_c32_strip_launch(x, wt, bias, y, n, h, w, act, stream);
+    }
     GemmParams p{};
     p.M = static_cast<int64_t>(n) * h * w;  // outputs on the input's grid; junk rows/cols dropped in the epilogue
     p.N = cout; p.K = cin;
