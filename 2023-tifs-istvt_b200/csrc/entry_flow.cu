@@ -417,11 +417,14 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
         const bool st0 = ch_ok && ox < w, st1 = ch_ok && ox + 1 < w;
         const int y_end = min(y0 + plan.seg_h, h);
 
-        float wk[9][4];
+        // fp32 PAIRS: the multiply-adds are FFMA2 (fma.rn.f32x2, sm_100), two per issue slot — the kernel was issue bound
+        // (62 % issue utilisation with 9 of ~14 slots per output on the FMA stream, profiles/README.md r3e)
+        f32x2_t wk[9][2];
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
             const float4 t = ch_ok ? __ldg(reinterpret_cast<const float4*>(wt + q * c + ch)) : make_float4(0, 0, 0, 0);
-            wk[q][0] = t.x; wk[q][1] = t.y; wk[q][2] = t.z; wk[q][3] = t.w;
+            wk[q][0] = f32x2_make(t.x, t.y);
+            wk[q][1] = f32x2_make(t.z, t.w);
         }
         // output pointer of "input row r - 2"; advanced by one image row per input row (no per-store multiplies)
         const int64_t pitch = static_cast<int64_t>(w) * c;
@@ -430,7 +433,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
         // three accumulator sets; at input row r, set r % 3 is fresh (ky = 0), (r-1) % 3 takes ky = 1 and (r-2) % 3
         // takes ky = 2 and is complete (output row r - 2).  Rows 0 / 1 of an item leave garbage in the sets that
         // would belong to output rows -2 / -1: never stored.
-        float acc[3][2][4];
+        f32x2_t acc[3][2][2];
         for (int st = 0; st < n_st; ++st, ++g) {
             if (tid == 0) produce(g + DS_STAGES - 1);
             __syncwarp();
@@ -440,7 +443,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
 #pragma unroll
             for (int i = 0; i < DS_R; ++i) {
                 if (st * DS_R + i >= static_cast<int>(rows_valid) + 2) break;   // slab rows past the segment's last input row (uniform)
-                float f[4][4];
+                f32x2_t f[4][2];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint2 t;
@@ -452,29 +455,32 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __
                         t.x = *reinterpret_cast<uint32_t*>(&lo);
                         t.y = *reinterpret_cast<uint32_t*>(&hi);
                     }
-                    f[q][0] = __uint_as_float(t.x << 16); f[q][1] = __uint_as_float(t.x & 0xffff0000u);
-                    f[q][2] = __uint_as_float(t.y << 16); f[q][3] = __uint_as_float(t.y & 0xffff0000u);
+                    f[q][0] = f32x2_make_bits(t.x << 16, t.x & 0xffff0000u);
+                    f[q][1] = f32x2_make_bits(t.y << 16, t.y & 0xffff0000u);
                 }
                 const int s_new = i % 3, s_mid = (i + 2) % 3, s_old = (i + 1) % 3;   // rows r, r-1, r-2 (DS_R % 3 == 0)
 #pragma unroll
                 for (int o = 0; o < 2; ++o) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float a = acc[s_old][o][e];
-                        a = fmaf(f[o][e], wk[6][e], a); a = fmaf(f[o + 1][e], wk[7][e], a); a = fmaf(f[o + 2][e], wk[8][e], a);
+                    for (int e = 0; e < 2; ++e) {
+                        f32x2_t a = acc[s_old][o][e];
+                        a = f32x2_fma(f[o][e], wk[6][e], a); a = f32x2_fma(f[o + 1][e], wk[7][e], a); a = f32x2_fma(f[o + 2][e], wk[8][e], a);
                         acc[s_old][o][e] = a;
-                        float b = acc[s_mid][o][e];
-                        b = fmaf(f[o][e], wk[3][e], b); b = fmaf(f[o + 1][e], wk[4][e], b); b = fmaf(f[o + 2][e], wk[5][e], b);
+                        f32x2_t b = acc[s_mid][o][e];
+                        b = f32x2_fma(f[o][e], wk[3][e], b); b = f32x2_fma(f[o + 1][e], wk[4][e], b); b = f32x2_fma(f[o + 2][e], wk[5][e], b);
                         acc[s_mid][o][e] = b;
-                        float d = f[o][e] * wk[0][e];
-                        d = fmaf(f[o + 1][e], wk[1][e], d); d = fmaf(f[o + 2][e], wk[2][e], d);
+                        f32x2_t d = f32x2_fma(f[o][e], wk[0][e], 0ull);
+                        d = f32x2_fma(f[o + 1][e], wk[1][e], d); d = f32x2_fma(f[o + 2][e], wk[2][e], d);
                         acc[s_new][o][e] = d;
                     }
                 }
                 // input row r = st * DS_R + i of the segment completes output row y0 + r - 2
                 const bool row_ok = rbase + i < rows_valid;        // unsigned: also false for r < 2
-                stg_bf16x4_pred(yp, acc[s_old][0], row_ok && st0);
-                stg_bf16x4_pred(yp + c, acc[s_old][1], row_ok && st1);
+                float o0[4], o1[4];
+                f32x2_split(acc[s_old][0][0], o0[0], o0[1]); f32x2_split(acc[s_old][0][1], o0[2], o0[3]);
+                f32x2_split(acc[s_old][1][0], o1[0], o1[1]); f32x2_split(acc[s_old][1][1], o1[2], o1[3]);
+                stg_bf16x4_pred(yp, o0, row_ok && st0);
+                stg_bf16x4_pred(yp + c, o1, row_ok && st1);
                 yp += pitch;
             }
             __syncwarp();

@@ -425,6 +425,27 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
     return fmaf(h, erf_x, h);
 }
 
+// Packed fp32 arithmetic (sm_100: FFMA2 — two fp32 FMAs per issue slot on a 64-bit register pair).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f32x2_make(float lo, float hi) {
+    f32x2_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ f32x2_t f32x2_make_bits(uint32_t lo, uint32_t hi) {
+    f32x2_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+__device__ __forceinline__ void f32x2_split(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f32x2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // gelu'(x) = Phi(x) + x phi(x) with the same erf approximation (one rcp, one ex2): the factor the ff2 data-gradient GEMM
 // applies in its epilogue (istvt_gemm_dgelu_fwd) and the stand-alone istvt_gelu_bwd kernel.
 __device__ __forceinline__ float gelu_grad_fast(float x) {

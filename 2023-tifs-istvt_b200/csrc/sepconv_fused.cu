@@ -190,31 +190,32 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int wpix = 2 * plan.pairs;               // pixels per tile row
         int slot = 0, ab = 0;
         uint32_t phase = 0, a_phase = 0;
-        float wk[9][4];
+        // fp32 pairs: FFMA2 (fma.rn.f32x2) does two of the 9 x 4 x 6 multiply-adds of a thread per issue slot — the
+        // depthwise arithmetic is what paces the 128 -> 128 layer (r7a), and the FMA stream was 216 of its ~410 instructions
+        f32x2_t wk[9][2];
         auto load_weights = [&](int g) {      // this thread's 4 channels of the 3x3 filters of channel group g
             const int ch = g * SF_CG + cq * 4;
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(dw + q * c + ch));
-                wk[q][0] = t.x; wk[q][1] = t.y; wk[q][2] = t.z; wk[q][3] = t.w;
+                wk[q][0] = f32x2_make(t.x, t.y);
+                wk[q][1] = f32x2_make(t.z, t.w);
             }
         };
         if (plan.cgroups == 1) load_weights(0);       // one group: the filters stay in registers for the whole kernel
         for (int k = 0; k < my_items; ++k) {
             for (int g = 0; g < plan.cgroups; ++g) {
                 if (plan.cgroups > 1) load_weights(g);
-                float acc[SF_ROWS][2][4];
+                f32x2_t acc[SF_ROWS][2][2];
 #pragma unroll
                 for (int r = 0; r < SF_ROWS; ++r)
 #pragma unroll
-                    for (int o = 0; o < 2; ++o)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[r][o][e] = 0.f;
+                    for (int o = 0; o < 2; ++o) { acc[r][o][0] = 0ull; acc[r][o][1] = 0ull; }
                 mbar_wait(&in_full[slot], phase);
                 const uint32_t srow = smem_u32(s_in) + slot * stage_bytes + (2 * pair_c) * (SF_CG * 2) + cq * 8;
 #pragma unroll
                 for (int i = 0; i < SF_IN_ROWS; ++i) {
-                    float f[4][4];
+                    f32x2_t f[4][2];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint2 t;
@@ -226,8 +227,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                             t.x = *reinterpret_cast<uint32_t*>(&lo);
                             t.y = *reinterpret_cast<uint32_t*>(&hi);
                         }
-                        f[q][0] = __uint_as_float(t.x << 16); f[q][1] = __uint_as_float(t.x & 0xffff0000u);
-                        f[q][2] = __uint_as_float(t.y << 16); f[q][3] = __uint_as_float(t.y & 0xffff0000u);
+                        f[q][0] = f32x2_make_bits(t.x << 16, t.x & 0xffff0000u);      // channels 0, 1 as fp32
+                        f[q][1] = f32x2_make_bits(t.y << 16, t.y & 0xffff0000u);      // channels 2, 3
                     }
                     // input row i is filter row ky of output row i - ky
 #pragma unroll
@@ -237,11 +238,11 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
                         for (int o = 0; o < 2; ++o)
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float a = acc[r][o][e];
-                                a = fmaf(f[o][e], wk[3 * ky][e], a);
-                                a = fmaf(f[o + 1][e], wk[3 * ky + 1][e], a);
-                                a = fmaf(f[o + 2][e], wk[3 * ky + 2][e], a);
+                            for (int e = 0; e < 2; ++e) {
+                                f32x2_t a = acc[r][o][e];
+                                a = f32x2_fma(f[o][e], wk[3 * ky][e], a);
+                                a = f32x2_fma(f[o + 1][e], wk[3 * ky + 1][e], a);
+                                a = f32x2_fma(f[o + 2][e], wk[3 * ky + 2][e], a);
                                 acc[r][o][e] = a;
                             }
                     }
@@ -262,9 +263,11 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                         for (int o = 0; o < 2; ++o) {
                             const int p = r * wpix + 2 * pair_c + o;
                             const uint32_t addr = abase + p * 128 + (((cq >> 1) ^ (p & 7)) << 4);
-                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr),
-                                         "r"(pack_bf16x2(acc[r][o][0], acc[r][o][1])),
-                                         "r"(pack_bf16x2(acc[r][o][2], acc[r][o][3]))
+                            float a0, a1, a2, a3;
+                            f32x2_split(acc[r][o][0], a0, a1);
+                            f32x2_split(acc[r][o][1], a2, a3);
+                            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(pack_bf16x2(a0, a1)),
+                                         "r"(pack_bf16x2(a2, a3))
                                          : "memory");
                         }
                 }
