@@ -10,6 +10,8 @@
 //   O[128 x 64] = P V            P staged in smem (bf16, K-major SW128), V is the MN-major B operand
 //   out = O / rowsum             TMEM -> registers -> global (128 B per row)
 // fp32 path: SIMT validation kernel (online softmax, K/V in smem).
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "simt_util.cuh"
@@ -559,6 +561,10 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
 //     0.338 ms — the per-chunk barrier puts the 4 warps of a scheduler in lockstep, so tcgen05.ld latency no longer
 //     overlaps the MUFU work of sibling warps; halving the TMEM reads (64 B/clk port) did not compensate.
 
+}  // namespace istvt
+#include "attn_spatial_pp.cuh"
+namespace istvt {
+
 // ------------------------------------------------------------------------------------------
 // fp32 validation kernel: one CTA per (frame, head); K and V in shared memory, one query per thread.
 // ------------------------------------------------------------------------------------------
@@ -667,11 +673,26 @@ static int attn_spatial_launch(const void* qkv, void* out, float* probs, float* 
     }
     const float scale_log2 = scale * 1.4426950408889634f;
     if (probs == nullptr) {
-        // production path: persistent pipelined kernel, one CTA per SM
-        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              SP_SMEM));
+        // production path: persistent kernel, one CTA per SM.  Inference default: two query tiles in flight, thread = query
+        // row, online softmax (attn_spatial_pp.cuh).  The training / relevance forward (lse wanted) stays on the exact-max
+        // kernel below: there the dominant key of a row is exactly 1.0 in bf16, and the spatial relevance maps — products
+        // of gradients and probabilities through 12 layers — react to that last bit (profiles/README.md r7o / r7p).
+        // ISTVT_SA_KERNEL=pipe | pp forces one kernel for A/B runs.
         const int items = batch_frames * heads;
         const int grid = items < sm_count() ? items : sm_count();
+        const char* sel = getenv("ISTVT_SA_KERNEL");
+        const bool use_pp = sel != nullptr ? strcmp(sel, "pipe") != 0 : lse == nullptr;
+        if (use_pp) {
+            const char* rnd = getenv("ISTVT_SA_ROUND");
+            auto kern = (rnd != nullptr && strcmp(rnd, "trunc") == 0) ? attn_spatial_pp_kernel<false> : attn_spatial_pp_kernel<true>;
+            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
+            kern<<<grid, S2_THREADS, S2_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens, heads, items,
+                                                    scale_log2);
+            count_launch();
+            return launch_status();
+        }
+        ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              SP_SMEM));
         attn_spatial_pipe_kernel<<<grid, SP_THREADS, SP_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), lse, tokens,
                                                                    heads, items, scale_log2);
         count_launch();

@@ -440,6 +440,11 @@ __device__ __forceinline__ f32x2_t f32x2_make_bits(uint32_t lo, uint32_t hi) {
 __device__ __forceinline__ void f32x2_split(f32x2_t v, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
+__device__ __forceinline__ f32x2_t f32x2_add(f32x2_t a, f32x2_t b) {
+    f32x2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ f32x2_t f32x2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
     f32x2_t d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));

@@ -496,6 +496,26 @@ def check_attn_spatial_bf16():
         out[f"pipe_{name}"] = _assert_close(f"attn_s bf16 pipelined out {name}", o2,
                                             oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 1.5e-2)
         out[f"pipe_vs_map_{name}"] = _assert_close(f"attn_s bf16 pipelined vs map kernel {name}", o2, o, 8e-3)
+        # both persistent kernels forced (the default picks by mode: online-softmax kernel for inference, exact-max kernel
+        # when the log-sum-exp is wanted), each also in its lse mode
+        lse_ref = torch.logsumexp(torch.matmul(split(qkv[:, :512]), split(qkv[:, 512:1024]).transpose(-1, -2)) * scale,
+                                  dim=-1) / math.log(2.0)
+        prev = os.environ.get("ISTVT_SA_KERNEL")
+        try:
+            for kern in ("pp", "pipe"):
+                os.environ["ISTVT_SA_KERNEL"] = kern
+                o3, _ = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=False)
+                o4, lse = ops.attn_spatial_lse(qkv, bf, p, heads, scale)
+                torch.cuda.synchronize()
+                out[f"{kern}_{name}"] = _assert_close(f"attn_s bf16 {kern} kernel out {name}", o3,
+                                                      oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 1.5e-2)
+                assert torch.equal(o3, o4), f"{kern} kernel: lse mode changes the output ({name})"
+                out[f"{kern}_lse_{name}"] = _assert_close(f"attn_s bf16 {kern} kernel lse {name}", lse, lse_ref.float(), 2e-3)
+        finally:
+            if prev is None:
+                os.environ.pop("ISTVT_SA_KERNEL", None)
+            else:
+                os.environ["ISTVT_SA_KERNEL"] = prev
     return out
 
 
@@ -518,15 +538,27 @@ def check_attn_spatial_spiky():
         qkv = qkv.reshape(bf * p, 1536).to(torch.bfloat16)
         split = lambda t: t.float().reshape(bf, p, heads, 64).permute(0, 2, 1, 3)
         oref, _ = _attn_ref(split(qkv[:, :512]), split(qkv[:, 512:1024]), split(qkv[:, 1024:]), scale)
-        o, none = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=False)
-        torch.cuda.synchronize()
-        assert torch.isfinite(o.float()).all(), "non-finite attention output"
-        out[f"spike_{p}_{key}_{int(boost)}"] = _assert_close(
-            f"attn_s spiky key={key} boost={boost}", o, oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 1.5e-2)
-        o2, lse = ops.attn_spatial_lse(qkv, bf, p, heads, scale)          # training forward: same kernel + LSE
         s = torch.einsum("bhid,bhjd->bhij", split(qkv[:, :512]), split(qkv[:, 512:1024])) * scale
         lse_ref = torch.logsumexp(s, dim=-1) * 1.4426950408889634       # log2 domain
-        out[f"lse_{p}_{key}_{int(boost)}"] = _assert_close("attn_s spiky lse", lse, lse_ref, 2e-3)
+        # both persistent kernels: the exact-max one, and the online-softmax one, whose reference is raised in the middle
+        # of a row here (spikes in the first / second half of a 128-key chunk, in the first and in later chunks: the
+        # rescale of O, of the half-written P chunk and of the denominator)
+        prev = os.environ.get("ISTVT_SA_KERNEL")
+        try:
+            for kern in ("pp", "pipe"):
+                os.environ["ISTVT_SA_KERNEL"] = kern
+                o, none = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=False)
+                torch.cuda.synchronize()
+                assert torch.isfinite(o.float()).all(), "non-finite attention output"
+                out[f"spike_{kern}_{p}_{key}_{int(boost)}"] = _assert_close(
+                    f"attn_s spiky {kern} key={key} boost={boost}", o, oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 1.5e-2)
+                o2, lse = ops.attn_spatial_lse(qkv, bf, p, heads, scale)          # training forward: same kernel + LSE
+                out[f"lse_{kern}_{p}_{key}_{int(boost)}"] = _assert_close("attn_s spiky lse", lse, lse_ref, 2e-3)
+        finally:
+            if prev is None:
+                os.environ.pop("ISTVT_SA_KERNEL", None)
+            else:
+                os.environ["ISTVT_SA_KERNEL"] = prev
     return out
 
 
