@@ -563,6 +563,7 @@ attn_spatial_pipe_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat
 
 }  // namespace istvt
 #include "attn_spatial_pp.cuh"
+#include "attn_spatial_pp3.cuh"
 namespace istvt {
 
 // ------------------------------------------------------------------------------------------
@@ -677,11 +678,22 @@ static int attn_spatial_launch(const void* qkv, void* out, float* probs, float* 
         // row, online softmax (attn_spatial_pp.cuh).  The training / relevance forward (lse wanted) stays on the exact-max
         // kernel below: there the dominant key of a row is exactly 1.0 in bf16, and the spatial relevance maps — products
         // of gradients and probabilities through 12 layers — react to that last bit (profiles/README.md r7o / r7p).
-        // ISTVT_SA_KERNEL=pipe | pp forces one kernel for A/B runs.
+        // ISTVT_SA_KERNEL=pipe | pp | pp3 forces one kernel for A/B runs (pp3: inference only).
         const int items = batch_frames * heads;
         const int grid = items < sm_count() ? items : sm_count();
         const char* sel = getenv("ISTVT_SA_KERNEL");
         const bool use_pp = sel != nullptr ? strcmp(sel, "pipe") != 0 : lse == nullptr;
+        const bool use_pp3 = sel != nullptr && strcmp(sel, "pp3") == 0 && lse == nullptr &&
+                             static_cast<int64_t>(batch_frames) * tokens * inner < (int64_t(1) << 31);
+        if (use_pp3) {
+            // three query tiles in flight (attn_spatial_pp3.cuh): measured equal to the two-tile kernel, opt-in
+            ISTVT_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_pp3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  S3_SMEM));
+            attn_spatial_pp3_kernel<<<grid, S3_THREADS, S3_SMEM, st>>>(tm, static_cast<__nv_bfloat16*>(out), tokens, heads,
+                                                                      items, scale_log2);
+            count_launch();
+            return launch_status();
+        }
         if (use_pp) {
             const char* rnd = getenv("ISTVT_SA_ROUND");
             auto kern = (rnd != nullptr && strcmp(rnd, "trunc") == 0) ? attn_spatial_pp_kernel<false> : attn_spatial_pp_kernel<true>;

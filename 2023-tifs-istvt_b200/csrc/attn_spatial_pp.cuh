@@ -59,26 +59,18 @@ __device__ __forceinline__ void s2_sub_max(const uint32_t* r, int vl, float (&mx
 template <bool MASK, bool RNE>
 __device__ __forceinline__ void s2_sub_exp(const uint32_t* r, uint32_t* pk, int vl, f32x2_t sc2, f32x2_t nm2,
                                            f32x2_t (&acc)[2]) {
-    // all 32 exponentials first, their consumers afterwards: a consumer right behind its MUFU pair waits for the MUFU
-    // latency, and with two softmax warps per scheduler nothing else covers it (profiles/README.md r7m: XU pipe 54 %)
-    float e[32];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const f32x2_t x = f32x2_fma(f32x2_make_bits(r[2 * j], r[2 * j + 1]), sc2, nm2);
         float x0, x1;
         f32x2_split(x, x0, x1);
-        e[2 * j] = ex2_approx(x0);
-        e[2 * j + 1] = ex2_approx(x1);
+        float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
         if (MASK) {
-            if (2 * j >= vl) e[2 * j] = 0.0f;
-            if (2 * j + 1 >= vl) e[2 * j + 1] = 0.0f;
+            if (2 * j >= vl) e0 = 0.0f;
+            if (2 * j + 1 >= vl) e1 = 0.0f;
         }
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        acc[j & 1] = f32x2_add(acc[j & 1], f32x2_make(e[2 * j], e[2 * j + 1]));
-        pk[j] = RNE ? pack_bf16x2_rne_alu(e[2 * j], e[2 * j + 1])
-                    : __byte_perm(__float_as_uint(e[2 * j]), __float_as_uint(e[2 * j + 1]), 0x7632);
+        acc[j & 1] = f32x2_add(acc[j & 1], f32x2_make(e0, e1));
+        pk[j] = RNE ? pack_bf16x2_rne_alu(e0, e1) : __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632);
     }
 }
 

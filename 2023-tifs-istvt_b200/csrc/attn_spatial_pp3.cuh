@@ -1,5 +1,9 @@
 // Spatial attention, inference kernel with THREE query tiles in flight per CTA (included by attn_spatial.cu, after
 // attn_spatial_pp.cuh whose softmax helpers it shares).  network/vivit/module.py:84-91.
+// OPT-IN (ISTVT_SA_KERNEL=pp3): parity-green, but it measures the same as the two-tile kernel (0.258 vs 0.260 ms per
+// launch at the C2 size, XU pipe 53 % in both, profiles/README.md r7r / r7u) — a third softmax warp per scheduler does
+// not raise the MUFU occupancy; the warps are not parked on barriers (pv_done 7 %, tcgen05.wait::st 6 %, s_full 4 % of
+// their samples) but issue ~6 instructions per score at 50 % issue utilisation with `wait` as the top stall.
 //
 // Why: with two tiles in flight (attn_spatial_pp_kernel) a scheduler holds two softmax warps; whenever one of them is in
 // its load / max / hand-off phase the other has the MUFU pipe to itself but cannot fill it alone — the XU pipe is 54 %
@@ -246,13 +250,38 @@ attn_spatial_pp3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
                 const float mxs = m_ref * scale_log2;
                 const f32x2_t nm2 = f32x2_make(-mxs, -mxs);
 
-                // ---- rare, warp-uniform: a row raised its reference -> rescale O (needs the previous PV retired);
-                //      before the exponentials so that the 32-register TMEM transfers do not collide with P ----
-                bool pv_waited = false;
+                // ---- P = exp2(S * scale - mxs) -> bf16 pairs -> TMEM, 32 keys at a time (the first store's latency hides
+                //      behind the second half's exponentials); denominator from the unrounded fp32 values.  The group's
+                //      previous PV (issued when the last step's P was complete) has had the load, the maximum and 32
+                //      exponentials to retire before the first store needs the P columns. ----
+                f32x2_t acc[2] = {0ull, 0ull};
+#pragma unroll
+                for (int sb = 0; sb < 2; ++sb) {
+                    uint32_t pk[16];
+                    const int vl = vh - sb * 32;
+                    if (vl >= 32) {
+                        s2_sub_exp<false, true>(r[sb], pk, vl, sc2, nm2, acc);
+                    } else if (vl > 0) {
+                        s2_sub_exp<true, true>(r[sb], pk, vl, sc2, nm2, acc);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                    }
+                    if (sb == 0 && gidx > 0) {
+                        mbar_wait(pv_done + g, (gidx - 1) & 1);
+                        tc_fence_after();
+                    }
+                    tmem_st_32x32b_x16(t_p + sb * 16, pk);
+                }
+                {
+                    float a0, a1, a2, a3;
+                    f32x2_split(acc[0], a0, a1);
+                    f32x2_split(acc[1], a2, a3);
+                    l_run = fmaf(l_run, corr, (a0 + a1) + (a2 + a3));
+                }
+                // ---- rare, warp-uniform: a row raised its reference -> O *= corr before this step's PV accumulates
+                //      (here, where neither the scores nor P are live: two 32-register TMEM transfers) ----
                 if (any_raise) {
-                    mbar_wait(pv_done + g, (gidx - 1) & 1);   // s > 0 here, so gidx > 0
-                    tc_fence_after();
-                    pv_waited = true;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         uint32_t ro[32];
@@ -263,36 +292,6 @@ attn_spatial_pp3_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat1
                         tmem_st_32x32b_x32(t_o + half * 32, ro);
                     }
                 }
-
-                // ---- P = exp2(S * scale - mxs) -> bf16 pairs; denominator from the unrounded fp32 values ----
-                f32x2_t acc[2] = {0ull, 0ull};
-                uint32_t pk[2][16];
-#pragma unroll
-                for (int sb = 0; sb < 2; ++sb) {
-                    const int vl = vh - sb * 32;
-                    if (vl >= 32) {
-                        s2_sub_exp<false, true>(r[sb], pk[sb], vl, sc2, nm2, acc);
-                    } else if (vl > 0) {
-                        s2_sub_exp<true, true>(r[sb], pk[sb], vl, sc2, nm2, acc);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[sb][j] = 0u;
-                    }
-                }
-                {
-                    float a0, a1, a2, a3;
-                    f32x2_split(acc[0], a0, a1);
-                    f32x2_split(acc[1], a2, a3);
-                    l_run = fmaf(l_run, corr, (a0 + a1) + (a2 + a3));
-                }
-                // ---- the group's previous PV (issued when the last step's P was complete) has had this step's
-                //      exponentials to retire: the P columns are free ----
-                if (gidx > 0 && !pv_waited) {
-                    mbar_wait(pv_done + g, (gidx - 1) & 1);
-                    tc_fence_after();
-                }
-                tmem_st_32x32b_x16(t_p, pk[0]);
-                tmem_st_32x32b_x16(t_p + 16, pk[1]);
                 if (s == 0 && t > g) epilogue();           // drain the previous tile's O before PV.0 overwrites it
                 tmem_st_wait();
                 tc_fence_before();

@@ -502,14 +502,15 @@ def check_attn_spatial_bf16():
                                   dim=-1) / math.log(2.0)
         prev = os.environ.get("ISTVT_SA_KERNEL")
         try:
-            for kern in ("pp", "pipe"):
+            for kern in ("pp3", "pp", "pipe"):       # pp3 has no lse mode (the launcher takes pp for it)
                 os.environ["ISTVT_SA_KERNEL"] = kern
                 o3, _ = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=False)
                 o4, lse = ops.attn_spatial_lse(qkv, bf, p, heads, scale)
                 torch.cuda.synchronize()
                 out[f"{kern}_{name}"] = _assert_close(f"attn_s bf16 {kern} kernel out {name}", o3,
                                                       oref.permute(0, 2, 1, 3).reshape(bf * p, 512), 1.5e-2)
-                assert torch.equal(o3, o4), f"{kern} kernel: lse mode changes the output ({name})"
+                if kern != "pp3":
+                    assert torch.equal(o3, o4), f"{kern} kernel: lse mode changes the output ({name})"
                 out[f"{kern}_lse_{name}"] = _assert_close(f"attn_s bf16 {kern} kernel lse {name}", lse, lse_ref.float(), 2e-3)
         finally:
             if prev is None:
@@ -545,7 +546,7 @@ def check_attn_spatial_spiky():
         # rescale of O, of the half-written P chunk and of the denominator)
         prev = os.environ.get("ISTVT_SA_KERNEL")
         try:
-            for kern in ("pp", "pipe"):
+            for kern in ("pp3", "pp", "pipe"):
                 os.environ["ISTVT_SA_KERNEL"] = kern
                 o, none = ops.attn_spatial(qkv, bf, p, heads, scale, want_probs=False)
                 torch.cuda.synchronize()
