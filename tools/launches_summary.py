@@ -11,7 +11,7 @@ import re
 from collections import defaultdict
 
 FAMILIES = [("gemm", r"gemm_tcgen05"), ("attn_joint", r"attn_joint"), ("attn_spatial", r"attn_spatial"), ("attn_temporal", r"attn_temporal"),
-            ("dwconv3x3", r"dwconv3x3"), ("layernorm_diff", r"layernorm_diff"), ("layernorm", r"layernorm"),
+            ("sepconv_fused", r"sepconv_fused"), ("dwconv3x3", r"dwconv3x3"), ("layernorm_diff", r"layernorm_diff"), ("layernorm", r"layernorm"),
             ("pool_add", r"pool_add"), ("conv_stem", r"conv_stem"), ("subsample2", r"subsample2"),
             ("token/head/gather", r"token_fill|token_build|mean_rows|head_kernel|gather_rows")]
 
