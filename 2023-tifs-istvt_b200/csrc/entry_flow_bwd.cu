@@ -284,43 +284,67 @@ pool_add_idx_kernel(const bf16* __restrict__ x, const bf16* __restrict__ skip, b
 }
 
 // dx[n, iy, ix, :] = sum over the (<= 4) windows that contain (iy, ix) of dy[window] where the window's arg-max is
-// this pixel.  Gather form: deterministic, no atomics.
+// this pixel.  Gather form: deterministic, no atomics.  Thread = a 2 x 2 block of input pixels x 8 channels: the block
+// (2a.., 2b..) lies in the four windows (a | a+1, b | b+1) only, so 4 window loads serve 9 (pixel, window) pairs — one
+// thread per pixel read 9 windows for the same four pixels (1.5 TB/s, profiles/README.md r7j); per pixel the windows are
+// added in the same order as before (bit-identical).
 __global__ void __launch_bounds__(256)
 pool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ amax, bf16* __restrict__ dx, int n, int h, int w,
                 int c, int ho, int wo) {
-    // grid = (ceil(w * c/8 / 256), h, n): one 32-bit division per thread (the flat 64-bit index cost three 64-bit
-    // divisions per thread and held the kernel at 1.4 TB/s, profiles/README.md r6f)
+    // grid = (ceil(ceil(w/2) * c/8 / 256), ceil(h/2), n): one 32-bit division per thread
     const int c8 = c >> 3;
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;        // ix * c8 + cg
-    if (col >= w * c8) return;
-    const int ix = col / c8;
-    const int cg = col - ix * c8;
-    const int iy = blockIdx.y;
+    const int wp = (w + 1) >> 1;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;        // b * c8 + cg
+    if (col >= wp * c8) return;
+    const int b = col / c8;
+    const int cg = col - b * c8;
+    const int a = blockIdx.y;
     const int img = blockIdx.z;
-    const int64_t idx = (static_cast<int64_t>(img) * h + iy) * (static_cast<int64_t>(w) * c8) + col;
-    float acc[8];
+    float acc[2][2][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    const int oy_lo = iy >> 1, oy_hi = (iy + 1) >> 1;     // windows oy with 2*oy - 1 <= iy <= 2*oy + 1
-    const int ox_lo = ix >> 1, ox_hi = (ix + 1) >> 1;
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[i][j][e] = 0.f;
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy) {
+        const int oy = a + wy;
         if (oy >= ho) continue;
-        const int ky = iy - (2 * oy - 1);
-        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+#pragma unroll
+        for (int wx = 0; wx < 2; ++wx) {
+            const int ox = b + wx;
             if (ox >= wo) continue;
-            const int code = ky * 3 + (ix - (2 * ox - 1));
             const int64_t o = ((static_cast<int64_t>(img) * ho + oy) * wo + ox) * c + cg * 8;
-            const uint2 a = *reinterpret_cast<const uint2*>(amax + o);
+            const uint2 am = *reinterpret_cast<const uint2*>(amax + o);
             float d[8];
             load8(dy + o, d);
+            // pixel (2a + py, 2b + px) sits at (ky, kx) = (py - 2 wy + 1, px - 2 wx + 1) of this window
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const uint32_t word = e < 4 ? a.x : a.y;
-                if (static_cast<int>((word >> (8 * (e & 3))) & 0xffu) == code) acc[e] += d[e];
+            for (int py = wy; py < 2; ++py) {
+#pragma unroll
+                for (int px = wx; px < 2; ++px) {
+                    const int code = (py - 2 * wy + 1) * 3 + (px - 2 * wx + 1);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const uint32_t word = e < 4 ? am.x : am.y;
+                        if (static_cast<int>((word >> (8 * (e & 3))) & 0xffu) == code) acc[py][px][e] += d[e];
+                    }
+                }
             }
         }
     }
-    store8(dx + idx * 8, acc);
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+        const int iy = 2 * a + py;
+        if (iy >= h) continue;
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+            const int ix = 2 * b + px;
+            if (ix >= w) continue;
+            store8(dx + ((static_cast<int64_t>(img) * h + iy) * w + ix) * c + cg * 8, acc[py][px]);
+        }
+    }
 }
 
 // d_out[n, oy, ox, :] (bf16) = g[b, f+1, 1 + oy*wo + ox, :] (fp32 token gradient)
@@ -516,38 +540,59 @@ block_input_grad_kernel(const bf16* __restrict__ d_main, const bf16* __restrict_
 //   conv1 (3x3 s2 p0, NCHW fp32 input [n, 3, h, w])  :  out[ci*9 + ky*3 + kx, m]  = x[n, ci, 2oy+ky, 2ox+kx]
 //                                                       (rows 27..31 zero so that K' = 32)
 // ------------------------------------------------------------------------------------------
+// CTA = 256 consecutive output pixels x all 9 taps.  The pixel -> input offset map is computed once; per tap every thread
+// loads 16 B (8 channels) of two neighbouring pixels and writes them TRANSPOSED into shared memory as 8 packed 32-bit
+// words (conflict-free: consecutive lanes = consecutive pixel pairs), then the tile leaves as 512-byte row segments with
+// 16-byte stores.  (The first version — 64 pixels x 1 tap per CTA, transposition on the read side of shared memory with
+// 8-way bank conflicts, three 64-bit divisions per load — wrote at 1.0 TB/s, profiles/README.md r7j.)
+constexpr int I2C_PIX = 256;
 __global__ void __launch_bounds__(256)
 im2col_t_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int n, int h, int w, int cin, int64_t ldo) {
-    __shared__ bf16 tile[64][72];       // 64 pixels x up to 64 channels
+    __shared__ int64_t base[I2C_PIX];                       // input pixel index of (img, oy, ox), -1 past the end
+    __shared__ __align__(16) uint32_t tile_t[64][I2C_PIX / 2 + 4];   // [channel][pixel pair], row pitch 528 B (16-byte aligned)
     const int ho = h - 2, wo = w - 2;
     const int64_t m_total = static_cast<int64_t>(n) * ho * wo;
-    const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 64;
-    const int tap = blockIdx.y;
-    const int ky = tap / 3, kx = tap - ky * 3;
-    const int chunks = cin >> 3;
-    for (int i = threadIdx.x; i < 64 * chunks; i += blockDim.x) {
-        const int r = i / chunks, cc = (i - r * chunks) * 8;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        const int64_t m = m0 + r;
+    const int64_t m0 = static_cast<int64_t>(blockIdx.x) * I2C_PIX;
+    {
+        const int64_t m = m0 + threadIdx.x;
+        int64_t bidx = -1;
         if (m < m_total) {
             const int ox = static_cast<int>(m % wo);
             const int64_t q = m / wo;
             const int oy = static_cast<int>(q % ho);
-            const int img = static_cast<int>(q / ho);
-            v = *reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(img) * h + oy + ky) * w + ox + kx) * cin + cc);
+            const int64_t img = q / ho;
+            bidx = (img * h + oy) * w + ox;
         }
-        *reinterpret_cast<uint4*>(&tile[r][cc]) = v;
+        base[threadIdx.x] = bidx;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < cin * 8; i += blockDim.x) {
-        const int ci = i >> 3, mm = (i & 7) * 8;
-        if (m0 + mm < ldo) {
-            bf16 tmp[8];
+    const int chunks = cin >> 3;                            // 16-byte channel chunks per pixel
+    const int n_ld = (I2C_PIX / 2) * chunks;                // (pixel pair, chunk) loads per tap
+    const int n_st = cin * (I2C_PIX / 8);                   // 16-byte stores per tap
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const int64_t shift = static_cast<int64_t>(ky) * w + kx;
+        for (int i = threadIdx.x; i < n_ld; i += blockDim.x) {
+            const int pr = i % (I2C_PIX / 2), cc = (i / (I2C_PIX / 2)) * 8;     // consecutive lanes = consecutive pairs
+            const int64_t b0 = base[2 * pr], b1 = base[2 * pr + 1];
+            uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+            if (b0 >= 0) v0 = *reinterpret_cast<const uint4*>(x + (b0 + shift) * cin + cc);
+            if (b1 >= 0) v1 = *reinterpret_cast<const uint4*>(x + (b1 + shift) * cin + cc);
+            const uint32_t a[4] = {v0.x, v0.y, v0.z, v0.w}, c[4] = {v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) tmp[e] = tile[mm + e][ci];
-            *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(tap) * cin + ci) * ldo + m0 + mm) =
-                *reinterpret_cast<const uint4*>(tmp);
+            for (int e = 0; e < 4; ++e) {
+                tile_t[cc + 2 * e][pr] = __byte_perm(a[e], c[e], 0x5410);         // channel 2e  : (pixel 2pr, pixel 2pr+1)
+                tile_t[cc + 2 * e + 1][pr] = __byte_perm(a[e], c[e], 0x7632);     // channel 2e+1
+            }
         }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_st; i += blockDim.x) {
+            const int ci = i / (I2C_PIX / 8), mm = (i % (I2C_PIX / 8)) * 8;
+            if (m0 + mm < ldo)
+                *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(tap) * cin + ci) * ldo + m0 + mm) =
+                    *reinterpret_cast<const uint4*>(&tile_t[ci][mm >> 1]);
+        }
+        __syncthreads();
     }
 }
 
@@ -681,7 +726,8 @@ extern "C" int istvt_pool_bwd(const void* dy, const void* argmax, void* dx, int 
     ISTVT_REQUIRE(dy && argmax && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0);
     const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
     ISTVT_REQUIRE(h <= 65535 && n <= 65535);
-    const dim3 grid(static_cast<unsigned>((w * (c / 8) + 255) / 256), static_cast<unsigned>(h), static_cast<unsigned>(n));
+    const dim3 grid(static_cast<unsigned>((((w + 1) / 2) * (c / 8) + 255) / 256), static_cast<unsigned>((h + 1) / 2),
+                    static_cast<unsigned>(n));
     pool_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const bf16*>(dy), static_cast<const uint8_t*>(argmax), static_cast<bf16*>(dx), n, h, w, c, ho, wo);
     count_launch();
@@ -739,7 +785,7 @@ extern "C" int istvt_im2col_t(const void* x, void* out, int n, int h, int w, int
                               istvt_stream_t stream) {
     ISTVT_REQUIRE(x && out && n > 0 && h > 2 && w > 2 && cin % 8 == 0 && cin <= 64 && ldo % 8 == 0);
     ISTVT_REQUIRE(ldo >= static_cast<int64_t>(n) * (h - 2) * (w - 2));
-    const dim3 grid(static_cast<unsigned>((ldo + 63) / 64), 9);
+    const dim3 grid(static_cast<unsigned>((ldo + I2C_PIX - 1) / I2C_PIX));
     im2col_t_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x),
                                                                          static_cast<bf16*>(out), n, h, w, cin, ldo);
     count_launch();

@@ -949,6 +949,14 @@ def check_entry_train_kernels():
     m = 2 * 9 * 7
     ref = torch.stack([xb[:, ky:ky + 9, kx:kx + 7, :].reshape(m, 32) for ky in range(3) for kx in range(3)], 0)  # [9, m, 32]
     assert torch.equal(cols[:, :m].reshape(9, 32, m), ref.permute(0, 2, 1)), "im2col_t"
+    # several 256-pixel tiles, image boundaries inside a tile, a ragged last tile, zero fill past the last pixel
+    for (nn, hh, ww, cc) in ((3, 13, 23, 32), (2, 19, 18, 64)):
+        xb = _rand(nn, hh, ww, cc, seed=hh).to(torch.bfloat16)
+        cols = ops.im2col_t(xb)
+        m = nn * (hh - 2) * (ww - 2)
+        ref = torch.stack([xb[:, ky:ky + hh - 2, kx:kx + ww - 2, :].reshape(m, cc) for ky in range(3) for kx in range(3)], 0)
+        assert torch.equal(cols[:, :m].reshape(9, cc, m), ref.permute(0, 2, 1)), f"im2col_t {nn}x{hh}x{ww}x{cc}"
+        assert not cols[:, m:].any(), "im2col_t: columns past the last pixel must be zero"
     xf = _rand(2, 3, 21, 19, seed=2)
     cols = ops.im2col_t_stem(xf)
     ho, wo = 10, 9
