@@ -30,6 +30,8 @@ SIGNATURES = {
     "istvt_gemm_act_dual_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _I, _P],
     "istvt_gemm_dgelu_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _P],
     "istvt_conv3x3_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "istvt_conv3x3_pair_pack": [_P, _P, _I, _P],
+    "istvt_conv3x3_pair_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "istvt_conv_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "istvt_conv_stem_u8_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "istvt_dwconv3x3_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

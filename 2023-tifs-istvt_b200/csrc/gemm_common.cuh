@@ -16,6 +16,8 @@ struct GemmParams {
     int taps;         // 1 (plain GEMM) or 9 (3x3 conv)
     int conv_w_in;    // conv mode: input width  (row shift of tap = ky * conv_w_in + kx)
     int conv_h_in;    // conv mode: input height
+    int pair;         // conv mode on PIXEL PAIRS (conv3x3_pair_launch): A rows are 2 adjacent pixels x cin, N = 2 x cout
+    int tap_shift[9]; // conv mode: A row shift of every tap relative to the tile's first row
     void* C;
     int64_t ldc;
     const float* bias;

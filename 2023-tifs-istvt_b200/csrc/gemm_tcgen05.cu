@@ -108,8 +108,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 // taps x k-blocks as nested counters: this single thread issues every TMA of the CTA, and for the 9-tap
                 // conv (one 12 KB stage per tap) its instruction count per stage — not the ring, not the MMAs — set the
                 // tile period (r4a: a second producer thread for the B boxes alone gave 10 %)
-                int row = static_cast<int>(m0), bcol = 0, kx = 0;
+                int bcol = 0;
                 for (int tap = 0; tap < p.taps; ++tap) {
+                    const int row = static_cast<int>(m0) + p.tap_shift[tap];     // 0 for a plain GEMM
                     for (int kcol = 0; kcol < p.K; kcol += BK) {
                         mbar_wait_hot(&empty_bar[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&full_bar[stage], p.split_producer ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
@@ -119,7 +120,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     bcol += p.K;
-                    if (++kx == 3) { kx = 0; row += p.conv_w_in - 2; } else { ++row; }     // next tap: (ky, kx) row shift
                 }
             }
         }
@@ -204,10 +204,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             // destination row (conv mode compacts the padded grid)
             bool row_ok = m < p.M;
             int64_t drow = m;
+            int ccol = n_blk * BN + col0;
             if (p.taps != 1) {
+                // pixel-pair mode: accumulator row m holds pixels 2m (columns 0..63) and 2m + 1 (columns 64..127)
+                int64_t lin = m;
+                if (p.pair) { lin = 2 * m + (col0 >> 6); ccol = col0 & 63; }
                 const int64_t img_sz = (int64_t)p.conv_h_in * p.conv_w_in;
-                const int64_t img = m / img_sz;
-                const int rem = static_cast<int>(m - img * img_sz);
+                const int64_t img = lin / img_sz;
+                const int rem = static_cast<int>(lin - img * img_sz);
                 const int y = rem / p.conv_w_in;
                 const int x = rem - y * p.conv_w_in;
                 const int ho = p.conv_h_in - 2, wo = p.conv_w_in - 2;
@@ -222,7 +226,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             tc_fence_after();
             uint64_t* te = &tmem_empty[acc];
             gemm_epilogue_64<PLAIN_BF16, PLAIN_BF16 ? 1 : 2>(p, tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, slab, drow_lane, drow_t,
-                             n_blk * BN + col0, lane, [&]() {
+                             ccol, lane, [&]() {
                                  tc_fence_before();
                                  __syncwarp();
                                  if (lane == 0) mbar_arrive(te);
@@ -336,15 +340,83 @@ int conv3x3_bf16(const void* x, const void* wt, const float* bias, void* y, int 
     p.M = static_cast<int64_t>(n) * h * w;  // outputs on the input's grid; junk rows/cols dropped in the epilogue
     p.N = cout; p.K = cin;
     p.taps = 9; p.conv_w_in = w; p.conv_h_in = h;
+    for (int t = 0; t < 9; ++t) p.tap_shift[t] = (t / 3) * w + (t % 3);
     p.C = y; p.ldc = cout;
     p.bias = bias; p.residual = nullptr; p.ldr = 0;
     p.act = act; p.c_f32 = 0;
     return gemm_bf16_dispatch(x, p.M, cin, wt, 9 * static_cast<int64_t>(cin), 9 * cin, p, stream);
 }
 
+// ------------------------------------------------------------------------------------------
+// conv2 (32 -> 64 channels) on PIXEL PAIRS.  The 9-tap formulation above fetches 64-byte box rows (32 channels), 9 x 128 of
+// them per 128-pixel tile, and is bound by the TMA unit's row rate (0.21-0.27 of the HBM roofline).  Two
+// adjacent NHWC pixels are 128 contiguous bytes, so the activation is ALSO a matrix of pixel pairs [n h w / 2, 64]: the
+// output pair (i, i + 1) of the input's linear pixel grid needs the input pixels i + ky W + {0..3} = two aligned pairs
+// when ky W is even, the middle of three pairs when it is odd.  That makes 6 (W even) or 7 (W odd) k-blocks of 64 with
+// 128-byte rows for TWO output pixels — 2.6 x fewer TMA rows per pixel — against a weight matrix [2 x 64, taps x 64]
+// that holds W[co, ky, kx, ci] at (pixel p, co) x (tap, pixel j, ci) with kx = 2 jblk + j - s - p and zeros elsewhere
+// (1.3-1.6 x the multiply-adds, on a tensor pipe that has them to spare).  Same kernel, same epilogue.
+// ------------------------------------------------------------------------------------------
+__global__ void conv3x3_pair_pack_kernel(const __nv_bfloat16* __restrict__ wt, __nv_bfloat16* __restrict__ wpair,
+                                         int parity, int taps) {
+    const int kcols = taps * 64;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 128 * kcols) return;
+    const int r = idx / kcols, c = idx - r * kcols;
+    const int p = r >> 6, co = r & 63;
+    const int t = c >> 6, j = (c >> 5) & 1, ci = c & 31;
+    const int nb1 = parity ? 3 : 2;                     // pair blocks of the ky = 1 row (ky W odd <=> W odd)
+    int ky, jblk, s;
+    if (t < 2) { ky = 0; jblk = t; s = 0; }
+    else if (t < 2 + nb1) { ky = 1; jblk = t - 2; s = parity; }
+    else { ky = 2; jblk = t - 2 - nb1; s = 0; }
+    const int kx = 2 * jblk + j - s - p;
+    wpair[idx] = (kx >= 0 && kx <= 2) ? wt[co * 288 + (ky * 3 + kx) * 32 + ci] : __float2bfloat16(0.0f);
+}
+
+static int conv3x3_pair_taps(int w) { return (w & 1) ? 7 : 6; }
+
+int conv3x3_pair_launch(const void* x, const void* wpair, const float* bias, void* y, int n, int h, int w, int act,
+                        cudaStream_t stream) {
+    const int64_t total = static_cast<int64_t>(n) * h * w;
+    ISTVT_REQUIRE(x && wpair && y && n > 0 && h >= 3 && w >= 3 && (total & 1) == 0);
+    ISTVT_REQUIRE(act == ISTVT_ACT_NONE || act == ISTVT_ACT_RELU);
+    GemmParams p{};
+    p.M = total / 2;  // pair rows on the input's grid; junk pixels dropped in the epilogue
+    p.N = 128; p.K = 64;
+    p.conv_w_in = w; p.conv_h_in = h; p.pair = 1;
+    int t = 0;
+    for (int ky = 0; ky < 3; ++ky) {
+        const int64_t off = static_cast<int64_t>(ky) * w;
+        const int s = static_cast<int>(off & 1);
+        const int nb = s ? 3 : 2;
+        for (int j = 0; j < nb; ++j) p.tap_shift[t++] = static_cast<int>((off - s) / 2) + j;
+    }
+    p.taps = t;
+    p.C = y; p.ldc = 64;
+    p.bias = bias; p.residual = nullptr; p.ldr = 0;
+    p.act = act; p.c_f32 = 0;
+    return gemm_bf16_dispatch(x, total / 2, 64, wpair, 64 * static_cast<int64_t>(t), 64 * t, p, stream);
+}
+
 }  // namespace istvt
 
 using namespace istvt;
+
+extern "C" int istvt_conv3x3_pair_pack(const void* wt, void* wpair, int w_in, istvt_stream_t stream) {
+    ISTVT_REQUIRE(wt && wpair && w_in >= 3);
+    const int taps = conv3x3_pair_taps(w_in);
+    const int total = 128 * taps * 64;
+    conv3x3_pair_pack_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(wt), static_cast<__nv_bfloat16*>(wpair), w_in & 1, taps);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int istvt_conv3x3_pair_fwd(const void* x, const void* wpair, const float* bias, void* y, int n, int h, int w,
+                                      int act, istvt_stream_t stream) {
+    return conv3x3_pair_launch(x, wpair, bias, y, n, h, w, act, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int istvt_gemm_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, void* c, int64_t ldc,
                               int c_dtype, int64_t m, int n, int k, const float* bias, const float* residual,

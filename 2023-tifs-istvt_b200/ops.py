@@ -361,14 +361,48 @@ def gemm_lnfold(a: torch.Tensor, w_folded: torch.Tensor, mu_rstd: torch.Tensor, 
     return out
 
 
-def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int = ACT_RELU) -> torch.Tensor:
-    """x: NHWC [n, h, w, cin]; w: [cout, 3, 3, cin] (same dtype); -> NHWC [n, h-2, w-2, cout]."""
+_CONV2_PAIR = os.environ.get("ISTVT_CONV2_KERNEL", "pair") == "pair"   # taps | strip | gather: istvt_conv3x3_fwd's own switch
+
+
+def conv3x3_pair_weights(w: torch.Tensor, w_in: int) -> torch.Tensor:
+    """conv2's weights [64, 3, 3, 32] (bf16) rearranged for the pixel-pair kernel: [128, taps * 64], taps = 7 / 6 for an odd
+    / even input width.  Memoised ON the weight tensor (per parity, invalidated by its version counter): an inference pack
+    is rearranged once, a training step — whose folded weight is a new tensor every step — once per step."""
+    memo = getattr(w, "_istvt_pair", None)
+    if memo is None:
+        memo = {}
+        w._istvt_pair = memo
+    hit = memo.get(w_in & 1)
+    if hit is None or hit[0] != w._version:
+        taps = 7 if (w_in & 1) else 6
+        wp = torch.empty(128, taps * 64, dtype=torch.bfloat16, device=w.device)
+        with _launch(w.device, "conv3x3_pack", 0.0, _nbytes(w, wp)):
+            _lib.check(_lib.lib().istvt_conv3x3_pair_pack(_ptr(w), _ptr(wp), w_in, _stream(w.device)),
+                       "istvt_conv3x3_pair_pack")
+        hit = (w._version, wp)
+        memo[w_in & 1] = hit
+    return hit[1]
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, act: int = ACT_RELU, kernel: Optional[str] = None
+            ) -> torch.Tensor:
+    """x: NHWC [n, h, w, cin]; w: [cout, 3, 3, cin] (same dtype); -> NHWC [n, h-2, w-2, cout].
+    conv2's shape (bf16, 32 -> 64, an even number of input pixels) runs on the pixel-pair kernel unless
+    ISTVT_CONV2_KERNEL / `kernel` names another construction."""
     dev = _chk(x, w, bias)
     n, h, wd, cin = x.shape
     cout = w.shape[0]
     if tuple(w.shape) != (cout, 3, 3, cin) or w.dtype != x.dtype:
         raise ValueError("conv3x3: weight must be [cout, 3, 3, cin] in the activation dtype")
     y = torch.empty(n, h - 2, wd - 2, cout, dtype=x.dtype, device=dev)
+    pair = _CONV2_PAIR if kernel is None else kernel == "pair"
+    if (pair and x.dtype == torch.bfloat16 and cin == 32 and cout == 64 and (n * h * wd) % 2 == 0
+            and act in (ACT_NONE, ACT_RELU) and x.is_contiguous() and w.is_contiguous()):
+        wp = conv3x3_pair_weights(w, wd)
+        with _launch(dev, "conv3x3", 2.0 * y.numel() * 9 * cin, _nbytes(x, w, y)):
+            _lib.check(_lib.lib().istvt_conv3x3_pair_fwd(_ptr(x), _ptr(wp), _ptr(bias), _ptr(y), n, h, wd, act,
+                                                         _stream(dev)), "istvt_conv3x3_pair_fwd")
+        return y
     with _launch(dev, "conv3x3", 2.0 * y.numel() * 9 * cin, _nbytes(x, w, y)):
         _lib.check(_lib.lib().istvt_conv3x3_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), _dt(x), n, h, wd, cin, cout,
                                                 act, _stream(dev)), "istvt_conv3x3_fwd")

@@ -145,6 +145,20 @@ int istvt_conv3x3_fwd(const void* x, const void* wt, const float* bias, void* y,
                       int cin, int cout, int act, istvt_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The same convolution for conv2's shape (bf16, 32 -> 64 channels) on PIXEL PAIRS: two adjacent NHWC pixels are one
+ * 128-byte row of a [n h w / 2, 64] matrix, so the implicit GEMM fetches whole 128-byte lines (6 or 7 k-blocks of 64
+ * for two output pixels instead of 9 x 32 for one) against a rearranged, zero-padded weight matrix.
+ * Replaces: conv2 + bn2 + relu, xception.py:122-123,198-200 (same results as istvt_conv3x3_fwd up to fp32 summation
+ * order).  n * h * w must be even.
+ * istvt_conv3x3_pair_pack: wt bf16 [64, 3, 3, 32] (BN scale folded) -> wpair bf16 [128, taps * 64], taps = 7 when the
+ *   input width w_in is odd and 6 when it is even (the layout depends on w_in's parity only).
+ * istvt_conv3x3_pair_fwd:  x NHWC bf16 [n, h, w, 32]; bias fp32 [64]; y NHWC bf16 [n, h-2, w-2, 64]; act none / ReLU.
+ * ------------------------------------------------------------------------------------------- */
+int istvt_conv3x3_pair_pack(const void* wt, void* wpair, int w_in, istvt_stream_t stream);
+int istvt_conv3x3_pair_fwd(const void* x, const void* wpair, const float* bias, void* y, int n, int h, int w, int act,
+                           istvt_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Stem: 3x3 stride-2 pad-0 convolution 3 -> cout on an NCHW fp32 clip + folded BN + ReLU, NHWC out.
  * Replaces: conv1 + bn1 + relu, xception.py:118-120,194-196 (input rearrange vivit.py:204 is a view).
  * x: fp32 NCHW [n, 3, h, w]; wt: fp32 [cout, 3, 3, 3] (BN scale folded); bias fp32 [cout];

@@ -260,20 +260,23 @@ def check_conv3x3():
         got = ops.conv3x3(x, wt, b, act=0)
         out[f"noact_{cin}_{cout}"] = _assert_close(f"conv3x3 no act {cin}->{cout}", got.reshape(-1, cout),
                                                    ref.reshape(-1, cout), TOL_BF16)
-    # conv2's shape (32 -> 64) has three kernels: the default 9-tap TMA formulation (exercised above), the strip kernel
-    # (conv3x3_strip.cu) and the gathered-operand kernel (conv3x3_tc.cu) — both measured slower and kept as A/B
-    # alternatives: same answers from all of them, ragged strips / row blocks / last tiles included, several items per CTA
+    # conv2's shape (32 -> 64) has four kernels: the pixel-pair formulation (default when the number of input pixels is
+    # even; odd and even input widths take 7 / 6 k-blocks), the 9-tap TMA formulation (every other shape), the strip
+    # kernel (conv3x3_strip.cu) and the gathered-operand kernel (conv3x3_tc.cu) — the last two measured slower and kept
+    # as A/B alternatives: same answers from all of them, ragged strips / row blocks / last tiles included, several items
+    # per CTA, 1 x 1 outputs
     prev = os.environ.get("ISTVT_CONV2_KERNEL")
     try:
-        for kern in ("strip", "taps", "gather"):
+        for kern in ("pair", "strip", "taps", "gather"):
             os.environ["ISTVT_CONV2_KERNEL"] = kern
-            for (n, h, w, act) in ((2, 13, 12, 0), (1, 149, 149, 1), (40, 41, 78, 1), (3, 3, 3, 0)):
+            for (n, h, w, act) in ((2, 13, 12, 0), (1, 149, 149, 1), (2, 149, 149, 1), (40, 41, 78, 1), (3, 3, 3, 0),
+                                   (2, 3, 3, 1), (4, 5, 4, 0), (6, 37, 51, 1)):
                 x = _rand(n, h, w, 32, seed=h).to(torch.bfloat16)
                 wt = (_rand(64, 3, 3, 32, seed=7) / math.sqrt(288)).to(torch.bfloat16)
                 b = _rand(64, seed=8) * 0.1
                 ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), b)
                 ref = (ref.relu() if act else ref).permute(0, 2, 3, 1)
-                got = ops.conv3x3(x, wt, b, act=act)
+                got = ops.conv3x3(x, wt, b, act=act, kernel=kern)
                 out[f"{kern}_{n}x{h}x{w}"] = _assert_close(f"conv3x3 {kern} {n}x{h}x{w}", got.reshape(-1, 64),
                                                            ref.reshape(-1, 64), TOL_BF16)
     finally:

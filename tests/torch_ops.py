@@ -114,7 +114,7 @@ def conv_stem_u8(x, w, bias, out_dtype):
     return _nhwc(F.relu(F.conv2d(_nchw(x), w, bias, stride=2)), out_dtype)
 
 
-def conv3x3(x, w, bias, act=1):
+def conv3x3(x, w, bias, act=1, kernel=None):
     y = F.conv2d(_nchw(x), w.float().permute(0, 3, 1, 2), bias)
     return _nhwc(F.relu(y) if act == 1 else y, x.dtype)
 
