@@ -18,6 +18,7 @@ struct GemmParams {
     int conv_h_in;    // conv mode: input height
     int pair;         // conv mode on PIXEL PAIRS (conv3x3_pair_launch): A rows are 2 adjacent pixels x cin, N = 2 x cout
     int tap_shift[9]; // conv mode: A row shift of every tap relative to the tile's first row
+    int b_resident;   // 1-CTA kernel, one N tile: the whole weight matrix is loaded into shared memory once per CTA
     void* C;
     int64_t ldc;
     const float* bias;

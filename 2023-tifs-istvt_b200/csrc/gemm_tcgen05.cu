@@ -54,6 +54,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+    uint8_t* smem_bres = smem;          // b_resident: [num_kb][B_BYTES] in front of a shorter A ring
     uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_WARPS * Cfg::SLAB);
     uint64_t* full_bar = bars;
@@ -61,6 +62,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     uint64_t* tmem_full = bars + 2 * STAGES;
     uint64_t* tmem_empty = bars + 2 * STAGES + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* b_full = bars + 2 * STAGES + 5;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -70,6 +72,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     const int n_tiles = (p.N + BN - 1) / BN;
     const int64_t m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
     const int64_t total_tiles = m_tiles * n_tiles;
+    // Weights resident in shared memory (conv2 on pixel pairs: 7 x 16 KB): without it every k-block fetches its B box from
+    // L2 again, and A + B fills ran at ~3/4 of one SM's L2 port (profiles/README.md r8h).  The A ring shrinks accordingly.
+    const bool b_res = p.b_resident != 0;
+    int nst = STAGES;
+    if (b_res) {
+        nst = (STAGES * Cfg::STAGE_BYTES - num_kb * Cfg::B_BYTES) / Cfg::A_BYTES;
+        if (nst > STAGES) nst = STAGES;
+        smem_a = smem + num_kb * Cfg::B_BYTES;
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -84,6 +95,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], Cfg::EPI_WARPS);
         }
+        mbar_init(b_full, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -100,6 +112,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            if (b_res && total_tiles > static_cast<int64_t>(blockIdx.x)) {
+                mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(num_kb) * Cfg::B_BYTES);
+                int kb = 0;
+                for (int tap = 0; tap < p.taps; ++tap)
+                    for (int kcol = 0; kcol < p.K; kcol += BK, ++kb)
+                        tma_load_2d(smem_bres + kb * Cfg::B_BYTES, &tm_b, b_full, tap * p.K + kcol, 0);
+            }
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int64_t m_blk = tile / n_tiles;
                 const int n_blk = static_cast<int>(tile % n_tiles);
@@ -113,11 +132,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const int row = static_cast<int>(m0) + p.tap_shift[tap];     // 0 for a plain GEMM
                     for (int kcol = 0; kcol < p.K; kcol += BK) {
                         mbar_wait_hot(&empty_bar[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], p.split_producer ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
+                        mbar_arrive_expect_tx(&full_bar[stage], (p.split_producer || b_res) ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
                         tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tm_a, &full_bar[stage], kcol, row);
-                        if (!p.split_producer)
+                        if (!p.split_producer && !b_res)
                             tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tm_b, &full_bar[stage], bcol + kcol, n0);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == nst) { stage = 0; phase ^= 1; }
                     }
                     bcol += p.K;
                 }
@@ -150,7 +169,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             constexpr int KSTEPS = BK / UMMA_K;
             const uint64_t desc_hi = make_smem_desc(0, 0, Cfg::SBO, Cfg::SWZ);
             const uint32_t a_field0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4;
-            const uint32_t b_field0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
+            const uint32_t b_field0 = (smem_u32(b_res ? smem_bres : smem_b) & 0x3FFFFu) >> 4;
+            if (b_res) {
+                mbar_wait(b_full, 0);
+                tc_fence_after();
+            }
             // MMAs of the last k-block of a tap (ragged K: the TMA zero-fills, whole zero k-steps are skipped)
             const int last_steps = (p.K - (kb_per_tap - 1) * BK + UMMA_K - 1) / UMMA_K;
             int stage = 0;
@@ -170,7 +193,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     mbar_wait_hot(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t a_desc = desc_hi | (a_field0 + stage * (Cfg::A_BYTES >> 4));
-                    const uint64_t b_desc = desc_hi | (b_field0 + stage * (Cfg::B_BYTES >> 4));
+                    const uint64_t b_desc = desc_hi | (b_field0 + (b_res ? kb : stage) * (Cfg::B_BYTES >> 4));
                     const bool tap_end = (++kb_in_tap == kb_per_tap);
                     if (tap_end) kb_in_tap = 0;
                     if (!tap_end || last_steps == KSTEPS) {
@@ -183,7 +206,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     }
                     umma_commit(&empty_bar[stage]);                      // smem slot free when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -254,6 +277,12 @@ static int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const G
     static const int split_env = []() { const char* e = getenv("ISTVT_G1_SPLIT_PRODUCER"); return e ? atoi(e) : -1; }();
     GemmParams q = p;
     q.split_producer = split_env >= 0 ? split_env : (p.taps > 1 ? 1 : 0);
+    if (q.b_resident) {   // one N tile, and room for the weights plus at least two A stages
+        using C0 = GemmCfg<BN, BK, true>;
+        const int num_kb = ((p.K + BK - 1) / BK) * p.taps;
+        if (n_tiles != 1 || num_kb * C0::B_BYTES + 2 * C0::A_BYTES > C0::STAGES * C0::STAGE_BYTES) q.b_resident = 0;
+        else q.split_producer = 0;
+    }
     if (!p.c_f32 && p.residual == nullptr) {
         using Cfg = GemmCfg<BN, BK, true>;
         auto kern = gemm_tcgen05_kernel<BN, BK, true>;
@@ -393,6 +422,7 @@ int conv3x3_pair_launch(const void* x, const void* wpair, const float* bias, voi
         for (int j = 0; j < nb; ++j) p.tap_shift[t++] = static_cast<int>((off - s) / 2) + j;
     }
     p.taps = t;
+    p.b_resident = 1;   // 7 x 16 KB of weights stay in shared memory; the A ring keeps 5 of its 6 stages
     p.C = y; p.ldc = 64;
     p.bias = bias; p.residual = nullptr; p.ldr = 0;
     p.act = act; p.c_f32 = 0;
