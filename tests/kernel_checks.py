@@ -284,6 +284,14 @@ def check_conv3x3():
             os.environ.pop("ISTVT_CONV2_KERNEL", None)
         else:
             os.environ["ISTVT_CONV2_KERNEL"] = prev
+    # the CUDA weight rearrangement of the pixel-pair kernel against its torch mirror (tests/torch_ops.py), bit for bit
+    import torch_ops
+    for w_in in (149, 78):
+        wt = (_rand(64, 3, 3, 32, seed=w_in) / math.sqrt(288)).to(torch.bfloat16)
+        wp = ops.conv3x3_pair_weights(wt, w_in)
+        torch.cuda.synchronize()
+        assert torch.equal(wp.cpu(), torch_ops.conv3x3_pair_pack_ref(wt.cpu(), w_in)), f"conv3x3_pair_pack w_in={w_in}"
+        assert ops.conv3x3_pair_weights(wt, w_in) is wp, "pair weights must be memoised on the weight tensor"
     return out
 
 

@@ -451,3 +451,49 @@ def install(monkeypatch, ops_module):
         monkeypatch.setattr(ops_module, name, rec(name, fn))
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True), raising=False)
     return calls
+
+
+# ---- conv2 on pixel pairs: a torch mirror of conv3x3_pair_pack_kernel / conv3x3_pair_launch (csrc/gemm_tcgen05.cu) ----
+def conv3x3_pair_taps(w_in):
+    """[(ky, jblk, s, pair-row shift)] in the kernel's k-block order for an input of width w_in."""
+    taps = []
+    for ky in range(3):
+        off = ky * w_in
+        s = off & 1
+        for jblk in range(3 if s else 2):
+            taps.append((ky, jblk, s, (off - s) // 2 + jblk))
+    return taps
+
+
+def conv3x3_pair_pack_ref(wt, w_in):
+    """wt [64, 3, 3, 32] -> [128, taps * 64]: row = (output pixel p of the pair, co), column = (k-block, input pixel j of
+    the pair, ci); W[co, ky, kx, ci] with kx = 2 jblk + j - s - p, zero where kx is outside the filter."""
+    taps = conv3x3_pair_taps(w_in)
+    out = torch.zeros(128, len(taps) * 64, dtype=wt.dtype)
+    for t, (ky, jblk, s, _) in enumerate(taps):
+        for p in range(2):
+            for j in range(2):
+                kx = 2 * jblk + j - s - p
+                if 0 <= kx <= 2:
+                    out[p * 64:(p + 1) * 64, t * 64 + j * 32:t * 64 + (j + 1) * 32] = wt[:, ky, kx, :]
+    return out
+
+
+def conv3x3_pair_ref(x, wt, bias, act=1):
+    """The kernel's data movement in torch: the NHWC input as a matrix of pixel pairs [n h w / 2, 64], one GEMM per k-block
+    on the matrix shifted down by the block's pair-row shift (zero fill past the end), outputs on the input's pixel grid
+    with the junk columns / rows dropped."""
+    n, h, w, cin = x.shape
+    assert cin == 32 and (n * h * w) % 2 == 0
+    taps = conv3x3_pair_taps(w)
+    wp = conv3x3_pair_pack_ref(wt.float(), w)
+    a = x.float().reshape(-1, 64)                          # pair rows
+    m = a.shape[0]
+    acc = torch.zeros(m, 128)
+    for t, (_, _, _, shift) in enumerate(taps):
+        sh = torch.zeros_like(a)
+        if shift < m:
+            sh[:m - shift] = a[shift:]
+        acc += sh @ wp[:, t * 64:(t + 1) * 64].t()
+    y = (acc.reshape(m * 2, 64) + bias.float()).reshape(n, h, w, 64)[:, :h - 2, :w - 2]
+    return (F.relu(y) if act == 1 else y).to(x.dtype)
