@@ -16,8 +16,9 @@ One JSON line on rank 0:
                HOST clips, H2D copy of every step's batch and D2H read of its logits inside the timed region;
                the copy of step i+1 overlaps the forward of step i (`serial_value`: no overlap, reference loop shape)
   roofline     the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs of its launches / their summed
-               CUDA-event durations, measured live in the timed region (ops.LaunchRecorder), against the
-               measured bf16 peak in MEASURED_PEAKS.json (or the profiling guide's fallback)
+               CUDA-event durations, measured live in the timed region (ops.LaunchRecorder: events around every
+               launch of every REC_STRIDE-th timed step — instrumenting all of them costs 0.5 ms per step), against
+               the measured bf16 peak in MEASURED_PEAKS.json (or the profiling guide's fallback)
   cpu_baseline the reference forward on the host cores (fp32, all host threads) on a bounded sample of the same
                workload — rank 0, N=1 only.  kind "reference": the UNMODIFIED reference modules staged under
                oracle/_ref by oracle/make_ref.py (they travel with the gpurun snapshot); kind "port": the oracle
@@ -45,6 +46,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 PKG = "2023-tifs-istvt_b200"
 
+REC_STRIDE = 5      # per-launch CUDA events on every REC_STRIDE-th timed step (0.5 ms per instrumented step)
 METRIC = "clips/sec forward"
 UNIT = "clips/s"
 GFLOP_PER_CLIP_T6 = 494.5            # 12 x 38.515 + 6 x 5.386
@@ -357,14 +359,18 @@ def run_ours(args) -> int:
         # ---------------- device-resident timed region ----------------
         sampler = ClockSampler(local) if rank == 0 else None
         time.sleep(0.25)
+        # Per-launch CUDA events (the kernel breakdown and the roofline) are recorded INSIDE the timed region, but only on
+        # every REC_STRIDE-th step: two events around each of ~170 launches cost 0.5 ms per step (1.1 %,
+        # profiles/README.md r8j, tools/rec_overhead.py), which `value` should not carry on every step.
         rec = ops.LaunchRecorder()
-        ops.set_recorder(rec)
+        rec_steps = [i for i in range(args.steps) if i % REC_STRIDE == 0]
         n0 = pkg._lib.launch_count()
         barrier()
         t_wall0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
+        for i in range(args.steps):
+            ops.set_recorder(rec if i % REC_STRIDE == 0 else None)
             logits = model(x_dev)
         e1.record()
         barrier()
@@ -429,8 +435,10 @@ def run_ours(args) -> int:
         peaks, peak_src = load_peaks()
         fam = rec.summary()
         kernels = {}
+        n_rec = len(rec_steps)                      # steps whose launches carry events
+        ms_rec = ms * n_rec / args.steps            # their share of the timed region
         for name, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
-            k = {"launches": d["launches"], "ms_per_step": d["ms"] / args.steps, "share": d["ms"] / ms}
+            k = {"launches": d["launches"], "ms_per_step": d["ms"] / n_rec, "share": d["ms"] / ms_rec}
             if d["flops"] > 0:
                 k["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
             k["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
@@ -453,9 +461,11 @@ def run_ours(args) -> int:
                         "traffic_source": traffic_src,
                         "algorithmic_bytes_per_launch": g["bytes"] / g["launches"],
                         "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
-                        "launches_per_step": g["launches"] / args.steps,
-                        "flops_per_step": g["flops"] / args.steps,
-                        "share_of_step": g["ms"] / ms}
+                        "launches_per_step": g["launches"] / n_rec,
+                        "flops_per_step": g["flops"] / n_rec,
+                        "share_of_step": g["ms"] / ms_rec,
+                        "events": f"CUDA events around every launch of {n_rec} of the {args.steps} timed steps "
+                                  f"(every {REC_STRIDE}th)"}
         flops_step = {6: GFLOP_PER_CLIP_T6, 32: GFLOP_PER_CLIP_T32}.get(args.frames)
         flops_step = flops_step * 1e9 * args.batch if flops_step else None
         line = {
@@ -544,14 +554,15 @@ def run_train(args) -> int:
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.25)
-    rec = ops.LaunchRecorder()
-    ops.set_recorder(rec)
+    rec = ops.LaunchRecorder()                  # events on every REC_STRIDE-th step only (see run_ours)
+    rec_steps = [i for i in range(args.steps) if i % REC_STRIDE == 0]
     n0 = pkg._lib.launch_count()
     barrier()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        ops.set_recorder(rec if i % REC_STRIDE == 0 else None)
         loss = trainer.step(x_dev, y_dev)
     e1.record()
     barrier()
@@ -583,8 +594,10 @@ def run_train(args) -> int:
         peaks, peak_src = load_peaks()
         fam = rec.summary()
         kernels = {}
+        n_rec = len(rec_steps)
+        ms_rec = ms * n_rec / args.steps
         for name, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
-            k = {"launches": d["launches"], "ms_per_step": d["ms"] / args.steps, "share": d["ms"] / ms}
+            k = {"launches": d["launches"], "ms_per_step": d["ms"] / n_rec, "share": d["ms"] / ms_rec}
             if d["flops"] > 0:
                 k["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
             k["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
@@ -596,7 +609,9 @@ def run_train(args) -> int:
         roofline = {"kernel": "gemm_tcgen05 kernels (forward, data-gradient and split-K weight-gradient GEMMs)",
                     "bound": "tensor", "achieved": g_fl / (g_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "frac": g_fl / (g_ms * 1e-3) / 1e12 / peak, "traffic": None,
-                    "peak_source": peak_src + ", sustained bf16", "share_of_step": g_ms / ms}
+                    "peak_source": peak_src + ", sustained bf16", "share_of_step": g_ms / ms_rec,
+                    "events": f"CUDA events around every launch of {n_rec} of the {args.steps} timed steps "
+                              f"(every {REC_STRIDE}th)"}
         line = {
             "metric": "clips/sec training step (fwd+bwd+AdamW)", "value": total_clips / (ms / 1e3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
