@@ -123,19 +123,32 @@ __device__ __forceinline__ void gemm_epilogue_64(const GemmParams& p, uint32_t t
                 if (hh == HALVES - 1) after_tmem_reads();
                 break;
             }
+            // the bias loads are issued BEFORE the TMEM load so that their latency hides behind it: behind it they sat
+            // on the epilogue's critical path once per 8 columns (14 % of the samples of the conv2 kernel, whose tile
+            // period is this epilogue: profiles/README.md r8l)
+            float4 bb[8];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int n = nb + g * 8;
+                if (p.bias != nullptr && n < p.N) {
+                    bb[2 * g] = ldg_nc_f4_ordered(p.bias + n);
+                    bb[2 * g + 1] = ldg_nc_f4_ordered(p.bias + n + 4);
+                } else {
+                    bb[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    bb[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
             uint32_t r[32];
             tmem_ld_32x32b_x32(taddr + hh * 32, r);
             tmem_ld_wait();
             if (hh == HALVES - 1) after_tmem_reads();
 #pragma unroll
             for (int g = 0; g < 4; ++g) {     // 8 columns -> one 16-byte chunk
-                const int n = nb + g * 8;
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-                if (p.bias != nullptr && n < p.N) {
-                    const float4 b0 = ldg_nc_f4_ordered(p.bias + n);
-                    const float4 b1 = ldg_nc_f4_ordered(p.bias + n + 4);
+                {
+                    const float4 b0 = bb[2 * g], b1 = bb[2 * g + 1];
                     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
                     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                 }
