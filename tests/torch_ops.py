@@ -497,3 +497,37 @@ def conv3x3_pair_ref(x, wt, bias, act=1):
         acc += sh @ wp[:, t * 64:(t + 1) * 64].t()
     y = (acc.reshape(m * 2, 64) + bias.float()).reshape(n, h, w, 64)[:, :h - 2, :w - 2]
     return (F.relu(y) if act == 1 else y).to(x.dtype)
+
+
+# ---- spatial attention, online softmax with a lazy rescale: a torch mirror of attn_spatial_pp_kernel's arithmetic ----
+def attn_online_lazy_ref(q, k, v, scale, step=64, raise_log2=8.0, count=None):
+    """q, k, v: [items, tokens, 64] fp32 holding bf16 values.  One row's keys are visited in `step`-key steps; the
+    reference m_ref (log2 domain, scores times scale * log2 e) is the first step's maximum and is raised only when a
+    later step's maximum exceeds it by more than `raise_log2` — then the accumulated output and denominator are
+    multiplied by 2^(old - new).  P is rounded to bf16 before the P.V product (fp32 accumulation), the denominator sums
+    the unrounded exponentials: csrc/attn_spatial_pp.cuh.  `count` (a list) receives the number of raises."""
+    sl2 = scale * 1.4426950408889634
+    n = q.shape[1]
+    s = torch.einsum("bid,bjd->bij", q, k)                      # fp32 scores
+    m_ref = None
+    o = torch.zeros_like(q)
+    l = torch.zeros(q.shape[0], n)
+    raises = 0
+    for j0 in range(0, n, step):
+        sj = s[:, :, j0:j0 + step]
+        mx = sj.max(dim=-1).values
+        if m_ref is None:
+            m_ref = mx.clone()
+            corr = torch.ones_like(mx)
+        else:
+            up = (mx - m_ref) * sl2 > raise_log2
+            corr = torch.where(up, torch.exp2((m_ref - mx) * sl2), torch.ones_like(mx))
+            m_ref = torch.where(up, mx, m_ref)
+            raises += int(up.sum())
+        p = torch.exp2(sj * sl2 - (m_ref * sl2)[..., None])
+        o = o * corr[..., None] + torch.einsum("bij,bjd->bid", p.to(torch.bfloat16).float(), v[:, j0:j0 + step])
+        l = l * corr + p.sum(dim=-1)
+    if count is not None:
+        count.append(raises)
+    lse = m_ref * sl2 + torch.log2(l)
+    return o / l[..., None], lse
